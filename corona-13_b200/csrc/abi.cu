@@ -1,0 +1,344 @@
+// abi.cu -- extern "C" entry points of libcorona_b200.so (declared in include/corona_b200.h)
+#include "internal.h"
+#include <atomic>
+#include <mutex>
+#include <vector>
+#include <cstring>
+#include <cstdio>
+#include <float.h>
+
+static thread_local std::string g_error;
+static std::atomic<uint64_t> g_launches{0};
+static int g_sm_count = 0;
+
+void cb200_set_error(const std::string &msg) { g_error = msg; }
+int cb200_cuda_fail(cudaError_t e, const char *what, const char *file, int line)
+{
+  char buf[512];
+  snprintf(buf, sizeof(buf), "%s:%d: %s -> %s", file, line, what, cudaGetErrorString(e));
+  g_error = buf;
+  if(e == cudaErrorNoDevice || e == cudaErrorInsufficientDriver) return CB200_ERR_NO_DEVICE;
+  if(e == cudaErrorMemoryAllocation) return CB200_ERR_NOMEM;
+  return CB200_ERR_CUDA;
+}
+void cb200_count_launch(uint64_t n) { g_launches += n; }
+int cb200_sm_count_cached()
+{
+  if(!g_sm_count)
+  {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&g_sm_count, cudaDevAttrMultiProcessorCount, dev);
+    if(g_sm_count <= 0) g_sm_count = 148;
+  }
+  return g_sm_count;
+}
+
+extern "C" {
+
+const char *cb200_version(void) { return "corona-13_b200 0.1 (sm_100a)"; }
+const char *cb200_last_error(void) { return g_error.c_str(); }
+uint64_t cb200_launch_count(void) { return g_launches.load(); }
+
+int cb200_device_count(void)
+{
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if(e != cudaSuccess) { cb200_cuda_fail(e, "cudaGetDeviceCount", __FILE__, __LINE__); return 0; }
+  return n;
+}
+
+int cb200_set_device(int device)
+{
+  if(device < 0 || device >= cb200_device_count()) { if(g_error.empty()) g_error = "no such CUDA device"; return CB200_ERR_NO_DEVICE; }
+  CB_CUDA(cudaSetDevice(device));
+  g_sm_count = 0;
+  return 0;
+}
+int cb200_sm_count(void) { if(cb200_device_count() < 1) return 0; return cb200_sm_count_cached(); }
+
+void *cb200_malloc(size_t bytes) { void *p = nullptr; CB_CUDA_NULL(cudaMalloc(&p, bytes ? bytes : 1)); return p; }
+int cb200_free(void *p) { CB_CUDA(cudaFree(p)); return 0; }
+void *cb200_malloc_host(size_t bytes) { void *p = nullptr; CB_CUDA_NULL(cudaMallocHost(&p, bytes ? bytes : 1)); return p; }
+int cb200_free_host(void *p) { CB_CUDA(cudaFreeHost(p)); return 0; }
+int cb200_memcpy_h2d(void *d, const void *h, size_t bytes, void *stream)
+{ CB_CUDA(cudaMemcpyAsync(d, h, bytes, cudaMemcpyHostToDevice, (cudaStream_t)stream)); return 0; }
+int cb200_memcpy_d2h(void *h, const void *d, size_t bytes, void *stream)
+{ CB_CUDA(cudaMemcpyAsync(h, d, bytes, cudaMemcpyDeviceToHost, (cudaStream_t)stream)); return 0; }
+int cb200_stream_sync(void *stream) { CB_CUDA(cudaStreamSynchronize((cudaStream_t)stream)); return 0; }
+
+// ---------------------------------------------------------------------------------------------
+cb200_scene_t *cb200_scene_create(const cb_shape_t *shapes, int num_shapes)
+{
+  if(num_shapes < 0 || (num_shapes > 0 && !shapes)) { g_error = "scene_create: bad arguments"; return nullptr; }
+  if(cb200_device_count() < 1) { if(g_error.empty()) g_error = "no CUDA device"; return nullptr; }
+  cb200_scene *s = new cb200_scene();
+  memset(s, 0, sizeof(*s));
+  cudaGetDevice(&s->device);
+  s->num_shapes = num_shapes;
+  std::vector<ShapeDev> sd(num_shapes > 0 ? num_shapes : 1);
+  for(int i=0;i<num_shapes;i++)
+  {
+    sd[i].vtx_off = s->num_vtx; sd[i].vtxidx_off = s->num_vtxidx;
+    s->num_vtx += shapes[i].num_vtx; s->num_vtxidx += shapes[i].num_vtxidx; s->num_prims += shapes[i].num_prims;
+    if(shapes[i].num_prims && (!shapes[i].primid || !shapes[i].vtxidx || !shapes[i].vtx))
+    { g_error = "scene_create: shape with null arrays"; delete s; return nullptr; }
+  }
+  // global primid list with the shape id patched in (prims_allocate_index, src/prims.c:741-757)
+  std::vector<uint64_t> primid(s->num_prims ? s->num_prims : 1);
+  uint64_t k = 0;
+  for(int i=0;i<num_shapes;i++)
+    for(uint64_t j=0;j<shapes[i].num_prims;j++)
+    {
+      const uint64_t p = cb_primid_with_shapeid(shapes[i].primid[j], (uint32_t)i);
+      const uint32_t vcnt = cb_primid_vcnt(p);
+      if(vcnt < 1 || vcnt > 4) { g_error = "scene_create: unsupported primitive type (shells are out of scope)"; delete s; return nullptr; }
+      if(cb_primid_vi(p) + vcnt > shapes[i].num_vtxidx) { g_error = "scene_create: vertex index out of range"; delete s; return nullptr; }
+      if(cb_primid_mb(p)) s->any_mb = 1;
+      primid[k++] = p;
+    }
+#define SC(call) do { cudaError_t e__ = (call); if(e__ != cudaSuccess) { cb200_cuda_fail(e__, #call, __FILE__, __LINE__); cb200_scene_destroy(s); return nullptr; } } while(0)
+  SC(cudaMalloc(&s->d_vtx, (s->num_vtx ? s->num_vtx : 1)*sizeof(cb_vtx_t)));
+  SC(cudaMalloc(&s->d_vtxidx, (s->num_vtxidx ? s->num_vtxidx : 1)*sizeof(cb_vtxidx_t)));
+  SC(cudaMalloc(&s->d_shapes, sd.size()*sizeof(ShapeDev)));
+  SC(cudaMalloc(&s->d_primid, primid.size()*sizeof(uint64_t)));
+  for(int i=0;i<num_shapes;i++)
+  {
+    if(shapes[i].num_vtx) SC(cudaMemcpy(s->d_vtx + sd[i].vtx_off, shapes[i].vtx, shapes[i].num_vtx*sizeof(cb_vtx_t), cudaMemcpyHostToDevice));
+    if(shapes[i].num_vtxidx) SC(cudaMemcpy(s->d_vtxidx + sd[i].vtxidx_off, shapes[i].vtxidx, shapes[i].num_vtxidx*sizeof(cb_vtxidx_t), cudaMemcpyHostToDevice));
+  }
+  SC(cudaMemcpy(s->d_shapes, sd.data(), sd.size()*sizeof(ShapeDev), cudaMemcpyHostToDevice));
+  SC(cudaMemcpy(s->d_primid, primid.data(), primid.size()*sizeof(uint64_t), cudaMemcpyHostToDevice));
+#undef SC
+  return s;
+}
+
+void cb200_scene_destroy(cb200_scene_t *s)
+{
+  if(!s) return;
+  cudaFree(s->d_vtx); cudaFree(s->d_vtxidx); cudaFree(s->d_shapes); cudaFree(s->d_primid);
+  delete s;
+}
+uint64_t cb200_scene_num_prims(const cb200_scene_t *s) { return s ? s->num_prims : 0; }
+
+// ---------------------------------------------------------------------------------------------
+static cb200_accel *accel_new(cb200_scene *s)
+{
+  cb200_accel *a = new cb200_accel();
+  memset(a, 0, sizeof(*a));
+  a->scene = s;
+  return a;
+}
+
+cb200_accel_t *cb200_accel_build(cb200_scene_t *s, const float *ghost_aabb, uint64_t *primid_out)
+{
+  if(!s) { g_error = "accel_build: null scene"; return nullptr; }
+  cb200_accel *a = accel_new(s);
+  if(cb200_build_lbvh(a, ghost_aabb)) { cb200_accel_destroy(a); return nullptr; }
+  if(primid_out && s->num_prims)
+  {
+    cudaError_t e = cudaMemcpy(primid_out, a->d_primid, s->num_prims*sizeof(uint64_t), cudaMemcpyDeviceToHost);
+    if(e != cudaSuccess) { cb200_cuda_fail(e, "copy primid", __FILE__, __LINE__); cb200_accel_destroy(a); return nullptr; }
+  }
+  return a;
+}
+
+static int tree_depth(const cb_qbvh_node_t *nodes, uint64_t num_nodes, uint64_t num_prims)
+{ // iterative depth of an imported tree, with bounds validation; -1 when malformed
+  if(num_nodes == 0) return -1;
+  std::vector<std::pair<uint64_t,int>> st;
+  st.push_back({0, 1});
+  int depth = 0;
+  uint64_t visited = 0;
+  while(!st.empty())
+  {
+    auto [ni, d] = st.back(); st.pop_back();
+    if(++visited > num_nodes) return -1;   // cycle or shared node
+    if(d > depth) depth = d;
+    const cb_qbvh_node_t &n = nodes[ni];
+    if(n.axis0 < 0 || n.axis0 > 2 || n.axis00 < 0 || n.axis00 > 2 || n.axis01 < 0 || n.axis01 > 2) return -1;
+    for(int c=0;c<4;c++)
+    {
+      const uint64_t ch = n.child[c];
+      if(ch & CB_LEAF_BIT)
+      {
+        const uint64_t beg = (ch ^ CB_LEAF_BIT) >> 5, cnt = ch & 31;
+        if(cnt && beg + cnt > num_prims) return -1;
+      }
+      else
+      {
+        if(ch >= num_nodes) return -1;
+        st.push_back({ch, d+1});
+      }
+    }
+  }
+  return depth;
+}
+
+cb200_accel_t *cb200_accel_import_qbvh(cb200_scene_t *s, const cb_qbvh_node_t *nodes, uint64_t num_nodes,
+                                       const uint64_t *primid_permuted, const float aabb[6])
+{
+  if(!s || !nodes || num_nodes == 0 || (s->num_prims && !primid_permuted)) { g_error = "accel_import_qbvh: bad arguments"; return nullptr; }
+  const int depth = tree_depth(nodes, num_nodes, s->num_prims);
+  if(depth < 0 || depth > 101) { g_error = "accel_import_qbvh: malformed tree"; return nullptr; }
+  cb200_accel *a = accel_new(s);
+  a->imported = 1;
+  a->depth = depth;
+#define AC(call) do { cudaError_t e__ = (call); if(e__ != cudaSuccess) { cb200_cuda_fail(e__, #call, __FILE__, __LINE__); cb200_accel_destroy(a); return nullptr; } } while(0)
+  AC(cudaMalloc(&a->d_nodes, num_nodes*sizeof(Node256)));
+  AC(cudaMemcpy(a->d_nodes, nodes, num_nodes*sizeof(Node256), cudaMemcpyHostToDevice));
+  AC(cudaMalloc(&a->d_primid, (s->num_prims ? s->num_prims : 1)*sizeof(uint64_t)));
+  if(s->num_prims) AC(cudaMemcpy(a->d_primid, primid_permuted, s->num_prims*sizeof(uint64_t), cudaMemcpyHostToDevice));
+#undef AC
+  a->dev.nodes = a->d_nodes;
+  a->dev.num_nodes = num_nodes;
+  a->dev.mb = 1;    // reference layout: always interpolates the two box sets, even for static scenes
+  if(aabb) memcpy(a->aabb, aabb, sizeof(float)*6);
+  if(cb200_build_records(a, 0)) { cb200_accel_destroy(a); return nullptr; }
+  if(cudaStreamSynchronize(0) != cudaSuccess) { g_error = "accel_import_qbvh: sync failed"; cb200_accel_destroy(a); return nullptr; }
+  return a;
+}
+
+void cb200_accel_destroy(cb200_accel_t *a)
+{
+  if(!a) return;
+  cudaFree(a->d_nodes); cudaFree(a->d_recs); cudaFree(a->d_primid);
+  delete a;
+}
+uint64_t cb200_accel_num_nodes(const cb200_accel_t *a) { return a ? a->dev.num_nodes : 0; }
+int cb200_accel_depth(const cb200_accel_t *a) { return a ? a->depth : 0; }
+int cb200_accel_aabb(const cb200_accel_t *a, float aabb[6])
+{
+  if(!a || !aabb) { g_error = "accel_aabb: bad arguments"; return CB200_ERR_ARG; }
+  memcpy(aabb, a->aabb, sizeof(float)*6);
+  return 0;
+}
+int cb200_accel_layout(const cb200_accel_t *a, uint32_t *node_bytes, uint32_t *prim_bytes)
+{
+  if(!a) { g_error = "accel_layout: null accel"; return CB200_ERR_ARG; }
+  if(node_bytes) *node_bytes = a->dev.mb ? 256 : 128;
+  if(prim_bytes) *prim_bytes = a->dev.rec_units*64;
+  return 0;
+}
+
+int cb200_accel_export_qbvh(const cb200_accel_t *a, cb_qbvh_node_t *nodes, uint64_t cap, uint64_t *primid_out)
+{
+  if(!a || !nodes || cap < a->dev.num_nodes) { g_error = "accel_export_qbvh: bad arguments"; return CB200_ERR_ARG; }
+  const uint64_t n = a->dev.num_nodes;
+  if(a->dev.mb) CB_CUDA(cudaMemcpy(nodes, a->d_nodes, n*sizeof(Node256), cudaMemcpyDeviceToHost));
+  else
+  {
+    std::vector<Node128> tmp(n);
+    CB_CUDA(cudaMemcpy(tmp.data(), a->d_nodes, n*sizeof(Node128), cudaMemcpyDeviceToHost));
+    for(uint64_t i=0;i<n;i++)
+    {
+      memcpy(nodes[i].aabb0, tmp[i].aabb0, sizeof(tmp[i].aabb0));
+      memcpy(nodes[i].aabb1, tmp[i].aabb0, sizeof(tmp[i].aabb0));
+      const uint32_t ax = (uint32_t)(tmp[i].child[0] >> CB_AXIS_SHIFT) & 63u;
+      nodes[i].child[0] = tmp[i].child[0] & CB_CHILD_MASK;
+      for(int c=1;c<4;c++) nodes[i].child[c] = tmp[i].child[c];
+      nodes[i].axis0 = ax & 3; nodes[i].axis00 = (ax >> 2) & 3; nodes[i].axis01 = (ax >> 4) & 3;
+      nodes[i].parent = ~0ull;
+    }
+    for(uint64_t i=0;i<n;i++)
+      for(int c=0;c<4;c++) if(!(nodes[i].child[c] & CB_LEAF_BIT)) nodes[nodes[i].child[c]].parent = i;
+  }
+  if(primid_out && a->dev.num_prims)
+    CB_CUDA(cudaMemcpy(primid_out, a->d_primid, a->dev.num_prims*sizeof(uint64_t), cudaMemcpyDeviceToHost));
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+int cb200_accel_intersect_dev(const cb200_accel_t *a, const void *d_rays, const void *d_max_dist, void *d_out, uint64_t n, void *stream)
+{
+  if(!a || (n && (!d_rays || !d_out))) { g_error = "accel_intersect_dev: bad arguments"; return CB200_ERR_ARG; }
+  return cb200_launch_intersect(a, (const cb_ray_t *)d_rays, (const float *)d_max_dist, (cb_hitrec_t *)d_out, n, (cudaStream_t)stream, nullptr);
+}
+
+int cb200_accel_visible_dev(const cb200_accel_t *a, const void *d_rays, const void *d_max_dist, void *d_out, uint64_t n, void *stream)
+{
+  if(!a || (n && (!d_rays || !d_out || !d_max_dist))) { g_error = "accel_visible_dev: bad arguments"; return CB200_ERR_ARG; }
+  return cb200_launch_visible(a, (const cb_ray_t *)d_rays, (const float *)d_max_dist, (int32_t *)d_out, n, (cudaStream_t)stream);
+}
+
+int cb200_accel_intersect_counted(const cb200_accel_t *a, const void *d_rays, const void *d_max_dist, void *d_out, uint64_t n, uint64_t counters[4])
+{
+  if(!a || !counters || (n && (!d_rays || !d_out))) { g_error = "accel_intersect_counted: bad arguments"; return CB200_ERR_ARG; }
+  unsigned long long *d_cnt = nullptr;
+  CB_CUDA(cudaMalloc(&d_cnt, 4*sizeof(unsigned long long)));
+  CB_CUDA(cudaMemset(d_cnt, 0, 4*sizeof(unsigned long long)));
+  int rc = cb200_launch_intersect(a, (const cb_ray_t *)d_rays, (const float *)d_max_dist, (cb_hitrec_t *)d_out, n, 0, d_cnt);
+  if(!rc)
+  {
+    cudaError_t e = cudaMemcpy(counters, d_cnt, 4*sizeof(uint64_t), cudaMemcpyDeviceToHost);
+    if(e != cudaSuccess) rc = cb200_cuda_fail(e, "copy counters", __FILE__, __LINE__);
+  }
+  cudaFree(d_cnt);
+  return rc;
+}
+
+} // extern "C"
+
+// host-buffer entry points: stage through device buffers in chunks so that arbitrarily large batches work and
+// the copy of chunk k+1 overlaps the traversal of chunk k (two streams, pinned staging is the caller's choice)
+template<typename OUT, typename LAUNCH>
+static int run_chunked(const cb_ray_t *rays, const float *max_dist, OUT *out, uint64_t n, LAUNCH launch)
+{
+  const uint64_t CH = 1ull << 22;
+  cudaStream_t st[2];
+  cb_ray_t *d_rays[2] = {nullptr, nullptr};
+  float *d_md[2] = {nullptr, nullptr};
+  OUT *d_out[2] = {nullptr, nullptr};
+  const uint64_t cap = n < CH ? n : CH;
+  int rc = 0;
+  for(int k=0;k<2;k++)
+  {
+    if(cudaStreamCreateWithFlags(&st[k], cudaStreamNonBlocking) != cudaSuccess) { st[k] = nullptr; rc = CB200_ERR_CUDA; }
+    if(cudaMalloc(&d_rays[k], cap*sizeof(cb_ray_t)) != cudaSuccess) rc = CB200_ERR_NOMEM;
+    if(max_dist && cudaMalloc(&d_md[k], cap*sizeof(float)) != cudaSuccess) rc = CB200_ERR_NOMEM;
+    if(cudaMalloc(&d_out[k], cap*sizeof(OUT)) != cudaSuccess) rc = CB200_ERR_NOMEM;
+  }
+  if(rc) g_error = "intersect_n: staging allocation failed";
+  for(uint64_t off=0, k=0; !rc && off<n; off+=CH, k^=1)
+  {
+    const uint64_t m = (n - off) < CH ? (n - off) : CH;
+    cudaError_t e = cudaMemcpyAsync(d_rays[k], rays + off, m*sizeof(cb_ray_t), cudaMemcpyHostToDevice, st[k]);
+    if(e == cudaSuccess && max_dist) e = cudaMemcpyAsync(d_md[k], max_dist + off, m*sizeof(float), cudaMemcpyHostToDevice, st[k]);
+    if(e != cudaSuccess) { rc = cb200_cuda_fail(e, "h2d", __FILE__, __LINE__); break; }
+    rc = launch(d_rays[k], d_md[k], d_out[k], m, st[k]);
+    if(rc) break;
+    e = cudaMemcpyAsync(out + off, d_out[k], m*sizeof(OUT), cudaMemcpyDeviceToHost, st[k]);
+    if(e != cudaSuccess) { rc = cb200_cuda_fail(e, "d2h", __FILE__, __LINE__); break; }
+  }
+  for(int k=0;k<2;k++)
+  {
+    if(st[k])
+    {
+      cudaError_t e = cudaStreamSynchronize(st[k]);
+      if(e != cudaSuccess && !rc) rc = cb200_cuda_fail(e, "sync", __FILE__, __LINE__);
+      cudaStreamDestroy(st[k]);
+    }
+    cudaFree(d_rays[k]); cudaFree(d_md[k]); cudaFree(d_out[k]);
+  }
+  return rc;
+}
+
+extern "C" {
+
+int cb200_accel_intersect_n(const cb200_accel_t *a, const cb_ray_t *rays, const float *max_dist, cb_hitrec_t *out, uint64_t n)
+{
+  if(!a || (n && (!rays || !out))) { g_error = "accel_intersect_n: bad arguments"; return CB200_ERR_ARG; }
+  if(n == 0) return 0;
+  return run_chunked<cb_hitrec_t>(rays, max_dist, out, n,
+    [a](cb_ray_t *dr, float *dm, cb_hitrec_t *dout, uint64_t m, cudaStream_t s) { return cb200_launch_intersect(a, dr, dm, dout, m, s, nullptr); });
+}
+
+int cb200_accel_visible_n(const cb200_accel_t *a, const cb_ray_t *rays, const float *max_dist, int32_t *out, uint64_t n)
+{
+  if(!a || (n && (!rays || !out || !max_dist))) { g_error = "accel_visible_n: bad arguments"; return CB200_ERR_ARG; }
+  if(n == 0) return 0;
+  return run_chunked<int32_t>(rays, max_dist, out, n,
+    [a](cb_ray_t *dr, float *dm, int32_t *dout, uint64_t m, cudaStream_t s) { return cb200_launch_visible(a, dr, dm, dout, m, s); });
+}
+
+} // extern "C"

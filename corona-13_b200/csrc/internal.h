@@ -1,0 +1,98 @@
+// internal.h -- data layout in HBM and host-side handles of libcorona_b200.so (not part of the ABI)
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string>
+#include "corona_b200.h"
+
+// ---------------------------------------------------------------------------------------------
+// HBM layout
+//
+// prim records ("leaf order"): one or two 64-byte units per primitive, stored in the order of the
+// build-permuted primid list so that leaf (begin,count) indexes them directly -- the reference's
+// two dependent loads per vertex (vtxidx -> vtx, include/geo.h:108-138) are resolved once at build
+// time.  Unit 0 = shutter-open vertices, unit 1 (only when the accel has rec_units == 2) =
+// shutter-close vertices.
+//   float4 r0 = (v0.xyz, primid.lo)      float4 r1 = (v1.xyz, primid.hi)
+//   float4 r2 = (v2.xyz, aux0)           float4 r3 = (v3.xyz, aux1)
+// sphere: v0 = centre, aux0 = radius bits.   line: v0,v1, aux0 = r0, aux1 = r1 (shutter-open radii).
+//
+// nodes: Node256 is bit-identical to the reference's qbvh_node_t (qbvhmp.c:62-81): used for scenes
+// with motion blur and for imported (mode A) trees.  Node128 drops the shutter-close boxes for
+// static scenes: half the bytes per node visit.
+// ---------------------------------------------------------------------------------------------
+struct __align__(16) Node256
+{
+  float    aabb0[6][4];
+  float    aabb1[6][4];
+  uint64_t child[4];
+  uint64_t parent;
+  int64_t  axis0, axis00, axis01;
+};
+struct __align__(16) Node128
+{
+  float    aabb0[6][4];
+  uint64_t child[4];       // child[0] bits 56..61 carry axis0 | axis00<<2 | axis01<<4
+};
+static_assert(sizeof(Node256) == 256, "Node256");
+static_assert(sizeof(Node128) == 128, "Node128");
+
+#define CB_CHILD_MASK  0x80ffffffffffffffull   // strips the axis bits from Node128::child[0]
+#define CB_AXIS_SHIFT  56
+
+struct DevAccel
+{
+  const void   *nodes;       // Node256* (mb != 0) or Node128*
+  const float4 *recs;        // prim records, rec_units*4 float4 per primitive
+  uint32_t      rec_units;   // 1: static scene, 2: open+close vertices
+  uint32_t      mb;          // nodes carry shutter-close boxes
+  uint64_t      num_nodes;
+  uint64_t      num_prims;
+};
+
+struct ShapeDev   // offsets of one shape inside the concatenated device arrays
+{
+  uint64_t vtx_off;
+  uint64_t vtxidx_off;
+};
+
+struct cb200_scene
+{
+  int        device;
+  int        num_shapes;
+  uint64_t   num_prims, num_vtx, num_vtxidx;
+  int        any_mb;
+  cb_vtx_t    *d_vtx;
+  cb_vtxidx_t *d_vtxidx;
+  ShapeDev    *d_shapes;
+  uint64_t    *d_primid;   // global list in load order (shapeid patched in, prims.c:741-757)
+};
+
+struct cb200_accel
+{
+  cb200_scene *scene;
+  DevAccel     dev;
+  void        *d_nodes;
+  float4      *d_recs;
+  uint64_t    *d_primid;   // permuted list the leaves index into
+  float        aabb[6];
+  int          depth;      // levels of 4-wide nodes
+  int          imported;
+};
+
+// error plumbing ------------------------------------------------------------------------------
+void cb200_set_error(const std::string &msg);
+int  cb200_cuda_fail(cudaError_t e, const char *what, const char *file, int line);
+#define CB_CUDA(call) do { cudaError_t e__ = (call); if(e__ != cudaSuccess) return cb200_cuda_fail(e__, #call, __FILE__, __LINE__); } while(0)
+#define CB_CUDA_NULL(call) do { cudaError_t e__ = (call); if(e__ != cudaSuccess) { cb200_cuda_fail(e__, #call, __FILE__, __LINE__); return nullptr; } } while(0)
+void cb200_count_launch(uint64_t n = 1);
+int  cb200_sm_count_cached();
+
+// build.cu
+int cb200_build_lbvh(cb200_accel *a, const float *ghost_aabb);
+int cb200_build_records(cb200_accel *a, cudaStream_t stream);
+// traverse.cu
+int cb200_launch_intersect(const cb200_accel *a, const cb_ray_t *d_rays, const float *d_max_dist, cb_hitrec_t *d_out,
+                           uint64_t n, cudaStream_t stream, unsigned long long *d_counters);
+int cb200_launch_visible(const cb200_accel *a, const cb_ray_t *d_rays, const float *d_max_dist, int32_t *d_out,
+                         uint64_t n, cudaStream_t stream);
