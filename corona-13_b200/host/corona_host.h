@@ -1,0 +1,86 @@
+/* corona_host.h -- the reference's module API for the hot path, served by libcorona_b200.so.
+ *
+ * Same function names, argument meaning and error behaviour as include/accel.h:28-50 of the
+ * reference (no error codes: failures print to stderr; NULL handles are tolerated nowhere, as in
+ * the reference).  Two build modes:
+ *
+ *   in-tree  (-DCORONA_B200_IN_TREE, compiled as src/accel.d/b200.c inside the reference tree):
+ *            the reference's own corona_common.h / prims.h / accel.h provide the types.
+ *   standalone (this repository): layout-compatible restatements below, so that the parity tests
+ *            can drive the very same C code through ctypes.
+ */
+#ifndef CORONA_HOST_H
+#define CORONA_HOST_H
+
+#include <stdint.h>
+#include <stdio.h>
+#include "corona_types.h"
+
+#ifdef CORONA_B200_IN_TREE
+#include "corona_common.h"
+#include "prims.h"
+#include "accel.h"
+#else
+/* restated with the reference's names so that host code reads like the reference's callers */
+typedef cb_ray_t ray_t;      /* include/corona_common.h:113-121 */
+typedef cb_hit_t hit_t;      /* include/corona_common.h:123-137 */
+
+typedef struct prims_shape_t /* include/prims.h:49-65, same field order and sizes */
+{
+  int64_t  material;
+  uint64_t num_prims;
+  char     name[1024];
+  char     tex[512];
+  int      fd;
+  void    *data;
+  size_t   data_size;
+  cb_vtxidx_t *vtxidx;
+  cb_vtx_t    *vtx;
+  uint64_t    *primid;       /* primid_t[] */
+}
+prims_shape_t;
+
+typedef struct prims_t       /* include/prims.h:67-83 */
+{
+  uint32_t num_shapes;
+  prims_shape_t *shape;
+  uint64_t num_loaded_prims;
+  uint32_t num_loaded_shapes;
+  uint64_t num_prims;
+  uint64_t *primid;          /* global index array, permuted by accel_build */
+  float ghost_aabb[6];
+}
+prims_t;
+
+struct accel_t;
+typedef struct accel_t accel_t;
+
+/* include/accel.h:28-50 */
+void         accel_print_info(FILE *fd);
+accel_t     *accel_init(prims_t *p);
+void         accel_cleanup(accel_t *b);
+void         accel_build(accel_t *b, const char *filename);
+void         accel_intersect(const accel_t *b, const ray_t *ray, hit_t *hit);
+int          accel_visible(const accel_t *b, const ray_t *ray, const float max_dist);
+void         accel_closest(const accel_t *b, ray_t *ray, hit_t *hit, const float centre);
+const float *accel_aabb(const accel_t *b);
+#endif
+
+/* batched extensions (one synchronous ray per call cannot feed a GPU).
+ * hits[i].dist is the search limit on input like accel_intersect; only prim,u,v,dist (spheres: x)
+ * are written, and only when a closer hit is found. */
+void accel_intersect_n(const accel_t *b, const ray_t *rays, hit_t *hits, uint64_t n);
+void accel_visible_n(const accel_t *b, const ray_t *rays, const float *max_dist, int *visible, uint64_t n);
+
+/* prims helpers for standalone use: the slice of prims_init/allocate/load/allocate_index the path needs
+ * (src/prims.c:703-828) */
+#ifndef CORONA_B200_IN_TREE
+void prims_init(prims_t *p);
+void prims_allocate(prims_t *p, const uint32_t num_shapes);
+int  prims_load(prims_t *p, const char *filename, const char *texture, const int shader);
+int  prims_add_shape_mem(prims_t *p, const cb_shape_t *s);   /* in-memory shape instead of a .geo file */
+void prims_allocate_index(prims_t *p);
+void prims_cleanup(prims_t *p);
+#endif
+
+#endif

@@ -1,0 +1,307 @@
+"""GPU parity tests proper (run with -m gpu on the B200 box).  Everything goes through the C ABI
+(corona-13_b200/lib.py is a ctypes veneer over include/corona_b200.h) and is checked against
+
+  * the golden vectors produced by the unmodified reference (tests/golden/*.npz),
+  * the CPU oracle on seeded scenes / rays at sizes it finishes in seconds,
+  * size-independent properties at the benchmark's full size (10 M triangles).
+
+Bar: prim id, dist, and triangle/quad u,v bit-exact; analytic-prim u,v within helpers.UV_TOL.
+Mode A = the GPU traverses the reference-built tree (ties included).  Mode B = GPU-built tree: every
+difference against the reference's answer must be a proven tie."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+from helpers import Golden, GOLDEN_NAMES, S, R, assert_hits_equal, classify_mismatches
+from oracle.binding import Oracle
+
+pytestmark = pytest.mark.gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def gpu(lib):
+    if lib.device_count() < 1:
+        pytest.fail("no CUDA device: " + lib.load().cb200_last_error().decode())
+    lib.set_device(0)
+    return lib
+
+
+# --------------------------------------------------------------------------------------------- golden
+@pytest.mark.parametrize("name", GOLDEN_NAMES)
+def test_mode_a_golden(gpu, name):
+    """reference-built tree, reference's own recorded answers"""
+    g = Golden(name)
+    acc = gpu.Accel(g.scene).import_qbvh(g.nodes, g.primid, g.aabb)
+    assert_hits_equal(acc.intersect(g.rays), g.hits, "closest")
+    assert_hits_equal(acc.intersect(g.bounce), g.hits_bounce, "bounce")
+    assert_hits_equal(acc.intersect(g.rays, g.max_dist), g.hits_md, "preset hit->dist")
+    assert np.array_equal(acc.visible(g.shadow, g.shadow_max_dist), g.vis)
+    assert np.array_equal(acc.aabb().view("u4"), g.aabb.view("u4"))
+    acc.close()
+
+
+@pytest.mark.parametrize("name", GOLDEN_NAMES)
+def test_mode_b_golden(gpu, name):
+    """GPU-built tree against the reference's recorded answers: differences must be proven ties"""
+    g = Golden(name)
+    acc = gpu.Accel(g.scene).build()
+    nodes, primid = acc.export_qbvh()
+    assert sorted(primid.tolist()) == sorted(g.primid.tolist())          # a permutation of the same prims
+    orc = Oracle(g.scene).import_tree(nodes, acc.aabb(), primid)
+    rc, stats = orc.check()
+    assert rc == 0 and stats[3] == g.scene.num_prims, f"tree check failed: {rc}"
+    has_lines = bool((R.primid_vcnt(g.primid) == R.PRIM_LINE).any())
+    if has_lines:   # line bounds go through libm (line.h:33-36): tolerance
+        assert np.allclose(acc.aabb(), g.aabb, rtol=1e-5, atol=1e-5)
+    else:
+        assert np.array_equal(acc.aabb().view("u4"), g.aabb.view("u4"))
+    for rays, want, md, what in [(g.rays, g.hits, None, "closest"), (g.bounce, g.hits_bounce, None, "bounce"),
+                                 (g.rays, g.hits_md, g.max_dist, "preset dist")]:
+        got = acc.intersect(rays, md)
+        assert_hits_equal(got, orc.intersect(rays, md), what + " vs oracle on the same tree")
+        nm, nt = classify_mismatches(orc, rays, got, want, md)
+        assert nm == nt, f"{what}: {nm - nt} of {nm} differences vs the reference are not ties"
+    assert np.array_equal(acc.visible(g.shadow, g.shadow_max_dist), g.vis)
+    acc.close()
+    orc.close()
+
+
+# --------------------------------------------------------------------------------------------- oracle, seeded
+CASES = {
+    "tris_100k": dict(num_tris=100000, seed=41),
+    "quads_mb_50k": dict(num_tris=50000, seed=42, quads=True, motion=True),
+    "analytic_mb_20k": dict(num_tris=20000, seed=43, analytic=True, motion=True),
+}
+
+
+@pytest.mark.parametrize("case", list(CASES))
+def test_mode_a_and_b_vs_oracle(gpu, case):
+    cfg = CASES[case]
+    tmax = 1.0 if cfg.get("motion") else 0.0
+    sc = S.synthetic_scene(**cfg)
+    orc = Oracle(sc).build()          # == reference tree for one build thread (tests/test_oracle_vs_ref.py)
+    rays = np.concatenate([S.camera_rays(150000, sc, time_max=tmax), S.random_rays(150000, sc, time_max=tmax)])
+    want = orc.intersect(rays)
+    br = S.bounce_rays(rays, want)
+    want_b = orc.intersect(br)
+    sr, md = S.shadow_rays(rays, want, (0.0, 0.0, 9.0))
+    want_v = orc.visible(sr, md)
+    acc = gpu.Accel(sc).import_qbvh(orc.nodes(), orc.primid(), orc.aabb())
+    assert_hits_equal(acc.intersect(rays), want, "mode A closest")
+    assert_hits_equal(acc.intersect(br), want_b, "mode A bounce")
+    assert np.array_equal(acc.visible(sr, md), want_v)
+    # counters follow ACCEL_DEBUG on the same tree
+    import torch
+    d_r = torch.from_numpy(rays[:50000].view("u1").reshape(-1).copy()).cuda()
+    d_o = torch.zeros(50000 * 24, dtype=torch.uint8, device="cuda")
+    cnt = acc.intersect_counted(d_r.data_ptr(), 0, d_o.data_ptr(), 50000)
+    _, oc = orc.intersect(rays[:50000], counters=True)
+    assert list(cnt) == list(oc)
+    # mode B
+    acc.build()
+    nodes, primid = acc.export_qbvh()
+    chk = Oracle(sc).import_tree(nodes, acc.aabb(), primid)
+    assert chk.check()[0] == 0
+    got = acc.intersect(rays)
+    assert_hits_equal(got, chk.intersect(rays), "mode B vs oracle on the GPU tree")
+    nm, nt = classify_mismatches(orc, rays, got, want)
+    assert nm == nt, f"{nm - nt} of {nm} mode-B differences are not ties"
+    got_b = acc.intersect(br)
+    nm, nt = classify_mismatches(orc, br, got_b, want_b)
+    assert nm == nt
+    assert np.array_equal(acc.visible(sr, md), want_v)
+    acc.close()
+    orc.close()
+    chk.close()
+
+
+# --------------------------------------------------------------------------------------------- edge cases
+def test_empty_scene(gpu):
+    sc = S.Scene([], "empty")
+    acc = gpu.Accel(sc).build()
+    rays = R.make_rays(np.zeros((5, 3), np.float32), np.float32([[0, 0, 1]] * 5))
+    h = acc.intersect(rays)
+    assert (R.hit_prim64(h) == R.INVALID_PRIMID).all() and (h["dist"] == R.FLT_MAX).all()
+    assert (acc.visible(rays, np.full(5, 3.0, np.float32)) == 1).all()
+    assert acc.num_nodes() == 1
+    acc.close()
+
+
+def test_zero_rays_and_tiny_scenes(gpu):
+    for ntri in (1, 2, 6, 7, 13):
+        pos = np.random.default_rng(ntri).random((3 * ntri, 3)).astype(np.float32)
+        sc = S.Scene([S.mesh_shape(pos, np.arange(3 * ntri).reshape(-1, 3))], f"tiny{ntri}")
+        acc = gpu.Accel(sc).build()
+        assert len(acc.intersect(np.zeros(0, R.RAY))) == 0
+        nodes, primid = acc.export_qbvh()
+        orc = Oracle(sc).import_tree(nodes, acc.aabb(), primid)
+        assert orc.check()[0] == 0
+        rays = S.random_rays(2000, sc, seed=ntri)
+        assert_hits_equal(acc.intersect(rays), orc.intersect(rays), f"{ntri} triangles")
+        acc.close()
+        orc.close()
+
+
+def test_duplicate_and_degenerate_prims(gpu):
+    """identical triangles (equal Morton codes: ties resolved by leaf order), zero-area triangles (det == 0 ->
+    inf/NaN comparisons fail closed, triangle.h:279-281)"""
+    rng = np.random.default_rng(7)
+    tri = rng.random((1, 3, 3)).astype(np.float32)
+    pos = np.concatenate([np.repeat(tri, 40, axis=0).reshape(-1, 3),           # 40 copies of one triangle
+                          np.repeat(rng.random((20, 1, 3)).astype(np.float32), 3, axis=1).reshape(-1, 3),  # points
+                          rng.random((300, 3)).astype(np.float32)])
+    sc = S.Scene([S.mesh_shape(pos, np.arange(len(pos)).reshape(-1, 3))], "dups")
+    acc = gpu.Accel(sc).build()
+    nodes, primid = acc.export_qbvh()
+    orc = Oracle(sc).import_tree(nodes, acc.aabb(), primid)
+    assert orc.check()[0] == 0
+    rays = S.random_rays(20000, sc, seed=8)
+    assert_hits_equal(acc.intersect(rays), orc.intersect(rays), "duplicates")
+    acc.close()
+    orc.close()
+
+
+def test_nan_inf_rays(gpu):
+    """axis-parallel directions (1/0 = inf, 0*inf = NaN in the slabs), NaN directions, zero directions:
+    must match the SSE select semantics of the reference (qbvhmp.c:1222-1223)"""
+    sc = S.synthetic_scene(3000, seed=9, quads=True)
+    orc = Oracle(sc).build()
+    lo, hi = sc.bounds()
+    rng = np.random.default_rng(10)
+    n = 6000
+    pos = (lo + rng.random((n, 3)) * (hi - lo)).astype(np.float32)
+    # snap many origins exactly onto vertex coordinates so that (box - pos) == 0 meets invdir == inf
+    vs = sc.shapes[0].vtx["v"]
+    pos[::2] = vs[rng.integers(0, len(vs), n // 2)]
+    d = np.zeros((n, 3), np.float32)
+    ax = rng.integers(0, 3, n)
+    d[np.arange(n), ax] = rng.choice(np.float32([-1, 1]), n)
+    d[5::7, :] = rng.choice(np.float32([0.0, -0.0, 1.0]), (len(d[5::7]), 3))
+    d[::11] = np.nan
+    rays = R.make_rays(pos, d)
+    acc = gpu.Accel(sc).import_qbvh(orc.nodes(), orc.primid(), orc.aabb())
+    assert_hits_equal(acc.intersect(rays), orc.intersect(rays), "degenerate rays")
+    md = np.full(n, 5.0, np.float32)
+    assert np.array_equal(acc.visible(rays, md), orc.visible(rays, md))
+    acc.close()
+    orc.close()
+
+
+def test_large_batch_is_chunked(gpu):
+    """> 4 Mi rays exercises the double-buffered staging path of cb200_accel_intersect_n"""
+    sc = S.synthetic_scene(20000, seed=11)
+    acc = gpu.Accel(sc).build()
+    rays = S.camera_rays((1 << 22) + 12345, sc, seed=12)
+    got = acc.intersect(rays)
+    nodes, primid = acc.export_qbvh()
+    orc = Oracle(sc).import_tree(nodes, acc.aabb(), primid)
+    idx = np.concatenate([np.arange(0, 50000), np.arange(len(rays) - 50000, len(rays))])
+    assert_hits_equal(got[idx], orc.intersect(rays[idx]), "chunked batch")
+    acc.close()
+    orc.close()
+
+
+# --------------------------------------------------------------------------------------------- host layer
+def test_host_layer_accel_h(gpu):
+    """the plain-C module (host/accel_b200.c): accel_init/build/intersect/visible/aabb through the reference's
+    own signatures, single rays and batches; accel_build permutes prims->primid like the reference"""
+    H = C.CDLL(os.path.join(ROOT, "corona-13_b200", "libcorona_host.so"))
+    H.accel_init.restype = C.c_void_p
+    H.accel_init.argtypes = [C.c_void_p]
+    H.accel_build.argtypes = [C.c_void_p, C.c_char_p]
+    H.accel_intersect.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+    H.accel_intersect_n.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64]
+    H.accel_visible.restype = C.c_int
+    H.accel_visible.argtypes = [C.c_void_p, C.c_void_p, C.c_float]
+    H.accel_aabb.restype = C.POINTER(C.c_float)
+    H.accel_aabb.argtypes = [C.c_void_p]
+    H.accel_cleanup.argtypes = [C.c_void_p]
+    H.prims_add_shape_mem.argtypes = [C.c_void_p, C.c_void_p]
+
+    class Prims(C.Structure):   # prims_t, include/prims.h:67-83
+        _fields_ = [("num_shapes", C.c_uint32), ("shape", C.c_void_p), ("num_loaded_prims", C.c_uint64),
+                    ("num_loaded_shapes", C.c_uint32), ("num_prims", C.c_uint64), ("primid", C.POINTER(C.c_uint64)),
+                    ("ghost_aabb", C.c_float * 6)]
+    sc = S.synthetic_scene(6000, seed=13, analytic=True)
+    p = Prims()
+    H.prims_init(C.byref(p))
+    H.prims_allocate(C.byref(p), len(sc.shapes))
+    cs = sc.cshapes()
+    for i in range(len(sc.shapes)):
+        H.prims_add_shape_mem(C.byref(p), C.byref(cs[i]))
+    H.prims_allocate_index(C.byref(p))
+    before = np.ctypeslib.as_array(p.primid, shape=(p.num_prims,)).copy()
+    a = H.accel_init(C.byref(p))
+    assert a
+    H.accel_build(a, None)
+    after = np.ctypeslib.as_array(p.primid, shape=(p.num_prims,)).copy()
+    assert not np.array_equal(before, after) and sorted(before.tolist()) == sorted(after.tolist())
+    acc = gpu.Accel(sc).build()
+    nodes, primid = acc.export_qbvh()
+    assert np.array_equal(primid, after)        # deterministic build: same permutation
+    orc = Oracle(sc).import_tree(nodes, acc.aabb(), primid)
+    rays = S.camera_rays(3000, sc, seed=14)
+    want = orc.intersect(rays)
+    hits = np.zeros(len(rays), R.HIT)
+    hits["prim"] = 0xFFFFFFFF
+    hits["dist"] = R.FLT_MAX
+    H.accel_intersect_n(a, rays.ctypes.data, hits.ctypes.data, len(rays))
+    got = np.zeros(len(rays), R.HITREC)
+    for f in ("prim", "u", "v", "dist"):
+        got[f] = hits[f]
+    assert_hits_equal(got, want, "accel_intersect_n")
+    sph = R.primid_vcnt(R.hit_prim64(want)) == R.PRIM_SPHERE
+    if sph.any():   # spheres also get hit->x (sphere.h:157)
+        x = rays["pos"][sph] + want["dist"][sph, None] * rays["dir"][sph]
+        assert np.allclose(hits["x"][sph], x, atol=1e-5)
+    for i in range(0, 40):   # single-ray entry = batch of one
+        h1 = np.zeros(1, R.HIT)
+        h1["prim"] = 0xFFFFFFFF
+        h1["dist"] = R.FLT_MAX
+        H.accel_intersect(a, rays[i:i + 1].ctypes.data, h1.ctypes.data)
+        assert h1["dist"][0].view("u4") == want["dist"][i].view("u4")
+        v = H.accel_visible(a, rays[i:i + 1].ctypes.data, C.c_float(1e3))
+        assert v == int(orc.visible(rays[i:i + 1], np.float32([1e3]))[0])
+    ab = np.ctypeslib.as_array(H.accel_aabb(a), shape=(6,))
+    assert np.allclose(ab, acc.aabb())
+    H.accel_cleanup(a)
+    acc.close()
+    orc.close()
+
+
+# --------------------------------------------------------------------------------------------- full size
+def test_full_size_properties(gpu):
+    """10 M triangles (BASELINE.json's synthetic config): properties that do not need the oracle at scale, plus an
+    oracle-checked sample"""
+    import torch
+    sc = S.synthetic_scene(10_000_000, seed=1)
+    acc = gpu.Accel(sc).build()
+    assert acc.num_prims() == sc.num_prims
+    n = 1 << 21
+    rays = np.concatenate([S.camera_rays(n, sc, seed=3), S.random_rays(n, sc, seed=4)])
+    h = acc.intersect(rays)
+    hit = R.hit_prim64(h) != R.INVALID_PRIMID
+    assert 0.2 < hit.mean() < 0.99
+    # (1) idempotence: searching again with hit->dist preset to the found distance returns the same hit
+    h2 = acc.intersect(rays, np.where(hit, h["dist"], R.FLT_MAX).astype(np.float32))
+    assert np.array_equal(h2.view("u1"), h.view("u1"))
+    # (2) closest-hit vs any-hit consistency: visible just short of the hit, occluded just beyond it
+    r = rays[hit]
+    d = h["dist"][hit]
+    ok = d > 1e-3
+    assert (acc.visible(r[ok], (d[ok] * np.float32(1 - 1e-4))) == 1).all()
+    assert (acc.visible(r[ok], (d[ok] * np.float32(1 + 1e-4))) == 0).all()
+    # (3) every prim appears exactly once in the permuted list; leaves reference valid ranges
+    nodes, primid = acc.export_qbvh()
+    assert len(np.unique(primid)) == sc.num_prims
+    # (4) oracle on the exported tree, 100 k ray sample
+    orc = Oracle(sc).import_tree(nodes, acc.aabb(), primid)
+    idx = np.random.default_rng(5).choice(len(rays), 100000, replace=False)
+    assert_hits_equal(h[idx], orc.intersect(rays[idx]), "10 M sample")
+    assert orc.check()[0] == 0
+    acc.close()
+    orc.close()
