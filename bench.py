@@ -82,10 +82,10 @@ class ClockSampler(threading.Thread):
         return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(self.rows[0][1]), "reasons": reasons, "samples": len(self.rows)}
 
 
-def make_waves(cb, scene, trace, n_primary, seed):
+def make_waves(cb, scene, trace, n_primary, seed, frame=None):
     """primary / bounce / shadow ray sets; `trace(rays)` returns closest hits (GPU arm: the GPU; reference arm: the reference)"""
     S = cb.scenes
-    prim = S.camera_rays(n_primary, scene, seed=100 + seed)
+    prim = S.camera_rays(n_primary, scene, seed=100 + seed, frame=frame)
     hits = trace(prim)
     bounce = S.bounce_rays(prim, hits, seed=200 + seed)
     shadow, smd = S.shadow_rays(prim, hits, LIGHT, seed=300 + seed)
@@ -112,7 +112,7 @@ def run_reference(args, rank, world):
         trace = lambda r, md=None: impl.intersect(r, md, nthreads=cores)
         vis = lambda r, md: impl.visible(r, md, nthreads=cores)
     n_sample = 1 << 19
-    prim, bounce, shadow, smd = make_waves(cb, scene, trace, n_sample, 0)
+    prim, bounce, shadow, smd = make_waves(cb, scene, trace, n_sample, 0, (1024, 512))
     rays_per_step = len(prim) + len(bounce) + len(shadow)
 
     def step():
@@ -172,7 +172,7 @@ def main():
     build_s = time.perf_counter() - t0
     node_b, prim_b = acc.layout()
     n_primary = WIDTH * HEIGHT
-    prim, bounce, shadow, smd = make_waves(cb, scene, lambda r: acc.intersect(r), n_primary, rank)
+    prim, bounce, shadow, smd = make_waves(cb, scene, lambda r: acc.intersect(r), n_primary, rank, (WIDTH, HEIGHT))
     waves = [("primary", prim, None), ("bounce", bounce, None), ("shadow", shadow, smd)]
     rays_per_step = sum(len(w[1]) for w in waves)
 

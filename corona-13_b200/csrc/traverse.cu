@@ -2,83 +2,109 @@
 //
 // Semantics follow accel_intersect / accel_visible (src/accel.d/qbvhmp.c:1262-1490):
 //   * four slab tests per node on time-interpolated boxes, clipped to [0, hit.dist]
-//     (tmin starts at 0, not ray.min_dist), SSE min/max select semantics spelled out so
-//     NaN/inf cases agree (second operand wins), qbvhmp.c:1188-1246;
+//     (tmin starts at 0, not ray.min_dist), SSE min/max select semantics (second operand wins on
+//     NaN), qbvhmp.c:1188-1246;
 //   * children visited in the reference's topological order from axis0/axis00/axis01 and the ray's
 //     sign bits, the others pushed far->near together with their entry distance, qbvhmp.c:1313-1354;
 //   * popped entries whose entry distance exceeds the current hit distance are skipped, :1357-1386;
 //   * leaf primitives tested in primid[] order, "dist <= hit.dist" so the last tested wins ties.
 //
-// Mapping: one ray per thread, while-while loop, persistent warps pulling 32-ray batches from a
-// global ticket counter; per-thread traversal stack in local memory (L1-resident).
+// Mapping (round-1 ncu finding: plain one-ray-per-thread while-while ran at 4.8 of 32 lanes active):
+//   * persistent warps; every lane owns one ray at a time and is REFILLED from a global ticket
+//     counter the moment its ray terminates, so short rays do not leave lanes idle;
+//   * each lane is in one of two states, NODE (next: a 4-box node test) or PRIM (next: one primitive
+//     test of its current leaf); per warp iteration a vote picks which of the two code paths runs, so
+//     both execute with many lanes active.  Every ray still sees exactly the reference's own sequence
+//     of node and primitive tests;
+//   * rays whose origin/direction are finite and non-zero take a slab test built from FMNMX
+//     min/max (identical results up to the sign of zero); all others take the exact select form.
 #include "prims.cuh"
+#include <atomic>
+#include <mutex>
+#include <cstdlib>
 
 #define TRACE_BLOCK 128
+#define FULL 0xffffffffu
 
 __device__ __forceinline__ float sse_min(float a, float b) { return a < b ? a : b; }   // _mm_min_ps
 __device__ __forceinline__ float sse_max(float a, float b) { return a > b ? a : b; }   // _mm_max_ps
 
-template<bool MB>
-__device__ __forceinline__ void node_slabs(const void *nodes, uint64_t idx, const RayD &r, float ix, float iy, float iz,
-                                           float t0, float t1, float tmax_init, float tmin[4], float tmax[4],
-                                           uint64_t child[4], int &axis0, int &axis00, int &axis01)
+struct NodeOut
 {
-  tmin[0] = tmin[1] = tmin[2] = tmin[3] = 0.0f;
-  tmax[0] = tmax[1] = tmax[2] = tmax[3] = tmax_init;
-  const float pos[3] = {r.px, r.py, r.pz};
+  float tmin[4];
+  bool hit[4];
+  uint64_t child[4];
+  int axis0, axis00, axis01;
+};
+
+// EXACT: reference select semantics; otherwise fminf/fmaxf (only valid when no NaN can occur)
+template<bool MB, bool EXACT>
+__device__ __forceinline__ void node_slabs(const void *nodes, uint64_t idx, float px, float py, float pz,
+                                           float ix, float iy, float iz, float t0, float t1, float tmax_init, NodeOut &o)
+{
+  float tmin[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+  float tmax[4] = {tmax_init, tmax_init, tmax_init, tmax_init};
+  const float pos[3] = {px, py, pz};
   const float inv[3] = {ix, iy, iz};
+  const float4 *a0;
+  const ulonglong2 *ch;
   if(MB)
   {
     const Node256 *n = reinterpret_cast<const Node256 *>(nodes) + idx;
-    const float4 *a0 = reinterpret_cast<const float4 *>(n->aabb0);
-    const float4 *a1 = reinterpret_cast<const float4 *>(n->aabb1);
-#pragma unroll
-    for(int k=0;k<3;k++)
-    {
-      const float4 m0 = __ldg(a0 + k), M0 = __ldg(a0 + k + 3);
-      const float4 m1 = __ldg(a1 + k), M1 = __ldg(a1 + k + 3);
-      const float mo[4] = {m0.x, m0.y, m0.z, m0.w}, Mo[4] = {M0.x, M0.y, M0.z, M0.w};
-      const float mc[4] = {m1.x, m1.y, m1.z, m1.w}, Mc[4] = {M1.x, M1.y, M1.z, M1.w};
-#pragma unroll
-      for(int c=0;c<4;c++)
-      {
-        const float lo = ((mo[c]*t0 + mc[c]*t1) - pos[k]) * inv[k];
-        const float hi = ((Mo[c]*t0 + Mc[c]*t1) - pos[k]) * inv[k];
-        tmin[c] = sse_max(tmin[c], sse_min(lo, hi));
-        tmax[c] = sse_min(tmax[c], sse_max(lo, hi));
-      }
-    }
-    const ulonglong2 c01 = __ldg(reinterpret_cast<const ulonglong2 *>(n->child));
-    const ulonglong2 c23 = __ldg(reinterpret_cast<const ulonglong2 *>(n->child) + 1);
-    child[0] = c01.x; child[1] = c01.y; child[2] = c23.x; child[3] = c23.y;
-    const ulonglong2 pa = __ldg(reinterpret_cast<const ulonglong2 *>(&n->parent));
-    const ulonglong2 aa = __ldg(reinterpret_cast<const ulonglong2 *>(&n->axis00));
-    axis0 = (int)pa.y; axis00 = (int)aa.x; axis01 = (int)aa.y;
+    a0 = reinterpret_cast<const float4 *>(n->aabb0);
+    ch = reinterpret_cast<const ulonglong2 *>(n->child);
   }
   else
   {
     const Node128 *n = reinterpret_cast<const Node128 *>(nodes) + idx;
-    const float4 *a0 = reinterpret_cast<const float4 *>(n->aabb0);
+    a0 = reinterpret_cast<const float4 *>(n->aabb0);
+    ch = reinterpret_cast<const ulonglong2 *>(n->child);
+  }
 #pragma unroll
-    for(int k=0;k<3;k++)
+  for(int k=0;k<3;k++)
+  {
+    const float4 m0 = __ldg(a0 + k), M0 = __ldg(a0 + k + 3);
+    float mo[4] = {m0.x, m0.y, m0.z, m0.w}, Mo[4] = {M0.x, M0.y, M0.z, M0.w};
+    if(MB)
     {
-      const float4 m0 = __ldg(a0 + k), M0 = __ldg(a0 + k + 3);
-      const float mo[4] = {m0.x, m0.y, m0.z, m0.w}, Mo[4] = {M0.x, M0.y, M0.z, M0.w};
+      const float4 m1 = __ldg(a0 + 6 + k), M1 = __ldg(a0 + 6 + k + 3);
+      const float mc[4] = {m1.x, m1.y, m1.z, m1.w}, Mc[4] = {M1.x, M1.y, M1.z, M1.w};
 #pragma unroll
-      for(int c=0;c<4;c++)
+      for(int c=0;c<4;c++) { mo[c] = mo[c]*t0 + mc[c]*t1; Mo[c] = Mo[c]*t0 + Mc[c]*t1; }
+    }
+#pragma unroll
+    for(int c=0;c<4;c++)
+    {
+      const float lo = (mo[c] - pos[k]) * inv[k];
+      const float hi = (Mo[c] - pos[k]) * inv[k];
+      if(EXACT)
       {
-        const float lo = (mo[c] - pos[k]) * inv[k];
-        const float hi = (Mo[c] - pos[k]) * inv[k];
         tmin[c] = sse_max(tmin[c], sse_min(lo, hi));
         tmax[c] = sse_min(tmax[c], sse_max(lo, hi));
       }
+      else
+      {
+        tmin[c] = fmaxf(tmin[c], fminf(lo, hi));
+        tmax[c] = fminf(tmax[c], fmaxf(lo, hi));
+      }
     }
-    const ulonglong2 c01 = __ldg(reinterpret_cast<const ulonglong2 *>(n->child));
-    const ulonglong2 c23 = __ldg(reinterpret_cast<const ulonglong2 *>(n->child) + 1);
-    const uint32_t ax = (uint32_t)(c01.x >> CB_AXIS_SHIFT) & 63u;
-    child[0] = c01.x & CB_CHILD_MASK; child[1] = c01.y; child[2] = c23.x; child[3] = c23.y;
-    axis0 = ax & 3; axis00 = (ax >> 2) & 3; axis01 = (ax >> 4) & 3;
   }
+  const ulonglong2 c01 = __ldg(ch), c23 = __ldg(ch + 1);
+  if(MB)
+  {
+    const ulonglong2 pa = __ldg(ch + 2), aa = __ldg(ch + 3);   // {parent, axis0}, {axis00, axis01}
+    o.child[0] = c01.x;
+    o.axis0 = (int)pa.y; o.axis00 = (int)aa.x; o.axis01 = (int)aa.y;
+  }
+  else
+  {
+    const uint32_t ax = (uint32_t)(c01.x >> CB_AXIS_SHIFT) & 63u;
+    o.child[0] = c01.x & CB_CHILD_MASK;
+    o.axis0 = ax & 3; o.axis00 = (ax >> 2) & 3; o.axis01 = (ax >> 4) & 3;
+  }
+  o.child[1] = c01.y; o.child[2] = c23.x; o.child[3] = c23.y;
+#pragma unroll
+  for(int c=0;c<4;c++) { o.tmin[c] = tmin[c]; o.hit[c] = tmin[c] <= tmax[c]; }
 }
 
 __device__ __forceinline__ void load_ray(const cb_ray_t *rays, uint64_t i, RayD &r)
@@ -90,196 +116,276 @@ __device__ __forceinline__ void load_ray(const cb_ray_t *rays, uint64_t i, RayD 
   r.ign_lo = __float_as_uint(e.x); r.ign_hi = __float_as_uint(e.y);
 }
 
-// one closest-hit traversal.  CNT adds the reference's ACCEL_DEBUG counters (qbvhmp.c:83-90).
-template<bool MB, bool CNT, int STACK>
-__device__ __forceinline__ void trace_closest(const DevAccel &A, const RayD &r, HitD &h, unsigned long long cnt[4])
-{
-  const uint32_t nearx = __float_as_uint(r.dx) >> 31, neary = __float_as_uint(r.dy) >> 31, nearz = __float_as_uint(r.dz) >> 31;
-  const uint32_t nearbits = nearx | (neary << 1) | (nearz << 2);
-  const float ix = 1.0f/r.dx, iy = 1.0f/r.dy, iz = 1.0f/r.dz;
-  const float t1 = r.time, t0 = 1.0f - r.time;
-  uint64_t stack[STACK];
-  float stack_dist[STACK];
-  int sp = 0;
-  uint64_t node = 0;
-  if(CNT) cnt[0]++;
-  while(true)
-  {
-    float tmin[4], tmax[4];
-    uint64_t child[4];
-    int axis0, axis00, axis01;
-    node_slabs<MB>(A.nodes, node, r, ix, iy, iz, t0, t1, h.dist, tmin, tmax, child, axis0, axis00, axis01);
-    bool hitc[4];
-    bool any = false;
-#pragma unroll
-    for(int c=0;c<4;c++) { hitc[c] = tmin[c] <= tmax[c]; any |= hitc[c]; }
-    uint64_t current = 0;
-    bool have = false;
-    if(any)
-    {
-      if(CNT) { cnt[1]++; for(int c=0;c<4;c++) cnt[2] += hitc[c] ? 1 : 0; }
-      // empty leaves (count 0) can only be popped and dropped again: never visit them
-#pragma unroll
-      for(int c=0;c<4;c++) if(child[c] == CB_LEAF_BIT) hitc[c] = false;
-      const uint32_t n0 = (nearbits >> axis0) & 1u;
-      const int axis1n = n0 ? axis01 : axis00;
-      const int axis1f = n0 ? axis00 : axis01;
-      const uint32_t n1n = (nearbits >> axis1n) & 1u, n1f = (nearbits >> axis1f) & 1u;
-      const uint32_t f0 = n0 ^ 1u;
-      const uint32_t n11 = (f0 << 1) | (n1f ^ 1u);
-      const uint32_t n10 = (f0 << 1) | n1f;
-      const uint32_t n01 = (n0 << 1) | (n1n ^ 1u);
-      const uint32_t n00 = (n0 << 1) | n1n;
-      // select by dynamic index without local-memory arrays
-#define SEL4(arr, i) ((i) == 0 ? arr[0] : (i) == 1 ? arr[1] : (i) == 2 ? arr[2] : arr[3])
-      const bool h00 = SEL4(hitc, n00), h01 = SEL4(hitc, n01), h10 = SEL4(hitc, n10), h11 = SEL4(hitc, n11);
-      // far -> near push order: n11, n10, n01; the nearest hit child becomes current
-      const int first = h00 ? 0 : h01 ? 1 : h10 ? 2 : h11 ? 3 : 4;
-      if(first < 4)
-      {
-        have = true;
-        if(h11 && first < 3) { stack_dist[sp] = SEL4(tmin, n11); stack[sp++] = SEL4(child, n11); }
-        if(h10 && first < 2) { stack_dist[sp] = SEL4(tmin, n10); stack[sp++] = SEL4(child, n10); }
-        if(h01 && first < 1) { stack_dist[sp] = SEL4(tmin, n01); stack[sp++] = SEL4(child, n01); }
-        const uint32_t nf = first == 0 ? n00 : first == 1 ? n01 : first == 2 ? n10 : n11;
-        current = SEL4(child, nf);
-      }
-#undef SEL4
-    }
-    if(!have)
-    {
-      do
-      {
-        if(sp == 0) return;
-        --sp;
-        current = stack[sp];
-      }
-      while(stack_dist[sp] > h.dist);
-    }
-    while(current & CB_LEAF_BIT)
-    {
-      const uint64_t begin = (current ^ CB_LEAF_BIT) >> 5;
-      const uint32_t num = (uint32_t)current & 31u;
-      const float4 *rec = A.recs + begin*(uint64_t)(A.rec_units*4);
-      for(uint32_t k=0;k<num;k++)
-      {
-        if(CNT) cnt[3]++;
-        prim_intersect(rec, A.rec_units, r, h);
-        rec += A.rec_units*4;
-      }
-      do
-      {
-        if(sp == 0) return;
-        --sp;
-        current = stack[sp];
-      }
-      while(stack_dist[sp] > h.dist);
-    }
-    node = current;
-  }
-}
+__device__ __forceinline__ bool finite_nonzero(float x) { const float a = fabsf(x); return a > 0.0f && a < __int_as_float(0x7f800000); }
+__device__ __forceinline__ bool finite(float x) { return fabsf(x) < __int_as_float(0x7f800000); }
 
-// any-hit sweep; returns 1 when nothing blocks the ray up to max_dist (accel_visible semantics).
-template<bool MB, int STACK>
-__device__ __forceinline__ int trace_visible(const DevAccel &A, const RayD &r, float max_dist)
-{
-  const float ix = 1.0f/r.dx, iy = 1.0f/r.dy, iz = 1.0f/r.dz;
-  const float t1 = r.time, t0 = 1.0f - r.time;
-  uint64_t stack[STACK];
-  int sp = 0;
-  uint64_t node = 0;
-  while(true)
-  {
-    float tmin[4], tmax[4];
-    uint64_t child[4];
-    int axis0, axis00, axis01;
-    node_slabs<MB>(A.nodes, node, r, ix, iy, iz, t0, t1, max_dist, tmin, tmax, child, axis0, axis00, axis01);
-#pragma unroll
-    for(int c=0;c<4;c++) if(tmin[c] <= tmax[c] && child[c] != CB_LEAF_BIT) stack[sp++] = child[c];
-    uint64_t current;
-    while(true)
-    {
-      if(sp == 0) return 1;
-      current = stack[--sp];
-      if(!(current & CB_LEAF_BIT)) break;
-      const uint64_t begin = (current ^ CB_LEAF_BIT) >> 5;
-      const uint32_t num = (uint32_t)current & 31u;
-      const float4 *rec = A.recs + begin*(uint64_t)(A.rec_units*4);
-      for(uint32_t k=0;k<num;k++, rec += A.rec_units*4)
-        if(prim_visible(rec, A.rec_units, r, max_dist)) return 0;
-    }
-    node = current;
-  }
-}
+// a leaf reference with count 0 (the reference builder emits them with a non-zero begin, qbvhmp.c:989)
+__device__ __forceinline__ bool is_empty_leaf(uint64_t c) { return (c & CB_LEAF_BIT) && !(c & 31ull); }
+
+#define SEL4(arr, i) ((i) == 0 ? arr[0] : (i) == 1 ? arr[1] : (i) == 2 ? arr[2] : arr[3])
+
+enum { ST_IDLE = 0, ST_NODE = 1, ST_PRIM = 2 };
 
 // ---------------------------------------------------------------------------------------------
-// kernels: persistent warps, each pulls 32 consecutive rays per ticket
+// closest hit
 // ---------------------------------------------------------------------------------------------
 template<bool MB, bool CNT, int STACK>
 __global__ void __launch_bounds__(TRACE_BLOCK)
 k_intersect(DevAccel A, const cb_ray_t *__restrict__ rays, const float *__restrict__ max_dist,
-            cb_hitrec_t *__restrict__ out, uint64_t n, unsigned long long *ticket, unsigned long long *counters)
+            cb_hitrec_t *__restrict__ out, uint64_t n, unsigned long long *ticket, unsigned long long *counters,
+            int prim_threshold)
 {
   const uint32_t lane = threadIdx.x & 31u;
+  const uint32_t lt_mask = (1u << lane) - 1u;
   unsigned long long cnt[4] = {0, 0, 0, 0};
+  uint64_t stack[STACK];
+  float stack_dist[STACK];
+  int sp = 0;
+  int state = ST_IDLE;
+  bool exhausted = false;
+  RayD r;
+  HitD h;
+  uint64_t ray_i = 0, cur = 0;
+  float ix = 0.0f, iy = 0.0f, iz = 0.0f, t0 = 1.0f, t1 = 0.0f;
+  uint32_t nearbits = 0;
+  bool exact = false;
+  const float4 *rec = nullptr;
+  uint32_t prims_left = 0;
+  const uint32_t rec_stride = A.rec_units*4;
+  r.px = r.py = r.pz = r.dx = r.dy = r.dz = r.time = r.min_dist = 0.0f; r.ign_lo = r.ign_hi = 0;
+  h.dist = 0.0f; h.u = h.v = 0.0f; h.prim_lo = h.prim_hi = 0;
+
   while(true)
   {
-    unsigned long long base = 0;
-    if(lane == 0) base = atomicAdd(ticket, 32ull);
-    base = __shfl_sync(0xffffffffu, base, 0);
-    if(base >= n) break;
-    const uint64_t i = base + lane;
-    if(i < n)
+    // ---- refill idle lanes from the global ray queue
+    const uint32_t idle = __ballot_sync(FULL, state == ST_IDLE);
+    if(idle && !exhausted)
     {
-      RayD r;
-      load_ray(rays, i, r);
-      HitD h;
-      h.dist = max_dist ? __ldg(max_dist + i) : FLT_MAX;
-      h.u = 0.0f; h.v = 0.0f;
-      h.prim_lo = 0xffffffffu; h.prim_hi = 0xffffffffu;
-      trace_closest<MB, CNT, STACK>(A, r, h, cnt);
-      // 24-byte record: three 8-byte stores
-      uint2 *o = reinterpret_cast<uint2 *>(out + i);
-      o[0] = make_uint2(h.prim_lo, h.prim_hi);
-      o[1] = make_uint2(__float_as_uint(h.u), __float_as_uint(h.v));
-      o[2] = make_uint2(__float_as_uint(h.dist), 0u);
+      const uint32_t want = __popc(idle);
+      unsigned long long base = 0;
+      if(lane == 0) base = atomicAdd(ticket, (unsigned long long)want);
+      base = __shfl_sync(FULL, base, 0);
+      if(base + want >= n) exhausted = true;
+      if(state == ST_IDLE)
+      {
+        const uint64_t i = base + __popc(idle & lt_mask);
+        if(i < n)
+        {
+          load_ray(rays, i, r);
+          ray_i = i;
+          h.dist = max_dist ? __ldg(max_dist + i) : FLT_MAX;
+          h.u = 0.0f; h.v = 0.0f; h.prim_lo = 0xffffffffu; h.prim_hi = 0xffffffffu;
+          nearbits = (__float_as_uint(r.dx) >> 31) | ((__float_as_uint(r.dy) >> 31) << 1) | ((__float_as_uint(r.dz) >> 31) << 2);
+          ix = 1.0f/r.dx; iy = 1.0f/r.dy; iz = 1.0f/r.dz;
+          t1 = r.time; t0 = 1.0f - r.time;
+          exact = !(finite_nonzero(ix) && finite_nonzero(iy) && finite_nonzero(iz) &&
+                    finite(r.px) && finite(r.py) && finite(r.pz) && finite(r.time) && !(h.dist != h.dist));
+          sp = 0; cur = 0; state = ST_NODE;
+          if(CNT) cnt[0]++;
+        }
+      }
+    }
+    const uint32_t mN = __ballot_sync(FULL, state == ST_NODE);
+    const uint32_t mP = __ballot_sync(FULL, state == ST_PRIM);
+    if(!(mN | mP)) break;
+    const bool do_prims = (mN == 0u) || (__popc(mP) >= prim_threshold);
+
+    bool need_pop = false, new_cur = false;
+    if(do_prims)
+    {
+      if(state == ST_PRIM)
+      {
+        if(CNT) cnt[3]++;
+        prim_intersect(rec, A.rec_units, r, h);
+        rec += rec_stride;
+        if(--prims_left == 0) need_pop = true;
+      }
+    }
+    else if(state == ST_NODE)
+    {
+      NodeOut o;
+      if(exact) node_slabs<MB, true >(A.nodes, cur, r.px, r.py, r.pz, ix, iy, iz, t0, t1, h.dist, o);
+      else      node_slabs<MB, false>(A.nodes, cur, r.px, r.py, r.pz, ix, iy, iz, t0, t1, h.dist, o);
+      const bool any = o.hit[0] | o.hit[1] | o.hit[2] | o.hit[3];
+      need_pop = true;
+      if(any)
+      {
+        if(CNT) { cnt[1]++; for(int c=0;c<4;c++) cnt[2] += o.hit[c] ? 1 : 0; }
+        // empty leaves (count 0) can only be popped and dropped again: never visit them
+#pragma unroll
+        for(int c=0;c<4;c++) if(is_empty_leaf(o.child[c])) o.hit[c] = false;
+        const uint32_t n0 = (nearbits >> o.axis0) & 1u;
+        const int axis1n = n0 ? o.axis01 : o.axis00;
+        const int axis1f = n0 ? o.axis00 : o.axis01;
+        const uint32_t n1n = (nearbits >> axis1n) & 1u, n1f = (nearbits >> axis1f) & 1u;
+        const uint32_t f0 = n0 ^ 1u;
+        const uint32_t n11 = (f0 << 1) | (n1f ^ 1u);
+        const uint32_t n10 = (f0 << 1) | n1f;
+        const uint32_t n01 = (n0 << 1) | (n1n ^ 1u);
+        const uint32_t n00 = (n0 << 1) | n1n;
+        const bool h00 = SEL4(o.hit, n00), h01 = SEL4(o.hit, n01), h10 = SEL4(o.hit, n10), h11 = SEL4(o.hit, n11);
+        // far -> near push order: n11, n10, n01; the nearest hit child becomes current
+        const int first = h00 ? 0 : h01 ? 1 : h10 ? 2 : h11 ? 3 : 4;
+        if(first < 4)
+        {
+          if(h11 && first < 3) { stack_dist[sp] = SEL4(o.tmin, n11); stack[sp++] = SEL4(o.child, n11); }
+          if(h10 && first < 2) { stack_dist[sp] = SEL4(o.tmin, n10); stack[sp++] = SEL4(o.child, n10); }
+          if(h01 && first < 1) { stack_dist[sp] = SEL4(o.tmin, n01); stack[sp++] = SEL4(o.child, n01); }
+          const uint32_t nf = first == 0 ? n00 : first == 1 ? n01 : first == 2 ? n10 : n11;
+          cur = SEL4(o.child, nf);
+          need_pop = false;
+          new_cur = true;
+        }
+      }
+    }
+    if(need_pop)
+    {
+      while(sp > 0)
+      {
+        --sp;
+        if(stack_dist[sp] > h.dist) continue;
+        cur = stack[sp];
+        new_cur = true;
+        break;
+      }
+      if(!new_cur)
+      { // ray finished: 24-byte record as three 8-byte stores
+        uint2 *o2 = reinterpret_cast<uint2 *>(out + ray_i);
+        o2[0] = make_uint2(h.prim_lo, h.prim_hi);
+        o2[1] = make_uint2(__float_as_uint(h.u), __float_as_uint(h.v));
+        o2[2] = make_uint2(__float_as_uint(h.dist), 0u);
+        state = ST_IDLE;
+      }
+    }
+    if(new_cur)
+    {
+      if(cur & CB_LEAF_BIT)
+      {
+        rec = A.recs + ((cur ^ CB_LEAF_BIT) >> 5)*(uint64_t)rec_stride;
+        prims_left = (uint32_t)cur & 31u;
+        state = ST_PRIM;   // empty leaves are never pushed, so prims_left >= 1
+      }
+      else state = ST_NODE;
     }
   }
   if(CNT)
     for(int k=0;k<4;k++) if(cnt[k]) atomicAdd(counters + k, cnt[k]);
 }
 
+// ---------------------------------------------------------------------------------------------
+// any hit: returns 1 when nothing blocks the ray up to max_dist (accel_visible semantics; the result
+// is a boolean, so visiting order is free)
+// ---------------------------------------------------------------------------------------------
 template<bool MB, int STACK>
 __global__ void __launch_bounds__(TRACE_BLOCK)
 k_visible(DevAccel A, const cb_ray_t *__restrict__ rays, const float *__restrict__ max_dist,
-          int32_t *__restrict__ out, uint64_t n, unsigned long long *ticket)
+          int32_t *__restrict__ out, uint64_t n, unsigned long long *ticket, int prim_threshold)
 {
   const uint32_t lane = threadIdx.x & 31u;
+  const uint32_t lt_mask = (1u << lane) - 1u;
+  uint64_t stack[STACK];
+  int sp = 0;
+  int state = ST_IDLE;
+  bool exhausted = false;
+  RayD r;
+  uint64_t ray_i = 0, cur = 0;
+  float ix = 0.0f, iy = 0.0f, iz = 0.0f, t0 = 1.0f, t1 = 0.0f, md = 0.0f;
+  bool exact = false;
+  const float4 *rec = nullptr;
+  uint32_t prims_left = 0;
+  const uint32_t rec_stride = A.rec_units*4;
+  r.px = r.py = r.pz = r.dx = r.dy = r.dz = r.time = r.min_dist = 0.0f; r.ign_lo = r.ign_hi = 0;
+
   while(true)
   {
-    unsigned long long base = 0;
-    if(lane == 0) base = atomicAdd(ticket, 32ull);
-    base = __shfl_sync(0xffffffffu, base, 0);
-    if(base >= n) break;
-    const uint64_t i = base + lane;
-    if(i < n)
+    const uint32_t idle = __ballot_sync(FULL, state == ST_IDLE);
+    if(idle && !exhausted)
     {
-      RayD r;
-      load_ray(rays, i, r);
-      out[i] = trace_visible<MB, STACK>(A, r, __ldg(max_dist + i));
+      const uint32_t want = __popc(idle);
+      unsigned long long base = 0;
+      if(lane == 0) base = atomicAdd(ticket, (unsigned long long)want);
+      base = __shfl_sync(FULL, base, 0);
+      if(base + want >= n) exhausted = true;
+      if(state == ST_IDLE)
+      {
+        const uint64_t i = base + __popc(idle & lt_mask);
+        if(i < n)
+        {
+          load_ray(rays, i, r);
+          ray_i = i;
+          md = __ldg(max_dist + i);
+          ix = 1.0f/r.dx; iy = 1.0f/r.dy; iz = 1.0f/r.dz;
+          t1 = r.time; t0 = 1.0f - r.time;
+          exact = !(finite_nonzero(ix) && finite_nonzero(iy) && finite_nonzero(iz) &&
+                    finite(r.px) && finite(r.py) && finite(r.pz) && finite(r.time) && !(md != md));
+          sp = 0; cur = 0; state = ST_NODE;
+        }
+      }
     }
+    const uint32_t mN = __ballot_sync(FULL, state == ST_NODE);
+    const uint32_t mP = __ballot_sync(FULL, state == ST_PRIM);
+    if(!(mN | mP)) break;
+    const bool do_prims = (mN == 0u) || (__popc(mP) >= prim_threshold);
+    bool need_pop = false;
+    int result = -1;
+    if(do_prims)
+    {
+      if(state == ST_PRIM)
+      {
+        if(prim_visible(rec, A.rec_units, r, md)) result = 0;
+        rec += rec_stride;
+        if(--prims_left == 0) need_pop = true;
+      }
+    }
+    else if(state == ST_NODE)
+    {
+      NodeOut o;
+      if(exact) node_slabs<MB, true >(A.nodes, cur, r.px, r.py, r.pz, ix, iy, iz, t0, t1, md, o);
+      else      node_slabs<MB, false>(A.nodes, cur, r.px, r.py, r.pz, ix, iy, iz, t0, t1, md, o);
+#pragma unroll
+      for(int c=0;c<4;c++) if(o.hit[c] && !is_empty_leaf(o.child[c])) stack[sp++] = o.child[c];
+      need_pop = true;
+    }
+    if(result < 0 && need_pop)
+    {
+      if(sp > 0)
+      {
+        cur = stack[--sp];
+        if(cur & CB_LEAF_BIT)
+        {
+          rec = A.recs + ((cur ^ CB_LEAF_BIT) >> 5)*(uint64_t)rec_stride;
+          prims_left = (uint32_t)cur & 31u;
+          state = ST_PRIM;
+        }
+        else state = ST_NODE;
+      }
+      else result = 1;
+    }
+    if(result >= 0) { out[ray_i] = result; state = ST_IDLE; }
   }
 }
 
 // ---------------------------------------------------------------------------------------------
 // host launchers
 // ---------------------------------------------------------------------------------------------
-#include <atomic>
-#include <mutex>
 static unsigned long long *g_tickets = nullptr;   // ring of ticket counters, zeroed asynchronously
 static std::atomic<unsigned> g_ticket_next{0};
 static std::mutex g_ticket_mutex;
 #define NUM_TICKETS 256
+static int g_prim_threshold = -1;
+
+static int prim_threshold()
+{
+  if(g_prim_threshold < 0)
+  {
+    const char *e = getenv("CB200_PRIM_THRESHOLD");
+    int v = e ? atoi(e) : 12;
+    if(v < 1) v = 1;
+    if(v > 32) v = 32;
+    g_prim_threshold = v;
+  }
+  return g_prim_threshold;
+}
 
 static int get_ticket(cudaStream_t stream, unsigned long long **t)
 {
@@ -299,7 +405,7 @@ static int grid_for(uint64_t n, const void *kernel)
   cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, TRACE_BLOCK, 0);
   if(per_sm < 1) per_sm = 1;
   const uint64_t want = (n + TRACE_BLOCK - 1)/TRACE_BLOCK;
-  const uint64_t full = (uint64_t)cb200_sm_count_cached()*per_sm;
+  const uint64_t full = (uint64_t)cb200_sm_count_cached()*per_sm;   // a multiple of the SM count: one resident wave
   return (int)(want < full ? (want ? want : 1) : full);
 }
 
@@ -315,20 +421,21 @@ static int launch_intersect_t(const cb200_accel *a, const cb_ray_t *d_rays, cons
   unsigned long long *ticket;
   if(get_ticket(stream, &ticket)) return CB200_ERR_CUDA;
   const int need = 3*a->depth + 1;
+  const int thr = prim_threshold();
   if(need <= STACK_SMALL)
   {
     auto k = k_intersect<MB, CNT, STACK_SMALL>;
-    k<<<grid_for(n, (const void *)k), TRACE_BLOCK, 0, stream>>>(a->dev, d_rays, d_max_dist, d_out, n, ticket, d_counters);
+    k<<<grid_for(n, (const void *)k), TRACE_BLOCK, 0, stream>>>(a->dev, d_rays, d_max_dist, d_out, n, ticket, d_counters, thr);
   }
   else if(need <= STACK_MID)
   {
     auto k = k_intersect<MB, CNT, STACK_MID>;
-    k<<<grid_for(n, (const void *)k), TRACE_BLOCK, 0, stream>>>(a->dev, d_rays, d_max_dist, d_out, n, ticket, d_counters);
+    k<<<grid_for(n, (const void *)k), TRACE_BLOCK, 0, stream>>>(a->dev, d_rays, d_max_dist, d_out, n, ticket, d_counters, thr);
   }
   else if(need <= STACK_BIG)
   {
     auto k = k_intersect<MB, CNT, STACK_BIG>;
-    k<<<grid_for(n, (const void *)k), TRACE_BLOCK, 0, stream>>>(a->dev, d_rays, d_max_dist, d_out, n, ticket, d_counters);
+    k<<<grid_for(n, (const void *)k), TRACE_BLOCK, 0, stream>>>(a->dev, d_rays, d_max_dist, d_out, n, ticket, d_counters, thr);
   }
   else { cb200_set_error("tree deeper than the reference's MAX_TREE_DEPTH"); return CB200_ERR_UNSUPPORTED; }
   cb200_count_launch();
@@ -352,16 +459,17 @@ static int launch_visible_t(const cb200_accel *a, const cb_ray_t *d_rays, const 
 {
   unsigned long long *ticket;
   if(get_ticket(stream, &ticket)) return CB200_ERR_CUDA;
-  const int need = 4*a->depth + 4;   // the any-hit sweep pushes up to 4 children per level
+  const int need = 3*a->depth + 4;   // the any-hit sweep pushes up to 4 children and pops one per level
+  const int thr = prim_threshold();
   if(need <= STACK_MID)
   {
     auto k = k_visible<MB, STACK_MID>;
-    k<<<grid_for(n, (const void *)k), TRACE_BLOCK, 0, stream>>>(a->dev, d_rays, d_max_dist, d_out, n, ticket);
+    k<<<grid_for(n, (const void *)k), TRACE_BLOCK, 0, stream>>>(a->dev, d_rays, d_max_dist, d_out, n, ticket, thr);
   }
-  else if(need <= 4*101 + 4)
+  else if(need <= STACK_BIG + 8)
   {
-    auto k = k_visible<MB, 4*101 + 4>;
-    k<<<grid_for(n, (const void *)k), TRACE_BLOCK, 0, stream>>>(a->dev, d_rays, d_max_dist, d_out, n, ticket);
+    auto k = k_visible<MB, STACK_BIG + 8>;
+    k<<<grid_for(n, (const void *)k), TRACE_BLOCK, 0, stream>>>(a->dev, d_rays, d_max_dist, d_out, n, ticket, thr);
   }
   else { cb200_set_error("tree deeper than the reference's MAX_TREE_DEPTH"); return CB200_ERR_UNSUPPORTED; }
   cb200_count_launch();

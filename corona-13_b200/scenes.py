@@ -329,8 +329,11 @@ def merge_shapes(shapes, material, name):
 
 
 # ----------------------------------------------------------------------------- ray sets
-def camera_rays(n, scene, seed=3, eye=None, time_max=0.0):
-    """pinhole-ish primary rays looking at the scene (kernel-only ray set 1)"""
+def camera_rays(n, scene, seed=3, eye=None, time_max=0.0, frame=None):
+    """pinhole-ish primary rays looking at the scene (kernel-only ray set 1).
+    frame=(w,h): one jittered ray per pixel in 8x4-pixel tile order (n must be w*h) -- the order a wavefront
+    camera kernel emits them in; otherwise uniformly random film positions (the reference's per-path pixel
+    sampling, thinlens.c:117-118)"""
     rng = np.random.default_rng(seed)
     lo, hi = scene.bounds()
     ctr = (lo + hi) / 2
@@ -341,7 +344,18 @@ def camera_rays(n, scene, seed=3, eye=None, time_max=0.0):
     right = np.cross(fwd, [0, 0, 1.0])
     right /= np.linalg.norm(right)
     up = np.cross(right, fwd)
-    uv = rng.random((n, 2)).astype(np.float32) - 0.5
+    if frame is not None:
+        w, h = frame
+        assert n == w * h and w % 8 == 0 and h % 4 == 0
+        i = np.arange(n, dtype=np.int64)
+        tile, inner = i // 32, i % 32
+        tx, ty = tile % (w // 8), tile // (w // 8)
+        px = (tx * 8 + inner % 8).astype(np.float32)
+        py = (ty * 4 + inner // 8).astype(np.float32)
+        jit = rng.random((n, 2)).astype(np.float32)
+        uv = np.stack([(px + jit[:, 0]) / np.float32(w), (py + jit[:, 1]) / np.float32(h)], -1).astype(np.float32) - 0.5
+    else:
+        uv = rng.random((n, 2)).astype(np.float32) - 0.5
     d = fwd[None, :] + 0.9 * uv[:, :1] * right[None, :] + 0.6 * uv[:, 1:] * up[None, :]
     d = (d / np.linalg.norm(d, axis=1)[:, None]).astype(np.float32)
     t = (rng.random(n) * time_max).astype(np.float32)

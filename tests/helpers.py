@@ -78,21 +78,63 @@ def reachable_nodes(nodes):
     return np.array(sorted(seen))
 
 
+def _slab_margin(orc, prim, ray, limit):
+    """width of the ray's slab interval against the primitive's own (time-interpolated) bounding box, relative
+    to the distance scale -- a flat or grazed box has a margin of a few ulps and may be culled by rounding"""
+    t = np.float32(ray["time"])
+    b0, b1 = orc.prim_bounds(prim, False), orc.prim_bounds(prim, True)
+    box = (b0 * (np.float32(1) - t) + b1 * t).astype(np.float32)
+    with np.errstate(all="ignore"):
+        inv = np.float32(1) / ray["dir"].astype(np.float32)
+        lo = (box[:3] - ray["pos"]) * inv
+        hi = (box[3:] - ray["pos"]) * inv
+        tmin = max(np.float32(0), np.nanmax(np.minimum(lo, hi)))
+        tmax = min(np.float32(limit), np.nanmin(np.maximum(lo, hi)))
+    return float(tmax - tmin) / max(1.0, abs(float(tmax)))
+
+
 def classify_mismatches(orc, rays, got, want, max_dist=None):
-    """mode-B bookkeeping: every ray where the GPU tree's answer differs from the reference tree's must be a
-    proven tie -- the oracle's single-primitive test of the *other* primitive returns the identical distance
-    bits.  returns (num_mismatch, num_proven_ties)"""
+    """mode-B bookkeeping.  The GPU result is asserted bit-identical to the reference ALGORITHM (the oracle) run
+    on the same GPU-built tree; what is classified here are the rays where that differs from the answer the
+    reference-built tree gives.  Two legitimate causes:
+      order : "dist <= hit->dist" lets the last-tested primitive win ties, and a quad's second triangle is only
+              tested when its first one is rejected (src/prims.c:654-663; matters for non-planar / moving quads).
+              Reproduced by applying the oracle's single-primitive test to the two candidates in both orders.
+      cull  : the slab test and the primitive test are different roundings of the same distance; a box that the
+              ray grazes or that is flat (axis-aligned quads) can be culled by one ulp when hit->dist is preset
+              to the hit distance itself.  Which boxes enclose a primitive depends on the tree.  Accepted when the
+              nearer answer's primitive, tested alone, reproduces that answer and the ray's slab interval against
+              the primitive's own box is empty to within 1e-5.
+    returns (num_mismatch, num_explained)"""
     gp, wp = R.hit_prim64(got), R.hit_prim64(want)
-    idx = np.nonzero(gp != wp)[0]
-    ties = 0
-    for i in idx:
-        if got["dist"][i].view("u4") != want["dist"][i].view("u4"):
-            continue
-        # same distance through a different primitive: test the GPU's prim alone with the oracle
+    idx = np.nonzero((gp != wp) | (got["dist"].view("u4") != want["dist"].view("u4")))[0]
+    explained = 0
+
+    def limit(i):
+        return R.FLT_MAX if max_dist is None else max_dist[i]
+
+    def run(order, i):
         h = np.zeros(1, R.HIT)
         h["prim"] = 0xFFFFFFFF
-        h["dist"] = R.FLT_MAX if max_dist is None else max_dist[i]
-        orc.prim_intersect(gp[i], rays[i:i + 1], h)
-        if h["dist"][0].view("u4") == want["dist"][i].view("u4"):
-            ties += 1
-    return len(idx), ties
+        h["dist"] = limit(i)
+        for p in order:
+            if p != R.INVALID_PRIMID:
+                orc.prim_intersect(p, rays[i:i + 1], h)
+        return R.hit_prim64(h)[0], h["dist"].view("u4")[0]
+
+    for i in idx:
+        a = run([gp[i], wp[i]], i)
+        b = run([wp[i], gp[i]], i)
+        g = (gp[i], got["dist"].view("u4")[i])
+        w = (wp[i], want["dist"].view("u4")[i])
+        if (a == g and b == w) or (a == w and b == g):
+            explained += 1
+            continue
+        # culling: one side holds a nearer (or the only) hit that the other tree's boxes rejected
+        near, far = (g, w) if got["dist"][i] < want["dist"][i] or wp[i] == R.INVALID_PRIMID else (w, g)
+        if near[0] != R.INVALID_PRIMID and run([near[0]], i) == near and _slab_margin(orc, near[0], rays[i], limit(i)) <= 1e-5:
+            explained += 1
+            continue
+        print(f"unexplained difference at ray {i}: ray={rays[i]} gpu={got[i]} ref={want[i]} "
+              f"order(gpu,ref)->{a} order(ref,gpu)->{b}")
+    return len(idx), explained
