@@ -5,4 +5,4 @@ plain-C host layer in host/ that mirrors the reference's accel.h module API.  Th
 numpy record views, procedural scenes and the ctypes binding used by tests and bench.py.
 The directory name contains a hyphen: import with importlib.import_module("corona-13_b200").
 """
-from . import records, scenes  # noqa: F401
+from . import records, scenes, scene_io  # noqa: F401

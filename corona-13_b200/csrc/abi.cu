@@ -73,8 +73,10 @@ cb200_scene_t *cb200_scene_create(const cb_shape_t *shapes, int num_shapes)
   if(num_shapes < 0 || (num_shapes > 0 && !shapes)) { g_error = "scene_create: bad arguments"; return nullptr; }
   if(cb200_device_count() < 1) { if(g_error.empty()) g_error = "no CUDA device"; return nullptr; }
   cb200_scene *s = new cb200_scene();
-  memset(s, 0, sizeof(*s));
+  s->num_shapes = 0; s->num_prims = s->num_vtx = s->num_vtxidx = 0; s->any_mb = 0;
+  s->d_vtx = nullptr; s->d_vtxidx = nullptr; s->d_shapes = nullptr; s->d_primid = nullptr;
   cudaGetDevice(&s->device);
+  for(int i=0;i<num_shapes;i++) s->h_material.push_back(shapes[i].material);
   s->num_shapes = num_shapes;
   std::vector<ShapeDev> sd(num_shapes > 0 ? num_shapes : 1);
   for(int i=0;i<num_shapes;i++)

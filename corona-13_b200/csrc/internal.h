@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <string>
+#include <vector>
 #include "corona_b200.h"
 
 // ---------------------------------------------------------------------------------------------
@@ -66,6 +67,7 @@ struct cb200_scene
   cb_vtxidx_t *d_vtxidx;
   ShapeDev    *d_shapes;
   uint64_t    *d_primid;   // global list in load order (shapeid patched in, prims.c:741-757)
+  std::vector<int64_t> h_material;   // shape -> material (prims_shader)
 };
 
 struct cb200_accel

@@ -1,0 +1,875 @@
+// render.cu -- wavefront pt / ptdl integrator (C ABI in include/corona_b200_render.h).
+//
+// One pass = path indices [first, first+count), processed in waves of `batch_paths` paths:
+//
+//   k_path_start     path_extend at length 0 (src/pathspace.c:205-250): lambda, time, thin-lens camera sample
+//                    (src/camera.d/thinlens.c:68-128) -> first ray
+//   loop per vertex:
+//     k_intersect    closest hit (traverse.cu) = accel_intersect in path_propagate (pathspace.c:763)
+//     k_shade        rest of path_propagate + path_extend bookkeeping + the sampler (pt.c:40-54 / ptdl.c:112-150):
+//                    vertex preparation, emission splat with MIS, next-event sample (nee.h:87-243) -> shadow ray,
+//                    bsdf sample (shader.c:577-590) -> next ray, stream compaction of surviving paths
+//     k_intersect    shadow rays with hit->dist preset = path_visible (pathspace.c:311-344)
+//     k_nee_resolve  visibility decision + splat
+//
+// Splat: spectrum_p_to_camera + 4x4 Blackman-Harris footprint (view.c:455-495, blackmanharris.h:43-77) with
+// float atomics into the W*H*3 accumulation buffer (the reference uses CAS loops the same way).
+// Scope: surfaces in vacuum / nested dielectrics, geometric lights, black sky.  Media and environment lighting
+// are SURVEY 8(f) rank 1/3.
+#include "shading.cuh"
+#include <vector>
+#include <string>
+#include <cstring>
+#include <cmath>
+#include <cstdlib>
+
+#define RB 128   // block size of the integrator kernels
+
+struct __align__(16) PathState   // 144 bytes, one per path in flight
+{
+  float x[3];        float time;        // vertex v position (un-offset)
+  float omega[3];    float lambda;      // e[v+1].omega as sampled
+  float thr, thr_prev, pdf_proj, cos_prev;   // throughput into v+1, throughput into v, bsdf pdf (proj. solid angle), |n_v . omega|
+  float pixel_i, pixel_j, scramble, cur_ior;
+  uint32_t prim_lo, prim_hi;            // primitive of vertex v (ignore / self-intersection test)
+  uint32_t index_lo, index_hi;          // path index
+  int32_t length;                       // path->length (number of finished vertices)
+  int32_t rand_beg;                     // rand_beg of the vertex the current ray is about to create
+  uint32_t bits;                        // bit0: nee_possible(v) (material_modes & (diffuse|glossy)); bits 8..: mt draw counter
+  int32_t med_n;
+  uint32_t med_shape[MED_MAX];
+  float med_ior[MED_MAX];
+};
+static_assert(sizeof(PathState) % 16 == 0, "PathState size");
+
+struct NeeRec   // pending next-event contribution, resolved after the shadow wave
+{
+  float value;       // throughput * mis weight (spectral, one wavelength)
+  float lambda;
+  float pixel_i, pixel_j;
+  float total_dist;
+  uint32_t light_lo, light_hi;
+  uint32_t pad;
+};
+
+struct CameraDev
+{
+  cb_camera_t c;
+  float width, height;
+  float fstop, exposure_time;
+};
+
+struct RenderDev
+{
+  DevAccel accel;
+  SceneGeo geo;
+  MaterialsDev mats;
+  LightsDev lights;
+  PointsDev points;
+  CameraDev cam;
+  float *fb;
+  uint32_t fb_w, fb_h;
+  int32_t sampler, colour, max_path_len;
+};
+
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void atomic_add_f(float *p, float v) { atomicAdd(p, v); }
+
+__device__ __forceinline__ float bh_w(float n)   // filter_bh_w, blackmanharris.h:28-41
+{
+  if(n > 3.0f || n < 0.0f) return 0.0f;
+  const float N_1 = 1.0f/3.0f;
+  const float cos1 = cosf(2.0f*PI_F*n*N_1), cos2 = cosf(4.0f*PI_F*n*N_1), cos3 = cosf(6.0f*PI_F*n*N_1);
+  return 0.35875f - 0.48829f*cos1 + 0.14128f*cos2 - 0.01168f*cos3;
+}
+
+// view_splat (view.c:455-495)
+__device__ bool splat(const RenderDev &R, float pixel_i, float pixel_j, float lambda, float value)
+{
+  if(!(value > 0.0f)) return false;
+  if(!(value < FLT_MAX)) return false;
+  float col[3];
+  spectrum_to_camera(lambda, value, R.colour, col);
+  const int wd = (int)R.fb_w, ht = (int)R.fb_h;
+  const int x0 = (int)(pixel_i - 1.5f), y0 = (int)(pixel_j - 1.5f);
+  const int u0 = -x0 < 0 ? 0 : -x0, v0 = -y0 < 0 ? 0 : -y0;
+  const int u4 = x0 + 4 > wd ? wd - x0 : 4, v4 = y0 + 4 > ht ? ht - y0 : 4;
+  float w[16];
+  float weight = 0.0f;
+  for(int v=v0;v<v4;v++) for(int u=u0;u<u4;u++)
+  {
+    const float uu = (x0 + u + .5f) - pixel_i, vv = (y0 + v + .5f) - pixel_j;
+    const float f = bh_w(sqrtf(uu*uu + vv*vv) + 1.5f);
+    w[4*v+u] = f;
+    weight += f;
+  }
+  if(weight <= 0.0f) return false;
+  weight = 1.0f/weight;
+  for(int v=v0;v<v4;v++) for(int u=u0;u<u4;u++)
+  {
+    const float f = weight*w[4*v+u];
+    float *p = R.fb + 3*((size_t)(x0+u) + (size_t)wd*(y0+v));
+    atomic_add_f(p+0, col[0]*f); atomic_add_f(p+1, col[1]*f); atomic_add_f(p+2, col[2]*f);
+  }
+  return true;
+}
+
+__device__ __forceinline__ void quat_mult(float *in, const float *p)   // quaternion.h:40-47 (w,x,y,z)
+{
+  const float rw = in[0], r0 = in[1], r1 = in[2], r2 = in[3];
+  in[1] = rw*p[1] + r0*p[0] + r1*p[3] - r2*p[2];
+  in[2] = rw*p[2] - r0*p[3] + r1*p[0] + r2*p[1];
+  in[3] = rw*p[3] + r0*p[2] - r1*p[1] + r2*p[0];
+  in[0] = rw*p[0] - r0*p[1] - r1*p[2] - r2*p[3];
+}
+__device__ __forceinline__ V3 quat_transform(const float *q, V3 p)
+{
+  float vq[4] = {0.0f, p.x, p.y, p.z};
+  float inv[4] = {q[0], -q[1], -q[2], -q[3]};
+  float res[4] = {q[0], q[1], q[2], q[3]};
+  quat_mult(res, vq);
+  quat_mult(res, inv);
+  return mk3(res[1], res[2], res[3]);
+}
+__device__ void quat_slerp(const float *q, const float *p, float t, float *res)   // quaternion.h:78-103
+{
+  const float c = q[0]*p[0] + (q[1]*p[1] + q[2]*p[2] + q[3]*p[3]);
+  if(fabsf(c) >= 1.0f) { for(int k=0;k<4;k++) res[k] = q[k]; return; }
+  const float theta = acosf(c);
+  const float s = sqrtf(1.0f - c*c);
+  if(fabsf(s) < 1e-10f) { for(int k=0;k<4;k++) res[k] = (q[k] + p[k])*.5f; return; }
+  const float a = sinf((1.0f - t)*theta)/s, b = sinf(t*theta)/s;
+  for(int k=0;k<4;k++) res[k] = q[k]*a + p[k]*b;
+}
+
+// view_cam_init_frame (view.c:903-921)
+__device__ void camera_frame(const CameraDev &C, float time, V3 &x, V3 &a, V3 &b, V3 &n)
+{
+  float q[4];
+  quat_slerp(C.c.orient, C.c.orient_t1, time, q);
+  a = normalise(quat_transform(q, mk3(1.0f, 0.0f, 0.0f)));
+  b = normalise(quat_transform(q, mk3(0.0f, 1.0f, 0.0f)));
+  n = normalise(quat_transform(q, mk3(0.0f, 0.0f, 1.0f)));
+  x = mk3(C.c.pos[0]*(1.0f-time) + C.c.pos_t1[0]*time, C.c.pos[1]*(1.0f-time) + C.c.pos_t1[1]*time, C.c.pos[2]*(1.0f-time) + C.c.pos_t1[2]*time);
+}
+
+__device__ __forceinline__ void write_ray(cb_ray_t *rays, uint64_t i, V3 pos, V3 dir, float time, uint32_t ign_lo, uint32_t ign_hi)
+{
+  float2 *p = reinterpret_cast<float2 *>(rays + i);
+  p[0] = make_float2(pos.x, pos.y); p[1] = make_float2(pos.z, dir.x); p[2] = make_float2(dir.y, dir.z);
+  p[3] = make_float2(time, 0.0f);
+  p[4] = make_float2(__uint_as_float(ign_lo), __uint_as_float(ign_hi));
+}
+
+// path_extend at length == 0: sensor vertex + first edge
+__device__ void path_start(const RenderDev &R, uint64_t index, PathState &s, V3 &ray_pos)
+{
+  const PointsDev &P = R.points;
+  const CameraDev &C = R.cam;
+  s.index_lo = (uint32_t)index; s.index_hi = (uint32_t)(index >> 32);
+  uint32_t mt = 0;
+  s.scramble = 0.1f + point_mt(P, index, mt++)*(0.9f - 0.1f);
+  s.lambda = 360.0f + (830.0f - 360.0f)*fmodf(point_dim(P, index, 2) + 0.0f, 1.0f);   // spectrum_sample_lambda
+  const float exposure_time = C.exposure_time;
+  s.time = point_dim(P, index, 3)*fminf(1.0f, exposure_time/(1.0f/30.0f));             // view_sample_time
+  (void)point_dim(P, index, 6);                                                          // camid: one camera
+  const float i = point_dim(P, index, 0)*C.width, j = point_dim(P, index, 1)*C.height;
+  const float r1 = point_dim(P, index, 4), r2 = point_dim(P, index, 5);
+  const float lens_radius = (.5f/C.fstop)*C.c.focal_length;
+  const float ang = (float)(2.0*PI_D*(double)r1);
+  const float u = cosf(ang)*sqrtf(r2)*lens_radius, v = sinf(ang)*sqrtf(r2)*lens_radius;
+  V3 x, a, b, n;
+  camera_frame(C, s.time, x, a, b, n);
+  const float f = C.c.focus/C.c.focal_length;
+  const float f_dir = C.c.focus;
+  const float f_rg = -C.c.film_width*f/C.width, f_up = -C.c.film_height*f/C.height;
+  const V3 aoff = mk3(u*a.x + v*b.x, u*a.y + v*b.y, u*a.z + v*b.z);
+  const float ci = (i - .5f*C.width)*f_rg, cj = (j - .5f*C.height)*f_up;
+  V3 om = mk3(f_dir*n.x + (ci*a.x + cj*b.x) - aoff.x, f_dir*n.y + (ci*a.y + cj*b.y) - aoff.y, f_dir*n.z + (ci*a.z + cj*b.z) - aoff.z);
+  om = normalise(om);
+  const float fs = C.fstop;
+  const float A = PI_F*C.c.focal_length*C.c.focal_length/(4.0f*fs*fs);
+  const float pdf_a = (float)(1.0/(double)A);
+  const float sensor = 106.86535f*100.0f*exposure_time;
+  const float dt = dot(om, n);
+  const float dot4 = dt*dt*dt*dt;
+  s.pixel_i = fminf(fmaxf(i, 0.0f), C.width - 1e-4f);
+  s.pixel_j = fminf(fmaxf(j, 0.0f), C.height - 1e-4f);
+  const float G = dot4/(C.c.focal_length*C.c.focal_length);
+  const float pdf_v = 1.0f/(C.c.film_width*C.c.film_height);
+  s.pdf_proj = pdf_v*pdf_a/G;
+  const float thr = sensor*G/(pdf_a*pdf_v);
+  s.x[0] = x.x + aoff.x; s.x[1] = x.y + aoff.y; s.x[2] = x.z + aoff.z;
+  s.omega[0] = om.x; s.omega[1] = om.y; s.omega[2] = om.z;
+  s.thr = thr; s.thr_prev = thr;
+  s.cos_prev = fabsf(dot(n, om));     // path_lambert at the sensor vertex
+  s.cur_ior = 1.0f;
+  s.prim_lo = s.prim_hi = 0xffffffffu;
+  s.length = 1;
+  s.rand_beg = 7;                     // v[0] used 7 dims; v[1] uses one (free path) (thinlens.c:101-104)
+  s.bits = (mt << 8);
+  s.med_n = 0;
+  for(int k=0;k<MED_MAX;k++) { s.med_shape[k] = 0; s.med_ior[k] = 1.0f; }
+  ray_pos = mk3(s.x[0], s.x[1], s.x[2]);   // sensor vertex has no primitive: no offset (pathspace.c:759-761)
+}
+
+__global__ void __launch_bounds__(RB)
+k_path_start(RenderDev R, uint64_t first_index, uint32_t n, PathState *st, cb_ray_t *rays, float *aux)
+{
+  const uint32_t i = blockIdx.x*blockDim.x + threadIdx.x;
+  if(i >= n) return;
+  PathState s;
+  V3 pos;
+  path_start(R, first_index + i, s, pos);
+  write_ray(rays, i, pos, mk3(s.omega[0], s.omega[1], s.omega[2]), s.time, 0xffffffffu, 0xffffffffu);
+  if(st) st[i] = s;
+  if(aux) { aux[4*i+0] = s.pixel_i; aux[4*i+1] = s.pixel_j; aux[4*i+2] = s.lambda; aux[4*i+3] = s.thr; }
+}
+
+__device__ __forceinline__ uint32_t sample_cdf_dev(const float *cdf, uint32_t num, float rand)   // sampler_common.h:206-226
+{
+  uint32_t mn = 0, mx = num, t = mx/2;
+  while(t != mn)
+  {
+    if(cdf[t] <= rand) mn = t; else mx = t;
+    t = (mn + mx)/2;
+  }
+  if(mx < num && cdf[t] <= rand) t = mx;
+  return t;
+}
+
+// prims_sample + prims_retime (prims.c:177-252) for triangles and quads
+__device__ void light_point(const SceneGeo &S, uint64_t pid, float r0, float r1, float time, Vtx &h)
+{
+  const uint32_t vcnt = (uint32_t)(pid >> 61) & 7u;
+  h.prim_lo = (uint32_t)pid; h.prim_hi = (uint32_t)(pid >> 32);
+  if(vcnt == CB_PRIM_QUAD)
+  {
+    h.u = r0; h.v = r1;
+    const V3 v0 = geo_vertex_time(S, pid, 0, time), v2 = geo_vertex_time(S, pid, 2, time);
+    V3 p1, p2; float u, v;
+    if(h.v >= h.u) { p1 = geo_vertex_time(S, pid, 1, time); p2 = v2; u = h.u; v = h.v - h.u; }
+    else           { p1 = v2; p2 = geo_vertex_time(S, pid, 3, time); u = h.u - h.v; v = h.v; }
+    const float w = 1.0f - u - v;
+    h.x = mk3(w*v0.x + v*p1.x + u*p2.x, w*v0.y + v*p1.y + u*p2.y, w*v0.z + v*p1.z + u*p2.z);
+  }
+  else
+  {
+    float a = sqrtf(r0);
+    const float b = (1.0f - r1)*a, c = r1*a;
+    a = 1.0f - a;
+    h.u = c; h.v = b;
+    const V3 v0 = geo_vertex_time(S, pid, 0, time), v1 = geo_vertex_time(S, pid, 1, time), v2 = geo_vertex_time(S, pid, 2, time);
+    const float w = 1.0f - h.u - h.v;
+    h.x = mk3(w*v0.x + h.v*v1.x + h.u*v2.x, w*v0.y + h.v*v1.y + h.u*v2.y, w*v0.z + h.v*v1.z + h.u*v2.z);
+  }
+}
+
+__device__ __forceinline__ float max3abs(V3 x) { return fmaxf(fmaxf(.5f, fabsf(x.x)), fmaxf(fabsf(x.y), fabsf(x.z))); }
+
+struct ShadeCounters { unsigned long long next, nee, splats; };
+
+// path_G for the edge between a surface vertex and the sampled light point (pathspace.c:58-69)
+__device__ __forceinline__ float cos_lambert(const Vtx &v, const Vtx &l, V3 d, float dist)
+{
+  return fabsf(dot(v.n, d))*fabsf(dot(l.n, d))/(dist*dist);
+}
+
+// one vertex of every live path
+__global__ void __launch_bounds__(RB)
+k_shade(RenderDev R, uint32_t n, const PathState *__restrict__ st_in, const cb_ray_t *__restrict__ rays_in,
+        const cb_hitrec_t *__restrict__ hits, PathState *__restrict__ st_out, cb_ray_t *__restrict__ rays_out,
+        cb_ray_t *__restrict__ nee_rays, float *__restrict__ nee_maxdist, NeeRec *__restrict__ nee_recs, ShadeCounters *cnt)
+{
+  const uint32_t i = blockIdx.x*blockDim.x + threadIdx.x;
+  bool alive = false, have_nee = false, did_splat = false;
+  PathState s;
+  V3 next_pos = mk3(0, 0, 0), next_dir = mk3(0, 0, 0);
+  cb_ray_t nray; NeeRec nrec; float nmax = 0.0f;
+  if(i < n)
+  {
+    s = st_in[i];
+    const cb_hitrec_t h = hits[i];
+    const uint64_t index = (uint64_t)s.index_lo | ((uint64_t)s.index_hi << 32);
+    const V3 omega = mk3(s.omega[0], s.omega[1], s.omega[2]);
+    const bool hit_geo = !((h.prim[0] & h.prim[1]) == 0xffffffffu);
+    // black sky: an environment vertex carries no emission and ends the path (pathspace.c:856-873, shader.c:464-470)
+    if(hit_geo)
+    {
+      const cb_ray_t ray = rays_in[i];
+      Vtx v;
+      v.prim_lo = h.prim[0]; v.prim_hi = h.prim[1];
+      v.u = h.u; v.v = h.v; v.s = v.t = 0.0f;
+      v.flags = 0; v.mode = M_ABSORB; v.material_modes = 0;
+      v.x = mk3(ray.pos[0] + h.dist*ray.dir[0], ray.pos[1] + h.dist*ray.dir[1], ray.pos[2] + h.dist*ray.dir[2]);
+      Media med; med.n = s.med_n;
+      for(int k=0;k<MED_MAX;k++) { med.shape[k] = s.med_shape[k]; med.ior[k] = s.med_ior[k]; }
+      prepare_vertex(R.geo, R.mats, v, omega, s.time, s.lambda, s.scramble, med, s.cur_ior);
+      // self intersection (pathspace.c:809-820)
+      const uint32_t vcnt = v.prim_hi >> 29;
+      const bool self = (vcnt > 2 || h.dist < 1e-4f) && v.prim_lo == s.prim_lo && v.prim_hi == s.prim_hi;
+      if(!self)
+      {
+        if(v.em > 0.0f && !(v.flags & F_INSIDE)) v.material_modes = v.mode = M_EMIT;
+        // on-surface pdf of this vertex (pathspace.c:252-253, 45-69)
+        const float cos_v = fabsf(dot(v.n, omega));
+        const float G = s.cos_prev*cos_v/(h.dist*h.dist);
+        const float pdf_v = s.pdf_proj*G;
+        const int vi = s.length;        // index of this vertex
+        s.length++;
+        const int rand_beg_v = s.rand_beg;
+        float thr = s.thr;
+        bool stop = false;
+        // ---- emission: path_update_throughput + sampler splat
+        if(v.mode & M_EMIT)
+        {
+          const float L = thr*light_eval(v, omega);
+          float w = 1.0f;
+          if(R.sampler == CB_SAMPLER_PTDL)
+          {
+            float pdf_nee = 0.0f;
+            if(s.length >= 3 && (s.bits & 1u) && R.lights.p_geo > 0.0f)
+              pdf_nee = R.lights.p_geo*R.lights.shape_pdf[v.prim_lo >> 3];
+            w = pdf_v/(pdf_nee + pdf_v);        // sampler_mis, ptdl.c:78-88 with one wavelength
+          }
+          did_splat = splat(R, s.pixel_i, s.pixel_j, s.lambda, L*w);
+          if(R.sampler == CB_SAMPLER_PT && s.length > 3)
+          { // path_russian_roulette (pathspace.c:273-292)
+            const float p_survival = fminf(1.0f, thr/s.thr_prev);
+            const float rr = point_dim(R.points, index, rand_beg_v + 4);
+            if(rr >= p_survival) stop = true;
+            else thr *= 1.0f/p_survival;
+          }
+        }
+        if(R.sampler == CB_SAMPLER_PTDL && s.length >= R.max_path_len) stop = true;
+        uint32_t mt = s.bits >> 8;
+        int rand_cnt_v = 5;
+        if(vi == 1) rand_cnt_v = 1;
+        // ---- next event estimation (ptdl.c:136-148, nee.h:87-243)
+        if(!stop && R.sampler == CB_SAMPLER_PTDL)
+        {
+          (void)point_mt(R.points, index, mt++);   // the rr draw against nee_probability() == 1
+          if(s.length >= 32) stop = true;          // nee_sample refuses at PATHSPACE_MAX_VERTS and the sampler returns
+          else
+          {
+            const int rb = rand_beg_v + rand_cnt_v; // rand_beg of the nee vertex (nee.h:107)
+            if((v.material_modes & (M_DIFFUSE | M_GLOSSY)) && R.lights.num > 0)
+            {
+              const float r0 = point_dim(R.points, index, rb + 0);
+              if(r0 < R.lights.p_geo)
+              {
+                const float rl = point_dim(R.points, index, rb + 1), rx = point_dim(R.points, index, rb + 2), ry = point_dim(R.points, index, rb + 3);
+                const uint32_t t = sample_cdf_dev(R.lights.cdf, R.lights.num, rl);
+                const uint64_t lpid = R.lights.primid[t];
+                Vtx l;
+                l.flags = 0; l.mode = 0; l.material_modes = 0; l.s = l.t = 0.0f;
+                light_point(R.geo, lpid, rx, ry, s.time, l);
+                V3 d = sub(l.x, v.x);
+                const float dist = sqrtf(dot(d, d));
+                const float il = (float)(1.0/(double)dist);
+                d = mk3(d.x*il, d.y*il, d.z*il);
+                prepare_vertex(R.geo, R.mats, l, d, s.time, s.lambda, s.scramble, med, s.cur_ior);
+                const float pdf_l = R.lights.L[t];
+                float edf = l.em/pdf_l;
+                if(l.roughness > 1.0f - 1e-4f) edf *= (float)(1.0/PI_D);
+                else
+                {
+                  const float phongexp = 2.0f/(l.roughness*l.roughness) - 2.0f;
+                  edf *= (float)((double)(powf(-dot(l.gn, d), phongexp)*(phongexp + 2.0f))/(2.0*PI_D));
+                }
+                edf = edf/R.lights.p_geo;
+                if(edf > 0.0f)
+                {
+                  Vtx vb = v;   // shader_brdf sets the mode on v; path_pop resets it afterwards
+                  const float bsdf = bsdf_eval(R.mats, vb, omega, d, s.lambda, s.cur_ior);
+                  if(bsdf > 0.0f)
+                  {
+                    // path_visible: prims_get_ray (prims.c:390-492)
+                    const float eps = 1e-4f*max3abs(v.x);
+                    V3 rd = sub(l.x, v.x);
+                    const float ilen = 1.0f/sqrtf(dot(rd, rd));
+                    rd = mk3(rd.x*ilen, rd.y*ilen, rd.z*ilen);
+                    const V3 rp = mk3(v.x.x + eps*rd.x, v.x.y + eps*rd.y, v.x.z + eps*rd.z);
+                    const V3 dv = mk3(l.x.x - eps*rd.x - rp.x, l.x.y - eps*rd.y - rp.y, l.x.z - eps*rd.z - rp.z);
+                    const float total_dist = sqrtf(dot(dv, dv));
+                    if(!(dot(l.gn, rd) >= 0.0f) && total_dist > 0.0f)
+                    {
+                      const float Gl = cos_lambert(vb, l, d, dist);
+                      const float thr_l = ((thr*bsdf)*(1.0f*edf))*Gl;
+                      // mis against extending the path into the light (ptdl.c:142-146)
+                      const float pdf_nee = R.lights.p_geo*pdf_l;
+                      const float pdf_ext = bsdf_pdf(R.mats, vb, omega, d)*Gl;
+                      const float w = pdf_nee/(pdf_ext + pdf_nee);
+                      if(thr_l > 0.0f)
+                      {
+                        have_nee = true;
+                        for(int k=0;k<3;k++) { nray.pos[k] = (&rp.x)[k]; nray.dir[k] = (&rd.x)[k]; }
+                        nray.time = s.time; nray.min_dist = 0.0f;
+                        nray.ignore[0] = v.prim_lo; nray.ignore[1] = v.prim_hi;
+                        nmax = total_dist;
+                        nrec.value = thr_l*w; nrec.lambda = s.lambda; nrec.pixel_i = s.pixel_i; nrec.pixel_j = s.pixel_j;
+                        nrec.total_dist = total_dist; nrec.light_lo = l.prim_lo; nrec.light_hi = l.prim_hi; nrec.pad = 0;
+                      }
+                    }
+                  }
+                }
+              }
+            }
+            rand_cnt_v += 4;   // path_pop folds the nee vertex' dimensions into v (pathspace.c:298)
+          }
+        }
+        // ---- extend: sample the bsdf at v (pathspace.c:186-203, shader.c:577-590)
+        if(!stop && thr > 0.0f && s.length < 32)
+        {
+          const int rb = rand_beg_v + rand_cnt_v;   // rand_beg of vertex vi+1 (pathspace.c:199)
+          const float rx = point_dim(R.points, index, rb + 1), ry = point_dim(R.points, index, rb + 2), rm = point_dim(R.points, index, rb + 3);
+          V3 wo; float pdf = 1.0f;
+          v.mode &= M_EMIT;
+          const uint32_t keep_emit = v.mode;
+          float weight = bsdf_sample(R.mats, v, omega, s.lambda, s.cur_ior, rx, ry, rm, wo, pdf);
+          wo = normalise(wo);
+          const float dt = ((v.flags & F_INSIDE) ? -1.0f : 1.0f)*dot(v.gn, wo);
+          if(((v.mode & M_REFLECT) && dt < 0.0f) || ((v.mode & M_TRANSMIT) && dt > 0.0f)) weight = 0.0f;
+          (void)keep_emit;
+          const float thr_next = thr*weight;
+          bool ok = thr_next > 0.0f;
+          if(ok && (v.mode & M_TRANSMIT))
+          { // path_edge_init_volume for the next edge
+            ok = media_transmit(med, v.prim_lo >> 3, v.ior, v.flags & F_INSIDE);
+            s.cur_ior = media_ior(med);
+          }
+          if(ok)
+          {
+            alive = true;
+            s.thr_prev = thr; s.thr = thr_next; s.pdf_proj = pdf;
+            s.cos_prev = fabsf(dot(v.n, wo));
+            s.x[0] = v.x.x; s.x[1] = v.x.y; s.x[2] = v.x.z;
+            s.omega[0] = wo.x; s.omega[1] = wo.y; s.omega[2] = wo.z;
+            s.prim_lo = v.prim_lo; s.prim_hi = v.prim_hi;
+            s.rand_beg = rb;
+            s.bits = (mt << 8) | ((v.material_modes & (M_DIFFUSE | M_GLOSSY)) ? 1u : 0u);
+            s.med_n = med.n;
+            for(int k=0;k<MED_MAX;k++) { s.med_shape[k] = med.shape[k]; s.med_ior[k] = med.ior[k]; }
+            const float eps = max3abs(v.x)*1e-4f;   // prims_offset_ray (prims.c:374-388)
+            next_pos = mk3(v.x.x + eps*wo.x, v.x.y + eps*wo.y, v.x.z + eps*wo.z);
+            next_dir = wo;
+          }
+        }
+      }
+    }
+  }
+  // warp-aggregated compaction of surviving paths and of pending next events
+  const uint32_t lane = threadIdx.x & 31u;
+  const uint32_t ma = __ballot_sync(0xffffffffu, alive);
+  if(ma)
+  {
+    unsigned long long base = 0;
+    if(lane == (uint32_t)(__ffs(ma) - 1)) base = atomicAdd(&cnt->next, (unsigned long long)__popc(ma));
+    base = __shfl_sync(0xffffffffu, base, __ffs(ma) - 1);
+    if(alive)
+    {
+      const uint64_t o = base + __popc(ma & ((1u << lane) - 1u));
+      st_out[o] = s;
+      write_ray(rays_out, o, next_pos, next_dir, s.time, s.prim_lo, s.prim_hi);
+    }
+  }
+  const uint32_t msp = __ballot_sync(0xffffffffu, did_splat);
+  if(msp && lane == 0) atomicAdd(&cnt->splats, (unsigned long long)__popc(msp));
+  const uint32_t mn = __ballot_sync(0xffffffffu, have_nee);
+  if(mn)
+  {
+    unsigned long long base = 0;
+    if(lane == (uint32_t)(__ffs(mn) - 1)) base = atomicAdd(&cnt->nee, (unsigned long long)__popc(mn));
+    base = __shfl_sync(0xffffffffu, base, __ffs(mn) - 1);
+    if(have_nee)
+    {
+      const uint64_t o = base + __popc(mn & ((1u << lane) - 1u));
+      nee_rays[o] = nray; nee_maxdist[o] = nmax; nee_recs[o] = nrec;
+    }
+  }
+}
+
+// path_visible's decision (pathspace.c:325-331) + the splat of ptdl.c:146
+__global__ void __launch_bounds__(RB)
+k_nee_resolve(RenderDev R, uint32_t n, const NeeRec *__restrict__ recs, const cb_hitrec_t *__restrict__ hits, ShadeCounters *cnt)
+{
+  const uint32_t i = blockIdx.x*blockDim.x + threadIdx.x;
+  bool did = false;
+  if(i < n)
+  {
+    const NeeRec r = recs[i];
+    const cb_hitrec_t h = hits[i];
+    const bool none = (h.prim[0] & h.prim[1]) == 0xffffffffu;
+    const bool visible = none || h.dist >= r.total_dist || (h.prim[0] == r.light_lo && h.prim[1] == r.light_hi);
+    if(visible) did = splat(R, r.pixel_i, r.pixel_j, r.lambda, r.value);
+  }
+  const uint32_t m = __ballot_sync(0xffffffffu, did);
+  if(m && (threadIdx.x & 31u) == 0) atomicAdd(&cnt->splats, (unsigned long long)__popc(m));
+}
+
+__global__ void k_points(PointsDev P, const uint64_t *index, const int32_t *dim, float *out, uint32_t n)
+{
+  const uint32_t i = blockIdx.x*blockDim.x + threadIdx.x;
+  if(i < n) out[i] = point_dim(P, index[i], dim[i]);
+}
+
+// emissive primitive areas at shutter open (prims_get_area, prims.c:133-153; triangle.h:36-49)
+__global__ void k_prim_area(SceneGeo S, const uint64_t *pid, uint32_t n, float *area)
+{
+  const uint32_t i = blockIdx.x*blockDim.x + threadIdx.x;
+  if(i >= n) return;
+  const uint64_t p = pid[i];
+  const uint32_t vcnt = (uint32_t)(p >> 61) & 7u;
+  float a = 0.0f;
+  if(vcnt == CB_PRIM_TRI || vcnt == CB_PRIM_QUAD)
+  {
+    const cb_vtx_t *q0 = geo_vtx(S, p, 0, 0), *q1 = geo_vtx(S, p, 1, 0), *q2 = geo_vtx(S, p, 2, 0);
+    const V3 v0 = mk3(q0->v[0], q0->v[1], q0->v[2]), v1 = mk3(q1->v[0], q1->v[1], q1->v[2]), v2 = mk3(q2->v[0], q2->v[1], q2->v[2]);
+    V3 nn = cross(sub(v1, v0), sub(v2, v0));
+    a = sqrtf(dot(nn, nn))*.5f;
+    if(vcnt == CB_PRIM_QUAD)
+    {
+      const cb_vtx_t *q3 = geo_vtx(S, p, 3, 0);
+      const V3 v3 = mk3(q3->v[0], q3->v[1], q3->v[2]);
+      nn = cross(sub(v2, v0), sub(v3, v0));
+      a = a + sqrtf(dot(nn, nn))*.5f;
+    }
+  }
+  else if(vcnt == CB_PRIM_SPHERE)
+  {
+    const float r = __uint_as_float(geo_vtx(S, p, 0, 0)->n);
+    a = (float)(4.0*PI_D*(double)r)*r;
+  }
+  area[i] = a;
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------
+static const float k_fstop[] = { 0.5f, 0.7f, 1.0f, 1.4f, 2, 2.8f, 4, 5.6f, 8, 11, 16, 22, 32, 45, 64, 90, 128 };   // view.c:71-73
+static const float k_exposure[] = { 60.0f, 30.0f, 15.0f, 8.0f, 4.0f, 2.0f, 1.0f, 0.5f, 1.0f/4.0f, 1.0f/8.0f, 1.0f/15.0f, 1.0f/30.0f,
+  1.0f/60.0f, 1.0f/125.0f, 1.0f/250.0f, 1.0f/500.0f, 1.0f/1000.0f, 1.0f/2000.0f, 1.0f/4000.0f, 1.0f/8000.0f };     // view.c:75-79
+
+struct cb200_render
+{
+  cb200_accel *accel;
+  RenderDev dev;
+  cb_render_desc_t desc;
+  uint64_t batch;
+  // owned device memory
+  std::vector<void *> owned;
+  PathState *st[2];
+  cb_ray_t *rays[2];
+  cb_hitrec_t *hits;
+  cb_ray_t *nee_rays; float *nee_md; NeeRec *nee_recs; cb_hitrec_t *nee_hits;
+  ShadeCounters *d_cnt, *h_cnt;
+  cb_render_stats_t stats;
+};
+
+template<typename T> static T *dev_upload(cb200_render *r, const T *src, size_t count)
+{
+  T *p = nullptr;
+  if(cudaMalloc(&p, (count ? count : 1)*sizeof(T)) != cudaSuccess) return nullptr;
+  r->owned.push_back(p);
+  if(count && src && cudaMemcpy(p, src, count*sizeof(T), cudaMemcpyHostToDevice) != cudaSuccess) return nullptr;
+  return p;
+}
+template<typename T> static T *dev_alloc(cb200_render *r, size_t count)
+{
+  T *p = nullptr;
+  if(cudaMalloc(&p, (count ? count : 1)*sizeof(T)) != cudaSuccess) return nullptr;
+  r->owned.push_back(p);
+  return p;
+}
+
+// Halton digit permutations exactly as halton_init_random builds them (ext/halton/halton.h:3244-3274): Fisher-Yates per base
+// driven by lrand48() after srand48(frame); bases 1..3 keep the identity.  Only the 256 primes' rows are uploaded.
+static int build_halton(cb200_render *r, uint64_t frame)
+{
+  const unsigned max_base = 1619u;
+  std::vector<std::vector<uint16_t>> perms(max_base + 1);
+  srand48((long)frame);
+  for(unsigned base=1; base<=max_base; ++base)
+  {
+    perms[base].resize(base);
+    for(unsigned i=0;i<base;i++) perms[base][i] = (uint16_t)i;
+    if(base < 4) continue;
+    for(unsigned i=0;i<base-1;i++)
+    {
+      const size_t j = i + lrand48() / ((1ul<<31) / (base - i) + 1);
+      std::swap(perms[base][j], perms[base][i]);
+    }
+  }
+  std::vector<uint16_t> flat, bases(HALTON_DIMS);
+  std::vector<uint32_t> off(HALTON_DIMS);
+  std::vector<uint8_t> digits(HALTON_DIMS);
+  std::vector<float> scale(HALTON_DIMS);
+  unsigned cand = 1;
+  for(int d=0; d<HALTON_DIMS; d++)
+  {
+    for(;;) { cand++; bool prime = true; for(unsigned k=2;k<cand;k++) if(cand % k == 0) { prime = false; break; } if(prime) break; }
+    bases[d] = (uint16_t)cand;
+    off[d] = (uint32_t)flat.size();
+    flat.insert(flat.end(), perms[cand].begin(), perms[cand].end());
+    // digits per table lookup: largest power of the base <= 500; lookups: largest power of that < 2^32 (halton_gen.py)
+    unsigned dg = 1; uint64_t pow_base = cand;
+    while(pow_base*cand <= 500) { pow_base *= cand; dg++; }
+    uint64_t max_power = pow_base; unsigned lookups = 1;
+    while(max_power*pow_base < (1ull << 32)) { max_power *= pow_base; lookups++; }
+    digits[d] = (uint8_t)(dg*lookups);
+    scale[d] = (float)(0x1.fffffcp-1 / (double)max_power);
+  }
+  HaltonDev &H = r->dev.points.halton;
+  H.perm = dev_upload(r, flat.data(), flat.size());
+  H.perm_off = dev_upload(r, off.data(), off.size());
+  H.base = dev_upload(r, bases.data(), bases.size());
+  H.digits = dev_upload(r, digits.data(), digits.size());
+  H.scale = dev_upload(r, scale.data(), scale.size());
+  return (H.perm && H.perm_off && H.base && H.digits && H.scale) ? 0 : CB200_ERR_NOMEM;
+}
+
+static float host_rgb2spec(const float *c, float lambda)
+{
+  const float x = fmaf(fmaf(c[0], lambda, c[1]), lambda, c[2]);
+  const float y = 1.0f/sqrtf(fmaf(x, x, 1.0f));
+  return fmaf(.5f*x, y, .5f);
+}
+
+// lights_init_light per emissive shape + lights_prepare_frame (list.c:56-104)
+static int build_lights(cb200_render *r)
+{
+  cb200_scene *s = r->accel->scene;
+  const cb_render_desc_t &d = r->desc;
+  std::vector<uint64_t> primid(s->num_prims ? s->num_prims : 1);
+  if(s->num_prims) if(cudaMemcpy(primid.data(), s->d_primid, s->num_prims*sizeof(uint64_t), cudaMemcpyDeviceToHost) != cudaSuccess) return CB200_ERR_CUDA;
+  std::vector<int32_t> shape_mat(s->num_shapes ? s->num_shapes : 1, 0);
+  {
+    std::vector<int64_t> tmp(s->num_shapes ? s->num_shapes : 1);
+    memcpy(tmp.data(), s->h_material.data(), sizeof(int64_t)*s->num_shapes);
+    for(int i=0;i<s->num_shapes;i++)
+    {
+      if(tmp[i] < 0 || tmp[i] >= d.num_materials) { cb200_set_error("render_create: shape references a material that was not supplied"); return CB200_ERR_ARG; }
+      shape_mat[i] = (int32_t)tmp[i];
+    }
+  }
+  r->dev.geo.shape_material = dev_upload(r, shape_mat.data(), shape_mat.size());
+  std::vector<float> shape_L(s->num_shapes ? s->num_shapes : 1, 0.0f);
+  for(int i=0;i<s->num_shapes;i++)
+  {
+    const cb_material_t &m = d.materials[shape_mat[i]];
+    for(int k=0;k<m.num_ops;k++) if(m.ops[k].op == CB_OP_COLOR && m.ops[k].slot == CB_SLOT_EMISSION)
+    { // color.c:65-73: mean of the spectrum at 660, 560, 480, 400 nm
+      const float *c = m.ops[k].coeff;
+      shape_L[i] = m.ops[k].mul*(host_rgb2spec(c, 660.0f) + host_rgb2spec(c, 560.0f) + host_rgb2spec(c, 480.0f) + host_rgb2spec(c, 400.0f))/4.0f;
+    }
+  }
+  std::vector<uint64_t> lp;
+  std::vector<float> lL;
+  for(uint64_t k=0;k<s->num_prims;k++)
+  {
+    const uint32_t sh = cb_primid_shapeid(primid[k]);
+    if(shape_L[sh] > 0.0f) { lp.push_back(primid[k]); lL.push_back(shape_L[sh]); }
+  }
+  // the global list is in load order, i.e. grouped by ascending shape id like lights_init_light appends them
+  const uint32_t n = (uint32_t)lp.size();
+  std::vector<float> area(n ? n : 1), cdf(n ? n : 1), shape_pdf(s->num_shapes ? s->num_shapes : 1, 0.0f);
+  LightsDev &L = r->dev.lights;
+  L.num = n; L.p_geo = n ? 1.0f : 0.0f;
+  L.primid = dev_upload(r, lp.data(), lp.size());
+  if(n)
+  {
+    float *d_area = dev_alloc<float>(r, n);
+    k_prim_area<<<(n + 127)/128, 128>>>(r->dev.geo, L.primid, n, d_area);
+    cb200_count_launch();
+    if(cudaMemcpy(area.data(), d_area, n*sizeof(float), cudaMemcpyDeviceToHost) != cudaSuccess) return CB200_ERR_CUDA;
+    float sum = 0.0f;
+    for(uint32_t k=0;k<n;k++) { cdf[k] = area[k]*lL[k]; sum += cdf[k]; }
+    for(uint32_t k=0;k<n;k++) lL[k] /= sum;
+    for(uint32_t k=1;k<n;k++) cdf[k] += cdf[k-1];
+    for(uint32_t k=0;k+1<n;k++) cdf[k] /= cdf[n-1];
+    cdf[n-1] = 1.0f;
+    for(uint32_t k=0;k<n;k++) shape_pdf[cb_primid_shapeid(lp[k])] = lL[k];
+  }
+  L.cdf = dev_upload(r, cdf.data(), cdf.size());
+  L.L = dev_upload(r, lL.data(), lL.size());
+  L.shape_pdf = dev_upload(r, shape_pdf.data(), shape_pdf.size());
+  return (L.cdf && L.L && L.shape_pdf && L.primid && r->dev.geo.shape_material) ? 0 : CB200_ERR_NOMEM;
+}
+
+extern "C" {
+
+void cb200_render_destroy(cb200_render_t *r)
+{
+  if(!r) return;
+  for(void *p : r->owned) cudaFree(p);
+  if(r->h_cnt) cudaFreeHost(r->h_cnt);
+  delete r;
+}
+
+cb200_render_t *cb200_render_create(cb200_accel_t *a, const cb_render_desc_t *desc)
+{
+  if(!a || !desc || !desc->materials || desc->num_materials < 1 || desc->width == 0 || desc->height == 0)
+  { cb200_set_error("render_create: bad arguments"); return nullptr; }
+  if(desc->camera.aperture_value < 0 || desc->camera.aperture_value >= (int)(sizeof(k_fstop)/sizeof(float)) ||
+     desc->camera.exposure_value < 0 || desc->camera.exposure_value >= (int)(sizeof(k_exposure)/sizeof(float)))
+  { cb200_set_error("render_create: aperture/exposure index out of range"); return nullptr; }
+  for(int i=0;i<desc->num_materials;i++)
+  {
+    const cb_material_t &m = desc->materials[i];
+    if(m.num_ops < 0 || m.num_ops > CB_MAX_MATOPS || m.bsdf < 0 || m.bsdf > CB_BSDF_METAL)
+    { cb200_set_error("render_create: unsupported material (no CPU fallback for unknown shaders)"); return nullptr; }
+    if(m.bsdf == CB_BSDF_METAL && (m.table < 0 || m.table >= desc->num_tables)) { cb200_set_error("render_create: metal without ior table"); return nullptr; }
+    for(int k=0;k<m.num_ops;k++) if(m.ops[k].op == CB_OP_CHECKERSG && (m.ops[k].table < 0 || m.ops[k].table >= desc->num_tables))
+    { cb200_set_error("render_create: colour checker without table"); return nullptr; }
+  }
+  cb200_render *r = new cb200_render();
+  r->accel = a;
+  r->desc = *desc;
+  memset(&r->stats, 0, sizeof(r->stats));
+  r->h_cnt = nullptr;
+  cb200_scene *s = a->scene;
+  RenderDev &D = r->dev;
+  memset(&D, 0, sizeof(D));
+  D.accel = a->dev;
+  D.geo.vtx = s->d_vtx; D.geo.vtxidx = s->d_vtxidx; D.geo.shapes = s->d_shapes;
+  D.sampler = desc->sampler; D.colour = desc->colour_camera;
+  D.max_path_len = desc->max_path_len > 0 && desc->max_path_len <= 32 ? desc->max_path_len : 32;
+  D.fb_w = desc->width; D.fb_h = desc->height;
+  D.cam.c = desc->camera; D.cam.width = (float)desc->width; D.cam.height = (float)desc->height;
+  D.cam.fstop = k_fstop[desc->camera.aperture_value];
+  D.cam.exposure_time = k_exposure[desc->camera.exposure_value];
+  D.points.mode = desc->pointsampler;
+  D.points.key = (desc->frame + 1)*0x9e3779b97f4a7c15ull ^ ((uint64_t)desc->rank << 32);
+  bool ok = true;
+  // materials and tables
+  std::vector<TableDev> tabs(desc->num_tables > 0 ? desc->num_tables : 1);
+  std::vector<float> tdata;
+  for(int i=0;i<desc->num_tables;i++)
+  {
+    const cb_table_t &t = desc->tables[i];
+    tabs[i].lambda_min = t.lambda_min; tabs[i].lambda_step = t.lambda_step; tabs[i].num_lambda = t.num_lambda; tabs[i].rows = t.rows;
+    tabs[i].offset = (uint32_t)tdata.size();
+    tdata.insert(tdata.end(), t.data, t.data + (size_t)t.num_lambda*t.rows);
+  }
+  D.mats.mat = dev_upload(r, desc->materials, desc->num_materials);
+  D.mats.tables = dev_upload(r, tabs.data(), tabs.size());
+  D.mats.table_data = dev_upload(r, tdata.data(), tdata.size());
+  ok = ok && D.mats.mat && D.mats.tables && D.mats.table_data;
+  ok = ok && cudaMemcpyToSymbol(c_cie, cie1931_xyz, sizeof(cie1931_xyz)) == cudaSuccess;
+  ok = ok && build_halton(r, desc->frame) == 0;
+  if(ok && build_lights(r)) { cb200_render_destroy(r); return nullptr; }
+  // wave buffers
+  r->batch = desc->batch_paths ? desc->batch_paths : (1ull << 22);
+  const uint64_t N = r->batch;
+  D.fb = dev_alloc<float>(r, (size_t)desc->width*desc->height*3);
+  for(int k=0;k<2;k++) { r->st[k] = dev_alloc<PathState>(r, N); r->rays[k] = dev_alloc<cb_ray_t>(r, N); ok = ok && r->st[k] && r->rays[k]; }
+  r->hits = dev_alloc<cb_hitrec_t>(r, N);
+  r->nee_rays = dev_alloc<cb_ray_t>(r, N); r->nee_md = dev_alloc<float>(r, N); r->nee_recs = dev_alloc<NeeRec>(r, N); r->nee_hits = dev_alloc<cb_hitrec_t>(r, N);
+  r->d_cnt = dev_alloc<ShadeCounters>(r, 1);
+  ok = ok && D.fb && r->hits && r->nee_rays && r->nee_md && r->nee_recs && r->nee_hits && r->d_cnt;
+  ok = ok && cudaMallocHost(&r->h_cnt, sizeof(ShadeCounters)) == cudaSuccess;
+  if(!ok)
+  {
+    cb200_set_error(std::string("render_create: device allocation/upload failed: ") + cudaGetErrorString(cudaGetLastError()));
+    cb200_render_destroy(r);
+    return nullptr;
+  }
+  cudaMemset(D.fb, 0, (size_t)desc->width*desc->height*3*sizeof(float));
+  return r;
+}
+
+int cb200_render_clear(cb200_render_t *r, void *stream)
+{
+  if(!r) { cb200_set_error("render_clear: null"); return CB200_ERR_ARG; }
+  CB_CUDA(cudaMemsetAsync(r->dev.fb, 0, (size_t)r->dev.fb_w*r->dev.fb_h*3*sizeof(float), (cudaStream_t)stream));
+  memset(&r->stats, 0, sizeof(r->stats));
+  return 0;
+}
+
+void *cb200_render_fb_device(cb200_render_t *r) { return r ? r->dev.fb : nullptr; }
+
+int cb200_render_download(cb200_render_t *r, float *fb_host, void *stream)
+{
+  if(!r || !fb_host) { cb200_set_error("render_download: bad arguments"); return CB200_ERR_ARG; }
+  CB_CUDA(cudaMemcpyAsync(fb_host, r->dev.fb, (size_t)r->dev.fb_w*r->dev.fb_h*3*sizeof(float), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+  CB_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+  return 0;
+}
+
+int cb200_render_stats(cb200_render_t *r, cb_render_stats_t *out)
+{
+  if(!r || !out) { cb200_set_error("render_stats: bad arguments"); return CB200_ERR_ARG; }
+  *out = r->stats;
+  return 0;
+}
+
+int cb200_render_pass(cb200_render_t *r, uint64_t first_index, uint64_t count, void *stream_)
+{
+  if(!r) { cb200_set_error("render_pass: null"); return CB200_ERR_ARG; }
+  cudaStream_t st = (cudaStream_t)stream_;
+  for(uint64_t off=0; off<count; off+=r->batch)
+  {
+    uint32_t n = (uint32_t)((count - off) < r->batch ? (count - off) : r->batch);
+    k_path_start<<<(n + RB - 1)/RB, RB, 0, st>>>(r->dev, first_index + off, n, r->st[0], r->rays[0], nullptr);
+    cb200_count_launch(); r->stats.kernel_launches++;
+    r->stats.paths += n;
+    int cur = 0;
+    for(int bounce=0; bounce<32 && n>0; bounce++)
+    {
+      int rc = cb200_launch_intersect(r->accel, r->rays[cur], nullptr, r->hits, n, st, nullptr);
+      if(rc) return rc;
+      r->stats.rays_closest += n; r->stats.kernel_launches++;
+      CB_CUDA(cudaMemsetAsync(r->d_cnt, 0, 2*sizeof(unsigned long long), st));   // next, nee (splats keeps counting)
+      k_shade<<<(n + RB - 1)/RB, RB, 0, st>>>(r->dev, n, r->st[cur], r->rays[cur], r->hits, r->st[cur^1], r->rays[cur^1],
+                                              r->nee_rays, r->nee_md, r->nee_recs, r->d_cnt);
+      cb200_count_launch(); r->stats.kernel_launches++;
+      CB_CUDA(cudaMemcpyAsync(r->h_cnt, r->d_cnt, sizeof(ShadeCounters), cudaMemcpyDeviceToHost, st));
+      CB_CUDA(cudaStreamSynchronize(st));
+      const uint32_t n_next = (uint32_t)r->h_cnt->next, n_nee = (uint32_t)r->h_cnt->nee;
+      if(n_nee)
+      {
+        rc = cb200_launch_intersect(r->accel, r->nee_rays, r->nee_md, r->nee_hits, n_nee, st, nullptr);
+        if(rc) return rc;
+        k_nee_resolve<<<(n_nee + RB - 1)/RB, RB, 0, st>>>(r->dev, n_nee, r->nee_recs, r->nee_hits, r->d_cnt);
+        cb200_count_launch(); r->stats.kernel_launches += 2;
+        r->stats.rays_shadow += n_nee;
+      }
+      n = n_next;
+      cur ^= 1;
+    }
+  }
+  CB_CUDA(cudaMemcpyAsync(r->h_cnt, r->d_cnt, sizeof(ShadeCounters), cudaMemcpyDeviceToHost, st));
+  CB_CUDA(cudaStreamSynchronize(st));
+  r->stats.splats = r->h_cnt->splats;
+  CB_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int cb200_render_point(cb200_render_t *r, const uint64_t *index, const int32_t *dim, float *out, uint64_t n)
+{
+  if(!r || !index || !dim || !out) { cb200_set_error("render_point: bad arguments"); return CB200_ERR_ARG; }
+  uint64_t *d_i = nullptr; int32_t *d_d = nullptr; float *d_o = nullptr;
+  CB_CUDA(cudaMalloc(&d_i, n*8 + 8)); CB_CUDA(cudaMalloc(&d_d, n*4 + 4)); CB_CUDA(cudaMalloc(&d_o, n*4 + 4));
+  CB_CUDA(cudaMemcpy(d_i, index, n*8, cudaMemcpyHostToDevice));
+  CB_CUDA(cudaMemcpy(d_d, dim, n*4, cudaMemcpyHostToDevice));
+  if(n) k_points<<<(unsigned)((n + 127)/128), 128>>>(r->dev.points, d_i, d_d, d_o, (uint32_t)n);
+  cb200_count_launch();
+  CB_CUDA(cudaMemcpy(out, d_o, n*4, cudaMemcpyDeviceToHost));
+  cudaFree(d_i); cudaFree(d_d); cudaFree(d_o);
+  return 0;
+}
+
+int cb200_render_camera_rays(cb200_render_t *r, uint64_t first_index, uint64_t n, cb_ray_t *out_rays, float *out_aux)
+{
+  if(!r || !out_rays || n > r->batch) { cb200_set_error("render_camera_rays: bad arguments (n must be <= batch_paths)"); return CB200_ERR_ARG; }
+  float *d_aux = nullptr;
+  CB_CUDA(cudaMalloc(&d_aux, n*16 + 16));
+  if(n) k_path_start<<<(unsigned)((n + RB - 1)/RB), RB>>>(r->dev, first_index, (uint32_t)n, nullptr, r->rays[0], d_aux);
+  cb200_count_launch();
+  CB_CUDA(cudaMemcpy(out_rays, r->rays[0], n*sizeof(cb_ray_t), cudaMemcpyDeviceToHost));
+  if(out_aux) CB_CUDA(cudaMemcpy(out_aux, d_aux, n*16, cudaMemcpyDeviceToHost));
+  cudaFree(d_aux);
+  return 0;
+}
+
+} // extern "C"

@@ -213,3 +213,112 @@ class Accel:
             self.close()
         except Exception:
             pass
+
+
+# ------------------------------------------------------------------------------------------------ integrator
+def _load_render():
+    L = load()
+    if getattr(L, "_render_ready", False):
+        return L
+    vp, u64 = C.c_void_p, C.c_uint64
+    L.cb200_render_create.restype = vp
+    L.cb200_render_create.argtypes = [vp, vp]
+    L.cb200_render_destroy.argtypes = [vp]
+    L.cb200_render_pass.argtypes = [vp, u64, u64, vp]
+    L.cb200_render_clear.argtypes = [vp, vp]
+    L.cb200_render_fb_device.restype = vp
+    L.cb200_render_fb_device.argtypes = [vp]
+    L.cb200_render_download.argtypes = [vp, vp, vp]
+    L.cb200_render_stats.argtypes = [vp, vp]
+    L.cb200_render_point.argtypes = [vp, vp, vp, vp, u64]
+    L.cb200_render_camera_rays.argtypes = [vp, u64, u64, vp, vp]
+    L._render_ready = True
+    return L
+
+
+RENDER_SYMBOLS = ["cb200_render_create", "cb200_render_destroy", "cb200_render_pass", "cb200_render_clear",
+                  "cb200_render_fb_device", "cb200_render_download", "cb200_render_stats", "cb200_render_point",
+                  "cb200_render_camera_rays"]
+
+
+class Render:
+    """wavefront pt/ptdl integrator on top of an Accel (include/corona_b200_render.h)"""
+
+    def __init__(self, accel, camera, materials, width, height, sampler=1, pointsampler=0, colour=0, max_path_len=32,
+                 frame=0, rank=0, world=1, batch_paths=0):
+        from . import scene_io as sio
+        self.L = _load_render()
+        self.accel = accel
+        self.width, self.height = (width + 31) // 32 * 32, (height + 31) // 32 * 32   # view.c:295-296
+        self.camera = camera
+        self._mats, self._tabs = materials.carrays()
+        self._materials = materials
+        d = sio.CRenderDesc()
+        d.width, d.height = self.width, self.height
+        d.camera = camera.cstruct(self.width, self.height)
+        d.materials = C.cast(self._mats, C.c_void_p)
+        d.num_materials = len(materials.materials)
+        d.tables = C.cast(self._tabs, C.c_void_p)
+        d.num_tables = len(materials.tables)
+        d.sampler, d.pointsampler, d.colour_camera, d.max_path_len = sampler, pointsampler, colour, max_path_len
+        d.frame, d.rank, d.world, d.batch_paths = frame, rank, world, batch_paths
+        self.desc = d
+        self.r = _nonnull(self.L.cb200_render_create(accel.a, C.byref(d)), "cb200_render_create")
+        self.spp = 0
+        self.next_index = 0
+
+    def render_pass(self, first=None, count=None, stream=0):
+        """one progression = width*height path indices (src/view.c:636-638)"""
+        count = self.width * self.height if count is None else count
+        first = self.next_index if first is None else first
+        _check(self.L.cb200_render_pass(self.r, first, count, stream or None), "cb200_render_pass")
+        self.next_index = first + count
+        self.spp += count / (self.width * self.height)
+
+    def clear(self):
+        _check(self.L.cb200_render_clear(self.r, None), "cb200_render_clear")
+        self.spp = 0
+        self.next_index = 0
+
+    def fb_device(self):
+        return self.L.cb200_render_fb_device(self.r)
+
+    def framebuffer(self):
+        fb = np.zeros((self.height, self.width, 3), np.float32)
+        _check(self.L.cb200_render_download(self.r, _ptr(fb), None), "cb200_render_download")
+        return fb
+
+    def image(self, spp=None):
+        """fb * gain, gain = iso / (100 * spp) (src/view.c:656)"""
+        spp = self.spp if spp is None else spp
+        return self.framebuffer() * np.float32(self.camera.iso / (100.0 * max(spp, 1e-9)))
+
+    def stats(self):
+        from . import scene_io as sio
+        s = sio.CRenderStats()
+        _check(self.L.cb200_render_stats(self.r, C.byref(s)), "cb200_render_stats")
+        return {k: int(getattr(s, k)) for k, _ in s._fields_}
+
+    def points(self, index, dim):
+        index = np.ascontiguousarray(index, np.uint64)
+        dim = np.ascontiguousarray(dim, np.int32)
+        out = np.zeros(len(index), np.float32)
+        _check(self.L.cb200_render_point(self.r, _ptr(index), _ptr(dim), _ptr(out), len(index)), "cb200_render_point")
+        return out
+
+    def camera_rays(self, first, n):
+        rays = np.zeros(n, RAY)
+        aux = np.zeros((n, 4), np.float32)
+        _check(self.L.cb200_render_camera_rays(self.r, first, n, _ptr(rays), _ptr(aux)), "cb200_render_camera_rays")
+        return rays, aux
+
+    def close(self):
+        if self.r:
+            self.L.cb200_render_destroy(self.r)
+            self.r = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -1,0 +1,143 @@
+/* corona_b200_render.h -- C ABI of the wavefront pt / ptdl integrator in libcorona_b200.so.
+ *
+ * Replaces the reference's per-thread recursive loop
+ *     view_render -> work_sample -> render_sample_path -> sampler_create_path      (src/view.c:618-645,
+ *     src/render.d/gi.c:81, src/sampler.d/pt.c:40 / ptdl.c:112)
+ * by kernels over batches of path indices: camera-ray generation (src/camera.d/thinlens.c:68-128),
+ * closest-hit traversal, vertex preparation + material chain (src/shader.c:462-542), emission with MIS,
+ * next-event estimation (include/pathspace/nee.h:87-243, src/lights.d/list.c) with shadow rays in
+ * path_visible semantics (src/pathspace.c:311-344), BSDF sampling, splatting (src/view.c:455-495,
+ * include/filter/blackmanharris.h:43-77).
+ *
+ * The scene description arrives flattened: the host layer (or a test) walks the reference's shader list
+ * (`.nra2`: mult / color / colorcheckersg / dielectric / metal / diffuse) once at load time and hands over one
+ * cb_material_t per shader index a shape may reference.  Unknown shader kinds are a hard error upstream --
+ * there is no CPU fallback.
+ */
+#ifndef CORONA_B200_RENDER_H
+#define CORONA_B200_RENDER_H
+
+#include "corona_b200.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- camera: the fields of camera_t the thin lens model reads (include/camera.h:13-35) ------------------- */
+typedef struct cb_camera_t
+{
+  float pos[3], pos_t1[3];
+  float orient[4], orient_t1[4];   /* quaternion w,x,y,z (include/quaternion.h) */
+  float focus;
+  float film_width, film_height;
+  int32_t aperture_value;          /* index into the f-stop table (src/view.c:71-73) */
+  int32_t exposure_value;          /* index into the exposure-time table (src/view.c:75-79) */
+  float focal_length;
+  float iso;
+}
+cb_camera_t;
+
+/* ---- materials ------------------------------------------------------------------------------------------
+ * A material = the reference's `mult <n> <pre...> <host>` flattened: up to CB_MAX_MATOPS prepare() steps that
+ * fill vertex_shading_t slots, then the host BSDF.                                                          */
+#define CB_MAX_MATOPS 6
+enum { CB_OP_NONE = 0,
+       CB_OP_COLOR = 1,          /* src/shaders/color.c:75-81: slot <- mul * rgb2spec(coeff, lambda), roughness */
+       CB_OP_CHECKERSG = 2 };    /* src/shaders/colorcheckersg.c:244-261: 14x10 ColorChecker SG by uv */
+enum { CB_SLOT_DIFFUSE = 0, CB_SLOT_SPECULAR = 1, CB_SLOT_EMISSION = 2, CB_SLOT_VOLUME = 3, CB_SLOT_GLOSSY = 4,
+       CB_SLOT_ROUGHNESS = 5, CB_SLOT_TRANSMIT_TO_EYE = 6 };   /* src/shaders/texture.h:8-21 */
+enum { CB_BSDF_DIFFUSE = 0,      /* src/shader.c:157-257 */
+       CB_BSDF_DIELECTRIC = 1,   /* src/shaders/dielectric.c */
+       CB_BSDF_METAL = 2 };      /* src/shaders/metal.c */
+
+typedef struct cb_matop_t
+{
+  int32_t op, slot;
+  float coeff[3];                /* rgb2spec sigmoid-polynomial coefficients (include/rgb2spec.h:87-128) */
+  float mul;
+  float roughness;
+  int32_t table;                 /* CB_OP_CHECKERSG: index into cb_render_desc_t.tables (140 rows x 36 wavelengths) */
+}
+cb_matop_t;
+
+/* wavelength-indexed lookup table, nearest sample like the reference's measured data:
+ * value(row, lambda) = data[row*num_lambda + (int)((lambda - lambda_min)/lambda_step)]
+ * (ColorChecker SG reflectances, src/shaders/colorcheckersg.c:168-179; complex IORs of metals as two rows n, k,
+ * src/shaders/fresnel.h:519-531).  The data stay with the caller's scene description; the library copies them. */
+typedef struct cb_table_t
+{
+  float lambda_min, lambda_step;
+  int32_t num_lambda, rows;
+  const float *data;
+}
+cb_table_t;
+
+typedef struct cb_material_t
+{
+  int32_t num_ops;
+  int32_t bsdf;
+  float param[4];                /* dielectric: n_d, abbe */
+  int32_t table;                 /* metal: index of its (n,k) table */
+  int32_t pad;
+  cb_matop_t ops[CB_MAX_MATOPS];
+}
+cb_material_t;
+
+/* ---- render description ---------------------------------------------------------------------------------- */
+enum { CB_SAMPLER_PT = 0, CB_SAMPLER_PTDL = 1 };          /* src/sampler.d/pt.c, ptdl.c */
+enum { CB_POINTS_RAND = 0, CB_POINTS_HALTON = 1 };        /* src/pointsampler.d/rand.c, halton.c */
+enum { CB_COLOUR_XYZ = 0, CB_COLOUR_REC709 = 1 };         /* COL_camera (Makefile:122-136) */
+
+typedef struct cb_render_desc_t
+{
+  uint32_t width, height;        /* already padded to multiples of 32 by the caller (src/view.c:295-296) */
+  cb_camera_t camera;
+  const cb_material_t *materials;
+  int32_t num_materials;
+  const cb_table_t *tables;
+  int32_t num_tables;
+  int32_t sampler;               /* CB_SAMPLER_* */
+  int32_t pointsampler;          /* CB_POINTS_* */
+  int32_t colour_camera;         /* CB_COLOUR_* */
+  int32_t max_path_len;          /* ptdl: rt.sampler->max_path_len, <= 32 (PATHSPACE_MAX_VERTS) */
+  uint64_t frame;                /* rt.anim_frame: seeds the Halton permutations / the counter RNG */
+  uint32_t rank, world;          /* sample-space split: decorrelates the counter RNG streams across GPUs */
+  uint64_t batch_paths;          /* paths in flight per wave (0 = default) */
+}
+cb_render_desc_t;
+
+typedef struct cb200_render cb200_render_t;
+
+typedef struct cb_render_stats_t
+{
+  uint64_t paths;                /* render_sample_path calls */
+  uint64_t rays_closest;         /* accel_intersect calls from path_propagate */
+  uint64_t rays_shadow;          /* accel_intersect calls from path_visible */
+  uint64_t splats;
+  uint64_t kernel_launches;
+}
+cb_render_stats_t;
+
+cb200_render_t *cb200_render_create(cb200_accel_t *a, const cb_render_desc_t *desc);
+void cb200_render_destroy(cb200_render_t *r);
+/* one call = the work of view_render()'s fan-out for path indices [first, first+count) (src/view.c:636-645);
+ * accumulates into the device framebuffer (W*H*3 floats), asynchronous on `stream` */
+int  cb200_render_pass(cb200_render_t *r, uint64_t first_index, uint64_t count, void *stream);
+int  cb200_render_clear(cb200_render_t *r, void *stream);
+/* device pointer of the accumulation buffer (for ncclReduce across ranks) and its download.  The image the
+ * reference writes is fb * gain, gain = iso / (100 * spp) (src/view.c:656) */
+void *cb200_render_fb_device(cb200_render_t *r);
+int  cb200_render_download(cb200_render_t *r, float *fb_host, void *stream);
+int  cb200_render_stats(cb200_render_t *r, cb_render_stats_t *out);
+
+/* component entry points for parity tests (device work, host buffers): */
+/* Halton / counter RNG value for (path index, dimension) as pointsampler() returns it (halton.c:69-84) */
+int  cb200_render_point(cb200_render_t *r, const uint64_t *index, const int32_t *dim, float *out, uint64_t n);
+/* primary rays for path indices: camera_sample (thinlens.c:115-128) with the path's own random dims;
+ * out_aux[n][4] = {pixel_i, pixel_j, lambda, throughput} */
+int  cb200_render_camera_rays(cb200_render_t *r, uint64_t first_index, uint64_t n, cb_ray_t *out_rays, float *out_aux);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

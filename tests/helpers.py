@@ -138,3 +138,39 @@ def classify_mismatches(orc, rays, got, want, max_dist=None):
         print(f"unexplained difference at ray {i}: ray={rays[i]} gpu={got[i]} ref={want[i]} "
               f"order(gpu,ref)->{a} order(ref,gpu)->{b}")
     return len(idx), explained
+
+
+class GoldenImage:
+    """scene + reference renders (two seeds per integrator) written by tests/golden/make_golden_images.py"""
+
+    def __init__(self, name):
+        import ctypes as C
+        IO = cb.scene_io
+        z = np.load(os.path.join(GOLDEN, "img_" + name + ".npz"))
+        self.z = z
+        shapes = []
+        mats = z["shape_mats"]
+        for i in range(int(z["num_shapes"])):
+            shapes.append(S.Shape(z[f"s{i}_primid"], np.ascontiguousarray(z[f"s{i}_vtxidx"]).view(R.VTXIDX).reshape(-1),
+                                  np.ascontiguousarray(z[f"s{i}_vtx"]).view(R.VTX).reshape(-1), int(mats[i]), f"s{i}"))
+        self.scene = S.Scene(shapes, name)
+        self.w, self.h, self.spp = int(z["w"]), int(z["h"]), int(z["spp"])
+        tmp = os.path.join("/tmp", f"golden_cam_{os.getpid()}_{name}.cam")
+        open(tmp, "wb").write(z["cam"].tobytes())
+        self.camera = IO.read_cam(tmp)
+        os.remove(tmp)
+        raw = z["materials"].tobytes()
+        n = len(raw) // C.sizeof(IO.CMaterial)
+        self.materials = IO.MaterialSet()
+        arr = (IO.CMaterial * n).from_buffer_copy(raw)
+        self.materials.materials = [arr[i] for i in range(n)]
+
+    def ref(self, key, seed):
+        return self.z[f"{key}_seed{seed}"]
+
+
+def image_stats(a, b):
+    """(relative RMSE of b against a, per-channel mean ratio b/a); relRMSE = sqrt(mean (a-b)^2) / mean(a)"""
+    a64, b64 = a.astype(np.float64), b.astype(np.float64)
+    rel = np.sqrt(((a64 - b64) ** 2).mean()) / max(a64.mean(), 1e-30)
+    return float(rel), b64.mean(axis=(0, 1)) / np.maximum(a64.mean(axis=(0, 1)), 1e-30)
