@@ -775,6 +775,7 @@ cb200_render_t *cb200_render_create(cb200_accel_t *a, const cb_render_desc_t *de
     return nullptr;
   }
   cudaMemset(D.fb, 0, (size_t)desc->width*desc->height*3*sizeof(float));
+  cudaMemset(r->d_cnt, 0, sizeof(ShadeCounters));
   return r;
 }
 
@@ -782,6 +783,7 @@ int cb200_render_clear(cb200_render_t *r, void *stream)
 {
   if(!r) { cb200_set_error("render_clear: null"); return CB200_ERR_ARG; }
   CB_CUDA(cudaMemsetAsync(r->dev.fb, 0, (size_t)r->dev.fb_w*r->dev.fb_h*3*sizeof(float), (cudaStream_t)stream));
+  CB_CUDA(cudaMemsetAsync(r->d_cnt, 0, sizeof(ShadeCounters), (cudaStream_t)stream));
   memset(&r->stats, 0, sizeof(r->stats));
   return 0;
 }

@@ -180,6 +180,8 @@ class Rgb2Spec:
             if rgb[j] >= rgb[i]:
                 i = j
         z = rgb[i]
+        if not z > 0:   # black: 0*inf = NaN coefficients in the reference too; CLAMP(NaN, 0, 1) = 0 downstream (corona_common.h:168-170)
+            return np.full(3, np.nan, np.float32)
         scale = np.float32(res - 1) / z
         x = rgb[(i + 1) % 3] * scale
         y = rgb[(i + 2) % 3] * scale
