@@ -649,6 +649,8 @@ static int build_lights(cb200_render *r)
     for(int i=0;i<s->num_shapes;i++)
     {
       if(tmp[i] < 0 || tmp[i] >= d.num_materials) { cb200_set_error("render_create: shape references a material that was not supplied"); return CB200_ERR_ARG; }
+      if(d.materials[tmp[i]].num_ops < 0)
+      { cb200_set_error("render_create: shape uses a shader outside the pt/ptdl surface path (no CPU fallback for unknown shaders)"); return CB200_ERR_UNSUPPORTED; }
       shape_mat[i] = (int32_t)tmp[i];
     }
   }
@@ -716,8 +718,9 @@ cb200_render_t *cb200_render_create(cb200_accel_t *a, const cb_render_desc_t *de
   for(int i=0;i<desc->num_materials;i++)
   {
     const cb_material_t &m = desc->materials[i];
-    if(m.num_ops < 0 || m.num_ops > CB_MAX_MATOPS || m.bsdf < 0 || m.bsdf > CB_BSDF_METAL)
-    { cb200_set_error("render_create: unsupported material (no CPU fallback for unknown shaders)"); return nullptr; }
+    if(m.num_ops < 0) continue;   // a shader outside the hot path (media, skies): only an error when a shape references it
+    if(m.num_ops > CB_MAX_MATOPS || m.bsdf < 0 || m.bsdf > CB_BSDF_METAL)
+    { cb200_set_error("render_create: malformed material"); return nullptr; }
     if(m.bsdf == CB_BSDF_METAL && (m.table < 0 || m.table >= desc->num_tables)) { cb200_set_error("render_create: metal without ior table"); return nullptr; }
     for(int k=0;k<m.num_ops;k++) if(m.ops[k].op == CB_OP_CHECKERSG && (m.ops[k].table < 0 || m.ops[k].table >= desc->num_tables))
     { cb200_set_error("render_create: colour checker without table"); return nullptr; }

@@ -1,11 +1,15 @@
 """Golden IMAGES from the unmodified reference renderer (oracle/_ref/corona_*, built by oracle/Makefile from the
 reference sources in place).  Run in the build container only:
 
-    python tests/golden/make_golden_images.py
+    python tests/golden/make_golden_images.py [case ...]
 
 For each case: writes the scene (.geo / .nra2 / .cam) to a scratch directory, runs the reference with two different
---frame seeds, and stores both images (fb*gain as the reference exports them) plus the scene description in
-tests/golden/img_<case>.npz.  The second seed gives the Monte Carlo noise floor the GPU image is judged against.
+--frame seeds per integrator variant, and stores the images (fb*gain as the reference exports them) plus the complete
+scene description (geometry, flattened materials, lookup tables, camera) in tests/golden/img_<case>.npz.  The second seed
+gives the Monte Carlo noise floor the GPU image is judged against; with the Halton point sampler and the same --frame the
+GPU integrator draws the SAME sample points as the reference, so those images agree far below the noise floor.
+
+Variant keys name the reference binary: <sampler>_<pointsampler>[_rec709]  (oracle/Makefile `render` targets).
 """
 import importlib
 import os
@@ -24,21 +28,22 @@ S, IO = cb.scenes, cb.scene_io
 REFDIR = os.path.join(ROOT, "oracle", "_ref")
 
 
-def run_reference(binary, scene_dir, nra2, w, h, spp, frame, threads=None):
+def run_reference(binary, nra2, w, h, spp, frame, threads=None):
     """corona <scene> -x -s spp -w w -h h -b 0 --frame f, cwd = oracle/_ref (data/ergb2spec.coeff is cwd-relative, main.c:292)"""
     threads = threads or os.cpu_count()
     cmd = [os.path.join(REFDIR, binary), nra2, "-x", "-s", str(spp), "-w", str(w), "-h", str(h), "-b", "0",
            "-t", str(threads), "--frame", str(frame), "-q"]
     subprocess.run(cmd, cwd=REFDIR, check=True, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
     base = os.path.splitext(nra2)[0]
-    img = IO.read_pfm(base + "render_fb00.pfm") if os.path.exists(base + "render_fb00.pfm") else None
-    if img is None:
-        cand = [f for f in os.listdir(os.path.dirname(nra2)) if f.endswith(".pfm")]
-        img = IO.read_pfm(os.path.join(os.path.dirname(nra2), cand[0]))
-    return img
+    return IO.read_pfm(base + "render_fb00.pfm")
 
 
-def synthetic_case(name, scene, shader_lines, shape_mats, cam, w, h, spp, binaries):
+def load_tables():
+    z = np.load(os.path.join(HERE, "ref_tables.npz"))
+    return z["checker"], {k[6:]: z[k] for k in z.files if k.startswith("metal_")}
+
+
+def golden_case(name, scene, shader_lines, shape_mats, cam, w, h, spp, variants):
     tmp = tempfile.mkdtemp(prefix="corona_golden_")
     try:
         shapes = []
@@ -49,15 +54,22 @@ def synthetic_case(name, scene, shader_lines, shape_mats, cam, w, h, spp, binari
         IO.write_nra2(nra2, shader_lines, shapes)
         cam.write(os.path.join(tmp, "test01.cam"))
         out = {}
-        for key, binary in binaries.items():
+        for key in variants:
             for seed in (1, 2):
-                out[f"{key}_seed{seed}"] = run_reference(binary, tmp, nra2, w, h, spp, seed)
-                print(name, key, seed, out[f"{key}_seed{seed}"].shape, out[f"{key}_seed{seed}"].mean(axis=(0, 1)))
-        ms, _, _ = IO.parse_nra2(nra2, IO.Rgb2Spec(IO.coeff_path(ROOT)))
+                img = run_reference("corona_" + key, nra2, w, h, spp, seed)
+                out[f"{key}_seed{seed}"] = img
+                print(name, key, seed, img.shape, img.mean(axis=(0, 1)), flush=True)
+        checker, metals = load_tables()
+        ms, _, _ = IO.parse_nra2(nra2, IO.Rgb2Spec(IO.coeff_path(ROOT)), checker, metals)
         mats, _ = ms.carrays()
-        matbytes = np.frombuffer(bytes(mats), np.uint8)   # flattened cb_material_t[] incl. the rgb2spec coefficients
-        pack = {"materials": matbytes, "num_shapes": np.int64(len(scene.shapes)), "shape_mats": np.int64(shape_mats), "w": np.int64(w), "h": np.int64(h),
-                "spp": np.int64(spp), "shader_lines": np.array(shader_lines), "cam": np.frombuffer(open(os.path.join(tmp, "test01.cam"), "rb").read(), np.uint8)}
+        pack = {"materials": np.frombuffer(bytes(mats), np.uint8),   # flattened cb_material_t[] incl. the rgb2spec coefficients
+                "num_shapes": np.int64(len(scene.shapes)), "shape_mats": np.int64(shape_mats), "w": np.int64(w), "h": np.int64(h),
+                "spp": np.int64(spp), "shader_lines": np.array(shader_lines), "variants": np.array(list(variants)),
+                "cam": np.frombuffer(open(os.path.join(tmp, "test01.cam"), "rb").read(), np.uint8),
+                "num_tables": np.int64(len(ms.tables))}
+        for i, (lmin, step, data) in enumerate(ms.tables):
+            pack[f"tab{i}_meta"] = np.float32([lmin, step])
+            pack[f"tab{i}_data"] = data
         for i, s in enumerate(scene.shapes):
             pack[f"s{i}_primid"] = s.primid
             pack[f"s{i}_vtxidx"] = s.vtxidx.view("<u4").reshape(-1, 2)
@@ -71,12 +83,99 @@ def synthetic_case(name, scene, shader_lines, shape_mats, cam, w, h, spp, binari
         shutil.rmtree(tmp, ignore_errors=True)
 
 
-if __name__ == "__main__":
-    subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "oracle"), "ref"])
-    # case 1: diffuse terrain + soup under a quad light, static
+def reference_shader_lines(nra2):
+    """the shader list of one of the reference's own regression scenes, comments stripped"""
+    lines = [l.split("#")[0].strip() for l in open(nra2).read().split("\n")]
+    n = int(lines[1].split()[0])
+    return lines[2:2 + n]
+
+
+def case_diffuse_static():
+    """diffuse terrain + icosphere soup under a quad light, triangles only"""
     sc = S.synthetic_scene(3000, seed=7)
     lines = ["diffuse", "color d 0.6 0.5 0.4", "mult 1 1 0", "color d 0 0 0", "color e 30 30 30 1.", "mult 2 3 4 0"]
-    mats = [2, 2, 5]   # terrain, soup, light
     cam = IO.Camera(pos=(14.0, 11.0, 9.0), lookat=(0.0, 0.0, 2.0), aperture_value=6, exposure_value=13, focal_length=0.35, iso=400.0)
-    synthetic_case("diffuse_static", sc, lines, mats, cam, 160, 96, 256,
-                   {"pt": "corona_pt_rand", "ptdl": "corona_ptdl_rand", "ptdl_halton": "corona_ptdl_halton"})
+    golden_case("diffuse_static", sc, lines, [2, 2, 5], cam, 160, 96, 256, ["pt_rand", "ptdl_rand", "ptdl_halton"])
+
+
+def case_c10():
+    """regression/0010_pt and 0011_ptdl as shipped offline: the six in-tree .geo files (4105 quads, analytic sphere /
+    cylinder / cone with the rough dispersive dielectric, colour checker plane), the scene's own shader list and camera;
+    the missing filllight.geo is regenerated as one emissive quad"""
+    geo = os.path.join(REFDIR, "scenes", "geo")
+    sc = S.c10_like_scene(geo)
+    assert sc.name == "0010_pt", "needs the reference .geo files (make -C oracle ref)"
+    order = [("plane", 2), ("emitter", 5), ("cone", 10), ("sphere", 10), ("cylinder", 10), ("cylinder_cap", 2)]   # test.nra2:17-22
+    by_name = {s.name.replace(".geo", ""): s for s in sc.shapes}
+    shapes = [by_name[n] for n, _ in order] + [S.quad_light((4.0, 0.0, 8.0), 1.5, 12)]
+    mats = [m for _, m in order] + [12]
+    lines = reference_shader_lines(os.path.join(REFDIR, "scenes", "0010_pt", "test.nra2"))
+    cam = IO.read_cam(os.path.join(REFDIR, "scenes", "0010_pt", "test01.cam"))
+    golden_case("c10", S.Scene(shapes, "0010_pt"), lines, mats, cam, 256, 160, 64, ["pt_rand", "ptdl_rand", "pt_halton", "ptdl_halton"])
+
+
+def case_motion():
+    """regression/0002_mb's ingredients (its geometry is not available offline): ptdl + halton + rec709 framebuffer, motion-blurred
+    triangle soup, a moving analytic sphere and a translating camera, 1/30 s exposure so that time covers [0,1)"""
+    terrain = S.terrain(1200, 3, quads=True, material=0)
+    soup = S.soup(1500, 4, material=0, motion=(0.9, 0.3, -0.4))
+    ball = S.analytic_shape("sphere", (2.0, 1.0, 4.5), 1.2, material=0, motion=(-1.0, 0.8, 0.3))
+    light = S.quad_light((0.0, 0.0, 9.0), 2.5, 1)
+    lines = ["diffuse", "color d 0.7 0.7 0.7", "mult 1 1 0", "color d 0 0 0", "color e 40 36 30 1.", "mult 2 3 4 0",
+             "color d 0.8 0.2 0.1", "mult 1 6 0"]
+    cam = IO.Camera(pos=(13.0, -12.0, 10.0), lookat=(0.0, 0.0, 3.0), aperture_value=5, exposure_value=11, focal_length=0.35,
+                    iso=100.0, pos_t1=(13.4, -11.7, 10.1))
+    golden_case("motion", S.Scene([terrain, soup, ball, light], "motion"), lines, [2, 7, 7, 5], cam, 160, 96, 128,
+                ["ptdl_halton_rec709", "ptdl_rand", "pt_halton"])
+
+
+def case_glass_metal():
+    """smooth and rough dielectrics (mesh with shading normals + analytic sphere: nested media, specular chains, dispersion),
+    rough gold, mirror-like silver, colour-checker floor with uvs"""
+    g = 8
+    xs = np.linspace(-8, 8, g + 1, dtype=np.float32)
+    X, Y = np.meshgrid(xs, xs, indexing="ij")
+    pos = np.stack([X, Y, np.zeros_like(X)], -1).reshape(-1, 3)
+    i, j = np.meshgrid(np.arange(g), np.arange(g), indexing="ij")
+    v00 = (i * (g + 1) + j).reshape(-1)
+    uv = np.stack([(X / 16 + 0.5).reshape(-1), (Y / 16 + 0.5).reshape(-1)], -1) * 0.999 + 0.0005
+    floor = S.mesh_shape(pos, np.stack([v00, v00 + g + 1, v00 + g + 2, v00 + 1], -1), 0, None, "floor", uv=uv)
+    iv, itri = S._icosahedron()
+    ctr = np.float32([[0.0, 0.0, 1.3], [-0.5, -4.5, 1.0], [3.0, -1.2, 1.5]])     # the third one intersects the analytic glass ball: nested media
+    rad = np.float32([1.3, 1.0, 1.0])
+    glass_mesh = S.mesh_shape((ctr[:, None, :] + rad[:, None, None] * iv[None]).reshape(-1, 3),
+                              (itri[None] + 12 * np.arange(3)[:, None, None]).reshape(-1, 3), 0, None, "glass_mesh")
+    glass_ball = S.analytic_shape("sphere", (3.0, -3.0, 1.5), 1.5, material=0)
+    rough_ball = S.analytic_shape("sphere", (-3.5, 3.0, 1.2), 1.2, material=0)
+    gold = S.analytic_shape("line", (-3.0, -3.5, 0.0), 0.9, (-3.0, -3.5, 2.5), 0.9, material=0)
+    silver = S.analytic_shape("line", (3.5, 3.5, 0.0), 1.2, (3.5, 3.5, 2.8), 0.3, material=0)
+    light = S.quad_light((0.0, 0.0, 8.0), 3.0, 1)
+    lines = ["diffuse",                       # 0
+             "colorcheckersg d",              # 1
+             "mult 1 1 0",                    # 2 floor
+             "color d 0 0 0",                 # 3
+             "color e 25 25 25 1.",           # 4
+             "mult 2 3 4 0",                  # 5 light
+             "dielectric 1.5 40",             # 6
+             "color g 1 1 1 0.0",             # 7
+             "mult 1 7 6",                    # 8 smooth glass
+             "color g 0.95 1 0.95 0.15",      # 9
+             "dielectric 1.3 23",             # 10
+             "mult 1 9 10",                   # 11 rough glass
+             "metal Au",                      # 12
+             "color g 1 1 1 0.2",             # 13
+             "mult 1 13 12",                  # 14 rough gold
+             "metal Ag",                      # 15
+             "color g 1 1 1 0.0",             # 16
+             "mult 1 16 15"]                  # 17 polished silver
+    cam = IO.Camera(pos=(12.0, -9.0, 8.0), lookat=(0.0, 0.0, 1.2), aperture_value=6, exposure_value=13, focal_length=0.4, iso=400.0)
+    golden_case("glass_metal", S.Scene([floor, glass_mesh, glass_ball, rough_ball, gold, silver, light], "glass_metal"), lines,
+                [2, 8, 8, 11, 14, 17, 5], cam, 192, 128, 128, ["pt_halton", "ptdl_halton", "ptdl_rand"])
+
+
+CASES = {"diffuse_static": case_diffuse_static, "c10": case_c10, "motion": case_motion, "glass_metal": case_glass_metal}
+
+if __name__ == "__main__":
+    subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "oracle"), "ref"])
+    for name in (sys.argv[1:] or list(CASES)):
+        CASES[name]()

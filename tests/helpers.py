@@ -141,13 +141,14 @@ def classify_mismatches(orc, rays, got, want, max_dist=None):
 
 
 class GoldenImage:
-    """scene + reference renders (two seeds per integrator) written by tests/golden/make_golden_images.py"""
+    """scene + reference renders (two seeds per integrator variant) written by tests/golden/make_golden_images.py"""
 
     def __init__(self, name):
         import ctypes as C
         IO = cb.scene_io
         z = np.load(os.path.join(GOLDEN, "img_" + name + ".npz"))
         self.z = z
+        self.name = name
         shapes = []
         mats = z["shape_mats"]
         for i in range(int(z["num_shapes"])):
@@ -155,6 +156,7 @@ class GoldenImage:
                                   np.ascontiguousarray(z[f"s{i}_vtx"]).view(R.VTX).reshape(-1), int(mats[i]), f"s{i}"))
         self.scene = S.Scene(shapes, name)
         self.w, self.h, self.spp = int(z["w"]), int(z["h"]), int(z["spp"])
+        self.variants = [str(v) for v in z["variants"]]
         tmp = os.path.join("/tmp", f"golden_cam_{os.getpid()}_{name}.cam")
         open(tmp, "wb").write(z["cam"].tobytes())
         self.camera = IO.read_cam(tmp)
@@ -164,9 +166,30 @@ class GoldenImage:
         self.materials = IO.MaterialSet()
         arr = (IO.CMaterial * n).from_buffer_copy(raw)
         self.materials.materials = [arr[i] for i in range(n)]
+        for i in range(int(z["num_tables"])):
+            lmin, step = z[f"tab{i}_meta"]
+            self.materials.add_table(lmin, step, z[f"tab{i}_data"])
 
     def ref(self, key, seed):
         return self.z[f"{key}_seed{seed}"]
+
+    @staticmethod
+    def variant_args(key):
+        """'ptdl_halton_rec709' -> keyword arguments of lib.Render"""
+        IO = cb.scene_io
+        f = key.split("_")
+        return dict(sampler=IO.SAMPLER_PTDL if f[0] == "ptdl" else IO.SAMPLER_PT,
+                    pointsampler=IO.POINTS_HALTON if f[1] == "halton" else IO.POINTS_RAND,
+                    colour=IO.COLOUR_REC709 if "rec709" in f else IO.COLOUR_XYZ)
+
+    def render(self, lib, acc, key, frame=1, spp=None, **kw):
+        """the GPU image of one variant at the golden's resolution and sample count"""
+        r = lib.Render(acc, self.camera, self.materials, self.w, self.h, frame=frame, **self.variant_args(key), **kw)
+        for _ in range(spp or self.spp):
+            r.render_pass()
+        img, st = r.image(), r.stats()
+        r.close()
+        return img, st
 
 
 def image_stats(a, b):

@@ -25,6 +25,11 @@ def test_exports_every_declared_symbol(lib):
     for s in syms:
         assert hasattr(L, s), f"libcorona_b200.so does not export {s}"
     assert sorted(lib.SYMBOLS) == syms
+    rsyms = declared_symbols("corona_b200_render.h")
+    assert len(rsyms) >= 9
+    for s in rsyms:
+        assert hasattr(L, s), f"libcorona_b200.so does not export {s}"
+    assert sorted(lib.RENDER_SYMBOLS) == rsyms
 
 
 def test_no_cpu_fallback(lib):
