@@ -73,7 +73,7 @@ cb200_scene_t *cb200_scene_create(const cb_shape_t *shapes, int num_shapes)
   if(num_shapes < 0 || (num_shapes > 0 && !shapes)) { g_error = "scene_create: bad arguments"; return nullptr; }
   if(cb200_device_count() < 1) { if(g_error.empty()) g_error = "no CUDA device"; return nullptr; }
   cb200_scene *s = new cb200_scene();
-  s->num_shapes = 0; s->num_prims = s->num_vtx = s->num_vtxidx = 0; s->any_mb = 0;
+  s->num_shapes = 0; s->num_prims = s->num_vtx = s->num_vtxidx = 0; s->any_mb = 0; s->any_analytic = 0;
   s->d_vtx = nullptr; s->d_vtxidx = nullptr; s->d_shapes = nullptr; s->d_primid = nullptr;
   cudaGetDevice(&s->device);
   for(int i=0;i<num_shapes;i++) s->h_material.push_back(shapes[i].material);
@@ -97,6 +97,7 @@ cb200_scene_t *cb200_scene_create(const cb_shape_t *shapes, int num_shapes)
       if(vcnt < 1 || vcnt > 4) { g_error = "scene_create: unsupported primitive type (shells are out of scope)"; delete s; return nullptr; }
       if(cb_primid_vi(p) + vcnt > shapes[i].num_vtxidx) { g_error = "scene_create: vertex index out of range"; delete s; return nullptr; }
       if(cb_primid_mb(p)) s->any_mb = 1;
+      if(cb_primid_vcnt(p) < CB_PRIM_TRI) s->any_analytic = 1;
       primid[k++] = p;
     }
 #define SC(call) do { cudaError_t e__ = (call); if(e__ != cudaSuccess) { cb200_cuda_fail(e__, #call, __FILE__, __LINE__); cb200_scene_destroy(s); return nullptr; } } while(0)

@@ -63,6 +63,7 @@ struct cb200_scene
   int        num_shapes;
   uint64_t   num_prims, num_vtx, num_vtxidx;
   int        any_mb;
+  int        any_analytic;   // spheres / lines present (selects the traversal kernel variant)
   cb_vtx_t    *d_vtx;
   cb_vtxidx_t *d_vtxidx;
   ShapeDev    *d_shapes;
@@ -98,3 +99,6 @@ int cb200_launch_intersect(const cb200_accel *a, const cb_ray_t *d_rays, const f
                            uint64_t n, cudaStream_t stream, unsigned long long *d_counters);
 int cb200_launch_visible(const cb200_accel *a, const cb_ray_t *d_rays, const float *d_max_dist, int32_t *d_out,
                          uint64_t n, cudaStream_t stream);
+// next-event visibility (path_visible semantics): any primitive other than d_light_prim[i] accepted by the closest-hit rules
+int cb200_launch_shadow(const cb200_accel *a, const cb_ray_t *d_rays, const float *d_max_dist, const uint2 *d_light_prim, int32_t *d_out,
+                        uint64_t n, cudaStream_t stream);

@@ -241,6 +241,7 @@ CBD V3 lerp_v(const float4 &o, const float4 &c, float t0, float t1)
 }
 
 // closest hit against one primitive record (prims_intersect, src/prims.c:638-672)
+template<bool ANALYTIC = true>
 CBD void prim_intersect(const float4 *__restrict__ rec, uint32_t rec_units, const RayD &r, HitD &h)
 {
   const float4 r0 = __ldg(rec + 0);
@@ -271,7 +272,7 @@ CBD void prim_intersect(const float4 *__restrict__ rec, uint32_t rec_units, cons
       if(tri_intersect(v0, v2, v3, id_lo, id_hi, r, h)) h.u += h.v;
     }
   }
-  else if(vcnt == CB_PRIM_SPHERE)
+  else if(ANALYTIC && vcnt == CB_PRIM_SPHERE)
   {
     const float4 r2 = __ldg(rec + 2);
     const float radius = r2.w;
@@ -289,7 +290,7 @@ CBD void prim_intersect(const float4 *__restrict__ rec, uint32_t rec_units, cons
       h.v = (float)((double)acosf(cl < 1.0f ? cl : 1.0f)/3.14159265358979323846);
     }
   }
-  else if(vcnt == CB_PRIM_LINE)
+  else if(ANALYTIC && vcnt == CB_PRIM_LINE)
   {
     const float4 r2 = __ldg(rec + 2);
     const float4 r3 = __ldg(rec + 3);
@@ -323,6 +324,7 @@ CBD void prim_intersect(const float4 *__restrict__ rec, uint32_t rec_units, cons
 }
 
 // any hit against one primitive record (prims_intersect_visible, src/prims.c:674-701)
+template<bool ANALYTIC = true>
 CBD int prim_visible(const float4 *__restrict__ rec, uint32_t rec_units, const RayD &r, float max_dist)
 {
   const float4 r0 = __ldg(rec + 0);
@@ -350,7 +352,7 @@ CBD int prim_visible(const float4 *__restrict__ rec, uint32_t rec_units, const R
     else   v3 = mk3(r3.x, r3.y, r3.z);
     return tri_visible(v0, v2, v3, r, max_dist);
   }
-  else if(vcnt == CB_PRIM_SPHERE)
+  else if(ANALYTIC && vcnt == CB_PRIM_SPHERE)
   {
     const float4 r2 = __ldg(rec + 2);
     V3 c;
@@ -359,7 +361,7 @@ CBD int prim_visible(const float4 *__restrict__ rec, uint32_t rec_units, const R
     const float t = sphere_t(c, r2.w, r);
     return (t > 0.0f && t <= max_dist) ? 1 : 0;
   }
-  else if(vcnt == CB_PRIM_LINE)
+  else if(ANALYTIC && vcnt == CB_PRIM_LINE)
   {
     const float4 r2 = __ldg(rec + 2);
     const float4 r3 = __ldg(rec + 3);

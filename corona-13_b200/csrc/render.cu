@@ -17,6 +17,7 @@
 // Scope: surfaces in vacuum / nested dielectrics, geometric lights, black sky.  Media and environment lighting
 // are SURVEY 8(f) rank 1/3.
 #include "shading.cuh"
+#include <cub/cub.cuh>
 #include <vector>
 #include <string>
 #include <cstring>
@@ -213,14 +214,39 @@ __device__ void path_start(const RenderDev &R, uint64_t index, PathState &s, V3 
   ray_pos = mk3(s.x[0], s.x[1], s.x[2]);   // sensor vertex has no primitive: no offset (pathspace.c:759-761)
 }
 
+// Wave ordering.  The reference draws the pixel of path i from its random dimensions 0/1 over the whole image
+// (thinlens.c:117-118), so consecutive path indices start at unrelated pixels and a warp's 32 camera rays share nothing.
+// The samples are a pure function of the path index, so the wave is free to process its indices in any order: sort them
+// by the Morton code of their pixel (24 bits) and neighbouring lanes trace neighbouring pixels.  Same samples, same image.
+__device__ __forceinline__ uint32_t part1by1(uint32_t x)
+{
+  x &= 0x0000ffffu;
+  x = (x | (x << 8)) & 0x00ff00ffu;
+  x = (x | (x << 4)) & 0x0f0f0f0fu;
+  x = (x | (x << 2)) & 0x33333333u;
+  x = (x | (x << 1)) & 0x55555555u;
+  return x;
+}
 __global__ void __launch_bounds__(RB)
-k_path_start(RenderDev R, uint64_t first_index, uint32_t n, PathState *st, cb_ray_t *rays, float *aux)
+k_pixel_keys(RenderDev R, uint64_t first_index, uint32_t n, uint32_t *keys, uint32_t *vals)
+{
+  const uint32_t i = blockIdx.x*blockDim.x + threadIdx.x;
+  if(i >= n) return;
+  const uint64_t index = first_index + i;
+  const float pi = point_dim(R.points, index, 0)*R.cam.width, pj = point_dim(R.points, index, 1)*R.cam.height;
+  const uint32_t x = (uint32_t)fminf(fmaxf(pi, 0.0f), R.cam.width - 1.0f), y = (uint32_t)fminf(fmaxf(pj, 0.0f), R.cam.height - 1.0f);
+  keys[i] = part1by1(x) | (part1by1(y) << 1);
+  vals[i] = i;
+}
+
+__global__ void __launch_bounds__(RB)
+k_path_start(RenderDev R, uint64_t first_index, uint32_t n, const uint32_t *__restrict__ order, PathState *st, cb_ray_t *rays, float *aux)
 {
   const uint32_t i = blockIdx.x*blockDim.x + threadIdx.x;
   if(i >= n) return;
   PathState s;
   V3 pos;
-  path_start(R, first_index + i, s, pos);
+  path_start(R, first_index + (order ? order[i] : i), s, pos);   // st / rays already point at the first free slot of the pool
   write_ray(rays, i, pos, mk3(s.omega[0], s.omega[1], s.omega[2]), s.time, 0xffffffffu, 0xffffffffu);
   if(st) st[i] = s;
   if(aux) { aux[4*i+0] = s.pixel_i; aux[4*i+1] = s.pixel_j; aux[4*i+2] = s.lambda; aux[4*i+3] = s.thr; }
@@ -265,6 +291,18 @@ __device__ void light_point(const SceneGeo &S, uint64_t pid, float r0, float r1,
   }
 }
 
+// accel_intersect's test of ONE primitive addressed through the geometry store (prims_intersect, prims.c:638-672): the same
+// vertices and the same arithmetic as the leaf records, used to find where a shadow ray first crosses its own light primitive
+__device__ void prim_test_geo(const SceneGeo &S, uint64_t pid, const RayD &r, HitD &h)
+{
+  const uint32_t vcnt = (uint32_t)(pid >> 61) & 7u;
+  if(vcnt != CB_PRIM_TRI && vcnt != CB_PRIM_QUAD) return;
+  const uint32_t id_lo = (uint32_t)pid, id_hi = (uint32_t)(pid >> 32);
+  const V3 v0 = geo_vertex_time(S, pid, 0, r.time), v1 = geo_vertex_time(S, pid, 1, r.time), v2 = geo_vertex_time(S, pid, 2, r.time);
+  if(tri_intersect(v0, v1, v2, id_lo, id_hi, r, h) || vcnt == CB_PRIM_TRI) return;
+  tri_intersect(v0, v2, geo_vertex_time(S, pid, 3, r.time), id_lo, id_hi, r, h);
+}
+
 __device__ __forceinline__ float max3abs(V3 x) { return fmaxf(fmaxf(.5f, fabsf(x.x)), fmaxf(fabsf(x.y), fabsf(x.z))); }
 
 struct ShadeCounters { unsigned long long next, nee, splats; };
@@ -279,7 +317,8 @@ __device__ __forceinline__ float cos_lambert(const Vtx &v, const Vtx &l, V3 d, f
 __global__ void __launch_bounds__(RB)
 k_shade(RenderDev R, uint32_t n, const PathState *__restrict__ st_in, const cb_ray_t *__restrict__ rays_in,
         const cb_hitrec_t *__restrict__ hits, PathState *__restrict__ st_out, cb_ray_t *__restrict__ rays_out,
-        cb_ray_t *__restrict__ nee_rays, float *__restrict__ nee_maxdist, NeeRec *__restrict__ nee_recs, ShadeCounters *cnt)
+        cb_ray_t *__restrict__ nee_rays, float *__restrict__ nee_maxdist, uint2 *__restrict__ nee_light, NeeRec *__restrict__ nee_recs,
+        ShadeCounters *cnt)
 {
   const uint32_t i = blockIdx.x*blockDim.x + threadIdx.x;
   bool alive = false, have_nee = false, did_splat = false;
@@ -406,7 +445,13 @@ k_shade(RenderDev R, uint32_t n, const PathState *__restrict__ st_in, const cb_r
                         for(int k=0;k<3;k++) { nray.pos[k] = (&rp.x)[k]; nray.dir[k] = (&rd.x)[k]; }
                         nray.time = s.time; nray.min_dist = 0.0f;
                         nray.ignore[0] = v.prim_lo; nray.ignore[1] = v.prim_hi;
-                        nmax = total_dist;
+                        // the search ends where the ray first crosses the light primitive itself (if it does before total_dist)
+                        RayD tr; HitD th;
+                        tr.px = rp.x; tr.py = rp.y; tr.pz = rp.z; tr.dx = rd.x; tr.dy = rd.y; tr.dz = rd.z;
+                        tr.time = s.time; tr.min_dist = 0.0f; tr.ign_lo = v.prim_lo; tr.ign_hi = v.prim_hi;
+                        th.dist = total_dist; th.u = th.v = 0.0f; th.prim_lo = th.prim_hi = 0xffffffffu;
+                        prim_test_geo(R.geo, lpid, tr, th);
+                        nmax = th.dist;
                         nrec.value = thr_l*w; nrec.lambda = s.lambda; nrec.pixel_i = s.pixel_i; nrec.pixel_j = s.pixel_j;
                         nrec.total_dist = total_dist; nrec.light_lo = l.prim_lo; nrec.light_hi = l.prim_hi; nrec.pad = 0;
                       }
@@ -484,24 +529,21 @@ k_shade(RenderDev R, uint32_t n, const PathState *__restrict__ st_in, const cb_r
     if(have_nee)
     {
       const uint64_t o = base + __popc(mn & ((1u << lane) - 1u));
-      nee_rays[o] = nray; nee_maxdist[o] = nmax; nee_recs[o] = nrec;
+      nee_rays[o] = nray; nee_maxdist[o] = nmax; nee_recs[o] = nrec; nee_light[o] = make_uint2(nrec.light_lo, nrec.light_hi);
     }
   }
 }
 
 // path_visible's decision (pathspace.c:325-331) + the splat of ptdl.c:146
 __global__ void __launch_bounds__(RB)
-k_nee_resolve(RenderDev R, uint32_t n, const NeeRec *__restrict__ recs, const cb_hitrec_t *__restrict__ hits, ShadeCounters *cnt)
+k_nee_resolve(RenderDev R, uint32_t n, const NeeRec *__restrict__ recs, const int32_t *__restrict__ vis, ShadeCounters *cnt)
 {
   const uint32_t i = blockIdx.x*blockDim.x + threadIdx.x;
   bool did = false;
-  if(i < n)
+  if(i < n && vis[i])
   {
     const NeeRec r = recs[i];
-    const cb_hitrec_t h = hits[i];
-    const bool none = (h.prim[0] & h.prim[1]) == 0xffffffffu;
-    const bool visible = none || h.dist >= r.total_dist || (h.prim[0] == r.light_lo && h.prim[1] == r.light_hi);
-    if(visible) did = splat(R, r.pixel_i, r.pixel_j, r.lambda, r.value);
+    did = splat(R, r.pixel_i, r.pixel_j, r.lambda, r.value);
   }
   const uint32_t m = __ballot_sync(0xffffffffu, did);
   if(m && (threadIdx.x & 31u) == 0) atomicAdd(&cnt->splats, (unsigned long long)__popc(m));
@@ -561,9 +603,40 @@ struct cb200_render
   PathState *st[2];
   cb_ray_t *rays[2];
   cb_hitrec_t *hits;
-  cb_ray_t *nee_rays; float *nee_md; NeeRec *nee_recs; cb_hitrec_t *nee_hits;
+  cb_ray_t *nee_rays; float *nee_md; NeeRec *nee_recs; uint2 *nee_light; int32_t *nee_vis;
   ShadeCounters *d_cnt, *h_cnt;
   cb_render_stats_t stats;
+  // wave ordering by pixel (k_pixel_keys + radix sort)
+  uint32_t *keys[2], *order[2];
+  void *sort_tmp; size_t sort_tmp_bytes;
+  // streaming wavefront: paths still alive when a pass has started all of its indices stay in the pool
+  // (st[cur] / rays[cur], slots [0, n_alive)) and ride along with the next pass' waves until cb200_render_flush
+  uint32_t n_alive; int cur;
+  // instrumentation (cb200_render_instrument): CUDA events around every launch on the pass' own stream, summed per
+  // kernel class after the pass; ACCEL_DEBUG-style traversal counters
+  int timing, counting;
+  std::vector<cudaEvent_t> ev_pool;
+  std::vector<int> ev_class;
+  std::vector<uint32_t> ev_n;      // rays / paths the launch worked on (CB200_RENDER_TRACE)
+  size_t ev_used;
+  unsigned long long *d_trav_cnt;   // [0..3] closest waves, [4..7] shadow waves
+};
+
+enum { KC_START = 0, KC_CLOSEST = 1, KC_SHADE = 2, KC_SHADOW = 3, KC_RESOLVE = 4, KC_NUM = 5 };
+
+struct TimeScope   // records an event pair around the launches of one kernel class
+{
+  cb200_render *r; cudaStream_t st; size_t slot;
+  TimeScope(cb200_render *r_, cudaStream_t st_, int cls, uint32_t n = 0) : r(r_), st(st_), slot(0)
+  {
+    if(!r->timing) return;
+    if(r->ev_used + 2 > r->ev_pool.size())
+      for(int k=0;k<2;k++) { cudaEvent_t e; cudaEventCreate(&e); r->ev_pool.push_back(e); r->ev_class.push_back(0); r->ev_n.push_back(0); }
+    slot = r->ev_used; r->ev_used += 2;
+    r->ev_class[slot] = cls; r->ev_n[slot] = n;
+    cudaEventRecord(r->ev_pool[slot], st);
+  }
+  ~TimeScope() { if(r->timing) cudaEventRecord(r->ev_pool[slot+1], st); }
 };
 
 template<typename T> static T *dev_upload(cb200_render *r, const T *src, size_t count)
@@ -704,6 +777,7 @@ void cb200_render_destroy(cb200_render_t *r)
 {
   if(!r) return;
   for(void *p : r->owned) cudaFree(p);
+  for(cudaEvent_t e : r->ev_pool) cudaEventDestroy(e);
   if(r->h_cnt) cudaFreeHost(r->h_cnt);
   delete r;
 }
@@ -730,6 +804,8 @@ cb200_render_t *cb200_render_create(cb200_accel_t *a, const cb_render_desc_t *de
   r->desc = *desc;
   memset(&r->stats, 0, sizeof(r->stats));
   r->h_cnt = nullptr;
+  r->timing = r->counting = 0; r->ev_used = 0; r->d_trav_cnt = nullptr;
+  r->n_alive = 0; r->cur = 0;
   cb200_scene *s = a->scene;
   RenderDev &D = r->dev;
   memset(&D, 0, sizeof(D));
@@ -762,14 +838,30 @@ cb200_render_t *cb200_render_create(cb200_accel_t *a, const cb_render_desc_t *de
   ok = ok && build_halton(r, desc->frame) == 0;
   if(ok && build_lights(r)) { cb200_render_destroy(r); return nullptr; }
   // wave buffers
-  r->batch = desc->batch_paths ? desc->batch_paths : (1ull << 22);
+  r->batch = desc->batch_paths;
+  if(!r->batch)
+  { // default: one wave per progression (W*H paths, view.c:636-638), at most 2^23 (covers a padded 4K frame, 3840 x 2176)
+    r->batch = (uint64_t)desc->width*desc->height;
+    if(r->batch > (1ull << 23)) r->batch = 1ull << 23;
+    if(r->batch < 65536) r->batch = 65536;
+  }
   const uint64_t N = r->batch;
   D.fb = dev_alloc<float>(r, (size_t)desc->width*desc->height*3);
   for(int k=0;k<2;k++) { r->st[k] = dev_alloc<PathState>(r, N); r->rays[k] = dev_alloc<cb_ray_t>(r, N); ok = ok && r->st[k] && r->rays[k]; }
   r->hits = dev_alloc<cb_hitrec_t>(r, N);
-  r->nee_rays = dev_alloc<cb_ray_t>(r, N); r->nee_md = dev_alloc<float>(r, N); r->nee_recs = dev_alloc<NeeRec>(r, N); r->nee_hits = dev_alloc<cb_hitrec_t>(r, N);
+  r->nee_rays = dev_alloc<cb_ray_t>(r, N); r->nee_md = dev_alloc<float>(r, N); r->nee_recs = dev_alloc<NeeRec>(r, N); r->nee_light = dev_alloc<uint2>(r, N); r->nee_vis = dev_alloc<int32_t>(r, N);
   r->d_cnt = dev_alloc<ShadeCounters>(r, 1);
-  ok = ok && D.fb && r->hits && r->nee_rays && r->nee_md && r->nee_recs && r->nee_hits && r->d_cnt;
+  for(int k=0;k<2;k++) { r->keys[k] = dev_alloc<uint32_t>(r, N); r->order[k] = dev_alloc<uint32_t>(r, N); ok = ok && r->keys[k] && r->order[k]; }
+  r->sort_tmp = nullptr; r->sort_tmp_bytes = 0;
+  if(ok)
+  {
+    cub::DeviceRadixSort::SortPairs(nullptr, r->sort_tmp_bytes, r->keys[0], r->keys[1], r->order[0], r->order[1], (int)N, 0, 24);
+    r->sort_tmp = dev_alloc<uint8_t>(r, r->sort_tmp_bytes);
+    ok = ok && r->sort_tmp;
+  }
+  r->d_trav_cnt = dev_alloc<unsigned long long>(r, 8);
+  if(r->d_trav_cnt) cudaMemset(r->d_trav_cnt, 0, 8*sizeof(unsigned long long));
+  ok = ok && r->d_trav_cnt && D.fb && r->hits && r->nee_rays && r->nee_md && r->nee_recs && r->nee_light && r->nee_vis && r->d_cnt;
   ok = ok && cudaMallocHost(&r->h_cnt, sizeof(ShadeCounters)) == cudaSuccess;
   if(!ok)
   {
@@ -787,6 +879,8 @@ int cb200_render_clear(cb200_render_t *r, void *stream)
   if(!r) { cb200_set_error("render_clear: null"); return CB200_ERR_ARG; }
   CB_CUDA(cudaMemsetAsync(r->dev.fb, 0, (size_t)r->dev.fb_w*r->dev.fb_h*3*sizeof(float), (cudaStream_t)stream));
   CB_CUDA(cudaMemsetAsync(r->d_cnt, 0, sizeof(ShadeCounters), (cudaStream_t)stream));
+  CB_CUDA(cudaMemsetAsync(r->d_trav_cnt, 0, 8*sizeof(unsigned long long), (cudaStream_t)stream));
+  r->n_alive = 0;   // paths still in flight are dropped with the image they belong to
   memset(&r->stats, 0, sizeof(r->stats));
   return 0;
 }
@@ -796,6 +890,7 @@ void *cb200_render_fb_device(cb200_render_t *r) { return r ? r->dev.fb : nullptr
 int cb200_render_download(cb200_render_t *r, float *fb_host, void *stream)
 {
   if(!r || !fb_host) { cb200_set_error("render_download: bad arguments"); return CB200_ERR_ARG; }
+  if(r->n_alive) { const int rc = cb200_render_flush(r, stream); if(rc) return rc; }
   CB_CUDA(cudaMemcpyAsync(fb_host, r->dev.fb, (size_t)r->dev.fb_w*r->dev.fb_h*3*sizeof(float), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
   CB_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
   return 0;
@@ -808,46 +903,122 @@ int cb200_render_stats(cb200_render_t *r, cb_render_stats_t *out)
   return 0;
 }
 
-int cb200_render_pass(cb200_render_t *r, uint64_t first_index, uint64_t count, void *stream_)
+int cb200_render_instrument(cb200_render_t *r, int timing, int counters)
 {
-  if(!r) { cb200_set_error("render_pass: null"); return CB200_ERR_ARG; }
-  cudaStream_t st = (cudaStream_t)stream_;
-  for(uint64_t off=0; off<count; off+=r->batch)
+  if(!r) { cb200_set_error("render_instrument: null"); return CB200_ERR_ARG; }
+  r->timing = timing ? 1 : 0;
+  r->counting = counters ? 1 : 0;
+  return 0;
+}
+
+// One wave of the pool: trace every path's pending ray, shade, trace and resolve the next-event rays.
+static int render_wave(cb200_render *r, uint32_t n, cudaStream_t st)
+{
+  const int cur = r->cur;
+  int rc;
   {
-    uint32_t n = (uint32_t)((count - off) < r->batch ? (count - off) : r->batch);
-    k_path_start<<<(n + RB - 1)/RB, RB, 0, st>>>(r->dev, first_index + off, n, r->st[0], r->rays[0], nullptr);
-    cb200_count_launch(); r->stats.kernel_launches++;
-    r->stats.paths += n;
-    int cur = 0;
-    for(int bounce=0; bounce<32 && n>0; bounce++)
-    {
-      int rc = cb200_launch_intersect(r->accel, r->rays[cur], nullptr, r->hits, n, st, nullptr);
-      if(rc) return rc;
-      r->stats.rays_closest += n; r->stats.kernel_launches++;
-      CB_CUDA(cudaMemsetAsync(r->d_cnt, 0, 2*sizeof(unsigned long long), st));   // next, nee (splats keeps counting)
-      k_shade<<<(n + RB - 1)/RB, RB, 0, st>>>(r->dev, n, r->st[cur], r->rays[cur], r->hits, r->st[cur^1], r->rays[cur^1],
-                                              r->nee_rays, r->nee_md, r->nee_recs, r->d_cnt);
-      cb200_count_launch(); r->stats.kernel_launches++;
-      CB_CUDA(cudaMemcpyAsync(r->h_cnt, r->d_cnt, sizeof(ShadeCounters), cudaMemcpyDeviceToHost, st));
-      CB_CUDA(cudaStreamSynchronize(st));
-      const uint32_t n_next = (uint32_t)r->h_cnt->next, n_nee = (uint32_t)r->h_cnt->nee;
-      if(n_nee)
-      {
-        rc = cb200_launch_intersect(r->accel, r->nee_rays, r->nee_md, r->nee_hits, n_nee, st, nullptr);
-        if(rc) return rc;
-        k_nee_resolve<<<(n_nee + RB - 1)/RB, RB, 0, st>>>(r->dev, n_nee, r->nee_recs, r->nee_hits, r->d_cnt);
-        cb200_count_launch(); r->stats.kernel_launches += 2;
-        r->stats.rays_shadow += n_nee;
-      }
-      n = n_next;
-      cur ^= 1;
-    }
+    TimeScope ts(r, st, KC_CLOSEST, n);
+    rc = cb200_launch_intersect(r->accel, r->rays[cur], nullptr, r->hits, n, st, r->counting ? r->d_trav_cnt : nullptr);
   }
+  if(rc) return rc;
+  r->stats.rays_closest += n; r->stats.kernel_launches++;
+  CB_CUDA(cudaMemsetAsync(r->d_cnt, 0, 2*sizeof(unsigned long long), st));   // next, nee (splats keeps counting)
+  {
+    TimeScope ts(r, st, KC_SHADE, n);
+    k_shade<<<(n + RB - 1)/RB, RB, 0, st>>>(r->dev, n, r->st[cur], r->rays[cur], r->hits, r->st[cur^1], r->rays[cur^1],
+                                            r->nee_rays, r->nee_md, r->nee_light, r->nee_recs, r->d_cnt);
+  }
+  cb200_count_launch(); r->stats.kernel_launches++;
+  CB_CUDA(cudaMemcpyAsync(r->h_cnt, r->d_cnt, sizeof(ShadeCounters), cudaMemcpyDeviceToHost, st));
+  CB_CUDA(cudaStreamSynchronize(st));
+  const uint32_t n_next = (uint32_t)r->h_cnt->next, n_nee = (uint32_t)r->h_cnt->nee;
+  if(n_nee)
+  {
+    {
+      TimeScope ts(r, st, KC_SHADOW, n_nee);
+      rc = cb200_launch_shadow(r->accel, r->nee_rays, r->nee_md, r->nee_light, r->nee_vis, n_nee, st);
+    }
+    if(rc) return rc;
+    {
+      TimeScope ts(r, st, KC_RESOLVE, n_nee);
+      k_nee_resolve<<<(n_nee + RB - 1)/RB, RB, 0, st>>>(r->dev, n_nee, r->nee_recs, r->nee_vis, r->d_cnt);
+    }
+    cb200_count_launch(2); r->stats.kernel_launches += 2;
+    r->stats.rays_shadow += n_nee;
+  }
+  r->n_alive = n_next;
+  r->cur = cur ^ 1;
+  return 0;
+}
+
+static int render_collect(cb200_render *r, cudaStream_t st)
+{
   CB_CUDA(cudaMemcpyAsync(r->h_cnt, r->d_cnt, sizeof(ShadeCounters), cudaMemcpyDeviceToHost, st));
   CB_CUDA(cudaStreamSynchronize(st));
   r->stats.splats = r->h_cnt->splats;
+  if(r->timing)
+    for(size_t k=0;k+1<r->ev_used;k+=2)
+    {
+      float ms = 0.0f;
+      if(cudaEventElapsedTime(&ms, r->ev_pool[k], r->ev_pool[k+1]) == cudaSuccess) r->stats.ms[r->ev_class[k]] += ms;
+      if(getenv("CB200_RENDER_TRACE")) fprintf(stderr, "[cb200 trace] class %d n %u ms %.3f -> %.1f M/s\n", r->ev_class[k], r->ev_n[k], ms, r->ev_n[k]/(ms*1e3));
+    }
+  r->ev_used = 0;
+  if(r->counting)
+  {
+    unsigned long long c[8];
+    CB_CUDA(cudaMemcpy(c, r->d_trav_cnt, sizeof(c), cudaMemcpyDeviceToHost));
+    for(int k=0;k<4;k++) { r->stats.trav_closest[k] = c[k]; r->stats.trav_shadow[k] = c[4+k]; }
+  }
   CB_CUDA(cudaGetLastError());
   return 0;
+}
+
+int cb200_render_pass_stream(cb200_render_t *r, uint64_t first_index, uint64_t count, void *stream_)
+{
+  if(!r) { cb200_set_error("render_pass: null"); return CB200_ERR_ARG; }
+  cudaStream_t st = (cudaStream_t)stream_;
+  const uint32_t N = (uint32_t)r->batch;
+  uint64_t started = 0;
+  while(started < count)
+  {
+    // top the pool up with new paths behind the survivors of the previous wave
+    const uint32_t room = N - r->n_alive;
+    const uint32_t n_new = (uint32_t)((count - started) < room ? (count - started) : room);
+    if(n_new)
+    {
+      TimeScope ts(r, st, KC_START, n_new);
+      k_pixel_keys<<<(n_new + RB - 1)/RB, RB, 0, st>>>(r->dev, first_index + started, n_new, r->keys[0], r->order[0]);
+      size_t tmp = r->sort_tmp_bytes;
+      CB_CUDA(cub::DeviceRadixSort::SortPairs(r->sort_tmp, tmp, r->keys[0], r->keys[1], r->order[0], r->order[1], (int)n_new, 0, 24, st));
+      k_path_start<<<(n_new + RB - 1)/RB, RB, 0, st>>>(r->dev, first_index + started, n_new, r->order[1],
+                                                        r->st[r->cur] + r->n_alive, r->rays[r->cur] + r->n_alive, nullptr);
+      cb200_count_launch(5); r->stats.kernel_launches += 5;   // keys, radix sort (histogram + digit passes, counted as 3), path start
+      r->stats.paths += n_new;
+      started += n_new;
+    }
+    const int rc = render_wave(r, r->n_alive + n_new, st);
+    if(rc) return rc;
+  }
+  return render_collect(r, st);
+}
+
+int cb200_render_flush(cb200_render_t *r, void *stream_)
+{
+  if(!r) { cb200_set_error("render_flush: null"); return CB200_ERR_ARG; }
+  cudaStream_t st = (cudaStream_t)stream_;
+  for(int guard=0; r->n_alive && guard<64; guard++)
+  {
+    const int rc = render_wave(r, r->n_alive, st);
+    if(rc) return rc;
+  }
+  return render_collect(r, st);
+}
+
+int cb200_render_pass(cb200_render_t *r, uint64_t first_index, uint64_t count, void *stream)
+{
+  const int rc = cb200_render_pass_stream(r, first_index, count, stream);
+  return rc ? rc : cb200_render_flush(r, stream);
 }
 
 int cb200_render_point(cb200_render_t *r, const uint64_t *index, const int32_t *dim, float *out, uint64_t n)
@@ -869,7 +1040,7 @@ int cb200_render_camera_rays(cb200_render_t *r, uint64_t first_index, uint64_t n
   if(!r || !out_rays || n > r->batch) { cb200_set_error("render_camera_rays: bad arguments (n must be <= batch_paths)"); return CB200_ERR_ARG; }
   float *d_aux = nullptr;
   CB_CUDA(cudaMalloc(&d_aux, n*16 + 16));
-  if(n) k_path_start<<<(unsigned)((n + RB - 1)/RB), RB>>>(r->dev, first_index, (uint32_t)n, nullptr, r->rays[0], d_aux);
+  if(n) k_path_start<<<(unsigned)((n + RB - 1)/RB), RB>>>(r->dev, first_index, (uint32_t)n, nullptr, nullptr, r->rays[0], d_aux);
   cb200_count_launch();
   CB_CUDA(cudaMemcpy(out_rays, r->rays[0], n*sizeof(cb_ray_t), cudaMemcpyDeviceToHost));
   if(out_aux) CB_CUDA(cudaMemcpy(out_aux, d_aux, n*16, cudaMemcpyDeviceToHost));

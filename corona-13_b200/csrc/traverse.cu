@@ -125,15 +125,46 @@ __device__ __forceinline__ bool is_empty_leaf(uint64_t c) { return (c & CB_LEAF_
 #define SEL4(arr, i) ((i) == 0 ? arr[0] : (i) == 1 ? arr[1] : (i) == 2 ? arr[2] : arr[3])
 
 enum { ST_IDLE = 0, ST_NODE = 1, ST_PRIM = 2 };
+#define KEY_MISS __int_as_float(0x7fc00000)
+#define KEY_HIT(k) ((k) == (k))
+
+// Fast slab test for static nodes and rays whose direction components are all finite and non-zero: the near / far plane
+// of every axis is picked by the ray's sign when the row is LOADED (rows 0..2 = min, 3..5 = max of Node128::aabb0), so that
+// lo <= hi holds by monotonicity of IEEE subtraction and multiplication and min(lo,hi) / max(lo,hi) of the reference
+// (qbvhmp.c:1222-1223) need not be computed: identical tmin, tmax and hit mask for every non-empty box.  (An inverted, empty
+// box "hits" in the reference and misses here; empty leaves are never visited either way.)
+// key[c] = entry distance when child c is hit, NaN otherwise (a hit implies tmin <= tmax, so tmin is never NaN itself;
+// it CAN be negative for rays with NaN slab products, where the reference's select semantics drop the clip at 0).
+__device__ __forceinline__ void node_slabs_fast(const Node128 *__restrict__ n, const uint32_t near_off[3], float px, float py, float pz,
+                                                float ix, float iy, float iz, float tmax_init, float key[4])
+{
+  const float4 *a0 = reinterpret_cast<const float4 *>(n->aabb0);
+  const float4 nx = __ldg(a0 + near_off[0]),     ny = __ldg(a0 + 1 + near_off[1]),     nz = __ldg(a0 + 2 + near_off[2]);
+  const float4 fx = __ldg(a0 + 3 - near_off[0]), fy = __ldg(a0 + 4 - near_off[1]),     fz = __ldg(a0 + 5 - near_off[2]);
+  const float nxa[4] = {nx.x, nx.y, nx.z, nx.w}, nya[4] = {ny.x, ny.y, ny.z, ny.w}, nza[4] = {nz.x, nz.y, nz.z, nz.w};
+  const float fxa[4] = {fx.x, fx.y, fx.z, fx.w}, fya[4] = {fy.x, fy.y, fy.z, fy.w}, fza[4] = {fz.x, fz.y, fz.z, fz.w};
+#pragma unroll
+  for(int c=0;c<4;c++)
+  {
+    const float tmin = fmaxf(fmaxf(0.0f, (nxa[c] - px)*ix), fmaxf((nya[c] - py)*iy, (nza[c] - pz)*iz));
+    const float tmax = fminf(fminf(tmax_init, (fxa[c] - px)*ix), fminf((fya[c] - py)*iy, (fza[c] - pz)*iz));
+    key[c] = tmin <= tmax ? tmin : KEY_MISS;
+  }
+}
+
+#define CSWAP(cond, ka, ca, kb, cb) do { const float tk__ = ka; const uint64_t tc__ = ca; \
+  ka = (cond) ? kb : ka; ca = (cond) ? cb : ca; kb = (cond) ? tk__ : kb; cb = (cond) ? tc__ : cb; } while(0)
 
 // ---------------------------------------------------------------------------------------------
 // closest hit
+//   ANALYTIC: the scene has spheres / cylinders / cones (their tests carry double precision and libm calls; scenes
+//             without them get a kernel without that code and with fewer registers)
 // ---------------------------------------------------------------------------------------------
-template<bool MB, bool CNT, int STACK>
+template<bool MB, bool CNT, int STACK, bool ANALYTIC>
 __global__ void __launch_bounds__(TRACE_BLOCK)
 k_intersect(DevAccel A, const cb_ray_t *__restrict__ rays, const float *__restrict__ max_dist,
             cb_hitrec_t *__restrict__ out, uint64_t n, unsigned long long *ticket, unsigned long long *counters,
-            int prim_threshold)
+            int prim_threshold, int refill_threshold)
 {
   const uint32_t lane = threadIdx.x & 31u;
   const uint32_t lt_mask = (1u << lane) - 1u;
@@ -148,6 +179,7 @@ k_intersect(DevAccel A, const cb_ray_t *__restrict__ rays, const float *__restri
   uint64_t ray_i = 0, cur = 0;
   float ix = 0.0f, iy = 0.0f, iz = 0.0f, t0 = 1.0f, t1 = 0.0f;
   uint32_t nearbits = 0;
+  uint32_t near_off[3] = {0, 0, 0};
   bool exact = false;
   const float4 *rec = nullptr;
   uint32_t prims_left = 0;
@@ -157,9 +189,10 @@ k_intersect(DevAccel A, const cb_ray_t *__restrict__ rays, const float *__restri
 
   while(true)
   {
-    // ---- refill idle lanes from the global ray queue
+    // ---- refill idle lanes from the global ray queue, but only once enough of them have gathered (or nothing else is
+    //      left to do): the fetch code would otherwise run on nearly every iteration for one or two lanes
     const uint32_t idle = __ballot_sync(FULL, state == ST_IDLE);
-    if(idle && !exhausted)
+    if(idle && !exhausted && (__popc(idle) >= refill_threshold || idle == FULL))
     {
       const uint32_t want = __popc(idle);
       unsigned long long base = 0;
@@ -176,6 +209,7 @@ k_intersect(DevAccel A, const cb_ray_t *__restrict__ rays, const float *__restri
           h.dist = max_dist ? __ldg(max_dist + i) : FLT_MAX;
           h.u = 0.0f; h.v = 0.0f; h.prim_lo = 0xffffffffu; h.prim_hi = 0xffffffffu;
           nearbits = (__float_as_uint(r.dx) >> 31) | ((__float_as_uint(r.dy) >> 31) << 1) | ((__float_as_uint(r.dz) >> 31) << 2);
+          near_off[0] = 3u*(nearbits & 1u); near_off[1] = 3u*((nearbits >> 1) & 1u); near_off[2] = 3u*(nearbits >> 2);
           ix = 1.0f/r.dx; iy = 1.0f/r.dy; iz = 1.0f/r.dz;
           t1 = r.time; t0 = 1.0f - r.time;
           exact = !(finite_nonzero(ix) && finite_nonzero(iy) && finite_nonzero(iz) &&
@@ -187,55 +221,70 @@ k_intersect(DevAccel A, const cb_ray_t *__restrict__ rays, const float *__restri
     }
     const uint32_t mN = __ballot_sync(FULL, state == ST_NODE);
     const uint32_t mP = __ballot_sync(FULL, state == ST_PRIM);
-    if(!(mN | mP)) break;
+    if(!(mN | mP)) break;   // nothing in flight: the refill above ran (all lanes idle) and the queue is empty
     const bool do_prims = (mN == 0u) || (__popc(mP) >= prim_threshold);
 
     bool need_pop = false, new_cur = false;
     if(do_prims)
     {
       if(state == ST_PRIM)
-      {
-        if(CNT) cnt[3]++;
-        prim_intersect(rec, A.rec_units, r, h);
-        rec += rec_stride;
-        if(--prims_left == 0) need_pop = true;
+      { // the whole leaf in primid[] order (qbvhmp.c:1371-1379)
+        do
+        {
+          if(CNT) cnt[3]++;
+          prim_intersect<ANALYTIC>(rec, A.rec_units, r, h);
+          rec += rec_stride;
+        }
+        while(--prims_left);
+        need_pop = true;
       }
     }
     else if(state == ST_NODE)
     {
-      NodeOut o;
-      if(exact) node_slabs<MB, true >(A.nodes, cur, r.px, r.py, r.pz, ix, iy, iz, t0, t1, h.dist, o);
-      else      node_slabs<MB, false>(A.nodes, cur, r.px, r.py, r.pz, ix, iy, iz, t0, t1, h.dist, o);
-      const bool any = o.hit[0] | o.hit[1] | o.hit[2] | o.hit[3];
-      need_pop = true;
-      if(any)
+      float key[4];
+      uint64_t child[4];
+      int axis0, axis00, axis01;
+      if(MB || CNT || exact)
       {
-        if(CNT) { cnt[1]++; for(int c=0;c<4;c++) cnt[2] += o.hit[c] ? 1 : 0; }
-        // empty leaves (count 0) can only be popped and dropped again: never visit them
+        NodeOut o;
+        if(exact) node_slabs<MB, true >(A.nodes, cur, r.px, r.py, r.pz, ix, iy, iz, t0, t1, h.dist, o);
+        else      node_slabs<MB, false>(A.nodes, cur, r.px, r.py, r.pz, ix, iy, iz, t0, t1, h.dist, o);
+        if(CNT && (o.hit[0] | o.hit[1] | o.hit[2] | o.hit[3])) { cnt[1]++; for(int c=0;c<4;c++) cnt[2] += o.hit[c] ? 1 : 0; }
 #pragma unroll
-        for(int c=0;c<4;c++) if(is_empty_leaf(o.child[c])) o.hit[c] = false;
-        const uint32_t n0 = (nearbits >> o.axis0) & 1u;
-        const int axis1n = n0 ? o.axis01 : o.axis00;
-        const int axis1f = n0 ? o.axis00 : o.axis01;
-        const uint32_t n1n = (nearbits >> axis1n) & 1u, n1f = (nearbits >> axis1f) & 1u;
-        const uint32_t f0 = n0 ^ 1u;
-        const uint32_t n11 = (f0 << 1) | (n1f ^ 1u);
-        const uint32_t n10 = (f0 << 1) | n1f;
-        const uint32_t n01 = (n0 << 1) | (n1n ^ 1u);
-        const uint32_t n00 = (n0 << 1) | n1n;
-        const bool h00 = SEL4(o.hit, n00), h01 = SEL4(o.hit, n01), h10 = SEL4(o.hit, n10), h11 = SEL4(o.hit, n11);
-        // far -> near push order: n11, n10, n01; the nearest hit child becomes current
-        const int first = h00 ? 0 : h01 ? 1 : h10 ? 2 : h11 ? 3 : 4;
-        if(first < 4)
-        {
-          if(h11 && first < 3) { stack_dist[sp] = SEL4(o.tmin, n11); stack[sp++] = SEL4(o.child, n11); }
-          if(h10 && first < 2) { stack_dist[sp] = SEL4(o.tmin, n10); stack[sp++] = SEL4(o.child, n10); }
-          if(h01 && first < 1) { stack_dist[sp] = SEL4(o.tmin, n01); stack[sp++] = SEL4(o.child, n01); }
-          const uint32_t nf = first == 0 ? n00 : first == 1 ? n01 : first == 2 ? n10 : n11;
-          cur = SEL4(o.child, nf);
-          need_pop = false;
-          new_cur = true;
-        }
+        for(int c=0;c<4;c++) { key[c] = o.hit[c] ? o.tmin[c] : KEY_MISS; child[c] = o.child[c]; }
+        axis0 = o.axis0; axis00 = o.axis00; axis01 = o.axis01;
+      }
+      else
+      {
+        const Node128 *nd = reinterpret_cast<const Node128 *>(A.nodes) + cur;
+        node_slabs_fast(nd, near_off, r.px, r.py, r.pz, ix, iy, iz, h.dist, key);
+        const ulonglong2 *ch = reinterpret_cast<const ulonglong2 *>(nd->child);
+        const ulonglong2 c01 = __ldg(ch), c23 = __ldg(ch + 1);
+        const uint32_t ax = (uint32_t)(c01.x >> CB_AXIS_SHIFT) & 63u;
+        child[0] = c01.x & CB_CHILD_MASK; child[1] = c01.y; child[2] = c23.x; child[3] = c23.y;
+        axis0 = ax & 3; axis00 = (ax >> 2) & 3; axis01 = (ax >> 4) & 3;
+      }
+      // empty leaves (count 0) can only be popped and dropped again: never visit them
+#pragma unroll
+      for(int c=0;c<4;c++) if(is_empty_leaf(child[c])) key[c] = KEY_MISS;
+      // the reference's topological order (qbvhmp.c:1313-1320) as three conditional swaps: inside the lower pair by the
+      // sign along axis00, inside the upper pair by the sign along axis01, the two pairs by the sign along axis0
+      const bool s00 = (nearbits >> axis00) & 1u, s01 = (nearbits >> axis01) & 1u, s0 = (nearbits >> axis0) & 1u;
+      CSWAP(s00, key[0], child[0], key[1], child[1]);
+      CSWAP(s01, key[2], child[2], key[3], child[3]);
+      CSWAP(s0,  key[0], child[0], key[2], child[2]);
+      CSWAP(s0,  key[1], child[1], key[3], child[3]);
+      // nearest hit child becomes current, the others are pushed far -> near with their entry distance
+      need_pop = true;
+      const int first = KEY_HIT(key[0]) ? 0 : KEY_HIT(key[1]) ? 1 : KEY_HIT(key[2]) ? 2 : KEY_HIT(key[3]) ? 3 : 4;
+      if(first < 4)
+      {
+        if(KEY_HIT(key[3]) && first < 3) { stack_dist[sp] = key[3]; stack[sp++] = child[3]; }
+        if(KEY_HIT(key[2]) && first < 2) { stack_dist[sp] = key[2]; stack[sp++] = child[2]; }
+        if(KEY_HIT(key[1]) && first < 1) { stack_dist[sp] = key[1]; stack[sp++] = child[1]; }
+        cur = first == 0 ? child[0] : first == 1 ? child[1] : first == 2 ? child[2] : child[3];
+        need_pop = false;
+        new_cur = true;
       }
     }
     if(need_pop)
@@ -276,10 +325,15 @@ k_intersect(DevAccel A, const cb_ray_t *__restrict__ rays, const float *__restri
 // any hit: returns 1 when nothing blocks the ray up to max_dist (accel_visible semantics; the result
 // is a boolean, so visiting order is free)
 // ---------------------------------------------------------------------------------------------
-template<bool MB, int STACK>
+//   SHADOW: next-event visibility in path_visible's terms (src/pathspace.c:311-344), which asks accel_intersect -- not
+//           accel_visible -- whether anything lies in front of the light: primitives are tested with the CLOSEST-hit rules
+//           (ray.ignore honoured, dist > min_dist && dist <= limit, strict < for analytic prims) and the sampled light
+//           primitive skip[i] never occludes.  The caller has already clipped max_dist to the first crossing of the light
+//           primitive itself, so "any accepted primitive" == "the closest hit is not the light".
+template<bool MB, int STACK, bool ANALYTIC, bool SHADOW>
 __global__ void __launch_bounds__(TRACE_BLOCK)
-k_visible(DevAccel A, const cb_ray_t *__restrict__ rays, const float *__restrict__ max_dist,
-          int32_t *__restrict__ out, uint64_t n, unsigned long long *ticket, int prim_threshold)
+k_visible(DevAccel A, const cb_ray_t *__restrict__ rays, const float *__restrict__ max_dist, const uint2 *__restrict__ skip,
+          int32_t *__restrict__ out, uint64_t n, unsigned long long *ticket, int prim_threshold, int refill_threshold)
 {
   const uint32_t lane = threadIdx.x & 31u;
   const uint32_t lt_mask = (1u << lane) - 1u;
@@ -290,16 +344,18 @@ k_visible(DevAccel A, const cb_ray_t *__restrict__ rays, const float *__restrict
   RayD r;
   uint64_t ray_i = 0, cur = 0;
   float ix = 0.0f, iy = 0.0f, iz = 0.0f, t0 = 1.0f, t1 = 0.0f, md = 0.0f;
+  uint32_t near_off[3] = {0, 0, 0};
   bool exact = false;
   const float4 *rec = nullptr;
   uint32_t prims_left = 0;
+  uint2 skip_id = make_uint2(0xffffffffu, 0xffffffffu);
   const uint32_t rec_stride = A.rec_units*4;
   r.px = r.py = r.pz = r.dx = r.dy = r.dz = r.time = r.min_dist = 0.0f; r.ign_lo = r.ign_hi = 0;
 
   while(true)
   {
     const uint32_t idle = __ballot_sync(FULL, state == ST_IDLE);
-    if(idle && !exhausted)
+    if(idle && !exhausted && (__popc(idle) >= refill_threshold || idle == FULL))
     {
       const uint32_t want = __popc(idle);
       unsigned long long base = 0;
@@ -314,6 +370,9 @@ k_visible(DevAccel A, const cb_ray_t *__restrict__ rays, const float *__restrict
           load_ray(rays, i, r);
           ray_i = i;
           md = __ldg(max_dist + i);
+          if(SHADOW) skip_id = __ldg(skip + i);
+          const uint32_t nearbits = (__float_as_uint(r.dx) >> 31) | ((__float_as_uint(r.dy) >> 31) << 1) | ((__float_as_uint(r.dz) >> 31) << 2);
+          near_off[0] = 3u*(nearbits & 1u); near_off[1] = 3u*((nearbits >> 1) & 1u); near_off[2] = 3u*(nearbits >> 2);
           ix = 1.0f/r.dx; iy = 1.0f/r.dy; iz = 1.0f/r.dz;
           t1 = r.time; t0 = 1.0f - r.time;
           exact = !(finite_nonzero(ix) && finite_nonzero(iy) && finite_nonzero(iz) &&
@@ -332,18 +391,43 @@ k_visible(DevAccel A, const cb_ray_t *__restrict__ rays, const float *__restrict
     {
       if(state == ST_PRIM)
       {
-        if(prim_visible(rec, A.rec_units, r, md)) result = 0;
-        rec += rec_stride;
-        if(--prims_left == 0) need_pop = true;
+        do
+        {
+          if(SHADOW)
+          {
+            HitD ht;
+            ht.dist = md; ht.u = ht.v = 0.0f; ht.prim_lo = ht.prim_hi = 0xffffffffu;
+            prim_intersect<ANALYTIC>(rec, A.rec_units, r, ht);
+            if((ht.prim_lo & ht.prim_hi) != 0xffffffffu && !(ht.prim_lo == skip_id.x && ht.prim_hi == skip_id.y)) { result = 0; break; }
+          }
+          else if(prim_visible<ANALYTIC>(rec, A.rec_units, r, md)) { result = 0; break; }
+          rec += rec_stride;
+        }
+        while(--prims_left);
+        need_pop = true;
       }
     }
     else if(state == ST_NODE)
     {
-      NodeOut o;
-      if(exact) node_slabs<MB, true >(A.nodes, cur, r.px, r.py, r.pz, ix, iy, iz, t0, t1, md, o);
-      else      node_slabs<MB, false>(A.nodes, cur, r.px, r.py, r.pz, ix, iy, iz, t0, t1, md, o);
+      if(MB || exact)
+      {
+        NodeOut o;
+        if(exact) node_slabs<MB, true >(A.nodes, cur, r.px, r.py, r.pz, ix, iy, iz, t0, t1, md, o);
+        else      node_slabs<MB, false>(A.nodes, cur, r.px, r.py, r.pz, ix, iy, iz, t0, t1, md, o);
 #pragma unroll
-      for(int c=0;c<4;c++) if(o.hit[c] && !is_empty_leaf(o.child[c])) stack[sp++] = o.child[c];
+        for(int c=0;c<4;c++) if(o.hit[c] && !is_empty_leaf(o.child[c])) stack[sp++] = o.child[c];
+      }
+      else
+      {
+        const Node128 *nd = reinterpret_cast<const Node128 *>(A.nodes) + cur;
+        float key[4];
+        node_slabs_fast(nd, near_off, r.px, r.py, r.pz, ix, iy, iz, md, key);
+        const ulonglong2 *ch = reinterpret_cast<const ulonglong2 *>(nd->child);
+        const ulonglong2 c01 = __ldg(ch), c23 = __ldg(ch + 1);
+        const uint64_t child[4] = {c01.x & CB_CHILD_MASK, c01.y, c23.x, c23.y};
+#pragma unroll
+        for(int c=0;c<4;c++) if(KEY_HIT(key[c]) && !is_empty_leaf(child[c])) stack[sp++] = child[c];
+      }
       need_pop = true;
     }
     if(result < 0 && need_pop)
@@ -410,71 +494,93 @@ static int grid_for(uint64_t n, const void *kernel)
 }
 
 // the stack must hold 3 entries per tree level (qbvhmp.c:1277); pick the smallest variant that fits
-#define STACK_SMALL 48
-#define STACK_MID   96
+#define STACK_SMALL 64
 #define STACK_BIG   304
 
-template<bool MB, bool CNT>
-static int launch_intersect_t(const cb200_accel *a, const cb_ray_t *d_rays, const float *d_max_dist, cb_hitrec_t *d_out,
+static int g_refill_threshold = -1;
+static int refill_threshold()
+{
+  if(g_refill_threshold < 0)
+  {
+    const char *e = getenv("CB200_REFILL_THRESHOLD");
+    int v = e ? atoi(e) : 8;
+    if(v < 1) v = 1;
+    if(v > 32) v = 32;
+    g_refill_threshold = v;
+  }
+  return g_refill_threshold;
+}
+
+template<bool MB, bool CNT, int STACK, bool ANALYTIC>
+static int launch_intersect_k(const cb200_accel *a, const cb_ray_t *d_rays, const float *d_max_dist, cb_hitrec_t *d_out,
                               uint64_t n, cudaStream_t stream, unsigned long long *d_counters)
 {
   unsigned long long *ticket;
   if(get_ticket(stream, &ticket)) return CB200_ERR_CUDA;
-  const int need = 3*a->depth + 1;
-  const int thr = prim_threshold();
-  if(need <= STACK_SMALL)
-  {
-    auto k = k_intersect<MB, CNT, STACK_SMALL>;
-    k<<<grid_for(n, (const void *)k), TRACE_BLOCK, 0, stream>>>(a->dev, d_rays, d_max_dist, d_out, n, ticket, d_counters, thr);
-  }
-  else if(need <= STACK_MID)
-  {
-    auto k = k_intersect<MB, CNT, STACK_MID>;
-    k<<<grid_for(n, (const void *)k), TRACE_BLOCK, 0, stream>>>(a->dev, d_rays, d_max_dist, d_out, n, ticket, d_counters, thr);
-  }
-  else if(need <= STACK_BIG)
-  {
-    auto k = k_intersect<MB, CNT, STACK_BIG>;
-    k<<<grid_for(n, (const void *)k), TRACE_BLOCK, 0, stream>>>(a->dev, d_rays, d_max_dist, d_out, n, ticket, d_counters, thr);
-  }
-  else { cb200_set_error("tree deeper than the reference's MAX_TREE_DEPTH"); return CB200_ERR_UNSUPPORTED; }
+  auto k = k_intersect<MB, CNT, STACK, ANALYTIC>;
+  k<<<grid_for(n, (const void *)k), TRACE_BLOCK, 0, stream>>>(a->dev, d_rays, d_max_dist, d_out, n, ticket, d_counters,
+                                                              prim_threshold(), refill_threshold());
   cb200_count_launch();
   CB_CUDA(cudaGetLastError());
   return 0;
+}
+
+template<bool MB>
+static int launch_intersect_t(const cb200_accel *a, const cb_ray_t *d_rays, const float *d_max_dist, cb_hitrec_t *d_out,
+                              uint64_t n, cudaStream_t stream, unsigned long long *d_counters)
+{
+  const int need = 3*a->depth + 1;
+  if(need > STACK_BIG) { cb200_set_error("tree deeper than the reference's MAX_TREE_DEPTH"); return CB200_ERR_UNSUPPORTED; }
+  if(d_counters) return launch_intersect_k<MB, true, STACK_BIG, true>(a, d_rays, d_max_dist, d_out, n, stream, d_counters);
+  const bool analytic = a->scene->any_analytic != 0;
+  if(need <= STACK_SMALL)
+    return analytic ? launch_intersect_k<MB, false, STACK_SMALL, true >(a, d_rays, d_max_dist, d_out, n, stream, nullptr)
+                    : launch_intersect_k<MB, false, STACK_SMALL, false>(a, d_rays, d_max_dist, d_out, n, stream, nullptr);
+  return analytic ? launch_intersect_k<MB, false, STACK_BIG, true >(a, d_rays, d_max_dist, d_out, n, stream, nullptr)
+                  : launch_intersect_k<MB, false, STACK_BIG, false>(a, d_rays, d_max_dist, d_out, n, stream, nullptr);
 }
 
 int cb200_launch_intersect(const cb200_accel *a, const cb_ray_t *d_rays, const float *d_max_dist, cb_hitrec_t *d_out,
                            uint64_t n, cudaStream_t stream, unsigned long long *d_counters)
 {
   if(n == 0) return 0;
-  if(a->dev.mb) return d_counters ? launch_intersect_t<true,  true>(a, d_rays, d_max_dist, d_out, n, stream, d_counters)
-                                  : launch_intersect_t<true,  false>(a, d_rays, d_max_dist, d_out, n, stream, nullptr);
-  else          return d_counters ? launch_intersect_t<false, true>(a, d_rays, d_max_dist, d_out, n, stream, d_counters)
-                                  : launch_intersect_t<false, false>(a, d_rays, d_max_dist, d_out, n, stream, nullptr);
+  return a->dev.mb ? launch_intersect_t<true >(a, d_rays, d_max_dist, d_out, n, stream, d_counters)
+                   : launch_intersect_t<false>(a, d_rays, d_max_dist, d_out, n, stream, d_counters);
 }
 
-template<bool MB>
-static int launch_visible_t(const cb200_accel *a, const cb_ray_t *d_rays, const float *d_max_dist, int32_t *d_out,
+template<bool MB, int STACK, bool ANALYTIC>
+static int launch_visible_k(const cb200_accel *a, const cb_ray_t *d_rays, const float *d_max_dist, const uint2 *d_skip, int32_t *d_out,
                             uint64_t n, cudaStream_t stream)
 {
   unsigned long long *ticket;
   if(get_ticket(stream, &ticket)) return CB200_ERR_CUDA;
-  const int need = 3*a->depth + 4;   // the any-hit sweep pushes up to 4 children and pops one per level
-  const int thr = prim_threshold();
-  if(need <= STACK_MID)
+  if(d_skip)
   {
-    auto k = k_visible<MB, STACK_MID>;
-    k<<<grid_for(n, (const void *)k), TRACE_BLOCK, 0, stream>>>(a->dev, d_rays, d_max_dist, d_out, n, ticket, thr);
+    auto k = k_visible<MB, STACK, ANALYTIC, true>;
+    k<<<grid_for(n, (const void *)k), TRACE_BLOCK, 0, stream>>>(a->dev, d_rays, d_max_dist, d_skip, d_out, n, ticket, prim_threshold(), refill_threshold());
   }
-  else if(need <= STACK_BIG + 8)
+  else
   {
-    auto k = k_visible<MB, STACK_BIG + 8>;
-    k<<<grid_for(n, (const void *)k), TRACE_BLOCK, 0, stream>>>(a->dev, d_rays, d_max_dist, d_out, n, ticket, thr);
+    auto k = k_visible<MB, STACK, ANALYTIC, false>;
+    k<<<grid_for(n, (const void *)k), TRACE_BLOCK, 0, stream>>>(a->dev, d_rays, d_max_dist, nullptr, d_out, n, ticket, prim_threshold(), refill_threshold());
   }
-  else { cb200_set_error("tree deeper than the reference's MAX_TREE_DEPTH"); return CB200_ERR_UNSUPPORTED; }
   cb200_count_launch();
   CB_CUDA(cudaGetLastError());
   return 0;
+}
+
+template<bool MB>
+static int launch_visible_t(const cb200_accel *a, const cb_ray_t *d_rays, const float *d_max_dist, const uint2 *d_skip, int32_t *d_out,
+                            uint64_t n, cudaStream_t stream)
+{
+  const int need = 3*a->depth + 4;   // the any-hit sweep pushes up to 4 children and pops one per level
+  if(need > STACK_BIG + 8) { cb200_set_error("tree deeper than the reference's MAX_TREE_DEPTH"); return CB200_ERR_UNSUPPORTED; }
+  const bool analytic = a->scene->any_analytic != 0;
+  if(need <= STACK_SMALL)
+    return analytic ? launch_visible_k<MB, STACK_SMALL, true >(a, d_rays, d_max_dist, d_skip, d_out, n, stream)
+                    : launch_visible_k<MB, STACK_SMALL, false>(a, d_rays, d_max_dist, d_skip, d_out, n, stream);
+  return analytic ? launch_visible_k<MB, STACK_BIG + 8, true >(a, d_rays, d_max_dist, d_skip, d_out, n, stream)
+                  : launch_visible_k<MB, STACK_BIG + 8, false>(a, d_rays, d_max_dist, d_skip, d_out, n, stream);
 }
 
 int cb200_launch_visible(const cb200_accel *a, const cb_ray_t *d_rays, const float *d_max_dist, int32_t *d_out,
@@ -482,6 +588,15 @@ int cb200_launch_visible(const cb200_accel *a, const cb_ray_t *d_rays, const flo
 {
   if(n == 0) return 0;
   if(!d_max_dist) { cb200_set_error("visible: max_dist is required"); return CB200_ERR_ARG; }
-  return a->dev.mb ? launch_visible_t<true>(a, d_rays, d_max_dist, d_out, n, stream)
-                   : launch_visible_t<false>(a, d_rays, d_max_dist, d_out, n, stream);
+  return a->dev.mb ? launch_visible_t<true>(a, d_rays, d_max_dist, nullptr, d_out, n, stream)
+                   : launch_visible_t<false>(a, d_rays, d_max_dist, nullptr, d_out, n, stream);
+}
+
+int cb200_launch_shadow(const cb200_accel *a, const cb_ray_t *d_rays, const float *d_max_dist, const uint2 *d_light_prim, int32_t *d_out,
+                        uint64_t n, cudaStream_t stream)
+{
+  if(n == 0) return 0;
+  if(!d_max_dist || !d_light_prim) { cb200_set_error("shadow: max_dist and light prims are required"); return CB200_ERR_ARG; }
+  return a->dev.mb ? launch_visible_t<true>(a, d_rays, d_max_dist, d_light_prim, d_out, n, stream)
+                   : launch_visible_t<false>(a, d_rays, d_max_dist, d_light_prim, d_out, n, stream);
 }

@@ -225,7 +225,10 @@ def _load_render():
     L.cb200_render_create.argtypes = [vp, vp]
     L.cb200_render_destroy.argtypes = [vp]
     L.cb200_render_pass.argtypes = [vp, u64, u64, vp]
+    L.cb200_render_pass_stream.argtypes = [vp, u64, u64, vp]
+    L.cb200_render_flush.argtypes = [vp, vp]
     L.cb200_render_clear.argtypes = [vp, vp]
+    L.cb200_render_instrument.argtypes = [vp, C.c_int, C.c_int]
     L.cb200_render_fb_device.restype = vp
     L.cb200_render_fb_device.argtypes = [vp]
     L.cb200_render_download.argtypes = [vp, vp, vp]
@@ -236,7 +239,7 @@ def _load_render():
     return L
 
 
-RENDER_SYMBOLS = ["cb200_render_create", "cb200_render_destroy", "cb200_render_pass", "cb200_render_clear",
+RENDER_SYMBOLS = ["cb200_render_create", "cb200_render_destroy", "cb200_render_pass", "cb200_render_pass_stream", "cb200_render_flush", "cb200_render_clear", "cb200_render_instrument",
                   "cb200_render_fb_device", "cb200_render_download", "cb200_render_stats", "cb200_render_point",
                   "cb200_render_camera_rays"]
 
@@ -267,11 +270,15 @@ class Render:
         self.spp = 0
         self.next_index = 0
 
-    def render_pass(self, first=None, count=None, stream=0):
-        """one progression = width*height path indices (src/view.c:636-638)"""
+    def flush(self, stream=0):
+        _check(self.L.cb200_render_flush(self.r, stream or None), "cb200_render_flush")
+
+    def render_pass(self, first=None, count=None, stream=0, streaming=False):
+        """one progression = width*height path indices (src/view.c:636-638); streaming=True leaves stragglers in the pool"""
         count = self.width * self.height if count is None else count
         first = self.next_index if first is None else first
-        _check(self.L.cb200_render_pass(self.r, first, count, stream or None), "cb200_render_pass")
+        f = self.L.cb200_render_pass_stream if streaming else self.L.cb200_render_pass
+        _check(f(self.r, first, count, stream or None), "cb200_render_pass")
         self.next_index = first + count
         self.spp += count / (self.width * self.height)
 
@@ -297,7 +304,14 @@ class Render:
         from . import scene_io as sio
         s = sio.CRenderStats()
         _check(self.L.cb200_render_stats(self.r, C.byref(s)), "cb200_render_stats")
-        return {k: int(getattr(s, k)) for k, _ in s._fields_}
+        out = {}
+        for k, _ in s._fields_:
+            v = getattr(s, k)
+            out[k] = list(v) if hasattr(v, "__len__") else int(v)
+        return out
+
+    def instrument(self, timing=True, counters=False):
+        _check(self.L.cb200_render_instrument(self.r, int(timing), int(counters)), "cb200_render_instrument")
 
     def points(self, index, dim):
         index = np.ascontiguousarray(index, np.uint64)

@@ -57,7 +57,8 @@ class CRenderDesc(C.Structure):
 
 class CRenderStats(C.Structure):
     _fields_ = [("paths", C.c_uint64), ("rays_closest", C.c_uint64), ("rays_shadow", C.c_uint64), ("splats", C.c_uint64),
-                ("kernel_launches", C.c_uint64)]
+                ("kernel_launches", C.c_uint64), ("ms", C.c_double * 5), ("trav_closest", C.c_uint64 * 4),
+                ("trav_shadow", C.c_uint64 * 4)]
 
 
 # ----------------------------------------------------------------------------------------------- camera

@@ -115,6 +115,12 @@ typedef struct cb_render_stats_t
   uint64_t rays_shadow;          /* accel_intersect calls from path_visible */
   uint64_t splats;
   uint64_t kernel_launches;
+  /* filled while cb200_render_instrument(timing) is on: milliseconds between CUDA events recorded on the pass' own stream
+   * around the launches of each kernel class: {path start, closest-hit traversal, shade, shadow traversal, nee resolve} */
+  double ms[5];
+  /* filled while cb200_render_instrument(counters) is on: the reference's ACCEL_DEBUG counters (qbvhmp.c:83-90) of the
+   * closest-hit and of the shadow waves: {accel_intersect, aabb_intersect, aabb_true, prims_intersect} */
+  uint64_t trav_closest[4], trav_shadow[4];
 }
 cb_render_stats_t;
 
@@ -123,7 +129,16 @@ void cb200_render_destroy(cb200_render_t *r);
 /* one call = the work of view_render()'s fan-out for path indices [first, first+count) (src/view.c:636-645);
  * accumulates into the device framebuffer (W*H*3 floats), asynchronous on `stream` */
 int  cb200_render_pass(cb200_render_t *r, uint64_t first_index, uint64_t count, void *stream);
+/* streaming form for back-to-back progressions: returns as soon as every index of the range has been STARTED; paths that are
+ * still bouncing stay in the pool and ride along with the next call's waves (so no launch ever runs on a nearly empty wave),
+ * their contributions arrive in the framebuffer later.  cb200_render_flush traces the stragglers to the end; it is implied by
+ * cb200_render_download and must precede any use of cb200_render_fb_device as a finished image.
+ * cb200_render_pass == cb200_render_pass_stream + cb200_render_flush.                                                        */
+int  cb200_render_pass_stream(cb200_render_t *r, uint64_t first_index, uint64_t count, void *stream);
+int  cb200_render_flush(cb200_render_t *r, void *stream);
 int  cb200_render_clear(cb200_render_t *r, void *stream);
+/* per-kernel-class CUDA event timing and/or traversal work counters for the following passes (bench.py's roofline) */
+int  cb200_render_instrument(cb200_render_t *r, int timing, int counters);
 /* device pointer of the accumulation buffer (for ncclReduce across ranks) and its download.  The image the
  * reference writes is fb * gain, gain = iso / (100 * spp) (src/view.c:656) */
 void *cb200_render_fb_device(cb200_render_t *r);
