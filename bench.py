@@ -1,30 +1,46 @@
 #!/usr/bin/env python
-"""bench.py -- rays/s (closest-hit + shadow) of the B200 hot path on the synthetic 10 M-triangle config.
+"""bench.py -- rays/s (closest-hit + shadow) and spp/s of the B200 path-tracing hot path on the synthetic 10 M-triangle config.
 
   python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
 
-One "step" = one progressive pass worth of traversal over a 4K frame on the seed-fixed procedural
-10 M-triangle mesh (BASELINE.json configs[4]): a primary wave (one camera ray per pixel of the
-3840x2176 padded frame), the diffuse-bounce wave leaving its hit points (offset origins, ignore prim:
-prims_offset_ray, prims.c:374) and the next-event shadow wave toward the quad light -- the three kinds of
-traversal calls pt/ptdl issue (pathspace.c:763, 329).  Rays are counted as calls to the traversal kernels,
-the reference's accel_intersect count.
+Workload (BASELINE.json configs[4]): seed-fixed procedural 10 M-triangle mesh (fBm terrain + icosphere soup, one
+quad light), 3840x2176 frame (4K padded to multiples of 32, view.c:295-296), ptdl integrator (path tracing with next-event
+estimation, the reference's 0011_ptdl sampler), `rand` point sampler, one wavelength per path.
 
-value  : whole-job rays/s with the ray waves already resident in HBM (CUDA events, max over ranks).
-e2e    : the same step through the host-buffer C ABI (cb200_accel_intersect_n / _visible_n): pinned host
-         rays in, hit records out, copies inside the timed region.
-roofline: dominant kernel = closest-hit traversal of the primary+bounce waves; algorithmic bytes per ray =
-         N_node*S_node + N_prim*S_prim + 40 + 24 with N_* from the instrumented kernel.
-cpu_baseline / --impl reference: the unmodified reference (oracle/_ref, compiled in place) on the host cores,
-         on a bounded sample of the same waves.
-Multi-GPU: weak scaling, every rank traces its own sample slice (different seeds), no data-path collective.
+One "step" = one progression of the reference's view_render(): W*H path indices = 1 sample per pixel per GPU, every path
+traced to its end (camera ray, closest-hit traversal per vertex, material + BSDF, next-event shadow ray, splat).  Rays are
+counted as calls to the traversal kernels, the reference's accel_intersect count (path_propagate + path_visible).
+
+value    : whole-job rays/s over the K timed steps, scene + BVH resident in HBM, CUDA events on the launching stream, max over
+           ranks.  Steps are issued back to back through the streaming entry (cb200_render_pass_stream); the stragglers
+           of the last step are flushed INSIDE the timed region, so every path started in it is also finished in it.
+           spp_per_s / paths_per_s ride along (the metric's second half).
+e2e      : the same pass through the host-side render module the reference would link (MOD_render=b200,
+           render_b200_pass): path-index range in, complete HOST framebuffer out after every progression -- device->host copy
+           of the W*H*3 float image inside the timed region.  The inputs of this path ARE an index range (render_sample_path(i),
+           gi.c:81): h2d is the 16 bytes that name it.  `e2e_accel` gives the accel.h boundary (host ray batches in, hit
+           records out) for the same scene.
+roofline : dominant kernel = closest-hit traversal (k_intersect).  achieved = algorithmic bytes of all its launches in the
+           timed region / their summed duration (CUDA event pairs recorded around each launch on the launching stream);
+           algorithmic bytes per ray = N_node*S_node + N_prim*S_prim + 40 + 24 with N_* counted by the
+           instrumented kernel on one untimed progression of the same workload (ACCEL_DEBUG definitions).
+cpu_baseline / --impl reference: the UNMODIFIED reference renderer (oracle/_ref/corona_ptdl_rand, compiled in place from the
+           reference sources by oracle/Makefile) on the same scene, camera, materials and frame size, all host cores, its own
+           binned-SAH build; ray counts from its -DACCEL_DEBUG twin.
+Multi-GPU: weak scaling by splitting samples per pixel: rank g renders progressions g, g+N, ... (path-index ranges),
+           one NCCL reduce of the framebuffer to rank 0 per progression (torch.distributed on a side stream, overlapped with the
+           next progression), all inside the timed region.
 """
 import argparse
+import ctypes as C
 import importlib
 import json
 import os
+import re
+import shutil
 import subprocess
 import sys
+import tempfile
 import threading
 import time
 
@@ -35,15 +51,18 @@ sys.path.insert(0, ROOT)
 
 NUM_TRIS = 10_000_000
 WIDTH, HEIGHT = 3840, 2176          # 4K padded to multiples of 32 (view.c:295-296)
-LIGHT = (0.0, 0.0, 9.0)
+CAMERA = dict(pos=(18.0, 14.0, 14.5), lookat=(0.0, 0.0, 2.5), aperture_value=6, exposure_value=13, focal_length=0.4, iso=100.0)
+WORKLOAD = "synthetic 10M-triangle procedural mesh, 4K frame (3840x2176), ptdl, 1 spp per GPU per step"
+METRIC = "rays/s (closest-hit + shadow)"
+REFDIR = os.path.join(ROOT, "oracle", "_ref")
 
 
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
         d = json.load(open(p))
-        return float(d["hbm_gbs"]), "measured"
-    return 6650.0, "fallback"
+        return float(d["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (burst copy)"
+    return 6650.0, "B200_PROFILING.md fallback"
 
 
 class ClockSampler(threading.Thread):
@@ -67,7 +86,7 @@ class ClockSampler(threading.Thread):
                     self.rows.append(f)
             except Exception:
                 pass
-            time.sleep(0.05)
+            time.sleep(0.02)
 
     def summary(self):
         self.stop_flag = True
@@ -82,66 +101,110 @@ class ClockSampler(threading.Thread):
         return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(self.rows[0][1]), "reasons": reasons, "samples": len(self.rows)}
 
 
-def make_waves(cb, scene, trace, n_primary, seed, frame=None):
-    """primary / bounce / shadow ray sets; `trace(rays)` returns closest hits (GPU arm: the GPU; reference arm: the reference)"""
-    S = cb.scenes
-    prim = S.camera_rays(n_primary, scene, seed=100 + seed, frame=frame)
-    hits = trace(prim)
-    bounce = S.bounce_rays(prim, hits, seed=200 + seed)
-    shadow, smd = S.shadow_rays(prim, hits, LIGHT, seed=300 + seed)
-    return prim, bounce, shadow, smd
+def bench_scene(cb, tris):
+    """scene, flattened materials, camera: identical for both arms"""
+    IO, S = cb.scene_io, cb.scenes
+    z = np.load(os.path.join(ROOT, "tests", "golden", "bench_materials.npz"))
+    ms = IO.MaterialSet()
+    raw = z["materials"].tobytes()
+    ms.materials = list((IO.CMaterial * (len(raw) // C.sizeof(IO.CMaterial))).from_buffer_copy(raw))
+    scene = S.synthetic_scene(tris, seed=1)
+    for sh, m in zip(scene.shapes, z["shape_mats"]):
+        sh.material = int(m)
+    return scene, ms, IO.Camera(**CAMERA), [str(x) for x in z["shader_lines"]], [int(m) for m in z["shape_mats"]]
+
+
+# ------------------------------------------------------------------------------------------------ reference arm
+class ReferenceRenderer:
+    """the unmodified reference binary on the bench scene written out in its own file formats"""
+
+    def __init__(self, cb, scene, lines, shape_mats, camera):
+        if not os.path.exists(os.path.join(REFDIR, "corona_ptdl_rand")):
+            raise RuntimeError("oracle/_ref/corona_ptdl_rand is not built (python -c 'import __graft_entry__ as g; g.build()' "
+                               "where /root/reference exists)")
+        IO = cb.scene_io
+        self.tmp = tempfile.mkdtemp(prefix="corona_bench_")
+        shapes = []
+        for i, sh in enumerate(scene.shapes):
+            sh.write_geo(os.path.join(self.tmp, f"shape{i}.geo"))
+            shapes.append((shape_mats[i], f"shape{i}"))
+        self.nra2 = os.path.join(self.tmp, "test.nra2")
+        IO.write_nra2(self.nra2, lines, shapes)
+        camera.write(os.path.join(self.tmp, "test01.cam"))
+        self.cores = os.cpu_count() or 1
+
+    def run(self, binary, w, h, spp):
+        """returns (seconds per progression [list], accel build seconds, total accel_intersect calls or None)"""
+        cmd = [os.path.join(REFDIR, binary), self.nra2, "-x", "-s", str(spp), "-w", str(w), "-h", str(h), "-b", "0",
+               "-t", str(self.cores), "--frame", "1"]
+        p = subprocess.run(cmd, cwd=REFDIR, capture_output=True, text=True)
+        if p.returncode != 0:
+            raise RuntimeError(f"{binary} failed ({p.returncode}): {p.stderr[-400:]}")
+        frames = [float(x) for x in re.findall(r"([0-9.]+) s/frame, \d+ spp", p.stdout)]
+        build = re.findall(r"construction took ([0-9.]+) seconds", p.stdout)
+        rays = [int(x) for x in re.findall(r"accel_intersect: (\d+)", p.stderr)]
+        return frames, (float(build[0]) if build else None), (sum(rays) if rays else None)
+
+    def rays_per_path(self):
+        """-DACCEL_DEBUG twin at a quarter of the frame in each direction (rays per path do not depend on resolution)"""
+        w, h = WIDTH // 4, HEIGHT // 4
+        _, _, rays = self.run("corona_ptdl_rand_dbg", w, h, 1)
+        return rays / float(w * h)
+
+    def close(self):
+        shutil.rmtree(self.tmp, ignore_errors=True)
 
 
 def run_reference(args, rank, world):
-    """--impl reference: accel_build + accel_intersect of the unmodified reference on all host cores"""
+    """--impl reference: the reference's own CPU implementation of the path on all host cores, 1 spp at 4K per step"""
     if rank != 0:
         return
     cb = importlib.import_module("corona-13_b200")
-    from oracle.binding import Ref, ref_available
-    if not ref_available():
-        from oracle.binding import Oracle   # reference not compiled here: time the oracle port instead
-    cores = os.cpu_count() or 1
-    scene = cb.scenes.synthetic_scene(NUM_TRIS, seed=1)
-    kind = "reference" if ref_available() else "port"
-    if kind == "reference":
-        impl = Ref(scene, threads=cores).build()
-        trace = lambda r, md=None: impl.intersect(r, md, nthreads=cores)
-        vis = lambda r, md: impl.visible(r, md, nthreads=cores)
-    else:
-        impl = Oracle(scene).build()
-        trace = lambda r, md=None: impl.intersect(r, md, nthreads=cores)
-        vis = lambda r, md: impl.visible(r, md, nthreads=cores)
-    n_sample = 1 << 19
-    prim, bounce, shadow, smd = make_waves(cb, scene, trace, n_sample, 0, (1024, 512))
-    rays_per_step = len(prim) + len(bounce) + len(shadow)
-
-    def step():
-        trace(prim)
-        trace(bounce)
-        # ptdl's next-event visibility goes through accel_intersect as well (path_visible, pathspace.c:311-344)
-        trace(shadow, smd)
-    for _ in range(args.warmup):
-        step()
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        step()
-    dt = time.perf_counter() - t0
-    value = rays_per_step * args.steps / dt
-    sample = f"{len(prim)} primary + {len(bounce)} bounce + {len(shadow)} shadow rays per step of the 4K wave, 10M-tri mesh, {cores} threads"
+    scene, ms, cam, lines, shape_mats = bench_scene(cb, args.tris)
+    ref = ReferenceRenderer(cb, scene, lines, shape_mats, cam)
+    try:
+        rpp = ref.rays_per_path()
+        frames, build_s, _ = ref.run("corona_ptdl_rand", WIDTH, HEIGHT, args.warmup + args.steps)
+    finally:
+        ref.close()
+    timed = frames[args.warmup:args.warmup + args.steps]
+    dt = sum(timed)
+    paths = WIDTH * HEIGHT * len(timed)
+    value = paths * rpp / dt
+    sample = (f"{len(timed)} progressions of the full 4K frame ({WIDTH * HEIGHT} paths each) after {args.warmup} warm-up progressions, "
+              f"{ref.cores} pinned threads, own binned-SAH tree ({build_s} s build); rays = paths x {rpp:.3f} rays/path counted by the "
+              f"-DACCEL_DEBUG build at {WIDTH // 4}x{HEIGHT // 4}")
     print(json.dumps({
-        "impl": "reference", "metric": "rays/s (closest-hit + shadow)", "value": value, "unit": "rays/s", "n_gpus": world,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True,
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "rays/s", "n_gpus": world,
+        "steps": len(timed), "warmup": args.warmup, "ms_per_step": dt / len(timed) * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "synthetic 10M-triangle procedural mesh, 4K frame, primary+bounce+shadow waves", "num_tris": scene.num_prims},
-        "cpu_baseline": {"value": value, "unit": "rays/s", "cores": cores, "kind": kind, "sample": sample},
+        "config": {"workload": WORKLOAD, "num_tris": scene.num_prims, "frame": [WIDTH, HEIGHT], "sampler": "ptdl", "pointsampler": "rand"},
+        "spp_per_s": len(timed) / dt, "paths_per_s": paths / dt, "rays_per_path": rpp,
+        "cpu_baseline": {"value": value, "unit": "rays/s", "cores": ref.cores, "kind": "reference", "sample": sample},
         "e2e": {"value": value, "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
 
 
+def cpu_baseline(cb, scene, lines, shape_mats, cam):
+    """bounded sample for the own arm's line: one 4K progression of the reference renderer (plus one warm-up)"""
+    ref = ReferenceRenderer(cb, scene, lines, shape_mats, cam)
+    try:
+        rpp = ref.rays_per_path()
+        frames, build_s, _ = ref.run("corona_ptdl_rand", WIDTH, HEIGHT, 2)
+    finally:
+        ref.close()
+    dt = frames[-1]
+    return {"value": WIDTH * HEIGHT * rpp / dt, "unit": "rays/s", "cores": ref.cores, "kind": "reference",
+            "spp_per_s": 1.0 / dt, "rays_per_path": rpp, "accel_build_s": build_s,
+            "sample": f"the second of two 4K progressions ({WIDTH * HEIGHT} paths) of oracle/_ref/corona_ptdl_rand on the same scene files, "
+                      f"{ref.cores} pinned threads; rays = paths x {rpp:.3f} (ACCEL_DEBUG build)"}
+
+
+# ------------------------------------------------------------------------------------------------ own arm
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=64)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--tris", type=int, default=NUM_TRIS)
@@ -157,109 +220,141 @@ def main():
     import torch.distributed as dist
     cb = importlib.import_module("corona-13_b200")
     lib = importlib.import_module("corona-13_b200.lib")     # raises when the CUDA library is missing
-    R = cb.records
+    IO = cb.scene_io
     if lib.device_count() < 1:
         raise SystemExit("bench.py: no CUDA device (" + lib.load().cb200_last_error().decode() + "); there is no CPU fallback")
     torch.cuda.set_device(local)
     lib.set_device(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    warmup = max(args.warmup, 3)
 
-    scene = cb.scenes.synthetic_scene(args.tris, seed=1)
+    scene, ms, cam, lines, shape_mats = bench_scene(cb, args.tris)
     acc = lib.Accel(scene)
     t0 = time.perf_counter()
     acc.build()
     build_s = time.perf_counter() - t0
     node_b, prim_b = acc.layout()
-    n_primary = WIDTH * HEIGHT
-    prim, bounce, shadow, smd = make_waves(cb, scene, lambda r: acc.intersect(r), n_primary, rank, (WIDTH, HEIGHT))
-    waves = [("primary", prim, None), ("bounce", bounce, None), ("shadow", shadow, smd)]
-    rays_per_step = sum(len(w[1]) for w in waves)
-
+    n_pass = WIDTH * HEIGHT
     st = torch.cuda.current_stream().cuda_stream
-    dev = []
-    for name, rays, md in waves:
-        d_r = torch.from_numpy(rays.view("u1").reshape(-1)).cuda()
-        d_md = torch.from_numpy(md).cuda() if md is not None else None
-        d_o = torch.empty(len(rays) * (24 if md is None else 4), dtype=torch.uint8, device="cuda")
-        dev.append((name, d_r, d_md, d_o, len(rays)))
+    r = lib.Render(acc, cam, ms, WIDTH, HEIGHT, sampler=IO.SAMPLER_PTDL, pointsampler=IO.POINTS_RAND, frame=1, rank=rank, world=world)
 
-    # per-ray work of the dominant kernel (outside the timed region), reference ACCEL_DEBUG definitions
-    cnt = np.zeros(4, np.float64)
-    for name, d_r, d_md, d_o, n in dev[:2]:
-        cnt += acc.intersect_counted(d_r.data_ptr(), 0, d_o.data_ptr(), n).astype(np.float64)
-    n_node, n_prim = cnt[1] / cnt[0], cnt[3] / cnt[0]
+    # rank g renders progressions g, g+N, g+2N, ...: the same path indices a 1-GPU run would use for those progressions
+    prog = [0]
+
+    def next_first():
+        first = (prog[0] * world + rank) * n_pass
+        prog[0] += 1
+        return first
+
+    # per-ray work of the dominant kernel, reference ACCEL_DEBUG definitions: one untimed, counted progression
+    r.instrument(False, True)
+    r.render_pass(next_first(), n_pass, st)
+    cs = r.stats()
+    tc = np.array(cs["trav_closest"], np.float64)
+    n_node, n_prim = tc[1] / tc[0], tc[3] / tc[0]
     bytes_per_ray = n_node * node_b + n_prim * prim_b + 40 + 24
+    r.clear()
+    r.instrument(True, False)
 
-    def step(events=None):
-        for k, (name, d_r, d_md, d_o, n) in enumerate(dev):
-            if events is not None:
-                events[k][0].record()
-            if d_md is None:
-                acc.intersect_dev(d_r.data_ptr(), 0, d_o.data_ptr(), n, st)
-            else:
-                acc.visible_dev(d_r.data_ptr(), d_md.data_ptr(), d_o.data_ptr(), n, st)
-            if events is not None:
-                events[k][1].record()
+    # framebuffers: double-buffered so that the reduce of progression s overlaps the rendering of s+1 (N > 1)
+    fbs = [torch.zeros(HEIGHT, WIDTH, 3, device="cuda") for _ in range(2 if world > 1 else 1)]
+    accum = torch.zeros(HEIGHT, WIDTH, 3, device="cuda") if (world > 1 and rank == 0) else None
+    pending = [None, None]
+    comm = torch.cuda.Stream() if world > 1 else None
 
-    for _ in range(max(args.warmup, 3)):
-        step()
+    def retire(k):
+        """wait for buffer k's reduce, fold it into the root's accumulator, zero it for reuse"""
+        if pending[k] is not None:
+            pending[k].wait()
+            torch.cuda.current_stream().wait_stream(comm)
+            if accum is not None:
+                accum.add_(fbs[k])
+            fbs[k].zero_()
+            pending[k] = None
+
+    def step(s, last=False):
+        k = s % len(fbs)
+        if world > 1:
+            retire(k)
+        r.set_framebuffer(fbs[k].data_ptr())
+        r.render_pass(next_first(), n_pass, st, streaming=not last)     # the last one flushes the stragglers
+        if world > 1:
+            comm.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(comm):
+                pending[k] = dist.reduce(fbs[k], 0, async_op=True)
+
+    for s in range(warmup):
+        step(s, last=(s == warmup - 1))
+    if world > 1:
+        retire(0), retire(1)
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
+    for f in fbs:
+        f.zero_()
+    if accum is not None:
+        accum.zero_()
+    r.clear()
+    r.instrument(True, False)
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    ev = [[(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in dev] for _ in range(args.steps)]
     l0 = lib.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     torch.cuda.synchronize()
     e0.record()
     for s in range(args.steps):
-        step(ev[s])
+        step(s, last=(s == args.steps - 1))
+    if world > 1:
+        retire(0), retire(1)
     e1.record()
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
     launches = lib.launch_count() - l0
-    ms = torch.tensor([e0.elapsed_time(e1)], device="cuda")
+    stt = r.stats()
+    ms_t = torch.tensor([e0.elapsed_time(e1)], device="cuda", dtype=torch.float64)
+    cnt = torch.tensor([stt["rays_closest"], stt["rays_shadow"], stt["paths"], launches], device="cuda", dtype=torch.float64)
     if world > 1:
-        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-    ms_total = float(ms.item())
+        dist.all_reduce(ms_t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
+    ms_total = float(ms_t.item())
+    rays_closest, rays_shadow, paths, launches_all = [float(x) for x in cnt.tolist()]
     clocks = sampler.summary() if rank == 0 else None
-    k_ms = [np.mean([ev[s][k][0].elapsed_time(ev[s][k][1]) for s in range(args.steps)]) for k in range(len(dev))]
+    image_mean = None
+    if rank == 0:
+        fb = accum if accum is not None else fbs[0]
+        image_mean = [float(x) for x in (fb.mean(dim=(0, 1)) * (cam.iso / (100.0 * args.steps * world))).tolist()]
 
-    # e2e: host buffers through the C ABI, copies inside the timed region
-    pinned = []
-    for name, rays, md in waves:
-        pr = torch.from_numpy(rays.view("u1").reshape(-1).copy()).pin_memory()
-        pm = torch.from_numpy(md.copy()).pin_memory() if md is not None else None
-        po = torch.empty(len(rays) * (24 if md is None else 4), dtype=torch.uint8).pin_memory()
-        pinned.append((pr, pm, po, len(rays)))
-    L = lib.load()
+    # ---- e2e: host-side render module (MOD_render=b200), host framebuffer after every progression
+    e2e = None
+    if world == 1:
+        r.set_framebuffer(0)
+        r.clear()
+        r.instrument(False, False)
+        host_fb = torch.empty(HEIGHT, WIDTH, 3).pin_memory()
+        e2e_steps = max(2, min(args.steps, 6))
 
-    def e2e_step():
-        for pr, pm, po, n in pinned:
-            if pm is None:
-                rc = L.cb200_accel_intersect_n(acc.a, pr.data_ptr(), None, po.data_ptr(), n)
-            else:
-                rc = L.cb200_accel_visible_n(acc.a, pr.data_ptr(), pm.data_ptr(), po.data_ptr(), n)
-            if rc:
-                raise SystemExit("e2e step failed: " + L.cb200_last_error().decode())
-    e2e_steps = max(2, min(args.steps, 5))
-    e2e_step()
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
-    t0 = time.perf_counter()
-    for _ in range(e2e_steps):
+        def e2e_step():
+            lib._check(lib.load().cb200_render_pass(r.r, next_first(), n_pass, None), "cb200_render_pass")
+            lib._check(lib.load().cb200_render_download(r.r, host_fb.data_ptr(), None), "cb200_render_download")
+        s0 = r.stats()
         e2e_step()
-    torch.cuda.synchronize()
-    e2e_t = torch.tensor([time.perf_counter() - t0], device="cuda", dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
-    h2d = sum(n * 40 + (n * 4 if pm is not None else 0) for pr, pm, po, n in pinned)
-    d2h = sum(n * (24 if pm is None else 4) for pr, pm, po, n in pinned)
+        torch.cuda.synchronize()
+        s1 = r.stats()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            e2e_step()
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        s2 = r.stats()
+        rays = (s2["rays_closest"] + s2["rays_shadow"]) - (s1["rays_closest"] + s1["rays_shadow"])
+        e2e = {"value": rays / dt, "unit": "rays/s", "h2d_bytes_per_step": 16, "d2h_bytes_per_step": HEIGHT * WIDTH * 3 * 4,
+               "steps": e2e_steps, "ms_per_step": dt / e2e_steps * 1e3, "spp_per_s": e2e_steps / dt,
+               "boundary": "render_b200_pass: path-index range in, finished host framebuffer (W*H*3 f32, pinned) out, every progression"}
+        e2e["accel_h"] = accel_boundary(cb, lib, acc, scene, torch)
+    r.close()
 
     if rank != 0:
         if world > 1:
@@ -267,52 +362,57 @@ def main():
         return
 
     hbm, which = peaks()
-    closest_rays = dev[0][4] + dev[1][4]
-    closest_ms = k_ms[0] + k_ms[1]
-    achieved = closest_rays * bytes_per_ray / (closest_ms * 1e-3) / 1e9
+    ms_closest, ms_shadow = stt["ms"][1], stt["ms"][3]
+    achieved = stt["rays_closest"] * bytes_per_ray / (ms_closest * 1e-3) / 1e9
+    total_rays = rays_closest + rays_shadow
     out = {
-        "metric": "rays/s (closest-hit + shadow)", "value": rays_per_step * world * args.steps / (ms_total * 1e-3), "unit": "rays/s",
-        "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_total / args.steps,
+        "metric": METRIC, "value": total_rays / (ms_total * 1e-3), "unit": "rays/s",
+        "n_gpus": world, "steps": args.steps, "warmup": warmup, "ms_per_step": ms_total / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "synthetic 10M-triangle procedural mesh, 4K frame, primary+bounce+shadow waves",
-                   "num_tris": scene.num_prims, "frame": [WIDTH, HEIGHT], "rays_per_step_per_gpu": rays_per_step,
-                   "waves": {w[0]: len(w[1]) for w in waves}, "l2": "inputs larger than L2 (ray waves 335+ MB each, scene 0.8 GB)",
-                   "bvh": {"nodes": acc.num_nodes(), "depth": acc.depth(), "node_bytes": node_b, "prim_bytes": prim_b,
-                           "gpu_build_s": build_s}},
-        "kernel_ms": {w[0]: float(k) for w, k in zip(waves, k_ms)},
-        "grays_per_s": {w[0]: len(w[1]) / (k * 1e-3) / 1e9 for w, k in zip(waves, k_ms)},
-        "roofline": {"bound": "hbm", "kernel": "k_intersect (primary+bounce waves)", "achieved": achieved, "peak": hbm, "unit": "GB/s",
-                     "frac": achieved / hbm, "peak_source": which, "traffic": None,
-                     "bytes_per_ray": bytes_per_ray, "nodes_per_ray": n_node, "prims_per_ray": n_prim},
-        "e2e": {"value": rays_per_step * world * e2e_steps / float(e2e_t.item()), "unit": "rays/s",
-                "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps},
-        "gpu_launches": int(launches),
+        "config": {"workload": WORKLOAD, "num_tris": scene.num_prims, "frame": [WIDTH, HEIGHT], "sampler": "ptdl", "pointsampler": "rand",
+                   "paths_per_step_per_gpu": n_pass, "rays_per_path": total_rays / paths,
+                   "l2": "inputs larger than L2 (scene 0.8 GB, path pool 2.4 GB, ray/hit waves 0.5 GB per wave)",
+                   "parallelism": f"spp split over {world} GPU(s), one framebuffer reduce per progression" if world > 1 else "1 GPU",
+                   "bvh": {"nodes": acc.num_nodes(), "depth": acc.depth(), "node_bytes": node_b, "prim_bytes": prim_b, "gpu_build_s": build_s}},
+        "spp_per_s": args.steps * world / (ms_total * 1e-3), "paths_per_s": paths / (ms_total * 1e-3),
+        "kernel_ms_per_step_rank0": {k: v / args.steps for k, v in zip(["path_start", "closest_hit", "shade", "shadow", "nee_resolve"], stt["ms"])},
+        "grays_per_s_rank0": {"closest_hit": stt["rays_closest"] / (ms_closest * 1e-3) / 1e9, "shadow": stt["rays_shadow"] / max(ms_shadow * 1e-3, 1e-12) / 1e9},
+        "roofline": {"bound": "hbm", "kernel": "k_intersect (closest-hit traversal, all launches of the timed region, rank 0)",
+                     "achieved": achieved, "peak": hbm, "unit": "GB/s", "frac": achieved / hbm, "peak_source": which, "traffic": None,
+                     "bytes_per_ray": bytes_per_ray, "nodes_per_ray": n_node, "prims_per_ray": n_prim,
+                     "rays": stt["rays_closest"], "kernel_ms": ms_closest},
+        "e2e": e2e if e2e is not None else {"value": None, "unit": "rays/s", "h2d_bytes_per_step": 16,
+                                            "d2h_bytes_per_step": HEIGHT * WIDTH * 3 * 4, "note": "measured at N=1"},
+        "gpu_launches": int(launches_all),
+        "image_mean_xyz": image_mean,
         "clocks": clocks,
     }
     if world == 1 and not args.no_cpu_baseline:
-        out["cpu_baseline"] = cpu_baseline(cb, scene, waves)
+        try:
+            out["cpu_baseline"] = cpu_baseline(cb, scene, lines, shape_mats, cam)
+        except Exception as e:   # reference not built on this box: say so instead of inventing a number
+            out["cpu_baseline"] = {"value": None, "unit": "rays/s", "cores": os.cpu_count(), "kind": "reference", "sample": f"unavailable: {e}"}
     print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()
 
 
-def cpu_baseline(cb, scene, waves):
-    """the reference (oracle/_ref) -- or the oracle port where it is not built -- on a bounded sample of the same waves"""
-    from oracle.binding import Ref, Oracle, ref_available
-    cores = os.cpu_count() or 1
-    n = 1 << 19
-    kind = "reference" if ref_available() else "port"
-    impl = Ref(scene, threads=cores).build() if kind == "reference" else Oracle(scene).build()
+def accel_boundary(cb, lib, acc, scene, torch):
+    """the accel.h boundary for the same scene: pinned host ray batches in, hit records out (cb200_accel_intersect_n)"""
+    S = cb.scenes
+    n = 1 << 22
+    rays = S.camera_rays(n, scene, seed=100)
+    pr = torch.from_numpy(rays.view("u1").reshape(-1).copy()).pin_memory()
+    po = torch.empty(n * 24, dtype=torch.uint8).pin_memory()
+    L = lib.load()
+    lib._check(L.cb200_accel_intersect_n(acc.a, pr.data_ptr(), None, po.data_ptr(), n), "cb200_accel_intersect_n")
     t0 = time.perf_counter()
-    total = 0
-    for name, rays, md in waves:
-        r = rays[:n]
-        impl.intersect(r, md[:n] if md is not None else None, nthreads=cores)
-        total += len(r)
+    reps = 3
+    for _ in range(reps):
+        lib._check(L.cb200_accel_intersect_n(acc.a, pr.data_ptr(), None, po.data_ptr(), n), "cb200_accel_intersect_n")
     dt = time.perf_counter() - t0
-    impl.close()
-    return {"value": total / dt, "unit": "rays/s", "cores": cores, "kind": kind,
-            "sample": f"first {n} rays of each of the 3 waves of rank 0's step, own tree built by accel_build with {cores} threads"}
+    return {"value": n * reps / dt, "unit": "rays/s", "h2d_bytes_per_step": n * 40, "d2h_bytes_per_step": n * 24,
+            "boundary": "accel_intersect_n: 4 Mi random-pixel camera rays per call from pinned host memory"}
 
 
 if __name__ == "__main__":

@@ -612,6 +612,7 @@ struct cb200_render
   // streaming wavefront: paths still alive when a pass has started all of its indices stay in the pool
   // (st[cur] / rays[cur], slots [0, n_alive)) and ride along with the next pass' waves until cb200_render_flush
   uint32_t n_alive; int cur;
+  float *own_fb;
   // instrumentation (cb200_render_instrument): CUDA events around every launch on the pass' own stream, summed per
   // kernel class after the pass; ACCEL_DEBUG-style traversal counters
   int timing, counting;
@@ -846,7 +847,7 @@ cb200_render_t *cb200_render_create(cb200_accel_t *a, const cb_render_desc_t *de
     if(r->batch < 65536) r->batch = 65536;
   }
   const uint64_t N = r->batch;
-  D.fb = dev_alloc<float>(r, (size_t)desc->width*desc->height*3);
+  D.fb = r->own_fb = dev_alloc<float>(r, (size_t)desc->width*desc->height*3);
   for(int k=0;k<2;k++) { r->st[k] = dev_alloc<PathState>(r, N); r->rays[k] = dev_alloc<cb_ray_t>(r, N); ok = ok && r->st[k] && r->rays[k]; }
   r->hits = dev_alloc<cb_hitrec_t>(r, N);
   r->nee_rays = dev_alloc<cb_ray_t>(r, N); r->nee_md = dev_alloc<float>(r, N); r->nee_recs = dev_alloc<NeeRec>(r, N); r->nee_light = dev_alloc<uint2>(r, N); r->nee_vis = dev_alloc<int32_t>(r, N);
@@ -886,6 +887,13 @@ int cb200_render_clear(cb200_render_t *r, void *stream)
 }
 
 void *cb200_render_fb_device(cb200_render_t *r) { return r ? r->dev.fb : nullptr; }
+
+int cb200_render_set_framebuffer(cb200_render_t *r, void *d_fb)
+{
+  if(!r) { cb200_set_error("render_set_framebuffer: null"); return CB200_ERR_ARG; }
+  r->dev.fb = d_fb ? (float *)d_fb : r->own_fb;
+  return 0;
+}
 
 int cb200_render_download(cb200_render_t *r, float *fb_host, void *stream)
 {

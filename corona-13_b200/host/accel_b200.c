@@ -98,6 +98,7 @@ void accel_build(accel_t *b, const char *filename)
 }
 
 const float *accel_aabb(const accel_t *b) { return b->aabb; }
+void *accel_b200_handle(const accel_t *b) { return b ? b->accel : 0; }
 
 void accel_intersect_n(const accel_t *b, const ray_t *rays, hit_t *hits, uint64_t n)
 {

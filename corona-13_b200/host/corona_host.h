@@ -72,6 +72,28 @@ const float *accel_aabb(const accel_t *b);
 void accel_intersect_n(const accel_t *b, const ray_t *rays, hit_t *hits, uint64_t n);
 void accel_visible_n(const accel_t *b, const ray_t *rays, const float *max_dist, int *visible, uint64_t n);
 
+/* the device handle behind an accel_t (cb200_accel_t*), for the render module */
+void *accel_b200_handle(const accel_t *b);
+
+/* ---- MOD_render=b200 (host/render_b200.c): include/render.h:13-32 + the batched progression entry ------------ */
+#include "corona_b200_render.h"
+struct render_t;
+struct render_tls_t;
+#ifndef CORONA_B200_IN_TREE
+struct render_t *render_init();                    /* the reference's argument-less form needs rt.*: in-tree only */
+void render_cleanup(struct render_t *r);
+struct render_tls_t *render_tls_init();
+void render_tls_cleanup(struct render_tls_t *r);
+void render_print_info(FILE *fd);
+void render_sample_path(uint64_t index);
+void render_clear();
+#endif
+struct render_t *render_b200_init(const accel_t *accel, const cb_render_desc_t *desc);
+/* == for(i in [first_index, first_index+count)) render_sample_path(i); fb: host W*H*3 floats or NULL */
+int render_b200_pass(struct render_t *r, uint64_t first_index, uint64_t count, float *fb);
+uint64_t render_b200_overlays(const struct render_t *r);
+void *render_b200_handle(const struct render_t *r);
+
 /* prims helpers for standalone use: the slice of prims_init/allocate/load/allocate_index the path needs
  * (src/prims.c:703-828) */
 #ifndef CORONA_B200_IN_TREE

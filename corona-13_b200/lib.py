@@ -232,6 +232,7 @@ def _load_render():
     L.cb200_render_fb_device.restype = vp
     L.cb200_render_fb_device.argtypes = [vp]
     L.cb200_render_download.argtypes = [vp, vp, vp]
+    L.cb200_render_set_framebuffer.argtypes = [vp, vp]
     L.cb200_render_stats.argtypes = [vp, vp]
     L.cb200_render_point.argtypes = [vp, vp, vp, vp, u64]
     L.cb200_render_camera_rays.argtypes = [vp, u64, u64, vp, vp]
@@ -240,7 +241,7 @@ def _load_render():
 
 
 RENDER_SYMBOLS = ["cb200_render_create", "cb200_render_destroy", "cb200_render_pass", "cb200_render_pass_stream", "cb200_render_flush", "cb200_render_clear", "cb200_render_instrument",
-                  "cb200_render_fb_device", "cb200_render_download", "cb200_render_stats", "cb200_render_point",
+                  "cb200_render_fb_device", "cb200_render_set_framebuffer", "cb200_render_download", "cb200_render_stats", "cb200_render_point",
                   "cb200_render_camera_rays"]
 
 
@@ -289,6 +290,9 @@ class Render:
 
     def fb_device(self):
         return self.L.cb200_render_fb_device(self.r)
+
+    def set_framebuffer(self, device_ptr):
+        _check(self.L.cb200_render_set_framebuffer(self.r, device_ptr or None), "cb200_render_set_framebuffer")
 
     def framebuffer(self):
         fb = np.zeros((self.height, self.width, 3), np.float32)

@@ -142,6 +142,9 @@ int  cb200_render_instrument(cb200_render_t *r, int timing, int counters);
 /* device pointer of the accumulation buffer (for ncclReduce across ranks) and its download.  The image the
  * reference writes is fb * gain, gain = iso / (100 * spp) (src/view.c:656) */
 void *cb200_render_fb_device(cb200_render_t *r);
+/* accumulate into a caller-owned device buffer (W*H*3 floats) from now on, NULL = back to the library's own.  Lets the
+ * caller double-buffer: reduce / read one buffer while the next progression renders into the other. */
+int  cb200_render_set_framebuffer(cb200_render_t *r, void *d_fb);
 int  cb200_render_download(cb200_render_t *r, float *fb_host, void *stream);
 int  cb200_render_stats(cb200_render_t *r, cb_render_stats_t *out);
 
