@@ -20,7 +20,8 @@
 #include <vector>
 
 #define BUILD_BLOCK 256
-#define LEAF_MAX 6   // NUM_TRIS_PER_LEAF, qbvhmp.c:44
+#define LEAF_MAX_REF 6   // NUM_TRIS_PER_LEAF, qbvhmp.c:44
+#define LEAF_MAX_DEFAULT 3
 
 struct Box { float lo[3], hi[3]; };
 
@@ -260,6 +261,7 @@ struct CollapseArgs
   Node128 *out128;
   uint32_t *num_wide;          // allocation counter
   uint32_t max_wide;           // capacity of the node buffer and of the queues
+  uint32_t leaf_max;           // subtrees with at most this many primitives become leaves
 };
 
 __device__ __forceinline__ uint32_t bref_count(const BNode *nodes, uint32_t r)
@@ -292,7 +294,7 @@ __global__ void k_collapse(CollapseArgs A, const CollapseItem *__restrict__ in, 
   // slots: bref or BNONE (empty)
   uint32_t slot[4] = {BNONE, BNONE, BNONE, BNONE};
   int axis0 = 0, axis00 = 0, axis01 = 0;
-  const bool root_is_leaf = (it.bref & BLEAF) || bref_count(A.nodes, it.bref) <= LEAF_MAX;
+  const bool root_is_leaf = (it.bref & BLEAF) || bref_count(A.nodes, it.bref) <= A.leaf_max;
   if(root_is_leaf) slot[0] = it.bref;   // only possible for the root of a tiny scene
   else
   {
@@ -302,9 +304,9 @@ __global__ void k_collapse(CollapseArgs A, const CollapseItem *__restrict__ in, 
     for(int s=0;s<2;s++)
     {
       const uint32_t r = side[s];
-      if((r & BLEAF) || bref_count(A.nodes, r) <= LEAF_MAX) slot[2*s] = r;
+      if(r & BLEAF) slot[2*s] = r;   // a single primitive: the pair's second slot stays empty
       else
-      {
+      { // also when the whole side would fit one leaf: its two halves fill both slots at no extra node, with tighter boxes
         const BNode c = A.nodes[r];
         slot[2*s] = c.left; slot[2*s+1] = c.right;
         if(s == 0) axis00 = c.axis; else axis01 = c.axis;
@@ -325,7 +327,7 @@ __global__ void k_collapse(CollapseArgs A, const CollapseItem *__restrict__ in, 
     bref_box(A, r, 0, b0[c]);
     if(A.any_mb) bref_box(A, r, 1, b1[c]); else for(int k=0;k<6;k++) b1[c][k] = b0[c][k];
     const uint32_t cnt = bref_count(A.nodes, r);
-    if((r & BLEAF) || cnt <= LEAF_MAX)
+    if((r & BLEAF) || cnt <= A.leaf_max)
       child[c] = CB_LEAF_BIT | ((uint64_t)bref_first(A.nodes, r) << 5) | cnt;
     else
     {
@@ -504,7 +506,11 @@ int cb200_build_lbvh(cb200_accel *a, const float *ghost_aabb)
 
   // collapse, level by level.  a 4-wide node consumes >= 2 binary nodes except at the fringes; n wide nodes
   // always suffice (the reference sizes its buffer the same way, qbvhmp.c:299).
-  const uint64_t max_wide = (uint64_t)n/2 + 8;
+  // leaf size: the reference builds to <= 6 primitives with a SAH (qbvhmp.c:44); Morton-ordered leaves overlap more, and a
+  // primitive test costs this kernel more than a node test (whole-leaf loops run at a third of the lanes), so smaller is better
+  uint32_t leaf_max = LEAF_MAX_DEFAULT;
+  if(const char *e = getenv("CB200_LEAF_MAX")) { const int v = atoi(e); if(v >= 1 && v <= 31) leaf_max = (uint32_t)v; }
+  const uint64_t max_wide = (uint64_t)n + 8;
   if(any_mb) CB_CUDA(cudaMalloc(&a->d_nodes, max_wide*sizeof(Node256)));
   else       CB_CUDA(cudaMalloc(&a->d_nodes, max_wide*sizeof(Node128)));
   CB_CUDA(q0.alloc(max_wide)); CB_CUDA(q1.alloc(max_wide));
@@ -521,6 +527,7 @@ int cb200_build_lbvh(cb200_accel *a, const float *ghost_aabb)
   CA.out128 = any_mb ? nullptr : (Node128 *)a->d_nodes;
   CA.num_wide = counters.p;
   CA.max_wide = (uint32_t)max_wide;
+  CA.leaf_max = leaf_max;
   uint32_t num_in = 1;
   int depth = 0;
   CollapseItem *qin = q0.p, *qout = q1.p;

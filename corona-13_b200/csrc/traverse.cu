@@ -24,6 +24,9 @@
 #include <cstdlib>
 
 #define TRACE_BLOCK 128
+#ifndef TRACE_MIN_BLOCKS
+#define TRACE_MIN_BLOCKS 8   // static triangle scenes: cap at 64 registers -> 32 resident warps per SM
+#endif
 #define FULL 0xffffffffu
 
 __device__ __forceinline__ float sse_min(float a, float b) { return a < b ? a : b; }   // _mm_min_ps
@@ -161,7 +164,7 @@ __device__ __forceinline__ void node_slabs_fast(const Node128 *__restrict__ n, c
 //             without them get a kernel without that code and with fewer registers)
 // ---------------------------------------------------------------------------------------------
 template<bool MB, bool CNT, int STACK, bool ANALYTIC>
-__global__ void __launch_bounds__(TRACE_BLOCK)
+__global__ void __launch_bounds__(TRACE_BLOCK, (!MB && !CNT && !ANALYTIC) ? TRACE_MIN_BLOCKS : 1)
 k_intersect(DevAccel A, const cb_ray_t *__restrict__ rays, const float *__restrict__ max_dist,
             cb_hitrec_t *__restrict__ out, uint64_t n, unsigned long long *ticket, unsigned long long *counters,
             int prim_threshold, int refill_threshold)
