@@ -240,10 +240,11 @@ def main():
     r = lib.Render(acc, cam, ms, WIDTH, HEIGHT, sampler=IO.SAMPLER_PTDL, pointsampler=IO.POINTS_RAND, frame=1, rank=rank, world=world)
 
     # rank g renders progressions g, g+N, g+2N, ...: the same path indices a 1-GPU run would use for those progressions
+    P = importlib.import_module("corona-13_b200.progressive")
     prog = [0]
 
     def next_first():
-        first = (prog[0] * world + rank) * n_pass
+        first, _ = P.progression_range(prog[0], rank, world, n_pass)
         prog[0] += 1
         return first
 
@@ -258,43 +259,19 @@ def main():
     r.instrument(True, False)
 
     # framebuffers: double-buffered so that the reduce of progression s overlaps the rendering of s+1 (N > 1)
-    fbs = [torch.zeros(HEIGHT, WIDTH, 3, device="cuda") for _ in range(2 if world > 1 else 1)]
-    accum = torch.zeros(HEIGHT, WIDTH, 3, device="cuda") if (world > 1 and rank == 0) else None
-    pending = [None, None]
-    comm = torch.cuda.Stream() if world > 1 else None
-
-    def retire(k):
-        """wait for buffer k's reduce, fold it into the root's accumulator, zero it for reuse"""
-        if pending[k] is not None:
-            pending[k].wait()
-            torch.cuda.current_stream().wait_stream(comm)
-            if accum is not None:
-                accum.add_(fbs[k])
-            fbs[k].zero_()
-            pending[k] = None
+    red = P.FramebufferReducer(HEIGHT, WIDTH, "cuda", rank, world, dist if world > 1 else None)
 
     def step(s, last=False):
-        k = s % len(fbs)
-        if world > 1:
-            retire(k)
-        r.set_framebuffer(fbs[k].data_ptr())
+        r.set_framebuffer(red.acquire(s).data_ptr())
         r.render_pass(next_first(), n_pass, st, streaming=not last)     # the last one flushes the stragglers
-        if world > 1:
-            comm.wait_stream(torch.cuda.current_stream())
-            with torch.cuda.stream(comm):
-                pending[k] = dist.reduce(fbs[k], 0, async_op=True)
+        red.submit(s)
 
     for s in range(warmup):
         step(s, last=(s == warmup - 1))
-    if world > 1:
-        retire(0), retire(1)
+    red.clear()
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
-    for f in fbs:
-        f.zero_()
-    if accum is not None:
-        accum.zero_()
     r.clear()
     r.instrument(True, False)
     sampler = ClockSampler(local)
@@ -306,8 +283,7 @@ def main():
     e0.record()
     for s in range(args.steps):
         step(s, last=(s == args.steps - 1))
-    if world > 1:
-        retire(0), retire(1)
+    fb_sum = red.finish()
     e1.record()
     torch.cuda.synchronize()
     if world > 1:
@@ -324,8 +300,7 @@ def main():
     clocks = sampler.summary() if rank == 0 else None
     image_mean = None
     if rank == 0:
-        fb = accum if accum is not None else fbs[0]
-        image_mean = [float(x) for x in (fb.mean(dim=(0, 1)) * (cam.iso / (100.0 * args.steps * world))).tolist()]
+        image_mean = [float(x) for x in (fb_sum.mean(dim=(0, 1)) * (cam.iso / (100.0 * args.steps * world))).tolist()]
 
     # ---- e2e: host-side render module (MOD_render=b200), host framebuffer after every progression
     e2e = None

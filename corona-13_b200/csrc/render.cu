@@ -549,6 +549,38 @@ k_nee_resolve(RenderDev R, uint32_t n, const NeeRec *__restrict__ recs, const in
   if(m && (threadIdx.x & 31u) == 0) atomicAdd(&cnt->splats, (unsigned long long)__popc(m));
 }
 
+__global__ void k_bsdf(MaterialsDev M, int32_t material, const cb_bsdf_query_t *__restrict__ q, cb_bsdf_result_t *__restrict__ out, uint32_t n)
+{
+  const uint32_t i = blockIdx.x*blockDim.x + threadIdx.x;
+  if(i >= n) return;
+  const cb_bsdf_query_t Q = q[i];
+  Vtx v;
+  v.x = mk3(0.0f, 0.0f, 0.0f);
+  v.n = v.gn = mk3(0.0f, 0.0f, Q.flip ? -1.0f : 1.0f);
+  onb(v.n, v.a, v.b);
+  v.u = v.v = v.s = v.t = 0.0f;
+  v.prim_lo = 0u; v.prim_hi = CB_PRIM_LINE << 29;   // battle-test.c:84-88: shape 0, vcnt 2
+  v.flags = 0; v.mode = M_ABSORB; v.material_modes = 0;
+  v.rd = Q.rd; v.rs = Q.rs; v.rg = Q.rg; v.em = 0.0f; v.roughness = Q.roughness;
+  v.ior = 1.0f; v.eta = 1.0f; v.mat = material;
+  Media med; med.n = 0;
+  for(int k=0;k<MED_MAX;k++) { med.shape[k] = 0; med.ior[k] = 1.0f; }
+  const float cur_ior = 1.0f;
+  bsdf_prepare(M, v, Q.lambda, med, cur_ior);
+  const V3 wi = mk3(Q.wi[0], Q.wi[1], Q.wi[2]), wo_q = mk3(Q.wo[0], Q.wo[1], Q.wo[2]);
+  cb_bsdf_result_t R;
+  Vtx vs = v;
+  V3 wo = mk3(0.0f, 0.0f, 0.0f);
+  float pdf = 1.0f;
+  R.s_weight = bsdf_sample(M, vs, wi, Q.lambda, cur_ior, Q.rand[0], Q.rand[1], Q.rand[2], wo, pdf);
+  R.s_wo[0] = wo.x; R.s_wo[1] = wo.y; R.s_wo[2] = wo.z; R.s_pdf = pdf; R.s_mode = vs.mode;
+  Vtx vb = v;
+  R.f = bsdf_eval(M, vb, wi, wo_q, Q.lambda, cur_ior);
+  R.f_mode = vb.mode;
+  R.pdf = bsdf_pdf(M, vb, wi, wo_q);
+  out[i] = R;
+}
+
 __global__ void k_points(PointsDev P, const uint64_t *index, const int32_t *dim, float *out, uint32_t n)
 {
   const uint32_t i = blockIdx.x*blockDim.x + threadIdx.x;
@@ -1040,6 +1072,20 @@ int cb200_render_point(cb200_render_t *r, const uint64_t *index, const int32_t *
   cb200_count_launch();
   CB_CUDA(cudaMemcpy(out, d_o, n*4, cudaMemcpyDeviceToHost));
   cudaFree(d_i); cudaFree(d_d); cudaFree(d_o);
+  return 0;
+}
+
+int cb200_render_bsdf(cb200_render_t *r, int32_t material, const cb_bsdf_query_t *queries, cb_bsdf_result_t *results, uint64_t n)
+{
+  if(!r || !queries || !results || material < 0 || material >= r->desc.num_materials || r->desc.materials[material].num_ops < 0)
+  { cb200_set_error("render_bsdf: bad arguments"); return CB200_ERR_ARG; }
+  cb_bsdf_query_t *d_q = nullptr; cb_bsdf_result_t *d_o = nullptr;
+  CB_CUDA(cudaMalloc(&d_q, (n + 1)*sizeof(cb_bsdf_query_t))); CB_CUDA(cudaMalloc(&d_o, (n + 1)*sizeof(cb_bsdf_result_t)));
+  CB_CUDA(cudaMemcpy(d_q, queries, n*sizeof(cb_bsdf_query_t), cudaMemcpyHostToDevice));
+  if(n) k_bsdf<<<(unsigned)((n + 127)/128), 128>>>(r->dev.mats, material, d_q, d_o, (uint32_t)n);
+  cb200_count_launch();
+  CB_CUDA(cudaMemcpy(results, d_o, n*sizeof(cb_bsdf_result_t), cudaMemcpyDeviceToHost));
+  cudaFree(d_q); cudaFree(d_o);
   return 0;
 }
 

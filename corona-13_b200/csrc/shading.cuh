@@ -306,6 +306,31 @@ CBD float dielectric_ior(float n_d, float V_d, float lambda)   // spectrum.h:40-
 #define HALFVEC_COS_THR .999f
 CBD bool indexmatched(float n1, float n2) { return fabsf(1.0f - n1/n2) < 1e-3f; }
 
+// the host bsdf's own prepare() (diffuse: shader.c:157-162, dielectric.c:67-81, metal.c:71-77) and the cached eta ratio
+// (shader.c:538): runs after the material chain has filled the shading slots
+CBD void bsdf_prepare(const MaterialsDev &M, Vtx &v, float lambda, const Media &med, float cur_ior)
+{
+  const cb_material_t &m = M.mat[v.mat];
+  if(m.bsdf == CB_BSDF_DIFFUSE)
+  {
+    if(v.rd > 0.0f) v.material_modes = M_REFLECT | M_DIFFUSE;
+  }
+  else if(m.bsdf == CB_BSDF_DIELECTRIC)
+  {
+    v.ior = dielectric_ior(m.param[0], m.param[1], lambda);
+    v.material_modes = M_REFLECT | M_TRANSMIT;
+    const float eta = eta_ratio(med, cur_ior, v);
+    if(indexmatched(eta, 1.0f)) v.roughness = 0.0f;
+    if(v.roughness > DIEL_GLOSSY_THR) v.material_modes |= M_GLOSSY; else v.material_modes |= M_SPECULAR;
+  }
+  else if(m.bsdf == CB_BSDF_METAL)
+  {
+    v.material_modes = M_REFLECT;
+    if(v.roughness > METAL_GLOSSY_THR) v.material_modes |= M_GLOSSY; else v.material_modes |= M_SPECULAR;
+  }
+  v.eta = eta_ratio(med, cur_ior, v);
+}
+
 // shader_prepare for a surface vertex whose x, u, v, prim are set and whose incoming direction is `omega`
 CBD void prepare_vertex(const SceneGeo &S, const MaterialsDev &M, Vtx &v, V3 omega, float time, float lambda, float scramble,
                         const Media &med, float cur_ior)
@@ -339,24 +364,7 @@ CBD void prepare_vertex(const SceneGeo &S, const MaterialsDev &M, Vtx &v, V3 ome
       set_slot(v, op.slot, val);
     }
   }
-  if(m.bsdf == CB_BSDF_DIFFUSE)
-  {
-    if(v.rd > 0.0f) v.material_modes = M_REFLECT | M_DIFFUSE;
-  }
-  else if(m.bsdf == CB_BSDF_DIELECTRIC)
-  {
-    v.ior = dielectric_ior(m.param[0], m.param[1], lambda);
-    v.material_modes = M_REFLECT | M_TRANSMIT;
-    const float eta = eta_ratio(med, cur_ior, v);
-    if(indexmatched(eta, 1.0f)) v.roughness = 0.0f;
-    if(v.roughness > DIEL_GLOSSY_THR) v.material_modes |= M_GLOSSY; else v.material_modes |= M_SPECULAR;
-  }
-  else if(m.bsdf == CB_BSDF_METAL)
-  {
-    v.material_modes = M_REFLECT;
-    if(v.roughness > METAL_GLOSSY_THR) v.material_modes |= M_GLOSSY; else v.material_modes |= M_SPECULAR;
-  }
-  v.eta = eta_ratio(med, cur_ior, v);
+  bsdf_prepare(M, v, lambda, med, cur_ior);
 }
 
 // ---------------------------------------------------------------------------------------------

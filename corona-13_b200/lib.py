@@ -236,13 +236,14 @@ def _load_render():
     L.cb200_render_stats.argtypes = [vp, vp]
     L.cb200_render_point.argtypes = [vp, vp, vp, vp, u64]
     L.cb200_render_camera_rays.argtypes = [vp, u64, u64, vp, vp]
+    L.cb200_render_bsdf.argtypes = [vp, C.c_int32, vp, vp, u64]
     L._render_ready = True
     return L
 
 
 RENDER_SYMBOLS = ["cb200_render_create", "cb200_render_destroy", "cb200_render_pass", "cb200_render_pass_stream", "cb200_render_flush", "cb200_render_clear", "cb200_render_instrument",
                   "cb200_render_fb_device", "cb200_render_set_framebuffer", "cb200_render_download", "cb200_render_stats", "cb200_render_point",
-                  "cb200_render_camera_rays"]
+                  "cb200_render_camera_rays", "cb200_render_bsdf"]
 
 
 class Render:
@@ -322,6 +323,14 @@ class Render:
         dim = np.ascontiguousarray(dim, np.int32)
         out = np.zeros(len(index), np.float32)
         _check(self.L.cb200_render_point(self.r, _ptr(index), _ptr(dim), _ptr(out), len(index)), "cb200_render_point")
+        return out
+
+    def bsdf(self, material, queries):
+        """battle-test protocol (tools/battle-test.c:57-236) for one material: scene_io.BSDF_QUERY[] -> BSDF_RESULT[]"""
+        from . import scene_io as sio
+        q = np.ascontiguousarray(queries, sio.BSDF_QUERY)
+        out = np.zeros(len(q), sio.BSDF_RESULT)
+        _check(self.L.cb200_render_bsdf(self.r, material, _ptr(q), _ptr(out), len(q)), "cb200_render_bsdf")
         return out
 
     def camera_rays(self, first, n):

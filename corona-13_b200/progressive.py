@@ -1,0 +1,75 @@
+"""Progressive rendering across the GPUs of one box: who renders which path indices, and how the per-rank
+framebuffers come together.
+
+Reference semantics being partitioned: view_render() covers path indices [counter, end) with end = counter + W*H per
+progression (src/view.c:636-638); paths are independent given their index (render_sample_path(i), src/render.d/gi.c:81-88) and
+the only shared state is the additive framebuffer.  Rank g of N renders progressions g, g+N, g+2N, ... -- the very index
+ranges a 1-GPU run uses for those progressions, so the union over ranks after K steps is exactly progressions 0..K*N-1 --
+and each progression's framebuffer is summed into rank 0 with one reduce (NCCL over NVLink on the box, gloo in the CPU tests).
+Buffers are double-buffered: the reduce of progression s runs on a side stream while s+1 renders into the other buffer.
+"""
+import torch
+
+
+def progression_range(step, rank, world, paths_per_progression):
+    """(first_index, count) of the progression rank `rank` renders at its local step `step`"""
+    return (step * world + rank) * paths_per_progression, paths_per_progression
+
+
+class FramebufferReducer:
+    """owns the per-rank accumulation buffers (H x W x 3 float32) and the root's running sum"""
+
+    def __init__(self, height, width, device, rank=0, world=1, dist=None, nbuf=2):
+        self.rank, self.world, self.dist = rank, world, dist
+        self.cuda = torch.device(device).type == "cuda"
+        n = nbuf if world > 1 else 1
+        self.bufs = [torch.zeros(height, width, 3, device=device) for _ in range(n)]
+        self.accum = torch.zeros(height, width, 3, device=device) if (world > 1 and rank == 0) else None
+        self.pending = [None] * n
+        self.comm = torch.cuda.Stream() if (self.cuda and world > 1) else None
+        self.submitted = 0
+
+    def _retire(self, k):
+        if self.pending[k] is None:
+            return
+        self.pending[k].wait()
+        if self.comm is not None:
+            torch.cuda.current_stream().wait_stream(self.comm)
+        if self.accum is not None:
+            self.accum.add_(self.bufs[k])
+        self.bufs[k].zero_()
+        self.pending[k] = None
+
+    def acquire(self, step):
+        """the buffer to render local step `step` into (waits for the reduce that last used it)"""
+        k = step % len(self.bufs)
+        self._retire(k)
+        return self.bufs[k]
+
+    def submit(self, step):
+        """the buffer of local step `step` is complete on the current stream: start summing it into rank 0"""
+        if self.world == 1:
+            return
+        k = step % len(self.bufs)
+        if self.comm is not None:
+            self.comm.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(self.comm):
+                self.pending[k] = self.dist.reduce(self.bufs[k], 0, async_op=True)
+        else:
+            self.pending[k] = self.dist.reduce(self.bufs[k], 0, async_op=True)
+        self.submitted += 1
+
+    def finish(self):
+        """all reduces retired; returns the summed framebuffer on rank 0 (the local one when world == 1), None elsewhere"""
+        for k in range(len(self.bufs)):
+            self._retire(k)
+        if self.world == 1:
+            return self.bufs[0]
+        return self.accum
+
+    def clear(self):
+        self.finish()
+        for b in self.bufs:
+            b.zero_()
+        if self.accum is not None:
+            self.accum.zero_()

@@ -61,6 +61,12 @@ class CRenderStats(C.Structure):
                 ("trav_shadow", C.c_uint64 * 4)]
 
 
+BSDF_QUERY = np.dtype([("wi", "<f4", 3), ("wo", "<f4", 3), ("lambda_", "<f4"), ("rand", "<f4", 3), ("rd", "<f4"), ("rs", "<f4"),
+                       ("rg", "<f4"), ("roughness", "<f4"), ("flip", "<i4")])
+BSDF_RESULT = np.dtype([("s_wo", "<f4", 3), ("s_weight", "<f4"), ("s_pdf", "<f4"), ("s_mode", "<u4"), ("f", "<f4"), ("f_mode", "<u4"),
+                        ("pdf", "<f4")])
+
+
 # ----------------------------------------------------------------------------------------------- camera
 def quat_from_frame(a, b, n):
     """quaternion (w,x,y,z) rotating the unit axes onto the orthonormal right-handed frame (a,b,n)"""

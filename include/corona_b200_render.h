@@ -155,6 +155,31 @@ int  cb200_render_point(cb200_render_t *r, const uint64_t *index, const int32_t 
  * out_aux[n][4] = {pixel_i, pixel_j, lambda, throughput} */
 int  cb200_render_camera_rays(cb200_render_t *r, uint64_t first_index, uint64_t n, cb_ray_t *out_rays, float *out_aux);
 
+/* one BSDF in isolation, the protocol of the reference's tools/battle-test.c:57-236 (regression/0052_dielectric, 0053): a
+ * surface vertex at the origin with n = gn = +z (flip: -z), tangent frame get_onb(n), vacuum outside, the shading slots preset
+ * by the caller, then the host bsdf's prepare(), sample() with the three given random dimensions, and brdf()/pdf() for the
+ * given outgoing direction.  Replaces the dlopen'ed sample/brdf/pdf callbacks (src/shader.h:34-111) for `material`.            */
+typedef struct cb_bsdf_query_t
+{
+  float wi[3];                     /* e[v].omega: unit, pointing AT the surface */
+  float wo[3];                     /* e[v+1].omega for brdf() / pdf() */
+  float lambda;
+  float rand[3];                   /* s_dim_omega_x, s_dim_omega_y, s_dim_scatter_mode (include/pathspace.h:39-45) */
+  float rd, rs, rg, roughness;     /* vertex_shading_t */
+  int32_t flip;
+}
+cb_bsdf_query_t;
+typedef struct cb_bsdf_result_t
+{
+  float s_wo[3], s_weight, s_pdf;  /* sample(): direction, throughput weight f*cos/p, pdf in projected solid angle */
+  uint32_t s_mode;                 /* vertex_scattermode_t bits after sample() */
+  float f;                         /* brdf() */
+  uint32_t f_mode;
+  float pdf;                       /* pdf(p, e1 = v, v, e2 = v+1) */
+}
+cb_bsdf_result_t;
+int  cb200_render_bsdf(cb200_render_t *r, int32_t material, const cb_bsdf_query_t *queries, cb_bsdf_result_t *results, uint64_t n);
+
 #ifdef __cplusplus
 }
 #endif

@@ -168,3 +168,105 @@ def test_unknown_shader_on_a_shape_is_a_hard_error(gpu):
     with pytest.raises(gpu.Cb200Error):
         gpu.Render(acc, g.camera, g.materials, g.w, g.h)      # shape 0 -> shader 8 = medium_rgb: outside the path, no fallback
     acc.close()
+
+
+# --------------------------------------------------------------------------------------------- BSDFs
+def bsdf_materials():
+    """shader index -> material for the cases of tests/golden/bsdf.npz (slots come with the queries, battle-test style)"""
+    IO = cb.scene_io
+    tabs = np.load(os.path.join(GOLDEN, "ref_tables.npz"))
+    ms = IO.MaterialSet()
+    index = {}
+    for name, bsdf, param, table in (("dielectric", IO.BSDF_DIELECTRIC, [1.7, 73.0, 0, 0], None),
+                                     ("dielectric_c10", IO.BSDF_DIELECTRIC, [1.3, 23.0, 0, 0], None),
+                                     ("metal_au", IO.BSDF_METAL, [0, 0, 0, 0], "metal_au"),
+                                     ("metal_ag", IO.BSDF_METAL, [0, 0, 0, 0], "metal_ag"),
+                                     ("diffuse", IO.BSDF_DIFFUSE, [0, 0, 0, 0], None)):
+        m = IO.CMaterial()
+        m.num_ops, m.bsdf = 0, bsdf
+        m.param[:] = param
+        m.table = ms.add_table(360.0, 5.0, tabs[table]) if table else -1
+        index[name] = len(ms.materials)
+        ms.materials.append(m)
+    return ms, index
+
+
+@pytest.fixture(scope="module")
+def bsdf_render(gpu):
+    g = GoldenImage("diffuse_static")
+    acc = gpu.Accel(g.scene).build()
+    ms, index = bsdf_materials()
+    for s in g.scene.shapes:      # the shapes only need SOME valid material; the BSDF entry addresses materials directly
+        pass
+    ms_all = cb.scene_io.MaterialSet()
+    ms_all.materials = list(g.materials.materials) + ms.materials
+    ms_all.tables = ms.tables
+    off = len(g.materials.materials)
+    r = gpu.Render(acc, g.camera, ms_all, g.w, g.h)
+    yield r, {k: v + off for k, v in index.items()}
+    r.close()
+    acc.close()
+
+
+BSDF_OUTLIERS = 2e-3   # fraction of queries allowed to land on the other side of a branch (libm ulps at thresholds)
+
+
+def close_frac(got, want, rtol, atol):
+    return float(np.mean(np.abs(got.astype(np.float64) - want.astype(np.float64)) <= atol + rtol * np.abs(want.astype(np.float64))))
+
+
+@pytest.mark.parametrize("case", ["dielectric", "dielectric_c10", "metal_au", "metal_ag", "diffuse"])
+def test_bsdf_matches_reference_callbacks(bsdf_render, case):
+    """sample() / brdf() / pdf() against the reference's own shader modules, query by query"""
+    r, index = bsdf_render
+    IO = cb.scene_io
+    z = np.load(os.path.join(GOLDEN, "bsdf.npz"))
+    q = np.ascontiguousarray(z[case + "_q"]).view(IO.BSDF_QUERY).reshape(-1)
+    want = np.ascontiguousarray(z[case + "_r"]).view(IO.BSDF_RESULT).reshape(-1)
+    got = r.bsdf(index[case], q)
+    assert np.isfinite(got["s_weight"]).all() and np.isfinite(got["f"]).all() and np.isfinite(got["pdf"]).all()
+    alive = want["s_weight"] > 0
+    assert close_frac(got["s_weight"], want["s_weight"], 2e-4, 1e-6) >= 1 - BSDF_OUTLIERS
+    both = alive & (got["s_weight"] > 0)
+    assert both.sum() >= (1 - BSDF_OUTLIERS) * alive.sum()
+    assert close_frac(got["s_wo"][both], want["s_wo"][both], 0.0, 5e-5) >= 1 - BSDF_OUTLIERS
+    assert close_frac(got["s_pdf"][both], want["s_pdf"][both], 1e-3, 1e-6) >= 1 - BSDF_OUTLIERS
+    assert np.mean(got["s_mode"][both] == want["s_mode"][both]) >= 1 - BSDF_OUTLIERS
+    assert close_frac(got["f"], want["f"], 1e-3, 1e-6) >= 1 - BSDF_OUTLIERS
+    assert close_frac(got["pdf"], want["pdf"], 1e-3, 1e-6) >= 1 - BSDF_OUTLIERS
+    lit = want["f"] > 0
+    assert np.mean(got["f_mode"][lit] == want["f_mode"][lit]) >= 1 - BSDF_OUTLIERS
+
+
+@pytest.mark.parametrize("flip", [0, 1])
+def test_battle_test_protocol(bsdf_render, flip):
+    """regression/0052_dielectric (reflect) and 0053 (transmit): tools/battle-test.c:57-236 on the device BSDF -- lambda 525 nm,
+    roughness 0.4, "dielectric 1.7 73", 4 incident angles u = k/3.5, 8*512^2 samples; the histogram sums of sample() must agree
+    with the integrals of brdf() and pdf() over the disk: the reference's own pass criterion (diff^2 < 1e-5, makebattletest.sh:13-14)"""
+    r, index = bsdf_render
+    IO = cb.scene_io
+    size, spp = 512, 8
+    n = spp * size * size
+    rng = np.random.default_rng(666 + flip)
+    j, i = np.meshgrid(np.arange(size), np.arange(size), indexing="ij")
+    x = (2.0 * i / np.float32(size) - 1.0).astype(np.float32).reshape(-1)
+    y = (2.0 * j / np.float32(size) - 1.0).astype(np.float32).reshape(-1)
+    len2 = x * x + y * y
+    inside = len2 < 1.0
+    for k in range(4):
+        u = np.float32(k / 3.5)
+        q = np.zeros(n, IO.BSDF_QUERY)
+        q["wi"] = np.float32([0.0, np.sqrt(u), (1.0 if flip else -1.0) * np.sqrt(1 - u)])
+        q["lambda_"], q["rd"], q["rs"], q["rg"], q["roughness"], q["flip"] = 525.0, 0.8, 0.06, 1.0, 0.4, flip
+        q["rand"] = rng.random((n, 3), dtype=np.float32)
+        wo = np.stack([x, y, np.sqrt(np.maximum(0.0, 1.0 - len2))], -1).astype(np.float32)
+        q["wo"] = np.tile(wo, (spp, 1))
+        out = r.bsdf(index["dielectric"], q)
+        ok = (out["s_wo"][:, 2] > 0) & (out["s_weight"] > 0)
+        ebsdf = float(out["s_weight"][ok].astype(np.float64).sum() / n)
+        epdf = float(ok.sum() / n)
+        grid = slice(0, size * size)                          # one evaluation per pixel is enough: brdf()/pdf() are deterministic
+        bsdf = float((out["f"][grid][inside].astype(np.float64) * 4.0 / (size * size)).sum())
+        pdf = float((out["pdf"][grid][inside].astype(np.float64) * 4.0 / (size * size)).sum())
+        assert (bsdf - ebsdf) ** 2 < 1e-5, f"angle {k}: ebsdf {ebsdf:.5f} vs bsdf {bsdf:.5f}"
+        assert (pdf - epdf) ** 2 < 1e-5, f"angle {k}: epdf {epdf:.5f} vs pdf {pdf:.5f}"
