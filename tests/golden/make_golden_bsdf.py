@@ -57,6 +57,36 @@ def queries(rng, roughness, n_random=1500):
     return out
 
 
+def battle_queries(flip, k, size=512, spp=8):
+    """tools/battle-test.c:108-211 for incident angle k: spp*size^2 sample() draws + one brdf()/pdf() evaluation per disk pixel"""
+    n = spp * size * size
+    rng = np.random.default_rng(666 + flip)
+    for _ in range(k):
+        rng.random((n, 3), dtype=np.float32)                  # angle k uses the k-th block of the stream
+    j, i = np.meshgrid(np.arange(size), np.arange(size), indexing="ij")
+    x = (2.0 * i / np.float32(size) - 1.0).astype(np.float32).reshape(-1)
+    y = (2.0 * j / np.float32(size) - 1.0).astype(np.float32).reshape(-1)
+    len2 = x * x + y * y
+    u = np.float32(k / 3.5)
+    q = np.zeros(n, IO.BSDF_QUERY)
+    q["wi"] = np.float32([0.0, np.sqrt(u), (1.0 if flip else -1.0) * np.sqrt(1 - u)])
+    q["lambda_"], q["rd"], q["rs"], q["rg"], q["roughness"], q["flip"] = 525.0, 0.8, 0.06, 1.0, 0.4, flip
+    q["rand"] = rng.random((n, 3), dtype=np.float32)
+    q["wo"] = np.tile(np.stack([x, y, np.sqrt(np.maximum(0.0, 1.0 - len2))], -1).astype(np.float32), (spp, 1))
+    return q, len2 < 1.0
+
+
+def battle_sums(out, inside, size=512):
+    """(ebsdf, bsdf, epdf, pdf) as battle-test prints them (tools/battle-test.c:155-162,213-219)"""
+    n = len(out)
+    ok = (out["s_wo"][:, 2] > 0) & (out["s_weight"] > 0)
+    g = slice(0, size * size)
+    return (float(out["s_weight"][ok].astype(np.float64).sum() / n),
+            float((out["f"][g][inside].astype(np.float64) * 4.0 / (size * size)).sum()),
+            float(ok.sum() / n),
+            float((out["pdf"][g][inside].astype(np.float64) * 4.0 / (size * size)).sum()))
+
+
 if __name__ == "__main__":
     subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "oracle"), "ref"])
     L = C.CDLL(os.path.join(REFDIR, "libref_bsdf.so"), mode=C.RTLD_GLOBAL)   # the shader modules resolve pointsampler / rt / path_eta_ratio against it
@@ -76,5 +106,16 @@ if __name__ == "__main__":
         ok = out["s_weight"] > 0
         print(f"{name}: {len(q)} queries, sample() > 0 in {ok.mean():.2f}, brdf() > 0 in {(out['f'] > 0).mean():.2f}, pdf() > 0 in {(out['pdf'] > 0).mean():.2f}, "
               f"mean weight {out['s_weight'][ok].mean():.4f}, NaNs {np.isnan(out['s_weight']).sum() + np.isnan(out['f']).sum()}")
+    # regression/0052_dielectric (reflect) and 0053 (transmit) run on the reference's own module
+    h = L.ref_bsdf_open(os.path.join(REFDIR, "shaders", "libdielectric.so").encode(), b"1.7 73")
+    sums = np.zeros((2, 4, 4))
+    for flip in (0, 1):
+        for k in range(4):
+            q, inside = battle_queries(flip, k)
+            out = np.zeros(len(q), IO.BSDF_RESULT)
+            L.ref_bsdf_eval(h, q.ctypes.data, out.ctypes.data, len(q))
+            sums[flip, k] = battle_sums(out, inside)
+            print("battle-test reference", "transmit" if flip else "reflect", k, sums[flip, k], flush=True)
+    pack["battle_sums"] = sums
     np.savez_compressed(os.path.join(HERE, "bsdf.npz"), **pack)
     print("wrote bsdf.npz", os.path.getsize(os.path.join(HERE, "bsdf.npz")) // 1024, "KiB")

@@ -241,32 +241,24 @@ def test_bsdf_matches_reference_callbacks(bsdf_render, case):
 @pytest.mark.parametrize("flip", [0, 1])
 def test_battle_test_protocol(bsdf_render, flip):
     """regression/0052_dielectric (reflect) and 0053 (transmit): tools/battle-test.c:57-236 on the device BSDF -- lambda 525 nm,
-    roughness 0.4, "dielectric 1.7 73", 4 incident angles u = k/3.5, 8*512^2 samples; the histogram sums of sample() must agree
-    with the integrals of brdf() and pdf() over the disk: the reference's own pass criterion (diff^2 < 1e-5, makebattletest.sh:13-14)"""
+    roughness 0.4, "dielectric 1.7 73", 4 incident angles u = k/3.5, 8*512^2 samples.  The four sums battle-test prints
+    (histogram estimates of sample() against the disk integrals of brdf() and pdf()) must equal those of the REFERENCE's own
+    module on the same queries (tests/golden/bsdf.npz, battle_sums), and satisfy the reference's pass criterion
+    (diff^2 < 1e-5, makebattletest.sh:13-14) wherever the reference's module satisfies it itself: its transmit lobe does not
+    (sample() weights and brdf() disagree by up to 0.09 there), and a drop-in must reproduce that, not repair it."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("make_golden_bsdf", os.path.join(GOLDEN, "make_golden_bsdf.py"))
+    mg = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mg)
     r, index = bsdf_render
-    IO = cb.scene_io
-    size, spp = 512, 8
-    n = spp * size * size
-    rng = np.random.default_rng(666 + flip)
-    j, i = np.meshgrid(np.arange(size), np.arange(size), indexing="ij")
-    x = (2.0 * i / np.float32(size) - 1.0).astype(np.float32).reshape(-1)
-    y = (2.0 * j / np.float32(size) - 1.0).astype(np.float32).reshape(-1)
-    len2 = x * x + y * y
-    inside = len2 < 1.0
+    ref = np.load(os.path.join(GOLDEN, "bsdf.npz"))["battle_sums"][flip]
     for k in range(4):
-        u = np.float32(k / 3.5)
-        q = np.zeros(n, IO.BSDF_QUERY)
-        q["wi"] = np.float32([0.0, np.sqrt(u), (1.0 if flip else -1.0) * np.sqrt(1 - u)])
-        q["lambda_"], q["rd"], q["rs"], q["rg"], q["roughness"], q["flip"] = 525.0, 0.8, 0.06, 1.0, 0.4, flip
-        q["rand"] = rng.random((n, 3), dtype=np.float32)
-        wo = np.stack([x, y, np.sqrt(np.maximum(0.0, 1.0 - len2))], -1).astype(np.float32)
-        q["wo"] = np.tile(wo, (spp, 1))
-        out = r.bsdf(index["dielectric"], q)
-        ok = (out["s_wo"][:, 2] > 0) & (out["s_weight"] > 0)
-        ebsdf = float(out["s_weight"][ok].astype(np.float64).sum() / n)
-        epdf = float(ok.sum() / n)
-        grid = slice(0, size * size)                          # one evaluation per pixel is enough: brdf()/pdf() are deterministic
-        bsdf = float((out["f"][grid][inside].astype(np.float64) * 4.0 / (size * size)).sum())
-        pdf = float((out["pdf"][grid][inside].astype(np.float64) * 4.0 / (size * size)).sum())
-        assert (bsdf - ebsdf) ** 2 < 1e-5, f"angle {k}: ebsdf {ebsdf:.5f} vs bsdf {bsdf:.5f}"
-        assert (pdf - epdf) ** 2 < 1e-5, f"angle {k}: epdf {epdf:.5f} vs pdf {pdf:.5f}"
+        q, inside = mg.battle_queries(flip, k)
+        ebsdf, bsdf, epdf, pdf = mg.battle_sums(r.bsdf(index["dielectric"], q), inside)
+        assert np.allclose([ebsdf, bsdf, epdf, pdf], ref[k], rtol=0, atol=2e-4), f"angle {k}: {(ebsdf, bsdf, epdf, pdf)} vs reference {ref[k]}"
+        if (ref[k][0] - ref[k][1]) ** 2 < 1e-5:
+            assert (bsdf - ebsdf) ** 2 < 1e-5, f"angle {k}: ebsdf {ebsdf:.5f} vs bsdf {bsdf:.5f}"
+        if (ref[k][2] - ref[k][3]) ** 2 < 1e-5:
+            assert (pdf - epdf) ** 2 < 1e-5, f"angle {k}: epdf {epdf:.5f} vs pdf {pdf:.5f}"
+    if flip == 0:
+        assert all((ref[k][0] - ref[k][1]) ** 2 < 1e-5 and (ref[k][2] - ref[k][3]) ** 2 < 1e-5 for k in range(4))   # 0052 passes in the reference
