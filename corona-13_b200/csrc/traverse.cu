@@ -334,7 +334,7 @@ k_intersect(DevAccel A, const cb_ray_t *__restrict__ rays, const float *__restri
 //           primitive skip[i] never occludes.  The caller has already clipped max_dist to the first crossing of the light
 //           primitive itself, so "any accepted primitive" == "the closest hit is not the light".
 template<bool MB, int STACK, bool ANALYTIC, bool SHADOW>
-__global__ void __launch_bounds__(TRACE_BLOCK)
+__global__ void __launch_bounds__(TRACE_BLOCK, (!MB && !ANALYTIC) ? TRACE_MIN_BLOCKS : 1)
 k_visible(DevAccel A, const cb_ray_t *__restrict__ rays, const float *__restrict__ max_dist, const uint2 *__restrict__ skip,
           int32_t *__restrict__ out, uint64_t n, unsigned long long *ticket, int prim_threshold, int refill_threshold)
 {

@@ -262,3 +262,66 @@ def test_battle_test_protocol(bsdf_render, flip):
             assert (pdf - epdf) ** 2 < 1e-5, f"angle {k}: epdf {epdf:.5f} vs pdf {pdf:.5f}"
     if flip == 0:
         assert all((ref[k][0] - ref[k][1]) ** 2 < 1e-5 and (ref[k][2] - ref[k][3]) ** 2 < 1e-5 for k in range(4))   # 0052 passes in the reference
+
+
+# --------------------------------------------------------------------------------------------- edge cases
+def test_empty_ranges_and_dark_scenes(gpu):
+    """count == 0 is a no-op; a scene without emitters renders black without tracing shadow rays; a camera looking away from
+    everything traces exactly one ray per path"""
+    IO = cb.scene_io
+    g = GoldenImage("diffuse_static")
+    acc = gpu.Accel(g.scene).build()
+    r = gpu.Render(acc, g.camera, g.materials, g.w, g.h, frame=1, **GoldenImage.variant_args("ptdl_halton"))
+    r.render_pass(0, 0)
+    assert r.stats()["paths"] == 0 and float(np.abs(r.framebuffer()).sum()) == 0.0
+    r.render_pass(5, 1)                         # a single path
+    assert r.stats()["paths"] == 1
+    r.close()
+    # no emitter: every material diffuse grey
+    dark = IO.MaterialSet()
+    dark.materials = [g.materials.materials[2]] * len(g.materials.materials)
+    r = gpu.Render(acc, g.camera, dark, g.w, g.h, frame=1, **GoldenImage.variant_args("ptdl_halton"))
+    r.render_pass()
+    st = r.stats()
+    assert st["rays_shadow"] == 0 and st["splats"] == 0 and float(np.abs(r.framebuffer()).sum()) == 0.0
+    r.close()
+    away = IO.Camera(pos=(0.0, 0.0, 50.0), lookat=(0.0, 0.0, 100.0), up=(0, 1, 0), focal_length=0.35)
+    r = gpu.Render(acc, away, g.materials, g.w, g.h, frame=1, **GoldenImage.variant_args("pt_halton"))
+    r.render_pass()
+    st = r.stats()
+    assert st["rays_closest"] == st["paths"] == r.width * r.height and st["splats"] == 0
+    r.close()
+    acc.close()
+
+
+def test_streaming_equals_flushed_passes(gpu):
+    """cb200_render_pass_stream + flush accumulates the same image as complete passes (stragglers only arrive later)"""
+    g = GoldenImage("glass_metal")
+    acc = gpu.Accel(g.scene).build()
+    args = GoldenImage.variant_args("ptdl_halton")
+    a = gpu.Render(acc, g.camera, g.materials, g.w, g.h, frame=1, **args)
+    b = gpu.Render(acc, g.camera, g.materials, g.w, g.h, frame=1, batch_paths=30000, **args)
+    for _ in range(3):
+        a.render_pass()
+        b.render_pass(streaming=True)
+    assert b.stats()["paths"] == a.stats()["paths"]
+    fa, fb = a.framebuffer(), b.framebuffer()          # download implies the flush
+    sa, sb = a.stats(), b.stats()
+    assert sa["rays_closest"] == sb["rays_closest"] and sa["rays_shadow"] == sb["rays_shadow"] and sa["splats"] == sb["splats"]
+    assert np.allclose(fa, fb, rtol=2e-4, atol=1e-6 * fa.max())
+    a.close(), b.close(), acc.close()
+
+
+def test_empty_scene_renders_black(gpu):
+    IO = cb.scene_io
+    empty = S.Scene([S.Shape(np.zeros(0, np.uint64), np.zeros(0, cb.records.VTXIDX), np.zeros(0, cb.records.VTX), 0, "none")], "empty")
+    acc = gpu.Accel(empty).build()
+    ms = IO.MaterialSet()
+    m = IO.CMaterial()
+    m.num_ops, m.bsdf = 0, IO.BSDF_DIFFUSE
+    ms.materials = [m]
+    r = gpu.Render(acc, IO.Camera(pos=(0, -5, 1), lookat=(0, 0, 1)), ms, 64, 32, frame=0)
+    r.render_pass()
+    st = r.stats()
+    assert st["paths"] == 64 * 32 == st["rays_closest"] and float(np.abs(r.framebuffer()).sum()) == 0.0
+    r.close(), acc.close()
