@@ -95,8 +95,9 @@ int  cb200_sm_count_cached();
 int cb200_build_lbvh(cb200_accel *a, const float *ghost_aabb);
 int cb200_build_records(cb200_accel *a, cudaStream_t stream);
 // traverse.cu
+// d_order (optional): process ray d_order[k] as the k-th ray; results still land in d_out[d_order[k]]
 int cb200_launch_intersect(const cb200_accel *a, const cb_ray_t *d_rays, const float *d_max_dist, cb_hitrec_t *d_out,
-                           uint64_t n, cudaStream_t stream, unsigned long long *d_counters);
+                           uint64_t n, cudaStream_t stream, unsigned long long *d_counters, const uint32_t *d_order = nullptr);
 int cb200_launch_visible(const cb200_accel *a, const cb_ray_t *d_rays, const float *d_max_dist, int32_t *d_out,
                          uint64_t n, cudaStream_t stream);
 // next-event visibility (path_visible semantics): any primitive other than d_light_prim[i] accepted by the closest-hit rules

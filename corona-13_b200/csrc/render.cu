@@ -71,6 +71,7 @@ struct RenderDev
   float *fb;
   uint32_t fb_w, fb_h;
   int32_t sampler, colour, max_path_len;
+  float box_lo[3], box_scale[3];   // scene box -> 7-bit cell per axis (ray coherence keys)
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -227,6 +228,27 @@ __device__ __forceinline__ uint32_t part1by1(uint32_t x)
   x = (x | (x << 1)) & 0x55555555u;
   return x;
 }
+// coherence key of a ray: Morton code of the origin's cell in a 128^3 grid over the scene box (21 bits) + direction octant
+// (3 bits).  Waves are TRACED in key order (k_intersect's `order`), storage order is untouched.
+__device__ __forceinline__ uint32_t part1by2(uint32_t x)
+{
+  x &= 0x000003ffu;
+  x = (x ^ (x << 16)) & 0xff0000ffu;
+  x = (x ^ (x << 8))  & 0x0300f00fu;
+  x = (x ^ (x << 4))  & 0x030c30c3u;
+  x = (x ^ (x << 2))  & 0x09249249u;
+  return x;
+}
+__device__ __forceinline__ uint32_t ray_key(const RenderDev &R, V3 pos, V3 dir)
+{
+  const float fx = fminf(fmaxf((pos.x - R.box_lo[0])*R.box_scale[0], 0.0f), 127.0f);
+  const float fy = fminf(fmaxf((pos.y - R.box_lo[1])*R.box_scale[1], 0.0f), 127.0f);
+  const float fz = fminf(fmaxf((pos.z - R.box_lo[2])*R.box_scale[2], 0.0f), 127.0f);
+  const uint32_t m = part1by2((uint32_t)fx) | (part1by2((uint32_t)fy) << 1) | (part1by2((uint32_t)fz) << 2);
+  const uint32_t oct = (__float_as_uint(dir.x) >> 31) | ((__float_as_uint(dir.y) >> 31) << 1) | ((__float_as_uint(dir.z) >> 31) << 2);
+  return (m << 3) | oct;
+}
+
 __global__ void __launch_bounds__(RB)
 k_pixel_keys(RenderDev R, uint64_t first_index, uint32_t n, uint32_t *keys, uint32_t *vals)
 {
@@ -240,7 +262,8 @@ k_pixel_keys(RenderDev R, uint64_t first_index, uint32_t n, uint32_t *keys, uint
 }
 
 __global__ void __launch_bounds__(RB)
-k_path_start(RenderDev R, uint64_t first_index, uint32_t n, const uint32_t *__restrict__ order, PathState *st, cb_ray_t *rays, float *aux)
+k_path_start(RenderDev R, uint64_t first_index, uint32_t n, const uint32_t *__restrict__ order, PathState *st, cb_ray_t *rays, float *aux,
+             uint32_t *rkeys)
 {
   const uint32_t i = blockIdx.x*blockDim.x + threadIdx.x;
   if(i >= n) return;
@@ -249,6 +272,7 @@ k_path_start(RenderDev R, uint64_t first_index, uint32_t n, const uint32_t *__re
   path_start(R, first_index + (order ? order[i] : i), s, pos);   // st / rays already point at the first free slot of the pool
   write_ray(rays, i, pos, mk3(s.omega[0], s.omega[1], s.omega[2]), s.time, 0xffffffffu, 0xffffffffu);
   if(st) st[i] = s;
+  if(rkeys) rkeys[i] = ray_key(R, pos, mk3(s.omega[0], s.omega[1], s.omega[2]));
   if(aux) { aux[4*i+0] = s.pixel_i; aux[4*i+1] = s.pixel_j; aux[4*i+2] = s.lambda; aux[4*i+3] = s.thr; }
 }
 
@@ -313,12 +337,15 @@ __device__ __forceinline__ float cos_lambert(const Vtx &v, const Vtx &l, V3 d, f
   return fabsf(dot(v.n, d))*fabsf(dot(l.n, d))/(dist*dist);
 }
 
-// one vertex of every live path
+// one vertex of every live path.  KINDS = bit mask of the BSDF kinds the scene's shapes use (1 diffuse, 2 dielectric,
+// 4 metal): a diffuse-only scene gets a kernel without the GGX / Fresnel / nested-media code (a third of the instructions,
+// fewer instruction-cache misses -- 24 % of k_shade's stall samples in the generic kernel were "no instruction")
+template<int KINDS>
 __global__ void __launch_bounds__(RB)
 k_shade(RenderDev R, uint32_t n, const PathState *__restrict__ st_in, const cb_ray_t *__restrict__ rays_in,
         const cb_hitrec_t *__restrict__ hits, PathState *__restrict__ st_out, cb_ray_t *__restrict__ rays_out,
         cb_ray_t *__restrict__ nee_rays, float *__restrict__ nee_maxdist, uint2 *__restrict__ nee_light, NeeRec *__restrict__ nee_recs,
-        ShadeCounters *cnt)
+        ShadeCounters *cnt, uint32_t *__restrict__ rkeys_out)
 {
   const uint32_t i = blockIdx.x*blockDim.x + threadIdx.x;
   bool alive = false, have_nee = false, did_splat = false;
@@ -343,7 +370,7 @@ k_shade(RenderDev R, uint32_t n, const PathState *__restrict__ st_in, const cb_r
       v.x = mk3(ray.pos[0] + h.dist*ray.dir[0], ray.pos[1] + h.dist*ray.dir[1], ray.pos[2] + h.dist*ray.dir[2]);
       Media med; med.n = s.med_n;
       for(int k=0;k<MED_MAX;k++) { med.shape[k] = s.med_shape[k]; med.ior[k] = s.med_ior[k]; }
-      prepare_vertex(R.geo, R.mats, v, omega, s.time, s.lambda, s.scramble, med, s.cur_ior);
+      prepare_vertex<KINDS>(R.geo, R.mats, v, omega, s.time, s.lambda, s.scramble, med, s.cur_ior);
       // self intersection (pathspace.c:809-820)
       const uint32_t vcnt = v.prim_hi >> 29;
       const bool self = (vcnt > 2 || h.dist < 1e-4f) && v.prim_lo == s.prim_lo && v.prim_hi == s.prim_hi;
@@ -407,7 +434,7 @@ k_shade(RenderDev R, uint32_t n, const PathState *__restrict__ st_in, const cb_r
                 const float dist = sqrtf(dot(d, d));
                 const float il = (float)(1.0/(double)dist);
                 d = mk3(d.x*il, d.y*il, d.z*il);
-                prepare_vertex(R.geo, R.mats, l, d, s.time, s.lambda, s.scramble, med, s.cur_ior);
+                prepare_vertex<KINDS>(R.geo, R.mats, l, d, s.time, s.lambda, s.scramble, med, s.cur_ior);
                 const float pdf_l = R.lights.L[t];
                 float edf = l.em/pdf_l;
                 if(l.roughness > 1.0f - 1e-4f) edf *= (float)(1.0/PI_D);
@@ -420,7 +447,7 @@ k_shade(RenderDev R, uint32_t n, const PathState *__restrict__ st_in, const cb_r
                 if(edf > 0.0f)
                 {
                   Vtx vb = v;   // shader_brdf sets the mode on v; path_pop resets it afterwards
-                  const float bsdf = bsdf_eval(R.mats, vb, omega, d, s.lambda, s.cur_ior);
+                  const float bsdf = bsdf_eval<KINDS>(R.mats, vb, omega, d, s.lambda, s.cur_ior);
                   if(bsdf > 0.0f)
                   {
                     // path_visible: prims_get_ray (prims.c:390-492)
@@ -437,7 +464,7 @@ k_shade(RenderDev R, uint32_t n, const PathState *__restrict__ st_in, const cb_r
                       const float thr_l = ((thr*bsdf)*(1.0f*edf))*Gl;
                       // mis against extending the path into the light (ptdl.c:142-146)
                       const float pdf_nee = R.lights.p_geo*pdf_l;
-                      const float pdf_ext = bsdf_pdf(R.mats, vb, omega, d)*Gl;
+                      const float pdf_ext = bsdf_pdf<KINDS>(R.mats, vb, omega, d)*Gl;
                       const float w = pdf_nee/(pdf_ext + pdf_nee);
                       if(thr_l > 0.0f)
                       {
@@ -471,7 +498,7 @@ k_shade(RenderDev R, uint32_t n, const PathState *__restrict__ st_in, const cb_r
           V3 wo; float pdf = 1.0f;
           v.mode &= M_EMIT;
           const uint32_t keep_emit = v.mode;
-          float weight = bsdf_sample(R.mats, v, omega, s.lambda, s.cur_ior, rx, ry, rm, wo, pdf);
+          float weight = bsdf_sample<KINDS>(R.mats, v, omega, s.lambda, s.cur_ior, rx, ry, rm, wo, pdf);
           wo = normalise(wo);
           const float dt = ((v.flags & F_INSIDE) ? -1.0f : 1.0f)*dot(v.gn, wo);
           if(((v.mode & M_REFLECT) && dt < 0.0f) || ((v.mode & M_TRANSMIT) && dt > 0.0f)) weight = 0.0f;
@@ -516,6 +543,7 @@ k_shade(RenderDev R, uint32_t n, const PathState *__restrict__ st_in, const cb_r
       const uint64_t o = base + __popc(ma & ((1u << lane) - 1u));
       st_out[o] = s;
       write_ray(rays_out, o, next_pos, next_dir, s.time, s.prim_lo, s.prim_hi);
+      if(rkeys_out) rkeys_out[o] = ray_key(R, next_pos, next_dir);
     }
   }
   const uint32_t msp = __ballot_sync(0xffffffffu, did_splat);
@@ -645,6 +673,11 @@ struct cb200_render
   // (st[cur] / rays[cur], slots [0, n_alive)) and ride along with the next pass' waves until cb200_render_flush
   uint32_t n_alive; int cur;
   float *own_fb;
+  // coherence sort of every traced wave: keys ride with the rays (ping-pong), iota -> order by radix sort
+  int ray_sort;
+  int bsdf_kinds;   // bit mask of the BSDF kinds referenced by shapes (selects the k_shade variant)
+  uint32_t *rkeys[2], *rkeys_sorted, *iota, *ray_order;
+  void *rsort_tmp; size_t rsort_tmp_bytes;
   // instrumentation (cb200_render_instrument): CUDA events around every launch on the pass' own stream, summed per
   // kernel class after the pass; ACCEL_DEBUG-style traversal counters
   int timing, counting;
@@ -761,6 +794,9 @@ static int build_lights(cb200_render *r)
     }
   }
   r->dev.geo.shape_material = dev_upload(r, shape_mat.data(), shape_mat.size());
+  r->bsdf_kinds = 0;
+  for(int i=0;i<s->num_shapes;i++) r->bsdf_kinds |= 1 << d.materials[shape_mat[i]].bsdf;
+  if(!r->bsdf_kinds) r->bsdf_kinds = 1;
   std::vector<float> shape_L(s->num_shapes ? s->num_shapes : 1, 0.0f);
   for(int i=0;i<s->num_shapes;i++)
   {
@@ -892,6 +928,29 @@ cb200_render_t *cb200_render_create(cb200_accel_t *a, const cb_render_desc_t *de
     r->sort_tmp = dev_alloc<uint8_t>(r, r->sort_tmp_bytes);
     ok = ok && r->sort_tmp;
   }
+  {
+    const char *e = getenv("CB200_RAY_SORT");
+    r->ray_sort = e ? atoi(e) : 0;   // measured on the 10 M-triangle bench: the sort costs what the coherence gains (+-1 %), so off by default
+    for(int k=0;k<2;k++) { r->rkeys[k] = dev_alloc<uint32_t>(r, N); ok = ok && r->rkeys[k]; }
+    r->rkeys_sorted = dev_alloc<uint32_t>(r, N); r->iota = dev_alloc<uint32_t>(r, N); r->ray_order = dev_alloc<uint32_t>(r, N);
+    ok = ok && r->rkeys_sorted && r->iota && r->ray_order;
+    r->rsort_tmp = nullptr; r->rsort_tmp_bytes = 0;
+    if(ok)
+    {
+      std::vector<uint32_t> h(N);
+      for(uint64_t k=0;k<N;k++) h[k] = (uint32_t)k;
+      ok = cudaMemcpy(r->iota, h.data(), N*sizeof(uint32_t), cudaMemcpyHostToDevice) == cudaSuccess;
+      cub::DeviceRadixSort::SortPairs(nullptr, r->rsort_tmp_bytes, r->rkeys[0], r->rkeys_sorted, r->iota, r->ray_order, (int)N, 0, 24);
+      r->rsort_tmp = dev_alloc<uint8_t>(r, r->rsort_tmp_bytes);
+      ok = ok && r->rsort_tmp;
+    }
+    for(int k=0;k<3;k++)
+    {
+      const float lo = a->aabb[k], hi = a->aabb[3+k];
+      D.box_lo[k] = lo;
+      D.box_scale[k] = (hi > lo) ? 128.0f/(hi - lo) : 0.0f;
+    }
+  }
   r->d_trav_cnt = dev_alloc<unsigned long long>(r, 8);
   if(r->d_trav_cnt) cudaMemset(r->d_trav_cnt, 0, 8*sizeof(unsigned long long));
   ok = ok && r->d_trav_cnt && D.fb && r->hits && r->nee_rays && r->nee_md && r->nee_recs && r->nee_light && r->nee_vis && r->d_cnt;
@@ -958,15 +1017,27 @@ static int render_wave(cb200_render *r, uint32_t n, cudaStream_t st)
   int rc;
   {
     TimeScope ts(r, st, KC_CLOSEST, n);
-    rc = cb200_launch_intersect(r->accel, r->rays[cur], nullptr, r->hits, n, st, r->counting ? r->d_trav_cnt : nullptr);
+    const uint32_t *order = nullptr;
+    if(r->ray_sort)
+    {
+      size_t tmp = r->rsort_tmp_bytes;
+      CB_CUDA(cub::DeviceRadixSort::SortPairs(r->rsort_tmp, tmp, r->rkeys[cur], r->rkeys_sorted, r->iota, r->ray_order, (int)n, 0, 24, st));
+      cb200_count_launch(3); r->stats.kernel_launches += 3;
+      order = r->ray_order;
+    }
+    rc = cb200_launch_intersect(r->accel, r->rays[cur], nullptr, r->hits, n, st, r->counting ? r->d_trav_cnt : nullptr, order);
   }
   if(rc) return rc;
   r->stats.rays_closest += n; r->stats.kernel_launches++;
   CB_CUDA(cudaMemsetAsync(r->d_cnt, 0, 2*sizeof(unsigned long long), st));   // next, nee (splats keeps counting)
   {
     TimeScope ts(r, st, KC_SHADE, n);
-    k_shade<<<(n + RB - 1)/RB, RB, 0, st>>>(r->dev, n, r->st[cur], r->rays[cur], r->hits, r->st[cur^1], r->rays[cur^1],
-                                            r->nee_rays, r->nee_md, r->nee_light, r->nee_recs, r->d_cnt);
+    if(r->bsdf_kinds == 1)
+      k_shade<1><<<(n + RB - 1)/RB, RB, 0, st>>>(r->dev, n, r->st[cur], r->rays[cur], r->hits, r->st[cur^1], r->rays[cur^1],
+                                                 r->nee_rays, r->nee_md, r->nee_light, r->nee_recs, r->d_cnt, r->ray_sort ? r->rkeys[cur^1] : nullptr);
+    else
+      k_shade<7><<<(n + RB - 1)/RB, RB, 0, st>>>(r->dev, n, r->st[cur], r->rays[cur], r->hits, r->st[cur^1], r->rays[cur^1],
+                                                 r->nee_rays, r->nee_md, r->nee_light, r->nee_recs, r->d_cnt, r->ray_sort ? r->rkeys[cur^1] : nullptr);
   }
   cb200_count_launch(); r->stats.kernel_launches++;
   CB_CUDA(cudaMemcpyAsync(r->h_cnt, r->d_cnt, sizeof(ShadeCounters), cudaMemcpyDeviceToHost, st));
@@ -1032,7 +1103,8 @@ int cb200_render_pass_stream(cb200_render_t *r, uint64_t first_index, uint64_t c
       size_t tmp = r->sort_tmp_bytes;
       CB_CUDA(cub::DeviceRadixSort::SortPairs(r->sort_tmp, tmp, r->keys[0], r->keys[1], r->order[0], r->order[1], (int)n_new, 0, 24, st));
       k_path_start<<<(n_new + RB - 1)/RB, RB, 0, st>>>(r->dev, first_index + started, n_new, r->order[1],
-                                                        r->st[r->cur] + r->n_alive, r->rays[r->cur] + r->n_alive, nullptr);
+                                                        r->st[r->cur] + r->n_alive, r->rays[r->cur] + r->n_alive, nullptr,
+                                                        r->ray_sort ? r->rkeys[r->cur] + r->n_alive : nullptr);
       cb200_count_launch(5); r->stats.kernel_launches += 5;   // keys, radix sort (histogram + digit passes, counted as 3), path start
       r->stats.paths += n_new;
       started += n_new;
@@ -1094,7 +1166,7 @@ int cb200_render_camera_rays(cb200_render_t *r, uint64_t first_index, uint64_t n
   if(!r || !out_rays || n > r->batch) { cb200_set_error("render_camera_rays: bad arguments (n must be <= batch_paths)"); return CB200_ERR_ARG; }
   float *d_aux = nullptr;
   CB_CUDA(cudaMalloc(&d_aux, n*16 + 16));
-  if(n) k_path_start<<<(unsigned)((n + RB - 1)/RB), RB>>>(r->dev, first_index, (uint32_t)n, nullptr, nullptr, r->rays[0], d_aux);
+  if(n) k_path_start<<<(unsigned)((n + RB - 1)/RB), RB>>>(r->dev, first_index, (uint32_t)n, nullptr, nullptr, r->rays[0], d_aux, nullptr);
   cb200_count_launch();
   CB_CUDA(cudaMemcpy(out_rays, r->rays[0], n*sizeof(cb_ray_t), cudaMemcpyDeviceToHost));
   if(out_aux) CB_CUDA(cudaMemcpy(out_aux, d_aux, n*16, cudaMemcpyDeviceToHost));

@@ -308,14 +308,15 @@ CBD bool indexmatched(float n1, float n2) { return fabsf(1.0f - n1/n2) < 1e-3f; 
 
 // the host bsdf's own prepare() (diffuse: shader.c:157-162, dielectric.c:67-81, metal.c:71-77) and the cached eta ratio
 // (shader.c:538): runs after the material chain has filled the shading slots
+template<int KINDS = 7>
 CBD void bsdf_prepare(const MaterialsDev &M, Vtx &v, float lambda, const Media &med, float cur_ior)
 {
   const cb_material_t &m = M.mat[v.mat];
-  if(m.bsdf == CB_BSDF_DIFFUSE)
+  if(KINDS == 1 || m.bsdf == CB_BSDF_DIFFUSE)
   {
     if(v.rd > 0.0f) v.material_modes = M_REFLECT | M_DIFFUSE;
   }
-  else if(m.bsdf == CB_BSDF_DIELECTRIC)
+  else if((KINDS & 2) && m.bsdf == CB_BSDF_DIELECTRIC)
   {
     v.ior = dielectric_ior(m.param[0], m.param[1], lambda);
     v.material_modes = M_REFLECT | M_TRANSMIT;
@@ -323,7 +324,7 @@ CBD void bsdf_prepare(const MaterialsDev &M, Vtx &v, float lambda, const Media &
     if(indexmatched(eta, 1.0f)) v.roughness = 0.0f;
     if(v.roughness > DIEL_GLOSSY_THR) v.material_modes |= M_GLOSSY; else v.material_modes |= M_SPECULAR;
   }
-  else if(m.bsdf == CB_BSDF_METAL)
+  else if((KINDS & 4) && m.bsdf == CB_BSDF_METAL)
   {
     v.material_modes = M_REFLECT;
     if(v.roughness > METAL_GLOSSY_THR) v.material_modes |= M_GLOSSY; else v.material_modes |= M_SPECULAR;
@@ -332,6 +333,7 @@ CBD void bsdf_prepare(const MaterialsDev &M, Vtx &v, float lambda, const Media &
 }
 
 // shader_prepare for a surface vertex whose x, u, v, prim are set and whose incoming direction is `omega`
+template<int KINDS = 7>
 CBD void prepare_vertex(const SceneGeo &S, const MaterialsDev &M, Vtx &v, V3 omega, float time, float lambda, float scramble,
                         const Media &med, float cur_ior)
 {
@@ -364,7 +366,7 @@ CBD void prepare_vertex(const SceneGeo &S, const MaterialsDev &M, Vtx &v, V3 ome
       set_slot(v, op.slot, val);
     }
   }
-  bsdf_prepare(M, v, lambda, med, cur_ior);
+  bsdf_prepare<KINDS>(M, v, lambda, med, cur_ior);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -487,11 +489,12 @@ CBD float fresnel_conductor(float n1, float n2, float k2, float cosr)   // metal
   return clamp01((Rs2 + Rp2)*.5f);
 }
 
+template<int KINDS = 7>
 CBD float bsdf_sample(const MaterialsDev &M, Vtx &v, V3 wi, float lambda, float cur_ior, float r_x, float r_y, float r_mode,
                       V3 &wo, float &pdf)
 {
   const cb_material_t &m = M.mat[v.mat];
-  if(m.bsdf == CB_BSDF_DIFFUSE)
+  if(KINDS == 1 || m.bsdf == CB_BSDF_DIFFUSE)
   { // sample_d, shader.c:165-205
     const float x1 = r_x, x2 = r_y;
     const float s = sqrtf(x1);
@@ -506,7 +509,7 @@ CBD float bsdf_sample(const MaterialsDev &M, Vtx &v, V3 wi, float lambda, float 
     if(v.rd > 0.0f) v.mode = M_DIFFUSE | M_REFLECT;
     return v.rd;
   }
-  if(m.bsdf == CB_BSDF_DIELECTRIC)
+  if((KINDS & 2) && m.bsdf == CB_BSDF_DIELECTRIC)
   { // dielectric.c:240-381 (MF_COUNT == 1 branch)
     const float eta = v.eta;
     if(eta < 0.0f) return 0.0f;
@@ -568,6 +571,7 @@ CBD float bsdf_sample(const MaterialsDev &M, Vtx &v, V3 wi, float lambda, float 
     return v.rg*ggx_G1(wo, v.n, v.roughness);
   }
   // metal.c:208-256
+  if(KINDS & 4)
   {
     V3 h = v.n;
     float pdf_h = 1.0f;
@@ -599,13 +603,15 @@ CBD float bsdf_sample(const MaterialsDev &M, Vtx &v, V3 wi, float lambda, float 
     v.mode |= M_SPECULAR;
     return R*v.rg;
   }
+  return 0.0f;   // a material kind this kernel variant was not compiled for: cb200_render_create never selects such a variant
 }
 
 // shader_brdf: evaluates f for (wi -> wo) and sets v.mode
+template<int KINDS = 7>
 CBD float bsdf_eval(const MaterialsDev &M, Vtx &v, V3 wi, V3 wo, float lambda, float cur_ior)
 {
   const cb_material_t &m = M.mat[v.mat];
-  if(m.bsdf == CB_BSDF_DIFFUSE)
+  if(KINDS == 1 || m.bsdf == CB_BSDF_DIFFUSE)
   { // brdf_d (sensor paths), shader.c:207-249
     v.mode = M_DIFFUSE | M_REFLECT;
     const float cos_out_ns = dot(v.n, wo);
@@ -615,7 +621,7 @@ CBD float bsdf_eval(const MaterialsDev &M, Vtx &v, V3 wi, V3 wo, float lambda, f
     else if(cos_out_ng <= 0.0f) return 0.0f;
     return v.rd*(float)(1.0/PI_D);
   }
-  if(m.bsdf == CB_BSDF_DIELECTRIC)
+  if((KINDS & 2) && m.bsdf == CB_BSDF_DIELECTRIC)
   { // dielectric.c:386-510
     const float cos_in = -dot(v.n, wi), cos_out = dot(v.n, wo);
     const float eta = v.eta;
@@ -680,6 +686,7 @@ CBD float bsdf_eval(const MaterialsDev &M, Vtx &v, V3 wi, V3 wo, float lambda, f
     return mask ? 0.0f : v.rg*clamp01(1.0f - R2);
   }
   // metal.c:259-310
+  if(KINDS & 4)
   {
     const float cos_in = -dot(v.n, wi), cos_out = dot(v.n, wo);
     if(cos_out <= 0.0f || cos_in <= 0.0f) return 0.0f;
@@ -699,14 +706,16 @@ CBD float bsdf_eval(const MaterialsDev &M, Vtx &v, V3 wi, V3 wo, float lambda, f
     if(cosh < HALFVEC_COS_THR) return 0.0f;
     return v.rg*R;
   }
+  return 0.0f;
 }
 
 // shader_pdf(p, v) for the forward direction (e1 < e2): projected solid angle pdf of wo given wi, for v.mode
+template<int KINDS = 7>
 CBD float bsdf_pdf(const MaterialsDev &M, const Vtx &v, V3 wi, V3 wo)
 {
   const cb_material_t &m = M.mat[v.mat];
-  if(m.bsdf == CB_BSDF_DIFFUSE) return (float)(1.0/PI_D);
-  if(m.bsdf == CB_BSDF_DIELECTRIC)
+  if(KINDS == 1 || m.bsdf == CB_BSDF_DIFFUSE) return (float)(1.0/PI_D);
+  if((KINDS & 2) && m.bsdf == CB_BSDF_DIELECTRIC)
   { // dielectric.c:96-237, culled_modes == 0
     const V3 n = v.n;
     const float cos_in = -dot(n, wi), cos_out = dot(n, wo);
@@ -769,6 +778,7 @@ CBD float bsdf_pdf(const MaterialsDev &M, const Vtx &v, V3 wi, V3 wo)
     return mask ? 0.0f : pdf;
   }
   // metal.c:166-205
+  if(KINDS & 4)
   {
     if(!(v.mode & M_REFLECT)) return 0.0f;
     const float cos_in = -dot(v.n, wi), cos_out = dot(v.n, wo);
@@ -780,6 +790,7 @@ CBD float bsdf_pdf(const MaterialsDev &M, const Vtx &v, V3 wi, V3 wo)
     pdf /= fabsf(cos_out);
     return pdf > 0.0f ? pdf : 0.0f;
   }
+  return 0.0f;
 }
 
 // lights_eval_vertex for a path that started at the sensor (list.c:242-275): emitted radiance towards -omega_in

@@ -167,7 +167,7 @@ template<bool MB, bool CNT, int STACK, bool ANALYTIC>
 __global__ void __launch_bounds__(TRACE_BLOCK, (!MB && !CNT && !ANALYTIC) ? TRACE_MIN_BLOCKS : 1)
 k_intersect(DevAccel A, const cb_ray_t *__restrict__ rays, const float *__restrict__ max_dist,
             cb_hitrec_t *__restrict__ out, uint64_t n, unsigned long long *ticket, unsigned long long *counters,
-            int prim_threshold, int refill_threshold)
+            int prim_threshold, int refill_threshold, const uint32_t *__restrict__ order)
 {
   const uint32_t lane = threadIdx.x & 31u;
   const uint32_t lt_mask = (1u << lane) - 1u;
@@ -204,9 +204,10 @@ k_intersect(DevAccel A, const cb_ray_t *__restrict__ rays, const float *__restri
       if(base + want >= n) exhausted = true;
       if(state == ST_IDLE)
       {
-        const uint64_t i = base + __popc(idle & lt_mask);
-        if(i < n)
+        const uint64_t q = base + __popc(idle & lt_mask);
+        if(q < n)
         {
+          const uint64_t i = order ? (uint64_t)__ldg(order + q) : q;   // processing order != storage order (coherence sort)
           load_ray(rays, i, r);
           ray_i = i;
           h.dist = max_dist ? __ldg(max_dist + i) : FLT_MAX;
@@ -516,13 +517,13 @@ static int refill_threshold()
 
 template<bool MB, bool CNT, int STACK, bool ANALYTIC>
 static int launch_intersect_k(const cb200_accel *a, const cb_ray_t *d_rays, const float *d_max_dist, cb_hitrec_t *d_out,
-                              uint64_t n, cudaStream_t stream, unsigned long long *d_counters)
+                              uint64_t n, cudaStream_t stream, unsigned long long *d_counters, const uint32_t *d_order)
 {
   unsigned long long *ticket;
   if(get_ticket(stream, &ticket)) return CB200_ERR_CUDA;
   auto k = k_intersect<MB, CNT, STACK, ANALYTIC>;
   k<<<grid_for(n, (const void *)k), TRACE_BLOCK, 0, stream>>>(a->dev, d_rays, d_max_dist, d_out, n, ticket, d_counters,
-                                                              prim_threshold(), refill_threshold());
+                                                              prim_threshold(), refill_threshold(), d_order);
   cb200_count_launch();
   CB_CUDA(cudaGetLastError());
   return 0;
@@ -530,25 +531,25 @@ static int launch_intersect_k(const cb200_accel *a, const cb_ray_t *d_rays, cons
 
 template<bool MB>
 static int launch_intersect_t(const cb200_accel *a, const cb_ray_t *d_rays, const float *d_max_dist, cb_hitrec_t *d_out,
-                              uint64_t n, cudaStream_t stream, unsigned long long *d_counters)
+                              uint64_t n, cudaStream_t stream, unsigned long long *d_counters, const uint32_t *d_order)
 {
   const int need = 3*a->depth + 1;
   if(need > STACK_BIG) { cb200_set_error("tree deeper than the reference's MAX_TREE_DEPTH"); return CB200_ERR_UNSUPPORTED; }
-  if(d_counters) return launch_intersect_k<MB, true, STACK_BIG, true>(a, d_rays, d_max_dist, d_out, n, stream, d_counters);
+  if(d_counters) return launch_intersect_k<MB, true, STACK_BIG, true>(a, d_rays, d_max_dist, d_out, n, stream, d_counters, d_order);
   const bool analytic = a->scene->any_analytic != 0;
   if(need <= STACK_SMALL)
-    return analytic ? launch_intersect_k<MB, false, STACK_SMALL, true >(a, d_rays, d_max_dist, d_out, n, stream, nullptr)
-                    : launch_intersect_k<MB, false, STACK_SMALL, false>(a, d_rays, d_max_dist, d_out, n, stream, nullptr);
-  return analytic ? launch_intersect_k<MB, false, STACK_BIG, true >(a, d_rays, d_max_dist, d_out, n, stream, nullptr)
-                  : launch_intersect_k<MB, false, STACK_BIG, false>(a, d_rays, d_max_dist, d_out, n, stream, nullptr);
+    return analytic ? launch_intersect_k<MB, false, STACK_SMALL, true >(a, d_rays, d_max_dist, d_out, n, stream, nullptr, d_order)
+                    : launch_intersect_k<MB, false, STACK_SMALL, false>(a, d_rays, d_max_dist, d_out, n, stream, nullptr, d_order);
+  return analytic ? launch_intersect_k<MB, false, STACK_BIG, true >(a, d_rays, d_max_dist, d_out, n, stream, nullptr, d_order)
+                  : launch_intersect_k<MB, false, STACK_BIG, false>(a, d_rays, d_max_dist, d_out, n, stream, nullptr, d_order);
 }
 
 int cb200_launch_intersect(const cb200_accel *a, const cb_ray_t *d_rays, const float *d_max_dist, cb_hitrec_t *d_out,
-                           uint64_t n, cudaStream_t stream, unsigned long long *d_counters)
+                           uint64_t n, cudaStream_t stream, unsigned long long *d_counters, const uint32_t *d_order)
 {
   if(n == 0) return 0;
-  return a->dev.mb ? launch_intersect_t<true >(a, d_rays, d_max_dist, d_out, n, stream, d_counters)
-                   : launch_intersect_t<false>(a, d_rays, d_max_dist, d_out, n, stream, d_counters);
+  return a->dev.mb ? launch_intersect_t<true >(a, d_rays, d_max_dist, d_out, n, stream, d_counters, d_order)
+                   : launch_intersect_t<false>(a, d_rays, d_max_dist, d_out, n, stream, d_counters, d_order);
 }
 
 template<bool MB, int STACK, bool ANALYTIC>
