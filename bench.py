@@ -15,9 +15,9 @@ value    : whole-job rays/s over the K timed steps, scene + BVH resident in HBM,
            ranks.  Steps are issued back to back through the streaming entry (cb200_render_pass_stream); the stragglers
            of the last step are flushed INSIDE the timed region, so every path started in it is also finished in it.
            spp_per_s / paths_per_s ride along (the metric's second half).
-e2e      : the same pass through the host-side render module the reference would link (MOD_render=b200,
-           render_b200_pass): path-index range in, complete HOST framebuffer out after every progression -- device->host copy
-           of the W*H*3 float image inside the timed region.  The inputs of this path ARE an index range (render_sample_path(i),
+e2e      : the same passes through the host-side render module the reference would link (MOD_render=b200,
+           render_b200_pass per progression + render_b200_finish at the end): path-index range in, HOST framebuffer out after
+           every progression -- a device->host copy of the W*H*3 float image per step inside the timed region.  The inputs of this path ARE an index range (render_sample_path(i),
            gi.c:81): h2d is the 16 bytes that name it.  `e2e_accel` gives the accel.h boundary (host ray batches in, hit
            records out) for the same scene.
 roofline : dominant kernel = closest-hit traversal (k_intersect).  achieved = algorithmic bytes of all its launches in the
@@ -55,6 +55,25 @@ CAMERA = dict(pos=(18.0, 14.0, 14.5), lookat=(0.0, 0.0, 2.5), aperture_value=6, 
 WORKLOAD = "synthetic 10M-triangle procedural mesh, 4K frame (3840x2176), ptdl, 1 spp per GPU per step"
 METRIC = "rays/s (closest-hit + shadow)"
 REFDIR = os.path.join(ROOT, "oracle", "_ref")
+
+
+def ncu_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel from the committed `ncu --set full` capture
+    of this same command (profiles/r1d_k_intersect_ncu.json); None when the summary is not there"""
+    p = os.path.join(ROOT, "profiles", "r1d_k_intersect_ncu.json")
+    try:
+        rows = json.load(open(p))
+        tot = []
+        for r in rows:
+            rd = [v for k, v in r.items() if k.startswith("dram__bytes_read.sum")]
+            wr = [v for k, v in r.items() if k.startswith("dram__bytes_write.sum")]
+            unit_r = [k for k in r if k.startswith("dram__bytes_read.sum")][0]
+            unit_w = [k for k in r if k.startswith("dram__bytes_write.sum")][0]
+            scale = lambda u: 1e9 if "Gbyte" in u else 1e6 if "Mbyte" in u else 1e3 if "Kbyte" in u else 1.0
+            tot.append(rd[0] * scale(unit_r) + wr[0] * scale(unit_w))
+        return sum(tot) / len(tot), os.path.relpath(p, ROOT)
+    except Exception:
+        return None, None
 
 
 def peaks():
@@ -309,25 +328,34 @@ def main():
         r.clear()
         r.instrument(False, False)
         host_fb = torch.empty(HEIGHT, WIDTH, 3).pin_memory()
-        e2e_steps = max(2, min(args.steps, 6))
+        e2e_steps = max(2, min(args.steps, 16))
 
-        def e2e_step():
-            lib._check(lib.load().cb200_render_pass(r.r, next_first(), n_pass, None), "cb200_render_pass")
-            lib._check(lib.load().cb200_render_download(r.r, host_fb.data_ptr(), None), "cb200_render_download")
-        s0 = r.stats()
+        L = lib.load()
+
+        def e2e_step():          # == host/render_b200.c: render_b200_pass(r, first, count, fb)
+            lib._check(L.cb200_render_pass_stream(r.r, next_first(), n_pass, None), "cb200_render_pass_stream")
+            lib._check(L.cb200_render_snapshot(r.r, host_fb.data_ptr(), None), "cb200_render_snapshot")
+
+        def e2e_finish():        # == render_b200_finish(r, fb)
+            lib._check(L.cb200_render_flush(r.r, None), "cb200_render_flush")
+            lib._check(L.cb200_render_download(r.r, host_fb.data_ptr(), None), "cb200_render_download")
         e2e_step()
+        e2e_finish()
         torch.cuda.synchronize()
         s1 = r.stats()
         t0 = time.perf_counter()
         for _ in range(e2e_steps):
             e2e_step()
+        e2e_finish()
         torch.cuda.synchronize()
         dt = time.perf_counter() - t0
         s2 = r.stats()
         rays = (s2["rays_closest"] + s2["rays_shadow"]) - (s1["rays_closest"] + s1["rays_shadow"])
-        e2e = {"value": rays / dt, "unit": "rays/s", "h2d_bytes_per_step": 16, "d2h_bytes_per_step": HEIGHT * WIDTH * 3 * 4,
+        e2e = {"value": rays / dt, "unit": "rays/s", "h2d_bytes_per_step": 16,
+               "d2h_bytes_per_step": HEIGHT * WIDTH * 3 * 4 * (e2e_steps + 1) // e2e_steps,
                "steps": e2e_steps, "ms_per_step": dt / e2e_steps * 1e3, "spp_per_s": e2e_steps / dt,
-               "boundary": "render_b200_pass: path-index range in, finished host framebuffer (W*H*3 f32, pinned) out, every progression"}
+               "boundary": "render_b200_pass per progression: path-index range in, the progressive HOST framebuffer (W*H*3 f32, pinned) "
+                           "out after every progression; render_b200_finish (flush + finished image) once at the end, inside the timing"}
         e2e["accel_h"] = accel_boundary(cb, lib, acc, scene, torch)
     r.close()
 
@@ -339,6 +367,8 @@ def main():
     hbm, which = peaks()
     ms_closest, ms_shadow = stt["ms"][1], stt["ms"][3]
     achieved = stt["rays_closest"] * bytes_per_ray / (ms_closest * 1e-3) / 1e9
+    traffic, traffic_src = ncu_traffic()
+    n_launch = max(1, stt["launches_closest"]) if "launches_closest" in stt else None
     total_rays = rays_closest + rays_shadow
     out = {
         "metric": METRIC, "value": total_rays / (ms_total * 1e-3), "unit": "rays/s",
@@ -353,7 +383,10 @@ def main():
         "kernel_ms_per_step_rank0": {k: v / args.steps for k, v in zip(["path_start", "closest_hit", "shade", "shadow", "nee_resolve"], stt["ms"])},
         "grays_per_s_rank0": {"closest_hit": stt["rays_closest"] / (ms_closest * 1e-3) / 1e9, "shadow": stt["rays_shadow"] / max(ms_shadow * 1e-3, 1e-12) / 1e9},
         "roofline": {"bound": "hbm", "kernel": "k_intersect (closest-hit traversal, all launches of the timed region, rank 0)",
-                     "achieved": achieved, "peak": hbm, "unit": "GB/s", "frac": achieved / hbm, "peak_source": which, "traffic": None,
+                     "achieved": achieved, "peak": hbm, "unit": "GB/s", "frac": achieved / hbm, "peak_source": which, "traffic": traffic,
+                     "traffic_note": f"DRAM bytes per ~8.3 M-ray launch from {traffic_src}: the ray and hit streams only -- nodes and primitives are "
+                                     "served by L1/L2, so HBM is not the binding roof (issue slots 67 %, L1 wavefronts 78 %)" if traffic else None,
+                     "algorithmic_bytes_per_launch": bytes_per_ray * 8.3e6,
                      "bytes_per_ray": bytes_per_ray, "nodes_per_ray": n_node, "prims_per_ray": n_prim,
                      "rays": stt["rays_closest"], "kernel_ms": ms_closest},
         "e2e": e2e if e2e is not None else {"value": None, "unit": "rays/s", "h2d_bytes_per_step": 16,

@@ -995,6 +995,14 @@ int cb200_render_download(cb200_render_t *r, float *fb_host, void *stream)
   return 0;
 }
 
+int cb200_render_snapshot(cb200_render_t *r, float *fb_host, void *stream)
+{
+  if(!r || !fb_host) { cb200_set_error("render_snapshot: bad arguments"); return CB200_ERR_ARG; }
+  CB_CUDA(cudaMemcpyAsync(fb_host, r->dev.fb, (size_t)r->dev.fb_w*r->dev.fb_h*3*sizeof(float), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+  CB_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+  return 0;
+}
+
 int cb200_render_stats(cb200_render_t *r, cb_render_stats_t *out)
 {
   if(!r || !out) { cb200_set_error("render_stats: bad arguments"); return CB200_ERR_ARG; }

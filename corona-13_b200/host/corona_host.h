@@ -91,6 +91,8 @@ void render_clear();
 struct render_t *render_b200_init(const accel_t *accel, const cb_render_desc_t *desc);
 /* == for(i in [first_index, first_index+count)) render_sample_path(i); fb: host W*H*3 floats or NULL */
 int render_b200_pass(struct render_t *r, uint64_t first_index, uint64_t count, float *fb);
+/* finish the paths still in flight and fetch the complete image (before fb_export / screenshots) */
+int render_b200_finish(struct render_t *r, float *fb);
 uint64_t render_b200_overlays(const struct render_t *r);
 void *render_b200_handle(const struct render_t *r);
 

@@ -9,6 +9,8 @@
  *
  * with `fb` the host framebuffer of the view (W*H*3 floats, un-gained like fb->fb, include/framebuffer.h:19-36); it
  * receives the accumulated image after the pass (NULL: keep it on the device, e.g. between the passes of a --batch).
+ * Progressions are streamed (paths that outlive their progression finish during the next one); render_b200_finish()
+ * completes them -- call it where the reference saves a screenshot or exits (src/main.c: main_screenshot / cleanup).
  * render_sample_path() itself is exported for link compatibility and refuses loudly: there is no CPU path in here.
  */
 #include "corona_host.h"
@@ -90,10 +92,22 @@ void render_sample_path(uint64_t index)
 int render_b200_pass(struct render_t *r, uint64_t first_index, uint64_t count, float *fb)
 {
   if(!r) { fprintf(stderr, "[render b200] pass: not initialised\n"); return 1; }
-  int rc = fb ? cb200_render_pass(r->r, first_index, count, 0) : cb200_render_pass_stream(r->r, first_index, count, 0);
-  if(!rc && fb) rc = cb200_render_download(r->r, fb, 0);
+  /* streamed: paths still bouncing when every index has been started ride along with the next progression; the
+   * framebuffer handed back is the progressive image as it stands (like the reference's display reading fb mid-flight) */
+  int rc = cb200_render_pass_stream(r->r, first_index, count, 0);
+  if(!rc && fb) rc = cb200_render_snapshot(r->r, fb, 0);
   if(rc) { fprintf(stderr, "[render b200] pass failed: %s\n", cb200_last_error()); return 1; }
   r->overlays += count/((uint64_t)r->width*r->height);
+  return 0;
+}
+
+/* trace the stragglers to the end and hand back the finished image: before fb_export / a screenshot / the end of a batch */
+int render_b200_finish(struct render_t *r, float *fb)
+{
+  if(!r) { fprintf(stderr, "[render b200] finish: not initialised\n"); return 1; }
+  int rc = cb200_render_flush(r->r, 0);
+  if(!rc && fb) rc = cb200_render_download(r->r, fb, 0);
+  if(rc) { fprintf(stderr, "[render b200] finish failed: %s\n", cb200_last_error()); return 1; }
   return 0;
 }
 

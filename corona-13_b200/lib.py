@@ -233,6 +233,7 @@ def _load_render():
     L.cb200_render_fb_device.argtypes = [vp]
     L.cb200_render_download.argtypes = [vp, vp, vp]
     L.cb200_render_set_framebuffer.argtypes = [vp, vp]
+    L.cb200_render_snapshot.argtypes = [vp, vp, vp]
     L.cb200_render_stats.argtypes = [vp, vp]
     L.cb200_render_point.argtypes = [vp, vp, vp, vp, u64]
     L.cb200_render_camera_rays.argtypes = [vp, u64, u64, vp, vp]
@@ -242,7 +243,7 @@ def _load_render():
 
 
 RENDER_SYMBOLS = ["cb200_render_create", "cb200_render_destroy", "cb200_render_pass", "cb200_render_pass_stream", "cb200_render_flush", "cb200_render_clear", "cb200_render_instrument",
-                  "cb200_render_fb_device", "cb200_render_set_framebuffer", "cb200_render_download", "cb200_render_stats", "cb200_render_point",
+                  "cb200_render_fb_device", "cb200_render_set_framebuffer", "cb200_render_download", "cb200_render_snapshot", "cb200_render_stats", "cb200_render_point",
                   "cb200_render_camera_rays", "cb200_render_bsdf"]
 
 

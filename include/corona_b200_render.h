@@ -145,7 +145,10 @@ void *cb200_render_fb_device(cb200_render_t *r);
 /* accumulate into a caller-owned device buffer (W*H*3 floats) from now on, NULL = back to the library's own.  Lets the
  * caller double-buffer: reduce / read one buffer while the next progression renders into the other. */
 int  cb200_render_set_framebuffer(cb200_render_t *r, void *d_fb);
-int  cb200_render_download(cb200_render_t *r, float *fb_host, void *stream);
+int  cb200_render_download(cb200_render_t *r, float *fb_host, void *stream);   /* flushes first: the finished image */
+/* the accumulation buffer as it stands, WITHOUT flushing: what a progressive display shows between streamed progressions
+ * (the stragglers' contributions arrive with a later snapshot; the reference's display reads its framebuffer mid-flight too) */
+int  cb200_render_snapshot(cb200_render_t *r, float *fb_host, void *stream);
 int  cb200_render_stats(cb200_render_t *r, cb_render_stats_t *out);
 
 /* component entry points for parity tests (device work, host buffers): */
