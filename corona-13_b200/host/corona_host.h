@@ -96,6 +96,21 @@ int render_b200_finish(struct render_t *r, float *fb);
 uint64_t render_b200_overlays(const struct render_t *r);
 void *render_b200_handle(const struct render_t *r);
 
+/* ---- scene ingestion (host/scene_b200.c): .nra2 shader + shape lists, .cam, rgb2spec coefficients, measured tables ---- */
+struct scene_b200_t;
+struct scene_b200_t *scene_b200_open(const char *nra2_file, const char *coeff_file, const char *table_file);   /* no GPU needed */
+void scene_b200_free(struct scene_b200_t *s);
+const cb_material_t *scene_b200_materials(const struct scene_b200_t *s, int *num);
+const char *scene_b200_basename(const struct scene_b200_t *s);
+uint64_t scene_b200_num_prims(const struct scene_b200_t *s);
+int scene_b200_read_camera(const char *filename, uint32_t width, uint32_t height, cb_camera_t *out);
+/* accel_init + accel_build + camera + render_b200_init: what main.c's init() does for the hot path */
+int scene_b200_prepare(struct scene_b200_t *s, uint32_t width, uint32_t height, int sampler, int pointsampler, int colour, uint64_t frame,
+                       const char *cam_file);
+struct render_t *scene_b200_render(struct scene_b200_t *s);
+const cb_render_desc_t *scene_b200_desc(const struct scene_b200_t *s);
+int scene_b200_write_pfm(const char *filename, const float *fb, uint32_t width, uint32_t height, float gain);
+
 /* prims helpers for standalone use: the slice of prims_init/allocate/load/allocate_index the path needs
  * (src/prims.c:703-828) */
 #ifndef CORONA_B200_IN_TREE

@@ -1,0 +1,95 @@
+/* main_b200.c -- `corona_b200`: the reference's offline command line for the hot path, on the GPU modules.
+ *
+ *   corona_b200 <scene.nra2> [-s spp] [-w width] [-h height] [--frame n] [-x [name]] [-c camfile] [--batch n]
+ *               [--sampler pt|ptdl] [--points rand|halton] [--colour xyz|rec709] [--coeff file] [--tables file]
+ *               [--dump-materials file] [-q]
+ *
+ * Same arguments and defaults as the reference binary where they exist there (src/main.c:250-282,415-437,
+ * src/view.c:262-297, src/display.d/null.c:47-56): -s samples per pixel then write the image and quit, -w/-h frame size
+ * (padded to multiples of 32), --frame = rt.anim_frame (seeds the point sampler, default 1), -x output name (default
+ * `render'), data/ergb2spec.coeff relative to the working directory.  --sampler / --points / --colour stand in for the
+ * reference's compile-time MOD_sampler / MOD_pointsampler / COL_camera.  Writes <basename><name>_fb00.pfm like
+ * view_write_images (src/view.c:549).  Without a CUDA device it refuses: there is no CPU path in this binary.
+ */
+#include "corona_host.h"
+#include "corona_b200.h"
+#include "corona_b200_render.h"
+
+#include <stdlib.h>
+#include <string.h>
+#include <time.h>
+
+static double now(void) { struct timespec t; clock_gettime(CLOCK_MONOTONIC, &t); return t.tv_sec + 1e-9*t.tv_nsec; }
+
+int main(int argc, char *argv[])
+{
+  if(argc < 2)
+  {
+    fprintf(stderr, "usage: %s <scene.nra2> [-s spp] [-w width] [-h height] [--frame n] [-x [name]] [-c camfile] [--batch n]\n"
+                    "          [--sampler pt|ptdl] [--points rand|halton] [--colour xyz|rec709] [--coeff file] [--tables file] [-q]\n", argv[0]);
+    return 1;
+  }
+  const char *scene = argv[1], *coeff = "data/ergb2spec.coeff", *tables = getenv("CORONA_B200_TABLES"), *camfile = 0, *dump = 0;
+  char outname[256] = "render";
+  uint64_t spp = 0, frame = 1, batch = 1;
+  uint32_t width = 1024, height = 576;       /* src/view.c:261-262 */
+  int sampler = CB_SAMPLER_PTDL, points = CB_POINTS_RAND, colour = CB_COLOUR_XYZ, quiet = 0;
+  for(int i=2;i<argc;i++)
+  {
+    if     (!strcmp(argv[i], "-s") && i+1 < argc) spp = strtoull(argv[++i], 0, 10);
+    else if(!strcmp(argv[i], "-w") && i+1 < argc) width = (uint32_t)atol(argv[++i]);
+    else if(!strcmp(argv[i], "-h") && i+1 < argc) height = (uint32_t)atol(argv[++i]);
+    else if(!strcmp(argv[i], "-c") && i+1 < argc) camfile = argv[++i];
+    else if(!strcmp(argv[i], "--frame") && i+1 < argc) frame = strtoull(argv[++i], 0, 10);
+    else if(!strcmp(argv[i], "--batch") && i+1 < argc) batch = strtoull(argv[++i], 0, 10);
+    else if(!strcmp(argv[i], "-x")) { if(i+1 < argc && argv[i+1][0] != '-') snprintf(outname, sizeof(outname), "%s", argv[++i]); }
+    else if(!strcmp(argv[i], "--sampler") && i+1 < argc) { ++i; sampler = !strcmp(argv[i], "pt") ? CB_SAMPLER_PT : CB_SAMPLER_PTDL; }
+    else if(!strcmp(argv[i], "--points") && i+1 < argc) { ++i; points = !strcmp(argv[i], "halton") ? CB_POINTS_HALTON : CB_POINTS_RAND; }
+    else if(!strcmp(argv[i], "--colour") && i+1 < argc) { ++i; colour = !strcmp(argv[i], "rec709") ? CB_COLOUR_REC709 : CB_COLOUR_XYZ; }
+    else if(!strcmp(argv[i], "--coeff") && i+1 < argc) coeff = argv[++i];
+    else if(!strcmp(argv[i], "--tables") && i+1 < argc) tables = argv[++i];
+    else if(!strcmp(argv[i], "--dump-materials") && i+1 < argc) dump = argv[++i];
+    else if(!strcmp(argv[i], "-q")) quiet = 1;
+    else if((!strcmp(argv[i], "-t") || !strcmp(argv[i], "-b") || !strcmp(argv[i], "-o")) && i+1 < argc) ++i;   /* cpu threads / backups / timeout: n/a */
+  }
+  if(batch < 1) batch = 1;
+  struct scene_b200_t *s = scene_b200_open(scene, coeff, tables);
+  if(!s) { fprintf(stderr, "[main] could not load nra2 file!\n"); return 2; }
+  if(dump)
+  { /* the flattened shader list, for the parser tests: no GPU needed */
+    int n = 0;
+    const cb_material_t *m = scene_b200_materials(s, &n);
+    FILE *f = fopen(dump, "wb");
+    if(!f || fwrite(m, sizeof(cb_material_t), n, f) != (size_t)n) { fprintf(stderr, "[main] could not write %s\n", dump); return 2; }
+    fclose(f);
+    if(!spp) { scene_b200_free(s); return 0; }
+  }
+  if(!quiet) { accel_print_info(stdout); render_print_info(stdout); }
+  double t0 = now();
+  if(scene_b200_prepare(s, width, height, sampler, points, colour, frame, camfile)) { fprintf(stderr, "[main] could not initialise the gpu modules\n"); scene_b200_free(s); return 2; }
+  const cb_render_desc_t *d = scene_b200_desc(s);
+  if(!quiet) printf("[main] %lu primitives, accel + upload took %.3f seconds\n", (unsigned long)scene_b200_num_prims(s), now() - t0);
+  if(!quiet) printf("[display] simulating %lu samples per pixel\n", (unsigned long)spp);
+  const uint64_t per_frame = (uint64_t)d->width*d->height;
+  float *fb = (float *)malloc(sizeof(float)*per_frame*3);
+  struct render_t *r = scene_b200_render(s);
+  t0 = now();
+  uint64_t done = 0;
+  while(done < spp)
+  { /* run(): view_render() per progression (src/main.c:388-412, src/view.c:630-645) */
+    const uint64_t n = (spp - done) < batch ? (spp - done) : batch;
+    if(render_b200_pass(r, done*per_frame, n*per_frame, 0)) { free(fb); scene_b200_free(s); return 3; }
+    done += n;
+  }
+  if(render_b200_finish(r, fb)) { free(fb); scene_b200_free(s); return 3; }
+  const double dt = now() - t0;
+  if(!quiet && spp) printf("[main] rendered %lu frames in an average of %.4f s/frame\n", (unsigned long)spp, dt/spp);
+  char filename[1400];
+  snprintf(filename, sizeof(filename), "%s%s_fb00.pfm", scene_b200_basename(s), outname);
+  const float gain = spp ? d->camera.iso/(100.0f*(float)spp) : 0.0f;    /* src/view.c:656 */
+  if(scene_b200_write_pfm(filename, fb, d->width, d->height, gain)) { fprintf(stderr, "[main] could not write %s\n", filename); free(fb); scene_b200_free(s); return 4; }
+  if(!quiet) printf("[main] saving framebuffers to %s%s\n", scene_b200_basename(s), outname);
+  free(fb);
+  scene_b200_free(s);
+  return 0;
+}

@@ -35,6 +35,13 @@ def main():
         out["metal_" + n.lower()] = np.ascontiguousarray(nk[i].T)   # rows: n, k
     path = os.path.join(HERE, "ref_tables.npz")
     np.savez_compressed(path, **out)
+    # the same tables for the C host layer (host/scene_b200.c: tables_load): "CBT1", count, {name[32], rows, cols, lambda_min, lambda_step, data}
+    import struct
+    with open(os.path.join(HERE, "ref_tables.cbt"), "wb") as f:
+        f.write(b"CBT1" + struct.pack("<I", len(out)))
+        for k, v in out.items():
+            lmin, step = (380.0, 10.0) if k == "checker" else (360.0, 5.0)
+            f.write(k.encode().ljust(32, b"\0") + struct.pack("<IIff", v.shape[0], v.shape[1], lmin, step) + np.ascontiguousarray(v, "<f4").tobytes())
     print("wrote", path, {k: v.shape for k, v in out.items()})
 
 

@@ -173,6 +173,18 @@ class GoldenImage:
     def ref(self, key, seed):
         return self.z[f"{key}_seed{seed}"]
 
+    def write_files(self, directory):
+        """the scene in the reference's own file formats: shape<i>.geo, test.nra2, test01.cam -> path of the .nra2"""
+        IO = cb.scene_io
+        shapes = []
+        for i, sh in enumerate(self.scene.shapes):
+            sh.write_geo(os.path.join(directory, f"shape{i}.geo"))
+            shapes.append((int(self.z["shape_mats"][i]), f"shape{i}"))
+        nra2 = os.path.join(directory, "test.nra2")
+        IO.write_nra2(nra2, [str(x) for x in self.z["shader_lines"]], shapes)
+        open(os.path.join(directory, "test01.cam"), "wb").write(self.z["cam"].tobytes())
+        return nra2
+
     @staticmethod
     def variant_args(key):
         """'ptdl_halton_rec709' -> keyword arguments of lib.Render"""
