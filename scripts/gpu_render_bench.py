@@ -13,8 +13,9 @@ ms = IO.MaterialSet()
 raw = z["materials"].tobytes()
 arr = (IO.CMaterial * (len(raw)//C.sizeof(IO.CMaterial))).from_buffer_copy(raw)
 ms.materials = list(arr)
-sc = S.synthetic_scene(tris, seed=1)
-for s, m in zip(sc.shapes, z["shape_mats"]): s.material = int(m)
+sc = S.synthetic_scene(tris, seed=1, motion=bool(os.environ.get('BENCH_MOTION')), analytic=bool(os.environ.get('BENCH_ANALYTIC')))
+mats = list(z['shape_mats']) + [7]*8
+for s, m in zip(sc.shapes, mats): s.material = int(m)
 acc = lib.Accel(sc).build()
 cam = IO.Camera(pos=(18.0, 14.0, 14.5), lookat=(0.0, 0.0, 2.5), aperture_value=6, exposure_value=13, focal_length=0.4, iso=100.0)
 for batch in (0,):
