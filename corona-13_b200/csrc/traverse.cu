@@ -268,9 +268,14 @@ k_intersect(DevAccel A, const cb_ray_t *__restrict__ rays, const float *__restri
         child[0] = c01.x & CB_CHILD_MASK; child[1] = c01.y; child[2] = c23.x; child[3] = c23.y;
         axis0 = ax & 3; axis00 = (ax >> 2) & 3; axis01 = (ax >> 4) & 3;
       }
-      // empty leaves (count 0) can only be popped and dropped again: never visit them
+      // empty leaves (count 0) can only be popped and dropped again: never visit them.  (The fast path needs no test: this
+      // library's builder gives empty slots an inverted box, which the sign-selected slab test misses by construction;
+      // imported reference trees are Node256 and take the other path.)
+      if(MB || CNT || exact)
+      {
 #pragma unroll
-      for(int c=0;c<4;c++) if(is_empty_leaf(child[c])) key[c] = KEY_MISS;
+        for(int c=0;c<4;c++) if(is_empty_leaf(child[c])) key[c] = KEY_MISS;
+      }
       // the reference's topological order (qbvhmp.c:1313-1320) as three conditional swaps: inside the lower pair by the
       // sign along axis00, inside the upper pair by the sign along axis01, the two pairs by the sign along axis0
       const bool s00 = (nearbits >> axis00) & 1u, s01 = (nearbits >> axis01) & 1u, s0 = (nearbits >> axis0) & 1u;
@@ -430,7 +435,7 @@ k_visible(DevAccel A, const cb_ray_t *__restrict__ rays, const float *__restrict
         const ulonglong2 c01 = __ldg(ch), c23 = __ldg(ch + 1);
         const uint64_t child[4] = {c01.x & CB_CHILD_MASK, c01.y, c23.x, c23.y};
 #pragma unroll
-        for(int c=0;c<4;c++) if(KEY_HIT(key[c]) && !is_empty_leaf(child[c])) stack[sp++] = child[c];
+        for(int c=0;c<4;c++) if(KEY_HIT(key[c])) stack[sp++] = child[c];   // empty slots carry inverted boxes: never hit here
       }
       need_pop = true;
     }
