@@ -336,6 +336,25 @@ int cb200_accel_intersect_n(const cb200_accel_t *a, const cb_ray_t *rays, const 
     [a](cb_ray_t *dr, float *dm, cb_hitrec_t *dout, uint64_t m, cudaStream_t s) { return cb200_launch_intersect(a, dr, dm, dout, m, s, nullptr); });
 }
 
+int cb200_accel_closest_n(const cb200_accel_t *a, cb_ray_t *rays, cb_hitrec_t *io, const float *centre, uint64_t n)
+{
+  if(!a || (n && (!rays || !io || !centre))) { g_error = "accel_closest_n: bad arguments"; return CB200_ERR_ARG; }
+  if(n == 0) return 0;
+  cb_ray_t *d_r = nullptr; cb_hitrec_t *d_io = nullptr; float *d_c = nullptr;
+  CB_CUDA(cudaMalloc(&d_r, n*sizeof(cb_ray_t))); CB_CUDA(cudaMalloc(&d_io, n*sizeof(cb_hitrec_t))); CB_CUDA(cudaMalloc(&d_c, n*sizeof(float)));
+  CB_CUDA(cudaMemcpy(d_r, rays, n*sizeof(cb_ray_t), cudaMemcpyHostToDevice));
+  CB_CUDA(cudaMemcpy(d_io, io, n*sizeof(cb_hitrec_t), cudaMemcpyHostToDevice));
+  CB_CUDA(cudaMemcpy(d_c, centre, n*sizeof(float), cudaMemcpyHostToDevice));
+  int rc = cb200_launch_closest(a, d_r, d_io, d_c, n, 0);
+  if(!rc)
+  {
+    CB_CUDA(cudaMemcpy(rays, d_r, n*sizeof(cb_ray_t), cudaMemcpyDeviceToHost));
+    CB_CUDA(cudaMemcpy(io, d_io, n*sizeof(cb_hitrec_t), cudaMemcpyDeviceToHost));
+  }
+  cudaFree(d_r); cudaFree(d_io); cudaFree(d_c);
+  return rc;
+}
+
 int cb200_accel_visible_n(const cb200_accel_t *a, const cb_ray_t *rays, const float *max_dist, int32_t *out, uint64_t n)
 {
   if(!a || (n && (!rays || !out || !max_dist))) { g_error = "accel_visible_n: bad arguments"; return CB200_ERR_ARG; }

@@ -100,6 +100,7 @@ int cb200_launch_intersect(const cb200_accel *a, const cb_ray_t *d_rays, const f
                            uint64_t n, cudaStream_t stream, unsigned long long *d_counters, const uint32_t *d_order = nullptr);
 int cb200_launch_visible(const cb200_accel *a, const cb_ray_t *d_rays, const float *d_max_dist, int32_t *d_out,
                          uint64_t n, cudaStream_t stream);
+int cb200_launch_closest(const cb200_accel *a, cb_ray_t *d_rays, cb_hitrec_t *d_io, const float *d_centre, uint64_t n, cudaStream_t stream);
 // next-event visibility (path_visible semantics): any primitive other than d_light_prim[i] accepted by the closest-hit rules
 int cb200_launch_shadow(const cb200_accel *a, const cb_ray_t *d_rays, const float *d_max_dist, const uint2 *d_light_prim, int32_t *d_out,
                         uint64_t n, cudaStream_t stream);

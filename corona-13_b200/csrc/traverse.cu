@@ -43,9 +43,10 @@ struct NodeOut
 // EXACT: reference select semantics; otherwise fminf/fmaxf (only valid when no NaN can occur)
 template<bool MB, bool EXACT>
 __device__ __forceinline__ void node_slabs(const void *nodes, uint64_t idx, float px, float py, float pz,
-                                           float ix, float iy, float iz, float t0, float t1, float tmax_init, NodeOut &o)
+                                           float ix, float iy, float iz, float t0, float t1, float tmax_init, NodeOut &o,
+                                           float tmin_init = 0.0f)
 {
-  float tmin[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+  float tmin[4] = {tmin_init, tmin_init, tmin_init, tmin_init};
   float tmax[4] = {tmax_init, tmax_init, tmax_init, tmax_init};
   const float pos[3] = {px, py, pz};
   const float inv[3] = {ix, iy, iz};
@@ -456,6 +457,87 @@ k_visible(DevAccel A, const cb_ray_t *__restrict__ rays, const float *__restrict
     }
     if(result >= 0) { out[ray_i] = result; state = ST_IDLE; }
   }
+}
+
+// ---------------------------------------------------------------------------------------------
+// accel_closest (qbvhmp.c:1493-1600): the hit nearest to `centre` along the ray, for the half-vector samplers.  One query
+// per thread in the reference's exact order (boxes clipped to [min_dist, hit.dist], no entry-distance culling, the search
+// interval re-centred after every primitive test); not a throughput path.
+// ---------------------------------------------------------------------------------------------
+template<bool MB, int STACK>
+__global__ void __launch_bounds__(TRACE_BLOCK)
+k_closest(DevAccel A, cb_ray_t *__restrict__ rays, cb_hitrec_t *__restrict__ io, const float *__restrict__ centre_in, uint64_t n)
+{
+  const uint64_t i = (uint64_t)blockIdx.x*blockDim.x + threadIdx.x;
+  if(i >= n) return;
+  RayD r;
+  load_ray(rays, i, r);
+  HitD h, tent;
+  h.prim_lo = io[i].prim[0]; h.prim_hi = io[i].prim[1]; h.u = io[i].u; h.v = io[i].v; h.dist = io[i].dist;
+  tent = h;
+  const float centre = centre_in[i];
+  const uint32_t nearbits = (__float_as_uint(r.dx) >> 31) | ((__float_as_uint(r.dy) >> 31) << 1) | ((__float_as_uint(r.dz) >> 31) << 2);
+  const float ix = 1.0f/r.dx, iy = 1.0f/r.dy, iz = 1.0f/r.dz, t1 = r.time, t0 = 1.0f - r.time;
+  uint64_t stack[STACK];
+  int sp = 0;
+  uint64_t cur = 0;
+  const uint32_t rec_stride = A.rec_units*4;
+  bool done = false, straight = false;
+  while(!done)
+  {
+    NodeOut o;
+    node_slabs<MB, true>(A.nodes, cur, r.px, r.py, r.pz, ix, iy, iz, t0, t1, h.dist, o, r.min_dist);
+    const uint32_t n0 = (nearbits >> o.axis0) & 1u;
+    const int axis1n = n0 ? o.axis01 : o.axis00, axis1f = n0 ? o.axis00 : o.axis01;
+    const uint32_t n1n = (nearbits >> axis1n) & 1u, n1f = (nearbits >> axis1f) & 1u, f0 = n0 ^ 1u;
+    const uint32_t n11 = (f0 << 1) | (n1f ^ 1u), n10 = (f0 << 1) | n1f, n01 = (n0 << 1) | (n1n ^ 1u), n00 = (n0 << 1) | n1n;
+    const bool h00 = SEL4(o.hit, n00), h01 = SEL4(o.hit, n01), h10 = SEL4(o.hit, n10), h11 = SEL4(o.hit, n11);
+    const int first = h00 ? 0 : h01 ? 1 : h10 ? 2 : h11 ? 3 : 4;
+    if(first < 4)
+    {
+      if(h11 && first < 3) stack[sp++] = SEL4(o.child, n11);
+      if(h10 && first < 2) stack[sp++] = SEL4(o.child, n10);
+      if(h01 && first < 1) stack[sp++] = SEL4(o.child, n01);
+      const uint32_t nf = first == 0 ? n00 : first == 1 ? n01 : first == 2 ? n10 : n11;
+      cur = SEL4(o.child, nf);
+    }
+    else
+    {
+      if(sp == 0) break;
+      cur = stack[--sp];
+    }
+    while(cur & CB_LEAF_BIT)
+    {
+      const float4 *rec = A.recs + ((cur ^ CB_LEAF_BIT) >> 5)*(uint64_t)rec_stride;
+      const uint32_t num = (uint32_t)cur & 31u;
+      for(uint32_t k=0;k<num && !done;k++, rec += rec_stride)
+      {
+        prim_intersect<true>(rec, A.rec_units, r, h);
+        if(fabsf(h.dist - centre) < fabsf(tent.dist - centre)) tent = h;
+        if(h.dist > centre + 1e-6f) r.min_dist = 2.0f*centre - h.dist;
+        else if(h.dist < centre - 1e-6f) { r.min_dist = h.dist; h.dist = 2.0f*centre - r.min_dist; }
+        else { done = true; straight = true; }
+      }
+      if(done) break;
+      if(sp == 0) { done = true; break; }
+      cur = stack[--sp];
+    }
+  }
+  if(!straight) h = tent;
+  io[i].prim[0] = h.prim_lo; io[i].prim[1] = h.prim_hi; io[i].u = h.u; io[i].v = h.v; io[i].dist = h.dist; io[i].pad = 0;
+  rays[i].min_dist = r.min_dist;
+}
+
+int cb200_launch_closest(const cb200_accel *a, cb_ray_t *d_rays, cb_hitrec_t *d_io, const float *d_centre, uint64_t n, cudaStream_t stream)
+{
+  if(n == 0) return 0;
+  if(3*a->depth + 1 > 304) { cb200_set_error("tree deeper than the reference's MAX_TREE_DEPTH"); return CB200_ERR_UNSUPPORTED; }
+  const unsigned grid = (unsigned)((n + TRACE_BLOCK - 1)/TRACE_BLOCK);
+  if(a->dev.mb) k_closest<true,  304><<<grid, TRACE_BLOCK, 0, stream>>>(a->dev, d_rays, d_io, d_centre, n);
+  else          k_closest<false, 304><<<grid, TRACE_BLOCK, 0, stream>>>(a->dev, d_rays, d_io, d_centre, n);
+  cb200_count_launch();
+  CB_CUDA(cudaGetLastError());
+  return 0;
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -139,12 +139,20 @@ int accel_visible(const accel_t *b, const ray_t *ray, const float max_dist)
 }
 
 void accel_closest(const accel_t *b, ray_t *ray, hit_t *hit, const float centre)
-{
-  /* only the half-vector MLT samplers call this (include/pathspace/halfvec.h:718,912); they are outside
-   * the pt/ptdl hot path.  Exported for link compatibility; refuses loudly instead of faking a result. */
-  (void)b; (void)ray; (void)hit; (void)centre;
-  fprintf(stderr, "[accel b200] accel_closest is not implemented on the gpu path (not used by pt/ptdl)\n");
-  abort();
+{ /* half-vector MLT samplers only (include/pathspace/halfvec.h:718,912); a batch of one, in/out like qbvhmp.c:1493-1600 */
+  cb_hitrec_t io;
+  memcpy(io.prim, &hit->prim, 8);
+  io.u = hit->u; io.v = hit->v; io.dist = hit->dist; io.pad = 0;
+  if(cb200_accel_closest_n(b->accel, (cb_ray_t *)ray, &io, &centre, 1))
+  { fprintf(stderr, "[accel b200] closest failed: %s\n", cb200_last_error()); return; }
+  if(memcmp(io.prim, &hit->prim, 8) || io.dist != hit->dist)
+  {
+    memcpy(&hit->prim, io.prim, 8);
+    hit->u = io.u; hit->v = io.v;
+    if((io.prim[1] >> 29) == CB_PRIM_SPHERE && (io.prim[0] & io.prim[1]) != 0xffffffffu)
+      for(int k=0;k<3;k++) hit->x[k] = ray->pos[k] + io.dist*ray->dir[k];
+  }
+  hit->dist = io.dist;
 }
 
 #ifndef CORONA_B200_IN_TREE

@@ -22,7 +22,7 @@ SYMBOLS = [
     "cb200_scene_create", "cb200_scene_destroy", "cb200_scene_num_prims",
     "cb200_accel_build", "cb200_accel_import_qbvh", "cb200_accel_destroy", "cb200_accel_num_nodes",
     "cb200_accel_depth", "cb200_accel_aabb", "cb200_accel_export_qbvh", "cb200_accel_layout",
-    "cb200_accel_intersect_n", "cb200_accel_visible_n", "cb200_accel_intersect_dev",
+    "cb200_accel_intersect_n", "cb200_accel_visible_n", "cb200_accel_closest_n", "cb200_accel_intersect_dev",
     "cb200_accel_visible_dev", "cb200_accel_intersect_counted", "cb200_launch_count",
 ]
 
@@ -75,6 +75,7 @@ def load():
     L.cb200_accel_layout.argtypes = [vp, vp, vp]
     L.cb200_accel_intersect_n.argtypes = [vp, vp, vp, vp, u64]
     L.cb200_accel_visible_n.argtypes = [vp, vp, vp, vp, u64]
+    L.cb200_accel_closest_n.argtypes = [vp, vp, vp, vp, u64]
     L.cb200_accel_intersect_dev.argtypes = [vp, vp, vp, vp, u64, vp]
     L.cb200_accel_visible_dev.argtypes = [vp, vp, vp, vp, u64, vp]
     L.cb200_accel_intersect_counted.argtypes = [vp, vp, vp, vp, u64, vp]
@@ -181,6 +182,14 @@ class Accel:
         out = np.zeros(len(rays), np.int32)
         _check(self.L.cb200_accel_visible_n(self.a, _ptr(rays), _ptr(md), _ptr(out), len(rays)), "cb200_accel_visible_n")
         return out
+
+    def closest(self, rays, hits, centre):
+        """accel_closest for a batch: returns (rays with updated min_dist, hits {prim,u,v,dist})"""
+        rays = np.array(rays, dtype=RAY, copy=True)
+        io = np.array(hits, dtype=HITREC, copy=True)
+        c = np.ascontiguousarray(centre, np.float32)
+        _check(self.L.cb200_accel_closest_n(self.a, _ptr(rays), _ptr(io), _ptr(c), len(rays)), "cb200_accel_closest_n")
+        return rays, io
 
     # device-pointer calls (ints from torch .data_ptr(), stream from torch.cuda.current_stream().cuda_stream)
     def intersect_dev(self, d_rays, d_max_dist, d_out, n, stream=0):

@@ -85,6 +85,9 @@ int cb200_accel_intersect_n(const cb200_accel_t *a, const cb_ray_t *rays, const 
                             cb_hitrec_t *out, uint64_t n);
 int cb200_accel_visible_n(const cb200_accel_t *a, const cb_ray_t *rays, const float *max_dist,
                           int32_t *out, uint64_t n);
+/* batched accel_closest (accel.h:47; qbvhmp.c:1493-1600): the hit nearest to centre[i] along ray i.  rays[i].min_dist and
+ * io[i] = {prim,u,v,dist} are in/out exactly like the reference's ray_t* / hit_t* arguments (io[i].dist = search limit in). */
+int cb200_accel_closest_n(const cb200_accel_t *a, cb_ray_t *rays, cb_hitrec_t *io, const float *centre, uint64_t n);
 int cb200_accel_intersect_dev(const cb200_accel_t *a, const void *d_rays, const void *d_max_dist,
                               void *d_out, uint64_t n, void *stream);
 int cb200_accel_visible_dev(const cb200_accel_t *a, const void *d_rays, const void *d_max_dist,

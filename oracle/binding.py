@@ -70,6 +70,7 @@ class Oracle:
             L.orc_accel_aabb.argtypes = [C.c_void_p]
             L.orc_intersect_n.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_int, C.c_void_p]
             L.orc_visible_n.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_int]
+            L.orc_closest_n.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64]
             L.orc_accel_check.restype = C.c_int
             L.orc_accel_check.argtypes = [C.c_void_p, C.c_void_p]
             cls._lib = L
@@ -134,6 +135,14 @@ class Oracle:
         self.L.orc_intersect_n(self.a, _ptr(rays), _ptr(md), _ptr(out), len(rays), nthreads or os.cpu_count(), _ptr(cnt))
         return (out, cnt) if counters else out
 
+    def closest(self, rays, hits, centre):
+        """accel_closest: returns (rays with updated min_dist, hits {prim,u,v,dist})"""
+        rays = np.array(rays, dtype=RAY, copy=True)
+        io = np.array(hits, dtype=HITREC, copy=True)
+        c = np.ascontiguousarray(centre, np.float32)
+        self.L.orc_closest_n(self.a, _ptr(rays), _ptr(io), _ptr(c), len(rays))
+        return rays, io
+
     def visible(self, rays, max_dist, nthreads=None):
         rays = np.ascontiguousarray(rays, dtype=RAY)
         md = np.ascontiguousarray(max_dist, np.float32)
@@ -190,6 +199,7 @@ class Ref:
             L.ref_intersect_n.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_int]
             L.ref_intersect_hits.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64]
             L.ref_visible_n.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_int]
+            L.ref_closest_n.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64]
             L.ref_counters.restype = C.c_int
             L.ref_counters.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
             cls._libs[dbg] = L
@@ -244,6 +254,14 @@ class Ref:
         rays = np.ascontiguousarray(rays, dtype=RAY)
         self.L.ref_intersect_hits(self.a, _ptr(rays), _ptr(hits), len(rays))
         return hits
+
+    def closest(self, rays, hits, centre):
+        """accel_closest: returns (rays with updated min_dist, hits {prim,u,v,dist})"""
+        rays = np.array(rays, dtype=RAY, copy=True)
+        io = np.array(hits, dtype=HITREC, copy=True)
+        c = np.ascontiguousarray(centre, np.float32)
+        self.L.ref_closest_n(self.a, _ptr(rays), _ptr(io), _ptr(c), len(rays))
+        return rays, io
 
     def visible(self, rays, max_dist, nthreads=None):
         rays = np.ascontiguousarray(rays, dtype=RAY)

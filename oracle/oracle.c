@@ -642,6 +642,97 @@ void orc_visible_n(const orc_accel_t *a, const cb_ray_t *rays, const float *max_
   for(uint64_t i=0;i<n;i++) out[i] = orc_visible(a, rays+i, max_dist[i]);
 }
 
+/* qbvhmp.c:1493-1600: nearest hit to `centre` along the ray for the half-vector samplers.  Boxes are clipped to
+ * [ray->min_dist, hit->dist] (the only traversal that uses min_dist for boxes), there is no entry-distance culling on pop,
+ * and after EVERY primitive test the search interval is re-centred around `centre` by mutating ray->min_dist / hit->dist;
+ * `tent` keeps the hit closest to centre. */
+void orc_closest(const orc_accel_t *acc, cb_ray_t *ray, cb_hit_t *hit, float centre)
+{
+  uint32_t near[3], far[3];
+  for(int k=0;k<3;k++) { near[k] = signbit_u(ray->dir[k]); far[k] = 1 ^ near[k]; }
+  const cb_qbvh_node_t *node = acc->tree;
+  uint64_t stack[3*ORC_MAX_TREE_DEPTH];
+  int stackpos = 0;
+  uint64_t current;
+  cb_hit_t tent = *hit;
+  const float t0 = 1.0f - ray->time, t1 = ray->time;
+  float invdir[3];
+  for(int k=0;k<3;k++) invdir[k] = 1.0f/ray->dir[k];
+  while(1)
+  {
+    float tmin[4] = {ray->min_dist, ray->min_dist, ray->min_dist, ray->min_dist};
+    float tmax[4] = {hit->dist, hit->dist, hit->dist, hit->dist};
+    node_boxes(node, t0, t1, ray->pos, invdir, tmin, tmax);
+    int i[4];
+    for(int c=0;c<4;c++) i[c] = tmin[c] <= tmax[c];
+    const int axis0  = (int)node->axis0;
+    const int axis1n = near[axis0] ? (int)node->axis01 : (int)node->axis00;
+    const int axis1f = near[axis0] ? (int)node->axis00 : (int)node->axis01;
+    const uint32_t n11 = (far [axis0]<<1) | far [axis1f];
+    const uint32_t n10 = (far [axis0]<<1) | near[axis1f];
+    const uint32_t n01 = (near[axis0]<<1) | far [axis1n];
+    const uint32_t n00 = (near[axis0]<<1) | near[axis1n];
+    if(i[n00])
+    {
+      current = node->child[n00];
+      if(i[n11]) stack[stackpos++] = node->child[n11];
+      if(i[n10]) stack[stackpos++] = node->child[n10];
+      if(i[n01]) stack[stackpos++] = node->child[n01];
+    }
+    else if(i[n01])
+    {
+      current = node->child[n01];
+      if(i[n11]) stack[stackpos++] = node->child[n11];
+      if(i[n10]) stack[stackpos++] = node->child[n10];
+    }
+    else if(i[n10])
+    {
+      current = node->child[n10];
+      if(i[n11]) stack[stackpos++] = node->child[n11];
+    }
+    else if(i[n11]) current = node->child[n11];
+    else
+    {
+      if(stackpos == 0) { *hit = tent; return; }
+      stackpos--;
+      current = stack[stackpos];
+    }
+    while(current & CB_LEAF_BIT)
+    {
+      uint64_t idx = (current ^ CB_LEAF_BIT) >> 5;
+      const uint64_t num = current & 31;
+      for(uint64_t k=0;k<num;k++)
+      {
+        orc_prim_intersect(acc->scene, acc->scene->primid[idx], ray, hit);
+        if(fabsf(hit->dist - centre) < fabsf(tent.dist - centre)) tent = *hit;
+        if(hit->dist > centre + 1e-6f) ray->min_dist = 2.0f*centre - hit->dist;
+        else if(hit->dist < centre - 1e-6f) { ray->min_dist = hit->dist; hit->dist = 2.0f*centre - ray->min_dist; }
+        else return;
+        idx++;
+      }
+      if(stackpos == 0) { *hit = tent; return; }
+      --stackpos;
+      current = stack[stackpos];
+    }
+    node = acc->tree + current;
+  }
+}
+
+/* batch form used by the tests: rays (min_dist is updated in place), hits {prim,u,v,dist} in/out */
+void orc_closest_n(const orc_accel_t *a, cb_ray_t *rays, cb_hitrec_t *io, const float *centre, uint64_t n)
+{
+  for(uint64_t i=0;i<n;i++)
+  {
+    cb_hit_t h;
+    memset(&h, 0, sizeof(h));
+    memcpy(h.prim, io[i].prim, 8);
+    h.u = io[i].u; h.v = io[i].v; h.dist = io[i].dist;
+    orc_closest(a, rays + i, &h, centre[i]);
+    memcpy(io[i].prim, h.prim, 8);
+    io[i].u = h.u; io[i].v = h.v; io[i].dist = h.dist; io[i].pad = 0;
+  }
+}
+
 /* ---------------------------------------------------------------------------- build */
 /* qbvhmp.c:425-525 (+ split_job_work :325-357): binned "kd" SAH along one axis */
 static float get_split_with_dim(orc_accel_t *b, int64_t left_in, int64_t right_in, const float aabb[6], int d, float *split)

@@ -40,6 +40,10 @@ const float *orc_accel_aabb(const orc_accel_t *a);
 void orc_intersect(const orc_accel_t *a, const cb_ray_t *ray, cb_hit_t *hit, uint64_t counters[4]);
 int  orc_visible(const orc_accel_t *a, const cb_ray_t *ray, float max_dist);
 
+/* accel_closest (accel.h:47): mutates ray->min_dist and *hit like the reference */
+void orc_closest(const orc_accel_t *a, cb_ray_t *ray, cb_hit_t *hit, float centre);
+void orc_closest_n(const orc_accel_t *a, cb_ray_t *rays, cb_hitrec_t *io, const float *centre, uint64_t n);
+
 /* batches; max_dist may be NULL (=FLT_MAX); counters (optional) accumulate
  * {rays, node visits with >=1 child hit, child boxes hit, prim tests} like ACCEL_DEBUG (qbvhmp.c:83-90) */
 void orc_intersect_n(const orc_accel_t *a, const cb_ray_t *rays, const float *max_dist, cb_hitrec_t *out,

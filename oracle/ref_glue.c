@@ -179,6 +179,21 @@ void ref_visible_n(void *a, const cb_ray_t *rays, const float *max_dist, int32_t
   }
 }
 
+/* accel_closest for n queries: ray.min_dist and {prim,u,v,dist} are in/out like the reference's ray_t / hit_t arguments */
+void ref_closest_n(void *a, cb_ray_t *rays, cb_hitrec_t *io, const float *centre, uint64_t n)
+{
+  for(uint64_t i=0;i<n;i++)
+  {
+    hit_t h;
+    memset(&h, 0, sizeof(h));
+    memcpy(&h.prim, io[i].prim, 8);
+    h.u = io[i].u; h.v = io[i].v; h.dist = io[i].dist;
+    accel_closest(a, (ray_t *)(rays+i), &h, centre[i]);
+    memcpy(io[i].prim, &h.prim, 8);
+    io[i].u = h.u; io[i].v = h.v; io[i].dist = h.dist; io[i].pad = 0;
+  }
+}
+
 /* ACCEL_DEBUG counters summed over threads: {accel_intersect, aabb_intersect, aabb_true, prims_intersect} */
 int ref_counters(void *va, uint64_t *out4, int reset)
 {

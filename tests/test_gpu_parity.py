@@ -268,6 +268,22 @@ def test_host_layer_accel_h(gpu):
         assert v == int(orc.visible(rays[i:i + 1], np.float32([1e3]))[0])
     ab = np.ctypeslib.as_array(H.accel_aabb(a), shape=(6,))
     assert np.allclose(ab, acc.aabb())
+    # accel_closest (accel.h:47): in/out ray->min_dist and hit, like qbvhmp.c:1493-1600
+    H.accel_closest.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_float]
+    hitmask = R.hit_prim64(want) != R.INVALID_PRIMID
+    for i in np.nonzero(hitmask)[0][:20]:
+        centre = np.float32(want["dist"][i] * (0.6 if i % 2 else 1.0))
+        r1 = rays[i:i + 1].copy()
+        io = np.zeros(1, R.HITREC)
+        io["prim"] = 0xFFFFFFFF
+        io["dist"] = 2 * centre
+        wr, wh = orc.closest(r1, io, [centre])
+        h1 = np.zeros(1, R.HIT)
+        h1["prim"] = 0xFFFFFFFF
+        h1["dist"] = 2 * centre
+        H.accel_closest(a, r1.ctypes.data, h1.ctypes.data, C.c_float(centre))
+        assert h1["dist"][0].view("u4") == wh["dist"][0].view("u4") and np.array_equal(h1["prim"][0], wh["prim"][0])
+        assert r1["min_dist"][0].view("u4") == wr["min_dist"][0].view("u4")
     H.accel_cleanup(a)
     acc.close()
     orc.close()
@@ -309,3 +325,23 @@ def test_full_size_properties(gpu):
     assert orc.check()[0] == 0
     acc.close()
     orc.close()
+
+
+@pytest.mark.parametrize("name", GOLDEN_NAMES)
+def test_accel_closest_golden(gpu, name):
+    """accel_closest on the reference-built tree against the reference's recorded answers (tests/golden/closest.npz), and
+    through the C host layer's single-query accel_closest()"""
+    z = np.load(os.path.join(ROOT, "tests", "golden", "closest.npz"))
+    g = Golden(name)
+    rec = lambda k, dt: np.ascontiguousarray(z[f"{name}_{k}"]).view(dt).reshape(-1)
+    acc = gpu.Accel(g.scene).import_qbvh(g.nodes, g.primid, g.aabb)
+    r, h = acc.closest(rec("rays", R.RAY), rec("io", R.HITREC), z[f"{name}_centre"])
+    assert_hits_equal(h, rec("out", R.HITREC), f"{name} closest")
+    assert np.array_equal(r["min_dist"].view("u4"), rec("out_rays", R.RAY)["min_dist"].view("u4"))
+    # GPU-built tree: same answers away from ties (the search is order dependent only through equal distances)
+    acc2 = gpu.Accel(g.scene).build()
+    r2, h2 = acc2.closest(rec("rays", R.RAY), rec("io", R.HITREC), z[f"{name}_centre"])
+    same = R.hit_prim64(h2) == R.hit_prim64(rec("out", R.HITREC))
+    assert same.mean() > 0.98, same.mean()
+    acc.close()
+    acc2.close()

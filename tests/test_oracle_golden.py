@@ -74,3 +74,17 @@ def test_empty_scene(cb, built):
     assert (R.hit_prim64(h) == R.INVALID_PRIMID).all() and (h["dist"] == R.FLT_MAX).all()
     assert (orc.visible(rays, np.full(4, 10.0, np.float32)) == 1).all()
     orc.close()
+
+
+def test_closest_matches_reference(built):
+    """accel_closest (qbvhmp.c:1493-1600): oracle restatement == the reference's recorded answers, incl. the mutated ray.min_dist"""
+    import os
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "closest.npz"))
+    for name in GOLDEN_NAMES:
+        g = Golden(name)
+        orc = Oracle(g.scene).import_tree(g.nodes, g.aabb, g.primid)
+        rec = lambda k, dt: np.ascontiguousarray(z[f"{name}_{k}"]).view(dt).reshape(-1)
+        r, h = orc.closest(rec("rays", R.RAY), rec("io", R.HITREC), z[f"{name}_centre"])
+        assert_hits_equal(h, rec("out", R.HITREC), f"{name} closest")
+        assert np.array_equal(r["min_dist"].view("u4"), rec("out_rays", R.RAY)["min_dist"].view("u4"))
+        orc.close()
