@@ -22,6 +22,7 @@
 #include <atomic>
 #include <mutex>
 #include <cstdlib>
+#include <type_traits>
 
 #define TRACE_BLOCK 128
 #ifndef TRACE_MIN_BLOCKS
@@ -156,7 +157,7 @@ __device__ __forceinline__ void node_slabs_fast(const Node128 *__restrict__ n, c
   }
 }
 
-#define CSWAP(cond, ka, ca, kb, cb) do { const float tk__ = ka; const uint64_t tc__ = ca; \
+#define CSWAP(cond, ka, ca, kb, cb) do { const float tk__ = ka; const ref_t tc__ = ca; \
   ka = (cond) ? kb : ka; ca = (cond) ? cb : ca; kb = (cond) ? tk__ : kb; cb = (cond) ? tc__ : cb; } while(0)
 
 // ---------------------------------------------------------------------------------------------
@@ -164,7 +165,11 @@ __device__ __forceinline__ void node_slabs_fast(const Node128 *__restrict__ n, c
 //   ANALYTIC: the scene has spheres / cylinders / cones (their tests carry double precision and libm calls; scenes
 //             without them get a kernel without that code and with fewer registers)
 // ---------------------------------------------------------------------------------------------
-template<bool MB, bool CNT, int STACK, bool ANALYTIC>
+//   C32     : child references are handled as 32 bits inside the kernel (leaf flag in bit 31, begin<<5|count or the node index
+//             below; possible while the scene has < 2^26 primitives): the (entry distance, child) pair of a stack entry is
+//             then ONE 8-byte word -- stack pushes/pops were 22 % of this kernel's instructions -- and the ordering
+//             swaps move half the registers.  Larger scenes use the 64-bit form.
+template<bool MB, bool CNT, int STACK, bool ANALYTIC, bool C32>
 __global__ void __launch_bounds__(TRACE_BLOCK, (!MB && !CNT && !ANALYTIC) ? TRACE_MIN_BLOCKS : 1)
 k_intersect(DevAccel A, const cb_ray_t *__restrict__ rays, const float *__restrict__ max_dist,
             cb_hitrec_t *__restrict__ out, uint64_t n, unsigned long long *ticket, unsigned long long *counters,
@@ -172,15 +177,17 @@ k_intersect(DevAccel A, const cb_ray_t *__restrict__ rays, const float *__restri
 {
   const uint32_t lane = threadIdx.x & 31u;
   const uint32_t lt_mask = (1u << lane) - 1u;
+  typedef typename std::conditional<C32, uint32_t, uint64_t>::type ref_t;
   unsigned long long cnt[4] = {0, 0, 0, 0};
-  uint64_t stack[STACK];
-  float stack_dist[STACK];
+  uint64_t stack[STACK];                      // C32: (child << 32) | entry distance bits
+  float stack_dist[C32 ? 1 : STACK];
   int sp = 0;
   int state = ST_IDLE;
   bool exhausted = false;
   RayD r;
   HitD h;
-  uint64_t ray_i = 0, cur = 0;
+  uint64_t ray_i = 0;
+  ref_t cur = 0;
   float ix = 0.0f, iy = 0.0f, iz = 0.0f, t0 = 1.0f, t1 = 0.0f;
   uint32_t nearbits = 0;
   uint32_t near_off[3] = {0, 0, 0};
@@ -247,7 +254,7 @@ k_intersect(DevAccel A, const cb_ray_t *__restrict__ rays, const float *__restri
     else if(state == ST_NODE)
     {
       float key[4];
-      uint64_t child[4];
+      ref_t child[4];
       int axis0, axis00, axis01;
       if(MB || CNT || exact)
       {
@@ -255,27 +262,31 @@ k_intersect(DevAccel A, const cb_ray_t *__restrict__ rays, const float *__restri
         if(exact) node_slabs<MB, true >(A.nodes, cur, r.px, r.py, r.pz, ix, iy, iz, t0, t1, h.dist, o);
         else      node_slabs<MB, false>(A.nodes, cur, r.px, r.py, r.pz, ix, iy, iz, t0, t1, h.dist, o);
         if(CNT && (o.hit[0] | o.hit[1] | o.hit[2] | o.hit[3])) { cnt[1]++; for(int c=0;c<4;c++) cnt[2] += o.hit[c] ? 1 : 0; }
+        // empty leaves (count 0) can only be popped and dropped again: never visit them
 #pragma unroll
-        for(int c=0;c<4;c++) { key[c] = o.hit[c] ? o.tmin[c] : KEY_MISS; child[c] = o.child[c]; }
+        for(int c=0;c<4;c++)
+        {
+          key[c] = (o.hit[c] && !is_empty_leaf(o.child[c])) ? o.tmin[c] : KEY_MISS;
+          child[c] = C32 ? (ref_t)((uint32_t)o.child[c] | (uint32_t)(o.child[c] >> 32)) : (ref_t)o.child[c];
+        }
         axis0 = o.axis0; axis00 = o.axis00; axis01 = o.axis01;
       }
       else
-      {
+      { // no empty-leaf test needed here: this library's builder gives empty slots an inverted box, which the sign-selected
+        // slab test misses by construction (imported reference trees are Node256 and take the other path)
         const Node128 *nd = reinterpret_cast<const Node128 *>(A.nodes) + cur;
         node_slabs_fast(nd, near_off, r.px, r.py, r.pz, ix, iy, iz, h.dist, key);
-        const ulonglong2 *ch = reinterpret_cast<const ulonglong2 *>(nd->child);
-        const ulonglong2 c01 = __ldg(ch), c23 = __ldg(ch + 1);
-        const uint32_t ax = (uint32_t)(c01.x >> CB_AXIS_SHIFT) & 63u;
-        child[0] = c01.x & CB_CHILD_MASK; child[1] = c01.y; child[2] = c23.x; child[3] = c23.y;
+        const uint4 *ch = reinterpret_cast<const uint4 *>(nd->child);
+        const uint4 c01 = __ldg(ch), c23 = __ldg(ch + 1);   // {lo0, hi0, lo1, hi1}, {lo2, hi2, lo3, hi3}
+        const uint32_t ax = (c01.y >> (CB_AXIS_SHIFT - 32)) & 63u;
+        const uint32_t hi0 = c01.y & (uint32_t)(CB_CHILD_MASK >> 32);
+        if(C32) { child[0] = (ref_t)(c01.x | hi0); child[1] = (ref_t)(c01.z | c01.w); child[2] = (ref_t)(c23.x | c23.y); child[3] = (ref_t)(c23.z | c23.w); }
+        else
+        {
+          child[0] = (ref_t)(((uint64_t)hi0 << 32) | c01.x);   child[1] = (ref_t)(((uint64_t)c01.w << 32) | c01.z);
+          child[2] = (ref_t)(((uint64_t)c23.y << 32) | c23.x); child[3] = (ref_t)(((uint64_t)c23.w << 32) | c23.z);
+        }
         axis0 = ax & 3; axis00 = (ax >> 2) & 3; axis01 = (ax >> 4) & 3;
-      }
-      // empty leaves (count 0) can only be popped and dropped again: never visit them.  (The fast path needs no test: this
-      // library's builder gives empty slots an inverted box, which the sign-selected slab test misses by construction;
-      // imported reference trees are Node256 and take the other path.)
-      if(MB || CNT || exact)
-      {
-#pragma unroll
-        for(int c=0;c<4;c++) if(is_empty_leaf(child[c])) key[c] = KEY_MISS;
       }
       // the reference's topological order (qbvhmp.c:1313-1320) as three conditional swaps: inside the lower pair by the
       // sign along axis00, inside the upper pair by the sign along axis01, the two pairs by the sign along axis0
@@ -289,9 +300,12 @@ k_intersect(DevAccel A, const cb_ray_t *__restrict__ rays, const float *__restri
       const int first = KEY_HIT(key[0]) ? 0 : KEY_HIT(key[1]) ? 1 : KEY_HIT(key[2]) ? 2 : KEY_HIT(key[3]) ? 3 : 4;
       if(first < 4)
       {
-        if(KEY_HIT(key[3]) && first < 3) { stack_dist[sp] = key[3]; stack[sp++] = child[3]; }
-        if(KEY_HIT(key[2]) && first < 2) { stack_dist[sp] = key[2]; stack[sp++] = child[2]; }
-        if(KEY_HIT(key[1]) && first < 1) { stack_dist[sp] = key[1]; stack[sp++] = child[1]; }
+#define PUSH(k) do { if(C32) stack[sp++] = ((uint64_t)child[k] << 32) | __float_as_uint(key[k]); \
+                     else { stack_dist[sp] = key[k]; stack[sp++] = child[k]; } } while(0)
+        if(KEY_HIT(key[3]) && first < 3) PUSH(3);
+        if(KEY_HIT(key[2]) && first < 2) PUSH(2);
+        if(KEY_HIT(key[1]) && first < 1) PUSH(1);
+#undef PUSH
         cur = first == 0 ? child[0] : first == 1 ? child[1] : first == 2 ? child[2] : child[3];
         need_pop = false;
         new_cur = true;
@@ -302,8 +316,17 @@ k_intersect(DevAccel A, const cb_ray_t *__restrict__ rays, const float *__restri
       while(sp > 0)
       {
         --sp;
-        if(stack_dist[sp] > h.dist) continue;
-        cur = stack[sp];
+        if(C32)
+        {
+          const uint64_t e = stack[sp];
+          if(__uint_as_float((uint32_t)e) > h.dist) continue;
+          cur = (ref_t)(e >> 32);
+        }
+        else
+        {
+          if(stack_dist[sp] > h.dist) continue;
+          cur = (ref_t)stack[sp];
+        }
         new_cur = true;
         break;
       }
@@ -318,9 +341,10 @@ k_intersect(DevAccel A, const cb_ray_t *__restrict__ rays, const float *__restri
     }
     if(new_cur)
     {
-      if(cur & CB_LEAF_BIT)
+      const ref_t leaf_bit = C32 ? (ref_t)0x80000000u : (ref_t)CB_LEAF_BIT;
+      if(cur & leaf_bit)
       {
-        rec = A.recs + ((cur ^ CB_LEAF_BIT) >> 5)*(uint64_t)rec_stride;
+        rec = A.recs + (uint64_t)((cur ^ leaf_bit) >> 5)*(uint64_t)rec_stride;
         prims_left = (uint32_t)cur & 31u;
         state = ST_PRIM;   // empty leaves are never pushed, so prims_left >= 1
       }
@@ -602,18 +626,28 @@ static int refill_threshold()
   return g_refill_threshold;
 }
 
-template<bool MB, bool CNT, int STACK, bool ANALYTIC>
-static int launch_intersect_k(const cb200_accel *a, const cb_ray_t *d_rays, const float *d_max_dist, cb_hitrec_t *d_out,
+template<bool MB, bool CNT, int STACK, bool ANALYTIC, bool C32>
+static int launch_intersect_k2(const cb200_accel *a, const cb_ray_t *d_rays, const float *d_max_dist, cb_hitrec_t *d_out,
                               uint64_t n, cudaStream_t stream, unsigned long long *d_counters, const uint32_t *d_order)
 {
   unsigned long long *ticket;
   if(get_ticket(stream, &ticket)) return CB200_ERR_CUDA;
-  auto k = k_intersect<MB, CNT, STACK, ANALYTIC>;
+  auto k = k_intersect<MB, CNT, STACK, ANALYTIC, C32>;
   k<<<grid_for(n, (const void *)k), TRACE_BLOCK, 0, stream>>>(a->dev, d_rays, d_max_dist, d_out, n, ticket, d_counters,
                                                               prim_threshold(), refill_threshold(), d_order);
   cb200_count_launch();
   CB_CUDA(cudaGetLastError());
   return 0;
+}
+
+template<bool MB, bool CNT, int STACK, bool ANALYTIC>
+static int launch_intersect_k(const cb200_accel *a, const cb_ray_t *d_rays, const float *d_max_dist, cb_hitrec_t *d_out,
+                              uint64_t n, cudaStream_t stream, unsigned long long *d_counters, const uint32_t *d_order)
+{
+  // 32-bit child references inside the kernel while begin<<5|count and node indices fit 31 bits
+  const bool c32 = !CNT && a->dev.num_prims < (1ull << 26) && a->dev.num_nodes < (1ull << 31);
+  if(c32) return launch_intersect_k2<MB, CNT, STACK, ANALYTIC, !CNT>(a, d_rays, d_max_dist, d_out, n, stream, d_counters, d_order);
+  return launch_intersect_k2<MB, CNT, STACK, ANALYTIC, false>(a, d_rays, d_max_dist, d_out, n, stream, d_counters, d_order);
 }
 
 template<bool MB>
