@@ -364,19 +364,21 @@ k_intersect(DevAccel A, const cb_ray_t *__restrict__ rays, const float *__restri
 //           (ray.ignore honoured, dist > min_dist && dist <= limit, strict < for analytic prims) and the sampled light
 //           primitive skip[i] never occludes.  The caller has already clipped max_dist to the first crossing of the light
 //           primitive itself, so "any accepted primitive" == "the closest hit is not the light".
-template<bool MB, int STACK, bool ANALYTIC, bool SHADOW>
+template<bool MB, int STACK, bool ANALYTIC, bool SHADOW, bool C32>
 __global__ void __launch_bounds__(TRACE_BLOCK, (!MB && !ANALYTIC) ? TRACE_MIN_BLOCKS : 1)
 k_visible(DevAccel A, const cb_ray_t *__restrict__ rays, const float *__restrict__ max_dist, const uint2 *__restrict__ skip,
           int32_t *__restrict__ out, uint64_t n, unsigned long long *ticket, int prim_threshold, int refill_threshold)
 {
   const uint32_t lane = threadIdx.x & 31u;
   const uint32_t lt_mask = (1u << lane) - 1u;
-  uint64_t stack[STACK];
+  typedef typename std::conditional<C32, uint32_t, uint64_t>::type ref_t;   // see k_intersect
+  ref_t stack[STACK];
   int sp = 0;
   int state = ST_IDLE;
   bool exhausted = false;
   RayD r;
-  uint64_t ray_i = 0, cur = 0;
+  uint64_t ray_i = 0;
+  ref_t cur = 0;
   float ix = 0.0f, iy = 0.0f, iz = 0.0f, t0 = 1.0f, t1 = 0.0f, md = 0.0f;
   uint32_t near_off[3] = {0, 0, 0};
   bool exact = false;
@@ -449,16 +451,24 @@ k_visible(DevAccel A, const cb_ray_t *__restrict__ rays, const float *__restrict
         if(exact) node_slabs<MB, true >(A.nodes, cur, r.px, r.py, r.pz, ix, iy, iz, t0, t1, md, o);
         else      node_slabs<MB, false>(A.nodes, cur, r.px, r.py, r.pz, ix, iy, iz, t0, t1, md, o);
 #pragma unroll
-        for(int c=0;c<4;c++) if(o.hit[c] && !is_empty_leaf(o.child[c])) stack[sp++] = o.child[c];
+        for(int c=0;c<4;c++) if(o.hit[c] && !is_empty_leaf(o.child[c]))
+          stack[sp++] = C32 ? (ref_t)((uint32_t)o.child[c] | (uint32_t)(o.child[c] >> 32)) : (ref_t)o.child[c];
       }
       else
       {
         const Node128 *nd = reinterpret_cast<const Node128 *>(A.nodes) + cur;
         float key[4];
         node_slabs_fast(nd, near_off, r.px, r.py, r.pz, ix, iy, iz, md, key);
-        const ulonglong2 *ch = reinterpret_cast<const ulonglong2 *>(nd->child);
-        const ulonglong2 c01 = __ldg(ch), c23 = __ldg(ch + 1);
-        const uint64_t child[4] = {c01.x & CB_CHILD_MASK, c01.y, c23.x, c23.y};
+        const uint4 *ch = reinterpret_cast<const uint4 *>(nd->child);
+        const uint4 c01 = __ldg(ch), c23 = __ldg(ch + 1);
+        const uint32_t hi0 = c01.y & (uint32_t)(CB_CHILD_MASK >> 32);
+        ref_t child[4];
+        if(C32) { child[0] = (ref_t)(c01.x | hi0); child[1] = (ref_t)(c01.z | c01.w); child[2] = (ref_t)(c23.x | c23.y); child[3] = (ref_t)(c23.z | c23.w); }
+        else
+        {
+          child[0] = (ref_t)(((uint64_t)hi0 << 32) | c01.x);   child[1] = (ref_t)(((uint64_t)c01.w << 32) | c01.z);
+          child[2] = (ref_t)(((uint64_t)c23.y << 32) | c23.x); child[3] = (ref_t)(((uint64_t)c23.w << 32) | c23.z);
+        }
 #pragma unroll
         for(int c=0;c<4;c++) if(KEY_HIT(key[c])) stack[sp++] = child[c];   // empty slots carry inverted boxes: never hit here
       }
@@ -469,9 +479,10 @@ k_visible(DevAccel A, const cb_ray_t *__restrict__ rays, const float *__restrict
       if(sp > 0)
       {
         cur = stack[--sp];
-        if(cur & CB_LEAF_BIT)
+        const ref_t leaf_bit = C32 ? (ref_t)0x80000000u : (ref_t)CB_LEAF_BIT;
+        if(cur & leaf_bit)
         {
-          rec = A.recs + ((cur ^ CB_LEAF_BIT) >> 5)*(uint64_t)rec_stride;
+          rec = A.recs + (uint64_t)((cur ^ leaf_bit) >> 5)*(uint64_t)rec_stride;
           prims_left = (uint32_t)cur & 31u;
           state = ST_PRIM;
         }
@@ -679,16 +690,12 @@ static int launch_visible_k(const cb200_accel *a, const cb_ray_t *d_rays, const 
 {
   unsigned long long *ticket;
   if(get_ticket(stream, &ticket)) return CB200_ERR_CUDA;
-  if(d_skip)
-  {
-    auto k = k_visible<MB, STACK, ANALYTIC, true>;
-    k<<<grid_for(n, (const void *)k), TRACE_BLOCK, 0, stream>>>(a->dev, d_rays, d_max_dist, d_skip, d_out, n, ticket, prim_threshold(), refill_threshold());
-  }
-  else
-  {
-    auto k = k_visible<MB, STACK, ANALYTIC, false>;
-    k<<<grid_for(n, (const void *)k), TRACE_BLOCK, 0, stream>>>(a->dev, d_rays, d_max_dist, nullptr, d_out, n, ticket, prim_threshold(), refill_threshold());
-  }
+  const bool c32 = a->dev.num_prims < (1ull << 26) && a->dev.num_nodes < (1ull << 31);
+#define VIS_LAUNCH(SH, C) do { auto k = k_visible<MB, STACK, ANALYTIC, SH, C>; \
+    k<<<grid_for(n, (const void *)k), TRACE_BLOCK, 0, stream>>>(a->dev, d_rays, d_max_dist, d_skip, d_out, n, ticket, prim_threshold(), refill_threshold()); } while(0)
+  if(d_skip) { if(c32) VIS_LAUNCH(true, true); else VIS_LAUNCH(true, false); }
+  else       { if(c32) VIS_LAUNCH(false, true); else VIS_LAUNCH(false, false); }
+#undef VIS_LAUNCH
   cb200_count_launch();
   CB_CUDA(cudaGetLastError());
   return 0;
