@@ -59,8 +59,8 @@ REFDIR = os.path.join(ROOT, "oracle", "_ref")
 
 def ncu_traffic():
     """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel from the committed `ncu --set full` capture
-    of this same command (profiles/r1d_k_intersect_ncu.json); None when the summary is not there"""
-    p = os.path.join(ROOT, "profiles", "r1d_k_intersect_ncu.json")
+    of this same command (profiles/r1e_k_intersect_ncu.json); None when the summary is not there"""
+    p = os.path.join(ROOT, "profiles", "r1e_k_intersect_ncu.json")
     try:
         rows = json.load(open(p))
         tot = []
@@ -385,7 +385,7 @@ def main():
         "roofline": {"bound": "hbm", "kernel": "k_intersect (closest-hit traversal, all launches of the timed region, rank 0)",
                      "achieved": achieved, "peak": hbm, "unit": "GB/s", "frac": achieved / hbm, "peak_source": which, "traffic": traffic,
                      "traffic_note": f"DRAM bytes per ~8.3 M-ray launch from {traffic_src}: the ray and hit streams only -- nodes and primitives are "
-                                     "served by L1/L2, so HBM is not the binding roof (issue slots 67 %, L1 wavefronts 78 %)" if traffic else None,
+                                     "served by L1/L2, so HBM is not the binding roof (issue slots 73 %, L1 wavefronts 71 %)" if traffic else None,
                      "algorithmic_bytes_per_launch": bytes_per_ray * 8.3e6,
                      "bytes_per_ray": bytes_per_ray, "nodes_per_ray": n_node, "prims_per_ray": n_prim,
                      "rays": stt["rays_closest"], "kernel_ms": ms_closest},
