@@ -329,7 +329,7 @@ __device__ void prim_test_geo(const SceneGeo &S, uint64_t pid, const RayD &r, Hi
 
 __device__ __forceinline__ float max3abs(V3 x) { return fmaxf(fmaxf(.5f, fabsf(x.x)), fmaxf(fabsf(x.y), fabsf(x.z))); }
 
-struct ShadeCounters { unsigned long long next, nee, hits, splats; };   // next, nee, hits are per wave; splats keeps counting
+struct ShadeCounters { unsigned long long next, nee, hits[3], splats; };   // next, nee, hits[kind] are per wave; splats keeps counting
 
 // path_G for the edge between a surface vertex and the sampled light point (pathspace.c:58-69)
 __device__ __forceinline__ float cos_lambert(const Vtx &v, const Vtx &l, V3 d, float dist)
@@ -338,44 +338,53 @@ __device__ __forceinline__ float cos_lambert(const Vtx &v, const Vtx &l, V3 d, f
 }
 
 // Paths whose ray escaped into the (black) sky have nothing left to do (pathspace.c:856-873): the shading kernel only runs
-// on the slots that hit something.  Their indices are compacted first, so that its warps are full instead of ~40 % occupied.
+// on the slots that hit something.  Their indices are compacted first -- into one list per BSDF kind of the surface that was
+// hit (diffuse / dielectric / metal), so that every shading launch has full warps AND a single material class: the
+// "material-sorted" part of the wavefront.  list[kind*n_cap + k] = slot.
 __global__ void __launch_bounds__(256)
-k_compact_hits(const cb_hitrec_t *__restrict__ hits, uint32_t n, uint32_t *__restrict__ list, ShadeCounters *cnt)
+k_compact_hits(RenderDev R, const cb_hitrec_t *__restrict__ hits, uint32_t n, uint32_t n_cap, uint32_t *__restrict__ list, ShadeCounters *cnt,
+               int single_kind)
 {
-  __shared__ uint32_t warp_count[8];
-  __shared__ uint32_t block_base;
+  __shared__ uint32_t warp_count[3][8];
+  __shared__ uint32_t block_base[3];
   const uint32_t i = blockIdx.x*blockDim.x + threadIdx.x, lane = threadIdx.x & 31u, w = threadIdx.x >> 5;
-  bool hit = false;
+  int kind = -1;
   if(i < n)
   {
     const uint2 p = *reinterpret_cast<const uint2 *>(hits + i);   // prim id words
-    hit = (p.x & p.y) != 0xffffffffu;
+    if((p.x & p.y) != 0xffffffffu)
+      kind = single_kind >= 0 ? single_kind : R.mats.mat[R.geo.shape_material[p.x >> 3]].bsdf;
   }
-  const uint32_t m = __ballot_sync(0xffffffffu, hit);
-  if(lane == 0) warp_count[w] = __popc(m);
+  uint32_t m[3];
+#pragma unroll
+  for(int k=0;k<3;k++) { m[k] = __ballot_sync(0xffffffffu, kind == k); if(lane == 0) warp_count[k][w] = __popc(m[k]); }
   __syncthreads();
-  if(threadIdx.x == 0)
+  if(threadIdx.x < 3)
   {
+    const int k = threadIdx.x;
     uint32_t tot = 0;
-    for(int k=0;k<8;k++) { const uint32_t c = warp_count[k]; warp_count[k] = tot; tot += c; }
-    block_base = tot ? (uint32_t)atomicAdd(&cnt->hits, (unsigned long long)tot) : 0u;
+    for(int q=0;q<8;q++) { const uint32_t c = warp_count[k][q]; warp_count[k][q] = tot; tot += c; }
+    block_base[k] = tot ? (uint32_t)atomicAdd(&cnt->hits[k], (unsigned long long)tot) : 0u;
   }
   __syncthreads();
-  if(hit) list[block_base + warp_count[w] + __popc(m & ((1u << lane) - 1u))] = i;
+#pragma unroll
+  for(int k=0;k<3;k++)
+    if(kind == k) list[(size_t)k*n_cap + block_base[k] + warp_count[k][w] + __popc(m[k] & ((1u << lane) - 1u))] = i;
 }
 
-// one vertex of every live path.  KINDS = bit mask of the BSDF kinds the scene's shapes use (1 diffuse, 2 dielectric,
-// 4 metal): a diffuse-only scene gets a kernel without the GGX / Fresnel / nested-media code (a third of the instructions,
-// fewer instruction-cache misses -- 24 % of k_shade's stall samples in the generic kernel were "no instruction")
+// one vertex of every live path whose surface has BSDF kind KIND (0 diffuse, 1 dielectric, 2 metal): each launch carries the
+// code of ONE BSDF (the all-in-one kernel was 17 k instructions and lost 24 % of its stall samples to instruction-cache
+// misses) and no lane waits for another material's branch.  KINDS = 1 << KIND for the templates of shading.cuh; light
+// vertices reached by next-event estimation only need their emission slots, which every variant fills.
 template<int KINDS>
 __global__ void __launch_bounds__(RB)
 k_shade(RenderDev R, uint32_t n, const PathState *__restrict__ st_in, const cb_ray_t *__restrict__ rays_in,
         const cb_hitrec_t *__restrict__ hits, PathState *__restrict__ st_out, cb_ray_t *__restrict__ rays_out,
         cb_ray_t *__restrict__ nee_rays, float *__restrict__ nee_maxdist, uint2 *__restrict__ nee_light, NeeRec *__restrict__ nee_recs,
-        ShadeCounters *cnt, uint32_t *__restrict__ rkeys_out, const uint32_t *__restrict__ hit_list)
+        ShadeCounters *cnt, uint32_t *__restrict__ rkeys_out, const uint32_t *__restrict__ hit_list, int kind)
 {
   const uint32_t t = blockIdx.x*blockDim.x + threadIdx.x;
-  const uint32_t n_hits = (uint32_t)*reinterpret_cast<volatile unsigned long long *>(&cnt->hits);   // written by k_compact_hits
+  const uint32_t n_hits = (uint32_t)*reinterpret_cast<volatile unsigned long long *>(&cnt->hits[kind]);   // written by k_compact_hits
   if(blockIdx.x*blockDim.x >= n_hits) return;   // whole block beyond the list (the grid is sized for n, the upper bound)
   (void)n;
   bool alive = false, have_nee = false, did_splat = false;
@@ -950,7 +959,7 @@ cb200_render_t *cb200_render_create(cb200_accel_t *a, const cb_render_desc_t *de
   D.fb = r->own_fb = dev_alloc<float>(r, (size_t)desc->width*desc->height*3);
   for(int k=0;k<2;k++) { r->st[k] = dev_alloc<PathState>(r, N); r->rays[k] = dev_alloc<cb_ray_t>(r, N); ok = ok && r->st[k] && r->rays[k]; }
   r->hits = dev_alloc<cb_hitrec_t>(r, N);
-  r->hit_list = dev_alloc<uint32_t>(r, N); ok = ok && r->hit_list;
+  r->hit_list = dev_alloc<uint32_t>(r, 3*N); ok = ok && r->hit_list;
   r->nee_rays = dev_alloc<cb_ray_t>(r, N); r->nee_md = dev_alloc<float>(r, N); r->nee_recs = dev_alloc<NeeRec>(r, N); r->nee_light = dev_alloc<uint2>(r, N); r->nee_vis = dev_alloc<int32_t>(r, N);
   r->d_cnt = dev_alloc<ShadeCounters>(r, 1);
   for(int k=0;k<2;k++) { r->keys[k] = dev_alloc<uint32_t>(r, N); r->order[k] = dev_alloc<uint32_t>(r, N); ok = ok && r->keys[k] && r->order[k]; }
@@ -1070,19 +1079,20 @@ static int render_wave(cb200_render *r, uint32_t n, cudaStream_t st)
   }
   if(rc) return rc;
   r->stats.rays_closest += n; r->stats.kernel_launches++;
-  CB_CUDA(cudaMemsetAsync(r->d_cnt, 0, 3*sizeof(unsigned long long), st));   // next, nee, hits (splats keeps counting)
+  CB_CUDA(cudaMemsetAsync(r->d_cnt, 0, 5*sizeof(unsigned long long), st));   // next, nee, hits[3] (splats keeps counting)
   {
     TimeScope ts(r, st, KC_SHADE, n);
-    k_compact_hits<<<(n + 255)/256, 256, 0, st>>>(r->hits, n, r->hit_list, r->d_cnt);
+    const int single = (r->bsdf_kinds == 1) ? 0 : (r->bsdf_kinds == 2) ? 1 : (r->bsdf_kinds == 4) ? 2 : -1;
+    k_compact_hits<<<(n + 255)/256, 256, 0, st>>>(r->dev, r->hits, n, (uint32_t)r->batch, r->hit_list, r->d_cnt, single);
     cb200_count_launch(); r->stats.kernel_launches++;
-    if(r->bsdf_kinds == 1)
-      k_shade<1><<<(n + RB - 1)/RB, RB, 0, st>>>(r->dev, n, r->st[cur], r->rays[cur], r->hits, r->st[cur^1], r->rays[cur^1],
-                                                 r->nee_rays, r->nee_md, r->nee_light, r->nee_recs, r->d_cnt, r->ray_sort ? r->rkeys[cur^1] : nullptr, r->hit_list);
-    else
-      k_shade<7><<<(n + RB - 1)/RB, RB, 0, st>>>(r->dev, n, r->st[cur], r->rays[cur], r->hits, r->st[cur^1], r->rays[cur^1],
-                                                 r->nee_rays, r->nee_md, r->nee_light, r->nee_recs, r->d_cnt, r->ray_sort ? r->rkeys[cur^1] : nullptr, r->hit_list);
+    uint32_t *rk = r->ray_sort ? r->rkeys[cur^1] : nullptr;
+#define SHADE_LAUNCH(K) k_shade<(1 << K)><<<(n + RB - 1)/RB, RB, 0, st>>>(r->dev, n, r->st[cur], r->rays[cur], r->hits, r->st[cur^1], r->rays[cur^1], \
+      r->nee_rays, r->nee_md, r->nee_light, r->nee_recs, r->d_cnt, rk, r->hit_list + (size_t)K*r->batch, K)
+    if(r->bsdf_kinds & 1) { SHADE_LAUNCH(0); cb200_count_launch(); r->stats.kernel_launches++; }
+    if(r->bsdf_kinds & 2) { SHADE_LAUNCH(1); cb200_count_launch(); r->stats.kernel_launches++; }
+    if(r->bsdf_kinds & 4) { SHADE_LAUNCH(2); cb200_count_launch(); r->stats.kernel_launches++; }
+#undef SHADE_LAUNCH
   }
-  cb200_count_launch(); r->stats.kernel_launches++;
   CB_CUDA(cudaMemcpyAsync(r->h_cnt, r->d_cnt, sizeof(ShadeCounters), cudaMemcpyDeviceToHost, st));
   CB_CUDA(cudaStreamSynchronize(st));
   const uint32_t n_next = (uint32_t)r->h_cnt->next, n_nee = (uint32_t)r->h_cnt->nee;

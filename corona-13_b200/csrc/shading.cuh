@@ -312,7 +312,7 @@ template<int KINDS = 7>
 CBD void bsdf_prepare(const MaterialsDev &M, Vtx &v, float lambda, const Media &med, float cur_ior)
 {
   const cb_material_t &m = M.mat[v.mat];
-  if(KINDS == 1 || m.bsdf == CB_BSDF_DIFFUSE)
+  if(KINDS == 1 || ((KINDS & 1) && m.bsdf == CB_BSDF_DIFFUSE))
   {
     if(v.rd > 0.0f) v.material_modes = M_REFLECT | M_DIFFUSE;
   }
@@ -494,7 +494,7 @@ CBD float bsdf_sample(const MaterialsDev &M, Vtx &v, V3 wi, float lambda, float 
                       V3 &wo, float &pdf)
 {
   const cb_material_t &m = M.mat[v.mat];
-  if(KINDS == 1 || m.bsdf == CB_BSDF_DIFFUSE)
+  if(KINDS == 1 || ((KINDS & 1) && m.bsdf == CB_BSDF_DIFFUSE))
   { // sample_d, shader.c:165-205
     const float x1 = r_x, x2 = r_y;
     const float s = sqrtf(x1);
@@ -611,7 +611,7 @@ template<int KINDS = 7>
 CBD float bsdf_eval(const MaterialsDev &M, Vtx &v, V3 wi, V3 wo, float lambda, float cur_ior)
 {
   const cb_material_t &m = M.mat[v.mat];
-  if(KINDS == 1 || m.bsdf == CB_BSDF_DIFFUSE)
+  if(KINDS == 1 || ((KINDS & 1) && m.bsdf == CB_BSDF_DIFFUSE))
   { // brdf_d (sensor paths), shader.c:207-249
     v.mode = M_DIFFUSE | M_REFLECT;
     const float cos_out_ns = dot(v.n, wo);
@@ -714,7 +714,7 @@ template<int KINDS = 7>
 CBD float bsdf_pdf(const MaterialsDev &M, const Vtx &v, V3 wi, V3 wo)
 {
   const cb_material_t &m = M.mat[v.mat];
-  if(KINDS == 1 || m.bsdf == CB_BSDF_DIFFUSE) return (float)(1.0/PI_D);
+  if(KINDS == 1 || ((KINDS & 1) && m.bsdf == CB_BSDF_DIFFUSE)) return (float)(1.0/PI_D);
   if((KINDS & 2) && m.bsdf == CB_BSDF_DIELECTRIC)
   { // dielectric.c:96-237, culled_modes == 0
     const V3 n = v.n;
