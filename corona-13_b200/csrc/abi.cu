@@ -196,6 +196,7 @@ cb200_accel_t *cb200_accel_import_qbvh(cb200_scene_t *s, const cb_qbvh_node_t *n
   a->dev.nodes = a->d_nodes;
   a->dev.num_nodes = num_nodes;
   a->dev.mb = 1;    // reference layout: always interpolates the two box sets, even for static scenes
+  a->dev.imported = 1;
   if(aabb) memcpy(a->aabb, aabb, sizeof(float)*6);
   if(cb200_build_records(a, 0)) { cb200_accel_destroy(a); return nullptr; }
   if(cudaStreamSynchronize(0) != cudaSuccess) { g_error = "accel_import_qbvh: sync failed"; cb200_accel_destroy(a); return nullptr; }

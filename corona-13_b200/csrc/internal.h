@@ -47,6 +47,8 @@ struct DevAccel
   const float4 *recs;        // prim records, rec_units*4 float4 per primitive
   uint32_t      rec_units;   // 1: static scene, 2: open+close vertices
   uint32_t      mb;          // nodes carry shutter-close boxes
+  uint32_t      imported;    // tree adopted from the reference builder (empty leaves may have ordinary boxes)
+  uint32_t      pad_;
   uint64_t      num_nodes;
   uint64_t      num_prims;
 };

@@ -157,6 +157,35 @@ __device__ __forceinline__ void node_slabs_fast(const Node128 *__restrict__ n, c
   }
 }
 
+// the same for nodes with shutter-open and shutter-close boxes: every plane is first interpolated to the ray's time exactly
+// like aabb_intersect does (box0*t0 + box1*t1, qbvhmp.c:1206-1215)
+__device__ __forceinline__ void node_slabs_fast_mb(const Node256 *__restrict__ n, const uint32_t near_off[3], float px, float py, float pz,
+                                                   float ix, float iy, float iz, float t0, float t1, float tmax_init, float key[4])
+{
+  const float4 *a0 = reinterpret_cast<const float4 *>(n->aabb0), *a1 = reinterpret_cast<const float4 *>(n->aabb1);
+  float4 q[6], w[6];
+  q[0] = __ldg(a0 + near_off[0]);     w[0] = __ldg(a1 + near_off[0]);
+  q[1] = __ldg(a0 + 1 + near_off[1]); w[1] = __ldg(a1 + 1 + near_off[1]);
+  q[2] = __ldg(a0 + 2 + near_off[2]); w[2] = __ldg(a1 + 2 + near_off[2]);
+  q[3] = __ldg(a0 + 3 - near_off[0]); w[3] = __ldg(a1 + 3 - near_off[0]);
+  q[4] = __ldg(a0 + 4 - near_off[1]); w[4] = __ldg(a1 + 4 - near_off[1]);
+  q[5] = __ldg(a0 + 5 - near_off[2]); w[5] = __ldg(a1 + 5 - near_off[2]);
+  float pl[6][4];
+#pragma unroll
+  for(int k=0;k<6;k++)
+  {
+    pl[k][0] = q[k].x*t0 + w[k].x*t1; pl[k][1] = q[k].y*t0 + w[k].y*t1;
+    pl[k][2] = q[k].z*t0 + w[k].z*t1; pl[k][3] = q[k].w*t0 + w[k].w*t1;
+  }
+#pragma unroll
+  for(int c=0;c<4;c++)
+  {
+    const float tmin = fmaxf(fmaxf(0.0f, (pl[0][c] - px)*ix), fmaxf((pl[1][c] - py)*iy, (pl[2][c] - pz)*iz));
+    const float tmax = fminf(fminf(tmax_init, (pl[3][c] - px)*ix), fminf((pl[4][c] - py)*iy, (pl[5][c] - pz)*iz));
+    key[c] = tmin <= tmax ? tmin : KEY_MISS;
+  }
+}
+
 #define CSWAP(cond, ka, ca, kb, cb) do { const float tk__ = ka; const ref_t tc__ = ca; \
   ka = (cond) ? kb : ka; ca = (cond) ? cb : ca; kb = (cond) ? tk__ : kb; cb = (cond) ? tc__ : cb; } while(0)
 
@@ -256,7 +285,22 @@ k_intersect(DevAccel A, const cb_ray_t *__restrict__ rays, const float *__restri
       float key[4];
       ref_t child[4];
       int axis0, axis00, axis01;
-      if(MB || CNT || exact)
+      if(MB && !CNT && !exact)
+      { // motion-blur nodes, ordinary ray
+        const Node256 *nd = reinterpret_cast<const Node256 *>(A.nodes) + cur;
+        node_slabs_fast_mb(nd, near_off, r.px, r.py, r.pz, ix, iy, iz, t0, t1, h.dist, key);
+        const ulonglong2 *ch = reinterpret_cast<const ulonglong2 *>(nd->child);
+        const ulonglong2 c01 = __ldg(ch), c23 = __ldg(ch + 1), pa = __ldg(ch + 2), aa = __ldg(ch + 3);
+        const uint64_t c64[4] = {c01.x, c01.y, c23.x, c23.y};
+#pragma unroll
+        for(int c=0;c<4;c++)
+        { // imported reference trees may carry empty leaves with ordinary boxes; this library's builder inverts them
+          if(A.imported && is_empty_leaf(c64[c])) key[c] = KEY_MISS;
+          child[c] = C32 ? (ref_t)((uint32_t)c64[c] | (uint32_t)(c64[c] >> 32)) : (ref_t)c64[c];
+        }
+        axis0 = (int)pa.y; axis00 = (int)aa.x; axis01 = (int)aa.y;
+      }
+      else if(MB || CNT || exact)
       {
         NodeOut o;
         if(exact) node_slabs<MB, true >(A.nodes, cur, r.px, r.py, r.pz, ix, iy, iz, t0, t1, h.dist, o);
@@ -445,7 +489,19 @@ k_visible(DevAccel A, const cb_ray_t *__restrict__ rays, const float *__restrict
     }
     else if(state == ST_NODE)
     {
-      if(MB || exact)
+      if(MB && !exact)
+      {
+        const Node256 *nd = reinterpret_cast<const Node256 *>(A.nodes) + cur;
+        float key[4];
+        node_slabs_fast_mb(nd, near_off, r.px, r.py, r.pz, ix, iy, iz, t0, t1, md, key);
+        const ulonglong2 *ch = reinterpret_cast<const ulonglong2 *>(nd->child);
+        const ulonglong2 c01 = __ldg(ch), c23 = __ldg(ch + 1);
+        const uint64_t c64[4] = {c01.x, c01.y, c23.x, c23.y};
+#pragma unroll
+        for(int c=0;c<4;c++) if(KEY_HIT(key[c]) && !(A.imported && is_empty_leaf(c64[c])))
+          stack[sp++] = C32 ? (ref_t)((uint32_t)c64[c] | (uint32_t)(c64[c] >> 32)) : (ref_t)c64[c];
+      }
+      else if(MB || exact)
       {
         NodeOut o;
         if(exact) node_slabs<MB, true >(A.nodes, cur, r.px, r.py, r.pz, ix, iy, iz, t0, t1, md, o);
