@@ -83,7 +83,7 @@ int main(int argc, char *argv[])
   }
   if(render_b200_finish(r, fb)) { free(fb); scene_b200_free(s); return 3; }
   const double dt = now() - t0;
-  if(!quiet && spp) printf("[main] rendered %lu frames in an average of %.4f s/frame\n", (unsigned long)spp, dt/spp);
+  if(!quiet && spp) printf("[main] rendered %lu frames in an average of %.6f s/frame\n", (unsigned long)spp, dt/spp);
   char filename[1400];
   snprintf(filename, sizeof(filename), "%s%s_fb00.pfm", scene_b200_basename(s), outname);
   const float gain = spp ? d->camera.iso/(100.0f*(float)spp) : 0.0f;    /* src/view.c:656 */
