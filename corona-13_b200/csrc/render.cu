@@ -953,7 +953,7 @@ cb200_render_t *cb200_render_create(cb200_accel_t *a, const cb_render_desc_t *de
   { // default: one wave per progression (W*H paths, view.c:636-638), at most 2^23 (covers a padded 4K frame, 3840 x 2176)
     r->batch = (uint64_t)desc->width*desc->height;
     if(r->batch > (1ull << 23)) r->batch = 1ull << 23;
-    if(r->batch < 65536) r->batch = 65536;
+    if(r->batch < (1ull << 21)) r->batch = 1ull << 21;   // small frames: room for several progressions per wave (--batch)
   }
   const uint64_t N = r->batch;
   D.fb = r->own_fb = dev_alloc<float>(r, (size_t)desc->width*desc->height*3);

@@ -12,7 +12,7 @@ nra2 = g.write_files(tmp)
 W, H, SPP = 1024, 576, int(sys.argv[1]) if len(sys.argv) > 1 else 128
 for sampler in ("pt", "ptdl"):
     t0 = time.time()
-    p = subprocess.run([os.path.join(ROOT, "corona-13_b200", "corona_b200"), nra2, "-s", str(SPP), "-w", str(W), "-h", str(H), "--frame", "1",
+    p = subprocess.run([os.path.join(ROOT, "corona-13_b200", "corona_b200"), nra2, "-s", str(SPP), "-w", str(W), "-h", str(H), "--frame", "1", "--batch", "16",
                         "--sampler", sampler, "--points", "rand", "--coeff", os.path.join(REF, "data", "ergb2spec.coeff"),
                         "--tables", os.path.join(ROOT, "tests", "golden", "ref_tables.cbt")], capture_output=True, text=True)
     gpu_wall = time.time() - t0
