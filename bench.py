@@ -180,7 +180,11 @@ def run_reference(args, rank, world):
         return
     cb = importlib.import_module("corona-13_b200")
     scene, ms, cam, lines, shape_mats = bench_scene(cb, args.tris)
-    ref = ReferenceRenderer(cb, scene, lines, shape_mats, cam)
+    try:
+        ref = ReferenceRenderer(cb, scene, lines, shape_mats, cam)
+    except RuntimeError as e:     # oracle/_ref was not built where this snapshot was taken
+        print(json.dumps({"impl": "reference", "unavailable": str(e)[:200]}))
+        return
     try:
         rpp = ref.rays_per_path()
         frames, build_s, _ = ref.run("corona_ptdl_rand", WIDTH, HEIGHT, args.warmup + args.steps)
