@@ -325,3 +325,54 @@ def test_empty_scene_renders_black(gpu):
     st = r.stats()
     assert st["paths"] == 64 * 32 == st["rays_closest"] and float(np.abs(r.framebuffer()).sum()) == 0.0
     r.close(), acc.close()
+
+
+# --------------------------------------------------------------------------------------------- full size (BASELINE configs[4])
+def test_full_size_render_properties(gpu):
+    """the bench workload itself (10 M triangles, 3840x2176, ptdl): size-independent properties --
+    (1) the wavefront issues the reference's amount of work: rays per path as counted by the reference's ACCEL_DEBUG build
+        on the same scene (2.889, profiles/README.md);
+    (2) path-index partition invariance at full size: progression 0 rendered whole == rendered as two "ranks"' halves, summed;
+    (3) streamed progressions + flush == complete progressions (same paths, same ray counts, same image);
+    (4) energy: every splat is finite and the image mean is the same for two disjoint index ranges within Monte Carlo noise."""
+    import ctypes as C
+    IO = cb.scene_io
+    z = np.load(os.path.join(GOLDEN, "bench_materials.npz"))
+    ms = IO.MaterialSet()
+    raw = z["materials"].tobytes()
+    ms.materials = list((IO.CMaterial * (len(raw) // C.sizeof(IO.CMaterial))).from_buffer_copy(raw))
+    sc = S.synthetic_scene(10_000_000, seed=1)
+    for sh, m in zip(sc.shapes, z["shape_mats"]):
+        sh.material = int(m)
+    acc = gpu.Accel(sc).build()
+    cam = IO.Camera(pos=(18.0, 14.0, 14.5), lookat=(0.0, 0.0, 2.5), aperture_value=6, exposure_value=13, focal_length=0.4, iso=100.0)
+    W, H = 3840, 2176
+    n = W * H
+    kw = dict(sampler=IO.SAMPLER_PTDL, pointsampler=IO.POINTS_RAND, frame=1)
+    whole = gpu.Render(acc, cam, ms, W, H, **kw)
+    whole.render_pass(0, n)
+    fb = whole.framebuffer()
+    st = whole.stats()
+    assert np.isfinite(fb).all() and fb.min() >= 0
+    rpp = (st["rays_closest"] + st["rays_shadow"]) / st["paths"]
+    assert abs(rpp - 2.889) < 0.03, rpp                                     # (1)
+    halves = gpu.Render(acc, cam, ms, W, H, batch_paths=1 << 21, **kw)
+    parts = np.zeros_like(fb)
+    for lo, hi in ((0, n // 2), (n // 2, n)):
+        halves.clear()
+        halves.render_pass(lo, hi - lo)
+        parts += halves.framebuffer()
+    assert np.allclose(parts, fb, rtol=1e-3, atol=1e-5 * fb.max())          # (2)
+    halves.clear()
+    for k in range(4):                                                      # (3): 4 streamed quarters through a small pool
+        halves.render_pass(k * (n // 4), n // 4, streaming=True)
+    fb3 = halves.framebuffer()
+    s3 = halves.stats()
+    assert (s3["paths"], s3["rays_closest"], s3["rays_shadow"]) == (st["paths"], st["rays_closest"], st["rays_shadow"])
+    assert np.allclose(fb3, fb, rtol=1e-3, atol=1e-5 * fb.max())
+    whole.clear()
+    whole.render_pass(n, n)                                                 # (4) the next progression: different paths
+    fb2 = whole.framebuffer()
+    m1, m2 = fb.astype(np.float64).mean(axis=(0, 1)), fb2.astype(np.float64).mean(axis=(0, 1))
+    assert np.all(np.abs(m2 / m1 - 1) < 0.02), (m1, m2)
+    whole.close(), halves.close(), acc.close()
