@@ -679,6 +679,9 @@ static int grid_for(uint64_t n, const void *kernel)
 #define STACK_SMALL 64
 #define STACK_BIG   304
 
+// CB200_FORCE_REF64=1 runs the 64-bit child-reference kernels that scenes with >= 2^26 primitives get (tests)
+static bool force_ref64() { static int v = -1; if(v < 0) { const char *e = getenv("CB200_FORCE_REF64"); v = (e && atoi(e)) ? 1 : 0; } return v == 1; }
+
 static int g_refill_threshold = -1;
 static int refill_threshold()
 {
@@ -712,7 +715,7 @@ static int launch_intersect_k(const cb200_accel *a, const cb_ray_t *d_rays, cons
                               uint64_t n, cudaStream_t stream, unsigned long long *d_counters, const uint32_t *d_order)
 {
   // 32-bit child references inside the kernel while begin<<5|count and node indices fit 31 bits
-  const bool c32 = !CNT && a->dev.num_prims < (1ull << 26) && a->dev.num_nodes < (1ull << 31);
+  const bool c32 = !CNT && a->dev.num_prims < (1ull << 26) && a->dev.num_nodes < (1ull << 31) && !force_ref64();
   if(c32) return launch_intersect_k2<MB, CNT, STACK, ANALYTIC, !CNT>(a, d_rays, d_max_dist, d_out, n, stream, d_counters, d_order);
   return launch_intersect_k2<MB, CNT, STACK, ANALYTIC, false>(a, d_rays, d_max_dist, d_out, n, stream, d_counters, d_order);
 }
@@ -746,7 +749,7 @@ static int launch_visible_k(const cb200_accel *a, const cb_ray_t *d_rays, const 
 {
   unsigned long long *ticket;
   if(get_ticket(stream, &ticket)) return CB200_ERR_CUDA;
-  const bool c32 = a->dev.num_prims < (1ull << 26) && a->dev.num_nodes < (1ull << 31);
+  const bool c32 = a->dev.num_prims < (1ull << 26) && a->dev.num_nodes < (1ull << 31) && !force_ref64();
 #define VIS_LAUNCH(SH, C) do { auto k = k_visible<MB, STACK, ANALYTIC, SH, C>; \
     k<<<grid_for(n, (const void *)k), TRACE_BLOCK, 0, stream>>>(a->dev, d_rays, d_max_dist, d_skip, d_out, n, ticket, prim_threshold(), refill_threshold()); } while(0)
   if(d_skip) { if(c32) VIS_LAUNCH(true, true); else VIS_LAUNCH(true, false); }

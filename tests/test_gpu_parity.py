@@ -345,3 +345,32 @@ def test_accel_closest_golden(gpu, name):
     assert same.mean() > 0.98, same.mean()
     acc.close()
     acc2.close()
+
+
+def test_64bit_reference_kernel_variants(gpu):
+    """scenes with >= 2^26 primitives run kernels with 64-bit child references and two-word stack entries; CB200_FORCE_REF64
+    selects them for a small scene so that they are held to the same bit-exact bar (fresh process: the switch is read once)"""
+    import subprocess
+    import sys
+    code = r'''
+import importlib, sys, numpy as np
+sys.path.insert(0, %r); sys.path.insert(0, %r)
+from helpers import S, R, assert_hits_equal
+from oracle.binding import Oracle
+lib = importlib.import_module("corona-13_b200.lib")
+lib.set_device(0)
+for motion in (False, True):
+    sc = S.synthetic_scene(30000, seed=31, motion=motion, quads=motion, analytic=motion)
+    acc = lib.Accel(sc).build()
+    nodes, primid = acc.export_qbvh()
+    orc = Oracle(sc).import_tree(nodes, acc.aabb(), primid)
+    rays = np.concatenate([S.camera_rays(40000, sc, seed=1, time_max=1.0), S.random_rays(40000, sc, seed=2, time_max=1.0)])
+    want = orc.intersect(rays)
+    assert_hits_equal(acc.intersect(rays), want, "64-bit variant closest")
+    sr, md = S.shadow_rays(rays, want, (0.0, 0.0, 9.0))
+    assert np.array_equal(acc.visible(sr, md), orc.visible(sr, md))
+print("ok")
+''' % (ROOT, os.path.join(ROOT, "tests"))
+    env = dict(os.environ, CB200_FORCE_REF64="1")
+    p = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, cwd=ROOT)
+    assert p.returncode == 0 and "ok" in p.stdout, p.stderr[-2000:]
