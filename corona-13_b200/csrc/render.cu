@@ -1,16 +1,19 @@
 // render.cu -- wavefront pt / ptdl integrator (C ABI in include/corona_b200_render.h).
 //
-// One pass = path indices [first, first+count), processed in waves of `batch_paths` paths:
+// One progression = path indices [first, first+count).  The pool holds up to `batch_paths` paths; every wave tops it up with
+// new paths behind the survivors of the previous wave (streaming: paths that outlive their progression ride along with the
+// next one, cb200_render_flush finishes them):
 //
-//   k_path_start     path_extend at length 0 (src/pathspace.c:205-250): lambda, time, thin-lens camera sample
-//                    (src/camera.d/thinlens.c:68-128) -> first ray
-//   loop per vertex:
-//     k_intersect    closest hit (traverse.cu) = accel_intersect in path_propagate (pathspace.c:763)
-//     k_shade        rest of path_propagate + path_extend bookkeeping + the sampler (pt.c:40-54 / ptdl.c:112-150):
+//   k_pixel_keys + radix sort + k_path_start
+//                    path_extend at length 0 (src/pathspace.c:205-250): lambda, time, thin-lens camera sample
+//                    (src/camera.d/thinlens.c:68-128) -> first ray; the wave's new indices are processed in pixel-Morton order
+//   k_intersect      closest hit (traverse.cu) = accel_intersect in path_propagate (pathspace.c:763)
+//   k_compact_hits   slots whose ray hit something -> one index list per BSDF kind (material-sorted shading)
+//   k_shade<kind>    rest of path_propagate + path_extend bookkeeping + the sampler (pt.c:40-54 / ptdl.c:112-150):
 //                    vertex preparation, emission splat with MIS, next-event sample (nee.h:87-243) -> shadow ray,
 //                    bsdf sample (shader.c:577-590) -> next ray, stream compaction of surviving paths
-//     k_intersect    shadow rays with hit->dist preset = path_visible (pathspace.c:311-344)
-//     k_nee_resolve  visibility decision + splat
+//   k_visible<SHADOW> shadow rays in path_visible's terms (pathspace.c:311-344), any-hit sweep (traverse.cu)
+//   k_nee_resolve    splat of the visible next-event contributions
 //
 // Splat: spectrum_p_to_camera + 4x4 Blackman-Harris footprint (view.c:455-495, blackmanharris.h:43-77) with
 // float atomics into the W*H*3 accumulation buffer (the reference uses CAS loops the same way).

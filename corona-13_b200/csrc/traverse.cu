@@ -9,15 +9,19 @@
 //   * popped entries whose entry distance exceeds the current hit distance are skipped, :1357-1386;
 //   * leaf primitives tested in primid[] order, "dist <= hit.dist" so the last tested wins ties.
 //
-// Mapping (round-1 ncu finding: plain one-ray-per-thread while-while ran at 4.8 of 32 lanes active):
-//   * persistent warps; every lane owns one ray at a time and is REFILLED from a global ticket
-//     counter the moment its ray terminates, so short rays do not leave lanes idle;
-//   * each lane is in one of two states, NODE (next: a 4-box node test) or PRIM (next: one primitive
-//     test of its current leaf); per warp iteration a vote picks which of the two code paths runs, so
-//     both execute with many lanes active.  Every ray still sees exactly the reference's own sequence
-//     of node and primitive tests;
-//   * rays whose origin/direction are finite and non-zero take a slab test built from FMNMX
-//     min/max (identical results up to the sign of zero); all others take the exact select form.
+// Mapping (each item follows an ncu finding, profiles/README.md; plain one-ray-per-thread while-while ran at 4.8 of 32 lanes):
+//   * persistent warps; every lane owns one ray at a time and idle lanes are REFILLED from a global ticket counter in
+//     batches (>= refill threshold idle lanes, or nothing else left to do), so short rays do not leave lanes idle and the
+//     fetch path (an atomic round trip + cold ray loads) does not run for one or two lanes on every iteration;
+//   * each lane is in one of two states, NODE (next: a 4-box node test) or PRIM (next: all primitives of its current
+//     leaf); per warp iteration a vote picks which of the two code paths runs, so both execute with many lanes active.
+//     Every ray still sees exactly the reference's own sequence of node and primitive tests;
+//   * static nodes + rays with finite non-zero direction: the near / far plane of each axis is selected when the row is
+//     loaded, so min(lo,hi) / max(lo,hi) disappear (identical tmin / tmax / hit mask); motion-blur nodes the same after the
+//     reference's time interpolation; all other rays take the exact SSE-select form;
+//   * the visiting order is three conditional swaps on (entry distance, child) pairs;
+//   * child references are 32 bits inside the kernel while the scene allows (< 2^26 primitives): one 8-byte stack word per
+//     entry; kernel variants by scene content (motion blur, analytic primitives, instrumentation).
 #include "prims.cuh"
 #include <atomic>
 #include <mutex>
