@@ -89,3 +89,38 @@ def test_cli_render_matches_reference_image(built, tmp_path, case, key):
     assert rel <= 0.45 * noise, f"{case}/{key}: relRMSE {rel:.4f} vs noise floor {noise:.4f}"
     assert np.all(np.abs(ratio - 1) < 0.01), ratio
     assert "rendered" in p.stdout and "s/frame" in p.stdout
+
+
+def test_c_camera_reader_matches_fixture_reader(built, tmp_path):
+    """host/scene_b200.c: scene_b200_read_camera (camera_t 104 B and legacy camera_v0_t 152 B, film back recomputed from the frame's
+    aspect like view_cam_read, src/view.c:933-952) against scene_io.read_cam / Camera.cstruct, field by field"""
+    IO = cb.scene_io
+    H = C.CDLL(os.path.join(ROOT, "corona-13_b200", "libcorona_host.so"))
+    H.scene_b200_read_camera.argtypes = [C.c_char_p, C.c_uint32, C.c_uint32, C.c_void_p]
+    import struct
+    cams = []
+    g = GoldenImage("motion")               # a 104-byte camera_t with a moving camera
+    p = str(tmp_path / "v1.cam")
+    open(p, "wb").write(g.z["cam"].tobytes())
+    cams.append(p)
+    c = IO.read_cam(p)                      # the same camera in the legacy layout (include/camera.h:77-99)
+    p = str(tmp_path / "v0.cam")
+    open(p, "wb").write(struct.pack("<i3f4ff7if4f3ff4ffffffiffi", 0, *c.pos, *c.orient, 1.0, *([0] * 7), c.iso, *c.orient_t1, *c.pos_t1,
+                                    0.0, 0.0, 0.0, 0.0, 0.0, c.focus, 0.0, 2.5, 0.0, 0.0, c.aperture_value, c.focal_length, 0.0, c.exposure_value))
+    cams.append(p)
+    ref_cam = os.path.join(ROOT, "oracle", "_ref", "scenes", "0010_pt", "test01.cam")
+    if os.path.exists(ref_cam):             # the reference's own legacy-format camera of 0010_pt
+        cams.append(ref_cam)
+    assert sorted(os.path.getsize(p) for p in cams)[:2] == [104, 152]
+    for p in cams:
+        for w, h in ((1024, 576), (576, 1024), (256, 256)):
+            got = IO.CCamera()
+            assert H.scene_b200_read_camera(p.encode(), w, h, C.byref(got)) == 0
+            want = IO.read_cam(p).cstruct(w, h)
+            for name, _ in IO.CCamera._fields_:
+                a, b = getattr(got, name), getattr(want, name)
+                a, b = (list(a), list(b)) if hasattr(a, "__len__") else (a, b)
+                assert a == b, (p, w, h, name, a, b)
+    bad = str(tmp_path / "bad.cam")
+    open(bad, "wb").write(b"x" * 77)
+    assert H.scene_b200_read_camera(bad.encode(), 64, 64, C.byref(IO.CCamera())) != 0
