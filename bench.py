@@ -325,41 +325,63 @@ def main():
     if rank == 0:
         image_mean = [float(x) for x in (fb_sum.mean(dim=(0, 1)) * (cam.iso / (100.0 * args.steps * world))).tolist()]
 
-    # ---- e2e: host-side render module (MOD_render=b200), host framebuffer after every progression
-    e2e = None
-    if world == 1:
-        r.set_framebuffer(0)
-        r.clear()
-        r.instrument(False, False)
-        host_fb = torch.empty(HEIGHT, WIDTH, 3).pin_memory()
-        e2e_steps = max(2, min(args.steps, 16))
+    # ---- e2e: host-side render module (MOD_render=b200), host framebuffer after every progression.  N > 1: every rank renders its
+    #      progressions, the per-progression reduce runs as in the device-timed loop, and rank 0 copies the summed image to the host
+    #      after every progression (what the reference's display / fb file sees)
+    r.clear()
+    red.clear()
+    r.instrument(False, False)
+    host_fb = torch.empty(HEIGHT, WIDTH, 3).pin_memory()
+    e2e_steps = max(2, min(args.steps, 16))
+    L = lib.load()
 
-        L = lib.load()
-
-        def e2e_step():          # == host/render_b200.c: render_b200_pass(r, first, count, fb)
+    def e2e_step(s):
+        if world == 1:           # == host/render_b200.c: render_b200_pass(r, first, count, fb)
             lib._check(L.cb200_render_pass_stream(r.r, next_first(), n_pass, None), "cb200_render_pass_stream")
             lib._check(L.cb200_render_snapshot(r.r, host_fb.data_ptr(), None), "cb200_render_snapshot")
+        else:
+            step(s)
+            if rank == 0:
+                host_fb.copy_(red.accum, non_blocking=True)
 
-        def e2e_finish():        # == render_b200_finish(r, fb)
+    def e2e_finish(s):           # == render_b200_finish(r, fb)
+        if world == 1:
             lib._check(L.cb200_render_flush(r.r, None), "cb200_render_flush")
             lib._check(L.cb200_render_download(r.r, host_fb.data_ptr(), None), "cb200_render_download")
-        e2e_step()
-        e2e_finish()
-        torch.cuda.synchronize()
-        s1 = r.stats()
-        t0 = time.perf_counter()
-        for _ in range(e2e_steps):
-            e2e_step()
-        e2e_finish()
-        torch.cuda.synchronize()
-        dt = time.perf_counter() - t0
-        s2 = r.stats()
-        rays = (s2["rays_closest"] + s2["rays_shadow"]) - (s1["rays_closest"] + s1["rays_shadow"])
-        e2e = {"value": rays / dt, "unit": "rays/s", "h2d_bytes_per_step": 16,
-               "d2h_bytes_per_step": HEIGHT * WIDTH * 3 * 4 * (e2e_steps + 1) // e2e_steps,
-               "steps": e2e_steps, "ms_per_step": dt / e2e_steps * 1e3, "spp_per_s": e2e_steps / dt,
-               "boundary": "render_b200_pass per progression: path-index range in, the progressive HOST framebuffer (W*H*3 f32, pinned) "
-                           "out after every progression; render_b200_finish (flush + finished image) once at the end, inside the timing"}
+        else:
+            r.set_framebuffer(red.acquire(s + 1).data_ptr())     # the last step's buffer is being reduced: stragglers go to the next one
+            lib._check(L.cb200_render_flush(r.r, None), "cb200_render_flush")
+            red.submit(s + 1)
+            total = red.finish()
+            if rank == 0:
+                host_fb.copy_(total)
+    if world == 1:
+        r.set_framebuffer(0)
+    e2e_step(0)
+    e2e_finish(0)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    s1 = r.stats()
+    t0 = time.perf_counter()
+    for s in range(e2e_steps):
+        e2e_step(s)
+    e2e_finish(e2e_steps - 1)
+    torch.cuda.synchronize()
+    dt_t = torch.tensor([time.perf_counter() - t0], device="cuda", dtype=torch.float64)
+    s2 = r.stats()
+    rays_t = torch.tensor([(s2["rays_closest"] + s2["rays_shadow"]) - (s1["rays_closest"] + s1["rays_shadow"])], device="cuda", dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(dt_t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(rays_t, op=dist.ReduceOp.SUM)
+    dt, rays = float(dt_t.item()), float(rays_t.item())
+    e2e = {"value": rays / dt, "unit": "rays/s", "h2d_bytes_per_step": 16,
+           "d2h_bytes_per_step": HEIGHT * WIDTH * 3 * 4 * (e2e_steps + 1) // e2e_steps,
+           "steps": e2e_steps, "ms_per_step": dt / e2e_steps * 1e3, "spp_per_s": e2e_steps * world / dt,
+           "boundary": "render_b200_pass per progression: path-index range in, the progressive HOST framebuffer (W*H*3 f32, pinned) "
+                       "out after every progression (N > 1: the reduced image on rank 0); render_b200_finish (flush + finished image) "
+                       "once at the end, inside the timing"}
+    if world == 1:
         e2e["accel_h"] = accel_boundary(cb, lib, acc, scene, torch)
     r.close()
 
@@ -393,8 +415,7 @@ def main():
                      "algorithmic_bytes_per_launch": bytes_per_ray * 8.3e6,
                      "bytes_per_ray": bytes_per_ray, "nodes_per_ray": n_node, "prims_per_ray": n_prim,
                      "rays": stt["rays_closest"], "kernel_ms": ms_closest},
-        "e2e": e2e if e2e is not None else {"value": None, "unit": "rays/s", "h2d_bytes_per_step": 16,
-                                            "d2h_bytes_per_step": HEIGHT * WIDTH * 3 * 4, "note": "measured at N=1"},
+        "e2e": e2e,
         "gpu_launches": int(launches_all),
         "image_mean_xyz": image_mean,
         "clocks": clocks,
