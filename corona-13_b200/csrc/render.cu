@@ -17,8 +17,8 @@
 //
 // Splat: spectrum_p_to_camera + 4x4 Blackman-Harris footprint (view.c:455-495, blackmanharris.h:43-77) with
 // float atomics into the W*H*3 accumulation buffer (the reference uses CAS loops the same way).
-// Scope: surfaces in vacuum / nested dielectrics, geometric lights, black sky.  Media and environment lighting
-// are SURVEY 8(f) rank 1/3.
+// Scope: surfaces in vacuum / nested dielectrics, geometric lights, the built-in `black' and `cloudy' skies.  Media and sky
+// modules (daylight, environment maps) are SURVEY 8(f) rank 1/3.
 #include "shading.cuh"
 #include <cub/cub.cuh>
 #include <vector>
@@ -75,6 +75,9 @@ struct RenderDev
   uint32_t fb_w, fb_h;
   int32_t sampler, colour, max_path_len;
   float box_lo[3], box_scale[3];   // scene box -> 7-bit cell per axis (ray coherence keys)
+  int32_t sky;                     // CB_SKY_*
+  float p_sky;                     // lights_pdf_type: probability of connecting to the sky (list.c:44-49,76-88)
+  float sky_far;                   // distance of the next-event point on the sky (shader.c:313-316)
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -340,6 +343,49 @@ __device__ __forceinline__ float cos_lambert(const Vtx &v, const Vtx &l, V3 d, f
   return fabsf(dot(v.n, d))*fabsf(dot(l.n, d))/(dist*dist);
 }
 
+// ---- the built-in `cloudy' sky (src/shader.c:268-334): L = 500 * (1 + omega_z)/2, sampled with pdf (1 + z)/2 / (2 pi) ----------
+__device__ __forceinline__ float sky_eval(V3 omega)   // sky_cloudy for v != 0 (shader.c:276-279)
+{
+  return (float)((double)(1.0f*500.0f*0.5f)*(1.0 + (double)omega.z));
+}
+__device__ __forceinline__ float sky_pdf(V3 omega)    // sky_cloudy_pdf, solid angle (shader.c:328-331)
+{
+  return (float)((double)(0.5f + omega.z*.5f)/(2.0*PI_D));
+}
+
+// A path whose ray left the scene under a non-black sky gets an environment vertex: emission with the sampler's weight, then
+// the path ends (path_propagate pathspace.c:856-873, path_extend / nee_sample refuse to continue :196 / nee.h:91).
+__global__ void __launch_bounds__(RB)
+k_sky_miss(RenderDev R, uint32_t n, const PathState *__restrict__ st, const cb_hitrec_t *__restrict__ hits, ShadeCounters *cnt)
+{
+  const uint32_t i = blockIdx.x*blockDim.x + threadIdx.x;
+  bool did = false;
+  if(i < n)
+  {
+    const uint2 p = *reinterpret_cast<const uint2 *>(hits + i);
+    if((p.x & p.y) == 0xffffffffu)
+    {
+      const PathState s = st[i];
+      const V3 omega = mk3(s.omega[0], s.omega[1], s.omega[2]);
+      const float em = sky_eval(omega);
+      if(em > 0.0f)
+      {
+        const float pdf_v = s.pdf_proj*s.cos_prev;      // path_G towards the environment = lambert at the previous vertex (pathspace.c:60-61)
+        float w = 1.0f;
+        if(R.sampler == CB_SAMPLER_PTDL)
+        {
+          float pdf_nee = 0.0f;
+          if(s.length + 1 >= 3 && (s.bits & 1u) && R.p_sky > 0.0f) pdf_nee = R.p_sky*sky_pdf(omega);   // nee_pdf_nee, nee.h:21-38
+          w = pdf_v/(pdf_nee + pdf_v);
+        }
+        did = splat(R, s.pixel_i, s.pixel_j, s.lambda, (s.thr*em)*w);   // lights_eval_vertex: isotropic for the envmap (list.c:272-273)
+      }
+    }
+  }
+  const uint32_t m = __ballot_sync(0xffffffffu, did);
+  if(m && (threadIdx.x & 31u) == 0) atomicAdd(&cnt->splats, (unsigned long long)__popc(m));
+}
+
 // Paths whose ray escaped into the (black) sky have nothing left to do (pathspace.c:856-873): the shading kernel only runs
 // on the slots that hit something.  Their indices are compacted first -- into one list per BSDF kind of the surface that was
 // hit (diffuse / dielectric / metal), so that every shading launch has full warps AND a single material class: the
@@ -462,10 +508,52 @@ k_shade(RenderDev R, uint32_t n, const PathState *__restrict__ st_in, const cb_r
           else
           {
             const int rb = rand_beg_v + rand_cnt_v; // rand_beg of the nee vertex (nee.h:107)
-            if((v.material_modes & (M_DIFFUSE | M_GLOSSY)) && R.lights.num > 0)
+            if((v.material_modes & (M_DIFFUSE | M_GLOSSY)) && (R.lights.num > 0 || R.p_sky > 0.0f))
             {
               const float r0 = point_dim(R.points, index, rb + 0);
-              if(r0 < R.lights.p_geo)
+              if(r0 < R.p_sky)
+              { // connect to the sky: sky_cloudy_sample (shader.c:281-326), then the common tail of nee_sample (nee.h:184-243)
+                const float x1 = point_dim(R.points, index, rb + 2), x2 = point_dim(R.points, index, rb + 3);
+                const float z = -(1.0f - 2.0f*sqrtf(1.0f - x1));
+                const float sin_theta = (float)sqrt(1.0 - (double)(z*z));
+                const float ang = (float)((double)2.f*PI_D*(double)x2);
+                const V3 d = mk3(sin_theta*cosf(ang), sin_theta*sinf(ang), z);
+                const float em = ((.5f + z*.5f)*1.0f)*500.0f;
+                const float pdf_sky = (float)((double)(.5f + z*.5f)/((double)2.0f*PI_D));
+                const float edf = (em/pdf_sky)/R.p_sky;
+                if(edf > 0.0f)
+                {
+                  Vtx vb = v;
+                  const float bsdf = bsdf_eval<KINDS>(R.mats, vb, omega, d, s.lambda, s.cur_ior);
+                  if(bsdf > 0.0f)
+                  {
+                    const V3 lx = mk3(v.x.x + R.sky_far*d.x, v.x.y + R.sky_far*d.y, v.x.z + R.sky_far*d.z);
+                    const float eps = 1e-4f*max3abs(v.x);                    // prims_get_ray towards a vertex without primitive
+                    V3 rd = sub(lx, v.x);
+                    const float ilen = 1.0f/sqrtf(dot(rd, rd));
+                    rd = mk3(rd.x*ilen, rd.y*ilen, rd.z*ilen);
+                    const V3 rp = mk3(v.x.x + eps*rd.x, v.x.y + eps*rd.y, v.x.z + eps*rd.z);
+                    const V3 dv = sub(lx, rp);
+                    const float total_dist = sqrtf(dot(dv, dv));
+                    const float Gl = fabsf(dot(vb.n, d));                    // path_G with an environment end point
+                    const float thr_l = ((thr*bsdf)*(1.0f*edf))*Gl;
+                    const float pdf_nee = pdf_sky*R.p_sky;
+                    const float pdf_ext = bsdf_pdf<KINDS>(R.mats, vb, omega, d)*Gl;
+                    const float w = pdf_nee/(pdf_ext + pdf_nee);
+                    if(thr_l > 0.0f && total_dist > 0.0f)
+                    {
+                      have_nee = true;
+                      for(int k=0;k<3;k++) { nray.pos[k] = (&rp.x)[k]; nray.dir[k] = (&rd.x)[k]; }
+                      nray.time = s.time; nray.min_dist = 0.0f;
+                      nray.ignore[0] = v.prim_lo; nray.ignore[1] = v.prim_hi;
+                      nmax = total_dist;
+                      nrec.value = thr_l*w; nrec.lambda = s.lambda; nrec.pixel_i = s.pixel_i; nrec.pixel_j = s.pixel_j;
+                      nrec.total_dist = total_dist; nrec.light_lo = nrec.light_hi = 0xffffffffu; nrec.pad = 0;
+                    }
+                  }
+                }
+              }
+              else if(r0 < R.p_sky + R.lights.p_geo)
               {
                 const float rl = point_dim(R.points, index, rb + 1), rx = point_dim(R.points, index, rb + 2), ry = point_dim(R.points, index, rb + 3);
                 const uint32_t t = sample_cdf_dev(R.lights.cdf, R.lights.num, rl);
@@ -862,7 +950,13 @@ static int build_lights(cb200_render *r)
   const uint32_t n = (uint32_t)lp.size();
   std::vector<float> area(n ? n : 1), cdf(n ? n : 1), shape_pdf(s->num_shapes ? s->num_shapes : 1, 0.0f);
   LightsDev &L = r->dev.lights;
-  L.num = n; L.p_geo = n ? 1.0f : 0.0f;
+  L.num = n;
+  { // lights_prepare_frame (list.c:76-88)
+    float p_sky = r->desc.sky != CB_SKY_BLACK ? 1.0f : 0.0f, p_geo = n ? 1.0f : 0.0f;
+    const float p_sum = p_sky + p_geo;
+    if(p_sum > 0.0f) { p_sky /= p_sum; p_geo /= p_sum; }
+    L.p_geo = p_geo; r->dev.p_sky = p_sky;
+  }
   L.primid = dev_upload(r, lp.data(), lp.size());
   if(n)
   {
@@ -912,6 +1006,7 @@ cb200_render_t *cb200_render_create(cb200_accel_t *a, const cb_render_desc_t *de
     for(int k=0;k<m.num_ops;k++) if(m.ops[k].op == CB_OP_CHECKERSG && (m.ops[k].table < 0 || m.ops[k].table >= desc->num_tables))
     { cb200_set_error("render_create: colour checker without table"); return nullptr; }
   }
+  if(desc->sky != CB_SKY_BLACK && desc->sky != CB_SKY_CLOUDY) { cb200_set_error("render_create: unsupported sky (no CPU fallback)"); return nullptr; }
   cb200_render *r = new cb200_render();
   r->accel = a;
   r->desc = *desc;
@@ -925,6 +1020,8 @@ cb200_render_t *cb200_render_create(cb200_accel_t *a, const cb_render_desc_t *de
   D.accel = a->dev;
   D.geo.vtx = s->d_vtx; D.geo.vtxidx = s->d_vtxidx; D.geo.shapes = s->d_shapes;
   D.sampler = desc->sampler; D.colour = desc->colour_camera;
+  D.sky = desc->sky;
+  D.sky_far = (a->aabb[3] + a->aabb[4] + a->aabb[5]) - a->aabb[0] - a->aabb[1] - a->aabb[2];
   D.max_path_len = desc->max_path_len > 0 && desc->max_path_len <= 32 ? desc->max_path_len : 32;
   D.fb_w = desc->width; D.fb_h = desc->height;
   D.cam.c = desc->camera; D.cam.width = (float)desc->width; D.cam.height = (float)desc->height;
@@ -1085,6 +1182,11 @@ static int render_wave(cb200_render *r, uint32_t n, cudaStream_t st)
   CB_CUDA(cudaMemsetAsync(r->d_cnt, 0, 5*sizeof(unsigned long long), st));   // next, nee, hits[3] (splats keeps counting)
   {
     TimeScope ts(r, st, KC_SHADE, n);
+    if(r->dev.sky != CB_SKY_BLACK)
+    {
+      k_sky_miss<<<(n + RB - 1)/RB, RB, 0, st>>>(r->dev, n, r->st[cur], r->hits, r->d_cnt);
+      cb200_count_launch(); r->stats.kernel_launches++;
+    }
     const int single = (r->bsdf_kinds == 1) ? 0 : (r->bsdf_kinds == 2) ? 1 : (r->bsdf_kinds == 4) ? 2 : -1;
     k_compact_hits<<<(n + 255)/256, 256, 0, st>>>(r->dev, r->hits, n, (uint32_t)r->batch, r->hit_list, r->d_cnt, single);
     cb200_count_launch(); r->stats.kernel_launches++;

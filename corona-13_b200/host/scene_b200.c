@@ -299,6 +299,7 @@ struct scene_b200_t
   rgb2spec_b200_t *rgb2spec;
   table_file_t tables;
   char basename[1024], searchpath[1024];
+  int sky;
 };
 
 static void chomp_comment(char *s)
@@ -350,9 +351,11 @@ struct scene_b200_t *scene_b200_open(const char *nra2_file, const char *coeff_fi
   chomp_comment(line);
   char sky[64] = "";
   sscanf(line, " %63s", sky);
-  if(strcmp(sky, "black"))
-  { /* environment lighting is SURVEY 8f rank 3 */
-    fprintf(stderr, "[scene b200] sky `%s' is not supported by the gpu path (only `black'); no cpu fallback\n", sky);
+  if(!strncmp(sky, "black", 5)) s->sky = CB_SKY_BLACK;          /* src/shader.c:633-641: prefix matches, like there */
+  else if(!strncmp(sky, "cloudy_sky", 10) || !strncmp(sky, "cloudy", 6) || !strncmp(sky, "clear_sky", 9)) s->sky = CB_SKY_CLOUDY;
+  else
+  { /* sky modules (envmaps, daylight) are SURVEY 8f rank 3 */
+    fprintf(stderr, "[scene b200] sky `%s' is not supported by the gpu path (only `black' and `cloudy'); no cpu fallback\n", sky);
     fclose(f); scene_b200_free(s); return 0;
   }
   if(!fgets(line, sizeof(line), f) || sscanf(line, "%d", &s->nra2->num_shaders) != 1 || s->nra2->num_shaders < 0 || s->nra2->num_shaders > MAX_SHADERS)
@@ -425,6 +428,7 @@ int scene_b200_prepare(struct scene_b200_t *s, uint32_t width, uint32_t height, 
   d->materials = s->materials; d->num_materials = s->nra2->num_shaders;
   d->tables = s->nra2->used; d->num_tables = s->nra2->num_used;
   d->sampler = sampler; d->pointsampler = pointsampler; d->colour_camera = colour;
+  d->sky = s->sky;
   d->max_path_len = 32; d->frame = frame; d->rank = 0; d->world = 1; d->batch_paths = 0;
   s->render = render_b200_init(s->accel, d);
   return s->render ? 0 : 1;

@@ -24,6 +24,8 @@ BSDF_DIFFUSE, BSDF_DIELECTRIC, BSDF_METAL = 0, 1, 2
 SAMPLER_PT, SAMPLER_PTDL = 0, 1
 POINTS_RAND, POINTS_HALTON = 0, 1
 COLOUR_XYZ, COLOUR_REC709 = 0, 1
+SKY_BLACK, SKY_CLOUDY = 0, 1
+SKIES = {"black": SKY_BLACK, "cloudy": SKY_CLOUDY, "cloudy_sky": SKY_CLOUDY, "clear_sky": SKY_CLOUDY}   # src/shader.c:626-641
 
 
 class CCamera(C.Structure):
@@ -52,7 +54,8 @@ class CRenderDesc(C.Structure):
                 ("materials", C.c_void_p), ("num_materials", C.c_int32),
                 ("tables", C.c_void_p), ("num_tables", C.c_int32),
                 ("sampler", C.c_int32), ("pointsampler", C.c_int32), ("colour_camera", C.c_int32), ("max_path_len", C.c_int32),
-                ("frame", C.c_uint64), ("rank", C.c_uint32), ("world", C.c_uint32), ("batch_paths", C.c_uint64)]
+                ("frame", C.c_uint64), ("rank", C.c_uint32), ("world", C.c_uint32), ("batch_paths", C.c_uint64),
+                ("sky", C.c_int32), ("pad", C.c_int32)]
 
 
 class CRenderStats(C.Structure):

@@ -43,7 +43,7 @@ def load_tables():
     return z["checker"], {k[6:]: z[k] for k in z.files if k.startswith("metal_")}
 
 
-def golden_case(name, scene, shader_lines, shape_mats, cam, w, h, spp, variants):
+def golden_case(name, scene, shader_lines, shape_mats, cam, w, h, spp, variants, sky="black"):
     tmp = tempfile.mkdtemp(prefix="corona_golden_")
     try:
         shapes = []
@@ -51,7 +51,7 @@ def golden_case(name, scene, shader_lines, shape_mats, cam, w, h, spp, variants)
             sh.write_geo(os.path.join(tmp, f"shape{i}.geo"))
             shapes.append((shape_mats[i], f"shape{i}"))
         nra2 = os.path.join(tmp, "test.nra2")
-        IO.write_nra2(nra2, shader_lines, shapes)
+        IO.write_nra2(nra2, shader_lines, shapes, sky=sky)
         cam.write(os.path.join(tmp, "test01.cam"))
         out = {}
         for key in variants:
@@ -66,7 +66,7 @@ def golden_case(name, scene, shader_lines, shape_mats, cam, w, h, spp, variants)
                 "num_shapes": np.int64(len(scene.shapes)), "shape_mats": np.int64(shape_mats), "w": np.int64(w), "h": np.int64(h),
                 "spp": np.int64(spp), "shader_lines": np.array(shader_lines), "variants": np.array(list(variants)),
                 "cam": np.frombuffer(open(os.path.join(tmp, "test01.cam"), "rb").read(), np.uint8),
-                "num_tables": np.int64(len(ms.tables))}
+                "num_tables": np.int64(len(ms.tables)), "sky": np.array(sky)}
         for i, (lmin, step, data) in enumerate(ms.tables):
             pack[f"tab{i}_meta"] = np.float32([lmin, step])
             pack[f"tab{i}_data"] = data
@@ -173,7 +173,26 @@ def case_glass_metal():
                 [2, 8, 8, 11, 14, 17, 5], cam, 192, 128, 128, ["pt_halton", "ptdl_halton", "ptdl_rand"])
 
 
-CASES = {"diffuse_static": case_diffuse_static, "c10": case_c10, "motion": case_motion, "glass_metal": case_glass_metal}
+def case_sky(with_light):
+    """the built-in `cloudy' sky (src/shader.c:268-334): environment vertices, sky next-event estimation and its MIS; with and
+    without a geometric light beside it (lights_pdf_type splits the next-event budget 50:50 then, list.c:76-88)"""
+    terrain = S.terrain(1800, 5, material=0)
+    soup = S.soup(800, 6, rmin=0.2, rmax=0.9, material=0)
+    ball = S.analytic_shape("sphere", (1.5, -1.0, 4.0), 1.3, material=0)
+    rod = S.analytic_shape("line", (-3.0, 2.0, 2.0), 0.7, (-3.0, 2.0, 5.5), 0.7, material=0)
+    shapes, mats = [terrain, soup, ball, rod], [2, 7, 10, 13]
+    if with_light:
+        shapes.append(S.quad_light((0.0, 0.0, 9.0), 1.5, 1))
+        mats.append(5)
+    lines = ["diffuse", "color d 0.5 0.55 0.4", "mult 1 1 0", "color d 0 0 0", "color e 2500 2300 2000 1.", "mult 2 3 4 0",
+             "color d 0.75 0.3 0.2", "mult 1 6 0", "dielectric 1.5 40", "color g 1 1 1 0.0", "mult 1 9 8",
+             "metal Cu", "color g 1 1 1 0.25", "mult 1 12 11"]
+    cam = IO.Camera(pos=(13.0, 10.0, 8.0), lookat=(0.0, 0.0, 3.0), aperture_value=7, exposure_value=14, focal_length=0.35, iso=100.0)
+    golden_case("sky_light" if with_light else "sky", S.Scene(shapes, "sky"), lines, mats, cam, 160, 96, 128,
+                ["ptdl_halton", "pt_halton", "ptdl_rand"], sky="cloudy")
+
+
+CASES = {"sky": lambda: case_sky(False), "sky_light": lambda: case_sky(True), "diffuse_static": case_diffuse_static, "c10": case_c10, "motion": case_motion, "glass_metal": case_glass_metal}
 
 if __name__ == "__main__":
     subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "oracle"), "ref"])

@@ -169,6 +169,7 @@ class GoldenImage:
         for i in range(int(z["num_tables"])):
             lmin, step = z[f"tab{i}_meta"]
             self.materials.add_table(lmin, step, z[f"tab{i}_data"])
+        self.sky = str(z["sky"]) if "sky" in z.files else "black"
 
     def ref(self, key, seed):
         return self.z[f"{key}_seed{seed}"]
@@ -181,7 +182,7 @@ class GoldenImage:
             sh.write_geo(os.path.join(directory, f"shape{i}.geo"))
             shapes.append((int(self.z["shape_mats"][i]), f"shape{i}"))
         nra2 = os.path.join(directory, "test.nra2")
-        IO.write_nra2(nra2, [str(x) for x in self.z["shader_lines"]], shapes)
+        IO.write_nra2(nra2, [str(x) for x in self.z["shader_lines"]], shapes, sky=self.sky)
         open(os.path.join(directory, "test01.cam"), "wb").write(self.z["cam"].tobytes())
         return nra2
 
@@ -196,7 +197,7 @@ class GoldenImage:
 
     def render(self, lib, acc, key, frame=1, spp=None, **kw):
         """the GPU image of one variant at the golden's resolution and sample count"""
-        r = lib.Render(acc, self.camera, self.materials, self.w, self.h, frame=frame, **self.variant_args(key), **kw)
+        r = lib.Render(acc, self.camera, self.materials, self.w, self.h, frame=frame, sky=cb.scene_io.SKIES[self.sky], **self.variant_args(key), **kw)
         for _ in range(spp or self.spp):
             r.render_pass()
         img, st = r.image(), r.stats()
