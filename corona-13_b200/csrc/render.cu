@@ -76,6 +76,7 @@ struct RenderDev
   int32_t sampler, colour, max_path_len;
   float box_lo[3], box_scale[3];   // scene box -> 7-bit cell per axis (ray coherence keys)
   int32_t sky;                     // CB_SKY_*
+  float sky_coeff[3], sky_scale;   // CB_SKY_CONST
   float p_sky;                     // lights_pdf_type: probability of connecting to the sky (list.c:44-49,76-88)
   float sky_far;                   // distance of the next-event point on the sky (shader.c:313-316)
 };
@@ -343,14 +344,37 @@ __device__ __forceinline__ float cos_lambert(const Vtx &v, const Vtx &l, V3 d, f
   return fabsf(dot(v.n, d))*fabsf(dot(l.n, d))/(dist*dist);
 }
 
-// ---- the built-in `cloudy' sky (src/shader.c:268-334): L = 500 * (1 + omega_z)/2, sampled with pdf (1 + z)/2 / (2 pi) ----------
-__device__ __forceinline__ float sky_eval(V3 omega)   // sky_cloudy for v != 0 (shader.c:276-279)
+// ---- skies: the built-in `cloudy' (src/shader.c:268-334: L = 500 (1 + omega_z)/2, sampled with pdf (1 + z)/2 / (2 pi)) and the
+//      constant-colour module (src/shaders/sky_const.c: L = scale * rgb2spec(lambda), uniform sphere) -----------------------------
+__device__ __forceinline__ float sky_eval(const RenderDev &R, V3 omega, float lambda)
 {
-  return (float)((double)(1.0f*500.0f*0.5f)*(1.0 + (double)omega.z));
+  if(R.sky == CB_SKY_CONST) return rgb2spec_eval(R.sky_coeff, lambda)*R.sky_scale;                      // sky_const.c:41-45
+  return (float)((double)(1.0f*500.0f*0.5f)*(1.0 + (double)omega.z));                                    // sky_cloudy, v != 0 (shader.c:276-279)
 }
-__device__ __forceinline__ float sky_pdf(V3 omega)    // sky_cloudy_pdf, solid angle (shader.c:328-331)
+__device__ __forceinline__ float sky_pdf(const RenderDev &R, V3 omega)    // solid angle
 {
-  return (float)((double)(0.5f + omega.z*.5f)/(2.0*PI_D));
+  if(R.sky == CB_SKY_CONST) return (float)(1.0/((double)4.0f*PI_D));                                     // sky_const.c:84-87
+  return (float)((double)(0.5f + omega.z*.5f)/(2.0*PI_D));                                               // shader.c:328-331
+}
+// next-event sample: direction, emission / pdf, pdf
+__device__ __forceinline__ V3 sky_sample(const RenderDev &R, float x1, float x2, float lambda, float &edf, float &pdf)
+{
+  if(R.sky == CB_SKY_CONST)
+  { // sample_sphere (sampler_common.h:136-143)
+    const float z = 1.f - 2.f*x1;
+    const float r = sqrtf(1.f - z*z);
+    const float phi = (float)((double)2.f*PI_D*(double)x2);
+    pdf = (float)((double)1.0f/((double)4.0f*PI_D));
+    edf = (rgb2spec_eval(R.sky_coeff, lambda)*R.sky_scale)/pdf;
+    return mk3(r*cosf(phi), r*sinf(phi), z);
+  }
+  const float z = -(1.0f - 2.0f*sqrtf(1.0f - x1));                                                        // shader.c:297-305
+  const float sin_theta = (float)sqrt(1.0 - (double)(z*z));
+  const float ang = (float)((double)2.f*PI_D*(double)x2);
+  const float em = ((.5f + z*.5f)*1.0f)*500.0f;
+  pdf = (float)((double)(.5f + z*.5f)/((double)2.0f*PI_D));
+  edf = em/pdf;
+  return mk3(sin_theta*cosf(ang), sin_theta*sinf(ang), z);
 }
 
 // A path whose ray left the scene under a non-black sky gets an environment vertex: emission with the sampler's weight, then
@@ -367,7 +391,7 @@ k_sky_miss(RenderDev R, uint32_t n, const PathState *__restrict__ st, const cb_h
     {
       const PathState s = st[i];
       const V3 omega = mk3(s.omega[0], s.omega[1], s.omega[2]);
-      const float em = sky_eval(omega);
+      const float em = sky_eval(R, omega, s.lambda);
       if(em > 0.0f)
       {
         const float pdf_v = s.pdf_proj*s.cos_prev;      // path_G towards the environment = lambert at the previous vertex (pathspace.c:60-61)
@@ -375,7 +399,7 @@ k_sky_miss(RenderDev R, uint32_t n, const PathState *__restrict__ st, const cb_h
         if(R.sampler == CB_SAMPLER_PTDL)
         {
           float pdf_nee = 0.0f;
-          if(s.length + 1 >= 3 && (s.bits & 1u) && R.p_sky > 0.0f) pdf_nee = R.p_sky*sky_pdf(omega);   // nee_pdf_nee, nee.h:21-38
+          if(s.length + 1 >= 3 && (s.bits & 1u) && R.p_sky > 0.0f) pdf_nee = R.p_sky*sky_pdf(R, omega);   // nee_pdf_nee, nee.h:21-38
           w = pdf_v/(pdf_nee + pdf_v);
         }
         did = splat(R, s.pixel_i, s.pixel_j, s.lambda, (s.thr*em)*w);   // lights_eval_vertex: isotropic for the envmap (list.c:272-273)
@@ -514,13 +538,9 @@ k_shade(RenderDev R, uint32_t n, const PathState *__restrict__ st_in, const cb_r
               if(r0 < R.p_sky)
               { // connect to the sky: sky_cloudy_sample (shader.c:281-326), then the common tail of nee_sample (nee.h:184-243)
                 const float x1 = point_dim(R.points, index, rb + 2), x2 = point_dim(R.points, index, rb + 3);
-                const float z = -(1.0f - 2.0f*sqrtf(1.0f - x1));
-                const float sin_theta = (float)sqrt(1.0 - (double)(z*z));
-                const float ang = (float)((double)2.f*PI_D*(double)x2);
-                const V3 d = mk3(sin_theta*cosf(ang), sin_theta*sinf(ang), z);
-                const float em = ((.5f + z*.5f)*1.0f)*500.0f;
-                const float pdf_sky = (float)((double)(.5f + z*.5f)/((double)2.0f*PI_D));
-                const float edf = (em/pdf_sky)/R.p_sky;
+                float edf, pdf_sky;
+                const V3 d = sky_sample(R, x1, x2, s.lambda, edf, pdf_sky);
+                edf = edf/R.p_sky;
                 if(edf > 0.0f)
                 {
                   Vtx vb = v;
@@ -1006,7 +1026,7 @@ cb200_render_t *cb200_render_create(cb200_accel_t *a, const cb_render_desc_t *de
     for(int k=0;k<m.num_ops;k++) if(m.ops[k].op == CB_OP_CHECKERSG && (m.ops[k].table < 0 || m.ops[k].table >= desc->num_tables))
     { cb200_set_error("render_create: colour checker without table"); return nullptr; }
   }
-  if(desc->sky != CB_SKY_BLACK && desc->sky != CB_SKY_CLOUDY) { cb200_set_error("render_create: unsupported sky (no CPU fallback)"); return nullptr; }
+  if(desc->sky != CB_SKY_BLACK && desc->sky != CB_SKY_CLOUDY && desc->sky != CB_SKY_CONST) { cb200_set_error("render_create: unsupported sky (no CPU fallback)"); return nullptr; }
   cb200_render *r = new cb200_render();
   r->accel = a;
   r->desc = *desc;
@@ -1021,6 +1041,8 @@ cb200_render_t *cb200_render_create(cb200_accel_t *a, const cb_render_desc_t *de
   D.geo.vtx = s->d_vtx; D.geo.vtxidx = s->d_vtxidx; D.geo.shapes = s->d_shapes;
   D.sampler = desc->sampler; D.colour = desc->colour_camera;
   D.sky = desc->sky;
+  for(int k=0;k<3;k++) D.sky_coeff[k] = desc->sky_coeff[k];
+  D.sky_scale = desc->sky_scale;
   D.sky_far = (a->aabb[3] + a->aabb[4] + a->aabb[5]) - a->aabb[0] - a->aabb[1] - a->aabb[2];
   D.max_path_len = desc->max_path_len > 0 && desc->max_path_len <= 32 ? desc->max_path_len : 32;
   D.fb_w = desc->width; D.fb_h = desc->height;

@@ -300,6 +300,7 @@ struct scene_b200_t
   table_file_t tables;
   char basename[1024], searchpath[1024];
   int sky;
+  float sky_coeff[3], sky_scale;
 };
 
 static void chomp_comment(char *s)
@@ -353,9 +354,16 @@ struct scene_b200_t *scene_b200_open(const char *nra2_file, const char *coeff_fi
   sscanf(line, " %63s", sky);
   if(!strncmp(sky, "black", 5)) s->sky = CB_SKY_BLACK;          /* src/shader.c:633-641: prefix matches, like there */
   else if(!strncmp(sky, "cloudy_sky", 10) || !strncmp(sky, "cloudy", 6) || !strncmp(sky, "clear_sky", 9)) s->sky = CB_SKY_CLOUDY;
+  else if(!strcmp(sky, "sky_const"))
+  { /* src/shaders/sky_const.c:89-101: "r g b [scale]" */
+    float col[3] = {1.0f, 1.0f, 1.0f}, scale = 1.0f;
+    sscanf(strstr(line, "sky_const") + 9, "%f %f %f %f", col, col+1, col+2, &scale);
+    s->sky = CB_SKY_CONST;
+    s->sky_scale = scale*rgb_to_coeff(s->rgb2spec, col, s->sky_coeff);
+  }
   else
   { /* sky modules (envmaps, daylight) are SURVEY 8f rank 3 */
-    fprintf(stderr, "[scene b200] sky `%s' is not supported by the gpu path (only `black' and `cloudy'); no cpu fallback\n", sky);
+    fprintf(stderr, "[scene b200] sky `%s' is not supported by the gpu path (only `black', `cloudy' and `sky_const'); no cpu fallback\n", sky);
     fclose(f); scene_b200_free(s); return 0;
   }
   if(!fgets(line, sizeof(line), f) || sscanf(line, "%d", &s->nra2->num_shaders) != 1 || s->nra2->num_shaders < 0 || s->nra2->num_shaders > MAX_SHADERS)
@@ -429,6 +437,8 @@ int scene_b200_prepare(struct scene_b200_t *s, uint32_t width, uint32_t height, 
   d->tables = s->nra2->used; d->num_tables = s->nra2->num_used;
   d->sampler = sampler; d->pointsampler = pointsampler; d->colour_camera = colour;
   d->sky = s->sky;
+  for(int k=0;k<3;k++) d->sky_coeff[k] = s->sky_coeff[k];
+  d->sky_scale = s->sky_scale;
   d->max_path_len = 32; d->frame = frame; d->rank = 0; d->world = 1; d->batch_paths = 0;
   s->render = render_b200_init(s->accel, d);
   return s->render ? 0 : 1;

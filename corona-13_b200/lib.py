@@ -260,7 +260,7 @@ class Render:
     """wavefront pt/ptdl integrator on top of an Accel (include/corona_b200_render.h)"""
 
     def __init__(self, accel, camera, materials, width, height, sampler=1, pointsampler=0, colour=0, max_path_len=32,
-                 frame=0, rank=0, world=1, batch_paths=0, sky=0):
+                 frame=0, rank=0, world=1, batch_paths=0, sky=0, sky_coeff=(0.0, 0.0, 0.0), sky_scale=1.0):
         from . import scene_io as sio
         self.L = _load_render()
         self.accel = accel
@@ -278,6 +278,8 @@ class Render:
         d.sampler, d.pointsampler, d.colour_camera, d.max_path_len = sampler, pointsampler, colour, max_path_len
         d.frame, d.rank, d.world, d.batch_paths = frame, rank, world, batch_paths
         d.sky = sky
+        d.sky_coeff[:] = [float(x) for x in sky_coeff]
+        d.sky_scale = float(sky_scale)
         self.desc = d
         self.r = _nonnull(self.L.cb200_render_create(accel.a, C.byref(d)), "cb200_render_create")
         self.spp = 0

@@ -24,8 +24,8 @@ BSDF_DIFFUSE, BSDF_DIELECTRIC, BSDF_METAL = 0, 1, 2
 SAMPLER_PT, SAMPLER_PTDL = 0, 1
 POINTS_RAND, POINTS_HALTON = 0, 1
 COLOUR_XYZ, COLOUR_REC709 = 0, 1
-SKY_BLACK, SKY_CLOUDY = 0, 1
-SKIES = {"black": SKY_BLACK, "cloudy": SKY_CLOUDY, "cloudy_sky": SKY_CLOUDY, "clear_sky": SKY_CLOUDY}   # src/shader.c:626-641
+SKY_BLACK, SKY_CLOUDY, SKY_CONST = 0, 1, 2
+SKIES = {"sky_const": SKY_CONST, "black": SKY_BLACK, "cloudy": SKY_CLOUDY, "cloudy_sky": SKY_CLOUDY, "clear_sky": SKY_CLOUDY}   # src/shader.c:626-641
 
 
 class CCamera(C.Structure):
@@ -55,7 +55,7 @@ class CRenderDesc(C.Structure):
                 ("tables", C.c_void_p), ("num_tables", C.c_int32),
                 ("sampler", C.c_int32), ("pointsampler", C.c_int32), ("colour_camera", C.c_int32), ("max_path_len", C.c_int32),
                 ("frame", C.c_uint64), ("rank", C.c_uint32), ("world", C.c_uint32), ("batch_paths", C.c_uint64),
-                ("sky", C.c_int32), ("pad", C.c_int32)]
+                ("sky", C.c_int32), ("sky_coeff", C.c_float * 3), ("sky_scale", C.c_float), ("pad", C.c_int32)]
 
 
 class CRenderStats(C.Structure):
@@ -338,6 +338,15 @@ def parse_nra2(path, rgb2spec, checker_table=None, metal_tables=None):
         r = lines[3 + n + i].split()
         shapes.append((int(r[0]), r[1]))
     return ms, shapes, sky
+
+
+def sky_const_params(rgb2spec, args):
+    """sky_const's init (src/shaders/sky_const.c:89-101): 'r g b [scale]' -> (coeff[3], scale*mul)"""
+    f = [float(x) for x in args.split()[:4]]
+    col = (f + [1.0, 1.0, 1.0])[:3] if len(f) < 3 else f[:3]
+    scale = f[3] if len(f) > 3 else 1.0
+    mul, co = rgb2spec.rgb_to_coeff(col)
+    return [float(x) for x in co], float(np.float32(scale) * np.float32(mul))
 
 
 def write_nra2(path, shader_lines, shapes, sky="black"):

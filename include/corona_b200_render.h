@@ -87,7 +87,8 @@ cb_material_t;
 enum { CB_SAMPLER_PT = 0, CB_SAMPLER_PTDL = 1 };          /* src/sampler.d/pt.c, ptdl.c */
 enum { CB_POINTS_RAND = 0, CB_POINTS_HALTON = 1 };        /* src/pointsampler.d/rand.c, halton.c */
 enum { CB_COLOUR_XYZ = 0, CB_COLOUR_REC709 = 1 };         /* COL_camera (Makefile:122-136) */
-enum { CB_SKY_BLACK = 0, CB_SKY_CLOUDY = 1 };             /* line 1 of the .nra2: built-in skies of src/shader.c:262-334,633-660 */
+enum { CB_SKY_BLACK = 0, CB_SKY_CLOUDY = 1,               /* line 1 of the .nra2: built-in skies of src/shader.c:262-334,633-660 */
+       CB_SKY_CONST = 2 };                                /* `sky_const r g b [scale]`: src/shaders/sky_const.c */
 
 typedef struct cb_render_desc_t
 {
@@ -105,6 +106,8 @@ typedef struct cb_render_desc_t
   uint32_t rank, world;          /* sample-space split: decorrelates the counter RNG streams across GPUs */
   uint64_t batch_paths;          /* paths in flight per wave (0 = default) */
   int32_t sky;                   /* CB_SKY_* */
+  float sky_coeff[3];            /* CB_SKY_CONST: rgb2spec coefficients of the colour and scale * mul (sky_const.c:89-101) */
+  float sky_scale;
   int32_t pad;
 }
 cb_render_desc_t;

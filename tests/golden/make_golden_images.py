@@ -67,6 +67,9 @@ def golden_case(name, scene, shader_lines, shape_mats, cam, w, h, spp, variants,
                 "spp": np.int64(spp), "shader_lines": np.array(shader_lines), "variants": np.array(list(variants)),
                 "cam": np.frombuffer(open(os.path.join(tmp, "test01.cam"), "rb").read(), np.uint8),
                 "num_tables": np.int64(len(ms.tables)), "sky": np.array(sky)}
+        if sky.startswith("sky_const"):
+            co, sc = IO.sky_const_params(IO.Rgb2Spec(IO.coeff_path(ROOT)), sky[len("sky_const"):])
+            pack["sky_coeff"], pack["sky_scale"] = np.float32(co), np.float32(sc)
         for i, (lmin, step, data) in enumerate(ms.tables):
             pack[f"tab{i}_meta"] = np.float32([lmin, step])
             pack[f"tab{i}_data"] = data
@@ -173,7 +176,7 @@ def case_glass_metal():
                 [2, 8, 8, 11, 14, 17, 5], cam, 192, 128, 128, ["pt_halton", "ptdl_halton", "ptdl_rand"])
 
 
-def case_sky(with_light):
+def case_sky(with_light, sky="cloudy", name=None):
     """the built-in `cloudy' sky (src/shader.c:268-334): environment vertices, sky next-event estimation and its MIS; with and
     without a geometric light beside it (lights_pdf_type splits the next-event budget 50:50 then, list.c:76-88)"""
     terrain = S.terrain(1800, 5, material=0)
@@ -188,11 +191,11 @@ def case_sky(with_light):
              "color d 0.75 0.3 0.2", "mult 1 6 0", "dielectric 1.5 40", "color g 1 1 1 0.0", "mult 1 9 8",
              "metal Cu", "color g 1 1 1 0.25", "mult 1 12 11"]
     cam = IO.Camera(pos=(13.0, 10.0, 8.0), lookat=(0.0, 0.0, 3.0), aperture_value=7, exposure_value=14, focal_length=0.35, iso=100.0)
-    golden_case("sky_light" if with_light else "sky", S.Scene(shapes, "sky"), lines, mats, cam, 160, 96, 128,
-                ["ptdl_halton", "pt_halton", "ptdl_rand"], sky="cloudy")
+    golden_case(name or ("sky_light" if with_light else "sky"), S.Scene(shapes, "sky"), lines, mats, cam, 160, 96, 128,
+                ["ptdl_halton", "pt_halton", "ptdl_rand"], sky=sky)
 
 
-CASES = {"sky": lambda: case_sky(False), "sky_light": lambda: case_sky(True), "diffuse_static": case_diffuse_static, "c10": case_c10, "motion": case_motion, "glass_metal": case_glass_metal}
+CASES = {"sky_const": lambda: case_sky(True, "sky_const 0.3 0.5 0.9 800", "sky_const"), "sky": lambda: case_sky(False), "sky_light": lambda: case_sky(True), "diffuse_static": case_diffuse_static, "c10": case_c10, "motion": case_motion, "glass_metal": case_glass_metal}
 
 if __name__ == "__main__":
     subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "oracle"), "ref"])

@@ -170,6 +170,9 @@ class GoldenImage:
             lmin, step = z[f"tab{i}_meta"]
             self.materials.add_table(lmin, step, z[f"tab{i}_data"])
         self.sky = str(z["sky"]) if "sky" in z.files else "black"
+        self.sky_args = dict(sky=cb.scene_io.SKIES[self.sky.split()[0]])
+        if "sky_coeff" in z.files:
+            self.sky_args.update(sky_coeff=[float(x) for x in z["sky_coeff"]], sky_scale=float(z["sky_scale"]))
 
     def ref(self, key, seed):
         return self.z[f"{key}_seed{seed}"]
@@ -197,7 +200,7 @@ class GoldenImage:
 
     def render(self, lib, acc, key, frame=1, spp=None, **kw):
         """the GPU image of one variant at the golden's resolution and sample count"""
-        r = lib.Render(acc, self.camera, self.materials, self.w, self.h, frame=frame, sky=cb.scene_io.SKIES[self.sky], **self.variant_args(key), **kw)
+        r = lib.Render(acc, self.camera, self.materials, self.w, self.h, frame=frame, **self.sky_args, **self.variant_args(key), **kw)
         for _ in range(spp or self.spp):
             r.render_pass()
         img, st = r.image(), r.stats()

@@ -27,7 +27,7 @@ HALTON_FRAC = 0.45   # measured: 0.006 (c10) .. 0.33 (motion/pt_halton: diffuse 
 RAND_FRAC = 1.15
 MEAN_TOL = 0.01      # per-channel mean, Halton variants (measured <= 0.005)
 
-CASES = ["diffuse_static", "c10", "motion", "glass_metal", "sky", "sky_light"]
+CASES = ["diffuse_static", "c10", "motion", "glass_metal", "sky", "sky_light", "sky_const"]
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
 
