@@ -8,7 +8,8 @@
 //                    path_extend at length 0 (src/pathspace.c:205-250): lambda, time, thin-lens camera sample
 //                    (src/camera.d/thinlens.c:68-128) -> first ray; the wave's new indices are processed in pixel-Morton order
 //   k_intersect      closest hit (traverse.cu) = accel_intersect in path_propagate (pathspace.c:763)
-//   k_compact_hits   slots whose ray hit something -> one index list per BSDF kind (material-sorted shading)
+//   k_compact_hits   slots whose ray hit something -> one index list per BSDF kind (material-sorted shading); rays that ended
+//                    at their sampled free-flight distance inside a medium form a fourth list (volume vertices)
 //   k_shade<kind>    rest of path_propagate + path_extend bookkeeping + the sampler (pt.c:40-54 / ptdl.c:112-150):
 //                    vertex preparation, emission splat with MIS, next-event sample (nee.h:87-243) -> shadow ray,
 //                    bsdf sample (shader.c:577-590) -> next ray, stream compaction of surviving paths
@@ -17,8 +18,9 @@
 //
 // Splat: spectrum_p_to_camera + 4x4 Blackman-Harris footprint (view.c:455-495, blackmanharris.h:43-77) with
 // float atomics into the W*H*3 accumulation buffer (the reference uses CAS loops the same way).
-// Scope: surfaces in vacuum / nested dielectrics, geometric lights, the built-in `black' and `cloudy' skies.  Media and sky
-// modules (daylight, environment maps) are SURVEY 8(f) rank 1/3.
+// Scope: surfaces, nested dielectrics, homogeneous participating media (interior / exterior, Henyey-Greenstein), geometric
+// lights, the built-in `black' and `cloudy' skies and the constant-colour sky module.  Heterogeneous media, volume lights and
+// the other sky modules (daylight, environment maps) are SURVEY 8(f).
 #include "shading.cuh"
 #include <cub/cub.cuh>
 #include <vector>
@@ -40,7 +42,7 @@ struct __align__(16) PathState   // 144 bytes, one per path in flight
   int32_t length;                       // path->length (number of finished vertices)
   int32_t rand_beg;                     // rand_beg of the vertex the current ray is about to create
   uint32_t bits;                        // bit0: nee_possible(v) (material_modes & (diffuse|glossy)); bits 8..: mt draw counter
-  int32_t med_n;
+  int32_t med_n;                        // media stack: entry count and the entries' medium ids (media_pack)
   uint32_t med_shape[MED_MAX];
   float med_ior[MED_MAX];
 };
@@ -79,6 +81,8 @@ struct RenderDev
   float sky_coeff[3], sky_scale;   // CB_SKY_CONST
   float p_sky;                     // lights_pdf_type: probability of connecting to the sky (list.c:44-49,76-88)
   float sky_far;                   // distance of the next-event point on the sky (shader.c:313-316)
+  uint32_t exterior_medium;        // 1 + index of the medium the camera sits in (shader_exterior_medium), 0 = vacuum
+  int32_t has_media;               // any medium in the scene: the free-flight / transmittance code paths are live
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -270,13 +274,21 @@ k_pixel_keys(RenderDev R, uint64_t first_index, uint32_t n, uint32_t *keys, uint
 
 __global__ void __launch_bounds__(RB)
 k_path_start(RenderDev R, uint64_t first_index, uint32_t n, const uint32_t *__restrict__ order, PathState *st, cb_ray_t *rays, float *aux,
-             uint32_t *rkeys)
+             uint32_t *rkeys, float *maxd)
 {
   const uint32_t i = blockIdx.x*blockDim.x + threadIdx.x;
   if(i >= n) return;
   PathState s;
   V3 pos;
-  path_start(R, first_index + (order ? order[i] : i), s, pos);   // st / rays already point at the first free slot of the pool
+  const uint64_t index = first_index + (order ? order[i] : i);
+  path_start(R, index, s, pos);   // st / rays already point at the first free slot of the pool
+  if(maxd)
+  { // the camera sits in the exterior medium: sample the free flight of the first edge before tracing it (pathspace.c:716-747)
+    float clip = FLT_MAX;
+    const Vol vol = medium_eval(R.mats, R.exterior_medium, s.lambda);
+    if(vol.present && vol.mu_s > 0.0f) clip = vol_free_flight(vol, point_dim(R.points, index, s.rand_beg + 0));
+    maxd[i] = clip;
+  }
   write_ray(rays, i, pos, mk3(s.omega[0], s.omega[1], s.omega[2]), s.time, 0xffffffffu, 0xffffffffu);
   if(st) st[i] = s;
   if(rkeys) rkeys[i] = ray_key(R, pos, mk3(s.omega[0], s.omega[1], s.omega[2]));
@@ -336,7 +348,7 @@ __device__ void prim_test_geo(const SceneGeo &S, uint64_t pid, const RayD &r, Hi
 
 __device__ __forceinline__ float max3abs(V3 x) { return fmaxf(fmaxf(.5f, fabsf(x.x)), fmaxf(fabsf(x.y), fabsf(x.z))); }
 
-struct ShadeCounters { unsigned long long next, nee, hits[3], splats; };   // next, nee, hits[kind] are per wave; splats keeps counting
+struct ShadeCounters { unsigned long long next, nee, hits[4], splats; };   // next, nee, hits[kind] are per wave; splats keeps counting
 
 // path_G for the edge between a surface vertex and the sampled light point (pathspace.c:58-69)
 __device__ __forceinline__ float cos_lambert(const Vtx &v, const Vtx &l, V3 d, float dist)
@@ -387,11 +399,18 @@ k_sky_miss(RenderDev R, uint32_t n, const PathState *__restrict__ st, const cb_h
   if(i < n)
   {
     const uint2 p = *reinterpret_cast<const uint2 *>(hits + i);
-    if((p.x & p.y) == 0xffffffffu)
+    if((p.x & p.y) == 0xffffffffu && !(R.has_media && hits[i].dist < FLT_MAX))   // (a clipped miss is a volume vertex)
     {
       const PathState s = st[i];
       const V3 omega = mk3(s.omega[0], s.omega[1], s.omega[2]);
-      const float em = sky_eval(R, omega, s.lambda);
+      float em = sky_eval(R, omega, s.lambda);
+      if(R.has_media)
+      { // an edge of infinite length through a medium has transmittance exp(-FLT_MAX mu_t) = 0 (pathspace.c:839-843, shader.c:57-64)
+        Media med; media_unpack(med, s.med_n);
+        for(int k=0;k<MED_MAX;k++) med.shape[k] = s.med_shape[k];
+        const Vol vol = medium_eval(R.mats, media_medium(med, R.exterior_medium), s.lambda);
+        if(vol.present && !(vol.mu_t == 0.0f)) em = 0.0f;
+      }
       if(em > 0.0f)
       {
         const float pdf_v = s.pdf_proj*s.cos_prev;      // path_G towards the environment = lambert at the previous vertex (pathspace.c:60-61)
@@ -418,8 +437,8 @@ __global__ void __launch_bounds__(256)
 k_compact_hits(RenderDev R, const cb_hitrec_t *__restrict__ hits, uint32_t n, uint32_t n_cap, uint32_t *__restrict__ list, ShadeCounters *cnt,
                int single_kind)
 {
-  __shared__ uint32_t warp_count[3][8];
-  __shared__ uint32_t block_base[3];
+  __shared__ uint32_t warp_count[4][8];
+  __shared__ uint32_t block_base[4];
   const uint32_t i = blockIdx.x*blockDim.x + threadIdx.x, lane = threadIdx.x & 31u, w = threadIdx.x >> 5;
   int kind = -1;
   if(i < n)
@@ -427,12 +446,13 @@ k_compact_hits(RenderDev R, const cb_hitrec_t *__restrict__ hits, uint32_t n, ui
     const uint2 p = *reinterpret_cast<const uint2 *>(hits + i);   // prim id words
     if((p.x & p.y) != 0xffffffffu)
       kind = single_kind >= 0 ? single_kind : R.mats.mat[R.geo.shape_material[p.x >> 3]].bsdf;
+    else if(R.has_media && hits[i].dist < FLT_MAX) kind = 3;   // the sampled free flight ended before any surface: volume vertex
   }
-  uint32_t m[3];
+  uint32_t m[4];
 #pragma unroll
-  for(int k=0;k<3;k++) { m[k] = __ballot_sync(0xffffffffu, kind == k); if(lane == 0) warp_count[k][w] = __popc(m[k]); }
+  for(int k=0;k<4;k++) { m[k] = __ballot_sync(0xffffffffu, kind == k); if(lane == 0) warp_count[k][w] = __popc(m[k]); }
   __syncthreads();
-  if(threadIdx.x < 3)
+  if(threadIdx.x < 4)
   {
     const int k = threadIdx.x;
     uint32_t tot = 0;
@@ -441,21 +461,40 @@ k_compact_hits(RenderDev R, const cb_hitrec_t *__restrict__ hits, uint32_t n, ui
   }
   __syncthreads();
 #pragma unroll
-  for(int k=0;k<3;k++)
+  for(int k=0;k<4;k++)
     if(kind == k) list[(size_t)k*n_cap + block_base[k] + warp_count[k][w] + __popc(m[k] & ((1u << lane) - 1u))] = i;
 }
 
-// one vertex of every live path whose surface has BSDF kind KIND (0 diffuse, 1 dielectric, 2 metal): each launch carries the
-// code of ONE BSDF (the all-in-one kernel was 17 k instructions and lost 24 % of its stall samples to instruction-cache
-// misses) and no lane waits for another material's branch.  KINDS = 1 << KIND for the templates of shading.cuh; light
-// vertices reached by next-event estimation only need their emission slots, which every variant fills.
+// The vertex-level callbacks of a volume vertex are the medium's (medium_rgb.c:62-103): Henyey-Greenstein around the incoming
+// direction, scaled by mu_s.  KINDS == 8 selects them, every other KINDS goes to the surface BSDFs of shading.cuh.
 template<int KINDS>
+__device__ __forceinline__ float vtx_eval(const MaterialsDev &M, Vtx &v, V3 wi, V3 wo, float lambda, float cur_ior)
+{
+  if constexpr(KINDS == 8) { v.mode |= M_GLOSSY | M_VOLUME; return v.vol_mu_s*hg_eval(v.vol_g, wi, wo); }
+  else return bsdf_eval<KINDS>(M, v, wi, wo, lambda, cur_ior);
+}
+template<int KINDS>
+__device__ __forceinline__ float vtx_pdf(const MaterialsDev &M, const Vtx &v, V3 wi, V3 wo)
+{
+  if constexpr(KINDS == 8) return (v.mode & M_VOLUME) ? hg_eval(v.vol_g, wi, wo) : 0.0f;
+  else return bsdf_pdf<KINDS>(M, v, wi, wo);
+}
+
+// one vertex of every live path whose surface has BSDF kind KIND (0 diffuse, 1 dielectric, 2 metal; 3 = volume vertex of a
+// homogeneous medium): each launch carries the code of ONE BSDF (the all-in-one kernel was 17 k instructions and lost 24 % of
+// its stall samples to instruction-cache misses) and no lane waits for another material's branch.  KINDS = 1 << KIND for the
+// templates of shading.cuh; light vertices reached by next-event estimation only need their emission slots, which every
+// variant fills.  MEDIA compiles the participating-media terms in (free-flight sampling of the next edge, transmittance and
+// distance pdf of the finished one: pathspace.c:716-747,822-843, shader.c:46-155); scenes without media run the MEDIA = false
+// variants, which are instruction for instruction the surface-only integrator.
+template<int KINDS, bool MEDIA>
 __global__ void __launch_bounds__(RB)
 k_shade(RenderDev R, uint32_t n, const PathState *__restrict__ st_in, const cb_ray_t *__restrict__ rays_in,
         const cb_hitrec_t *__restrict__ hits, PathState *__restrict__ st_out, cb_ray_t *__restrict__ rays_out,
         cb_ray_t *__restrict__ nee_rays, float *__restrict__ nee_maxdist, uint2 *__restrict__ nee_light, NeeRec *__restrict__ nee_recs,
-        ShadeCounters *cnt, uint32_t *__restrict__ rkeys_out, const uint32_t *__restrict__ hit_list, int kind)
+        ShadeCounters *cnt, uint32_t *__restrict__ rkeys_out, const uint32_t *__restrict__ hit_list, int kind, float *__restrict__ maxd_out)
 {
+  constexpr bool VOLV = KINDS == 8;   // this launch shades volume vertices
   const uint32_t t = blockIdx.x*blockDim.x + threadIdx.x;
   const uint32_t n_hits = (uint32_t)*reinterpret_cast<volatile unsigned long long *>(&cnt->hits[kind]);   // written by k_compact_hits
   if(blockIdx.x*blockDim.x >= n_hits) return;   // whole block beyond the list (the grid is sized for n, the upper bound)
@@ -463,6 +502,7 @@ k_shade(RenderDev R, uint32_t n, const PathState *__restrict__ st_in, const cb_r
   bool alive = false, have_nee = false, did_splat = false;
   PathState s;
   V3 next_pos = mk3(0, 0, 0), next_dir = mk3(0, 0, 0);
+  float next_clip = FLT_MAX;
   cb_ray_t nray; NeeRec nrec; float nmax = 0.0f;
   if(t < n_hits)
   {
@@ -473,7 +513,7 @@ k_shade(RenderDev R, uint32_t n, const PathState *__restrict__ st_in, const cb_r
     const V3 omega = mk3(s.omega[0], s.omega[1], s.omega[2]);
     const bool hit_geo = !((h.prim[0] & h.prim[1]) == 0xffffffffu);
     // black sky: an environment vertex carries no emission and ends the path (pathspace.c:856-873, shader.c:464-470)
-    if(hit_geo)
+    if(hit_geo || VOLV)
     {
       const cb_ray_t ray = rays_in[i];
       Vtx v;
@@ -481,23 +521,44 @@ k_shade(RenderDev R, uint32_t n, const PathState *__restrict__ st_in, const cb_r
       v.u = h.u; v.v = h.v; v.s = v.t = 0.0f;
       v.flags = 0; v.mode = M_ABSORB; v.material_modes = 0;
       v.x = mk3(ray.pos[0] + h.dist*ray.dir[0], ray.pos[1] + h.dist*ray.dir[1], ray.pos[2] + h.dist*ray.dir[2]);
-      Media med; med.n = s.med_n;
+      Media med; media_unpack(med, s.med_n);
       for(int k=0;k<MED_MAX;k++) { med.shape[k] = s.med_shape[k]; med.ior[k] = s.med_ior[k]; }
-      prepare_vertex<KINDS>(R.geo, R.mats, v, omega, s.time, s.lambda, s.scramble, med, s.cur_ior);
+      Vol vol; vol.present = false; vol.mu_t = vol.mu_s = vol.g = 0.0f;   // e[v].vol: the medium of the edge that just ended
+      if(MEDIA) vol = medium_eval(R.mats, media_medium(med, R.exterior_medium), s.lambda);
+      if constexpr(VOLV)
+      { // manifold_init + shader_prepare of a vertex without primitive (manifold.h:236-240, shader.c:478-503)
+        v.n = v.gn = omega;
+        scrambled_onb(s.scramble, v.n, v.a, v.b);
+        v.material_modes = M_VOLUME | M_GLOSSY;
+        v.rd = v.rs = v.rg = v.em = 0.0f; v.roughness = 1.0f; v.ior = 1.0f; v.eta = 1.0f; v.mat = -1;
+        v.vol_mu_s = vol.mu_s; v.vol_g = vol.g;
+      }
+      else prepare_vertex<KINDS>(R.geo, R.mats, v, omega, s.time, s.lambda, s.scramble, med, s.cur_ior);
       // self intersection (pathspace.c:809-820)
       const uint32_t vcnt = v.prim_hi >> 29;
-      const bool self = (vcnt > 2 || h.dist < 1e-4f) && v.prim_lo == s.prim_lo && v.prim_hi == s.prim_hi;
+      const bool self = !VOLV && (vcnt > 2 || h.dist < 1e-4f) && v.prim_lo == s.prim_lo && v.prim_hi == s.prim_hi;
       if(!self)
       {
-        if(v.em > 0.0f && !(v.flags & F_INSIDE)) v.material_modes = v.mode = M_EMIT;
-        // on-surface pdf of this vertex (pathspace.c:252-253, 45-69)
-        const float cos_v = fabsf(dot(v.n, omega));
+        if(!VOLV && v.em > 0.0f && !(v.flags & F_INSIDE)) v.material_modes = v.mode = M_EMIT;
+        // on-surface pdf of this vertex (pathspace.c:252-253, 45-69); no cosine at a volume vertex
+        const float cos_v = VOLV ? 1.0f : fabsf(dot(v.n, omega));
         const float G = s.cos_prev*cos_v/(h.dist*h.dist);
-        const float pdf_v = s.pdf_proj*G;
+        float pdf_v, thr;
+        if(MEDIA)
+        { // distance sampling: pdf and transmittance of the edge (shader_vol_sample / shader_vol_transmittance, pathspace.c:822-843)
+          float e_pdf = 1.0f, e_T = 1.0f;
+          if(vol.present)
+          {
+            e_T = expf(-h.dist*vol.mu_t);
+            if(vol.mu_s > 0.0f) e_pdf = VOLV ? e_T*vol.mu_t : e_T;   // scattering medium: free flight sampled first
+          }
+          pdf_v = (s.pdf_proj*e_pdf)*G;          // pathspace.c:889-890, then :252
+          thr = s.thr*(e_T/e_pdf);               // path_update_throughput (pathspace.c:158)
+        }
+        else { pdf_v = s.pdf_proj*G; thr = s.thr; }
         const int vi = s.length;        // index of this vertex
         s.length++;
         const int rand_beg_v = s.rand_beg;
-        float thr = s.thr;
         bool stop = false;
         // ---- emission: path_update_throughput + sampler splat
         if(v.mode & M_EMIT)
@@ -544,21 +605,39 @@ k_shade(RenderDev R, uint32_t n, const PathState *__restrict__ st_in, const cb_r
                 if(edf > 0.0f)
                 {
                   Vtx vb = v;
-                  const float bsdf = bsdf_eval<KINDS>(R.mats, vb, omega, d, s.lambda, s.cur_ior);
-                  if(bsdf > 0.0f)
+                  const float bsdf = vtx_eval<KINDS>(R.mats, vb, omega, d, s.lambda, s.cur_ior);
+                  float T_nee = 1.0f, vol_pdf = 1.0f;
+                  bool edge_ok = true;
+                  if(MEDIA && bsdf > 0.0f)
+                  { // path_edge_init_volume for the connection edge (nee.h:192), its transmittance with the environment clamp
+                    // (shader.c:57-60) and shader_vol_pdf for the extension the sample competes with (shader.c:107-131)
+                    Vol ve = vol;
+                    if(!VOLV && (vb.mode & M_TRANSMIT))
+                    {
+                      Media tm = med;
+                      edge_ok = media_transmit(tm, v.prim_lo >> 3, v.ior, v.flags & F_INSIDE, (uint32_t)R.mats.mat[v.mat].medium);
+                      ve = medium_eval(R.mats, media_medium(tm, R.exterior_medium), s.lambda);
+                    }
+                    if(ve.present)
+                    {
+                      T_nee = expf(-10000.0f*ve.mu_t);
+                      if(ve.mu_s > 0.0f) vol_pdf = expf(-R.sky_far*ve.mu_t);
+                    }
+                  }
+                  if(bsdf > 0.0f && edge_ok)
                   {
                     const V3 lx = mk3(v.x.x + R.sky_far*d.x, v.x.y + R.sky_far*d.y, v.x.z + R.sky_far*d.z);
                     const float eps = 1e-4f*max3abs(v.x);                    // prims_get_ray towards a vertex without primitive
                     V3 rd = sub(lx, v.x);
                     const float ilen = 1.0f/sqrtf(dot(rd, rd));
                     rd = mk3(rd.x*ilen, rd.y*ilen, rd.z*ilen);
-                    const V3 rp = mk3(v.x.x + eps*rd.x, v.x.y + eps*rd.y, v.x.z + eps*rd.z);
+                    const V3 rp = VOLV ? v.x : mk3(v.x.x + eps*rd.x, v.x.y + eps*rd.y, v.x.z + eps*rd.z);
                     const V3 dv = sub(lx, rp);
                     const float total_dist = sqrtf(dot(dv, dv));
-                    const float Gl = fabsf(dot(vb.n, d));                    // path_G with an environment end point
-                    const float thr_l = ((thr*bsdf)*(1.0f*edf))*Gl;
+                    const float Gl = VOLV ? 1.0f : fabsf(dot(vb.n, d));      // path_G with an environment end point
+                    const float thr_l = ((thr*bsdf)*(T_nee*edf))*Gl;
                     const float pdf_nee = pdf_sky*R.p_sky;
-                    const float pdf_ext = bsdf_pdf<KINDS>(R.mats, vb, omega, d)*Gl;
+                    const float pdf_ext = (vol_pdf*vtx_pdf<KINDS>(R.mats, vb, omega, d))*Gl;
                     const float w = pdf_nee/(pdf_ext + pdf_nee);
                     if(thr_l > 0.0f && total_dist > 0.0f)
                     {
@@ -598,24 +677,41 @@ k_shade(RenderDev R, uint32_t n, const PathState *__restrict__ st_in, const cb_r
                 if(edf > 0.0f)
                 {
                   Vtx vb = v;   // shader_brdf sets the mode on v; path_pop resets it afterwards
-                  const float bsdf = bsdf_eval<KINDS>(R.mats, vb, omega, d, s.lambda, s.cur_ior);
-                  if(bsdf > 0.0f)
+                  const float bsdf = vtx_eval<KINDS>(R.mats, vb, omega, d, s.lambda, s.cur_ior);
+                  float T_nee = 1.0f, vol_pdf = 1.0f;
+                  bool edge_ok = true;
+                  if(MEDIA && bsdf > 0.0f)
+                  { // path_edge_init_volume for the connection edge (nee.h:192), shader_vol_transmittance (:205), shader_vol_pdf
+                    Vol ve = vol;
+                    if(!VOLV && (vb.mode & M_TRANSMIT))
+                    {
+                      Media tm = med;
+                      edge_ok = media_transmit(tm, v.prim_lo >> 3, v.ior, v.flags & F_INSIDE, (uint32_t)R.mats.mat[v.mat].medium);
+                      ve = medium_eval(R.mats, media_medium(tm, R.exterior_medium), s.lambda);
+                    }
+                    if(ve.present)
+                    {
+                      T_nee = expf(-dist*ve.mu_t);
+                      if(ve.mu_s > 0.0f) vol_pdf = T_nee;
+                    }
+                  }
+                  if(bsdf > 0.0f && edge_ok)
                   {
-                    // path_visible: prims_get_ray (prims.c:390-492)
+                    // path_visible: prims_get_ray (prims.c:390-492); a vertex without primitive starts at its own position
                     const float eps = 1e-4f*max3abs(v.x);
                     V3 rd = sub(l.x, v.x);
                     const float ilen = 1.0f/sqrtf(dot(rd, rd));
                     rd = mk3(rd.x*ilen, rd.y*ilen, rd.z*ilen);
-                    const V3 rp = mk3(v.x.x + eps*rd.x, v.x.y + eps*rd.y, v.x.z + eps*rd.z);
+                    const V3 rp = VOLV ? v.x : mk3(v.x.x + eps*rd.x, v.x.y + eps*rd.y, v.x.z + eps*rd.z);
                     const V3 dv = mk3(l.x.x - eps*rd.x - rp.x, l.x.y - eps*rd.y - rp.y, l.x.z - eps*rd.z - rp.z);
                     const float total_dist = sqrtf(dot(dv, dv));
                     if(!(dot(l.gn, rd) >= 0.0f) && total_dist > 0.0f)
                     {
-                      const float Gl = cos_lambert(vb, l, d, dist);
-                      const float thr_l = ((thr*bsdf)*(1.0f*edf))*Gl;
+                      const float Gl = VOLV ? fabsf(dot(l.n, d))/(dist*dist) : cos_lambert(vb, l, d, dist);
+                      const float thr_l = ((thr*bsdf)*(T_nee*edf))*Gl;
                       // mis against extending the path into the light (ptdl.c:142-146)
                       const float pdf_nee = R.lights.p_geo*pdf_l;
-                      const float pdf_ext = bsdf_pdf<KINDS>(R.mats, vb, omega, d)*Gl;
+                      const float pdf_ext = (vol_pdf*vtx_pdf<KINDS>(R.mats, vb, omega, d))*Gl;
                       const float w = pdf_nee/(pdf_ext + pdf_nee);
                       if(thr_l > 0.0f)
                       {
@@ -648,34 +744,46 @@ k_shade(RenderDev R, uint32_t n, const PathState *__restrict__ st_in, const cb_r
           const float rx = point_dim(R.points, index, rb + 1), ry = point_dim(R.points, index, rb + 2), rm = point_dim(R.points, index, rb + 3);
           V3 wo; float pdf = 1.0f;
           v.mode &= M_EMIT;
-          const uint32_t keep_emit = v.mode;
-          float weight = bsdf_sample<KINDS>(R.mats, v, omega, s.lambda, s.cur_ior, rx, ry, rm, wo, pdf);
+          float weight;
+          if constexpr(VOLV)
+          { // medium_rgb.c:62-73: Henyey-Greenstein around the incoming direction, weight mu_s
+            (void)rm;
+            float out[3];
+            hg_sample(v.vol_g, rx, ry, out, pdf);
+            v.mode |= M_GLOSSY | M_VOLUME;
+            wo = mk3(v.n.x*out[0] + v.a.x*out[1] + v.b.x*out[2], v.n.y*out[0] + v.a.y*out[1] + v.b.y*out[2], v.n.z*out[0] + v.a.z*out[1] + v.b.z*out[2]);
+            weight = v.vol_mu_s;
+          }
+          else weight = bsdf_sample<KINDS>(R.mats, v, omega, s.lambda, s.cur_ior, rx, ry, rm, wo, pdf);
           wo = normalise(wo);
           const float dt = ((v.flags & F_INSIDE) ? -1.0f : 1.0f)*dot(v.gn, wo);
           if(((v.mode & M_REFLECT) && dt < 0.0f) || ((v.mode & M_TRANSMIT) && dt > 0.0f)) weight = 0.0f;
-          (void)keep_emit;
           const float thr_next = thr*weight;
           bool ok = thr_next > 0.0f;
-          if(ok && (v.mode & M_TRANSMIT))
+          Vol vnext = vol;   // medium of the next edge: unchanged unless the path crosses the interface
+          if(!VOLV && ok && (v.mode & M_TRANSMIT))
           { // path_edge_init_volume for the next edge
-            ok = media_transmit(med, v.prim_lo >> 3, v.ior, v.flags & F_INSIDE);
+            ok = media_transmit(med, v.prim_lo >> 3, v.ior, v.flags & F_INSIDE, MEDIA ? (uint32_t)R.mats.mat[v.mat].medium : 0u);
             s.cur_ior = media_ior(med);
+            if(MEDIA) vnext = medium_eval(R.mats, media_medium(med, R.exterior_medium), s.lambda);
           }
           if(ok)
           {
             alive = true;
             s.thr_prev = thr; s.thr = thr_next; s.pdf_proj = pdf;
-            s.cos_prev = fabsf(dot(v.n, wo));
+            s.cos_prev = VOLV ? 1.0f : fabsf(dot(v.n, wo));
             s.x[0] = v.x.x; s.x[1] = v.x.y; s.x[2] = v.x.z;
             s.omega[0] = wo.x; s.omega[1] = wo.y; s.omega[2] = wo.z;
             s.prim_lo = v.prim_lo; s.prim_hi = v.prim_hi;
             s.rand_beg = rb;
             s.bits = (mt << 8) | ((v.material_modes & (M_DIFFUSE | M_GLOSSY)) ? 1u : 0u);
-            s.med_n = med.n;
+            s.med_n = media_pack(med);
             for(int k=0;k<MED_MAX;k++) { s.med_shape[k] = med.shape[k]; s.med_ior[k] = med.ior[k]; }
-            const float eps = max3abs(v.x)*1e-4f;   // prims_offset_ray (prims.c:374-388)
-            next_pos = mk3(v.x.x + eps*wo.x, v.x.y + eps*wo.y, v.x.z + eps*wo.z);
+            const float eps = max3abs(v.x)*1e-4f;   // prims_offset_ray (prims.c:374-388), only on geometry (pathspace.c:759-761)
+            next_pos = VOLV ? v.x : mk3(v.x.x + eps*wo.x, v.x.y + eps*wo.y, v.x.z + eps*wo.z);
             next_dir = wo;
+            // a scattering medium ahead: draw the free flight now, it clips the next closest-hit ray (pathspace.c:742-747)
+            if(MEDIA && vnext.present && vnext.mu_s > 0.0f) next_clip = vol_free_flight(vnext, point_dim(R.points, index, rb + 0));
           }
         }
       }
@@ -695,6 +803,7 @@ k_shade(RenderDev R, uint32_t n, const PathState *__restrict__ st_in, const cb_r
       st_out[o] = s;
       write_ray(rays_out, o, next_pos, next_dir, s.time, s.prim_lo, s.prim_hi);
       if(rkeys_out) rkeys_out[o] = ray_key(R, next_pos, next_dir);
+      if(MEDIA) maxd_out[o] = next_clip;
     }
   }
   const uint32_t msp = __ballot_sync(0xffffffffu, did_splat);
@@ -760,6 +869,43 @@ __global__ void k_bsdf(MaterialsDev M, int32_t material, const cb_bsdf_query_t *
   out[i] = R;
 }
 
+// cb200_render_medium: the medium helpers of shading.cuh exactly as k_path_start / k_shade<8> call them
+__global__ void k_medium(MaterialsDev M, uint32_t medium, const cb_medium_query_t *__restrict__ q, cb_medium_result_t *__restrict__ out, uint32_t n)
+{
+  const uint32_t i = blockIdx.x*blockDim.x + threadIdx.x;
+  if(i >= n) return;
+  const cb_medium_query_t Q = q[i];
+  cb_medium_result_t o;
+  const Vol vol = medium_eval(M, medium, Q.lambda);
+  o.mu_t = vol.mu_t; o.mu_s = vol.mu_s;
+  o.free_dist = FLT_MAX; o.free_pdf = 1.0f;
+  o.transmittance = expf(-Q.dist*vol.mu_t);
+  o.vol_pdf = 1.0f;
+  if(vol.mu_s > 0.0f)
+  {
+    o.free_dist = vol_free_flight(vol, Q.rand[2]);
+    o.free_pdf = expf(-o.free_dist*vol.mu_t)*vol.mu_t;
+    o.vol_pdf = o.transmittance*vol.mu_t;
+  }
+  const V3 wi = mk3(Q.wi[0], Q.wi[1], Q.wi[2]), wo_q = mk3(Q.wo[0], Q.wo[1], Q.wo[2]);
+  Vtx v;
+  v.n = v.gn = wi;
+  scrambled_onb(0.5f, v.n, v.a, v.b);
+  v.mode = M_ABSORB; v.material_modes = M_VOLUME | M_GLOSSY;
+  v.vol_mu_s = vol.mu_s; v.vol_g = vol.g;
+  float out3[3], pdf;
+  hg_sample(v.vol_g, Q.rand[0], Q.rand[1], out3, pdf);
+  o.s_wo[0] = v.n.x*out3[0] + v.a.x*out3[1] + v.b.x*out3[2];
+  o.s_wo[1] = v.n.y*out3[0] + v.a.y*out3[1] + v.b.y*out3[2];
+  o.s_wo[2] = v.n.z*out3[0] + v.a.z*out3[1] + v.b.z*out3[2];
+  o.s_weight = v.vol_mu_s; o.s_pdf = pdf; o.s_mode = M_GLOSSY | M_VOLUME;
+  Vtx vb = v;
+  o.f = vtx_eval<8>(M, vb, wi, wo_q, Q.lambda, 1.0f);
+  o.f_mode = vb.mode;
+  o.pdf = vtx_pdf<8>(M, vb, wi, wo_q);
+  out[i] = o;
+}
+
 __global__ void k_points(PointsDev P, const uint64_t *index, const int32_t *dim, float *out, uint32_t n)
 {
   const uint32_t i = blockIdx.x*blockDim.x + threadIdx.x;
@@ -814,6 +960,7 @@ struct cb200_render
   PathState *st[2];
   cb_ray_t *rays[2];
   cb_hitrec_t *hits;
+  float *maxd[2];                // sampled free-flight distance of every pending ray (scenes with media only), rides with rays[]
   cb_ray_t *nee_rays; float *nee_md; NeeRec *nee_recs; uint2 *nee_light; int32_t *nee_vis;
   ShadeCounters *d_cnt, *h_cnt;
   cb_render_stats_t stats;
@@ -948,6 +1095,8 @@ static int build_lights(cb200_render *r)
   r->dev.geo.shape_material = dev_upload(r, shape_mat.data(), shape_mat.size());
   r->bsdf_kinds = 0;
   for(int i=0;i<s->num_shapes;i++) r->bsdf_kinds |= 1 << d.materials[shape_mat[i]].bsdf;
+  r->dev.has_media = d.exterior_medium ? 1 : 0;
+  for(int i=0;i<s->num_shapes;i++) if(d.materials[shape_mat[i]].medium) r->dev.has_media = 1;
   if(!r->bsdf_kinds) r->bsdf_kinds = 1;
   std::vector<float> shape_L(s->num_shapes ? s->num_shapes : 1, 0.0f);
   for(int i=0;i<s->num_shapes;i++)
@@ -1027,6 +1176,14 @@ cb200_render_t *cb200_render_create(cb200_accel_t *a, const cb_render_desc_t *de
     { cb200_set_error("render_create: colour checker without table"); return nullptr; }
   }
   if(desc->sky != CB_SKY_BLACK && desc->sky != CB_SKY_CLOUDY && desc->sky != CB_SKY_CONST) { cb200_set_error("render_create: unsupported sky (no CPU fallback)"); return nullptr; }
+  if(desc->num_media < 0 || desc->num_media > CB_MAX_MEDIA || (desc->num_media > 0 && !desc->media) ||
+     desc->exterior_medium < 0 || desc->exterior_medium > desc->num_media)
+  { cb200_set_error("render_create: malformed media list"); return nullptr; }
+  for(int i=0;i<desc->num_materials;i++)
+    if(desc->materials[i].num_ops >= 0 && (desc->materials[i].medium < 0 || desc->materials[i].medium > desc->num_media))
+    { cb200_set_error("render_create: material references a medium that was not supplied"); return nullptr; }
+  if(desc->exterior_medium && desc->sky != CB_SKY_BLACK)
+  { cb200_set_error("render_create: an exterior medium under a non-black sky is not supported (no CPU fallback)"); return nullptr; }
   cb200_render *r = new cb200_render();
   r->accel = a;
   r->desc = *desc;
@@ -1065,7 +1222,9 @@ cb200_render_t *cb200_render_create(cb200_accel_t *a, const cb_render_desc_t *de
   D.mats.mat = dev_upload(r, desc->materials, desc->num_materials);
   D.mats.tables = dev_upload(r, tabs.data(), tabs.size());
   D.mats.table_data = dev_upload(r, tdata.data(), tdata.size());
-  ok = ok && D.mats.mat && D.mats.tables && D.mats.table_data;
+  D.mats.media = dev_upload(r, desc->media, (size_t)desc->num_media);
+  D.exterior_medium = (uint32_t)desc->exterior_medium;
+  ok = ok && D.mats.mat && D.mats.tables && D.mats.table_data && D.mats.media;
   ok = ok && cudaMemcpyToSymbol(c_cie, cie1931_xyz, sizeof(cie1931_xyz)) == cudaSuccess;
   ok = ok && build_halton(r, desc->frame) == 0;
   if(ok && build_lights(r)) { cb200_render_destroy(r); return nullptr; }
@@ -1081,7 +1240,9 @@ cb200_render_t *cb200_render_create(cb200_accel_t *a, const cb_render_desc_t *de
   D.fb = r->own_fb = dev_alloc<float>(r, (size_t)desc->width*desc->height*3);
   for(int k=0;k<2;k++) { r->st[k] = dev_alloc<PathState>(r, N); r->rays[k] = dev_alloc<cb_ray_t>(r, N); ok = ok && r->st[k] && r->rays[k]; }
   r->hits = dev_alloc<cb_hitrec_t>(r, N);
-  r->hit_list = dev_alloc<uint32_t>(r, 3*N); ok = ok && r->hit_list;
+  r->hit_list = dev_alloc<uint32_t>(r, 4*N); ok = ok && r->hit_list;
+  r->maxd[0] = r->maxd[1] = nullptr;
+  if(D.has_media) for(int k=0;k<2;k++) { r->maxd[k] = dev_alloc<float>(r, N); ok = ok && r->maxd[k]; }
   r->nee_rays = dev_alloc<cb_ray_t>(r, N); r->nee_md = dev_alloc<float>(r, N); r->nee_recs = dev_alloc<NeeRec>(r, N); r->nee_light = dev_alloc<uint2>(r, N); r->nee_vis = dev_alloc<int32_t>(r, N);
   r->d_cnt = dev_alloc<ShadeCounters>(r, 1);
   for(int k=0;k<2;k++) { r->keys[k] = dev_alloc<uint32_t>(r, N); r->order[k] = dev_alloc<uint32_t>(r, N); ok = ok && r->keys[k] && r->order[k]; }
@@ -1197,11 +1358,11 @@ static int render_wave(cb200_render *r, uint32_t n, cudaStream_t st)
       cb200_count_launch(3); r->stats.kernel_launches += 3;
       order = r->ray_order;
     }
-    rc = cb200_launch_intersect(r->accel, r->rays[cur], nullptr, r->hits, n, st, r->counting ? r->d_trav_cnt : nullptr, order);
+    rc = cb200_launch_intersect(r->accel, r->rays[cur], r->maxd[cur], r->hits, n, st, r->counting ? r->d_trav_cnt : nullptr, order);
   }
   if(rc) return rc;
   r->stats.rays_closest += n; r->stats.kernel_launches++;
-  CB_CUDA(cudaMemsetAsync(r->d_cnt, 0, 5*sizeof(unsigned long long), st));   // next, nee, hits[3] (splats keeps counting)
+  CB_CUDA(cudaMemsetAsync(r->d_cnt, 0, 6*sizeof(unsigned long long), st));   // next, nee, hits[4] (splats keeps counting)
   {
     TimeScope ts(r, st, KC_SHADE, n);
     if(r->dev.sky != CB_SKY_BLACK)
@@ -1209,16 +1370,25 @@ static int render_wave(cb200_render *r, uint32_t n, cudaStream_t st)
       k_sky_miss<<<(n + RB - 1)/RB, RB, 0, st>>>(r->dev, n, r->st[cur], r->hits, r->d_cnt);
       cb200_count_launch(); r->stats.kernel_launches++;
     }
-    const int single = (r->bsdf_kinds == 1) ? 0 : (r->bsdf_kinds == 2) ? 1 : (r->bsdf_kinds == 4) ? 2 : -1;
+    const int single = r->dev.has_media ? -1 : (r->bsdf_kinds == 1) ? 0 : (r->bsdf_kinds == 2) ? 1 : (r->bsdf_kinds == 4) ? 2 : -1;
     k_compact_hits<<<(n + 255)/256, 256, 0, st>>>(r->dev, r->hits, n, (uint32_t)r->batch, r->hit_list, r->d_cnt, single);
     cb200_count_launch(); r->stats.kernel_launches++;
     uint32_t *rk = r->ray_sort ? r->rkeys[cur^1] : nullptr;
-#define SHADE_LAUNCH(K) k_shade<(1 << K)><<<(n + RB - 1)/RB, RB, 0, st>>>(r->dev, n, r->st[cur], r->rays[cur], r->hits, r->st[cur^1], r->rays[cur^1], \
-      r->nee_rays, r->nee_md, r->nee_light, r->nee_recs, r->d_cnt, rk, r->hit_list + (size_t)K*r->batch, K)
-    if(r->bsdf_kinds & 1) { SHADE_LAUNCH(0); cb200_count_launch(); r->stats.kernel_launches++; }
-    if(r->bsdf_kinds & 2) { SHADE_LAUNCH(1); cb200_count_launch(); r->stats.kernel_launches++; }
-    if(r->bsdf_kinds & 4) { SHADE_LAUNCH(2); cb200_count_launch(); r->stats.kernel_launches++; }
+#define SHADE_ARGS(K) (r->dev, n, r->st[cur], r->rays[cur], r->hits, r->st[cur^1], r->rays[cur^1], \
+      r->nee_rays, r->nee_md, r->nee_light, r->nee_recs, r->d_cnt, rk, r->hit_list + (size_t)K*r->batch, K, r->maxd[cur^1])
+#define SHADE_LAUNCH(K) do { if(r->dev.has_media) k_shade<(1 << K), true><<<(n + RB - 1)/RB, RB, 0, st>>>SHADE_ARGS(K); \
+                             else k_shade<(1 << K), false><<<(n + RB - 1)/RB, RB, 0, st>>>SHADE_ARGS(K); \
+                             cb200_count_launch(); r->stats.kernel_launches++; } while(0)
+    if(r->bsdf_kinds & 1) SHADE_LAUNCH(0);
+    if(r->bsdf_kinds & 2) SHADE_LAUNCH(1);
+    if(r->bsdf_kinds & 4) SHADE_LAUNCH(2);
+    if(r->dev.has_media)
+    { // volume vertices of scattering media (kind 3)
+      k_shade<8, true><<<(n + RB - 1)/RB, RB, 0, st>>>SHADE_ARGS(3);
+      cb200_count_launch(); r->stats.kernel_launches++;
+    }
 #undef SHADE_LAUNCH
+#undef SHADE_ARGS
   }
   CB_CUDA(cudaMemcpyAsync(r->h_cnt, r->d_cnt, sizeof(ShadeCounters), cudaMemcpyDeviceToHost, st));
   CB_CUDA(cudaStreamSynchronize(st));
@@ -1284,7 +1454,8 @@ int cb200_render_pass_stream(cb200_render_t *r, uint64_t first_index, uint64_t c
       CB_CUDA(cub::DeviceRadixSort::SortPairs(r->sort_tmp, tmp, r->keys[0], r->keys[1], r->order[0], r->order[1], (int)n_new, 0, 24, st));
       k_path_start<<<(n_new + RB - 1)/RB, RB, 0, st>>>(r->dev, first_index + started, n_new, r->order[1],
                                                         r->st[r->cur] + r->n_alive, r->rays[r->cur] + r->n_alive, nullptr,
-                                                        r->ray_sort ? r->rkeys[r->cur] + r->n_alive : nullptr);
+                                                        r->ray_sort ? r->rkeys[r->cur] + r->n_alive : nullptr,
+                                                        r->maxd[r->cur] ? r->maxd[r->cur] + r->n_alive : nullptr);
       cb200_count_launch(5); r->stats.kernel_launches += 5;   // keys, radix sort (histogram + digit passes, counted as 3), path start
       r->stats.paths += n_new;
       started += n_new;
@@ -1341,12 +1512,26 @@ int cb200_render_bsdf(cb200_render_t *r, int32_t material, const cb_bsdf_query_t
   return 0;
 }
 
+int cb200_render_medium(cb200_render_t *r, int32_t medium, const cb_medium_query_t *queries, cb_medium_result_t *results, uint64_t n)
+{
+  if(!r || !queries || !results || medium < 0 || medium >= r->desc.num_media)
+  { cb200_set_error("render_medium: bad arguments"); return CB200_ERR_ARG; }
+  cb_medium_query_t *d_q = nullptr; cb_medium_result_t *d_o = nullptr;
+  CB_CUDA(cudaMalloc(&d_q, (n + 1)*sizeof(cb_medium_query_t))); CB_CUDA(cudaMalloc(&d_o, (n + 1)*sizeof(cb_medium_result_t)));
+  CB_CUDA(cudaMemcpy(d_q, queries, n*sizeof(cb_medium_query_t), cudaMemcpyHostToDevice));
+  if(n) k_medium<<<(unsigned)((n + 127)/128), 128>>>(r->dev.mats, (uint32_t)medium + 1u, d_q, d_o, (uint32_t)n);
+  cb200_count_launch();
+  CB_CUDA(cudaMemcpy(results, d_o, n*sizeof(cb_medium_result_t), cudaMemcpyDeviceToHost));
+  cudaFree(d_q); cudaFree(d_o);
+  return 0;
+}
+
 int cb200_render_camera_rays(cb200_render_t *r, uint64_t first_index, uint64_t n, cb_ray_t *out_rays, float *out_aux)
 {
   if(!r || !out_rays || n > r->batch) { cb200_set_error("render_camera_rays: bad arguments (n must be <= batch_paths)"); return CB200_ERR_ARG; }
   float *d_aux = nullptr;
   CB_CUDA(cudaMalloc(&d_aux, n*16 + 16));
-  if(n) k_path_start<<<(unsigned)((n + RB - 1)/RB), RB>>>(r->dev, first_index, (uint32_t)n, nullptr, nullptr, r->rays[0], d_aux, nullptr);
+  if(n) k_path_start<<<(unsigned)((n + RB - 1)/RB), RB>>>(r->dev, first_index, (uint32_t)n, nullptr, nullptr, r->rays[0], d_aux, nullptr, nullptr);
   cb200_count_launch();
   CB_CUDA(cudaMemcpy(out_rays, r->rays[0], n*sizeof(cb_ray_t), cudaMemcpyDeviceToHost));
   if(out_aux) CB_CUDA(cudaMemcpy(out_aux, d_aux, n*16, cudaMemcpyDeviceToHost));

@@ -38,6 +38,7 @@ struct MaterialsDev
   const cb_material_t *mat;
   const TableDev *tables;
   const float *table_data;
+  const cb_medium_t *media;   // homogeneous media (cb_material_t.medium / cb_render_desc_t.exterior_medium are 1 + index)
 };
 
 struct LightsDev   // src/lights.d/list.c
@@ -60,34 +61,60 @@ struct Vtx
   float ior;         // interior.ior of the shape's material (vacuum 1)
   float eta;         // cached path_eta_ratio
   int32_t mat;
+  float vol_mu_s, vol_g;   // volume vertices: interior.mu_s / mean_cos of the medium the vertex sits in
 };
 
-// media the path is currently inside of (nested dielectrics): the incremental form of _path_edge_medium
+// media the path is currently inside of (nested dielectrics / participating media): the incremental form of _path_edge_medium
 #define MED_MAX 4
 struct Media
 {
   uint32_t shape[MED_MAX];
   float ior[MED_MAX];
   int n;
+  uint32_t ids;      // 6 bits per entry: 1 + index of the entry's homogeneous medium (0 = none)
 };
+// PathState packs {n, ids} into one word: bits 0..2 n, bits 8+6k..13+6k the medium of entry k
+CBD void media_unpack(Media &m, int32_t word) { m.n = word & 7; m.ids = (uint32_t)word >> 8; }
+CBD int32_t media_pack(const Media &m) { return (int32_t)((uint32_t)m.n | (m.ids << 8)); }
+CBD uint32_t media_id(const Media &m, int k) { return (m.ids >> (6*k)) & 63u; }
+CBD void media_set_id(Media &m, int k, uint32_t id) { m.ids = (m.ids & ~(63u << (6*k))) | (id << (6*k)); }
+// highest priority = smallest shape id; empty = global exterior (pathspace.c:107-113).  Returns the entry or -1.
+CBD int media_top(const Media &m)
+{
+  int top = -1;
+  uint32_t best = 0xffffffffu;
+  for(int i=0;i<m.n;i++) if(m.shape[i] < best) { best = m.shape[i]; top = i; }
+  return top;
+}
 CBD float media_ior(const Media &m)
-{ // highest priority = smallest shape id; empty = global exterior (vacuum)
+{
   float ior = 1.0f;
   uint32_t best = 0xffffffffu;
   for(int i=0;i<m.n;i++) if(m.shape[i] < best) { best = m.shape[i]; ior = m.ior[i]; }
   return ior;
 }
+// 1 + index of the medium the current edge runs through (0 = vacuum)
+CBD uint32_t media_medium(const Media &m, uint32_t exterior)
+{
+  const int top = media_top(m);
+  return top < 0 ? exterior : media_id(m, top);
+}
 // cross the interface of `shape`: returns false on broken nesting
-CBD bool media_transmit(Media &m, uint32_t shape, float ior, bool inside)
+CBD bool media_transmit(Media &m, uint32_t shape, float ior, bool inside, uint32_t medium = 0)
 {
   if(!inside)
   {
     if(m.n >= MED_MAX) return false;
-    m.shape[m.n] = shape; m.ior[m.n] = ior; m.n++;
+    m.shape[m.n] = shape; m.ior[m.n] = ior; media_set_id(m, m.n, medium); m.n++;
     return true;
   }
   for(int i=m.n-1;i>=0;i--)
-    if(m.shape[i] == shape) { m.shape[i] = m.shape[m.n-1]; m.ior[i] = m.ior[m.n-1]; m.n--; return true; }
+    if(m.shape[i] == shape)
+    {
+      m.shape[i] = m.shape[m.n-1]; m.ior[i] = m.ior[m.n-1]; media_set_id(m, i, media_id(m, m.n-1));
+      m.n--;
+      return true;
+    }
   return false;
 }
 // path_eta_ratio: n1/n2 with n2 on the other side of vertex v; < 0 on broken nesting
@@ -271,6 +298,58 @@ CBD float rgb2spec_eval(const float *c, float lambda)   // include/rgb2spec.h:14
   return fmaf(0.5f*x, y, 0.5f);
 }
 CBD float clamp01(float x) { return fminf(fmaxf(x, 0.0f), 1.0f); }
+
+// ---- homogeneous media ------------------------------------------------------------------------
+// vertex_volume_t of a medium at one wavelength: what `color v` (texture.h:46-52: mu_s <- clamp(albedo), mu_t <- 1) followed by
+// medium_rgb's prepare() (medium_rgb.c:46-60: mu_t <- mul*rgb2spec, mu_s *= mu_t/old mu_t) leave in vertex.interior.
+// Without a `color v` the old mu_t is vacuum's 0 and mu_s becomes NaN like upstream: such a medium only absorbs.
+struct Vol { float mu_t, mu_s, g; bool present; };
+CBD Vol medium_eval(const MaterialsDev &M, uint32_t medium, float lambda)
+{
+  Vol v; v.present = medium > 0; v.mu_t = v.mu_s = v.g = 0.0f;   // path_volume_vacuum (pathspace.h:348-353)
+  if(medium > 0)
+  {
+    const cb_medium_t &m = M.media[medium - 1];
+    float mu_s = 0.0f, old_mu_t = 0.0f;
+    if(m.has_albedo) { mu_s = clamp01(m.albedo_mul*rgb2spec_eval(m.albedo_coeff, lambda)); old_mu_t = 1.0f; }
+    v.mu_t = m.mu_t_mul*rgb2spec_eval(m.mu_t_coeff, lambda);
+    v.mu_s = mu_s*(v.mu_t/old_mu_t);
+    v.g = m.g;
+  }
+  return v;
+}
+// shader_vol_sample's free-flight distance in a scattering medium (shader.c:96-99)
+CBD float vol_free_flight(const Vol &v, float rf)
+{
+  float dist = -logf(1.0f - rf)/v.mu_t;
+  if(!(dist > 0.0f)) dist = 1e-15f;
+  return dist;
+}
+// Henyey-Greenstein: sample_eval_hg / sample_hg (sampler_common.h:286-316,338-356); out[0] is along the incoming direction
+CBD float hg_eval(float g, V3 wi, V3 wo)
+{
+  if(g == 0.0f) return (float)(1.0/(4.0*PI_D));
+  const float cos_theta = dot(wi, wo);
+  return (float)(1.0/(4.0*PI_D)*(double)(1.0f - g*g)/(double)powf(1.0f + g*g - 2.0f*g*cos_theta, 3.0f/2.0f));
+}
+CBD void hg_sample(float g, float r1, float r2, float *out, float &pdf)
+{
+  if(g == 0.0f)
+  { // sample_sphere (sampler_common.h:136-143)
+    out[2] = 1.f - 2.f*r1;
+    const float r = sqrtf(1.f - out[2]*out[2]);
+    const float phi = (float)(2.0*PI_D*(double)r2);
+    out[0] = r*cosf(phi); out[1] = r*sinf(phi);
+    pdf = (float)(1.0/(4.0*PI_D));
+    return;
+  }
+  const float sqr = (1.0f - g*g)/(1.0f + g*(2.0f*r1 - 1.0f));
+  const float cos_theta = 1.0f/(2.0f*g)*(1.0f + g*g - sqr*sqr);
+  const float phi = (float)(2.0*PI_D*(double)r2);
+  const float l = sqrtf(fmaxf(0.0f, 1.0f - cos_theta*cos_theta));
+  out[0] = cos_theta; out[1] = cosf(phi)*l; out[2] = sinf(phi)*l;
+  pdf = (float)(1.0/(4.0*PI_D)*(double)(1.0f - g*g)/(double)powf(1.0f + g*g - 2.0f*g*cos_theta, 3.0f/2.0f));
+}
 CBD float table_lookup(const MaterialsDev &M, int table, int row, float lambda, bool clamp_index)
 {
   const TableDev t = M.tables[table];
@@ -289,7 +368,7 @@ CBD void set_slot(Vtx &v, int slot, float data)   // texture.h:38-64 (sensor pat
     case CB_SLOT_ROUGHNESS: v.roughness = data; return;
     case CB_SLOT_EMISSION:  v.em = data; return;
     case CB_SLOT_TRANSMIT_TO_EYE: if(!(v.flags & F_INSIDE)) v.rg = data; return;
-    default: return;   // volume slot: media are outside the pt/ptdl surface path
+    default: return;   // volume slot: part of a medium's chain (cb_medium_t), never of a surface material
   }
 }
 CBD float dielectric_ior(float n_d, float V_d, float lambda)   // spectrum.h:40-63
@@ -347,6 +426,9 @@ CBD void prepare_vertex(const SceneGeo &S, const MaterialsDev &M, Vtx &v, V3 ome
   v.roughness = 1.0f;
   v.ior = 1.0f;
   const cb_material_t &m = M.mat[v.mat];
+  // `interior`: the medium's chain runs first and its `color v` announces a volume lobe (interior.c:113-118, texture.h:46-52);
+  // the surface bsdf's prepare() normally replaces it
+  if(m.medium > 0 && M.media[m.medium - 1].has_albedo) v.material_modes = M_VOLUME | M_GLOSSY;
   for(int k=0;k<m.num_ops;k++)
   {
     const cb_matop_t &op = m.ops[k];

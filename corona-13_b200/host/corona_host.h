@@ -101,6 +101,8 @@ struct scene_b200_t;
 struct scene_b200_t *scene_b200_open(const char *nra2_file, const char *coeff_file, const char *table_file);   /* no GPU needed */
 void scene_b200_free(struct scene_b200_t *s);
 const cb_material_t *scene_b200_materials(const struct scene_b200_t *s, int *num);
+/* the homogeneous media the shader list defines (cb_material_t.medium / *exterior are 1 + index, 0 = vacuum) */
+const cb_medium_t *scene_b200_media(const struct scene_b200_t *s, int *num, int *exterior);
 const char *scene_b200_basename(const struct scene_b200_t *s);
 uint64_t scene_b200_num_prims(const struct scene_b200_t *s);
 int scene_b200_read_camera(const char *filename, uint32_t width, uint32_t height, cb_camera_t *out);

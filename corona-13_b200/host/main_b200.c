@@ -62,6 +62,16 @@ int main(int argc, char *argv[])
     FILE *f = fopen(dump, "wb");
     if(!f || fwrite(m, sizeof(cb_material_t), n, f) != (size_t)n) { fprintf(stderr, "[main] could not write %s\n", dump); return 2; }
     fclose(f);
+    int32_t nm[2] = {0, 0};
+    const cb_medium_t *med = scene_b200_media(s, nm, nm + 1);
+    if(nm[0] || nm[1])
+    { /* <file>.media: count, exterior medium, cb_medium_t[] */
+      char name[1100];
+      snprintf(name, sizeof(name), "%s.media", dump);
+      f = fopen(name, "wb");
+      if(!f || fwrite(nm, sizeof(nm), 1, f) != 1 || fwrite(med, sizeof(cb_medium_t), nm[0], f) != (size_t)nm[0]) { fprintf(stderr, "[main] could not write %s\n", name); return 2; }
+      fclose(f);
+    }
     if(!spp) { scene_b200_free(s); return 0; }
   }
   if(!quiet) { accel_print_info(stdout); render_print_info(stdout); }

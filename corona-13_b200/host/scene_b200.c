@@ -133,6 +133,11 @@ typedef struct nra2_t
   cb_table_t used[MAX_SHADERS];
   int used_src[MAX_SHADERS];
   int num_used;
+  /* homogeneous media, in cb_render_desc_t order; medium_of[k] = 1 + index for shader k once flattened */
+  cb_medium_t media[CB_MAX_MEDIA];
+  int medium_of[MAX_SHADERS];
+  int num_media;
+  int exterior_medium;
 }
 nra2_t;
 
@@ -217,7 +222,51 @@ static int flatten(nra2_t *n, int k, cb_material_t *m, int *have_bsdf, int depth
     for(int i=0;i<cnt;i++) { int hb = 0; if(flatten(n, idx[i], m, &hb, depth+1)) return 1; }
     return flatten(n, idx[cnt], m, have_bsdf, depth+1);
   }
-  return 1;   /* medium_rgb, skies, hair, ...: SURVEY 2.1 marks them outside the hot path */
+  return 1;   /* skies, hair, heterogeneous media, ...: SURVEY 2.1 marks them outside the hot path */
+}
+
+/* shader k as a homogeneous medium: `medium_rgb r g b g` (src/shaders/medium_rgb.c:112-139) or a mult whose pre steps are
+ * `color v` and whose host is one.  Returns 1 + index into n->media, 0 when k is something else. */
+static int flatten_medium(nra2_t *n, int k)
+{
+  if(k < 0 || k >= n->num_shaders) return 0;
+  if(n->medium_of[k]) return n->medium_of[k];
+  const shader_line_t *l = n->line + k;
+  cb_medium_t m;
+  memset(&m, 0, sizeof(m));
+  int host = k;
+  if(!strcmp(l->name, "mult"))
+  {
+    int cnt = 0, pos = 0, adv = 0, idx[17];
+    if(sscanf(l->args, " %d%n", &cnt, &adv) < 1 || cnt < 0 || cnt > 16) return 0;
+    pos = adv;
+    for(int i=0;i<=cnt;i++)
+    {
+      if(sscanf(l->args + pos, " %d%n", idx + i, &adv) < 1) return 0;
+      pos += adv;
+      if(idx[i] < 0) idx[i] += k;
+      if(idx[i] < 0 || idx[i] >= n->num_shaders) return 0;
+    }
+    for(int i=0;i<cnt;i++)
+    {
+      const shader_line_t *p = n->line + idx[i];
+      char c; float col[3];
+      if(strcmp(p->name, "color") || sscanf(p->args, " %c %f %f %f", &c, col, col+1, col+2) < 4 || c != 'v') return 0;
+      m.has_albedo = 1;
+      m.albedo_mul = rgb_to_coeff(n->rgb2spec, col, m.albedo_coeff);
+    }
+    host = idx[cnt];
+  }
+  const shader_line_t *h = n->line + host;
+  float mfp[3], g = 0.0f;
+  if(strcmp(h->name, "medium_rgb") || sscanf(h->args, " %f %f %f %f", mfp, mfp+1, mfp+2, &g) != 4) return 0;
+  float mu_t[3];
+  for(int i=0;i<3;i++) mu_t[i] = 1.0f/mfp[i];   /* mean free path -> collision coefficient */
+  m.mu_t_mul = rgb_to_coeff(n->rgb2spec, mu_t, m.mu_t_coeff);
+  m.g = g;
+  if(n->num_media >= CB_MAX_MEDIA) return 0;
+  n->media[n->num_media++] = m;
+  return n->medium_of[k] = n->num_media;
 }
 
 /* ---------------------------------------------------------------------------------------------- camera */
@@ -383,6 +432,31 @@ struct scene_b200_t *scene_b200_open(const char *nra2_file, const char *coeff_fi
     cb_material_t *m = s->materials + k;
     int have_bsdf = 0;
     m->table = -1;
+    const shader_line_t *l = s->nra2->line + k;
+    if(!strcmp(l->name, "exterior"))
+    { /* src/shader.c:699-716: "<medium shader> [volume light]"; the line itself is no material */
+      int id = -1, light = 0;
+      sscanf(l->args, " %d %d", &id, &light);
+      if(light) { fprintf(stderr, "[scene b200] volume lights are not supported by the gpu path; no cpu fallback\n"); fclose(f); scene_b200_free(s); return 0; }
+      if(id >= 0 && !(s->nra2->exterior_medium = flatten_medium(s->nra2, id)))
+      { fprintf(stderr, "[scene b200] exterior medium %d is not a homogeneous medium_rgb chain; no cpu fallback\n", id); fclose(f); scene_b200_free(s); return 0; }
+      m->num_ops = -1; m->bsdf = -1;
+      continue;
+    }
+    if(!strcmp(l->name, "interior"))
+    { /* src/shaders/interior.c:53-72: "<surface id> <interior id>", negative = relative */
+      int surf = 0, inner = 0, medium = 0;
+      if(sscanf(l->args, " %d %d", &surf, &inner) == 2)
+      {
+        if(surf < 0) surf += k;
+        if(inner < 0) inner += k;
+        medium = flatten_medium(s->nra2, inner);
+      }
+      if(!medium || flatten(s->nra2, surf, m, &have_bsdf, 0)) { memset(m, 0, sizeof(*m)); m->num_ops = -1; m->bsdf = -1; continue; }
+      if(!have_bsdf) m->bsdf = CB_BSDF_DIFFUSE;
+      m->medium = medium;
+      continue;
+    }
     if(flatten(s->nra2, k, m, &have_bsdf, 0)) { memset(m, 0, sizeof(*m)); m->num_ops = -1; m->bsdf = -1; continue; }
     if(!have_bsdf) m->bsdf = CB_BSDF_DIFFUSE;   /* a prepare-only shader on a shape gets the default diffuse callbacks (shader.c:761-787) */
   }
@@ -413,6 +487,8 @@ struct scene_b200_t *scene_b200_open(const char *nra2_file, const char *coeff_fi
 }
 
 const cb_material_t *scene_b200_materials(const struct scene_b200_t *s, int *num) { if(num) *num = s->nra2->num_shaders; return s->materials; }
+const cb_medium_t *scene_b200_media(const struct scene_b200_t *s, int *num, int *exterior)
+{ if(num) *num = s->nra2->num_media; if(exterior) *exterior = s->nra2->exterior_medium; return s->nra2->media; }
 const char *scene_b200_basename(const struct scene_b200_t *s) { return s->basename; }
 uint64_t scene_b200_num_prims(const struct scene_b200_t *s) { return s->prims.num_prims; }
 
@@ -439,6 +515,7 @@ int scene_b200_prepare(struct scene_b200_t *s, uint32_t width, uint32_t height, 
   d->sky = s->sky;
   for(int k=0;k<3;k++) d->sky_coeff[k] = s->sky_coeff[k];
   d->sky_scale = s->sky_scale;
+  d->media = s->nra2->media; d->num_media = s->nra2->num_media; d->exterior_medium = s->nra2->exterior_medium;
   d->max_path_len = 32; d->frame = frame; d->rank = 0; d->world = 1; d->batch_paths = 0;
   s->render = render_b200_init(s->accel, d);
   return s->render ? 0 : 1;

@@ -247,13 +247,14 @@ def _load_render():
     L.cb200_render_point.argtypes = [vp, vp, vp, vp, u64]
     L.cb200_render_camera_rays.argtypes = [vp, u64, u64, vp, vp]
     L.cb200_render_bsdf.argtypes = [vp, C.c_int32, vp, vp, u64]
+    L.cb200_render_medium.argtypes = [vp, C.c_int32, vp, vp, u64]
     L._render_ready = True
     return L
 
 
 RENDER_SYMBOLS = ["cb200_render_create", "cb200_render_destroy", "cb200_render_pass", "cb200_render_pass_stream", "cb200_render_flush", "cb200_render_clear", "cb200_render_instrument",
                   "cb200_render_fb_device", "cb200_render_set_framebuffer", "cb200_render_download", "cb200_render_snapshot", "cb200_render_stats", "cb200_render_point",
-                  "cb200_render_camera_rays", "cb200_render_bsdf"]
+                  "cb200_render_camera_rays", "cb200_render_bsdf", "cb200_render_medium"]
 
 
 class Render:
@@ -280,6 +281,10 @@ class Render:
         d.sky = sky
         d.sky_coeff[:] = [float(x) for x in sky_coeff]
         d.sky_scale = float(sky_scale)
+        self._media = materials.cmedia()
+        d.media = C.cast(self._media, C.c_void_p)
+        d.num_media = len(materials.media)
+        d.exterior_medium = materials.exterior_medium
         self.desc = d
         self.r = _nonnull(self.L.cb200_render_create(accel.a, C.byref(d)), "cb200_render_create")
         self.spp = 0
@@ -344,6 +349,15 @@ class Render:
         q = np.ascontiguousarray(queries, sio.BSDF_QUERY)
         out = np.zeros(len(q), sio.BSDF_RESULT)
         _check(self.L.cb200_render_bsdf(self.r, material, _ptr(q), _ptr(out), len(q)), "cb200_render_bsdf")
+        return out
+
+    def medium(self, medium, queries):
+        """free flight, edge terms and phase function of medium `medium` (index into the material set's media):
+        scene_io.MEDIUM_QUERY[] -> MEDIUM_RESULT[]"""
+        from . import scene_io as sio
+        q = np.ascontiguousarray(queries, sio.MEDIUM_QUERY)
+        out = np.zeros(len(q), sio.MEDIUM_RESULT)
+        _check(self.L.cb200_render_medium(self.r, medium, _ptr(q), _ptr(out), len(q)), "cb200_render_medium")
         return out
 
     def camera_rays(self, first, n):

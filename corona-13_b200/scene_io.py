@@ -40,8 +40,13 @@ class CMatOp(C.Structure):
 
 
 class CMaterial(C.Structure):
-    _fields_ = [("num_ops", C.c_int32), ("bsdf", C.c_int32), ("param", C.c_float * 4), ("table", C.c_int32), ("pad", C.c_int32),
+    _fields_ = [("num_ops", C.c_int32), ("bsdf", C.c_int32), ("param", C.c_float * 4), ("table", C.c_int32), ("medium", C.c_int32),
                 ("ops", CMatOp * CB_MAX_MATOPS)]
+
+
+class CMedium(C.Structure):
+    _fields_ = [("mu_t_coeff", C.c_float * 3), ("mu_t_mul", C.c_float), ("g", C.c_float), ("has_albedo", C.c_int32),
+                ("albedo_coeff", C.c_float * 3), ("albedo_mul", C.c_float)]
 
 
 class CTable(C.Structure):
@@ -55,7 +60,8 @@ class CRenderDesc(C.Structure):
                 ("tables", C.c_void_p), ("num_tables", C.c_int32),
                 ("sampler", C.c_int32), ("pointsampler", C.c_int32), ("colour_camera", C.c_int32), ("max_path_len", C.c_int32),
                 ("frame", C.c_uint64), ("rank", C.c_uint32), ("world", C.c_uint32), ("batch_paths", C.c_uint64),
-                ("sky", C.c_int32), ("sky_coeff", C.c_float * 3), ("sky_scale", C.c_float), ("pad", C.c_int32)]
+                ("sky", C.c_int32), ("sky_coeff", C.c_float * 3), ("sky_scale", C.c_float), ("exterior_medium", C.c_int32),
+                ("media", C.c_void_p), ("num_media", C.c_int32), ("pad", C.c_int32)]
 
 
 class CRenderStats(C.Structure):
@@ -68,6 +74,10 @@ BSDF_QUERY = np.dtype([("wi", "<f4", 3), ("wo", "<f4", 3), ("lambda_", "<f4"), (
                        ("rg", "<f4"), ("roughness", "<f4"), ("flip", "<i4")])
 BSDF_RESULT = np.dtype([("s_wo", "<f4", 3), ("s_weight", "<f4"), ("s_pdf", "<f4"), ("s_mode", "<u4"), ("f", "<f4"), ("f_mode", "<u4"),
                         ("pdf", "<f4")])
+MEDIUM_QUERY = np.dtype([("wi", "<f4", 3), ("wo", "<f4", 3), ("lambda_", "<f4"), ("rand", "<f4", 3), ("dist", "<f4")])
+MEDIUM_RESULT = np.dtype([("mu_t", "<f4"), ("mu_s", "<f4"), ("free_dist", "<f4"), ("free_pdf", "<f4"), ("transmittance", "<f4"),
+                          ("vol_pdf", "<f4"), ("s_wo", "<f4", 3), ("s_weight", "<f4"), ("s_pdf", "<f4"), ("s_mode", "<u4"), ("f", "<f4"),
+                          ("f_mode", "<u4"), ("pdf", "<f4")])
 
 
 # ----------------------------------------------------------------------------------------------- camera
@@ -243,6 +253,8 @@ class MaterialSet:
         self.materials = []   # CMaterial
         self.tables = []      # (lambda_min, step, np.ndarray rows x num)
         self.text = []        # the .nra2 shader lines this set corresponds to
+        self.media = []       # CMedium; CMaterial.medium / exterior_medium are 1 + index
+        self.exterior_medium = 0
 
     def add_table(self, lambda_min, step, data):
         self.tables.append((float(lambda_min), float(step), np.ascontiguousarray(data, np.float32)))
@@ -257,11 +269,16 @@ class MaterialSet:
             tabs[i].data = d.ctypes.data
         return mats, tabs
 
+    def cmedia(self):
+        return (CMedium * max(1, len(self.media)))(*self.media)
+
 
 def parse_nra2(path, rgb2spec, checker_table=None, metal_tables=None):
     """shader list of a .nra2 -> (MaterialSet indexed by shader number, [(shader index, geo path)], sky).
     Mirrors shader_init (src/shader.c:605-788): every line is one shader; `mult n pre... host` is flattened
-    (src/shaders/mult.c:90-128,154-167).  Shader kinds outside the hot path raise (no fallback)."""
+    (src/shaders/mult.c:90-128,154-167); a chain that ends in `medium_rgb` becomes a CMedium, `interior s m` attaches it to
+    surface s (src/shaders/interior.c), `exterior id` makes it the camera's medium (src/shader.c:699-716).
+    Shader kinds outside the hot path raise (no fallback)."""
     lines = [l.split("#")[0].strip() for l in open(path).read().split("\n")]
     sky = lines[0].split()[0]
     n = int(lines[1].split()[0])
@@ -269,6 +286,42 @@ def parse_nra2(path, rgb2spec, checker_table=None, metal_tables=None):
     ms = MaterialSet()
     ms.text = [" ".join(r) for r in raw]
     chk = None
+    medium_of = {}    # shader index -> 1 + index into ms.media
+
+    def medium_index(i):
+        """shader i as a homogeneous medium: `medium_rgb` itself or a mult of `color v` steps ending in one"""
+        if i in medium_of:
+            return medium_of[i]
+        r = raw[i]
+        albedo = None
+        host = i
+        if r[0] == "mult":
+            k = int(r[1])
+            pre = [int(x) for x in r[2:2 + k]]
+            host = int(r[2 + k])
+            pre = [i + q if q < 0 else q for q in pre]
+            host = i + host if host < 0 else host
+            for q in pre:
+                if raw[q][0] != "color" or raw[q][1] != "v":
+                    raise ValueError("only `color v' steps may precede a medium")
+                albedo = rgb2spec.rgb_to_coeff([float(raw[q][2]), float(raw[q][3]), float(raw[q][4])])
+        if raw[host][0] != "medium_rgb":
+            raise ValueError(f"shader {i} is not a homogeneous medium")
+        h = raw[host]
+        with np.errstate(divide="ignore"):
+            mu_t = (np.float32(1.0) / np.array([float(h[1]), float(h[2]), float(h[3])], np.float32)).astype(np.float32)   # medium_rgb.c:127-128
+        mul, co = rgb2spec.rgb_to_coeff(mu_t)
+        m = CMedium()
+        m.mu_t_coeff[:] = [float(x) for x in co]
+        m.mu_t_mul = float(mul)
+        m.g = float(h[4])
+        if albedo is not None:
+            m.has_albedo = 1
+            m.albedo_mul = float(albedo[0])
+            m.albedo_coeff[:] = [float(x) for x in albedo[1]]
+        ms.media.append(m)
+        medium_of[i] = len(ms.media)
+        return medium_of[i]
 
     def op_of(i):
         """prepare() steps shader i contributes, and its bsdf if it has one"""
@@ -317,8 +370,22 @@ def parse_nra2(path, rgb2spec, checker_table=None, metal_tables=None):
 
     for i in range(n):
         m = CMaterial()
+        medium = 0
         try:
-            ops, bsdf = op_of(i)
+            if raw[i][0] == "exterior":
+                eid = int(raw[i][1])
+                if len(raw[i]) > 2 and int(raw[i][2]):
+                    raise ValueError("volume lights are outside the hot path")
+                ms.exterior_medium = medium_index(eid) if eid >= 0 else 0
+                raise ValueError("not a surface")
+            if raw[i][0] == "interior":
+                surf, inner = int(raw[i][1]), int(raw[i][2])
+                surf = i + surf if surf < 0 else surf
+                inner = i + inner if inner < 0 else inner
+                medium = medium_index(inner)
+                ops, bsdf = op_of(surf)
+            else:
+                ops, bsdf = op_of(i)
         except ValueError:
             m.num_ops, m.bsdf = -1, -1     # not usable as a shape material; rejected by cb200_render_create if referenced
             ms.materials.append(m)
@@ -331,6 +398,7 @@ def parse_nra2(path, rgb2spec, checker_table=None, metal_tables=None):
         m.bsdf = bsdf[0]
         m.param[:] = bsdf[1]
         m.table = bsdf[2]
+        m.medium = medium
         ms.materials.append(m)
     ns = int(lines[2 + n].split()[0])
     shapes = []

@@ -10,8 +10,8 @@
  * include/filter/blackmanharris.h:43-77).
  *
  * The scene description arrives flattened: the host layer (or a test) walks the reference's shader list
- * (`.nra2`: mult / color / colorcheckersg / dielectric / metal / diffuse) once at load time and hands over one
- * cb_material_t per shader index a shape may reference.  Unknown shader kinds are a hard error upstream --
+ * (`.nra2`: mult / color / colorcheckersg / dielectric / metal / diffuse / interior / medium_rgb / exterior) once at
+ * load time and hands over one cb_material_t per shader index a shape may reference.  Unknown shader kinds are a hard error upstream --
  * there is no CPU fallback.
  */
 #ifndef CORONA_B200_RENDER_H
@@ -78,10 +78,27 @@ typedef struct cb_material_t
   int32_t bsdf;
   float param[4];                /* dielectric: n_d, abbe */
   int32_t table;                 /* metal: index of its (n,k) table */
-  int32_t pad;
+  int32_t medium;                /* `interior <surface> <medium>` (src/shaders/interior.c): 1 + index into cb_render_desc_t.media of
+                                    the homogeneous medium behind this surface, 0 = vacuum */
   cb_matop_t ops[CB_MAX_MATOPS];
 }
 cb_material_t;
+
+/* homogeneous participating medium = the reference's `mult 1 <color v ...> <medium_rgb ...>` chain flattened
+ * (src/shaders/medium_rgb.c:46-60,112-139, src/shaders/texture.h:46-52): mu_t(lambda) = mu_t_mul * rgb2spec(mu_t_coeff),
+ * single-scattering albedo from the `color v` step (mu_s = albedo * mu_t; without one the medium only absorbs),
+ * Henyey-Greenstein phase function with mean cosine g. */
+#define CB_MAX_MEDIA 63
+typedef struct cb_medium_t
+{
+  float mu_t_coeff[3];
+  float mu_t_mul;
+  float g;
+  int32_t has_albedo;
+  float albedo_coeff[3];
+  float albedo_mul;
+}
+cb_medium_t;
 
 /* ---- render description ---------------------------------------------------------------------------------- */
 enum { CB_SAMPLER_PT = 0, CB_SAMPLER_PTDL = 1 };          /* src/sampler.d/pt.c, ptdl.c */
@@ -108,6 +125,10 @@ typedef struct cb_render_desc_t
   int32_t sky;                   /* CB_SKY_* */
   float sky_coeff[3];            /* CB_SKY_CONST: rgb2spec coefficients of the colour and scale * mul (sky_const.c:89-101) */
   float sky_scale;
+  int32_t exterior_medium;       /* `exterior <id>` (src/shader.c:544-566,699-716): 1 + index into media of the medium the camera
+                                    sits in, 0 = vacuum */
+  const cb_medium_t *media;
+  int32_t num_media;
   int32_t pad;
 }
 cb_render_desc_t;
@@ -188,6 +209,33 @@ typedef struct cb_bsdf_result_t
 }
 cb_bsdf_result_t;
 int  cb200_render_bsdf(cb200_render_t *r, int32_t material, const cb_bsdf_query_t *queries, cb_bsdf_result_t *results, uint64_t n);
+
+/* The same for a homogeneous medium (index into cb_render_desc_t.media), evaluated the way the integrator's kernels do: the
+ * medium's coefficients at lambda (medium_rgb.c:46-60 behind its `color v`), the sampled free-flight distance and its pdf for
+ * rand[2] (shader_vol_sample, src/shader.c:76-104), transmittance and distance pdf of an edge of length `dist` that ends on a
+ * volume vertex (shader.c:46-72,107-131), and the phase-function callbacks at that vertex (medium_rgb.c:62-103) with incoming
+ * direction wi, tangent frame scrambling 0.5, random dimensions rand[0..1] and outgoing direction wo for brdf()/pdf(). */
+typedef struct cb_medium_query_t
+{
+  float wi[3], wo[3];
+  float lambda;
+  float rand[3];                   /* s_dim_omega_x, s_dim_omega_y, s_dim_free_path */
+  float dist;
+}
+cb_medium_query_t;
+typedef struct cb_medium_result_t
+{
+  float mu_t, mu_s;
+  float free_dist, free_pdf;
+  float transmittance, vol_pdf;
+  float s_wo[3], s_weight, s_pdf;
+  uint32_t s_mode;
+  float f;
+  uint32_t f_mode;
+  float pdf;
+}
+cb_medium_result_t;
+int  cb200_render_medium(cb200_render_t *r, int32_t medium, const cb_medium_query_t *queries, cb_medium_result_t *results, uint64_t n);
 
 #ifdef __cplusplus
 }

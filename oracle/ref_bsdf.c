@@ -7,6 +7,8 @@
 #include "pathspace.h"
 #include "shader.h"
 #include "points.h"
+#include "spectrum.h"
+#include "pathspace/manifold.h"
 #include <dlfcn.h>
 #include <stdio.h>
 #include <string.h>
@@ -52,7 +54,7 @@ int ref_bsdf_open(const char *so_path, const char *init_line)
   s->pdf     = (pdf_t)dlsym(h, "pdf");
   s->prepare = (prepare_t)dlsym(h, "prepare");
   s->init    = (init_t)dlsym(h, "init");
-  if(!s->sample || !s->brdf || !s->pdf) return -1;
+  if((!s->sample || !s->brdf || !s->pdf) && !s->prepare) return -1;   /* prepare-only modules (color) are fine */
   if(s->init)
   {
     char line[1024];
@@ -108,5 +110,75 @@ void ref_bsdf_eval(int handle, const cb_bsdf_query_t *q, cb_bsdf_result_t *out, 
     out[i].f = s->brdf(&path, 1, s->data);
     out[i].f_mode = path.v[1].mode;
     out[i].pdf = s->pdf(&path, 1, 1, 2, s->data);
+  }
+}
+
+/* ---- homogeneous media: the reference's medium_rgb module behind an optional `color v' step, its free-flight sampling and
+ * edge terms (src/shader.c:46-131) and the phase function callbacks at a volume vertex (src/shaders/medium_rgb.c:62-103).
+ * coeff_file: the rgb2spec model `color' / `medium_rgb' fetch their coefficients from at init (src/main.c:292-293). */
+int ref_medium_setup(const char *coeff_file)
+{
+  if(!rt.rgb2spec) rt.rgb2spec = rgb2spec_init(coeff_file);
+  if(!rt.shader)
+  {
+    rt.shader = calloc(1, sizeof(shader_t));
+    rt.shader->shader = g_shader;
+    rt.shader->exterior_medium_shader = -1;
+  }
+  return rt.rgb2spec ? 0 : -1;
+}
+
+/* h_medium: handle of a medium_rgb, h_albedo: handle of the `color v ...' that precedes it in its mult chain, or -1 */
+void ref_medium_eval(int h_medium, int h_albedo, const cb_medium_query_t *q, cb_medium_result_t *out, uint64_t n)
+{
+  shader_so_t *s = g_shader + h_medium;
+  static path_t path;
+  rt.shader->num_shaders = g_num;
+  for(uint64_t i=0;i<n;i++)
+  {
+    const cb_medium_query_t *Q = q + i;
+    path_init(&path, 0, 0);
+    path.lambda = Q->lambda;
+    path.tangent_frame_scrambling = 0.5f;
+    path.v[0].hit.prim = INVALID_PRIMID;
+    path.v[0].mode = s_sensor;
+    path.v[1].hit.prim = INVALID_PRIMID;
+    /* what mult.prepare leaves in vertex.interior (mult.c:154-167): vacuum, pre steps, host */
+    path_volume_vacuum(&path.v[1].interior);
+    if(h_albedo >= 0) g_shader[h_albedo].prepare(&path, 1, g_shader[h_albedo].data);
+    s->prepare(&path, 1, s->data);
+    path.v[1].interior.shader = h_medium;
+    path.e[1].vol = path.v[1].interior;
+    out[i].mu_t = mf(path.e[1].vol.mu_t, 0);
+    out[i].mu_s = mf(path.e[1].vol.mu_s, 0);
+    for(int k=0;k<3;k++) path.e[1].omega[k] = Q->wi[k];
+    /* distance sampling of edge 1 as path_propagate does it (pathspace.c:742-747) */
+    path.length = 1;
+    g_rand[s_dim_free_path] = Q->rand[2];
+    path.e[1].dist = FLT_MAX;
+    out[i].free_dist = shader_vol_sample(&path, 1);
+    out[i].free_pdf = mf(path.e[1].pdf, 0);
+    /* an edge of length dist that ends on this volume vertex: transmittance and distance pdf (shader.c:46-72,107-131) */
+    path.e[1].dist = Q->dist;
+    out[i].transmittance = mf(shader_vol_transmittance(&path, 1), 0);
+    out[i].vol_pdf = mf(shader_vol_pdf(&path, 1), 0);
+    /* phase function at the volume vertex */
+    path.length = 2;
+    manifold_init(&path, 1);
+    path.v[1].material_modes = s_volume | s_glossy;
+    path.v[1].mode = s_absorb;
+    path.e[2].vol = path.e[1].vol;
+    path.v[2].pdf = 1.0f;
+    g_rand[s_dim_omega_x] = Q->rand[0]; g_rand[s_dim_omega_y] = Q->rand[1];
+    const vertex_t keep = path.v[1];
+    out[i].s_weight = mf(s->sample(&path, s->data), 0);
+    for(int k=0;k<3;k++) out[i].s_wo[k] = path.e[2].omega[k];
+    out[i].s_pdf = mf(path.v[2].pdf, 0);
+    out[i].s_mode = path.v[1].mode;
+    path.v[1] = keep;
+    for(int k=0;k<3;k++) path.e[2].omega[k] = Q->wo[k];
+    out[i].f = mf(s->brdf(&path, 1, s->data), 0);
+    out[i].f_mode = path.v[1].mode;
+    out[i].pdf = mf(s->pdf(&path, 1, 1, 2, s->data), 0);
   }
 }

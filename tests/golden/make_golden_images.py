@@ -67,6 +67,9 @@ def golden_case(name, scene, shader_lines, shape_mats, cam, w, h, spp, variants,
                 "spp": np.int64(spp), "shader_lines": np.array(shader_lines), "variants": np.array(list(variants)),
                 "cam": np.frombuffer(open(os.path.join(tmp, "test01.cam"), "rb").read(), np.uint8),
                 "num_tables": np.int64(len(ms.tables)), "sky": np.array(sky)}
+        if ms.media:
+            pack["media"] = np.frombuffer(bytes(ms.cmedia()), np.uint8)   # flattened cb_medium_t[]
+            pack["exterior_medium"] = np.int64(ms.exterior_medium)
         if sky.startswith("sky_const"):
             co, sc = IO.sky_const_params(IO.Rgb2Spec(IO.coeff_path(ROOT)), sky[len("sky_const"):])
             pack["sky_coeff"], pack["sky_scale"] = np.float32(co), np.float32(sc)
@@ -195,7 +198,73 @@ def case_sky(with_light, sky="cloudy", name=None):
                 ["ptdl_halton", "pt_halton", "ptdl_rand"], sky=sky)
 
 
-CASES = {"sky_const": lambda: case_sky(True, "sky_const 0.3 0.5 0.9 800", "sky_const"), "sky": lambda: case_sky(False), "sky_light": lambda: case_sky(True), "diffuse_static": case_diffuse_static, "c10": case_c10, "motion": case_motion, "glass_metal": case_glass_metal}
+def case_fog():
+    """the whole scene inside a forward-scattering homogeneous medium (`exterior`, medium_rgb + color v): free-flight sampling on
+    every edge, volume vertices with the Henyey-Greenstein phase function, transmittance on the next-event edges"""
+    terrain = S.terrain(1800, 5, material=0)
+    soup = S.soup(600, 6, rmin=0.3, rmax=1.0, material=0)
+    ball = S.analytic_shape("sphere", (1.5, -1.0, 4.0), 1.3, material=0)
+    light = S.quad_light((0.0, 0.0, 9.0), 1.2, 1)
+    lines = ["diffuse", "color d 0.5 0.55 0.4", "mult 1 1 0", "color d 0 0 0", "color e 6000 5500 5000 1.", "mult 2 3 4 0",
+             "color d 0.75 0.3 0.2", "mult 1 6 0",
+             "medium_rgb 9 12 16 0.6",        # 8 mean free paths per colour, mean cosine
+             "color v 0.95 0.95 0.9",         # 9 albedo
+             "mult 1 9 8",                    # 10 fog
+             "exterior 10 0"]                 # 11
+    cam = IO.Camera(pos=(13.0, 10.0, 8.0), lookat=(0.0, 0.0, 3.0), aperture_value=7, exposure_value=14, focal_length=0.35, iso=100.0)
+    golden_case("fog", S.Scene([terrain, soup, ball, light], "fog"), lines, [2, 7, 7, 5], cam, 160, 96, 128,
+                ["ptdl_halton", "pt_halton", "ptdl_rand"])
+
+
+def case_subsurf():
+    """media behind dielectric interfaces (`interior`): a rough-glass ball and a smooth icosphere mesh filled with coloured
+    scattering media, an overlapping pair (nested media: the smaller shape id wins, pathspace.c:107-113), an index-matched
+    absorbing-only medium (no `color v`), all on a colour-checker floor"""
+    g = 8
+    xs = np.linspace(-8, 8, g + 1, dtype=np.float32)
+    X, Y = np.meshgrid(xs, xs, indexing="ij")
+    pos = np.stack([X, Y, np.zeros_like(X)], -1).reshape(-1, 3)
+    i, j = np.meshgrid(np.arange(g), np.arange(g), indexing="ij")
+    v00 = (i * (g + 1) + j).reshape(-1)
+    uv = np.stack([(X / 16 + 0.5).reshape(-1), (Y / 16 + 0.5).reshape(-1)], -1) * 0.999 + 0.0005
+    floor = S.mesh_shape(pos, np.stack([v00, v00 + g + 1, v00 + g + 2, v00 + 1], -1), 0, None, "floor", uv=uv)
+    iv, itri = S._icosahedron()
+    ctr = np.float32([[0.0, 0.0, 1.3], [3.0, -1.6, 1.5]])       # the second one intersects the analytic ball below
+    rad = np.float32([1.3, 1.1])
+    milk_mesh = S.mesh_shape((ctr[:, None, :] + rad[:, None, None] * iv[None]).reshape(-1, 3),
+                             (itri[None] + 12 * np.arange(2)[:, None, None]).reshape(-1, 3), 0, None, "milk_mesh")
+    skin_ball = S.analytic_shape("sphere", (3.0, -3.0, 1.5), 1.5, material=0)
+    ink_ball = S.analytic_shape("sphere", (-3.5, 3.0, 1.2), 1.2, material=0)
+    light = S.quad_light((0.0, 0.0, 8.0), 3.0, 1)
+    lines = ["diffuse",                       # 0
+             "colorcheckersg d",              # 1
+             "mult 1 1 0",                    # 2 floor
+             "color d 0 0 0",                 # 3
+             "color e 40 40 40 1.",           # 4
+             "mult 2 3 4 0",                  # 5 light
+             "dielectric 1.33 40",            # 6
+             "color g 1 1 1 0.0",             # 7
+             "mult 1 7 6",                    # 8 smooth interface
+             "color g 1 1 1 0.15",            # 9
+             "mult 1 9 6",                    # 10 rough interface
+             "medium_rgb 0.5 0.35 0.25 0.0",  # 11 milk: isotropic
+             "color v 0.98 0.96 0.9",         # 12
+             "mult 1 12 11",                  # 13
+             "medium_rgb 0.3 0.12 0.08 0.7",  # 14 skin: forward scattering
+             "color v 0.95 0.8 0.7",          # 15
+             "mult 1 15 14",                  # 16
+             "medium_rgb 4 1.5 0.8 0.0",      # 17 ink: absorbs only (no colour v)
+             "dielectric 1.0 0",              # 18 index-matched boundary
+             "mult 1 7 18",                   # 19
+             "interior 8 13",                 # 20 milk mesh
+             "interior 10 16",                # 21 skin ball
+             "interior 19 17"]                # 22 ink ball
+    cam = IO.Camera(pos=(12.0, -9.0, 8.0), lookat=(0.0, 0.0, 1.2), aperture_value=6, exposure_value=13, focal_length=0.4, iso=400.0)
+    golden_case("subsurf", S.Scene([floor, milk_mesh, skin_ball, ink_ball, light], "subsurf"), lines,
+                [2, 20, 21, 22, 5], cam, 192, 128, 128, ["pt_halton", "ptdl_halton", "ptdl_rand"])
+
+
+CASES = {"fog": case_fog, "subsurf": case_subsurf, "sky_const": lambda: case_sky(True, "sky_const 0.3 0.5 0.9 800", "sky_const"), "sky": lambda: case_sky(False), "sky_light": lambda: case_sky(True), "diffuse_static": case_diffuse_static, "c10": case_c10, "motion": case_motion, "glass_metal": case_glass_metal}
 
 if __name__ == "__main__":
     subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "oracle"), "ref"])

@@ -169,6 +169,12 @@ class GoldenImage:
         for i in range(int(z["num_tables"])):
             lmin, step = z[f"tab{i}_meta"]
             self.materials.add_table(lmin, step, z[f"tab{i}_data"])
+        if "media" in z.files:
+            rawm = z["media"].tobytes()
+            nm = len(rawm) // C.sizeof(IO.CMedium)
+            arrm = (IO.CMedium * nm).from_buffer_copy(rawm)
+            self.materials.media = [arrm[i] for i in range(nm)]
+            self.materials.exterior_medium = int(z["exterior_medium"])
         self.sky = str(z["sky"]) if "sky" in z.files else "black"
         self.sky_args = dict(sky=cb.scene_io.SKIES[self.sky.split()[0]])
         if "sky_coeff" in z.files:

@@ -27,7 +27,15 @@ HALTON_FRAC = 0.45   # measured: 0.006 (c10) .. 0.33 (motion/pt_halton: diffuse 
 RAND_FRAC = 1.15
 MEAN_TOL = 0.01      # per-channel mean, Halton variants (measured <= 0.005)
 
-CASES = ["diffuse_static", "c10", "motion", "glass_metal", "sky", "sky_light", "sky_const"]
+# Volume vertices take their tangent frame from get_scrambled_onb(path->tangent_frame_scrambling, omega): the scrambling value
+# comes from the reference's per-thread Mersenne twister (pathspace.c:216-217, not reproducible) and decides
+# the frame for most directions (surface normals in the other cases are mostly axis aligned and escape it).  Halton renders of
+# the media cases therefore decorrelate from the reference's after the first scattering events and are judged like the rand
+# variants, plus a bound that they stay below the independent-seed floor (measured 0.40 .. 0.74 of it).  The exact check of
+# the media code is test_medium_matches_reference.
+MEDIA_CASES = ("fog", "subsurf")
+MEDIA_HALTON_FRAC = 0.9
+CASES = ["diffuse_static", "c10", "motion", "glass_metal", "sky", "sky_light", "sky_const", "fog", "subsurf"]
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
 
@@ -56,10 +64,12 @@ def test_images_match_reference(gpu, case):
         noise, _ = image_stats(a, b)
         rel, ratio = image_stats(a, img)
         assert st["paths"] == g.spp * img.shape[0] * img.shape[1]
-        if "halton" in key:
+        if "halton" in key and g.name not in MEDIA_CASES:
             assert rel <= HALTON_FRAC * noise, f"{g.name}/{key}: relRMSE {rel:.4f} vs noise floor {noise:.4f}"
             assert np.all(np.abs(ratio - 1) < MEAN_TOL), f"{g.name}/{key}: channel means off: {ratio}"
         else:
+            if "halton" in key:   # still the same points where the frames agree: visibly below the independent-seed floor
+                assert rel <= MEDIA_HALTON_FRAC * noise, f"{g.name}/{key}: relRMSE {rel:.4f} vs noise floor {noise:.4f}"
             rel2, _ = image_stats(b, img)
             assert min(rel, rel2) <= RAND_FRAC * noise, f"{g.name}/{key}: relRMSE {rel:.4f}/{rel2:.4f} vs noise floor {noise:.4f}"
             # standard error of a channel mean: 4x4 filter footprints correlate neighbouring pixels -> factor 4, then 3 sigma
@@ -236,6 +246,58 @@ def test_bsdf_matches_reference_callbacks(bsdf_render, case):
     assert close_frac(got["pdf"], want["pdf"], 1e-3, 1e-6) >= 1 - BSDF_OUTLIERS
     lit = want["f"] > 0
     assert np.mean(got["f_mode"][lit] == want["f_mode"][lit]) >= 1 - BSDF_OUTLIERS
+
+
+def test_medium_matches_reference(gpu):
+    """homogeneous media against the reference's own medium_rgb / color modules and src/shader.c's volume functions, query by
+    query (tests/golden/medium.npz from oracle/ref_bsdf.c:ref_medium_eval): coefficients at lambda, free-flight distance and
+    pdf, transmittance and distance pdf of an edge, Henyey-Greenstein sample() / brdf() / pdf() at a volume vertex.  The
+    cb_medium_t records are what scene_io.parse_nra2 produced from the same shader lines."""
+    import ctypes as C
+    IO = cb.scene_io
+    z = np.load(os.path.join(GOLDEN, "medium.npz"))
+    g = GoldenImage("diffuse_static")
+    acc = gpu.Accel(g.scene).build()
+    names = [str(x) for x in z["cases"]]
+    ms = IO.MaterialSet()
+    ms.materials = list(g.materials.materials)
+    ms.tables = g.materials.tables
+    ms.media = [IO.CMedium.from_buffer_copy(z[n + "_medium"].tobytes()[:C.sizeof(IO.CMedium)]) for n in names]
+    r = gpu.Render(acc, g.camera, ms, g.w, g.h)
+    for k, name in enumerate(names):
+        q = np.ascontiguousarray(z[name + "_q"]).view(IO.MEDIUM_QUERY).reshape(-1)
+        want = np.ascontiguousarray(z[name + "_r"]).view(IO.MEDIUM_RESULT).reshape(-1)
+        got = r.medium(k, q)
+        # the reference evaluates rgb2spec's sigmoid with the 12-bit SSE reciprocal square root (include/rgb2spec.h:145-149):
+        # spectra agree to 2e-4 absolute (times the colour's scale), and what is computed from mu_t inherits that error
+        f64 = lambda x: x.astype(np.float64)
+        d_mu = 2e-4 * ms.media[k].mu_t_mul
+        assert np.all(np.abs(f64(got["mu_t"]) - want["mu_t"]) <= d_mu), name
+        assert np.array_equal(np.isnan(got["mu_s"]), np.isnan(want["mu_s"])), name      # no `color v`: NaN upstream, absorbs only
+        ok = ~np.isnan(want["mu_s"])
+        d_s = 2e-4 * (ms.media[k].mu_t_mul + np.abs(f64(want["mu_t"])))
+        assert np.all(np.abs(f64(got["mu_s"]) - want["mu_s"])[ok] <= d_s[ok]), name
+        scat = want["mu_s"] > 0
+        assert np.array_equal(want["free_dist"] >= 3e38, ~scat) and np.array_equal(got["free_dist"] >= 3e38, ~scat), name
+        rel_mu = d_mu / np.maximum(np.abs(f64(want["mu_t"])), 1e-30)
+        rel_s = d_s / np.maximum(np.abs(f64(want["mu_s"])), 1e-30)
+
+        def within(a, b, rel):
+            return bool(np.all(np.abs(f64(a) - b) <= np.abs(f64(b)) * rel + 1e-37))
+        assert within(got["free_dist"][scat], want["free_dist"][scat], rel_mu[scat] + 1e-5), name
+        assert within(got["free_pdf"][scat], want["free_pdf"][scat], rel_mu[scat] + 1e-4), name
+        tau = np.abs(f64(q["dist"]) * want["mu_t"])
+        assert within(got["transmittance"], want["transmittance"], tau * rel_mu + 1e-5), name
+        assert within(got["vol_pdf"][scat], want["vol_pdf"][scat], ((tau + 1) * rel_mu)[scat] + 1e-5), name
+        assert np.all(got["vol_pdf"][~scat] == 1.0) and np.all(want["vol_pdf"][~scat] == 1.0), name
+        assert close_frac(got["s_wo"], want["s_wo"], 0.0, 5e-6) == 1.0, name
+        assert close_frac(got["s_pdf"], want["s_pdf"], 1e-4, 1e-9) == 1.0, name
+        assert close_frac(got["pdf"], want["pdf"], 1e-4, 1e-9) == 1.0, name
+        assert np.all(np.abs(f64(got["s_weight"]) - want["s_weight"])[ok] <= d_s[ok]), name
+        assert within(got["f"][ok], want["f"][ok], rel_s[ok] + 1e-4), name
+        assert np.array_equal(got["s_mode"], want["s_mode"]) and np.array_equal(got["f_mode"], want["f_mode"]), name
+    r.close()
+    acc.close()
 
 
 @pytest.mark.parametrize("flip", [0, 1])
