@@ -402,7 +402,7 @@ def main():
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": WORKLOAD, "num_tris": scene.num_prims, "frame": [WIDTH, HEIGHT], "sampler": "ptdl", "pointsampler": "rand",
                    "paths_per_step_per_gpu": n_pass, "rays_per_path": total_rays / paths,
-                   "l2": "inputs larger than L2 (scene 0.8 GB, path pool 2.4 GB, ray/hit waves 0.5 GB per wave)",
+                   "l2": "inputs larger than L2 (scene 0.8 GB, path pool 2.1 GB, ray/hit waves 0.5 GB per wave)",
                    "parallelism": f"spp split over {world} GPU(s), one framebuffer reduce per progression" if world > 1 else "1 GPU",
                    "bvh": {"nodes": acc.num_nodes(), "depth": acc.depth(), "node_bytes": node_b, "prim_bytes": prim_b, "gpu_build_s": build_s}},
         "spp_per_s": args.steps * world / (ms_total * 1e-3), "paths_per_s": paths / (ms_total * 1e-3),

@@ -31,7 +31,7 @@
 
 #define RB 128   // block size of the integrator kernels
 
-struct __align__(16) PathState   // 144 bytes, one per path in flight
+struct __align__(16) PathState   // 128 bytes, one per path in flight
 {
   float x[3];        float time;        // vertex v position (un-offset)
   float omega[3];    float lambda;      // e[v+1].omega as sampled
@@ -46,7 +46,7 @@ struct __align__(16) PathState   // 144 bytes, one per path in flight
   uint32_t med_shape[MED_MAX];
   float med_ior[MED_MAX];
 };
-static_assert(sizeof(PathState) % 16 == 0, "PathState size");
+static_assert(sizeof(PathState) == 128, "PathState size");
 
 struct NeeRec   // pending next-event contribution, resolved after the shadow wave
 {
