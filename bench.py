@@ -338,7 +338,7 @@ def main():
     def e2e_step(s):
         if world == 1:           # == host/render_b200.c: render_b200_pass(r, first, count, fb)
             lib._check(L.cb200_render_pass_stream(r.r, next_first(), n_pass, None), "cb200_render_pass_stream")
-            lib._check(L.cb200_render_snapshot(r.r, host_fb.data_ptr(), None), "cb200_render_snapshot")
+            lib._check(L.cb200_render_snapshot_async(r.r, host_fb.data_ptr(), None), "cb200_render_snapshot_async")
         else:
             step(s)
             if rank == 0:

@@ -972,6 +972,8 @@ struct cb200_render
   // (st[cur] / rays[cur], slots [0, n_alive)) and ride along with the next pass' waves until cb200_render_flush
   uint32_t n_alive; int cur;
   float *own_fb;
+  // asynchronous snapshots: device-side copy of the accumulation buffer, drained to the host on a stream of its own
+  float *snap_stage; cudaStream_t snap_stream; cudaEvent_t snap_ready, snap_done; int snap_pending;
   // coherence sort of every traced wave: keys ride with the rays (ping-pong), iota -> order by radix sort
   int ray_sort;
   int bsdf_kinds;   // bit mask of the BSDF kinds referenced by shapes (selects the k_shade variant)
@@ -1152,6 +1154,7 @@ extern "C" {
 void cb200_render_destroy(cb200_render_t *r)
 {
   if(!r) return;
+  if(r->snap_stream) { cudaStreamSynchronize(r->snap_stream); cudaStreamDestroy(r->snap_stream); cudaEventDestroy(r->snap_ready); cudaEventDestroy(r->snap_done); }
   for(void *p : r->owned) cudaFree(p);
   for(cudaEvent_t e : r->ev_pool) cudaEventDestroy(e);
   if(r->h_cnt) cudaFreeHost(r->h_cnt);
@@ -1191,6 +1194,7 @@ cb200_render_t *cb200_render_create(cb200_accel_t *a, const cb_render_desc_t *de
   r->h_cnt = nullptr;
   r->timing = r->counting = 0; r->ev_used = 0; r->d_trav_cnt = nullptr;
   r->n_alive = 0; r->cur = 0;
+  r->snap_stage = nullptr; r->snap_stream = nullptr; r->snap_pending = 0;
   cb200_scene *s = a->scene;
   RenderDev &D = r->dev;
   memset(&D, 0, sizeof(D));
@@ -1311,9 +1315,46 @@ int cb200_render_set_framebuffer(cb200_render_t *r, void *d_fb)
   return 0;
 }
 
+// an asynchronous snapshot still on its way must land before anything else is written to (possibly) the same host buffer
+static int snapshot_drain(cb200_render *r)
+{
+  if(r->snap_pending) { CB_CUDA(cudaEventSynchronize(r->snap_done)); r->snap_pending = 0; }
+  return 0;
+}
+
+int cb200_render_snapshot_wait(cb200_render_t *r)
+{
+  if(!r) { cb200_set_error("render_snapshot_wait: null"); return CB200_ERR_ARG; }
+  return snapshot_drain(r);
+}
+
+int cb200_render_snapshot_async(cb200_render_t *r, float *fb_host, void *stream_)
+{
+  if(!r || !fb_host) { cb200_set_error("render_snapshot_async: bad arguments"); return CB200_ERR_ARG; }
+  cudaStream_t st = (cudaStream_t)stream_;
+  const size_t bytes = (size_t)r->dev.fb_w*r->dev.fb_h*3*sizeof(float);
+  if(!r->snap_stream)
+  {
+    CB_CUDA(cudaStreamCreateWithFlags(&r->snap_stream, cudaStreamNonBlocking));
+    CB_CUDA(cudaEventCreateWithFlags(&r->snap_ready, cudaEventDisableTiming));
+    CB_CUDA(cudaEventCreateWithFlags(&r->snap_done, cudaEventDisableTiming));
+    r->snap_stage = dev_alloc<float>(r, (size_t)r->dev.fb_w*r->dev.fb_h*3);
+    if(!r->snap_stage) { cb200_set_error("render_snapshot_async: out of device memory"); return CB200_ERR_NOMEM; }
+  }
+  if(r->snap_pending) CB_CUDA(cudaStreamWaitEvent(st, r->snap_done, 0));   // the staging copy is still being drained
+  CB_CUDA(cudaMemcpyAsync(r->snap_stage, r->dev.fb, bytes, cudaMemcpyDeviceToDevice, st));
+  CB_CUDA(cudaEventRecord(r->snap_ready, st));
+  CB_CUDA(cudaStreamWaitEvent(r->snap_stream, r->snap_ready, 0));
+  CB_CUDA(cudaMemcpyAsync(fb_host, r->snap_stage, bytes, cudaMemcpyDeviceToHost, r->snap_stream));
+  CB_CUDA(cudaEventRecord(r->snap_done, r->snap_stream));
+  r->snap_pending = 1;
+  return 0;
+}
+
 int cb200_render_download(cb200_render_t *r, float *fb_host, void *stream)
 {
   if(!r || !fb_host) { cb200_set_error("render_download: bad arguments"); return CB200_ERR_ARG; }
+  { const int rc = snapshot_drain(r); if(rc) return rc; }
   if(r->n_alive) { const int rc = cb200_render_flush(r, stream); if(rc) return rc; }
   CB_CUDA(cudaMemcpyAsync(fb_host, r->dev.fb, (size_t)r->dev.fb_w*r->dev.fb_h*3*sizeof(float), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
   CB_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
@@ -1323,6 +1364,7 @@ int cb200_render_download(cb200_render_t *r, float *fb_host, void *stream)
 int cb200_render_snapshot(cb200_render_t *r, float *fb_host, void *stream)
 {
   if(!r || !fb_host) { cb200_set_error("render_snapshot: bad arguments"); return CB200_ERR_ARG; }
+  { const int rc = snapshot_drain(r); if(rc) return rc; }
   CB_CUDA(cudaMemcpyAsync(fb_host, r->dev.fb, (size_t)r->dev.fb_w*r->dev.fb_h*3*sizeof(float), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
   CB_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
   return 0;

@@ -8,7 +8,8 @@
  *     render_b200_pass(r, first_index, count, fb)      == for(i in [first, first+count)) render_sample_path(i);
  *
  * with `fb` the host framebuffer of the view (W*H*3 floats, un-gained like fb->fb, include/framebuffer.h:19-36); it
- * receives the accumulated image after the pass (NULL: keep it on the device, e.g. between the passes of a --batch).
+ * receives the accumulated image of the pass asynchronously, while the next pass renders (NULL: keep it on the device, e.g.
+ * between the passes of a --batch).
  * Progressions are streamed (paths that outlive their progression finish during the next one); render_b200_finish()
  * completes them -- call it where the reference saves a screenshot or exits (src/main.c: main_screenshot / cleanup).
  * render_sample_path() itself is exported for link compatibility and refuses loudly: there is no CPU path in here.
@@ -95,7 +96,9 @@ int render_b200_pass(struct render_t *r, uint64_t first_index, uint64_t count, f
   /* streamed: paths still bouncing when every index has been started ride along with the next progression; the
    * framebuffer handed back is the progressive image as it stands (like the reference's display reading fb mid-flight) */
   int rc = cb200_render_pass_stream(r->r, first_index, count, 0);
-  if(!rc && fb) rc = cb200_render_snapshot(r->r, fb, 0);
+  /* the copy to the host runs behind this progression on its own stream and overlaps the next one: what `fb` shows lags by at
+   * most one progression, and it must stay valid until render_b200_finish / render_cleanup (the view's framebuffer does) */
+  if(!rc && fb) rc = cb200_render_snapshot_async(r->r, fb, 0);
   if(rc) { fprintf(stderr, "[render b200] pass failed: %s\n", cb200_last_error()); return 1; }
   r->overlays += count/((uint64_t)r->width*r->height);
   return 0;

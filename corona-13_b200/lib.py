@@ -243,6 +243,8 @@ def _load_render():
     L.cb200_render_download.argtypes = [vp, vp, vp]
     L.cb200_render_set_framebuffer.argtypes = [vp, vp]
     L.cb200_render_snapshot.argtypes = [vp, vp, vp]
+    L.cb200_render_snapshot_async.argtypes = [vp, vp, vp]
+    L.cb200_render_snapshot_wait.argtypes = [vp]
     L.cb200_render_stats.argtypes = [vp, vp]
     L.cb200_render_point.argtypes = [vp, vp, vp, vp, u64]
     L.cb200_render_camera_rays.argtypes = [vp, u64, u64, vp, vp]
@@ -253,7 +255,7 @@ def _load_render():
 
 
 RENDER_SYMBOLS = ["cb200_render_create", "cb200_render_destroy", "cb200_render_pass", "cb200_render_pass_stream", "cb200_render_flush", "cb200_render_clear", "cb200_render_instrument",
-                  "cb200_render_fb_device", "cb200_render_set_framebuffer", "cb200_render_download", "cb200_render_snapshot", "cb200_render_stats", "cb200_render_point",
+                  "cb200_render_fb_device", "cb200_render_set_framebuffer", "cb200_render_download", "cb200_render_snapshot", "cb200_render_snapshot_async", "cb200_render_snapshot_wait", "cb200_render_stats", "cb200_render_point",
                   "cb200_render_camera_rays", "cb200_render_bsdf", "cb200_render_medium"]
 
 
@@ -317,6 +319,21 @@ class Render:
         fb = np.zeros((self.height, self.width, 3), np.float32)
         _check(self.L.cb200_render_download(self.r, _ptr(fb), None), "cb200_render_download")
         return fb
+
+    def snapshot(self):
+        """the accumulation buffer as it stands (no flush): what a progressive display shows between streamed progressions"""
+        fb = np.zeros((self.height, self.width, 3), np.float32)
+        _check(self.L.cb200_render_snapshot(self.r, _ptr(fb), None), "cb200_render_snapshot")
+        return fb
+
+    def snapshot_async(self, fb, stream=0):
+        """the same into the caller's (ideally pinned) float32 buffer without waiting; snapshot_wait() / the next synchronous
+        download waits for it"""
+        assert fb.dtype == np.float32 and fb.size == self.height * self.width * 3 and fb.flags["C_CONTIGUOUS"]
+        _check(self.L.cb200_render_snapshot_async(self.r, _ptr(fb), stream or None), "cb200_render_snapshot_async")
+
+    def snapshot_wait(self):
+        _check(self.L.cb200_render_snapshot_wait(self.r), "cb200_render_snapshot_wait")
 
     def image(self, spp=None):
         """fb * gain, gain = iso / (100 * spp) (src/view.c:656)"""

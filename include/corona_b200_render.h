@@ -176,6 +176,12 @@ int  cb200_render_download(cb200_render_t *r, float *fb_host, void *stream);   /
 /* the accumulation buffer as it stands, WITHOUT flushing: what a progressive display shows between streamed progressions
  * (the stragglers' contributions arrive with a later snapshot; the reference's display reads its framebuffer mid-flight too) */
 int  cb200_render_snapshot(cb200_render_t *r, float *fb_host, void *stream);
+/* the same without waiting: the buffer is copied on the device behind the work queued on `stream` and drained to `fb_host`
+ * (pinned memory, or the call degrades to a synchronous copy) on a stream of the library's own, so the transfer overlaps the
+ * next progression's kernels.  `fb_host` must stay valid until cb200_render_snapshot_wait / _snapshot / _download / _destroy
+ * returns; those wait for the transfer. */
+int  cb200_render_snapshot_async(cb200_render_t *r, float *fb_host, void *stream);
+int  cb200_render_snapshot_wait(cb200_render_t *r);
 int  cb200_render_stats(cb200_render_t *r, cb_render_stats_t *out);
 
 /* component entry points for parity tests (device work, host buffers): */

@@ -374,6 +374,29 @@ def test_streaming_equals_flushed_passes(gpu):
     a.close(), b.close(), acc.close()
 
 
+def test_asynchronous_snapshot_is_the_progressive_image(gpu):
+    """cb200_render_snapshot_async (what render_b200_pass hands the view's framebuffer to): after snapshot_wait the buffer holds
+    exactly the accumulation buffer as it stood behind the pass it was queued after, later passes do not leak into it, and a
+    synchronous download issued while one is in flight waits for it"""
+    g = GoldenImage("diffuse_static")
+    acc = gpu.Accel(g.scene).build()
+    r = gpu.Render(acc, g.camera, g.materials, g.w, g.h, frame=1, batch_paths=40000, **GoldenImage.variant_args("ptdl_halton"))
+    buf = np.zeros((r.height, r.width, 3), np.float32)
+    r.render_pass(streaming=True)
+    want1 = r.snapshot()
+    r.snapshot_async(buf)
+    r.render_pass(streaming=True)          # overlaps the transfer
+    r.snapshot_wait()
+    assert np.array_equal(buf, want1) and buf.sum() > 0
+    want2 = r.snapshot()
+    assert not np.array_equal(want1, want2)
+    r.snapshot_async(buf)
+    final = r.framebuffer()                # flush + download: must wait for the transfer in flight
+    assert np.array_equal(buf, want2)
+    assert final.sum() >= want2.sum()
+    r.close(), acc.close()
+
+
 def test_empty_scene_renders_black(gpu):
     IO = cb.scene_io
     empty = S.Scene([S.Shape(np.zeros(0, np.uint64), np.zeros(0, cb.records.VTXIDX), np.zeros(0, cb.records.VTX), 0, "none")], "empty")
