@@ -53,8 +53,10 @@ int main(int argc, char *argv[])
     else if((!strcmp(argv[i], "-t") || !strcmp(argv[i], "-b") || !strcmp(argv[i], "-o")) && i+1 < argc) ++i;   /* cpu threads / backups / timeout: n/a */
   }
   if(batch < 1) batch = 1;
+  const double t_open = now();
   struct scene_b200_t *s = scene_b200_open(scene, coeff, tables);
   if(!s) { fprintf(stderr, "[main] could not load nra2 file!\n"); return 2; }
+  if(!quiet) printf("[main] shader list and geometry files mapped in %.3f seconds\n", now() - t_open);
   if(dump)
   { /* the flattened shader list, for the parser tests: no GPU needed */
     int n = 0;

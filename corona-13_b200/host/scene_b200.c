@@ -19,6 +19,7 @@
 
 #include <math.h>
 #include <stdlib.h>
+#include <time.h>
 #include <string.h>
 #include <strings.h>
 
@@ -498,10 +499,17 @@ int scene_b200_prepare(struct scene_b200_t *s, uint32_t width, uint32_t height, 
 {
   while(width & 0x1f) width++;      /* src/view.c:295-296 */
   while(height & 0x1f) height++;
+  const int timing = getenv("CB200_TIMING") != 0;
+  struct timespec ts0, ts1, ts2;
+  clock_gettime(CLOCK_MONOTONIC, &ts0);
   s->accel = accel_init(&s->prims);
   if(!s->accel) return 1;
+  clock_gettime(CLOCK_MONOTONIC, &ts1);
   accel_build(s->accel, s->basename);
   if(!accel_b200_handle(s->accel)) return 1;
+  clock_gettime(CLOCK_MONOTONIC, &ts2);
+  if(timing) fprintf(stderr, "[scene b200] accel_init (device / context) %.3f s, accel_build (upload + gpu build + primid read-back) %.3f s\n",
+                     (ts1.tv_sec - ts0.tv_sec) + 1e-9*(ts1.tv_nsec - ts0.tv_nsec), (ts2.tv_sec - ts1.tv_sec) + 1e-9*(ts2.tv_nsec - ts1.tv_nsec));
   char cam[1100];
   if(cam_file) snprintf(cam, sizeof(cam), "%s", cam_file);
   else snprintf(cam, sizeof(cam), "%s01.cam", s->basename);        /* src/view.c:301-312 */
@@ -518,6 +526,9 @@ int scene_b200_prepare(struct scene_b200_t *s, uint32_t width, uint32_t height, 
   d->media = s->nra2->media; d->num_media = s->nra2->num_media; d->exterior_medium = s->nra2->exterior_medium;
   d->max_path_len = 32; d->frame = frame; d->rank = 0; d->world = 1; d->batch_paths = 0;
   s->render = render_b200_init(s->accel, d);
+  clock_gettime(CLOCK_MONOTONIC, &ts0);
+  if(timing) fprintf(stderr, "[scene b200] camera + render_b200_init (materials, lights, halton tables, path pool) %.3f s\n",
+                     (ts0.tv_sec - ts2.tv_sec) + 1e-9*(ts0.tv_nsec - ts2.tv_nsec));
   return s->render ? 0 : 1;
 }
 

@@ -129,9 +129,9 @@ def test_counter_rng_is_uniform(gpu):
     acc.close()
 
 
-@pytest.mark.parametrize("key", ["ptdl_halton", "ptdl_rand"])
-def test_path_index_partition_invariance(gpu, key):
-    g = GoldenImage("glass_metal")
+@pytest.mark.parametrize("key,scene", [("ptdl_halton", "glass_metal"), ("ptdl_rand", "glass_metal"), ("ptdl_halton", "subsurf"), ("ptdl_rand", "fog")])
+def test_path_index_partition_invariance(gpu, key, scene):
+    g = GoldenImage(scene)
     acc = gpu.Accel(g.scene).build()
     args = GoldenImage.variant_args(key)
     n = g.w * g.h * 4
@@ -356,9 +356,10 @@ def test_empty_ranges_and_dark_scenes(gpu):
     acc.close()
 
 
-def test_streaming_equals_flushed_passes(gpu):
+@pytest.mark.parametrize("scene", ["glass_metal", "fog"])
+def test_streaming_equals_flushed_passes(gpu, scene):
     """cb200_render_pass_stream + flush accumulates the same image as complete passes (stragglers only arrive later)"""
-    g = GoldenImage("glass_metal")
+    g = GoldenImage(scene)
     acc = gpu.Accel(g.scene).build()
     args = GoldenImage.variant_args("ptdl_halton")
     a = gpu.Render(acc, g.camera, g.materials, g.w, g.h, frame=1, **args)
