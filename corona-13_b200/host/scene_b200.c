@@ -411,10 +411,16 @@ struct scene_b200_t *scene_b200_open(const char *nra2_file, const char *coeff_fi
     s->sky = CB_SKY_CONST;
     s->sky_scale = scale*rgb_to_coeff(s->rgb2spec, col, s->sky_coeff);
   }
-  else
-  { /* sky modules (envmaps, daylight) are SURVEY 8f rank 3 */
+  else if(!strncmp(sky, "daylight", 8) || !strcmp(sky, "sky_envmap"))
+  { /* the reference's other sky implementations (src/shaders/daylight.h, sky_envmap.c) are SURVEY 8f rank 3 */
     fprintf(stderr, "[scene b200] sky `%s' is not supported by the gpu path (only `black', `cloudy' and `sky_const'); no cpu fallback\n", sky);
     fclose(f); scene_b200_free(s); return 0;
+  }
+  else
+  { /* any other name: upstream tries dlopen("lib<name>.so"), which fails for everything that is not one of its modules, and
+     * keeps the default sky -- the cloudy one (src/shader.c:612-614,643-675; regression/0090_vstack says `const 1 1 1 2000') */
+    printf("[shader_init] failed to load sky shader `lib%s.so'\n", sky);
+    s->sky = CB_SKY_CLOUDY;
   }
   if(!fgets(line, sizeof(line), f) || sscanf(line, "%d", &s->nra2->num_shaders) != 1 || s->nra2->num_shaders < 0 || s->nra2->num_shaders > MAX_SHADERS)
   { fprintf(stderr, "[scene b200] corrupt model file: could not read number of shaders!\n"); fclose(f); scene_b200_free(s); return 0; }

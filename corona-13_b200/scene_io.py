@@ -26,6 +26,23 @@ POINTS_RAND, POINTS_HALTON = 0, 1
 COLOUR_XYZ, COLOUR_REC709 = 0, 1
 SKY_BLACK, SKY_CLOUDY, SKY_CONST = 0, 1, 2
 SKIES = {"sky_const": SKY_CONST, "black": SKY_BLACK, "cloudy": SKY_CLOUDY, "cloudy_sky": SKY_CLOUDY, "clear_sky": SKY_CLOUDY}   # src/shader.c:626-641
+SKY_MODULES = ("daylight", "sky_envmap")    # real sky implementations the GPU path does not have: refused, never substituted
+
+
+def sky_kind(name):
+    """line 1 of a .nra2 -> SKY_*, following shader_init (src/shader.c:612-676): prefix matches for the built-ins, `sky_const`
+    is the module of that name, and a name that is neither a built-in nor one of the reference's sky modules fails its
+    dlopen() there and leaves the default in place, which is the cloudy sky (regression/0090_vstack's `const 1 1 1 2000`)."""
+    if name.startswith("black"):
+        return SKY_BLACK
+    if name.startswith("cloudy") or name.startswith("clear_sky"):
+        return SKY_CLOUDY
+    if name == "sky_const":
+        return SKY_CONST
+    if name.startswith("daylight") or name in SKY_MODULES:
+        raise ValueError(f"sky `{name}' is not supported by the gpu path (no cpu fallback)")
+    return SKY_CLOUDY
+
 
 
 class CCamera(C.Structure):

@@ -264,7 +264,40 @@ def case_subsurf():
                 [2, 20, 21, 22, 5], cam, 192, 128, 128, ["pt_halton", "ptdl_halton", "ptdl_rand"])
 
 
-CASES = {"fog": case_fog, "subsurf": case_subsurf, "sky_const": lambda: case_sky(True, "sky_const 0.3 0.5 0.9 800", "sky_const"), "sky": lambda: case_sky(False), "sky_light": lambda: case_sky(True), "diffuse_static": case_diffuse_static, "c10": case_c10, "motion": case_motion, "glass_metal": case_glass_metal}
+def _box(lo, hi, name):
+    """axis-aligned box as 6 quads with their own corners (flat shading normals), wound counter-clockwise seen from outside"""
+    lo, hi = np.float32(lo), np.float32(hi)
+    c = np.float32([[x, y, z] for z in (lo[2], hi[2]) for y in (lo[1], hi[1]) for x in (lo[0], hi[0])])   # index = x + 2y + 4z
+    quads = [[0, 2, 3, 1], [4, 5, 7, 6], [0, 1, 5, 4], [2, 6, 7, 3], [0, 4, 6, 2], [1, 3, 7, 5]]      # -z +z -y +y -x +x
+    pos = np.concatenate([c[q] for q in quads])
+    return S.mesh_shape(pos, np.arange(24).reshape(6, 4), 0, None, name)
+
+
+def case_vstack():
+    """regression/0090_vstack ("volume stack priorities") as shipped: its shader list, its camera and its first line
+    `const 1 1 1 2000` -- not a sky module of the reference, so dlopen fails there and the default cloudy sky stays
+    (src/shader.c:612-614,643-675).  Two overlapping dielectric cubes filled with absorbing media (interior + medium_rgb behind
+    a black `color v`), the smaller shape id wins inside the overlap (pathspace.c:107-113).  The scene's geometry is not
+    available offline: plane, cubes and emitter are regenerated in the places the camera looks at."""
+    ref = os.path.join(REFDIR, "scenes", "0090_vstack")
+    lines = reference_shader_lines(os.path.join(ref, "test.nra2"))
+    cam = IO.read_cam(os.path.join(ref, "test01.cam"))
+    sky = open(os.path.join(ref, "test.nra2")).read().split("\n")[0].split("#")[0].strip()
+    g = 6
+    xs = np.linspace(-9, 9, g + 1, dtype=np.float32)
+    X, Y = np.meshgrid(xs, xs, indexing="ij")
+    pos = np.stack([X, Y, np.zeros_like(X)], -1).reshape(-1, 3)
+    i, j = np.meshgrid(np.arange(g), np.arange(g), indexing="ij")
+    v00 = (i * (g + 1) + j).reshape(-1)
+    plane = S.mesh_shape(pos, np.stack([v00, v00 + g + 1, v00 + g + 2, v00 + 1], -1), 0, None, "plane")
+    cube2 = _box((-0.2, -1.0, 0.02), (2.2, 1.4, 2.4), "cube2")
+    cube = _box((-2.0, -1.4, 0.02), (0.6, 1.0, 2.0), "cube")
+    emitter = S.quad_light((0.5, -1.0, 7.0), 0.6, 1)
+    golden_case("vstack", S.Scene([plane, cube2, cube, emitter], "vstack"), lines, [2, 17, 16, 5], cam, 192, 128, 128,
+                ["pt_halton", "ptdl_halton", "ptdl_rand"], sky=sky)
+
+
+CASES = {"vstack": case_vstack, "fog": case_fog, "subsurf": case_subsurf, "sky_const": lambda: case_sky(True, "sky_const 0.3 0.5 0.9 800", "sky_const"), "sky": lambda: case_sky(False), "sky_light": lambda: case_sky(True), "diffuse_static": case_diffuse_static, "c10": case_c10, "motion": case_motion, "glass_metal": case_glass_metal}
 
 if __name__ == "__main__":
     subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "oracle"), "ref"])

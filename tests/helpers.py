@@ -176,7 +176,7 @@ class GoldenImage:
             self.materials.media = [arrm[i] for i in range(nm)]
             self.materials.exterior_medium = int(z["exterior_medium"])
         self.sky = str(z["sky"]) if "sky" in z.files else "black"
-        self.sky_args = dict(sky=cb.scene_io.SKIES[self.sky.split()[0]])
+        self.sky_args = dict(sky=cb.scene_io.sky_kind(self.sky.split()[0]))
         if "sky_coeff" in z.files:
             self.sky_args.update(sky_coeff=[float(x) for x in z["sky_coeff"]], sky_scale=float(z["sky_scale"]))
 
