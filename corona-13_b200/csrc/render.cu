@@ -39,8 +39,10 @@ struct __align__(16) PathState   // 128 bytes, one per path in flight
   float pixel_i, pixel_j, scramble, cur_ior;
   uint32_t prim_lo, prim_hi;            // primitive of vertex v (ignore / self-intersection test)
   uint32_t index_lo, index_hi;          // path index
-  int32_t length;                       // path->length (number of finished vertices)
-  int32_t rand_beg;                     // rand_beg of the vertex the current ray is about to create
+  uint32_t lre;                         // bits 0-5 path->length (finished vertices), 6-15 rand_beg of the vertex the current ray is
+                                        // about to create, 16-31 binary exponent of the path pdf (PathPdf)
+  float pdf_m;                          // mantissa of the path pdf: the product of v[1..length-1].pdf the reference's
+                                        // sampler_mis() forms in double precision (pt.c:30-38, ptdl.c:78-88)
   uint32_t bits;                        // bit0: nee_possible(v) (material_modes & (diffuse|glossy)); bits 8..: mt draw counter
   int32_t med_n;                        // media stack: entry count and the entries' medium ids (media_pack)
   uint32_t med_shape[MED_MAX];
@@ -57,6 +59,58 @@ struct NeeRec   // pending next-event contribution, resolved after the shadow wa
   uint32_t light_lo, light_hi;
   uint32_t pad;
 };
+
+// The reference weighs every contribution with sampler_mis(): own pdf and competing pdf are each multiplied by the product of
+// ALL previous vertex pdfs (vertex area measure) in double precision and then converted to float for the division
+// (pt.c:30-38, ptdl.c:78-88).  The conversion overflows to inf beyond 3.4e38 and flushes to 0 below 1.4e-45, the quotient becomes
+// NaN or 0 and view_splat drops the sample: paths whose pdf product leaves the float range do not contribute -- in dense
+// participating media (vertex pdfs of 1e7 and more) that is every path after a handful of scattering events, and it halves
+// the brightness of 0030_subsurf-style skin.  A drop-in has to do the same, so the product rides along with the path as
+// mantissa (float, [0.5,1)) and exponent: exact in range where a double would have overflowed, sticky like a double there.
+struct PathPdf
+{
+  float m; int e;     // value = m * 2^e; e == PP_INF: +inf, e == PP_ZERO: 0, m != m: NaN
+};
+#define PP_INF 32767
+#define PP_ZERO (-32768)
+__device__ __forceinline__ PathPdf pp_one() { PathPdf p; p.m = 0.5f; p.e = 1; return p; }
+__device__ __forceinline__ PathPdf pp_mul(PathPdf p, float x)     // p *= (double)x with IEEE double range semantics
+{
+  if(p.m != p.m) return p;
+  if(x != x) { p.m = x; return p; }
+  if(p.e == PP_INF) { if(x == 0.0f) p.m = __int_as_float(0x7fc00000); return p; }
+  if(p.e == PP_ZERO) { if(isinf(x)) p.m = __int_as_float(0x7fc00000); return p; }
+  if(x == 0.0f) { p.e = PP_ZERO; return p; }
+  if(isinf(x)) { p.e = PP_INF; return p; }     // (a negative pdf does not occur)
+  int ex;
+  const float mm = frexpf(p.m*fabsf(x), &ex);   // |m*x| in [2^-150, 2^128): the float product neither overflows nor vanishes
+  if(mm == 0.0f) { p.e = PP_ZERO; return p; }    // (x was a denormal at the very bottom of the float range)
+  p.m = mm; p.e += ex;
+  if(p.e > 1024) p.e = PP_INF;
+  else if(p.e < -1073) p.e = PP_ZERO;
+  return p;
+}
+// (float)(p * (double)y): 0 = finite and not zero, 1 = inf, -1 = zero, 2 = NaN
+__device__ __forceinline__ int pp_class(PathPdf p, float y)
+{
+  p = pp_mul(p, y);
+  if(p.m != p.m) return 2;
+  if(p.e == PP_INF) return 1;
+  if(p.e == PP_ZERO) return -1;
+  if(p.e > 128) return 1;      // >= 2^128 > FLT_MAX
+  if(p.e < -149) return -1;    // < 2^-150: rounds to zero
+  return 0;
+}
+// does a sample with own pdf `own` and competing pdf `other` (both still to be multiplied by the path pdf) survive the
+// reference's float(own P) / float(own P + other P)?  (NaN and 0 weights are dropped by view_splat, view.c:457-458)
+__device__ __forceinline__ bool pp_contributes(PathPdf p, float own, float other)
+{
+  return pp_class(p, own) == 0 && pp_class(p, own + other) == 0;
+}
+__device__ __forceinline__ uint32_t lre_pack(int length, int rand_beg, int e) { return (uint32_t)length | ((uint32_t)rand_beg << 6) | ((uint32_t)(e & 0xffff) << 16); }
+__device__ __forceinline__ int lre_length(uint32_t w) { return (int)(w & 63u); }
+__device__ __forceinline__ int lre_rand_beg(uint32_t w) { return (int)((w >> 6) & 1023u); }
+__device__ __forceinline__ int lre_exp(uint32_t w) { return (int)(int16_t)(w >> 16); }
 
 struct CameraDev
 {
@@ -218,8 +272,8 @@ __device__ void path_start(const RenderDev &R, uint64_t index, PathState &s, V3 
   s.cos_prev = fabsf(dot(n, om));     // path_lambert at the sensor vertex
   s.cur_ior = 1.0f;
   s.prim_lo = s.prim_hi = 0xffffffffu;
-  s.length = 1;
-  s.rand_beg = 7;                     // v[0] used 7 dims; v[1] uses one (free path) (thinlens.c:101-104)
+  { const PathPdf one = pp_one(); s.lre = lre_pack(1, 7, one.e); s.pdf_m = one.m; }   // v[0] used 7 dims; v[1] uses one (free path)
+                                                                                       // (thinlens.c:101-104)
   s.bits = (mt << 8);
   s.med_n = 0;
   for(int k=0;k<MED_MAX;k++) { s.med_shape[k] = 0; s.med_ior[k] = 1.0f; }
@@ -286,7 +340,7 @@ k_path_start(RenderDev R, uint64_t first_index, uint32_t n, const uint32_t *__re
   { // the camera sits in the exterior medium: sample the free flight of the first edge before tracing it (pathspace.c:716-747)
     float clip = FLT_MAX;
     const Vol vol = medium_eval(R.mats, R.exterior_medium, s.lambda);
-    if(vol.present && vol.mu_s > 0.0f) clip = vol_free_flight(vol, point_dim(R.points, index, s.rand_beg + 0));
+    if(vol.present && vol.mu_s > 0.0f) clip = vol_free_flight(vol, point_dim(R.points, index, lre_rand_beg(s.lre) + 0));
     maxd[i] = clip;
   }
   write_ray(rays, i, pos, mk3(s.omega[0], s.omega[1], s.omega[2]), s.time, 0xffffffffu, 0xffffffffu);
@@ -348,7 +402,7 @@ __device__ void prim_test_geo(const SceneGeo &S, uint64_t pid, const RayD &r, Hi
 
 __device__ __forceinline__ float max3abs(V3 x) { return fmaxf(fmaxf(.5f, fabsf(x.x)), fmaxf(fabsf(x.y), fabsf(x.z))); }
 
-struct ShadeCounters { unsigned long long next, nee, hits[4], splats; };   // next, nee, hits[kind] are per wave; splats keeps counting
+struct ShadeCounters { unsigned long long next, nee, hits[5], splats; };   // next, nee, hits[kind] are per wave; splats keeps counting
 
 // path_G for the edge between a surface vertex and the sampled light point (pathspace.c:58-69)
 __device__ __forceinline__ float cos_lambert(const Vtx &v, const Vtx &l, V3 d, float dist)
@@ -414,13 +468,15 @@ k_sky_miss(RenderDev R, uint32_t n, const PathState *__restrict__ st, const cb_h
       if(em > 0.0f)
       {
         const float pdf_v = s.pdf_proj*s.cos_prev;      // path_G towards the environment = lambert at the previous vertex (pathspace.c:60-61)
+        PathPdf pp; pp.m = s.pdf_m; pp.e = lre_exp(s.lre);
         float w = 1.0f;
+        float pdf_nee = 0.0f;
         if(R.sampler == CB_SAMPLER_PTDL)
         {
-          float pdf_nee = 0.0f;
-          if(s.length + 1 >= 3 && (s.bits & 1u) && R.p_sky > 0.0f) pdf_nee = R.p_sky*sky_pdf(R, omega);   // nee_pdf_nee, nee.h:21-38
+          if(lre_length(s.lre) + 1 >= 3 && (s.bits & 1u) && R.p_sky > 0.0f) pdf_nee = R.p_sky*sky_pdf(R, omega);   // nee_pdf_nee, nee.h:21-38
           w = pdf_v/(pdf_nee + pdf_v);
         }
+        if(!pp_contributes(pp, pdf_v, pdf_nee)) w = 0.0f;   // sampler_mis in float range only (PathPdf)
         did = splat(R, s.pixel_i, s.pixel_j, s.lambda, (s.thr*em)*w);   // lights_eval_vertex: isotropic for the envmap (list.c:272-273)
       }
     }
@@ -437,8 +493,8 @@ __global__ void __launch_bounds__(256)
 k_compact_hits(RenderDev R, const cb_hitrec_t *__restrict__ hits, uint32_t n, uint32_t n_cap, uint32_t *__restrict__ list, ShadeCounters *cnt,
                int single_kind)
 {
-  __shared__ uint32_t warp_count[4][8];
-  __shared__ uint32_t block_base[4];
+  __shared__ uint32_t warp_count[5][8];
+  __shared__ uint32_t block_base[5];
   const uint32_t i = blockIdx.x*blockDim.x + threadIdx.x, lane = threadIdx.x & 31u, w = threadIdx.x >> 5;
   int kind = -1;
   if(i < n)
@@ -446,13 +502,13 @@ k_compact_hits(RenderDev R, const cb_hitrec_t *__restrict__ hits, uint32_t n, ui
     const uint2 p = *reinterpret_cast<const uint2 *>(hits + i);   // prim id words
     if((p.x & p.y) != 0xffffffffu)
       kind = single_kind >= 0 ? single_kind : R.mats.mat[R.geo.shape_material[p.x >> 3]].bsdf;
-    else if(R.has_media && hits[i].dist < FLT_MAX) kind = 3;   // the sampled free flight ended before any surface: volume vertex
+    else if(R.has_media && hits[i].dist < FLT_MAX) kind = 4;   // the sampled free flight ended before any surface: volume vertex
   }
-  uint32_t m[4];
+  uint32_t m[5];
 #pragma unroll
-  for(int k=0;k<4;k++) { m[k] = __ballot_sync(0xffffffffu, kind == k); if(lane == 0) warp_count[k][w] = __popc(m[k]); }
+  for(int k=0;k<5;k++) { m[k] = __ballot_sync(0xffffffffu, kind == k); if(lane == 0) warp_count[k][w] = __popc(m[k]); }
   __syncthreads();
-  if(threadIdx.x < 4)
+  if(threadIdx.x < 5)
   {
     const int k = threadIdx.x;
     uint32_t tot = 0;
@@ -461,27 +517,27 @@ k_compact_hits(RenderDev R, const cb_hitrec_t *__restrict__ hits, uint32_t n, ui
   }
   __syncthreads();
 #pragma unroll
-  for(int k=0;k<4;k++)
+  for(int k=0;k<5;k++)
     if(kind == k) list[(size_t)k*n_cap + block_base[k] + warp_count[k][w] + __popc(m[k] & ((1u << lane) - 1u))] = i;
 }
 
 // The vertex-level callbacks of a volume vertex are the medium's (medium_rgb.c:62-103): Henyey-Greenstein around the incoming
-// direction, scaled by mu_s.  KINDS == 8 selects them, every other KINDS goes to the surface BSDFs of shading.cuh.
+// direction, scaled by mu_s.  KINDS == 16 selects them, every other KINDS goes to the surface BSDFs of shading.cuh.
 template<int KINDS>
 __device__ __forceinline__ float vtx_eval(const MaterialsDev &M, Vtx &v, V3 wi, V3 wo, float lambda, float cur_ior)
 {
-  if constexpr(KINDS == 8) { v.mode |= M_GLOSSY | M_VOLUME; return v.vol_mu_s*hg_eval(v.vol_g, wi, wo); }
+  if constexpr(KINDS == 16) { v.mode |= M_GLOSSY | M_VOLUME; return v.vol_mu_s*hg_eval(v.vol_g, wi, wo); }
   else return bsdf_eval<KINDS>(M, v, wi, wo, lambda, cur_ior);
 }
 template<int KINDS>
 __device__ __forceinline__ float vtx_pdf(const MaterialsDev &M, const Vtx &v, V3 wi, V3 wo)
 {
-  if constexpr(KINDS == 8) return (v.mode & M_VOLUME) ? hg_eval(v.vol_g, wi, wo) : 0.0f;
+  if constexpr(KINDS == 16) return (v.mode & M_VOLUME) ? hg_eval(v.vol_g, wi, wo) : 0.0f;
   else return bsdf_pdf<KINDS>(M, v, wi, wo);
 }
 
-// one vertex of every live path whose surface has BSDF kind KIND (0 diffuse, 1 dielectric, 2 metal; 3 = volume vertex of a
-// homogeneous medium): each launch carries the code of ONE BSDF (the all-in-one kernel was 17 k instructions and lost 24 % of
+// one vertex of every live path whose surface has BSDF kind KIND (0 diffuse, 1 dielectric, 2 metal, 3 diffdiel; 4 = volume
+// vertex of a homogeneous medium): each launch carries the code of ONE BSDF (the all-in-one kernel was 17 k instructions and lost 24 % of
 // its stall samples to instruction-cache misses) and no lane waits for another material's branch.  KINDS = 1 << KIND for the
 // templates of shading.cuh; light vertices reached by next-event estimation only need their emission slots, which every
 // variant fills.  MEDIA compiles the participating-media terms in (free-flight sampling of the next edge, transmittance and
@@ -494,7 +550,7 @@ k_shade(RenderDev R, uint32_t n, const PathState *__restrict__ st_in, const cb_r
         cb_ray_t *__restrict__ nee_rays, float *__restrict__ nee_maxdist, uint2 *__restrict__ nee_light, NeeRec *__restrict__ nee_recs,
         ShadeCounters *cnt, uint32_t *__restrict__ rkeys_out, const uint32_t *__restrict__ hit_list, int kind, float *__restrict__ maxd_out)
 {
-  constexpr bool VOLV = KINDS == 8;   // this launch shades volume vertices
+  constexpr bool VOLV = KINDS == 16;   // this launch shades volume vertices
   const uint32_t t = blockIdx.x*blockDim.x + threadIdx.x;
   const uint32_t n_hits = (uint32_t)*reinterpret_cast<volatile unsigned long long *>(&cnt->hits[kind]);   // written by k_compact_hits
   if(blockIdx.x*blockDim.x >= n_hits) return;   // whole block beyond the list (the grid is sized for n, the upper bound)
@@ -556,32 +612,36 @@ k_shade(RenderDev R, uint32_t n, const PathState *__restrict__ st_in, const cb_r
           thr = s.thr*(e_T/e_pdf);               // path_update_throughput (pathspace.c:158)
         }
         else { pdf_v = s.pdf_proj*G; thr = s.thr; }
-        const int vi = s.length;        // index of this vertex
-        s.length++;
-        const int rand_beg_v = s.rand_beg;
+        const int vi = lre_length(s.lre);        // index of this vertex
+        const int len = vi + 1;                  // path->length from here on
+        const int rand_beg_v = lre_rand_beg(s.lre);
+        PathPdf pp; pp.m = s.pdf_m; pp.e = lre_exp(s.lre);   // product of v[1..vi-1].pdf
+        float pdf_v_final = pdf_v;                           // v[vi].pdf as later vertices will see it
         bool stop = false;
         // ---- emission: path_update_throughput + sampler splat
         if(v.mode & M_EMIT)
         {
           const float L = thr*light_eval(v, omega);
           float w = 1.0f;
+          float pdf_nee = 0.0f;
           if(R.sampler == CB_SAMPLER_PTDL)
           {
-            float pdf_nee = 0.0f;
-            if(s.length >= 3 && (s.bits & 1u) && R.lights.p_geo > 0.0f)
+            if(len >= 3 && (s.bits & 1u) && R.lights.p_geo > 0.0f)
               pdf_nee = R.lights.p_geo*R.lights.shape_pdf[v.prim_lo >> 3];
             w = pdf_v/(pdf_nee + pdf_v);        // sampler_mis, ptdl.c:78-88 with one wavelength
           }
+          if(!pp_contributes(pp, pdf_v, pdf_nee)) w = 0.0f;   // ... which only exists inside the float range (PathPdf)
           did_splat = splat(R, s.pixel_i, s.pixel_j, s.lambda, L*w);
-          if(R.sampler == CB_SAMPLER_PT && s.length > 3)
+          if(R.sampler == CB_SAMPLER_PT && len > 3)
           { // path_russian_roulette (pathspace.c:273-292)
             const float p_survival = fminf(1.0f, thr/s.thr_prev);
             const float rr = point_dim(R.points, index, rand_beg_v + 4);
             if(rr >= p_survival) stop = true;
-            else thr *= 1.0f/p_survival;
+            else { thr *= 1.0f/p_survival; pdf_v_final = pdf_v*p_survival; }
           }
         }
-        if(R.sampler == CB_SAMPLER_PTDL && s.length >= R.max_path_len) stop = true;
+        if(R.sampler == CB_SAMPLER_PTDL && len >= R.max_path_len) stop = true;
+        const PathPdf pp_v = pp_mul(pp, pdf_v_final);        // product of v[1..vi].pdf
         uint32_t mt = s.bits >> 8;
         int rand_cnt_v = 5;
         if(vi == 1) rand_cnt_v = 1;
@@ -589,7 +649,7 @@ k_shade(RenderDev R, uint32_t n, const PathState *__restrict__ st_in, const cb_r
         if(!stop && R.sampler == CB_SAMPLER_PTDL)
         {
           (void)point_mt(R.points, index, mt++);   // the rr draw against nee_probability() == 1
-          if(s.length >= 32) stop = true;          // nee_sample refuses at PATHSPACE_MAX_VERTS and the sampler returns
+          if(len >= 32) stop = true;               // nee_sample refuses at PATHSPACE_MAX_VERTS and the sampler returns
           else
           {
             const int rb = rand_beg_v + rand_cnt_v; // rand_beg of the nee vertex (nee.h:107)
@@ -638,8 +698,8 @@ k_shade(RenderDev R, uint32_t n, const PathState *__restrict__ st_in, const cb_r
                     const float thr_l = ((thr*bsdf)*(T_nee*edf))*Gl;
                     const float pdf_nee = pdf_sky*R.p_sky;
                     const float pdf_ext = (vol_pdf*vtx_pdf<KINDS>(R.mats, vb, omega, d))*Gl;
-                    const float w = pdf_nee/(pdf_ext + pdf_nee);
-                    if(thr_l > 0.0f && total_dist > 0.0f)
+                    const float w = pp_contributes(pp_v, pdf_nee, pdf_ext) ? pdf_nee/(pdf_ext + pdf_nee) : 0.0f;
+                    if(thr_l*w > 0.0f && total_dist > 0.0f)
                     {
                       have_nee = true;
                       for(int k=0;k<3;k++) { nray.pos[k] = (&rp.x)[k]; nray.dir[k] = (&rd.x)[k]; }
@@ -712,8 +772,8 @@ k_shade(RenderDev R, uint32_t n, const PathState *__restrict__ st_in, const cb_r
                       // mis against extending the path into the light (ptdl.c:142-146)
                       const float pdf_nee = R.lights.p_geo*pdf_l;
                       const float pdf_ext = (vol_pdf*vtx_pdf<KINDS>(R.mats, vb, omega, d))*Gl;
-                      const float w = pdf_nee/(pdf_ext + pdf_nee);
-                      if(thr_l > 0.0f)
+                      const float w = pp_contributes(pp_v, pdf_nee, pdf_ext) ? pdf_nee/(pdf_ext + pdf_nee) : 0.0f;
+                      if(thr_l*w > 0.0f)
                       {
                         have_nee = true;
                         for(int k=0;k<3;k++) { nray.pos[k] = (&rp.x)[k]; nray.dir[k] = (&rd.x)[k]; }
@@ -738,7 +798,7 @@ k_shade(RenderDev R, uint32_t n, const PathState *__restrict__ st_in, const cb_r
           }
         }
         // ---- extend: sample the bsdf at v (pathspace.c:186-203, shader.c:577-590)
-        if(!stop && thr > 0.0f && s.length < 32)
+        if(!stop && thr > 0.0f && len < 32)
         {
           const int rb = rand_beg_v + rand_cnt_v;   // rand_beg of vertex vi+1 (pathspace.c:199)
           const float rx = point_dim(R.points, index, rb + 1), ry = point_dim(R.points, index, rb + 2), rm = point_dim(R.points, index, rb + 3);
@@ -775,7 +835,8 @@ k_shade(RenderDev R, uint32_t n, const PathState *__restrict__ st_in, const cb_r
             s.x[0] = v.x.x; s.x[1] = v.x.y; s.x[2] = v.x.z;
             s.omega[0] = wo.x; s.omega[1] = wo.y; s.omega[2] = wo.z;
             s.prim_lo = v.prim_lo; s.prim_hi = v.prim_hi;
-            s.rand_beg = rb;
+            s.lre = lre_pack(len, rb, pp_v.m != pp_v.m ? PP_ZERO : pp_v.e);
+            s.pdf_m = pp_v.m;
             s.bits = (mt << 8) | ((v.material_modes & (M_DIFFUSE | M_GLOSSY)) ? 1u : 0u);
             s.med_n = media_pack(med);
             for(int k=0;k<MED_MAX;k++) { s.med_shape[k] = med.shape[k]; s.med_ior[k] = med.ior[k]; }
@@ -900,9 +961,9 @@ __global__ void k_medium(MaterialsDev M, uint32_t medium, const cb_medium_query_
   o.s_wo[2] = v.n.z*out3[0] + v.a.z*out3[1] + v.b.z*out3[2];
   o.s_weight = v.vol_mu_s; o.s_pdf = pdf; o.s_mode = M_GLOSSY | M_VOLUME;
   Vtx vb = v;
-  o.f = vtx_eval<8>(M, vb, wi, wo_q, Q.lambda, 1.0f);
+  o.f = vtx_eval<16>(M, vb, wi, wo_q, Q.lambda, 1.0f);
   o.f_mode = vb.mode;
-  o.pdf = vtx_pdf<8>(M, vb, wi, wo_q);
+  o.pdf = vtx_pdf<16>(M, vb, wi, wo_q);
   out[i] = o;
 }
 
@@ -1172,7 +1233,7 @@ cb200_render_t *cb200_render_create(cb200_accel_t *a, const cb_render_desc_t *de
   {
     const cb_material_t &m = desc->materials[i];
     if(m.num_ops < 0) continue;   // a shader outside the hot path (media, skies): only an error when a shape references it
-    if(m.num_ops > CB_MAX_MATOPS || m.bsdf < 0 || m.bsdf > CB_BSDF_METAL)
+    if(m.num_ops > CB_MAX_MATOPS || m.bsdf < 0 || m.bsdf > CB_BSDF_DIFFDIEL)
     { cb200_set_error("render_create: malformed material"); return nullptr; }
     if(m.bsdf == CB_BSDF_METAL && (m.table < 0 || m.table >= desc->num_tables)) { cb200_set_error("render_create: metal without ior table"); return nullptr; }
     for(int k=0;k<m.num_ops;k++) if(m.ops[k].op == CB_OP_CHECKERSG && (m.ops[k].table < 0 || m.ops[k].table >= desc->num_tables))
@@ -1244,7 +1305,7 @@ cb200_render_t *cb200_render_create(cb200_accel_t *a, const cb_render_desc_t *de
   D.fb = r->own_fb = dev_alloc<float>(r, (size_t)desc->width*desc->height*3);
   for(int k=0;k<2;k++) { r->st[k] = dev_alloc<PathState>(r, N); r->rays[k] = dev_alloc<cb_ray_t>(r, N); ok = ok && r->st[k] && r->rays[k]; }
   r->hits = dev_alloc<cb_hitrec_t>(r, N);
-  r->hit_list = dev_alloc<uint32_t>(r, 4*N); ok = ok && r->hit_list;
+  r->hit_list = dev_alloc<uint32_t>(r, 5*N); ok = ok && r->hit_list;
   r->maxd[0] = r->maxd[1] = nullptr;
   if(D.has_media) for(int k=0;k<2;k++) { r->maxd[k] = dev_alloc<float>(r, N); ok = ok && r->maxd[k]; }
   r->nee_rays = dev_alloc<cb_ray_t>(r, N); r->nee_md = dev_alloc<float>(r, N); r->nee_recs = dev_alloc<NeeRec>(r, N); r->nee_light = dev_alloc<uint2>(r, N); r->nee_vis = dev_alloc<int32_t>(r, N);
@@ -1404,7 +1465,7 @@ static int render_wave(cb200_render *r, uint32_t n, cudaStream_t st)
   }
   if(rc) return rc;
   r->stats.rays_closest += n; r->stats.kernel_launches++;
-  CB_CUDA(cudaMemsetAsync(r->d_cnt, 0, 6*sizeof(unsigned long long), st));   // next, nee, hits[4] (splats keeps counting)
+  CB_CUDA(cudaMemsetAsync(r->d_cnt, 0, 7*sizeof(unsigned long long), st));   // next, nee, hits[5] (splats keeps counting)
   {
     TimeScope ts(r, st, KC_SHADE, n);
     if(r->dev.sky != CB_SKY_BLACK)
@@ -1412,7 +1473,7 @@ static int render_wave(cb200_render *r, uint32_t n, cudaStream_t st)
       k_sky_miss<<<(n + RB - 1)/RB, RB, 0, st>>>(r->dev, n, r->st[cur], r->hits, r->d_cnt);
       cb200_count_launch(); r->stats.kernel_launches++;
     }
-    const int single = r->dev.has_media ? -1 : (r->bsdf_kinds == 1) ? 0 : (r->bsdf_kinds == 2) ? 1 : (r->bsdf_kinds == 4) ? 2 : -1;
+    const int single = r->dev.has_media ? -1 : (r->bsdf_kinds == 1) ? 0 : (r->bsdf_kinds == 2) ? 1 : (r->bsdf_kinds == 4) ? 2 : (r->bsdf_kinds == 8) ? 3 : -1;
     k_compact_hits<<<(n + 255)/256, 256, 0, st>>>(r->dev, r->hits, n, (uint32_t)r->batch, r->hit_list, r->d_cnt, single);
     cb200_count_launch(); r->stats.kernel_launches++;
     uint32_t *rk = r->ray_sort ? r->rkeys[cur^1] : nullptr;
@@ -1424,9 +1485,10 @@ static int render_wave(cb200_render *r, uint32_t n, cudaStream_t st)
     if(r->bsdf_kinds & 1) SHADE_LAUNCH(0);
     if(r->bsdf_kinds & 2) SHADE_LAUNCH(1);
     if(r->bsdf_kinds & 4) SHADE_LAUNCH(2);
+    if(r->bsdf_kinds & 8) SHADE_LAUNCH(3);
     if(r->dev.has_media)
-    { // volume vertices of scattering media (kind 3)
-      k_shade<8, true><<<(n + RB - 1)/RB, RB, 0, st>>>SHADE_ARGS(3);
+    { // volume vertices of scattering media (kind 4)
+      k_shade<16, true><<<(n + RB - 1)/RB, RB, 0, st>>>SHADE_ARGS(4);
       cb200_count_launch(); r->stats.kernel_launches++;
     }
 #undef SHADE_LAUNCH

@@ -8,6 +8,7 @@
 //   diffuse                : src/shader.c:157-257
 //   dielectric / ggx       : src/shaders/dielectric.c:96-541, src/shaders/ggx.h
 //   metal                  : src/shaders/metal.c:79-310
+//   diffdiel               : src/shaders/diffdiel.c (ggx reflection + diffuse transmission, 0030_subsurf's skin surface)
 //   media nesting          : src/pathspace.c:80-146 (_path_edge_medium, path_eta_ratio, path_edge_init_volume)
 #pragma once
 #include "prims.cuh"
@@ -382,12 +383,13 @@ CBD float dielectric_ior(float n_d, float V_d, float lambda)   // spectrum.h:40-
 }
 #define DIEL_GLOSSY_THR 1e-3f
 #define METAL_GLOSSY_THR 1e-4f
+#define DIFFDIEL_GLOSSY_THR 1e-4f
 #define HALFVEC_COS_THR .999f
 CBD bool indexmatched(float n1, float n2) { return fabsf(1.0f - n1/n2) < 1e-3f; }
 
 // the host bsdf's own prepare() (diffuse: shader.c:157-162, dielectric.c:67-81, metal.c:71-77) and the cached eta ratio
 // (shader.c:538): runs after the material chain has filled the shading slots
-template<int KINDS = 7>
+template<int KINDS = 15>
 CBD void bsdf_prepare(const MaterialsDev &M, Vtx &v, float lambda, const Media &med, float cur_ior)
 {
   const cb_material_t &m = M.mat[v.mat];
@@ -408,11 +410,19 @@ CBD void bsdf_prepare(const MaterialsDev &M, Vtx &v, float lambda, const Media &
     v.material_modes = M_REFLECT;
     if(v.roughness > METAL_GLOSSY_THR) v.material_modes |= M_GLOSSY; else v.material_modes |= M_SPECULAR;
   }
+  else if((KINDS & 8) && m.bsdf == CB_BSDF_DIFFDIEL)
+  { // diffdiel.c:71-85
+    v.ior = dielectric_ior(m.param[0], m.param[1], lambda);
+    v.material_modes = M_REFLECT | M_TRANSMIT;
+    const float eta = eta_ratio(med, cur_ior, v);
+    if(indexmatched(eta, 1.0f)) v.roughness = 0.0f;
+    if(v.roughness > DIFFDIEL_GLOSSY_THR) v.material_modes |= M_GLOSSY; else v.material_modes |= M_SPECULAR;
+  }
   v.eta = eta_ratio(med, cur_ior, v);
 }
 
 // shader_prepare for a surface vertex whose x, u, v, prim are set and whose incoming direction is `omega`
-template<int KINDS = 7>
+template<int KINDS = 15>
 CBD void prepare_vertex(const SceneGeo &S, const MaterialsDev &M, Vtx &v, V3 omega, float time, float lambda, float scramble,
                         const Media &med, float cur_ior)
 {
@@ -571,7 +581,7 @@ CBD float fresnel_conductor(float n1, float n2, float k2, float cosr)   // metal
   return clamp01((Rs2 + Rp2)*.5f);
 }
 
-template<int KINDS = 7>
+template<int KINDS = 15>
 CBD float bsdf_sample(const MaterialsDev &M, Vtx &v, V3 wi, float lambda, float cur_ior, float r_x, float r_y, float r_mode,
                       V3 &wo, float &pdf)
 {
@@ -652,8 +662,62 @@ CBD float bsdf_sample(const MaterialsDev &M, Vtx &v, V3 wi, float lambda, float 
     v.mode = M_TRANSMIT | M_GLOSSY;
     return v.rg*ggx_G1(wo, v.n, v.roughness);
   }
+  if((KINDS & 8) && m.bsdf == CB_BSDF_DIFFDIEL)
+  { // diffdiel.c:223-306 (culled_modes == 0): ggx reflection off the interface, cosine-distributed diffuse transmission
+    const float eta = v.eta;
+    if(eta < 0.0f) return 0.0f;
+    if(indexmatched(eta, 1.0f))
+    {
+      wo = wi; v.mode = M_SPECULAR | M_TRANSMIT; pdf = 1.0f;
+      return v.rg;
+    }
+    V3 h = v.n;
+    float pdf_h = 1.0f;
+    const float r = v.roughness;
+    const float cos_in = -dot(v.n, wi);
+    if(r > DIFFDIEL_GLOSSY_THR)
+    {
+      const V3 wit = mk3(-dot(v.a, wi), -dot(v.b, wi), cos_in);
+      const V3 ht = ggx_sample_h(wit, r, r, r_x, r_y);
+      h = mk3(ht.x*v.a.x + ht.y*v.b.x + ht.z*v.n.x, ht.x*v.a.y + ht.y*v.b.y + ht.z*v.n.y, ht.x*v.a.z + ht.y*v.b.z + ht.z*v.n.z);
+      pdf_h = ggx_pdf_h(wi, h, v.n, r);
+    }
+    float p = pdf_h;
+    const float cosr = -dot(wi, h);
+    if(cosr <= 0.0f) return 0.0f;
+    const float n1 = eta, n2 = 1.0f;
+    const float nr = n1/n2;
+    const float cost2 = 1.0f - (nr*nr)*(1.0f - cos_in*cos_in);   // "non-reciprocal fake fresnel": on the macro normal
+    const float cost = cost2 <= 0.0f ? 0.0f : sqrtf(cost2);
+    const float R = fresnel_dielectric(n1, n2, cos_in, cost);
+    if(r_mode <= R)
+    {
+      v.mode = M_REFLECT;
+      wo = mk3(wi.x + 2.0f*cosr*h.x, wi.y + 2.0f*cosr*h.y, wi.z + 2.0f*cosr*h.z);
+      if(dot(wo, v.n) <= 0.0f) return 0.0f;
+      p *= 1.0f/(4.0f*cosr);
+      if(r > DIFFDIEL_GLOSSY_THR)
+      {
+        pdf = R*(p/fabsf(dot(wo, v.n)));
+        v.mode |= M_GLOSSY;
+        if(dot(wo, v.n)*dot(wo, h) < 0.0f) return 0.0f;
+        return v.rg*ggx_G1(wo, v.n, v.roughness);
+      }
+      pdf = R;
+      v.mode |= M_SPECULAR;
+      return v.rg;
+    }
+    v.mode = M_GLOSSY | M_TRANSMIT;
+    pdf = (1.0f - R)/PI_F;
+    // sample_cos (sampler_common.h:156-162)
+    const float su = sqrtf(r_x);
+    const float ang = (float)((double)2.f*PI_D*(double)r_y);
+    const float c0 = su*cosf(ang), c1 = su*sinf(ang), c2 = sqrtf((float)(1.0 - (double)r_x));
+    wo = mk3(v.a.x*c0 + v.b.x*c1 - v.n.x*c2, v.a.y*c0 + v.b.y*c1 - v.n.y*c2, v.a.z*c0 + v.b.z*c1 - v.n.z*c2);
+    return v.rg;
+  }
   // metal.c:208-256
-  if(KINDS & 4)
+  if((KINDS & 4) && (KINDS == 4 || m.bsdf == CB_BSDF_METAL))
   {
     V3 h = v.n;
     float pdf_h = 1.0f;
@@ -689,7 +753,7 @@ CBD float bsdf_sample(const MaterialsDev &M, Vtx &v, V3 wi, float lambda, float 
 }
 
 // shader_brdf: evaluates f for (wi -> wo) and sets v.mode
-template<int KINDS = 7>
+template<int KINDS = 15>
 CBD float bsdf_eval(const MaterialsDev &M, Vtx &v, V3 wi, V3 wo, float lambda, float cur_ior)
 {
   const cb_material_t &m = M.mat[v.mat];
@@ -767,8 +831,47 @@ CBD float bsdf_eval(const MaterialsDev &M, Vtx &v, V3 wi, V3 wo, float lambda, f
     mask |= cosh2 < HALFVEC_COS_THR;
     return mask ? 0.0f : v.rg*clamp01(1.0f - R2);
   }
+  if((KINDS & 8) && m.bsdf == CB_BSDF_DIFFDIEL)
+  { // diffdiel.c:309-383
+    const float cos_in = -dot(v.n, wi), cos_out = dot(v.n, wo);
+    const float eta = v.eta;
+    if(eta < 0.0f) return 0.0f;
+    const float n1 = eta, n2 = 1.0f;
+    const bool matched = indexmatched(n1, n2);
+    if(cos_out == 0.0f || cos_in == 0.0f) return 0.0f;
+    if(!matched && (cos_in*cos_out > 0.0f)) v.mode = M_REFLECT; else v.mode = M_TRANSMIT;
+    const float r = v.roughness;
+    if((r > DIFFDIEL_GLOSSY_THR) && !matched) v.mode |= M_GLOSSY; else v.mode |= M_SPECULAR;
+    const float nr = n1/n2;
+    const float cost2 = 1.0f - (nr*nr)*(1.0f - cos_in*cos_in);
+    const float cost = cost2 <= 0.0f ? 0.0f : sqrtf(cost2);
+    const float R = fresnel_dielectric(n1, n2, cos_in, cost);
+    if(matched)
+    {
+      const float dwn = dot(wo, v.n);
+      const V3 h = normalise(mk3(-wi.x + wo.x - 2.0f*dwn*v.n.x, -wi.y + wo.y - 2.0f*dwn*v.n.y, -wi.z + wo.z - 2.0f*dwn*v.n.z));
+      const float cosh = dot(h, v.n);
+      if(cosh < 0.0f || cosh < HALFVEC_COS_THR) return 0.0f;
+      return v.rg;
+    }
+    if(v.mode & M_REFLECT)
+    {
+      const V3 h = normalise(mk3(-wi.x + wo.x, -wi.y + wo.y, -wi.z + wo.z));
+      const float cosh = dot(h, v.n);
+      if(cosh < 0.0f) return 0.0f;
+      const float cosr = dot(h, wo);
+      const float DG1 = (v.mode & M_SPECULAR) ? 1.0f : ggx_pdf_h(wi, h, v.n, v.roughness);
+      if(DG1 == 0.0f) return 0.0f;
+      const float G1 = ggx_G1(wo, v.n, v.roughness);
+      if(v.mode & M_GLOSSY) return (v.rg*R)*(DG1*G1/(4.0f*fabsf(cosr*cos_out)));
+      if(cosh < HALFVEC_COS_THR) return 0.0f;
+      return v.rg*R;
+    }
+    if(v.mode & M_GLOSSY) return v.rg*(clamp01(1.0f - R)/PI_F);
+    return 0.0f;   // "pure specular case": cosh is still 0 there and fails the half vector test
+  }
   // metal.c:259-310
-  if(KINDS & 4)
+  if((KINDS & 4) && (KINDS == 4 || m.bsdf == CB_BSDF_METAL))
   {
     const float cos_in = -dot(v.n, wi), cos_out = dot(v.n, wo);
     if(cos_out <= 0.0f || cos_in <= 0.0f) return 0.0f;
@@ -792,7 +895,7 @@ CBD float bsdf_eval(const MaterialsDev &M, Vtx &v, V3 wi, V3 wo, float lambda, f
 }
 
 // shader_pdf(p, v) for the forward direction (e1 < e2): projected solid angle pdf of wo given wi, for v.mode
-template<int KINDS = 7>
+template<int KINDS = 15>
 CBD float bsdf_pdf(const MaterialsDev &M, const Vtx &v, V3 wi, V3 wo)
 {
   const cb_material_t &m = M.mat[v.mat];
@@ -859,8 +962,58 @@ CBD float bsdf_pdf(const MaterialsDev &M, const Vtx &v, V3 wi, V3 wo)
     mask |= !(pdf > 0.0f);
     return mask ? 0.0f : pdf;
   }
+  if((KINDS & 8) && m.bsdf == CB_BSDF_DIFFDIEL)
+  { // diffdiel.c:96-221, culled_modes == 0, forward direction
+    const V3 n = v.n;
+    const float cos_in = -dot(n, wi), cos_out = dot(n, wo);
+    if(cos_in*cos_out == 0.0f) return 0.0f;
+    if(cos_out > 0.0f && !(v.mode & M_REFLECT)) return 0.0f;
+    if(cos_out < 0.0f && !(v.mode & M_TRANSMIT)) return 0.0f;
+    const float eta = v.eta;
+    if(eta < 0.0f) return 0.0f;
+    const float n1 = eta, n2 = 1.0f;
+    bool mask = false;
+    float cosr = 0.0f, cosh = 0.0f;
+    V3 h = mk3(0.0f, 0.0f, 0.0f);
+    if(indexmatched(n1, n2))
+    {
+      const float dwn = dot(wo, n);
+      h = normalise(mk3(-wi.x + wo.x - 2.0f*dwn*n.x, -wi.y + wo.y - 2.0f*dwn*n.y, -wi.z + wo.z - 2.0f*dwn*n.z));
+      if(v.mode != (M_TRANSMIT | M_SPECULAR)) return 0.0f;
+      if(dot(h, n) < HALFVEC_COS_THR) return 0.0f;
+      return 1.0f;
+    }
+    else if(v.mode & M_REFLECT)
+    {
+      h = normalise(sub(wi, wo));
+      cosh = fabsf(dot(h, n));
+      cosr = fabsf(dot(h, wi));
+    }
+    const float nr = n1/n2;
+    const float cost2 = 1.0f - (nr*nr)*(1.0f - cos_in*cos_in);
+    const float cost = cost2 <= 0.0f ? 0.0f : sqrtf(cost2);
+    const float R = fresnel_dielectric(n1, n2, cos_in, cost);
+    float pdf = 1.0f;
+    if(v.mode & M_REFLECT)
+    {
+      if(v.mode & M_SPECULAR) { mask |= cosh < HALFVEC_COS_THR; return mask ? 0.0f : R; }
+      pdf *= 1.0f/(4.0f*fabsf(dot(wo, h)));
+      pdf *= R;
+    }
+    else
+    {
+      if(v.mode & M_SPECULAR) return 0.0f;   // cosh == 0 < HALFVEC_COS_THR masks the specular transmit case out
+      pdf = (float)(1.0/PI_D);
+      pdf *= clamp01(1.0f - R);
+      return (pdf > 0.0f) ? pdf : 0.0f;
+    }
+    pdf *= ggx_pdf_h_cos(cosh, cos_in, cosr, v.roughness);
+    pdf /= fabsf(cos_out);
+    mask |= !(pdf > 0.0f);
+    return mask ? 0.0f : pdf;
+  }
   // metal.c:166-205
-  if(KINDS & 4)
+  if((KINDS & 4) && (KINDS == 4 || m.bsdf == CB_BSDF_METAL))
   {
     if(!(v.mode & M_REFLECT)) return 0.0f;
     const float cos_in = -dot(v.n, wi), cos_out = dot(v.n, wo);

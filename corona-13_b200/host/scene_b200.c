@@ -196,6 +196,13 @@ static int flatten(nra2_t *n, int k, cb_material_t *m, int *have_bsdf, int depth
     m->bsdf = CB_BSDF_DIELECTRIC; m->param[0] = nd; m->param[1] = vd; *have_bsdf = 1;
     return 0;
   }
+  if(!strcmp(l->name, "diffdiel"))
+  { /* src/shaders/diffdiel.c:39-58: same arguments as dielectric */
+    float nd = 1.5f, vd = 50.0f;
+    if(sscanf(l->args, " %f %f", &nd, &vd) < 1) return 1;
+    m->bsdf = CB_BSDF_DIFFDIEL; m->param[0] = nd; m->param[1] = vd; *have_bsdf = 1;
+    return 0;
+  }
   if(!strcmp(l->name, "metal"))
   { /* src/shaders/metal.c:43-64: material name looked up in fresnel.h's list; unknown names fall back to the first (Ti) */
     char mat[64] = "", tn[80];

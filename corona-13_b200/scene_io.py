@@ -20,7 +20,7 @@ FULL_FRAME_WIDTH = 0.35                                                         
 CB_MAX_MATOPS = 6
 OP_COLOR, OP_CHECKERSG = 1, 2
 SLOTS = {"d": 0, "s": 1, "e": 2, "v": 3, "g": 4, "r": 5, "t": 6}
-BSDF_DIFFUSE, BSDF_DIELECTRIC, BSDF_METAL = 0, 1, 2
+BSDF_DIFFUSE, BSDF_DIELECTRIC, BSDF_METAL, BSDF_DIFFDIEL = 0, 1, 2, 3
 SAMPLER_PT, SAMPLER_PTDL = 0, 1
 POINTS_RAND, POINTS_HALTON = 0, 1
 COLOUR_XYZ, COLOUR_REC709 = 0, 1
@@ -366,6 +366,8 @@ def parse_nra2(path, rgb2spec, checker_table=None, metal_tables=None):
             return [], (BSDF_DIFFUSE, [0, 0, 0, 0], -1)
         if kind == "dielectric":
             return [], (BSDF_DIELECTRIC, [float(r[1]), float(r[2]) if len(r) > 2 else 50.0, 0, 0], -1)
+        if kind == "diffdiel":
+            return [], (BSDF_DIFFDIEL, [float(r[1]), float(r[2]) if len(r) > 2 else 50.0, 0, 0], -1)
         if kind == "metal":
             if metal_tables is None or r[1].lower() not in metal_tables:
                 raise ValueError(f"metal `{r[1]}' needs its ior table fixture")

@@ -10,7 +10,7 @@
  * include/filter/blackmanharris.h:43-77).
  *
  * The scene description arrives flattened: the host layer (or a test) walks the reference's shader list
- * (`.nra2`: mult / color / colorcheckersg / dielectric / metal / diffuse / interior / medium_rgb / exterior) once at
+ * (`.nra2`: mult / color / colorcheckersg / dielectric / diffdiel / metal / diffuse / interior / medium_rgb / exterior) once at
  * load time and hands over one cb_material_t per shader index a shape may reference.  Unknown shader kinds are a hard error upstream --
  * there is no CPU fallback.
  */
@@ -48,7 +48,8 @@ enum { CB_SLOT_DIFFUSE = 0, CB_SLOT_SPECULAR = 1, CB_SLOT_EMISSION = 2, CB_SLOT_
        CB_SLOT_ROUGHNESS = 5, CB_SLOT_TRANSMIT_TO_EYE = 6 };   /* src/shaders/texture.h:8-21 */
 enum { CB_BSDF_DIFFUSE = 0,      /* src/shader.c:157-257 */
        CB_BSDF_DIELECTRIC = 1,   /* src/shaders/dielectric.c */
-       CB_BSDF_METAL = 2 };      /* src/shaders/metal.c */
+       CB_BSDF_METAL = 2,        /* src/shaders/metal.c */
+       CB_BSDF_DIFFDIEL = 3 };   /* src/shaders/diffdiel.c: dielectric reflection, diffuse transmission */
 
 typedef struct cb_matop_t
 {
@@ -76,7 +77,7 @@ typedef struct cb_material_t
 {
   int32_t num_ops;
   int32_t bsdf;
-  float param[4];                /* dielectric: n_d, abbe */
+  float param[4];                /* dielectric, diffdiel: n_d, abbe */
   int32_t table;                 /* metal: index of its (n,k) table */
   int32_t medium;                /* `interior <surface> <medium>` (src/shaders/interior.c): 1 + index into cb_render_desc_t.media of
                                     the homogeneous medium behind this surface, 0 = vacuum */

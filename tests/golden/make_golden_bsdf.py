@@ -27,7 +27,8 @@ CASES = {"dielectric": ("libdielectric.so", "1.7 73", [0.4, 0.05, 0.0]),
          "dielectric_c10": ("libdielectric.so", "1.3 23", [0.04]),
          "metal_au": ("libmetal.so", "Au", [0.2, 0.0]),
          "metal_ag": ("libmetal.so", "Ag", [0.1]),
-         "diffuse": ("diffuse", "", [1.0])}
+         "diffuse": ("diffuse", "", [1.0]),
+         "diffdiel": ("libdiffdiel.so", "1.33 30", [0.13, 0.4, 0.0])}     # regression/0030_subsurf: `diffdiel 1.33 30` under roughness 0.13
 
 
 def unit(v):

@@ -33,9 +33,9 @@ MEAN_TOL = 0.01      # per-channel mean, Halton variants (measured <= 0.005)
 # the media cases therefore decorrelate from the reference's after the first scattering events and are judged like the rand
 # variants, plus a bound that they stay below the independent-seed floor (measured 0.40 .. 0.74 of it).  The exact check of
 # the media code is test_medium_matches_reference.
-MEDIA_CASES = ("fog", "subsurf")
+MEDIA_CASES = ("fog", "subsurf", "skin", "furnace")
 MEDIA_HALTON_FRAC = 0.9
-CASES = ["diffuse_static", "c10", "motion", "glass_metal", "sky", "sky_light", "sky_const", "fog", "subsurf", "vstack"]
+CASES = ["diffuse_static", "c10", "motion", "glass_metal", "sky", "sky_light", "sky_const", "fog", "subsurf", "vstack", "skin", "furnace"]
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
 
@@ -191,7 +191,8 @@ def bsdf_materials():
                                      ("dielectric_c10", IO.BSDF_DIELECTRIC, [1.3, 23.0, 0, 0], None),
                                      ("metal_au", IO.BSDF_METAL, [0, 0, 0, 0], "metal_au"),
                                      ("metal_ag", IO.BSDF_METAL, [0, 0, 0, 0], "metal_ag"),
-                                     ("diffuse", IO.BSDF_DIFFUSE, [0, 0, 0, 0], None)):
+                                     ("diffuse", IO.BSDF_DIFFUSE, [0, 0, 0, 0], None),
+                                     ("diffdiel", IO.BSDF_DIFFDIEL, [1.33, 30.0, 0, 0], None)):
         m = IO.CMaterial()
         m.num_ops, m.bsdf = 0, bsdf
         m.param[:] = param
@@ -225,7 +226,7 @@ def close_frac(got, want, rtol, atol):
     return float(np.mean(np.abs(got.astype(np.float64) - want.astype(np.float64)) <= atol + rtol * np.abs(want.astype(np.float64))))
 
 
-@pytest.mark.parametrize("case", ["dielectric", "dielectric_c10", "metal_au", "metal_ag", "diffuse"])
+@pytest.mark.parametrize("case", ["dielectric", "dielectric_c10", "metal_au", "metal_ag", "diffuse", "diffdiel"])
 def test_bsdf_matches_reference_callbacks(bsdf_render, case):
     """sample() / brdf() / pdf() against the reference's own shader modules, query by query"""
     r, index = bsdf_render

@@ -28,7 +28,7 @@ def run_cli(nra2, *args):
 
 
 @needs_coeff
-@pytest.mark.parametrize("case", ["diffuse_static", "c10", "motion", "glass_metal", "sky_light", "sky_const", "fog", "subsurf", "vstack"])
+@pytest.mark.parametrize("case", ["diffuse_static", "c10", "motion", "glass_metal", "sky_light", "sky_const", "fog", "subsurf", "vstack", "skin"])
 def test_c_parser_flattens_shader_list_like_the_fixture(built, tmp_path, case):
     IO = cb.scene_io
     g = GoldenImage(case)
@@ -102,7 +102,7 @@ def test_cli_render_matches_reference_image(built, tmp_path, case, key):
 
 @needs_coeff
 @pytest.mark.gpu
-@pytest.mark.parametrize("case,key", [("fog", "ptdl_halton"), ("subsurf", "ptdl_halton")])
+@pytest.mark.parametrize("case,key", [("fog", "ptdl_halton"), ("subsurf", "ptdl_halton"), ("skin", "ptdl_halton")])
 def test_cli_render_of_media_scenes(built, tmp_path, case, key):
     """`exterior` / `interior` + medium_rgb + `color v` through the C reader and the command line.  Judged statistically: the
     tangent frames of volume vertices depend on the reference's unreproducible per-thread scrambling value (see
