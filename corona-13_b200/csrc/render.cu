@@ -76,6 +76,15 @@ struct PathPdf
 __device__ __forceinline__ PathPdf pp_one() { PathPdf p; p.m = 0.5f; p.e = 1; return p; }
 __device__ __forceinline__ PathPdf pp_mul(PathPdf p, float x)     // p *= (double)x with IEEE double range semantics
 {
+  const uint32_t xb = __float_as_uint(x), xe = (xb >> 23) & 0xffu;
+  if(xe != 0u && xe != 0xffu && !(xb >> 31) && p.m == p.m && p.e != PP_INF && p.e != PP_ZERO)
+  { // the usual case: a normal positive float times a finite product
+    float mm = p.m*__uint_as_float((xb & 0x007fffffu) | 0x3f000000u);   // [0.5,1) x [0.5,1)
+    int e = p.e + (int)xe - 126;
+    if(mm < 0.5f) { mm *= 2.0f; e--; }
+    p.m = mm; p.e = e > 1024 ? PP_INF : (e < -1073 ? PP_ZERO : e);
+    return p;
+  }
   if(p.m != p.m) return p;
   if(x != x) { p.m = x; return p; }
   if(p.e == PP_INF) { if(x == 0.0f) p.m = __int_as_float(0x7fc00000); return p; }
@@ -83,11 +92,11 @@ __device__ __forceinline__ PathPdf pp_mul(PathPdf p, float x)     // p *= (doubl
   if(x == 0.0f) { p.e = PP_ZERO; return p; }
   if(isinf(x)) { p.e = PP_INF; return p; }     // (a negative pdf does not occur)
   int ex;
-  const float mm = frexpf(p.m*fabsf(x), &ex);   // |m*x| in [2^-150, 2^128): the float product neither overflows nor vanishes
-  if(mm == 0.0f) { p.e = PP_ZERO; return p; }    // (x was a denormal at the very bottom of the float range)
-  p.m = mm; p.e += ex;
-  if(p.e > 1024) p.e = PP_INF;
-  else if(p.e < -1073) p.e = PP_ZERO;
+  const float mx = frexpf(fabsf(x), &ex);       // denormal x
+  float mm = p.m*mx;
+  int e = p.e + ex;
+  if(mm < 0.5f) { mm *= 2.0f; e--; }
+  p.m = mm; p.e = e > 1024 ? PP_INF : (e < -1073 ? PP_ZERO : e);
   return p;
 }
 // (float)(p * (double)y): 0 = finite and not zero, 1 = inf, -1 = zero, 2 = NaN
@@ -105,6 +114,8 @@ __device__ __forceinline__ int pp_class(PathPdf p, float y)
 // reference's float(own P) / float(own P + other P)?  (NaN and 0 weights are dropped by view_splat, view.c:457-458)
 __device__ __forceinline__ bool pp_contributes(PathPdf p, float own, float other)
 {
+  // nearly always: a product within 2^+-100 times pdfs within 1e-6 .. 1e6 stays far inside the float range
+  if(p.m == p.m && p.e > -100 && p.e < 100 && own > 1e-6f && own + other < 1e6f) return true;
   return pp_class(p, own) == 0 && pp_class(p, own + other) == 0;
 }
 __device__ __forceinline__ uint32_t lre_pack(int length, int rand_beg, int e) { return (uint32_t)length | ((uint32_t)rand_beg << 6) | ((uint32_t)(e & 0xffff) << 16); }
@@ -117,6 +128,17 @@ struct CameraDev
   cb_camera_t c;
   float width, height;
   float fstop, exposure_time;
+};
+
+struct EnvDev   // sky_envmap.c's rgbe_t on the device
+{
+  const float4 *px;          // width*height texels: rgb2spec coefficients + scale
+  const float *mip;          // importance hierarchy, level k at mip + mip_off[k], (w2n >> k) x (h2n >> k)
+  uint32_t mip_off[16];
+  int32_t width, height, w2n, h2n, levels;
+  float aspectx, aspecty, mul;
+  double sum;
+  float world[9], world_inv[9];
 };
 
 struct RenderDev
@@ -135,6 +157,7 @@ struct RenderDev
   float sky_coeff[3], sky_scale;   // CB_SKY_CONST
   float p_sky;                     // lights_pdf_type: probability of connecting to the sky (list.c:44-49,76-88)
   float sky_far;                   // distance of the next-event point on the sky (shader.c:313-316)
+  const EnvDev *env;               // CB_SKY_ENVMAP: in device memory (the out-of-line env_* functions take its address)
   uint32_t exterior_medium;        // 1 + index of the medium the camera sits in (shader_exterior_medium), 0 = vacuum
   int32_t has_media;               // any medium in the scene: the free-flight / transmittance code paths are live
 };
@@ -412,19 +435,112 @@ __device__ __forceinline__ float cos_lambert(const Vtx &v, const Vtx &l, V3 d, f
 
 // ---- skies: the built-in `cloudy' (src/shader.c:268-334: L = 500 (1 + omega_z)/2, sampled with pdf (1 + z)/2 / (2 pi)) and the
 //      constant-colour module (src/shaders/sky_const.c: L = scale * rgb2spec(lambda), uniform sphere) -----------------------------
+// ---- sky_envmap.c: latitude-longitude map of spectral coefficients with a mip hierarchy for importance sampling ------------
+__device__ __forceinline__ float env_sh(const float4 c)   // sky_envmap_sh (:40-45): the spectrum at 660, 560, 480, 400 nm
+{
+  const float cf[3] = {c.x, c.y, c.z};
+  return ((rgb2spec_eval(cf, 660.0f)*c.w + rgb2spec_eval(cf, 560.0f)*c.w) + rgb2spec_eval(cf, 480.0f)*c.w) + rgb2spec_eval(cf, 400.0f)*c.w;
+}
+__device__ __forceinline__ float4 env_fetch(const EnvDev &E, int i, int j)   // fb_fetchi (framebuffer.h:211-215)
+{
+  if(i < 0 || i >= E.width || j < 0 || j >= E.height) return E.px[0];
+  return E.px[(size_t)E.width*j + i];
+}
+__device__ __forceinline__ V3 env_mulv(const float *a, V3 v)   // mat3_mulv (matrix3.inc:41-50)
+{
+  V3 r;
+  r.x = ((0.0f + a[0]*v.x) + a[1]*v.y) + a[2]*v.z;
+  r.y = ((0.0f + a[3]*v.x) + a[4]*v.y) + a[5]*v.z;
+  r.z = ((0.0f + a[6]*v.x) + a[7]*v.y) + a[8]*v.z;
+  return r;
+}
+__device__ __noinline__ float env_eval(const EnvDev &E, V3 omega, float lambda)   // eval (:59-94), sensor paths
+{
+  const V3 dir = env_mulv(E.world_inv, omega);
+  float x, y;
+  if(fabsf(dir.z) > 1.0f) { x = 0.0f; y = 0.0f; }
+  else
+  {
+    y = (float)((double)acosf(dir.z)/PI_D*(double)E.height);
+    x = (float)(((PI_D + (double)atan2f(dir.x, dir.y))/(2.0*PI_D))*(double)E.width);
+  }
+  if(!(x < E.width && x >= 0.0f && y < E.height && y >= 0.0f)) x = y = 0.0f;
+  const float4 c = env_fetch(E, (int)x, (int)y);
+  const float cf[3] = {c.x, c.y, c.z};
+  return rgb2spec_eval(cf, lambda)*(E.mul*c.w);
+}
+__device__ __noinline__ float env_pdf(const EnvDev &E, V3 omega)   // pdf (:194-219), solid angle
+{
+  const V3 dir = env_mulv(E.world_inv, omega);
+  const double yd = (double)acosf(dir.z)/PI_D*(double)E.height, xd = ((PI_D + (double)atan2f(dir.x, dir.y))/(2.0*PI_D))*(double)E.width;
+  const float y = (float)fmin(fmax(yd, 0.0), (double)(E.height - 1)), x = (float)fmin(fmax(xd, 0.0), (double)(E.width - 1));
+  const float sin_theta = sqrtf(fmaxf(1e-12f, 1.0f - dir.z*dir.z));
+  const int i = (int)x, j = (int)y;
+  const float qs = sinf((float)(PI_D*(double)(.5f + j)/(double)E.height));
+  return (float)((double)(env_sh(env_fetch(E, i, j))*E.mul*qs)/(E.sum*(double)sin_theta*(double)2.0f*PI_D*PI_D));
+}
+__device__ __noinline__ V3 env_sample(const EnvDev &E, float x1, float x2, float lambda, float &edf, float &pdf)   // sample (:96-192), next event
+{
+  double wx = x1, wy = x2;
+  const float *top = E.mip + E.mip_off[E.levels-1];
+  if(wx < top[0]) wx *= .5/(double)top[0];
+  else wx = 1.0 - (1.0 - wx)*.5/(1.0 - (double)top[0]);
+  wx *= 2.0;
+  for(int m=E.levels-2;m>=0;m--)
+  {
+    const float *mp = E.mip + E.mip_off[m];
+    int i = (int)wx, j = (int)wy;
+    const int wd = E.w2n >> m;
+    if(2*i >= wd) i = (wd-1)/2;
+    if(4*j >= wd) j = (wd-1)/4;
+    const float up = mp[2*i + 2*j*wd] + mp[2*i+1 + 2*j*wd];
+    if(wy < (double)((float)j + up))
+    {
+      wy = j + (wy - j)*.5/(double)up;
+      j = 2*j;
+    }
+    else if((double)up < 0.999)
+    {
+      wy = j + 1.0 - (1.0 - (wy - j))*.5/(1.0 - (double)up);
+      j = 2*j + 1;
+    }
+    const double f = (double)(mp[2*i + j*wd]/(mp[2*i + j*wd] + mp[2*i+1 + j*wd]));
+    if(wx <= i + f) wx = i + (wx - i)*.5/f;
+    else if(wx > i + f) wx = i + 1.0 - (1.0 - wx + i)*.5/(1.0 - f);
+    wx *= 2.0; wy *= 2.0;
+  }
+  const float x = (float)(wx*(double)E.aspectx), y = (float)(wy*(double)E.aspecty);
+  const int i = (int)x, j = (int)y;
+  const float4 c = env_fetch(E, i, j);
+  const float theta = (float)(PI_D*(double)(y/E.height));
+  const float phi = (float)(2.0*PI_D*(double)(x/E.width) - PI_D);
+  float sin_theta, cos_theta, sin_phi, cos_phi;
+  sincosf(theta, &sin_theta, &cos_theta);
+  const float qs = sinf((float)(PI_D*(double)(.5f + j)/(double)E.height));
+  sincosf(phi, &sin_phi, &cos_phi);
+  pdf = (float)((double)(env_sh(c)*E.mul*qs)/(PI_D*PI_D*2.0*E.sum*(double)sin_theta));
+  const float cf[3] = {c.x, c.y, c.z};
+  const float em = rgb2spec_eval(cf, lambda)*(E.mul*c.w);
+  edf = em/pdf;
+  return env_mulv(E.world, mk3(sin_phi*sin_theta, cos_phi*sin_theta, cos_theta));
+}
+
 __device__ __forceinline__ float sky_eval(const RenderDev &R, V3 omega, float lambda)
 {
+  if(R.sky == CB_SKY_ENVMAP) return env_eval(*R.env, omega, lambda);
   if(R.sky == CB_SKY_CONST) return rgb2spec_eval(R.sky_coeff, lambda)*R.sky_scale;                      // sky_const.c:41-45
   return (float)((double)(1.0f*500.0f*0.5f)*(1.0 + (double)omega.z));                                    // sky_cloudy, v != 0 (shader.c:276-279)
 }
 __device__ __forceinline__ float sky_pdf(const RenderDev &R, V3 omega)    // solid angle
 {
+  if(R.sky == CB_SKY_ENVMAP) return env_pdf(*R.env, omega);
   if(R.sky == CB_SKY_CONST) return (float)(1.0/((double)4.0f*PI_D));                                     // sky_const.c:84-87
   return (float)((double)(0.5f + omega.z*.5f)/(2.0*PI_D));                                               // shader.c:328-331
 }
 // next-event sample: direction, emission / pdf, pdf
 __device__ __forceinline__ V3 sky_sample(const RenderDev &R, float x1, float x2, float lambda, float &edf, float &pdf)
 {
+  if(R.sky == CB_SKY_ENVMAP) return env_sample(*R.env, x1, x2, lambda, edf, pdf);
   if(R.sky == CB_SKY_CONST)
   { // sample_sphere (sampler_common.h:136-143)
     const float z = 1.f - 2.f*x1;
@@ -1136,6 +1252,70 @@ static float host_rgb2spec(const float *c, float lambda)
   return fmaf(.5f*x, y, .5f);
 }
 
+// sky_envmap.c's init() (:303-366): texels to the device, importance mip hierarchy built exactly like there (float arithmetic,
+// the four children of a cell normalised by their sum where that is >= 0.001, top level = the two halves)
+static float host_env_sh(const float *c)
+{
+  return ((host_rgb2spec(c, 660.0f)*c[3] + host_rgb2spec(c, 560.0f)*c[3]) + host_rgb2spec(c, 480.0f)*c[3]) + host_rgb2spec(c, 400.0f)*c[3];
+}
+static int build_envmap(cb200_render *r, const cb_envmap_t *em)
+{
+  EnvDev E;
+  memset(&E, 0, sizeof(E));
+  E.width = (int)em->width; E.height = (int)em->height; E.mul = em->mul;
+  for(int k=0;k<9;k++) { E.world[k] = em->world[k]; E.world_inv[k] = em->world_inv[k]; }
+  E.w2n = 1; E.h2n = 1;
+  while(E.w2n <= E.width) E.w2n <<= 1;
+  E.w2n >>= 1;
+  while(E.h2n <= E.height) E.h2n <<= 1;
+  E.h2n >>= 1;
+  E.aspectx = E.width/(float)E.w2n;
+  E.aspecty = E.height/(float)E.h2n;
+  E.levels = 0;
+  size_t size = 0;
+  for(int h=E.h2n;h>0;h>>=1,E.levels++) size += (size_t)h*h*2;
+  if(E.levels > 16) { cb200_set_error("render_create: environment map too large"); return CB200_ERR_ARG; }
+  std::vector<float> pix(size, 0.0f);
+  std::vector<float *> mip(E.levels);
+  mip[0] = pix.data();
+  E.mip_off[0] = 0;
+  for(int k=0;k<E.levels-1;k++) { mip[k+1] = mip[k] + (size_t)(E.w2n >> k)*(E.h2n >> k); E.mip_off[k+1] = (uint32_t)(mip[k+1] - mip[0]); }
+  auto fetch = [&](int i, int j) -> const float * {
+    if(i < 0 || i >= E.width || j < 0 || j >= E.height) return em->pixels;
+    return em->pixels + 4*((size_t)E.width*j + i);
+  };
+  const float b = em->mul;
+  E.sum = 0.0;
+  for(int j=0;j<E.h2n;j++) for(int i=0;i<E.w2n;i++)
+  {
+    const int ii = (int)(i*E.aspectx + 0.5f), jj = (int)(j*E.aspecty + 0.5f);
+    const float sn = sinf((float)(M_PI*jj/(float)E.height));
+    mip[0][i + E.w2n*j] = host_env_sh(fetch(ii, jj))*b*sn;
+    E.sum += mip[0][i + E.w2n*j];
+  }
+  E.sum /= E.w2n*E.h2n;
+  for(int m=1;m<E.levels;m++)
+  {
+    const int wp = E.w2n >> (m-1);
+    for(int j=0;j<(E.h2n >> m);j++) for(int i=0;i<(E.w2n >> m);i++)
+    {
+      float &a00 = mip[m-1][i*2 + wp*j*2], &a01 = mip[m-1][i*2 + wp*(j*2+1)], &a10 = mip[m-1][i*2 + 1 + wp*j*2], &a11 = mip[m-1][i*2 + 1 + wp*(j*2+1)];
+      const float all = a00 + a01 + a10 + a11;
+      mip[m][i + (E.w2n >> m)*j] = .25f*all;
+      if(all >= 0.001f) { a00 /= all; a10 /= all; a11 /= all; a01 /= all; }
+    }
+  }
+  {
+    const float all = mip[E.levels-1][0] + mip[E.levels-1][1];
+    mip[E.levels-1][0] /= all;
+    mip[E.levels-1][1] /= all;
+  }
+  E.px = reinterpret_cast<const float4 *>(dev_upload(r, em->pixels, (size_t)E.width*E.height*4));
+  E.mip = dev_upload(r, pix.data(), pix.size());
+  r->dev.env = dev_upload(r, &E, 1);
+  return (E.px && E.mip && r->dev.env) ? 0 : CB200_ERR_NOMEM;
+}
+
 // lights_init_light per emissive shape + lights_prepare_frame (list.c:56-104)
 static int build_lights(cb200_render *r)
 {
@@ -1239,7 +1419,9 @@ cb200_render_t *cb200_render_create(cb200_accel_t *a, const cb_render_desc_t *de
     for(int k=0;k<m.num_ops;k++) if(m.ops[k].op == CB_OP_CHECKERSG && (m.ops[k].table < 0 || m.ops[k].table >= desc->num_tables))
     { cb200_set_error("render_create: colour checker without table"); return nullptr; }
   }
-  if(desc->sky != CB_SKY_BLACK && desc->sky != CB_SKY_CLOUDY && desc->sky != CB_SKY_CONST) { cb200_set_error("render_create: unsupported sky (no CPU fallback)"); return nullptr; }
+  if(desc->sky != CB_SKY_BLACK && desc->sky != CB_SKY_CLOUDY && desc->sky != CB_SKY_CONST && desc->sky != CB_SKY_ENVMAP) { cb200_set_error("render_create: unsupported sky (no CPU fallback)"); return nullptr; }
+  if(desc->sky == CB_SKY_ENVMAP && (!desc->envmap || !desc->envmap->pixels || desc->envmap->height < 2 || desc->envmap->width != 2*desc->envmap->height))
+  { cb200_set_error("render_create: environment map missing or not 2:1 (sky_envmap.c:309)"); return nullptr; }
   if(desc->num_media < 0 || desc->num_media > CB_MAX_MEDIA || (desc->num_media > 0 && !desc->media) ||
      desc->exterior_medium < 0 || desc->exterior_medium > desc->num_media)
   { cb200_set_error("render_create: malformed media list"); return nullptr; }
@@ -1292,6 +1474,7 @@ cb200_render_t *cb200_render_create(cb200_accel_t *a, const cb_render_desc_t *de
   ok = ok && D.mats.mat && D.mats.tables && D.mats.table_data && D.mats.media;
   ok = ok && cudaMemcpyToSymbol(c_cie, cie1931_xyz, sizeof(cie1931_xyz)) == cudaSuccess;
   ok = ok && build_halton(r, desc->frame) == 0;
+  if(ok && desc->sky == CB_SKY_ENVMAP) ok = build_envmap(r, desc->envmap) == 0;
   if(ok && build_lights(r)) { cb200_render_destroy(r); return nullptr; }
   // wave buffers
   r->batch = desc->batch_paths;

@@ -358,7 +358,65 @@ struct scene_b200_t
   char basename[1024], searchpath[1024];
   int sky;
   float sky_coeff[3], sky_scale;
+  cb_envmap_t envmap;          /* `sky_envmap`: texels point into env_map (the mapped .fb file) */
+  void *env_map; size_t env_size;
 };
+
+/* sky_envmap.c:272-311: "<file.fb> [brightness] [rot_x rot_y rot_z]" (degrees); the .fb layout is include/framebuffer.h:26-35 */
+static void rotation(const float *axis, float angle, float *res)   /* mat3_rotate, include/matrix3.inc:111-134 */
+{
+  angle = angle/((float)180)*M_PI;
+  const float s = sinf(angle), c = cosf(angle);
+  res[0] = axis[0]*axis[0] + (1 - axis[0]*axis[0])*c; res[1] = axis[0]*axis[1]*(1 - c) - axis[2]*s; res[2] = axis[0]*axis[2]*(1 - c) + axis[1]*s;
+  res[3] = axis[1]*axis[0]*(1 - c) + axis[2]*s; res[4] = axis[1]*axis[1] + (1 - axis[1]*axis[1])*c; res[5] = axis[1]*axis[2]*(1 - c) - axis[0]*s;
+  res[6] = axis[2]*axis[0]*(1 - c) - axis[1]*s; res[7] = axis[2]*axis[1]*(1 - c) + axis[0]*s; res[8] = axis[2]*axis[2] + (1 - axis[2]*axis[2])*c;
+}
+static void mat3_product(const float *a, const float *b, float *res)   /* mat3_mul, matrix3.inc:29-39 */
+{
+  for(int k=0;k<9;k++) res[k] = 0.0f;
+  for(int j=0;j<3;j++) for(int i=0;i<3;i++) for(int k=0;k<3;k++) res[i+3*j] += a[3*j+k]*b[3*k+i];
+}
+static int mat3_inverse(const float *a, float *inv)                    /* mat3_invert, matrix3.inc:67-95 */
+{
+#define A(y, x) a[(y - 1)*3 + (x - 1)]
+  const float det = A(1, 1)*(A(3, 3)*A(2, 2) - A(3, 2)*A(2, 3)) - A(2, 1)*(A(3, 3)*A(1, 2) - A(3, 2)*A(1, 3)) + A(3, 1)*(A(2, 3)*A(1, 2) - A(2, 2)*A(1, 3));
+  if(!(det != 0.0f)) return 1;
+  const float invdet = 1.0f/det;
+  inv[0] =  invdet*(A(3, 3)*A(2, 2) - A(3, 2)*A(2, 3)); inv[1] = -invdet*(A(3, 3)*A(1, 2) - A(3, 2)*A(1, 3)); inv[2] =  invdet*(A(2, 3)*A(1, 2) - A(2, 2)*A(1, 3));
+  inv[3] = -invdet*(A(3, 3)*A(2, 1) - A(3, 1)*A(2, 3)); inv[4] =  invdet*(A(3, 3)*A(1, 1) - A(3, 1)*A(1, 3)); inv[5] = -invdet*(A(2, 3)*A(1, 1) - A(2, 1)*A(1, 3));
+  inv[6] =  invdet*(A(3, 2)*A(2, 1) - A(3, 1)*A(2, 2)); inv[7] = -invdet*(A(3, 2)*A(1, 1) - A(3, 1)*A(1, 2)); inv[8] =  invdet*(A(2, 2)*A(1, 1) - A(2, 1)*A(1, 2));
+#undef A
+  return 0;
+}
+typedef struct { uint64_t magic, width, height; uint16_t channels, flags; float gain; } fb_header_b200_t;
+static int envmap_open(struct scene_b200_t *s, const char *args)
+{
+  char name[1024] = "", path[2200];
+  float b = 1.0f, rot[3] = {0.0f, 0.0f, 0.0f};
+  if(sscanf(args, "%1023s %f %f %f %f", name, &b, rot, rot+1, rot+2) < 1) return 1;
+  snprintf(path, sizeof(path), "%s", name);
+  FILE *f = fopen(path, "rb");
+  if(!f) { snprintf(path, sizeof(path), "%s/%s", s->searchpath, name); f = fopen(path, "rb"); }   /* fb_map: as given, then beside the scene */
+  if(!f) return 1;
+  fseek(f, 0, SEEK_END);
+  const long size = ftell(f);
+  fseek(f, 0, SEEK_SET);
+  fb_header_b200_t h;
+  if(size < (long)sizeof(h) || fread(&h, sizeof(h), 1, f) != 1 || h.magic != 1936686951lu || h.channels != 4 ||
+     (long)(h.width*h.height*4*sizeof(float) + sizeof(h)) != size || h.width != 2*h.height) { fclose(f); return 1; }
+  s->env_size = (size_t)size - sizeof(h);
+  s->env_map = malloc(s->env_size);
+  if(!s->env_map || fread(s->env_map, 1, s->env_size, f) != s->env_size) { fclose(f); return 1; }
+  fclose(f);
+  cb_envmap_t *e = &s->envmap;
+  e->width = (uint32_t)h.width; e->height = (uint32_t)h.height; e->pixels = (const float *)s->env_map; e->mul = b;
+  const float ax[3] = {1, 0, 0}, ay[3] = {0, 1, 0}, az[3] = {0, 0, 1};
+  float rx[9], ry[9], rz[9], tmp[9];
+  rotation(ax, rot[0], rx); rotation(ay, rot[1], ry); rotation(az, rot[2], rz);
+  mat3_product(ry, rz, tmp);
+  mat3_product(rx, tmp, e->world);
+  return mat3_inverse(e->world, e->world_inv);
+}
 
 static void chomp_comment(char *s)
 {
@@ -375,6 +433,7 @@ void scene_b200_free(struct scene_b200_t *s)
   if(s->accel) accel_cleanup(s->accel);
   if(s->prims.shape) prims_cleanup(&s->prims);
   free(s->materials);
+  free(s->env_map);
   free(s->nra2);
   rgb2spec_b200_free(s->rgb2spec);
   tables_free(&s->tables);
@@ -418,8 +477,14 @@ struct scene_b200_t *scene_b200_open(const char *nra2_file, const char *coeff_fi
     s->sky = CB_SKY_CONST;
     s->sky_scale = scale*rgb_to_coeff(s->rgb2spec, col, s->sky_coeff);
   }
-  else if(!strncmp(sky, "daylight", 8) || !strcmp(sky, "sky_envmap"))
-  { /* the reference's other sky implementations (src/shaders/daylight.h, sky_envmap.c) are SURVEY 8f rank 3 */
+  else if(!strcmp(sky, "sky_envmap"))
+  {
+    if(envmap_open(s, strstr(line, "sky_envmap") + 10))
+    { fprintf(stderr, "[envmap] could not read hdri file (w = 2h, four channels of rgb2spec coefficients + scale)!\n"); fclose(f); scene_b200_free(s); return 0; }
+    s->sky = CB_SKY_ENVMAP;
+  }
+  else if(!strncmp(sky, "daylight", 8))
+  { /* the reference's analytic daylight model (src/shaders/daylight.h) is SURVEY 8f rank 3 */
     fprintf(stderr, "[scene b200] sky `%s' is not supported by the gpu path (only `black', `cloudy' and `sky_const'); no cpu fallback\n", sky);
     fclose(f); scene_b200_free(s); return 0;
   }
@@ -536,6 +601,7 @@ int scene_b200_prepare(struct scene_b200_t *s, uint32_t width, uint32_t height, 
   d->sky = s->sky;
   for(int k=0;k<3;k++) d->sky_coeff[k] = s->sky_coeff[k];
   d->sky_scale = s->sky_scale;
+  d->envmap = s->sky == CB_SKY_ENVMAP ? &s->envmap : 0;
   d->media = s->nra2->media; d->num_media = s->nra2->num_media; d->exterior_medium = s->nra2->exterior_medium;
   d->max_path_len = 32; d->frame = frame; d->rank = 0; d->world = 1; d->batch_paths = 0;
   s->render = render_b200_init(s->accel, d);

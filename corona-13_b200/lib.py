@@ -263,7 +263,7 @@ class Render:
     """wavefront pt/ptdl integrator on top of an Accel (include/corona_b200_render.h)"""
 
     def __init__(self, accel, camera, materials, width, height, sampler=1, pointsampler=0, colour=0, max_path_len=32,
-                 frame=0, rank=0, world=1, batch_paths=0, sky=0, sky_coeff=(0.0, 0.0, 0.0), sky_scale=1.0):
+                 frame=0, rank=0, world=1, batch_paths=0, sky=0, sky_coeff=(0.0, 0.0, 0.0), sky_scale=1.0, envmap=None):
         from . import scene_io as sio
         self.L = _load_render()
         self.accel = accel
@@ -283,6 +283,16 @@ class Render:
         d.sky = sky
         d.sky_coeff[:] = [float(x) for x in sky_coeff]
         d.sky_scale = float(sky_scale)
+        if envmap is not None:   # dict(pixels (h, w, 4) float32, mul, world, world_inv) as scene_io.envmap_params returns it
+            self._env_px = np.ascontiguousarray(envmap["pixels"], np.float32)
+            e = sio.CEnvmap()
+            e.height, e.width = self._env_px.shape[:2]
+            e.pixels = self._env_px.ctypes.data
+            e.mul = float(envmap["mul"])
+            e.world[:] = [float(x) for x in np.asarray(envmap["world"], np.float32).reshape(-1)]
+            e.world_inv[:] = [float(x) for x in np.asarray(envmap["world_inv"], np.float32).reshape(-1)]
+            self._env = e
+            d.envmap = C.cast(C.pointer(e), C.c_void_p)
         self._media = materials.cmedia()
         d.media = C.cast(self._media, C.c_void_p)
         d.num_media = len(materials.media)

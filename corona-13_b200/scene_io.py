@@ -24,9 +24,9 @@ BSDF_DIFFUSE, BSDF_DIELECTRIC, BSDF_METAL, BSDF_DIFFDIEL = 0, 1, 2, 3
 SAMPLER_PT, SAMPLER_PTDL = 0, 1
 POINTS_RAND, POINTS_HALTON = 0, 1
 COLOUR_XYZ, COLOUR_REC709 = 0, 1
-SKY_BLACK, SKY_CLOUDY, SKY_CONST = 0, 1, 2
+SKY_BLACK, SKY_CLOUDY, SKY_CONST, SKY_ENVMAP = 0, 1, 2, 3
 SKIES = {"sky_const": SKY_CONST, "black": SKY_BLACK, "cloudy": SKY_CLOUDY, "cloudy_sky": SKY_CLOUDY, "clear_sky": SKY_CLOUDY}   # src/shader.c:626-641
-SKY_MODULES = ("daylight", "sky_envmap")    # real sky implementations the GPU path does not have: refused, never substituted
+SKY_MODULES = ("daylight",)    # real sky implementations the GPU path does not have: refused, never substituted
 
 
 def sky_kind(name):
@@ -39,6 +39,8 @@ def sky_kind(name):
         return SKY_CLOUDY
     if name == "sky_const":
         return SKY_CONST
+    if name == "sky_envmap":
+        return SKY_ENVMAP
     if name.startswith("daylight") or name in SKY_MODULES:
         raise ValueError(f"sky `{name}' is not supported by the gpu path (no cpu fallback)")
     return SKY_CLOUDY
@@ -78,7 +80,12 @@ class CRenderDesc(C.Structure):
                 ("sampler", C.c_int32), ("pointsampler", C.c_int32), ("colour_camera", C.c_int32), ("max_path_len", C.c_int32),
                 ("frame", C.c_uint64), ("rank", C.c_uint32), ("world", C.c_uint32), ("batch_paths", C.c_uint64),
                 ("sky", C.c_int32), ("sky_coeff", C.c_float * 3), ("sky_scale", C.c_float), ("exterior_medium", C.c_int32),
-                ("media", C.c_void_p), ("num_media", C.c_int32), ("pad", C.c_int32)]
+                ("media", C.c_void_p), ("num_media", C.c_int32), ("pad", C.c_int32), ("envmap", C.c_void_p)]
+
+
+class CEnvmap(C.Structure):
+    _fields_ = [("width", C.c_uint32), ("height", C.c_uint32), ("pixels", C.c_void_p), ("mul", C.c_float),
+                ("world", C.c_float * 9), ("world_inv", C.c_float * 9)]
 
 
 class CRenderStats(C.Structure):
@@ -425,6 +432,54 @@ def parse_nra2(path, rgb2spec, checker_table=None, metal_tables=None):
         r = lines[3 + n + i].split()
         shapes.append((int(r[0]), r[1]))
     return ms, shapes, sky
+
+
+FB_MAGIC = 1936686951
+
+
+def write_fb(path, pixels):
+    """framebuffer file as fb_map reads it (include/framebuffer.h:26-35,52-84): 32-byte header + float32 texels"""
+    px = np.ascontiguousarray(pixels, np.float32)
+    h, w, c = px.shape
+    with open(path, "wb") as f:
+        f.write(np.array([FB_MAGIC, w, h], "<u8").tobytes() + np.array([c, 0], "<u2").tobytes() + np.float32(1.0).tobytes())
+        f.write(px.tobytes())
+
+
+def read_fb(path):
+    raw = open(path, "rb").read()
+    magic, w, h = np.frombuffer(raw[:24], "<u8")
+    c = int(np.frombuffer(raw[24:26], "<u2")[0])
+    if magic != FB_MAGIC or len(raw) != 32 + int(w) * int(h) * c * 4:
+        raise ValueError(f"{path}: not a framebuffer file")
+    return np.frombuffer(raw[32:], "<f4").reshape(int(h), int(w), c).copy()
+
+
+def _mat3_rotate(axis, angle_deg):
+    """mat3_rotate (include/matrix3.inc:111-134), float arithmetic"""
+    f = np.float32
+    a = f(angle_deg) / f(180) * np.pi
+    s, c = f(np.sin(f(a))), f(np.cos(f(a)))
+    x, y, z = (f(v) for v in axis)
+    one = f(1)
+    return np.array([[x*x + (one - x*x)*c, x*y*(one - c) - z*s, x*z*(one - c) + y*s],
+                     [y*x*(one - c) + z*s, y*y + (one - y*y)*c, y*z*(one - c) - x*s],
+                     [z*x*(one - c) - y*s, z*y*(one - c) + x*s, z*z + (one - z*z)*c]], np.float32)
+
+
+def envmap_params(args, searchpath="."):
+    """sky_envmap's init (src/shaders/sky_envmap.c:272-311): '<file.fb> [brightness] [rot_x rot_y rot_z]' (degrees) ->
+    dict(pixels, mul, world, world_inv)"""
+    f = args.split()
+    name = f[0]
+    vals = [float(x) for x in f[1:5]] + [1.0, 0.0, 0.0, 0.0][len(f[1:5]):]
+    path = name if os.path.exists(name) else os.path.join(searchpath, name)
+    px = read_fb(path)
+    if px.shape[2] != 4 or px.shape[1] != 2 * px.shape[0]:
+        raise ValueError("environment map has to be w = 2 h with 4 channels (rgb2spec coefficients + scale)")
+    rx, ry, rz = _mat3_rotate((1, 0, 0), vals[1]), _mat3_rotate((0, 1, 0), vals[2]), _mat3_rotate((0, 0, 1), vals[3])
+    world = (rx.astype(np.float32) @ (ry @ rz).astype(np.float32)).astype(np.float32)     # mat3_mul(ry, rz, tmp); mat3_mul(rx, tmp, world)
+    return dict(pixels=px, mul=vals[0], world=world, world_inv=np.linalg.inv(world.astype(np.float64)).astype(np.float32))
 
 
 def sky_const_params(rgb2spec, args):

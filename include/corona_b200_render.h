@@ -106,7 +106,20 @@ enum { CB_SAMPLER_PT = 0, CB_SAMPLER_PTDL = 1 };          /* src/sampler.d/pt.c,
 enum { CB_POINTS_RAND = 0, CB_POINTS_HALTON = 1 };        /* src/pointsampler.d/rand.c, halton.c */
 enum { CB_COLOUR_XYZ = 0, CB_COLOUR_REC709 = 1 };         /* COL_camera (Makefile:122-136) */
 enum { CB_SKY_BLACK = 0, CB_SKY_CLOUDY = 1,               /* line 1 of the .nra2: built-in skies of src/shader.c:262-334,633-660 */
-       CB_SKY_CONST = 2 };                                /* `sky_const r g b [scale]`: src/shaders/sky_const.c */
+       CB_SKY_CONST = 2,                                  /* `sky_const r g b [scale]`: src/shaders/sky_const.c */
+       CB_SKY_ENVMAP = 3 };                               /* `sky_envmap file.fb brightness [rot_x rot_y rot_z]`: src/shaders/sky_envmap.c */
+
+/* latitude-longitude environment map as sky_envmap.c maps it from its `.fb` file (include/framebuffer.h:26-35: four floats per
+ * texel = rgb2spec coefficients + scale, width == 2*height), brightness and the rotation built from the three angles
+ * (sky_envmap.c:286-300).  The library builds the importance-sampling mip hierarchy of sky_envmap.c:329-361 itself. */
+typedef struct cb_envmap_t
+{
+  uint32_t width, height;
+  const float *pixels;
+  float mul;
+  float world[9], world_inv[9];  /* row major, dir_world = world * dir_map */
+}
+cb_envmap_t;
 
 typedef struct cb_render_desc_t
 {
@@ -131,6 +144,7 @@ typedef struct cb_render_desc_t
   const cb_medium_t *media;
   int32_t num_media;
   int32_t pad;
+  const cb_envmap_t *envmap;     /* CB_SKY_ENVMAP */
 }
 cb_render_desc_t;
 

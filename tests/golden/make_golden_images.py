@@ -43,9 +43,11 @@ def load_tables():
     return z["checker"], {k[6:]: z[k] for k in z.files if k.startswith("metal_")}
 
 
-def golden_case(name, scene, shader_lines, shape_mats, cam, w, h, spp, variants, sky="black"):
+def golden_case(name, scene, shader_lines, shape_mats, cam, w, h, spp, variants, sky="black", env_pixels=None):
     tmp = tempfile.mkdtemp(prefix="corona_golden_")
     try:
+        if env_pixels is not None:    # `sky_envmap <file> ...`: the map lives beside the scene (fb_map falls back to rt.searchpath)
+            IO.write_fb(os.path.join(tmp, sky.split()[1]), env_pixels)
         shapes = []
         for i, sh in enumerate(scene.shapes):
             sh.write_geo(os.path.join(tmp, f"shape{i}.geo"))
@@ -70,6 +72,9 @@ def golden_case(name, scene, shader_lines, shape_mats, cam, w, h, spp, variants,
         if ms.media:
             pack["media"] = np.frombuffer(bytes(ms.cmedia()), np.uint8)   # flattened cb_medium_t[]
             pack["exterior_medium"] = np.int64(ms.exterior_medium)
+        if env_pixels is not None:
+            e = IO.envmap_params(sky[len("sky_envmap"):], tmp)
+            pack["env_pixels"], pack["env_mul"], pack["env_world"], pack["env_world_inv"] = e["pixels"], np.float32(e["mul"]), e["world"], e["world_inv"]
         if sky.startswith("sky_const"):
             co, sc = IO.sky_const_params(IO.Rgb2Spec(IO.coeff_path(ROOT)), sky[len("sky_const"):])
             pack["sky_coeff"], pack["sky_scale"] = np.float32(co), np.float32(sc)
@@ -179,7 +184,36 @@ def case_glass_metal():
                 [2, 8, 8, 11, 14, 17, 5], cam, 192, 128, 128, ["pt_halton", "ptdl_halton", "ptdl_rand"])
 
 
-def case_sky(with_light, sky="cloudy", name=None):
+def synthetic_envmap(w=128, h=64):
+    """a small HDR latitude-longitude map in sky_envmap's texel format (rgb2spec coefficients + scale): blue-white gradient above
+    the horizon, a sun 500x brighter than the sky, brown ground; row 0 is the +z pole (theta = pi*y/h, sky_envmap.c:150-160)"""
+    r2s = IO.Rgb2Spec(IO.coeff_path(ROOT))
+    px = np.zeros((h, w, 4), np.float32)
+    sun = np.float64([np.sin(1.0) * np.sin(0.6), np.sin(1.0) * np.cos(0.6), np.cos(1.0)])
+    for j in range(h):
+        th = np.pi * (j + 0.5) / h
+        for i in range(w):
+            ph = 2 * np.pi * (i + 0.5) / w - np.pi
+            d = np.float64([np.sin(ph) * np.sin(th), np.cos(ph) * np.sin(th), np.cos(th)])
+            if d[2] > 0:
+                t = d[2]
+                rgb = np.float64([0.35, 0.5, 0.9]) * t + np.float64([0.9, 0.9, 0.85]) * (1 - t)
+                if d @ sun > 0.985:
+                    rgb = rgb + np.float64([500.0, 450.0, 350.0])
+            else:
+                rgb = np.float64([0.25, 0.18, 0.1])
+            mul, co = r2s.rgb_to_coeff(rgb.astype(np.float32))
+            px[j, i, :3], px[j, i, 3] = co, mul
+    return px
+
+
+def case_envmap():
+    """the environment-map sky module (src/shaders/sky_envmap.c): emission lookup, mip-hierarchy importance sampling for next event
+    estimation and its pdf for MIS, brightness and a rotation about two axes; a geometric light beside it"""
+    case_sky(True, "sky_envmap env.fb 40 0 25 30", "envmap", env_pixels=synthetic_envmap())
+
+
+def case_sky(with_light, sky="cloudy", name=None, env_pixels=None):
     """the built-in `cloudy' sky (src/shader.c:268-334): environment vertices, sky next-event estimation and its MIS; with and
     without a geometric light beside it (lights_pdf_type splits the next-event budget 50:50 then, list.c:76-88)"""
     terrain = S.terrain(1800, 5, material=0)
@@ -195,7 +229,7 @@ def case_sky(with_light, sky="cloudy", name=None):
              "metal Cu", "color g 1 1 1 0.25", "mult 1 12 11"]
     cam = IO.Camera(pos=(13.0, 10.0, 8.0), lookat=(0.0, 0.0, 3.0), aperture_value=7, exposure_value=14, focal_length=0.35, iso=100.0)
     golden_case(name or ("sky_light" if with_light else "sky"), S.Scene(shapes, "sky"), lines, mats, cam, 160, 96, 128,
-                ["ptdl_halton", "pt_halton", "ptdl_rand"], sky=sky)
+                ["ptdl_halton", "pt_halton", "ptdl_rand"], sky=sky, env_pixels=env_pixels)
 
 
 def case_fog():
@@ -340,7 +374,7 @@ def case_furnace():
                 sky="sky_const 1 1 1 1")
 
 
-CASES = {"furnace": case_furnace, "skin": case_skin, "vstack": case_vstack, "fog": case_fog, "subsurf": case_subsurf, "sky_const": lambda: case_sky(True, "sky_const 0.3 0.5 0.9 800", "sky_const"), "sky": lambda: case_sky(False), "sky_light": lambda: case_sky(True), "diffuse_static": case_diffuse_static, "c10": case_c10, "motion": case_motion, "glass_metal": case_glass_metal}
+CASES = {"envmap": case_envmap, "furnace": case_furnace, "skin": case_skin, "vstack": case_vstack, "fog": case_fog, "subsurf": case_subsurf, "sky_const": lambda: case_sky(True, "sky_const 0.3 0.5 0.9 800", "sky_const"), "sky": lambda: case_sky(False), "sky_light": lambda: case_sky(True), "diffuse_static": case_diffuse_static, "c10": case_c10, "motion": case_motion, "glass_metal": case_glass_metal}
 
 if __name__ == "__main__":
     subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "oracle"), "ref"])

