@@ -160,6 +160,8 @@ struct RenderDev
   const EnvDev *env;               // CB_SKY_ENVMAP: in device memory (the out-of-line env_* functions take its address)
   uint32_t exterior_medium;        // 1 + index of the medium the camera sits in (shader_exterior_medium), 0 = vacuum
   int32_t has_media;               // any medium in the scene: the free-flight / transmittance code paths are live
+  float *dbor;                     // `--dbor n` (view.c:291,339-350): n cascade buffers of fb_w*fb_h*3 floats, level major; NULL = off
+  int32_t num_dbors;
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -200,6 +202,37 @@ __device__ bool splat(const RenderDev &R, float pixel_i, float pixel_j, float la
     const float f = weight*w[4*v+u];
     float *p = R.fb + 3*((size_t)(x0+u) + (size_t)wd*(y0+v));
     atomic_add_f(p+0, col[0]*f); atomic_add_f(p+1, col[1]*f); atomic_add_f(p+2, col[2]*f);
+  }
+  if(R.num_dbors > 1)
+  { // density based outlier rejection cascade (view_splat_col, view.c:497-522): the sample goes to the two buffers whose
+    // brightness range [2^l, 2^(l+1)) brackets its mean colour, split linearly in 1/value, through the same filter taps
+    const float value = (col[0] + col[1] + col[2])/3.f;
+    if(value > 0.0f)
+    {
+      const float lg = log2f(value);
+      const float logval = 0.0f > lg ? 0.0f : lg;
+      const int li = (int)logval;
+      const int l = li < 0 ? 0 : li > R.num_dbors-1 ? R.num_dbors-1 : li;
+      const int up = l + 1;
+      const float lraw = value < 1.f ? 1.f : (((float)(1 << l)/value) - 0.5f)/0.5f;
+      const float lv = lraw < 0.0f ? 0.0f : lraw > 1.0f ? 1.0f : lraw;
+      const float uv = 1.f - lv;
+      const bool last = l == R.num_dbors-1;
+      const size_t level = (size_t)wd*ht*3;
+      float coll[3], colu[3];
+      for(int k=0;k<3;k++) { coll[k] = last ? col[k] : lv*col[k]; colu[k] = uv*col[k]; }
+      for(int v=v0;v<v4;v++) for(int u=u0;u<u4;u++)
+      {
+        const float f = weight*w[4*v+u];
+        float *p = R.dbor + level*l + 3*((size_t)(x0+u) + (size_t)wd*(y0+v));
+        atomic_add_f(p+0, coll[0]*f); atomic_add_f(p+1, coll[1]*f); atomic_add_f(p+2, coll[2]*f);
+        if(up < R.num_dbors)
+        {
+          p += level;
+          atomic_add_f(p+0, colu[0]*f); atomic_add_f(p+1, colu[1]*f); atomic_add_f(p+2, colu[2]*f);
+        }
+      }
+    }
   }
   return true;
 }
@@ -593,6 +626,7 @@ k_sky_miss(RenderDev R, uint32_t n, const PathState *__restrict__ st, const cb_h
           w = pdf_v/(pdf_nee + pdf_v);
         }
         if(!pp_contributes(pp, pdf_v, pdf_nee)) w = 0.0f;   // sampler_mis in float range only (PathPdf)
+        if(R.sampler == CB_SAMPLER_PTNEE) w = lre_length(s.lre) + 1 == 2 ? 1.0f : 0.0f;   // ptnee.c:53-58: only the directly visible sky
         did = splat(R, s.pixel_i, s.pixel_j, s.lambda, (s.thr*em)*w);   // lights_eval_vertex: isotropic for the envmap (list.c:272-273)
       }
     }
@@ -735,7 +769,14 @@ k_shade(RenderDev R, uint32_t n, const PathState *__restrict__ st_in, const cb_r
         float pdf_v_final = pdf_v;                           // v[vi].pdf as later vertices will see it
         bool stop = false;
         // ---- emission: path_update_throughput + sampler splat
-        if(v.mode & M_EMIT)
+        if((v.mode & M_EMIT) && R.sampler == CB_SAMPLER_PTNEE)
+        { // ptnee.c:53-58: emission found by extension only counts where next-event estimation cannot create the path, on
+          // directly visible emitters, unweighted.  (Upstream tests `v[2].mode` of the two-vertex path there -- the slot
+          // BEHIND its last vertex, i.e. whatever the worker thread's previous path left in it -- so its own result on those
+          // pixels depends on thread scheduling; the vertex the comment in the source means, v[1], is used here.)
+          if(len == 2) did_splat = splat(R, s.pixel_i, s.pixel_j, s.lambda, thr*light_eval(v, omega));
+        }
+        else if(v.mode & M_EMIT)
         {
           const float L = thr*light_eval(v, omega);
           float w = 1.0f;
@@ -756,15 +797,16 @@ k_shade(RenderDev R, uint32_t n, const PathState *__restrict__ st_in, const cb_r
             else { thr *= 1.0f/p_survival; pdf_v_final = pdf_v*p_survival; }
           }
         }
-        if(R.sampler == CB_SAMPLER_PTDL && len >= R.max_path_len) stop = true;
+        const bool nee_only = R.sampler == CB_SAMPLER_PTNEE;   // ptnee.c: next events without a competing technique, weight 1
+        if((R.sampler == CB_SAMPLER_PTDL || nee_only) && len >= R.max_path_len) stop = true;
         const PathPdf pp_v = pp_mul(pp, pdf_v_final);        // product of v[1..vi].pdf
         uint32_t mt = s.bits >> 8;
         int rand_cnt_v = 5;
         if(vi == 1) rand_cnt_v = 1;
         // ---- next event estimation (ptdl.c:136-148, nee.h:87-243)
-        if(!stop && R.sampler == CB_SAMPLER_PTDL)
+        if(!stop && (R.sampler == CB_SAMPLER_PTDL || nee_only))
         {
-          (void)point_mt(R.points, index, mt++);   // the rr draw against nee_probability() == 1
+          if(!nee_only) (void)point_mt(R.points, index, mt++);   // ptdl's rr draw against nee_probability() == 1 (ptdl.c:136-137)
           if(len >= 32) stop = true;               // nee_sample refuses at PATHSPACE_MAX_VERTS and the sampler returns
           else
           {
@@ -814,7 +856,7 @@ k_shade(RenderDev R, uint32_t n, const PathState *__restrict__ st_in, const cb_r
                     const float thr_l = ((thr*bsdf)*(T_nee*edf))*Gl;
                     const float pdf_nee = pdf_sky*R.p_sky;
                     const float pdf_ext = (vol_pdf*vtx_pdf<KINDS>(R.mats, vb, omega, d))*Gl;
-                    const float w = pp_contributes(pp_v, pdf_nee, pdf_ext) ? pdf_nee/(pdf_ext + pdf_nee) : 0.0f;
+                    const float w = nee_only ? 1.0f : pp_contributes(pp_v, pdf_nee, pdf_ext) ? pdf_nee/(pdf_ext + pdf_nee) : 0.0f;
                     if(thr_l*w > 0.0f && total_dist > 0.0f)
                     {
                       have_nee = true;
@@ -888,7 +930,7 @@ k_shade(RenderDev R, uint32_t n, const PathState *__restrict__ st_in, const cb_r
                       // mis against extending the path into the light (ptdl.c:142-146)
                       const float pdf_nee = R.lights.p_geo*pdf_l;
                       const float pdf_ext = (vol_pdf*vtx_pdf<KINDS>(R.mats, vb, omega, d))*Gl;
-                      const float w = pp_contributes(pp_v, pdf_nee, pdf_ext) ? pdf_nee/(pdf_ext + pdf_nee) : 0.0f;
+                      const float w = nee_only ? 1.0f : pp_contributes(pp_v, pdf_nee, pdf_ext) ? pdf_nee/(pdf_ext + pdf_nee) : 0.0f;
                       if(thr_l*w > 0.0f)
                       {
                         have_nee = true;
@@ -1149,6 +1191,7 @@ struct cb200_render
   // (st[cur] / rays[cur], slots [0, n_alive)) and ride along with the next pass' waves until cb200_render_flush
   uint32_t n_alive; int cur;
   float *own_fb;
+  float *own_dbor;               // cb200_render_set_dbor
   // asynchronous snapshots: device-side copy of the accumulation buffer, drained to the host on a stream of its own
   float *snap_stage; cudaStream_t snap_stream; cudaEvent_t snap_ready, snap_done; int snap_pending;
   // coherence sort of every traced wave: keys ride with the rays (ping-pong), iota -> order by radix sort
@@ -1397,6 +1440,7 @@ void cb200_render_destroy(cb200_render_t *r)
   if(!r) return;
   if(r->snap_stream) { cudaStreamSynchronize(r->snap_stream); cudaStreamDestroy(r->snap_stream); cudaEventDestroy(r->snap_ready); cudaEventDestroy(r->snap_done); }
   for(void *p : r->owned) cudaFree(p);
+  if(r->own_dbor) cudaFree(r->own_dbor);
   for(cudaEvent_t e : r->ev_pool) cudaEventDestroy(e);
   if(r->h_cnt) cudaFreeHost(r->h_cnt);
   delete r;
@@ -1430,6 +1474,8 @@ cb200_render_t *cb200_render_create(cb200_accel_t *a, const cb_render_desc_t *de
     { cb200_set_error("render_create: material references a medium that was not supplied"); return nullptr; }
   if(desc->exterior_medium && desc->sky != CB_SKY_BLACK)
   { cb200_set_error("render_create: an exterior medium under a non-black sky is not supported (no CPU fallback)"); return nullptr; }
+  if(desc->sampler != CB_SAMPLER_PT && desc->sampler != CB_SAMPLER_PTDL && desc->sampler != CB_SAMPLER_PTNEE)
+  { cb200_set_error("render_create: unknown sampler (pt, ptdl and ptnee exist on the gpu; no CPU fallback)"); return nullptr; }
   cb200_render *r = new cb200_render();
   r->accel = a;
   r->desc = *desc;
@@ -1438,6 +1484,7 @@ cb200_render_t *cb200_render_create(cb200_accel_t *a, const cb_render_desc_t *de
   r->timing = r->counting = 0; r->ev_used = 0; r->d_trav_cnt = nullptr;
   r->n_alive = 0; r->cur = 0;
   r->snap_stage = nullptr; r->snap_stream = nullptr; r->snap_pending = 0;
+  r->own_dbor = nullptr;
   cb200_scene *s = a->scene;
   RenderDev &D = r->dev;
   memset(&D, 0, sizeof(D));
@@ -1543,6 +1590,7 @@ int cb200_render_clear(cb200_render_t *r, void *stream)
 {
   if(!r) { cb200_set_error("render_clear: null"); return CB200_ERR_ARG; }
   CB_CUDA(cudaMemsetAsync(r->dev.fb, 0, (size_t)r->dev.fb_w*r->dev.fb_h*3*sizeof(float), (cudaStream_t)stream));
+  if(r->dev.dbor) CB_CUDA(cudaMemsetAsync(r->dev.dbor, 0, (size_t)r->dev.num_dbors*r->dev.fb_w*r->dev.fb_h*3*sizeof(float), (cudaStream_t)stream));
   CB_CUDA(cudaMemsetAsync(r->d_cnt, 0, sizeof(ShadeCounters), (cudaStream_t)stream));
   CB_CUDA(cudaMemsetAsync(r->d_trav_cnt, 0, 8*sizeof(unsigned long long), (cudaStream_t)stream));
   r->n_alive = 0;   // paths still in flight are dropped with the image they belong to
@@ -1601,6 +1649,43 @@ int cb200_render_download(cb200_render_t *r, float *fb_host, void *stream)
   { const int rc = snapshot_drain(r); if(rc) return rc; }
   if(r->n_alive) { const int rc = cb200_render_flush(r, stream); if(rc) return rc; }
   CB_CUDA(cudaMemcpyAsync(fb_host, r->dev.fb, (size_t)r->dev.fb_w*r->dev.fb_h*3*sizeof(float), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+  CB_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+  return 0;
+}
+
+// `--dbor n` (view.c:291: clamped to [0, 20]; the cascade exists for n > 1, view.c:339)
+int cb200_render_set_dbor(cb200_render_t *r, int32_t levels)
+{
+  if(!r) { cb200_set_error("render_set_dbor: null"); return CB200_ERR_ARG; }
+  if(levels < 0) levels = 0;
+  if(levels > 20) levels = 20;
+  CB_CUDA(cudaDeviceSynchronize());
+  if(r->own_dbor) { cudaFree(r->own_dbor); r->own_dbor = nullptr; }
+  r->dev.dbor = nullptr; r->dev.num_dbors = 0;
+  if(levels > 1)
+  {
+    const size_t bytes = (size_t)levels*r->dev.fb_w*r->dev.fb_h*3*sizeof(float);
+    if(cudaMalloc(&r->own_dbor, bytes) != cudaSuccess) { r->own_dbor = nullptr; cb200_set_error("render_set_dbor: out of device memory"); return CB200_ERR_NOMEM; }
+    CB_CUDA(cudaMemset(r->own_dbor, 0, bytes));
+    r->dev.dbor = r->own_dbor; r->dev.num_dbors = levels;
+  }
+  return 0;
+}
+
+int cb200_render_num_dbors(cb200_render_t *r) { return r ? r->dev.num_dbors : 0; }
+
+void *cb200_render_dbor_device(cb200_render_t *r, int32_t level)
+{
+  if(!r || level < 0 || level >= r->dev.num_dbors) return nullptr;
+  return r->dev.dbor + (size_t)level*r->dev.fb_w*r->dev.fb_h*3;
+}
+
+int cb200_render_download_dbor(cb200_render_t *r, int32_t level, float *fb_host, void *stream)
+{
+  if(!r || !fb_host || level < 0 || level >= r->dev.num_dbors) { cb200_set_error("render_download_dbor: bad arguments"); return CB200_ERR_ARG; }
+  if(r->n_alive) { const int rc = cb200_render_flush(r, stream); if(rc) return rc; }
+  const size_t count = (size_t)r->dev.fb_w*r->dev.fb_h*3;
+  CB_CUDA(cudaMemcpyAsync(fb_host, r->dev.dbor + count*level, count*sizeof(float), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
   CB_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
   return 0;
 }

@@ -94,6 +94,10 @@ int render_b200_pass(struct render_t *r, uint64_t first_index, uint64_t count, f
 /* finish the paths still in flight and fetch the complete image (before fb_export / screenshots) */
 int render_b200_finish(struct render_t *r, float *fb);
 uint64_t render_b200_overlays(const struct render_t *r);
+/* `--dbor n` of the reference's view (src/view.c:291,339-350,497-522): switch the outlier rejection cascade on (n > 1) before
+ * the first progression, fetch level `level` (host W*H*3 floats, un-gained like the framebuffer) after render_b200_finish */
+int render_b200_set_dbor(struct render_t *r, int levels);
+int render_b200_dbor(struct render_t *r, int level, float *fb);
 void *render_b200_handle(const struct render_t *r);
 
 /* ---- scene ingestion (host/scene_b200.c): .nra2 shader + shape lists, .cam, rgb2spec coefficients, measured tables ---- */

@@ -1,15 +1,16 @@
 /* main_b200.c -- `corona_b200`: the reference's offline command line for the hot path, on the GPU modules.
  *
  *   corona_b200 <scene.nra2> [-s spp] [-w width] [-h height] [--frame n] [-x [name]] [-c camfile] [--batch n]
- *               [--sampler pt|ptdl] [--points rand|halton] [--colour xyz|rec709] [--coeff file] [--tables file]
- *               [--dump-materials file] [-q]
+ *               [--sampler pt|ptdl|ptnee] [--points rand|halton] [--colour xyz|rec709] [--coeff file] [--tables file]
+ *               [--dump-materials file] [--dbor n] [-q]
  *
  * Same arguments and defaults as the reference binary where they exist there (src/main.c:250-282,415-437,
  * src/view.c:262-297, src/display.d/null.c:47-56): -s samples per pixel then write the image and quit, -w/-h frame size
  * (padded to multiples of 32), --frame = rt.anim_frame (seeds the point sampler, default 1), -x output name (default
  * `render'), data/ergb2spec.coeff relative to the working directory.  --sampler / --points / --colour stand in for the
  * reference's compile-time MOD_sampler / MOD_pointsampler / COL_camera.  Writes <basename><name>_fb00.pfm like
- * view_write_images (src/view.c:549).  Without a CUDA device it refuses: there is no CPU path in this binary.
+ * view_write_images (src/view.c:549); --dbor n (src/view.c:291) adds the outlier rejection cascade of view_splat_col and its
+ * <basename><name>_dbor%02d.pfm files (view.c:553-556).  Without a CUDA device it refuses: there is no CPU path in this binary.
  */
 #include "corona_host.h"
 #include "corona_b200.h"
@@ -26,14 +27,14 @@ int main(int argc, char *argv[])
   if(argc < 2)
   {
     fprintf(stderr, "usage: %s <scene.nra2> [-s spp] [-w width] [-h height] [--frame n] [-x [name]] [-c camfile] [--batch n]\n"
-                    "          [--sampler pt|ptdl] [--points rand|halton] [--colour xyz|rec709] [--coeff file] [--tables file] [-q]\n", argv[0]);
+                    "          [--sampler pt|ptdl|ptnee] [--points rand|halton] [--colour xyz|rec709] [--coeff file] [--tables file] [--dbor n] [-q]\n", argv[0]);
     return 1;
   }
   const char *scene = argv[1], *coeff = "data/ergb2spec.coeff", *tables = getenv("CORONA_B200_TABLES"), *camfile = 0, *dump = 0;
   char outname[256] = "render";
   uint64_t spp = 0, frame = 1, batch = 1;
   uint32_t width = 1024, height = 576;       /* src/view.c:261-262 */
-  int sampler = CB_SAMPLER_PTDL, points = CB_POINTS_RAND, colour = CB_COLOUR_XYZ, quiet = 0;
+  int sampler = CB_SAMPLER_PTDL, points = CB_POINTS_RAND, colour = CB_COLOUR_XYZ, quiet = 0, dbor = 0;
   for(int i=2;i<argc;i++)
   {
     if     (!strcmp(argv[i], "-s") && i+1 < argc) spp = strtoull(argv[++i], 0, 10);
@@ -43,12 +44,13 @@ int main(int argc, char *argv[])
     else if(!strcmp(argv[i], "--frame") && i+1 < argc) frame = strtoull(argv[++i], 0, 10);
     else if(!strcmp(argv[i], "--batch") && i+1 < argc) batch = strtoull(argv[++i], 0, 10);
     else if(!strcmp(argv[i], "-x")) { if(i+1 < argc && argv[i+1][0] != '-') snprintf(outname, sizeof(outname), "%s", argv[++i]); }
-    else if(!strcmp(argv[i], "--sampler") && i+1 < argc) { ++i; sampler = !strcmp(argv[i], "pt") ? CB_SAMPLER_PT : CB_SAMPLER_PTDL; }
+    else if(!strcmp(argv[i], "--sampler") && i+1 < argc) { ++i; sampler = !strcmp(argv[i], "pt") ? CB_SAMPLER_PT : !strcmp(argv[i], "ptnee") ? CB_SAMPLER_PTNEE : CB_SAMPLER_PTDL; }
     else if(!strcmp(argv[i], "--points") && i+1 < argc) { ++i; points = !strcmp(argv[i], "halton") ? CB_POINTS_HALTON : CB_POINTS_RAND; }
     else if(!strcmp(argv[i], "--colour") && i+1 < argc) { ++i; colour = !strcmp(argv[i], "rec709") ? CB_COLOUR_REC709 : CB_COLOUR_XYZ; }
     else if(!strcmp(argv[i], "--coeff") && i+1 < argc) coeff = argv[++i];
     else if(!strcmp(argv[i], "--tables") && i+1 < argc) tables = argv[++i];
     else if(!strcmp(argv[i], "--dump-materials") && i+1 < argc) dump = argv[++i];
+    else if(!strcmp(argv[i], "--dbor") && i+1 < argc) { dbor = atoi(argv[++i]); dbor = dbor < 0 ? 0 : dbor > 20 ? 20 : dbor; }   /* view.c:291 */
     else if(!strcmp(argv[i], "-q")) quiet = 1;
     else if((!strcmp(argv[i], "-t") || !strcmp(argv[i], "-b") || !strcmp(argv[i], "-o")) && i+1 < argc) ++i;   /* cpu threads / backups / timeout: n/a */
   }
@@ -85,6 +87,7 @@ int main(int argc, char *argv[])
   const uint64_t per_frame = (uint64_t)d->width*d->height;
   float *fb = (float *)malloc(sizeof(float)*per_frame*3);
   struct render_t *r = scene_b200_render(s);
+  if(dbor > 1 && render_b200_set_dbor(r, dbor)) { free(fb); scene_b200_free(s); return 3; }
   t0 = now();
   uint64_t done = 0;
   while(done < spp)
@@ -100,6 +103,11 @@ int main(int argc, char *argv[])
   snprintf(filename, sizeof(filename), "%s%s_fb00.pfm", scene_b200_basename(s), outname);
   const float gain = spp ? d->camera.iso/(100.0f*(float)spp) : 0.0f;    /* src/view.c:656 */
   if(scene_b200_write_pfm(filename, fb, d->width, d->height, gain)) { fprintf(stderr, "[main] could not write %s\n", filename); free(fb); scene_b200_free(s); return 4; }
+  for(int l=0;dbor>1&&l<dbor;l++)
+  { /* view_write_images, src/view.c:553-556 (the gcov buffers next to them are never written to upstream and are not produced) */
+    snprintf(filename, sizeof(filename), "%s%s_dbor%02d.pfm", scene_b200_basename(s), outname, l);
+    if(render_b200_dbor(r, l, fb) || scene_b200_write_pfm(filename, fb, d->width, d->height, gain)) { fprintf(stderr, "[main] could not write %s\n", filename); free(fb); scene_b200_free(s); return 4; }
+  }
   if(!quiet) printf("[main] saving framebuffers to %s%s\n", scene_b200_basename(s), outname);
   free(fb);
   scene_b200_free(s);

@@ -114,5 +114,19 @@ int render_b200_finish(struct render_t *r, float *fb)
   return 0;
 }
 
+int render_b200_set_dbor(struct render_t *r, int levels)
+{
+  if(!r) { fprintf(stderr, "[render b200] dbor: not initialised\n"); return 1; }
+  if(cb200_render_set_dbor(r->r, levels)) { fprintf(stderr, "[render b200] dbor failed: %s\n", cb200_last_error()); return 1; }
+  return 0;
+}
+
+int render_b200_dbor(struct render_t *r, int level, float *fb)
+{
+  if(!r || !fb) { fprintf(stderr, "[render b200] dbor: bad arguments\n"); return 1; }
+  if(cb200_render_download_dbor(r->r, level, fb, 0)) { fprintf(stderr, "[render b200] dbor failed: %s\n", cb200_last_error()); return 1; }
+  return 0;
+}
+
 uint64_t render_b200_overlays(const struct render_t *r) { return r ? r->overlays : 0; }
 void *render_b200_handle(const struct render_t *r) { return r ? r->r : 0; }

@@ -242,6 +242,11 @@ def _load_render():
     L.cb200_render_fb_device.argtypes = [vp]
     L.cb200_render_download.argtypes = [vp, vp, vp]
     L.cb200_render_set_framebuffer.argtypes = [vp, vp]
+    L.cb200_render_set_dbor.argtypes = [vp, C.c_int32]
+    L.cb200_render_num_dbors.argtypes = [vp]
+    L.cb200_render_dbor_device.restype = vp
+    L.cb200_render_dbor_device.argtypes = [vp, C.c_int32]
+    L.cb200_render_download_dbor.argtypes = [vp, C.c_int32, vp, vp]
     L.cb200_render_snapshot.argtypes = [vp, vp, vp]
     L.cb200_render_snapshot_async.argtypes = [vp, vp, vp]
     L.cb200_render_snapshot_wait.argtypes = [vp]
@@ -256,7 +261,8 @@ def _load_render():
 
 RENDER_SYMBOLS = ["cb200_render_create", "cb200_render_destroy", "cb200_render_pass", "cb200_render_pass_stream", "cb200_render_flush", "cb200_render_clear", "cb200_render_instrument",
                   "cb200_render_fb_device", "cb200_render_set_framebuffer", "cb200_render_download", "cb200_render_snapshot", "cb200_render_snapshot_async", "cb200_render_snapshot_wait", "cb200_render_stats", "cb200_render_point",
-                  "cb200_render_camera_rays", "cb200_render_bsdf", "cb200_render_medium"]
+                  "cb200_render_camera_rays", "cb200_render_bsdf", "cb200_render_medium",
+                  "cb200_render_set_dbor", "cb200_render_num_dbors", "cb200_render_dbor_device", "cb200_render_download_dbor"]
 
 
 class Render:
@@ -324,6 +330,24 @@ class Render:
 
     def set_framebuffer(self, device_ptr):
         _check(self.L.cb200_render_set_framebuffer(self.r, device_ptr or None), "cb200_render_set_framebuffer")
+
+    def set_dbor(self, levels):
+        """`--dbor n` (src/view.c:291): n > 1 switches the outlier rejection cascade of view_splat_col on"""
+        _check(self.L.cb200_render_set_dbor(self.r, int(levels)), "cb200_render_set_dbor")
+
+    def num_dbors(self):
+        return int(self.L.cb200_render_num_dbors(self.r))
+
+    def dbor_device(self, level):
+        return self.L.cb200_render_dbor_device(self.r, int(level))
+
+    def dbor_images(self, spp=None):
+        """the cascade buffers scaled by the framebuffer's gain (view.c:659-664), (levels, H, W, 3)"""
+        spp = self.spp if spp is None else spp
+        out = np.zeros((self.num_dbors(), self.height, self.width, 3), np.float32)
+        for l in range(out.shape[0]):
+            _check(self.L.cb200_render_download_dbor(self.r, l, _ptr(out[l]), None), "cb200_render_download_dbor")
+        return out * np.float32(self.camera.iso / (100.0 * max(spp, 1e-9)))
 
     def framebuffer(self):
         fb = np.zeros((self.height, self.width, 3), np.float32)

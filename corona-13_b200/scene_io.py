@@ -21,7 +21,7 @@ CB_MAX_MATOPS = 6
 OP_COLOR, OP_CHECKERSG = 1, 2
 SLOTS = {"d": 0, "s": 1, "e": 2, "v": 3, "g": 4, "r": 5, "t": 6}
 BSDF_DIFFUSE, BSDF_DIELECTRIC, BSDF_METAL, BSDF_DIFFDIEL = 0, 1, 2, 3
-SAMPLER_PT, SAMPLER_PTDL = 0, 1
+SAMPLER_PT, SAMPLER_PTDL, SAMPLER_PTNEE = 0, 1, 2
 POINTS_RAND, POINTS_HALTON = 0, 1
 COLOUR_XYZ, COLOUR_REC709 = 0, 1
 SKY_BLACK, SKY_CLOUDY, SKY_CONST, SKY_ENVMAP = 0, 1, 2, 3

@@ -102,7 +102,8 @@ typedef struct cb_medium_t
 cb_medium_t;
 
 /* ---- render description ---------------------------------------------------------------------------------- */
-enum { CB_SAMPLER_PT = 0, CB_SAMPLER_PTDL = 1 };          /* src/sampler.d/pt.c, ptdl.c */
+enum { CB_SAMPLER_PT = 0, CB_SAMPLER_PTDL = 1,            /* src/sampler.d/pt.c, ptdl.c */
+       CB_SAMPLER_PTNEE = 2 };                            /* src/sampler.d/ptnee.c: next-event estimation only, no mis */
 enum { CB_POINTS_RAND = 0, CB_POINTS_HALTON = 1 };        /* src/pointsampler.d/rand.c, halton.c */
 enum { CB_COLOUR_XYZ = 0, CB_COLOUR_REC709 = 1 };         /* COL_camera (Makefile:122-136) */
 enum { CB_SKY_BLACK = 0, CB_SKY_CLOUDY = 1,               /* line 1 of the .nra2: built-in skies of src/shader.c:262-334,633-660 */
@@ -188,6 +189,15 @@ void *cb200_render_fb_device(cb200_render_t *r);
  * caller double-buffer: reduce / read one buffer while the next progression renders into the other. */
 int  cb200_render_set_framebuffer(cb200_render_t *r, void *d_fb);
 int  cb200_render_download(cb200_render_t *r, float *fb_host, void *stream);   /* flushes first: the finished image */
+/* `--dbor n` (src/view.c:291,339-350): the density based outlier rejection cascade of view_splat_col (view.c:497-522).  With
+ * n > 1 every splat also goes, through the same Blackman-Harris taps, into the two of n extra buffers (W*H*3 floats each)
+ * whose brightness range brackets the sample; n <= 1 switches the cascade off.  Call between progressions (it synchronises the
+ * device); the buffers start at zero and are cleared by cb200_render_clear.  Level buffers are scaled by the same gain as the
+ * framebuffer (view.c:659-664) and written as `<basename><suffix>_dbor%02d.pfm` by the reference (view.c:553-556). */
+int  cb200_render_set_dbor(cb200_render_t *r, int32_t levels);
+int  cb200_render_num_dbors(cb200_render_t *r);
+void *cb200_render_dbor_device(cb200_render_t *r, int32_t level);              /* for the reduce across ranks */
+int  cb200_render_download_dbor(cb200_render_t *r, int32_t level, float *fb_host, void *stream);   /* flushes first */
 /* the accumulation buffer as it stands, WITHOUT flushing: what a progressive display shows between streamed progressions
  * (the stragglers' contributions arrive with a later snapshot; the reference's display reads its framebuffer mid-flight too) */
 int  cb200_render_snapshot(cb200_render_t *r, float *fb_host, void *stream);

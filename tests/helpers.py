@@ -204,7 +204,7 @@ class GoldenImage:
         """'ptdl_halton_rec709' -> keyword arguments of lib.Render"""
         IO = cb.scene_io
         f = key.split("_")
-        return dict(sampler=IO.SAMPLER_PTDL if f[0] == "ptdl" else IO.SAMPLER_PT,
+        return dict(sampler={"pt": IO.SAMPLER_PT, "ptdl": IO.SAMPLER_PTDL, "ptnee": IO.SAMPLER_PTNEE}[f[0]],
                     pointsampler=IO.POINTS_HALTON if f[1] == "halton" else IO.POINTS_RAND,
                     colour=IO.COLOUR_REC709 if "rec709" in f else IO.COLOUR_XYZ)
 

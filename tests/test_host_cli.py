@@ -156,3 +156,27 @@ def test_c_camera_reader_matches_fixture_reader(built, tmp_path):
     bad = str(tmp_path / "bad.cam")
     open(bad, "wb").write(b"x" * 77)
     assert H.scene_b200_read_camera(bad.encode(), 64, 64, C.byref(IO.CCamera())) != 0
+
+
+@needs_coeff
+@pytest.mark.gpu
+def test_cli_dbor_writes_the_cascade(built, tmp_path):
+    """`--dbor n` through the command line: <basename>render_dbor%02d.pfm next to the framebuffer (view_write_images,
+    src/view.c:553-556), each level matching the reference's file of the same name (tests/golden/dbor.npz)"""
+    IO = cb.scene_io
+    g = GoldenImage("c10")
+    z = np.load(os.path.join(ROOT, "tests", "golden", "dbor.npz"))
+    nra2 = g.write_files(str(tmp_path))
+    p = run_cli(nra2, "-s", str(g.spp), "-w", str(g.w), "-h", str(g.h), "--frame", "1", "--sampler", "pt", "--points", "halton", "--dbor", "12", "-q")
+    assert p.returncode == 0, p.stderr + p.stdout
+    img = IO.read_pfm(os.path.join(str(tmp_path), "testrender_fb00.pfm"))
+    lv = np.stack([IO.read_pfm(os.path.join(str(tmp_path), f"testrender_dbor{l:02d}.pfm")) for l in range(12)])
+    assert not os.path.exists(os.path.join(str(tmp_path), "testrender_dbor12.pfm"))
+    assert np.all(np.abs(lv.sum(axis=0) - img) <= 1e-3 * np.maximum(img, img.mean()))
+    a, b = z["c10_pt_halton_dbor_seed1"], z["c10_pt_halton_dbor_seed2"]
+    for l in range(12):
+        if a[l].mean() < 1e-4 * img.mean():
+            continue
+        noise, _ = image_stats(a[l], b[l])
+        rel, _ = image_stats(a[l], lv[l])
+        assert rel <= 0.45 * noise, f"level {l}: relRMSE {rel:.4f} vs noise floor {noise:.4f}"
