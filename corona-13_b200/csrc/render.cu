@@ -417,12 +417,25 @@ __device__ __forceinline__ uint32_t sample_cdf_dev(const float *cdf, uint32_t nu
   return t;
 }
 
-// prims_sample + prims_retime (prims.c:177-252) for triangles and quads
+// prims_sample + prims_retime (prims.c:177-252) for triangles, quads and spheres (line primitives have a zero or negative
+// area upstream, line.h:55-67, and are never picked)
 __device__ void light_point(const SceneGeo &S, uint64_t pid, float r0, float r1, float time, Vtx &h)
 {
   const uint32_t vcnt = (uint32_t)(pid >> 61) & 7u;
   h.prim_lo = (uint32_t)pid; h.prim_hi = (uint32_t)(pid >> 32);
-  if(vcnt == CB_PRIM_QUAD)
+  if(vcnt == CB_PRIM_SPHERE)
+  { // prims.c:225-230 + geo_sphere_retime (sphere.h:38-49) + sample_sphere (sampler_common.h:136-143)
+    h.u = r0;
+    h.v = (float)((double)acosf(r1)/PI_D);
+    const float x1 = -(cosf((float)((double)h.v*PI_D)) - 1.f)/2.f;
+    const float z = 1.f - 2.f*x1;
+    const float rr = sqrtf(1.f - z*z);
+    const float phi = (float)((double)2.f*PI_D*(double)h.u);
+    const float radius = __uint_as_float(geo_vtx(S, pid, 0, 0)->n);
+    const V3 c = geo_vertex_time(S, pid, 0, time);
+    h.x = mk3(c.x + radius*(rr*cosf(phi)), c.y + radius*(rr*sinf(phi)), c.z + radius*z);
+  }
+  else if(vcnt == CB_PRIM_QUAD)
   {
     h.u = r0; h.v = r1;
     const V3 v0 = geo_vertex_time(S, pid, 0, time), v2 = geo_vertex_time(S, pid, 2, time);
@@ -449,6 +462,12 @@ __device__ void light_point(const SceneGeo &S, uint64_t pid, float r0, float r1,
 __device__ void prim_test_geo(const SceneGeo &S, uint64_t pid, const RayD &r, HitD &h)
 {
   const uint32_t vcnt = (uint32_t)(pid >> 61) & 7u;
+  if(vcnt == CB_PRIM_SPHERE)
+  { // geo_sphere_intersect (sphere.h:112-166): only the distance matters here
+    const float t = sphere_t(geo_vertex_time(S, pid, 0, r.time), __uint_as_float(geo_vtx(S, pid, 0, 0)->n), r);
+    if(t > r.min_dist && t < h.dist) h.dist = t;
+    return;
+  }
   if(vcnt != CB_PRIM_TRI && vcnt != CB_PRIM_QUAD) return;
   const uint32_t id_lo = (uint32_t)pid, id_hi = (uint32_t)(pid >> 32);
   const V3 v0 = geo_vertex_time(S, pid, 0, r.time), v1 = geo_vertex_time(S, pid, 1, r.time), v2 = geo_vertex_time(S, pid, 2, r.time);

@@ -374,7 +374,24 @@ def case_furnace():
                 sky="sky_const 1 1 1 1")
 
 
-CASES = {"envmap": case_envmap, "furnace": case_furnace, "skin": case_skin, "vstack": case_vstack, "fog": case_fog, "subsurf": case_subsurf, "sky_const": lambda: case_sky(True, "sky_const 0.3 0.5 0.9 800", "sky_const"), "sky": lambda: case_sky(False), "sky_light": lambda: case_sky(True), "diffuse_static": case_diffuse_static, "c10": case_c10, "motion": case_motion, "glass_metal": case_glass_metal}
+def case_sphere_light():
+    """emissive analytic spheres (one of them moving) beside a quad light: next-event estimation picks primitives by area x
+    radiance over all three (lights/list.c:56-104), samples sphere points with prims_sample's sphere branch (prims.c:225-230,
+    sphere.h:38-49), and the shadow ray ends on the sphere's own near side (path_visible, pathspace.c:311-344)"""
+    terrain = S.terrain(1800, 11, material=0)
+    soup = S.soup(900, 12, rmin=0.2, rmax=0.8, material=0)
+    ball = S.analytic_shape("sphere", (-2.5, 1.5, 3.2), 1.0, material=0)
+    lamp0 = S.analytic_shape("sphere", (2.0, -1.5, 5.5), 0.6, material=0)
+    lamp1 = S.analytic_shape("sphere", (-4.0, -3.0, 4.0), 0.35, material=0, motion=(0.8, 0.4, 0.3))
+    light = S.quad_light((3.0, 4.0, 9.0), 1.0, 1)
+    lines = ["diffuse", "color d 0.6 0.6 0.55", "mult 1 1 0", "color d 0 0 0", "color e 60 50 40 1.", "mult 2 3 4 0",
+             "color d 0.2 0.5 0.8", "mult 1 6 0", "color e 90 120 160 1.", "mult 2 3 8 0", "dielectric 1.5 40", "color g 1 1 1 0.0", "mult 1 11 10"]
+    cam = IO.Camera(pos=(13.0, -11.0, 9.0), lookat=(0.0, 0.0, 3.0), aperture_value=6, exposure_value=11, focal_length=0.35, iso=100.0)
+    golden_case("sphere_light", S.Scene([terrain, soup, ball, lamp0, lamp1, light], "sphere_light"), lines, [2, 7, 12, 5, 9, 5], cam, 160, 96, 128,
+                ["ptdl_halton", "pt_halton", "ptdl_rand"])
+
+
+CASES = {"sphere_light": case_sphere_light, "envmap": case_envmap, "furnace": case_furnace, "skin": case_skin, "vstack": case_vstack, "fog": case_fog, "subsurf": case_subsurf, "sky_const": lambda: case_sky(True, "sky_const 0.3 0.5 0.9 800", "sky_const"), "sky": lambda: case_sky(False), "sky_light": lambda: case_sky(True), "diffuse_static": case_diffuse_static, "c10": case_c10, "motion": case_motion, "glass_metal": case_glass_metal}
 
 if __name__ == "__main__":
     subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "oracle"), "ref"])

@@ -35,7 +35,7 @@ MEAN_TOL = 0.01      # per-channel mean, Halton variants (measured <= 0.005)
 # the media code is test_medium_matches_reference.
 MEDIA_CASES = ("fog", "subsurf", "skin", "furnace")
 MEDIA_HALTON_FRAC = 0.9
-CASES = ["diffuse_static", "c10", "motion", "glass_metal", "sky", "sky_light", "sky_const", "fog", "subsurf", "vstack", "skin", "furnace", "envmap"]
+CASES = ["diffuse_static", "c10", "motion", "glass_metal", "sky", "sky_light", "sky_const", "fog", "subsurf", "vstack", "skin", "furnace", "envmap", "sphere_light"]
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
 

@@ -28,7 +28,7 @@ def run_cli(nra2, *args):
 
 
 @needs_coeff
-@pytest.mark.parametrize("case", ["diffuse_static", "c10", "motion", "glass_metal", "sky_light", "sky_const", "fog", "subsurf", "vstack", "skin", "envmap"])
+@pytest.mark.parametrize("case", ["diffuse_static", "c10", "motion", "glass_metal", "sky_light", "sky_const", "fog", "subsurf", "vstack", "skin", "envmap", "sphere_light"])
 def test_c_parser_flattens_shader_list_like_the_fixture(built, tmp_path, case):
     IO = cb.scene_io
     g = GoldenImage(case)
@@ -81,7 +81,7 @@ def test_cli_refuses_without_a_gpu_and_on_foreign_skies(built, lib, tmp_path):
 @needs_coeff
 @pytest.mark.gpu
 @pytest.mark.parametrize("case,key", [("c10", "ptdl_halton"), ("c10", "pt_halton"), ("glass_metal", "ptdl_halton"), ("motion", "ptdl_halton_rec709"),
-                                      ("sky_light", "ptdl_halton"), ("sky_const", "ptdl_halton"), ("vstack", "pt_halton"), ("envmap", "ptdl_halton")])
+                                      ("sky_light", "ptdl_halton"), ("sky_const", "ptdl_halton"), ("vstack", "pt_halton"), ("envmap", "ptdl_halton"), ("sphere_light", "ptdl_halton")])
 def test_cli_render_matches_reference_image(built, tmp_path, case, key):
     IO = cb.scene_io
     g = GoldenImage(case)
