@@ -267,7 +267,11 @@ k_intersect(DevAccel A, const cb_ray_t *__restrict__ rays, const float *__restri
     const uint32_t mN = __ballot_sync(FULL, state == ST_NODE);
     const uint32_t mP = __ballot_sync(FULL, state == ST_PRIM);
     if(!(mN | mP)) break;   // nothing in flight: the refill above ran (all lanes idle) and the queue is empty
-    const bool do_prims = (mN == 0u) || (__popc(mP) >= prim_threshold);
+    // prim_threshold < 0: relative to the lanes that hold a ray (-12 = 12/32 of them), so that a warp waiting for its next
+    // refill with many finished lanes does not wait for nearly all remaining lanes to reach a leaf
+    const int live = __popc(mN | mP);
+    const int thr = prim_threshold >= 0 ? prim_threshold : max(2, (live*(-prim_threshold) + 31) >> 5);
+    const bool do_prims = (mN == 0u) || (__popc(mP) >= thr);
 
     bool need_pop = false, new_cur = false;
     if(do_prims)
@@ -468,7 +472,11 @@ k_visible(DevAccel A, const cb_ray_t *__restrict__ rays, const float *__restrict
     const uint32_t mN = __ballot_sync(FULL, state == ST_NODE);
     const uint32_t mP = __ballot_sync(FULL, state == ST_PRIM);
     if(!(mN | mP)) break;
-    const bool do_prims = (mN == 0u) || (__popc(mP) >= prim_threshold);
+    // prim_threshold < 0: relative to the lanes that hold a ray (-12 = 12/32 of them), so that a warp waiting for its next
+    // refill with many finished lanes does not wait for nearly all remaining lanes to reach a leaf
+    const int live = __popc(mN | mP);
+    const int thr = prim_threshold >= 0 ? prim_threshold : max(2, (live*(-prim_threshold) + 31) >> 5);
+    const bool do_prims = (mN == 0u) || (__popc(mP) >= thr);
     bool need_pop = false;
     int result = -1;
     if(do_prims)
@@ -642,16 +650,17 @@ static unsigned long long *g_tickets = nullptr;   // ring of ticket counters, ze
 static std::atomic<unsigned> g_ticket_next{0};
 static std::mutex g_ticket_mutex;
 #define NUM_TICKETS 256
-static int g_prim_threshold = -1;
+static int g_prim_threshold = 1000;
 
 static int prim_threshold()
 {
-  if(g_prim_threshold < 0)
+  if(g_prim_threshold == 1000)
   {
     const char *e = getenv("CB200_PRIM_THRESHOLD");
-    int v = e ? atoi(e) : 12;
-    if(v < 1) v = 1;
+    int v = e ? atoi(e) : -16;   // swept on the 10 M-triangle bench: absolute 12 -> 104.5 ms of closest-hit time per 8 progressions, relative 10/12/16/20/24/28 of 32 -> 103.8/102.4/101.4/102.5/105.9/115.0
+    if(v == 0) v = 1;
     if(v > 32) v = 32;
+    if(v < -32) v = -32;
     g_prim_threshold = v;
   }
   return g_prim_threshold;
