@@ -73,3 +73,14 @@ class FramebufferReducer:
             b.zero_()
         if self.accum is not None:
             self.accum.zero_()
+
+
+def reduce_dbor(levels, rank=0, world=1, dist=None):
+    """the `--dbor n` cascade buffers (src/view.c:497-522) are additive like the framebuffer, but only needed at export
+    (view_write_images, view.c:553-556): one reduce of the stacked (n, H, W, 3) tensor to rank 0 at the end instead of one per
+    progression.  Returns the sum on rank 0, None on the other ranks (the tensor itself when world == 1)."""
+    if world == 1:
+        return levels
+    dist.reduce(levels, 0)
+    return levels if rank == 0 else None
+

@@ -34,6 +34,12 @@ def worker(rank, world, port, out):
         fb.add_(fake_progression(first, count))
         red.submit(s)
     total = red.finish()
+    # the outlier rejection cascade: per-rank level buffers, summed once at export
+    lv = P.reduce_dbor(torch.stack([fake_progression(1000 * rank + l, PATHS) for l in range(3)]), rank, world, dist)
+    assert (lv is None) == (rank != 0)
+    if lv is not None:
+        want = sum(torch.stack([fake_progression(1000 * r + l, PATHS) for l in range(3)]) for r in range(world))
+        assert torch.allclose(lv, want)
     out[rank] = (ranges, None if total is None else total.clone().numpy())
     dist.barrier()
     dist.destroy_process_group()
