@@ -32,7 +32,7 @@ int main(int argc, char *argv[])
   }
   const char *scene = argv[1], *coeff = "data/ergb2spec.coeff", *tables = getenv("CORONA_B200_TABLES"), *camfile = 0, *dump = 0;
   char outname[256] = "render";
-  uint64_t spp = 0, frame = 1, batch = 1;
+  uint64_t spp = 0, frame = 1, batch = 0;
   uint32_t width = 1024, height = 576;       /* src/view.c:261-262 */
   int sampler = CB_SAMPLER_PTDL, points = CB_POINTS_RAND, colour = CB_COLOUR_XYZ, quiet = 0, dbor = 0;
   for(int i=2;i<argc;i++)
@@ -54,7 +54,6 @@ int main(int argc, char *argv[])
     else if(!strcmp(argv[i], "-q")) quiet = 1;
     else if((!strcmp(argv[i], "-t") || !strcmp(argv[i], "-b") || !strcmp(argv[i], "-o")) && i+1 < argc) ++i;   /* cpu threads / backups / timeout: n/a */
   }
-  if(batch < 1) batch = 1;
   const double t_open = now();
   struct scene_b200_t *s = scene_b200_open(scene, coeff, tables);
   if(!s) { fprintf(stderr, "[main] could not load nra2 file!\n"); return 2; }
@@ -85,6 +84,12 @@ int main(int argc, char *argv[])
   if(!quiet) printf("[main] %lu primitives, accel + upload took %.3f seconds\n", (unsigned long)scene_b200_num_prims(s), now() - t0);
   if(!quiet) printf("[display] simulating %lu samples per pixel\n", (unsigned long)spp);
   const uint64_t per_frame = (uint64_t)d->width*d->height;
+  if(batch < 1)
+  { /* no --batch given: hand the device as many progressions per call as fill its path pool (the image does not depend on
+     * the grouping: a path is a function of its index; rt.batch_frames only groups work upstream too, src/view.c:630-638) */
+    batch = ((1ull << 22) + per_frame - 1)/per_frame;
+    if(batch > 64) batch = 64;
+  }
   float *fb = (float *)malloc(sizeof(float)*per_frame*3);
   struct render_t *r = scene_b200_render(s);
   if(dbor > 1 && render_b200_set_dbor(r, dbor)) { free(fb); scene_b200_free(s); return 3; }
