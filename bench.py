@@ -59,8 +59,9 @@ REFDIR = os.path.join(ROOT, "oracle", "_ref")
 
 def ncu_traffic():
     """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel from the committed `ncu --set full` capture
-    of this same command (profiles/r1e_k_intersect_ncu.json); None when the summary is not there"""
-    p = os.path.join(ROOT, "profiles", "r1e_k_intersect_ncu.json")
+    of the same workload (profiles/r1h_k_intersect_ncu.json: the full ~8.3 M-ray waves among the captured launches); None when the
+    summary is not there"""
+    p = os.path.join(ROOT, "profiles", "r1h_k_intersect_ncu.json")
     try:
         rows = json.load(open(p))
         tot = []
@@ -70,8 +71,9 @@ def ncu_traffic():
             unit_r = [k for k in r if k.startswith("dram__bytes_read.sum")][0]
             unit_w = [k for k in r if k.startswith("dram__bytes_write.sum")][0]
             scale = lambda u: 1e9 if "Gbyte" in u else 1e6 if "Mbyte" in u else 1e3 if "Kbyte" in u else 1.0
-            tot.append(rd[0] * scale(unit_r) + wr[0] * scale(unit_w))
-        return sum(tot) / len(tot), os.path.relpath(p, ROOT)
+            tot.append((wr[0] * scale(unit_w), rd[0] * scale(unit_r) + wr[0] * scale(unit_w)))
+        full = [t for w, t in tot if w >= 0.9 * max(w for w, _ in tot)]   # hit records written ~ rays of the launch
+        return sum(full) / len(full), os.path.relpath(p, ROOT)
     except Exception:
         return None, None
 
@@ -411,7 +413,7 @@ def main():
         "roofline": {"bound": "hbm", "kernel": "k_intersect (closest-hit traversal, all launches of the timed region, rank 0)",
                      "achieved": achieved, "peak": hbm, "unit": "GB/s", "frac": achieved / hbm, "peak_source": which, "traffic": traffic,
                      "traffic_note": f"DRAM bytes per ~8.3 M-ray launch from {traffic_src}: the ray and hit streams only -- nodes and primitives are "
-                                     "served by L1/L2, so HBM is not the binding roof (issue slots 73 %, L1 wavefronts 71 %)" if traffic else None,
+                                     "served by L1/L2, so HBM is not the binding roof (issue slots 72 %, L1 LSU data-pipe wavefronts 75 %)" if traffic else None,
                      "algorithmic_bytes_per_launch": bytes_per_ray * 8.3e6,
                      "bytes_per_ray": bytes_per_ray, "nodes_per_ray": n_node, "prims_per_ray": n_prim,
                      "rays": stt["rays_closest"], "kernel_ms": ms_closest},
