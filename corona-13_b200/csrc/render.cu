@@ -197,9 +197,12 @@ __device__ bool splat(const RenderDev &R, float pixel_i, float pixel_j, float la
   }
   if(weight <= 0.0f) return false;
   weight = 1.0f/weight;
+  // taps further than 1.5 pixels from the sample have weight exactly 0 (filter_bh_w returns 0 beyond its support): on average 9
+  // of the 16; adding +-0 leaves a pixel unchanged, so they are skipped (the reference adds them, with the same result)
   for(int v=v0;v<v4;v++) for(int u=u0;u<u4;u++)
   {
     const float f = weight*w[4*v+u];
+    if(f == 0.0f) continue;
     float *p = R.fb + 3*((size_t)(x0+u) + (size_t)wd*(y0+v));
     atomic_add_f(p+0, col[0]*f); atomic_add_f(p+1, col[1]*f); atomic_add_f(p+2, col[2]*f);
   }
@@ -224,6 +227,7 @@ __device__ bool splat(const RenderDev &R, float pixel_i, float pixel_j, float la
       for(int v=v0;v<v4;v++) for(int u=u0;u<u4;u++)
       {
         const float f = weight*w[4*v+u];
+        if(f == 0.0f) continue;
         float *p = R.dbor + level*l + 3*((size_t)(x0+u) + (size_t)wd*(y0+v));
         atomic_add_f(p+0, coll[0]*f); atomic_add_f(p+1, coll[1]*f); atomic_add_f(p+2, coll[2]*f);
         if(up < R.num_dbors)
