@@ -283,46 +283,77 @@ int cb200_accel_intersect_counted(const cb200_accel_t *a, const void *d_rays, co
 
 } // extern "C"
 
-// host-buffer entry points: stage through device buffers in chunks so that arbitrarily large batches work and
-// the copy of chunk k+1 overlaps the traversal of chunk k (two streams, pinned staging is the caller's choice)
+// host-buffer entry points: stage through device buffers in chunks so that arbitrarily large batches work and the upload of
+// chunk k+1, the traversal of chunk k and the download of chunk k-1 overlap (four streams; pinned host memory is the caller's
+// choice -- pageable buffers still work, the copies then run one after the other).  The staging buffers and streams are
+// allocated once per process and kept: a cudaMalloc / cudaFree pair per call cost as much as the traversal of a 4 Mi-ray batch.
+// Calls are serialised by a mutex (the pinned-worker callers of the single-ray entry points each hand in a batch of one).
+namespace {
+struct Staging
+{
+  static const int NS = 4;
+  static const uint64_t CH = 1ull << 19;          // rays per chunk: 21 MB up, 12.6 MB down
+  cudaStream_t st[NS] = {nullptr, nullptr, nullptr, nullptr};
+  cb_ray_t *d_rays[NS] = {nullptr, nullptr, nullptr, nullptr};
+  float *d_md[NS] = {nullptr, nullptr, nullptr, nullptr};
+  void *d_out[NS] = {nullptr, nullptr, nullptr, nullptr};
+  int device = -1;
+  std::mutex mutex;
+  void release()
+  {
+    for(int k=0;k<NS;k++)
+    {
+      if(st[k]) cudaStreamDestroy(st[k]);
+      cudaFree(d_rays[k]); cudaFree(d_md[k]); cudaFree(d_out[k]);
+      st[k] = nullptr; d_rays[k] = nullptr; d_md[k] = nullptr; d_out[k] = nullptr;
+    }
+    device = -1;
+  }
+  int prepare()
+  {
+    int dev = 0;
+    if(cudaGetDevice(&dev) != cudaSuccess) return CB200_ERR_CUDA;
+    if(device == dev) return 0;
+    if(device >= 0) release();   // (buffers of another device: start over on this one)
+    for(int k=0;k<NS;k++)
+    {
+      if(cudaStreamCreateWithFlags(&st[k], cudaStreamNonBlocking) != cudaSuccess) { st[k] = nullptr; release(); return CB200_ERR_CUDA; }
+      if(cudaMalloc(&d_rays[k], CH*sizeof(cb_ray_t)) != cudaSuccess || cudaMalloc(&d_md[k], CH*sizeof(float)) != cudaSuccess ||
+         cudaMalloc(&d_out[k], CH*sizeof(cb_hitrec_t)) != cudaSuccess) { release(); return CB200_ERR_NOMEM; }
+    }
+    device = dev;
+    return 0;
+  }
+};
+Staging g_staging;
+}
+
 template<typename OUT, typename LAUNCH>
 static int run_chunked(const cb_ray_t *rays, const float *max_dist, OUT *out, uint64_t n, LAUNCH launch)
 {
-  const uint64_t CH = 1ull << 22;
-  cudaStream_t st[2];
-  cb_ray_t *d_rays[2] = {nullptr, nullptr};
-  float *d_md[2] = {nullptr, nullptr};
-  OUT *d_out[2] = {nullptr, nullptr};
-  const uint64_t cap = n < CH ? n : CH;
-  int rc = 0;
-  for(int k=0;k<2;k++)
-  {
-    if(cudaStreamCreateWithFlags(&st[k], cudaStreamNonBlocking) != cudaSuccess) { st[k] = nullptr; rc = CB200_ERR_CUDA; }
-    if(cudaMalloc(&d_rays[k], cap*sizeof(cb_ray_t)) != cudaSuccess) rc = CB200_ERR_NOMEM;
-    if(max_dist && cudaMalloc(&d_md[k], cap*sizeof(float)) != cudaSuccess) rc = CB200_ERR_NOMEM;
-    if(cudaMalloc(&d_out[k], cap*sizeof(OUT)) != cudaSuccess) rc = CB200_ERR_NOMEM;
-  }
-  if(rc) g_error = "intersect_n: staging allocation failed";
-  for(uint64_t off=0, k=0; !rc && off<n; off+=CH, k^=1)
+  static_assert(sizeof(OUT) <= sizeof(cb_hitrec_t), "staging output slot");
+  std::lock_guard<std::mutex> lock(g_staging.mutex);
+  int rc = g_staging.prepare();
+  if(rc) { g_error = "intersect_n: staging allocation failed"; return rc; }
+  const uint64_t CH = Staging::CH;
+  uint64_t k = 0;
+  for(uint64_t off=0; !rc && off<n; off+=CH, k=(k+1)%Staging::NS)
   {
     const uint64_t m = (n - off) < CH ? (n - off) : CH;
-    cudaError_t e = cudaMemcpyAsync(d_rays[k], rays + off, m*sizeof(cb_ray_t), cudaMemcpyHostToDevice, st[k]);
-    if(e == cudaSuccess && max_dist) e = cudaMemcpyAsync(d_md[k], max_dist + off, m*sizeof(float), cudaMemcpyHostToDevice, st[k]);
+    cudaStream_t st = g_staging.st[k];
+    OUT *d_out = reinterpret_cast<OUT *>(g_staging.d_out[k]);
+    cudaError_t e = cudaMemcpyAsync(g_staging.d_rays[k], rays + off, m*sizeof(cb_ray_t), cudaMemcpyHostToDevice, st);
+    if(e == cudaSuccess && max_dist) e = cudaMemcpyAsync(g_staging.d_md[k], max_dist + off, m*sizeof(float), cudaMemcpyHostToDevice, st);
     if(e != cudaSuccess) { rc = cb200_cuda_fail(e, "h2d", __FILE__, __LINE__); break; }
-    rc = launch(d_rays[k], d_md[k], d_out[k], m, st[k]);
+    rc = launch(g_staging.d_rays[k], max_dist ? g_staging.d_md[k] : nullptr, d_out, m, st);
     if(rc) break;
-    e = cudaMemcpyAsync(out + off, d_out[k], m*sizeof(OUT), cudaMemcpyDeviceToHost, st[k]);
+    e = cudaMemcpyAsync(out + off, d_out, m*sizeof(OUT), cudaMemcpyDeviceToHost, st);
     if(e != cudaSuccess) { rc = cb200_cuda_fail(e, "d2h", __FILE__, __LINE__); break; }
   }
-  for(int k=0;k<2;k++)
+  for(int j=0;j<Staging::NS;j++)
   {
-    if(st[k])
-    {
-      cudaError_t e = cudaStreamSynchronize(st[k]);
-      if(e != cudaSuccess && !rc) rc = cb200_cuda_fail(e, "sync", __FILE__, __LINE__);
-      cudaStreamDestroy(st[k]);
-    }
-    cudaFree(d_rays[k]); cudaFree(d_md[k]); cudaFree(d_out[k]);
+    cudaError_t e = cudaStreamSynchronize(g_staging.st[j]);
+    if(e != cudaSuccess && !rc) rc = cb200_cuda_fail(e, "sync", __FILE__, __LINE__);
   }
   return rc;
 }
