@@ -80,7 +80,10 @@ int      cb200_accel_layout(const cb200_accel_t *a, uint32_t *node_bytes, uint32
  *      hit->dist, pathspace.c:762);  out: n cb_hitrec_t {prim,u,v,dist}, prim == INVALID and
  *      dist == max_dist when nothing was hit.  visible_n writes 1 = unoccluded like accel_visible.
  *      *_n take HOST pointers and include the copies; *_dev take DEVICE pointers and only
- *      enqueue on `stream` (a cudaStream_t, NULL = default stream).                            */
+ *      enqueue on `stream` (a cudaStream_t, NULL = default stream).
+ *      intersect_n / visible_n stage through persistent device buffers in 512 Ki-ray chunks on four streams (upload,
+ *      traversal and download of consecutive chunks overlap when the host buffers are pinned); calls from several host
+ *      threads are serialised.                                                                  */
 int cb200_accel_intersect_n(const cb200_accel_t *a, const cb_ray_t *rays, const float *max_dist,
                             cb_hitrec_t *out, uint64_t n);
 int cb200_accel_visible_n(const cb200_accel_t *a, const cb_ray_t *rays, const float *max_dist,
