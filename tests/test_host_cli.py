@@ -180,3 +180,22 @@ def test_cli_dbor_writes_the_cascade(built, tmp_path):
         noise, _ = image_stats(a[l], b[l])
         rel, _ = image_stats(a[l], lv[l])
         assert rel <= 0.45 * noise, f"level {l}: relRMSE {rel:.4f} vs noise floor {noise:.4f}"
+
+
+@needs_coeff
+@pytest.mark.gpu
+def test_cli_ptnee_matches_reference_image(built, tmp_path):
+    """`--sampler ptnee` (MOD_sampler=ptnee upstream) through the command line on the fixture scene whose emitter is not seen
+    directly, against the reference's own ptnee binary with the same Halton points (tests/golden/ptnee.npz)"""
+    IO = cb.scene_io
+    g = GoldenImage("diffuse_static")
+    z = np.load(os.path.join(ROOT, "tests", "golden", "ptnee.npz"))
+    nra2 = g.write_files(str(tmp_path))
+    p = run_cli(nra2, "-s", str(g.spp), "-w", str(g.w), "-h", str(g.h), "--frame", "1", "--sampler", "ptnee", "--points", "halton", "-q")
+    assert p.returncode == 0, p.stderr + p.stdout
+    img = IO.read_pfm(os.path.join(str(tmp_path), "testrender_fb00.pfm"))
+    a, b = z["diffuse_static_seed1"], z["diffuse_static_seed2"]
+    noise, _ = image_stats(a, b)
+    rel, ratio = image_stats(a, img)
+    assert rel <= 0.45 * noise, f"relRMSE {rel:.4f} vs noise floor {noise:.4f}"
+    assert np.all(np.abs(ratio - 1) < 0.01), ratio
