@@ -490,6 +490,12 @@ def test_dbor_cascade_matches_reference(gpu, run):
     assert not r.dbor_images(spp=1).any(), "render_clear leaves the cascade alone"
     r.set_dbor(0)
     assert r.num_dbors() == 0
+    r.set_dbor(1)                       # the cascade exists for n > 1 only (view.c:339)
+    assert r.num_dbors() == 0 and not r.dbor_device(0)
+    r.set_dbor(25)                      # clamped like view.c:291
+    assert r.num_dbors() == 20 and r.dbor_device(19) and not r.dbor_device(20)
+    import ctypes as C
+    assert r.L.cb200_render_download_dbor(r.r, 20, C.c_void_p(img.ctypes.data), None) != 0   # no such level: an error, not a crash
     r.close()
     acc.close()
     assert lv.shape == (levels, ) + img.shape and np.isfinite(lv).all()
