@@ -199,3 +199,38 @@ def test_cli_ptnee_matches_reference_image(built, tmp_path):
     rel, ratio = image_stats(a, img)
     assert rel <= 0.45 * noise, f"relRMSE {rel:.4f} vs noise floor {noise:.4f}"
     assert np.all(np.abs(ratio - 1) < 0.01), ratio
+
+
+@needs_coeff
+def test_c_parser_survives_malformed_scene_files(built, tmp_path):
+    """empty, truncated and ragged .nra2 files through the C reader (no GPU needed: --dump-materials stops after parsing): it
+    either loads what the reference's shader_init / common_load_scene would load (warning on stderr like upstream) or refuses
+    with exit code 2 -- never a signal"""
+    g = GoldenImage("c10")
+    nra2 = g.write_files(str(tmp_path))
+    lines = open(nra2).read().split("\n")
+    nsh = int(lines[1].split()[0])
+
+    def edit(k, text):
+        l2 = list(lines)
+        l2[k] = text
+        return "\n".join(l2)
+
+    cases = {"empty": ("", 2), "only_sky": (lines[0] + "\n", 2), "nothing_in_it": (lines[0] + "\n0\n0\n", 0),
+             "no_shape_section": ("\n".join(lines[:2 + nsh]) + "\n", 2), "zero_shapes": ("\n".join(lines[:2 + nsh]) + "\n0\n", 0),
+             "truncated_shader_list": ("\n".join(lines[:2 + nsh // 2]) + "\n", 2), "crlf": ("\r\n".join(lines), 0),
+             "huge_count": (edit(1, "999999"), 2), "negative_count": (edit(1, "-3"), 2), "garbage_count": (edit(1, "abc"), 2),
+             "mult_out_of_range": (edit(4, "mult 1 99 0"), 0), "mult_self_reference": (edit(4, "mult 2 2 0"), 0),
+             "color_without_arguments": (edit(3, "color d"), 0), "unknown_shader": (edit(3, "frobnicate 1 2 3"), 0),
+             "shape_material_out_of_range": (edit(2 + nsh + 1, "99 shape0"), 0), "missing_geo": (edit(2 + nsh + 1, "2 does_not_exist"), 0),
+             "shape_line_without_name": (edit(2 + nsh + 1, "2"), 0), "long_garbage": ("x" * 100000, 2)}
+    for name, (text, want) in cases.items():
+        path = str(tmp_path / (name + ".nra2"))
+        open(path, "w").write(text)
+        p = run_cli(path, "--dump-materials", str(tmp_path / (name + ".bin")))
+        assert p.returncode == want, f"{name}: exit code {p.returncode}, stderr: {p.stderr[-300:]}"
+    # upstream's own words for the two ragged shape lines (src/corona_common.c:44-62, src/prims.c:801-806)
+    p = run_cli(str(tmp_path / "missing_geo.nra2"), "--dump-materials", str(tmp_path / "x.bin"))
+    assert "could not load geo" in p.stderr and "decreasing shape count" in p.stderr
+    p = run_cli(str(tmp_path / "shape_material_out_of_range.nra2"), "--dump-materials", str(tmp_path / "x.bin"))
+    assert "out of bounds" in p.stderr
