@@ -229,7 +229,7 @@ def test_c_parser_survives_malformed_scene_files(built, tmp_path):
         open(path, "w").write(text)
         p = run_cli(path, "--dump-materials", str(tmp_path / (name + ".bin")))
         assert p.returncode == want, f"{name}: exit code {p.returncode}, stderr: {p.stderr[-300:]}"
-    # upstream's own words for the two ragged shape lines (src/corona_common.c:44-62, src/prims.c:801-806)
+    # upstream's own words for the two ragged shape lines (src/corona_common.c:57, src/prims.c:786)
     p = run_cli(str(tmp_path / "missing_geo.nra2"), "--dump-materials", str(tmp_path / "x.bin"))
     assert "could not load geo" in p.stderr and "decreasing shape count" in p.stderr
     p = run_cli(str(tmp_path / "shape_material_out_of_range.nra2"), "--dump-materials", str(tmp_path / "x.bin"))
