@@ -96,6 +96,13 @@ cb200_scene_t *cb200_scene_create(const cb_shape_t *shapes, int num_shapes)
       const uint32_t vcnt = cb_primid_vcnt(p);
       if(vcnt < 1 || vcnt > 4) { g_error = "scene_create: unsupported primitive type (shells are out of scope)"; delete s; return nullptr; }
       if(cb_primid_vi(p) + vcnt > shapes[i].num_vtxidx) { g_error = "scene_create: vertex index out of range"; delete s; return nullptr; }
+      { // ... and the vertices those indices name: vtx[(mb+1)*v (+mb)] (include/geo.h:108-138); an index outside the array would
+        // make the build and shading kernels read outside their buffers
+        const uint64_t mb = cb_primid_mb(p), nv = shapes[i].num_vtx;
+        const cb_vtxidx_t *ix = shapes[i].vtxidx + cb_primid_vi(p);
+        for(uint32_t c=0;c<vcnt;c++)
+          if((mb + 1)*(uint64_t)ix[c].v + mb >= nv) { g_error = "scene_create: vertex index out of range"; delete s; return nullptr; }
+      }
       if(cb_primid_mb(p)) s->any_mb = 1;
       if(cb_primid_vcnt(p) < CB_PRIM_TRI) s->any_analytic = 1;
       primid[k++] = p;

@@ -175,6 +175,31 @@ void prims_allocate(prims_t *p, const uint32_t num_shapes)
   p->shape = (prims_shape_t *)calloc(num_shapes ? num_shapes : 1, sizeof(prims_shape_t));
 }
 
+/* .geo layout: header, num_prims primids, vertex indices at vtxidx_offset, vertices at vertex_offset up to
+ * the end of the file.  Every section must lie inside the file and every primitive's indices inside their sections:
+ * primitive -> vtxidx[vi .. vi+vcnt) -> vtx[(mb+1)*v (+mb)] (include/geo.h:108-138). */
+static int geo_validate(const cb_geo_header_t *h, uint64_t size)
+{
+  const uint64_t np = h->num_prims;
+  if(np > (size - sizeof(*h))/sizeof(uint64_t)) return 1;
+  if(h->vtxidx_offset < sizeof(*h) + np*sizeof(uint64_t) || h->vtxidx_offset > size) return 1;
+  if(h->vertex_offset < h->vtxidx_offset || h->vertex_offset > size) return 1;
+  if((h->vtxidx_offset % 8) || (h->vertex_offset % 16)) return 1;
+  const uint64_t num_idx = (h->vertex_offset - h->vtxidx_offset)/sizeof(cb_vtxidx_t);
+  const uint64_t num_vtx = (size - h->vertex_offset)/sizeof(cb_vtx_t);
+  const uint64_t *primid = (const uint64_t *)(h + 1);
+  const cb_vtxidx_t *idx = (const cb_vtxidx_t *)((const uint8_t *)h + h->vtxidx_offset);
+  for(uint64_t k=0;k<np;k++)
+  {
+    const uint32_t vcnt = cb_primid_vcnt(primid[k]), vi = cb_primid_vi(primid[k]), mb = cb_primid_mb(primid[k]);
+    if(vcnt < 1 || vcnt > 4) return 1;   /* sphere, line, triangle, quad (prims.h:9-18); shells are not part of the hot path */
+    if((uint64_t)vi + vcnt > num_idx) return 1;
+    for(uint32_t c=0;c<vcnt;c++)
+      if((uint64_t)(mb + 1)*idx[vi + c].v + mb >= num_vtx) return 1;
+  }
+  return 0;
+}
+
 /* maps <filename>.geo read-only; on failure drops the shape like the reference (prims.c:783-788) */
 int prims_load(prims_t *p, const char *filename, const char *texture, const int shader)
 {
@@ -203,6 +228,15 @@ int prims_load(prims_t *p, const char *filename, const char *texture, const int 
   if(s->data_size < sizeof(*h) || h->magic != CB_GEO_MAGIC || h->version != CB_GEO_VERSION)
   {
     fprintf(stderr, "[prims_load] geo `%s' magic/version mismatch!\n", filename);
+    munmap(s->data, s->data_size); s->data = 0;
+    p->num_shapes--;
+    return 1;
+  }
+  if(geo_validate(h, s->data_size))
+  { /* the reference maps the file and trusts it (prims.c:790-806); a truncated or inconsistent file would make the device
+     * kernels read outside their buffers here, so it is dropped like an unreadable one */
+    fprintf(stderr, "[prims_load] geo `%s' is truncated or inconsistent (sections or indices outside the file)! decreasing shape count to %d.\n",
+            filename, p->num_shapes - 1);
     munmap(s->data, s->data_size); s->data = 0;
     p->num_shapes--;
     return 1;

@@ -374,3 +374,13 @@ print("ok")
     env = dict(os.environ, CB200_FORCE_REF64="1")
     p = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, cwd=ROOT)
     assert p.returncode == 0 and "ok" in p.stdout, p.stderr[-2000:]
+
+
+def test_scene_create_refuses_wild_vertex_indices(gpu):
+    """a vertex index outside the shape's vertex array must be refused at upload (the kernels would read outside their buffers)"""
+    sc = S.synthetic_scene(500, seed=3)
+    sc.shapes[0].vtxidx = sc.shapes[0].vtxidx.copy()
+    sc.shapes[0].vtxidx["v"][7] = 0x7fffffff
+    with pytest.raises(Exception, match="out of range"):
+        gpu.Accel(sc).build()
+

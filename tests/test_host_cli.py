@@ -234,3 +234,32 @@ def test_c_parser_survives_malformed_scene_files(built, tmp_path):
     assert "could not load geo" in p.stderr and "decreasing shape count" in p.stderr
     p = run_cli(str(tmp_path / "shape_material_out_of_range.nra2"), "--dump-materials", str(tmp_path / "x.bin"))
     assert "out of bounds" in p.stderr
+
+
+@needs_coeff
+def test_c_geo_reader_drops_truncated_and_inconsistent_files(built, tmp_path):
+    """a .geo whose sections or indices point outside the file (truncated copy, corrupted header, wild vertex index) is dropped
+    with a message, like an unreadable one (src/prims.c:783-788) -- the reference maps the file and trusts it; here the device
+    kernels would read outside their buffers"""
+    import struct
+    g = GoldenImage("diffuse_static")
+    nra2 = g.write_files(str(tmp_path))
+    geo = str(tmp_path / "shape0.geo")
+    orig = open(geo, "rb").read()
+    vtxidx_offset = struct.unpack("<Q", orig[16:24])[0]
+
+    def patched(off, fmt, value):
+        h = bytearray(orig)
+        h[off:off + struct.calcsize(fmt)] = struct.pack(fmt, value)
+        return bytes(h)
+
+    bad = {"half": orig[:len(orig) // 2], "header_only": orig[:32], "num_prims": patched(8, "<Q", 0x7fffffffffff),
+           "vtxidx_offset": patched(16, "<Q", 0x7fffffffffff), "vertex_offset": patched(24, "<Q", 0x7fffffffffff),
+           "prim_vi": patched(32 + 4, "<I", 0x6fffffff), "vertex_index": patched(vtxidx_offset, "<I", 0x7fffffff)}
+    for name, data in bad.items():
+        open(geo, "wb").write(data)
+        p = run_cli(nra2, "--dump-materials", str(tmp_path / "m.bin"))
+        assert p.returncode == 0 and "truncated or inconsistent" in p.stderr, f"{name}: rc {p.returncode}: {p.stderr[-200:]}"
+    open(geo, "wb").write(orig)
+    p = run_cli(nra2, "--dump-materials", str(tmp_path / "m.bin"))
+    assert p.returncode == 0 and "inconsistent" not in p.stderr
