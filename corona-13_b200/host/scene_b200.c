@@ -91,15 +91,19 @@ static int tables_load(table_file_t *t, const char *filename)
   FILE *f = fopen(filename, "rb");
   if(!f) return 1;
   char magic[4];
-  if(fread(magic, 4, 1, f) != 1 || memcmp(magic, "CBT1", 4) || fread(&t->count, 4, 1, f) != 1 || t->count > 1024) { fclose(f); return 1; }
+  uint32_t count = 0;
+  if(fread(magic, 4, 1, f) != 1 || memcmp(magic, "CBT1", 4) || fread(&count, 4, 1, f) != 1 || count > 1024) { fclose(f); return 1; }
+  t->count = count;   /* (only once it is known to be sane: tables_free walks `count` entries) */
   t->name = calloc(t->count ? t->count : 1, 32);
   t->tab = calloc(t->count ? t->count : 1, sizeof(cb_table_t));
   t->data = calloc(t->count ? t->count : 1, sizeof(float *));
+  if(!t->name || !t->tab || !t->data) { fclose(f); return 1; }
   for(uint32_t k=0;k<t->count;k++)
   {
     uint32_t rc[2]; float lm[2];
     if(fread(t->name[k], 32, 1, f) != 1 || fread(rc, 8, 1, f) != 1 || fread(lm, 8, 1, f) != 1) { fclose(f); return 1; }
     t->name[k][31] = 0;
+    if(rc[0] == 0 || rc[1] == 0 || (uint64_t)rc[0]*rc[1] > (1u << 24)) { fclose(f); return 1; }   /* 140 x 36 and 3 x n in practice */
     t->data[k] = malloc(sizeof(float)*(size_t)rc[0]*rc[1]);
     if(!t->data[k] || fread(t->data[k], sizeof(float)*(size_t)rc[0]*rc[1], 1, f) != 1) { fclose(f); return 1; }
     t->tab[k].rows = rc[0]; t->tab[k].num_lambda = rc[1]; t->tab[k].lambda_min = lm[0]; t->tab[k].lambda_step = lm[1];
@@ -110,7 +114,7 @@ static int tables_load(table_file_t *t, const char *filename)
 }
 static void tables_free(table_file_t *t)
 {
-  for(uint32_t k=0;k<t->count;k++) free(t->data[k]);
+  for(uint32_t k=0;t->data && k<t->count;k++) free(t->data[k]);
   free(t->data); free(t->tab); free(t->name);
   memset(t, 0, sizeof(*t));
 }

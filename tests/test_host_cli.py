@@ -263,3 +263,36 @@ def test_c_geo_reader_drops_truncated_and_inconsistent_files(built, tmp_path):
     open(geo, "wb").write(orig)
     p = run_cli(nra2, "--dump-materials", str(tmp_path / "m.bin"))
     assert p.returncode == 0 and "inconsistent" not in p.stderr
+
+
+@needs_coeff
+def test_c_readers_refuse_garbage_side_files(built, tmp_path):
+    """the files beside the scene -- measured tables, rgb2spec coefficients, the environment map -- truncated, empty, with absurd
+    sizes or missing: the loader refuses (exit code 2), it does not crash"""
+    import struct
+    g = GoldenImage("envmap")
+    nra2 = g.write_files(str(tmp_path))
+    dump = str(tmp_path / "m.bin")
+    fb = str(tmp_path / g.sky.split()[1])
+    orig = open(fb, "rb").read()
+    huge = bytearray(orig)
+    huge[8:16] = struct.pack("<Q", 1 << 40)
+    for name, data in {"truncated": orig[:100], "half": orig[:len(orig) // 2], "empty": b"", "huge_width": bytes(huge)}.items():
+        open(fb, "wb").write(data)
+        p = run_cli(nra2, "--dump-materials", dump)
+        assert p.returncode == 2, f"environment map {name}: rc {p.returncode}"
+    os.remove(fb)
+    assert run_cli(nra2, "--dump-materials", dump).returncode == 2
+    open(fb, "wb").write(orig)
+    assert run_cli(nra2, "--dump-materials", dump).returncode == 0
+    for name, data in {"absurd_count": b"CBT1\xff\xff\xff\x7f", "short": b"CBT1\x02\x00\x00\x00", "wrong_magic": b"XXXX", "empty": b"",
+                       "absurd_table": b"CBT1\x01\x00\x00\x00" + b"n" * 32 + struct.pack("<IIff", 1 << 30, 1 << 30, 380.0, 10.0)}.items():
+        t = str(tmp_path / "t.cbt")
+        open(t, "wb").write(data)
+        p = subprocess.run([BIN, nra2, "--coeff", COEFF, "--tables", t, "--dump-materials", dump], capture_output=True, text=True)
+        assert p.returncode == 2 and "table file" in p.stderr, f"tables {name}: rc {p.returncode}"
+    c = str(tmp_path / "c.coeff")
+    open(c, "wb").write(b"abc")
+    for coeff in (c, str(tmp_path / "nonexistent.coeff")):
+        p = subprocess.run([BIN, nra2, "--coeff", coeff, "--tables", TABLES, "--dump-materials", dump], capture_output=True, text=True)
+        assert p.returncode == 2, f"coeff {coeff}: rc {p.returncode}"
