@@ -50,8 +50,17 @@ static void shape_extent(const prims_shape_t *sh, uint64_t *num_vtxidx, uint64_t
   *num_vtx = nv*(mb + 1);
 }
 
+/* accel_init returns NULL without a CUDA device; the reference's callers do not check (src/main.c:344-347), so every other
+ * entry point says what happened and stops instead of dereferencing it */
+static void no_accel(const char *fn)
+{
+  fprintf(stderr, "[accel b200] %s: no accel (accel_init failed or was never called). there is no cpu fallback in this module.\n", fn);
+  abort();
+}
+
 accel_t *accel_init(prims_t *p)
 {
+  if(!p) { fprintf(stderr, "[accel b200] accel_init: no primitives\n"); return 0; }
   if(cb200_device_count() < 1)
   {
     fprintf(stderr, "[accel b200] no CUDA device: %s. there is no cpu fallback in this module.\n", cb200_last_error());
@@ -75,6 +84,7 @@ void accel_cleanup(accel_t *b)
 void accel_build(accel_t *b, const char *filename)
 {
   (void)filename; /* unused by qbvhmp as well */
+  if(!b) no_accel("accel_build");
   prims_t *p = b->prims;
   cb_shape_t *sh = (cb_shape_t *)calloc(p->num_shapes ? p->num_shapes : 1, sizeof(cb_shape_t));
   for(uint32_t k=0;k<p->num_shapes;k++)
@@ -97,12 +107,13 @@ void accel_build(accel_t *b, const char *filename)
   cb200_accel_aabb(b->accel, b->aabb);
 }
 
-const float *accel_aabb(const accel_t *b) { return b->aabb; }
+const float *accel_aabb(const accel_t *b) { if(!b) no_accel("accel_aabb"); return b->aabb; }
 void *accel_b200_handle(const accel_t *b) { return b ? b->accel : 0; }
 
 void accel_intersect_n(const accel_t *b, const ray_t *rays, hit_t *hits, uint64_t n)
 {
   if(!n) return;
+  if(!b) no_accel("accel_intersect");
   float *md = (float *)malloc(sizeof(float)*n);
   cb_hitrec_t *out = (cb_hitrec_t *)malloc(sizeof(cb_hitrec_t)*n);
   for(uint64_t i=0;i<n;i++) md[i] = hits[i].dist;
@@ -127,6 +138,7 @@ void accel_intersect(const accel_t *b, const ray_t *ray, hit_t *hit)
 void accel_visible_n(const accel_t *b, const ray_t *rays, const float *max_dist, int *visible, uint64_t n)
 {
   if(!n) return;
+  if(!b) no_accel("accel_visible");
   if(cb200_accel_visible_n(b->accel, (const cb_ray_t *)rays, max_dist, (int32_t *)visible, n))
     fprintf(stderr, "[accel b200] visible failed: %s\n", cb200_last_error());
 }
@@ -140,6 +152,7 @@ int accel_visible(const accel_t *b, const ray_t *ray, const float max_dist)
 
 void accel_closest(const accel_t *b, ray_t *ray, hit_t *hit, const float centre)
 { /* half-vector MLT samplers only (include/pathspace/halfvec.h:718,912); a batch of one, in/out like qbvhmp.c:1493-1600 */
+  if(!b) no_accel("accel_closest");
   cb_hitrec_t io;
   memcpy(io.prim, &hit->prim, 8);
   io.u = hit->u; io.v = hit->v; io.dist = hit->dist; io.pad = 0;

@@ -100,3 +100,24 @@ int main(void) {
                                             R.HIT.fields["dist"][1], R.HIT.fields["x"][1], R.RAY.fields["ignore"][1],
                                             1600, 1576]
     assert int(l2) == int(R.primid_make(5, 1234567, np.uint64(7654321), 1, 4))
+
+
+def test_host_layer_stops_loudly_without_an_accel(built):
+    """accel_init returns NULL without a CUDA device and the reference's callers do not check it (src/main.c:344-347): the
+    other accel.h entry points must say so and stop, not dereference it; cleanup of nothing is a no-op"""
+    import subprocess
+    import sys
+    code = '''
+import ctypes as C
+H = C.CDLL(%r)
+f = getattr(H, %r); f.argtypes = [C.c_void_p] * %d; f.restype = C.c_void_p
+f(*([None] * %d))
+print("returned")
+'''
+    so = os.path.join(ROOT, "corona-13_b200", "libcorona_host.so")
+    for name, nargs in (("accel_build", 2), ("accel_aabb", 1)):
+        p = subprocess.run([sys.executable, "-c", code % (so, name, nargs, nargs)], capture_output=True, text=True)
+        assert p.returncode == -6 and "no cpu fallback" in p.stderr and "returned" not in p.stdout, (name, p.returncode, p.stderr[-200:])
+    for name in ("accel_cleanup", "render_cleanup"):
+        p = subprocess.run([sys.executable, "-c", code % (so, name, 1, 1)], capture_output=True, text=True)
+        assert p.returncode == 0 and "returned" in p.stdout, (name, p.returncode, p.stderr[-200:])
