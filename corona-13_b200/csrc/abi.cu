@@ -9,7 +9,7 @@
 
 static thread_local std::string g_error;
 static std::atomic<uint64_t> g_launches{0};
-static int g_sm_count = 0;
+static std::atomic<int> g_sm_count[64];   // per device (the current device can change between calls: multi-GPU hosts)
 
 void cb200_set_error(const std::string &msg) { g_error = msg; }
 int cb200_cuda_fail(cudaError_t e, const char *what, const char *file, int line)
@@ -24,14 +24,17 @@ int cb200_cuda_fail(cudaError_t e, const char *what, const char *file, int line)
 void cb200_count_launch(uint64_t n) { g_launches += n; }
 int cb200_sm_count_cached()
 {
-  if(!g_sm_count)
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if(dev < 0 || dev >= 64) dev = 0;
+  int n = g_sm_count[dev].load();
+  if(!n)
   {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&g_sm_count, cudaDevAttrMultiProcessorCount, dev);
-    if(g_sm_count <= 0) g_sm_count = 148;
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if(n <= 0) n = 148;
+    g_sm_count[dev] = n;
   }
-  return g_sm_count;
+  return n;
 }
 
 extern "C" {
@@ -52,7 +55,6 @@ int cb200_set_device(int device)
 {
   if(device < 0 || device >= cb200_device_count()) { if(g_error.empty()) g_error = "no such CUDA device"; return CB200_ERR_NO_DEVICE; }
   CB_CUDA(cudaSetDevice(device));
-  g_sm_count = 0;
   return 0;
 }
 int cb200_sm_count(void) { if(cb200_device_count() < 1) return 0; return cb200_sm_count_cached(); }

@@ -97,9 +97,8 @@ int  cb200_sm_count_cached();
 int cb200_build_lbvh(cb200_accel *a, const float *ghost_aabb);
 int cb200_build_records(cb200_accel *a, cudaStream_t stream);
 // traverse.cu
-// d_order (optional): process ray d_order[k] as the k-th ray; results still land in d_out[d_order[k]]
 int cb200_launch_intersect(const cb200_accel *a, const cb_ray_t *d_rays, const float *d_max_dist, cb_hitrec_t *d_out,
-                           uint64_t n, cudaStream_t stream, unsigned long long *d_counters, const uint32_t *d_order = nullptr);
+                           uint64_t n, cudaStream_t stream, unsigned long long *d_counters);
 int cb200_launch_visible(const cb200_accel *a, const cb_ray_t *d_rays, const float *d_max_dist, int32_t *d_out,
                          uint64_t n, cudaStream_t stream);
 int cb200_launch_closest(const cb200_accel *a, cb_ray_t *d_rays, cb_hitrec_t *d_io, const float *d_centre, uint64_t n, cudaStream_t stream);

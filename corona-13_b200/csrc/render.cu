@@ -152,7 +152,6 @@ struct RenderDev
   float *fb;
   uint32_t fb_w, fb_h;
   int32_t sampler, colour, max_path_len;
-  float box_lo[3], box_scale[3];   // scene box -> 7-bit cell per axis (ray coherence keys)
   int32_t sky;                     // CB_SKY_*
   float sky_coeff[3], sky_scale;   // CB_SKY_CONST
   float p_sky;                     // lights_pdf_type: probability of connecting to the sky (list.c:44-49,76-88)
@@ -353,27 +352,6 @@ __device__ __forceinline__ uint32_t part1by1(uint32_t x)
   x = (x | (x << 1)) & 0x55555555u;
   return x;
 }
-// coherence key of a ray: Morton code of the origin's cell in a 128^3 grid over the scene box (21 bits) + direction octant
-// (3 bits).  Waves are TRACED in key order (k_intersect's `order`), storage order is untouched.
-__device__ __forceinline__ uint32_t part1by2(uint32_t x)
-{
-  x &= 0x000003ffu;
-  x = (x ^ (x << 16)) & 0xff0000ffu;
-  x = (x ^ (x << 8))  & 0x0300f00fu;
-  x = (x ^ (x << 4))  & 0x030c30c3u;
-  x = (x ^ (x << 2))  & 0x09249249u;
-  return x;
-}
-__device__ __forceinline__ uint32_t ray_key(const RenderDev &R, V3 pos, V3 dir)
-{
-  const float fx = fminf(fmaxf((pos.x - R.box_lo[0])*R.box_scale[0], 0.0f), 127.0f);
-  const float fy = fminf(fmaxf((pos.y - R.box_lo[1])*R.box_scale[1], 0.0f), 127.0f);
-  const float fz = fminf(fmaxf((pos.z - R.box_lo[2])*R.box_scale[2], 0.0f), 127.0f);
-  const uint32_t m = part1by2((uint32_t)fx) | (part1by2((uint32_t)fy) << 1) | (part1by2((uint32_t)fz) << 2);
-  const uint32_t oct = (__float_as_uint(dir.x) >> 31) | ((__float_as_uint(dir.y) >> 31) << 1) | ((__float_as_uint(dir.z) >> 31) << 2);
-  return (m << 3) | oct;
-}
-
 __global__ void __launch_bounds__(RB)
 k_pixel_keys(RenderDev R, uint64_t first_index, uint32_t n, uint32_t *keys, uint32_t *vals)
 {
@@ -388,7 +366,7 @@ k_pixel_keys(RenderDev R, uint64_t first_index, uint32_t n, uint32_t *keys, uint
 
 __global__ void __launch_bounds__(RB)
 k_path_start(RenderDev R, uint64_t first_index, uint32_t n, const uint32_t *__restrict__ order, PathState *st, cb_ray_t *rays, float *aux,
-             uint32_t *rkeys, float *maxd)
+             float *maxd)
 {
   const uint32_t i = blockIdx.x*blockDim.x + threadIdx.x;
   if(i >= n) return;
@@ -405,7 +383,6 @@ k_path_start(RenderDev R, uint64_t first_index, uint32_t n, const uint32_t *__re
   }
   write_ray(rays, i, pos, mk3(s.omega[0], s.omega[1], s.omega[2]), s.time, 0xffffffffu, 0xffffffffu);
   if(st) st[i] = s;
-  if(rkeys) rkeys[i] = ray_key(R, pos, mk3(s.omega[0], s.omega[1], s.omega[2]));
   if(aux) { aux[4*i+0] = s.pixel_i; aux[4*i+1] = s.pixel_j; aux[4*i+2] = s.lambda; aux[4*i+3] = s.thr; }
 }
 
@@ -721,7 +698,7 @@ __global__ void __launch_bounds__(RB)
 k_shade(RenderDev R, uint32_t n, const PathState *__restrict__ st_in, const cb_ray_t *__restrict__ rays_in,
         const cb_hitrec_t *__restrict__ hits, PathState *__restrict__ st_out, cb_ray_t *__restrict__ rays_out,
         cb_ray_t *__restrict__ nee_rays, float *__restrict__ nee_maxdist, uint2 *__restrict__ nee_light, NeeRec *__restrict__ nee_recs,
-        ShadeCounters *cnt, uint32_t *__restrict__ rkeys_out, const uint32_t *__restrict__ hit_list, int kind, float *__restrict__ maxd_out)
+        ShadeCounters *cnt, const uint32_t *__restrict__ hit_list, int kind, float *__restrict__ maxd_out)
 {
   constexpr bool VOLV = KINDS == 16;   // this launch shades volume vertices
   const uint32_t t = blockIdx.x*blockDim.x + threadIdx.x;
@@ -1044,7 +1021,6 @@ k_shade(RenderDev R, uint32_t n, const PathState *__restrict__ st_in, const cb_r
       const uint64_t o = base + __popc(ma & ((1u << lane) - 1u));
       st_out[o] = s;
       write_ray(rays_out, o, next_pos, next_dir, s.time, s.prim_lo, s.prim_hi);
-      if(rkeys_out) rkeys_out[o] = ray_key(R, next_pos, next_dir);
       if(MEDIA) maxd_out[o] = next_clip;
     }
   }
@@ -1217,11 +1193,7 @@ struct cb200_render
   float *own_dbor;               // cb200_render_set_dbor
   // asynchronous snapshots: device-side copy of the accumulation buffer, drained to the host on a stream of its own
   float *snap_stage; cudaStream_t snap_stream; cudaEvent_t snap_ready, snap_done; int snap_pending;
-  // coherence sort of every traced wave: keys ride with the rays (ping-pong), iota -> order by radix sort
-  int ray_sort;
   int bsdf_kinds;   // bit mask of the BSDF kinds referenced by shapes (selects the k_shade variant)
-  uint32_t *rkeys[2], *rkeys_sorted, *iota, *ray_order;
-  void *rsort_tmp; size_t rsort_tmp_bytes;
   // instrumentation (cb200_render_instrument): CUDA events around every launch on the pass' own stream, summed per
   // kernel class after the pass; ACCEL_DEBUG-style traversal counters
   int timing, counting;
@@ -1571,29 +1543,6 @@ cb200_render_t *cb200_render_create(cb200_accel_t *a, const cb_render_desc_t *de
     r->sort_tmp = dev_alloc<uint8_t>(r, r->sort_tmp_bytes);
     ok = ok && r->sort_tmp;
   }
-  {
-    const char *e = getenv("CB200_RAY_SORT");
-    r->ray_sort = e ? atoi(e) : 0;   // measured on the 10 M-triangle bench: the sort costs what the coherence gains (+-1 %), so off by default
-    for(int k=0;k<2;k++) { r->rkeys[k] = dev_alloc<uint32_t>(r, N); ok = ok && r->rkeys[k]; }
-    r->rkeys_sorted = dev_alloc<uint32_t>(r, N); r->iota = dev_alloc<uint32_t>(r, N); r->ray_order = dev_alloc<uint32_t>(r, N);
-    ok = ok && r->rkeys_sorted && r->iota && r->ray_order;
-    r->rsort_tmp = nullptr; r->rsort_tmp_bytes = 0;
-    if(ok)
-    {
-      std::vector<uint32_t> h(N);
-      for(uint64_t k=0;k<N;k++) h[k] = (uint32_t)k;
-      ok = cudaMemcpy(r->iota, h.data(), N*sizeof(uint32_t), cudaMemcpyHostToDevice) == cudaSuccess;
-      cub::DeviceRadixSort::SortPairs(nullptr, r->rsort_tmp_bytes, r->rkeys[0], r->rkeys_sorted, r->iota, r->ray_order, (int)N, 0, 24);
-      r->rsort_tmp = dev_alloc<uint8_t>(r, r->rsort_tmp_bytes);
-      ok = ok && r->rsort_tmp;
-    }
-    for(int k=0;k<3;k++)
-    {
-      const float lo = a->aabb[k], hi = a->aabb[3+k];
-      D.box_lo[k] = lo;
-      D.box_scale[k] = (hi > lo) ? 128.0f/(hi - lo) : 0.0f;
-    }
-  }
   r->d_trav_cnt = dev_alloc<unsigned long long>(r, 8);
   if(r->d_trav_cnt) cudaMemset(r->d_trav_cnt, 0, 8*sizeof(unsigned long long));
   ok = ok && r->d_trav_cnt && D.fb && r->hits && r->nee_rays && r->nee_md && r->nee_recs && r->nee_light && r->nee_vis && r->d_cnt;
@@ -1744,15 +1693,7 @@ static int render_wave(cb200_render *r, uint32_t n, cudaStream_t st)
   int rc;
   {
     TimeScope ts(r, st, KC_CLOSEST, n);
-    const uint32_t *order = nullptr;
-    if(r->ray_sort)
-    {
-      size_t tmp = r->rsort_tmp_bytes;
-      CB_CUDA(cub::DeviceRadixSort::SortPairs(r->rsort_tmp, tmp, r->rkeys[cur], r->rkeys_sorted, r->iota, r->ray_order, (int)n, 0, 24, st));
-      cb200_count_launch(3); r->stats.kernel_launches += 3;
-      order = r->ray_order;
-    }
-    rc = cb200_launch_intersect(r->accel, r->rays[cur], r->maxd[cur], r->hits, n, st, r->counting ? r->d_trav_cnt : nullptr, order);
+    rc = cb200_launch_intersect(r->accel, r->rays[cur], r->maxd[cur], r->hits, n, st, r->counting ? r->d_trav_cnt : nullptr);
   }
   if(rc) return rc;
   r->stats.rays_closest += n; r->stats.kernel_launches++;
@@ -1767,9 +1708,8 @@ static int render_wave(cb200_render *r, uint32_t n, cudaStream_t st)
     const int single = r->dev.has_media ? -1 : (r->bsdf_kinds == 1) ? 0 : (r->bsdf_kinds == 2) ? 1 : (r->bsdf_kinds == 4) ? 2 : (r->bsdf_kinds == 8) ? 3 : -1;
     k_compact_hits<<<(n + 255)/256, 256, 0, st>>>(r->dev, r->hits, n, (uint32_t)r->batch, r->hit_list, r->d_cnt, single);
     cb200_count_launch(); r->stats.kernel_launches++;
-    uint32_t *rk = r->ray_sort ? r->rkeys[cur^1] : nullptr;
 #define SHADE_ARGS(K) (r->dev, n, r->st[cur], r->rays[cur], r->hits, r->st[cur^1], r->rays[cur^1], \
-      r->nee_rays, r->nee_md, r->nee_light, r->nee_recs, r->d_cnt, rk, r->hit_list + (size_t)K*r->batch, K, r->maxd[cur^1])
+      r->nee_rays, r->nee_md, r->nee_light, r->nee_recs, r->d_cnt, r->hit_list + (size_t)K*r->batch, K, r->maxd[cur^1])
 #define SHADE_LAUNCH(K) do { if(r->dev.has_media) k_shade<(1 << K), true><<<(n + RB - 1)/RB, RB, 0, st>>>SHADE_ARGS(K); \
                              else k_shade<(1 << K), false><<<(n + RB - 1)/RB, RB, 0, st>>>SHADE_ARGS(K); \
                              cb200_count_launch(); r->stats.kernel_launches++; } while(0)
@@ -1849,7 +1789,6 @@ int cb200_render_pass_stream(cb200_render_t *r, uint64_t first_index, uint64_t c
       CB_CUDA(cub::DeviceRadixSort::SortPairs(r->sort_tmp, tmp, r->keys[0], r->keys[1], r->order[0], r->order[1], (int)n_new, 0, 24, st));
       k_path_start<<<(n_new + RB - 1)/RB, RB, 0, st>>>(r->dev, first_index + started, n_new, r->order[1],
                                                         r->st[r->cur] + r->n_alive, r->rays[r->cur] + r->n_alive, nullptr,
-                                                        r->ray_sort ? r->rkeys[r->cur] + r->n_alive : nullptr,
                                                         r->maxd[r->cur] ? r->maxd[r->cur] + r->n_alive : nullptr);
       cb200_count_launch(5); r->stats.kernel_launches += 5;   // keys, radix sort (histogram + digit passes, counted as 3), path start
       r->stats.paths += n_new;
@@ -1926,7 +1865,7 @@ int cb200_render_camera_rays(cb200_render_t *r, uint64_t first_index, uint64_t n
   if(!r || !out_rays || n > r->batch) { cb200_set_error("render_camera_rays: bad arguments (n must be <= batch_paths)"); return CB200_ERR_ARG; }
   float *d_aux = nullptr;
   CB_CUDA(cudaMalloc(&d_aux, n*16 + 16));
-  if(n) k_path_start<<<(unsigned)((n + RB - 1)/RB), RB>>>(r->dev, first_index, (uint32_t)n, nullptr, nullptr, r->rays[0], d_aux, nullptr, nullptr);
+  if(n) k_path_start<<<(unsigned)((n + RB - 1)/RB), RB>>>(r->dev, first_index, (uint32_t)n, nullptr, nullptr, r->rays[0], d_aux, nullptr);
   cb200_count_launch();
   CB_CUDA(cudaMemcpy(out_rays, r->rays[0], n*sizeof(cb_ray_t), cudaMemcpyDeviceToHost));
   if(out_aux) CB_CUDA(cudaMemcpy(out_aux, d_aux, n*16, cudaMemcpyDeviceToHost));

@@ -12,7 +12,10 @@
 // Mapping (each item follows an ncu finding, profiles/README.md; plain one-ray-per-thread while-while ran at 4.8 of 32 lanes):
 //   * persistent warps; every lane owns one ray at a time and idle lanes are REFILLED from a global ticket counter in
 //     batches (>= refill threshold idle lanes, or nothing else left to do), so short rays do not leave lanes idle and the
-//     fetch path (an atomic round trip + cold ray loads) does not run for one or two lanes on every iteration;
+//     fetch path (an atomic round trip + cold ray loads) does not run for one or two lanes on every iteration.  (A per-warp
+//     ray queue in shared memory -- 32 rays per ticket, lanes pop individually -- was measured in round 2: it keeps 30 of 32
+//     lanes busy, and is 10 % SLOWER: the kernel is bound by L1 wavefronts per ray, which lane packing does not change, and
+//     the 45 KB of shared memory per SM come out of the L1 that serves the node gathers;  profiles/README.md);
 //   * each lane is in one of two states, NODE (next: a 4-box node test) or PRIM (next: all primitives of its current
 //     leaf); per warp iteration a vote picks which of the two code paths runs, so both execute with many lanes active.
 //     Every ray still sees exactly the reference's own sequence of node and primitive tests;
@@ -116,7 +119,7 @@ __device__ __forceinline__ void node_slabs(const void *nodes, uint64_t idx, floa
   for(int c=0;c<4;c++) { o.tmin[c] = tmin[c]; o.hit[c] = tmin[c] <= tmax[c]; }
 }
 
-__device__ __forceinline__ void load_ray(const cb_ray_t *rays, uint64_t i, RayD &r)
+__device__ __forceinline__ void load_ray(const cb_ray_t *rays, uint32_t i, RayD &r)
 {
   const float2 *p = reinterpret_cast<const float2 *>(rays + i);   // 40-byte records are 8-byte aligned
   const float2 a = __ldg(p), b = __ldg(p+1), c = __ldg(p+2), d = __ldg(p+3), e = __ldg(p+4);
@@ -193,6 +196,7 @@ __device__ __forceinline__ void node_slabs_fast_mb(const Node256 *__restrict__ n
 #define CSWAP(cond, ka, ca, kb, cb) do { const float tk__ = ka; const ref_t tc__ = ca; \
   ka = (cond) ? kb : ka; ca = (cond) ? cb : ca; kb = (cond) ? tk__ : kb; cb = (cond) ? tc__ : cb; } while(0)
 
+
 // ---------------------------------------------------------------------------------------------
 // closest hit
 //   ANALYTIC: the scene has spheres / cylinders / cones (their tests carry double precision and libm calls; scenes
@@ -205,8 +209,8 @@ __device__ __forceinline__ void node_slabs_fast_mb(const Node256 *__restrict__ n
 template<bool MB, bool CNT, int STACK, bool ANALYTIC, bool C32>
 __global__ void __launch_bounds__(TRACE_BLOCK, (!MB && !CNT && !ANALYTIC) ? TRACE_MIN_BLOCKS : 1)
 k_intersect(DevAccel A, const cb_ray_t *__restrict__ rays, const float *__restrict__ max_dist,
-            cb_hitrec_t *__restrict__ out, uint64_t n, unsigned long long *ticket, unsigned long long *counters,
-            int prim_threshold, int refill_threshold, const uint32_t *__restrict__ order)
+            cb_hitrec_t *__restrict__ out, uint32_t n, unsigned int *ticket, unsigned long long *counters,
+            int prim_threshold, int refill_threshold)
 {
   const uint32_t lane = threadIdx.x & 31u;
   const uint32_t lt_mask = (1u << lane) - 1u;
@@ -219,7 +223,7 @@ k_intersect(DevAccel A, const cb_ray_t *__restrict__ rays, const float *__restri
   bool exhausted = false;
   RayD r;
   HitD h;
-  uint64_t ray_i = 0;
+  uint32_t ray_i = 0;
   ref_t cur = 0;
   float ix = 0.0f, iy = 0.0f, iz = 0.0f, t0 = 1.0f, t1 = 0.0f;
   uint32_t nearbits = 0;
@@ -239,16 +243,15 @@ k_intersect(DevAccel A, const cb_ray_t *__restrict__ rays, const float *__restri
     if(idle && !exhausted && (__popc(idle) >= refill_threshold || idle == FULL))
     {
       const uint32_t want = __popc(idle);
-      unsigned long long base = 0;
-      if(lane == 0) base = atomicAdd(ticket, (unsigned long long)want);
+      unsigned int base = 0;
+      if(lane == 0) base = atomicAdd(ticket, want);
       base = __shfl_sync(FULL, base, 0);
       if(base + want >= n) exhausted = true;
       if(state == ST_IDLE)
       {
-        const uint64_t q = base + __popc(idle & lt_mask);
-        if(q < n)
+        const uint32_t i = base + __popc(idle & lt_mask);
+        if(i < n)
         {
-          const uint64_t i = order ? (uint64_t)__ldg(order + q) : q;   // processing order != storage order (coherence sort)
           load_ray(rays, i, r);
           ray_i = i;
           h.dist = max_dist ? __ldg(max_dist + i) : FLT_MAX;
@@ -419,7 +422,7 @@ k_intersect(DevAccel A, const cb_ray_t *__restrict__ rays, const float *__restri
 template<bool MB, int STACK, bool ANALYTIC, bool SHADOW, bool C32>
 __global__ void __launch_bounds__(TRACE_BLOCK, (!MB && !ANALYTIC) ? TRACE_MIN_BLOCKS : 1)
 k_visible(DevAccel A, const cb_ray_t *__restrict__ rays, const float *__restrict__ max_dist, const uint2 *__restrict__ skip,
-          int32_t *__restrict__ out, uint64_t n, unsigned long long *ticket, int prim_threshold, int refill_threshold)
+          int32_t *__restrict__ out, uint32_t n, unsigned int *ticket, int prim_threshold, int refill_threshold)
 {
   const uint32_t lane = threadIdx.x & 31u;
   const uint32_t lt_mask = (1u << lane) - 1u;
@@ -429,7 +432,7 @@ k_visible(DevAccel A, const cb_ray_t *__restrict__ rays, const float *__restrict
   int state = ST_IDLE;
   bool exhausted = false;
   RayD r;
-  uint64_t ray_i = 0;
+  uint32_t ray_i = 0;
   ref_t cur = 0;
   float ix = 0.0f, iy = 0.0f, iz = 0.0f, t0 = 1.0f, t1 = 0.0f, md = 0.0f;
   uint32_t near_off[3] = {0, 0, 0};
@@ -446,13 +449,13 @@ k_visible(DevAccel A, const cb_ray_t *__restrict__ rays, const float *__restrict
     if(idle && !exhausted && (__popc(idle) >= refill_threshold || idle == FULL))
     {
       const uint32_t want = __popc(idle);
-      unsigned long long base = 0;
-      if(lane == 0) base = atomicAdd(ticket, (unsigned long long)want);
+      unsigned int base = 0;
+      if(lane == 0) base = atomicAdd(ticket, want);
       base = __shfl_sync(FULL, base, 0);
       if(base + want >= n) exhausted = true;
       if(state == ST_IDLE)
       {
-        const uint64_t i = base + __popc(idle & lt_mask);
+        const uint32_t i = base + __popc(idle & lt_mask);
         if(i < n)
         {
           load_ray(rays, i, r);
@@ -646,10 +649,13 @@ int cb200_launch_closest(const cb200_accel *a, cb_ray_t *d_rays, cb_hitrec_t *d_
 // ---------------------------------------------------------------------------------------------
 // host launchers
 // ---------------------------------------------------------------------------------------------
-static unsigned long long *g_tickets = nullptr;   // ring of ticket counters, zeroed asynchronously
-static std::atomic<unsigned> g_ticket_next{0};
+// ticket counters: one ring per device (a launch takes the next counter of the CURRENT device's ring and zeroes it on its own
+// stream, so launches on different streams never share a live counter while fewer than NUM_TICKETS are in flight per device)
+#define NUM_TICKETS 1024
+#define MAX_DEVICES 64
+static unsigned int *g_tickets[MAX_DEVICES] = {nullptr};
+static std::atomic<unsigned> g_ticket_next[MAX_DEVICES];
 static std::mutex g_ticket_mutex;
-#define NUM_TICKETS 256
 static int g_prim_threshold = 1000;
 
 static int prim_threshold()
@@ -666,14 +672,17 @@ static int prim_threshold()
   return g_prim_threshold;
 }
 
-static int get_ticket(cudaStream_t stream, unsigned long long **t)
+static int get_ticket(cudaStream_t stream, unsigned int **t)
 {
+  int dev = 0;
+  CB_CUDA(cudaGetDevice(&dev));
+  if(dev < 0 || dev >= MAX_DEVICES) { cb200_set_error("device index beyond the ticket table"); return CB200_ERR_UNSUPPORTED; }
   {
     std::lock_guard<std::mutex> lock(g_ticket_mutex);
-    if(!g_tickets) CB_CUDA(cudaMalloc(&g_tickets, sizeof(unsigned long long)*NUM_TICKETS));
+    if(!g_tickets[dev]) CB_CUDA(cudaMalloc(&g_tickets[dev], sizeof(unsigned int)*NUM_TICKETS));
   }
-  unsigned long long *p = g_tickets + (g_ticket_next++ % NUM_TICKETS);
-  CB_CUDA(cudaMemsetAsync(p, 0, sizeof(unsigned long long), stream));
+  unsigned int *p = g_tickets[dev] + (g_ticket_next[dev]++ % NUM_TICKETS);
+  CB_CUDA(cudaMemsetAsync(p, 0, sizeof(unsigned int), stream));
   *t = p;
   return 0;
 }
@@ -691,6 +700,8 @@ static int grid_for(uint64_t n, const void *kernel)
 // the stack must hold 3 entries per tree level (qbvhmp.c:1277); pick the smallest variant that fits
 #define STACK_SMALL 64
 #define STACK_BIG   304
+// rays per launch: tickets are 32 bits and every warp draws one batch beyond the end
+#define LAUNCH_MAX_RAYS (1ull << 30)
 
 // CB200_FORCE_REF64=1 runs the 64-bit child-reference kernels that scenes with >= 2^26 primitives get (tests)
 static bool force_ref64() { static int v = -1; if(v < 0) { const char *e = getenv("CB200_FORCE_REF64"); v = (e && atoi(e)) ? 1 : 0; } return v == 1; }
@@ -711,65 +722,74 @@ static int refill_threshold()
 
 template<bool MB, bool CNT, int STACK, bool ANALYTIC, bool C32>
 static int launch_intersect_k2(const cb200_accel *a, const cb_ray_t *d_rays, const float *d_max_dist, cb_hitrec_t *d_out,
-                              uint64_t n, cudaStream_t stream, unsigned long long *d_counters, const uint32_t *d_order)
+                              uint64_t n, cudaStream_t stream, unsigned long long *d_counters)
 {
-  unsigned long long *ticket;
-  if(get_ticket(stream, &ticket)) return CB200_ERR_CUDA;
   auto k = k_intersect<MB, CNT, STACK, ANALYTIC, C32>;
-  k<<<grid_for(n, (const void *)k), TRACE_BLOCK, 0, stream>>>(a->dev, d_rays, d_max_dist, d_out, n, ticket, d_counters,
-                                                              prim_threshold(), refill_threshold(), d_order);
-  cb200_count_launch();
-  CB_CUDA(cudaGetLastError());
+  for(uint64_t first=0; first<n; first+=LAUNCH_MAX_RAYS)
+  {
+    const uint64_t m = n - first < LAUNCH_MAX_RAYS ? n - first : LAUNCH_MAX_RAYS;
+    unsigned int *ticket;
+    if(int rc = get_ticket(stream, &ticket)) return rc;
+    k<<<grid_for(m, (const void *)k), TRACE_BLOCK, 0, stream>>>(a->dev, d_rays + first, d_max_dist ? d_max_dist + first : nullptr, d_out + first,
+                                                                (uint32_t)m, ticket, d_counters, prim_threshold(), refill_threshold());
+    cb200_count_launch();
+    CB_CUDA(cudaGetLastError());
+  }
   return 0;
 }
 
 template<bool MB, bool CNT, int STACK, bool ANALYTIC>
 static int launch_intersect_k(const cb200_accel *a, const cb_ray_t *d_rays, const float *d_max_dist, cb_hitrec_t *d_out,
-                              uint64_t n, cudaStream_t stream, unsigned long long *d_counters, const uint32_t *d_order)
+                              uint64_t n, cudaStream_t stream, unsigned long long *d_counters)
 {
   // 32-bit child references inside the kernel while begin<<5|count and node indices fit 31 bits
   const bool c32 = !CNT && a->dev.num_prims < (1ull << 26) && a->dev.num_nodes < (1ull << 31) && !force_ref64();
-  if(c32) return launch_intersect_k2<MB, CNT, STACK, ANALYTIC, !CNT>(a, d_rays, d_max_dist, d_out, n, stream, d_counters, d_order);
-  return launch_intersect_k2<MB, CNT, STACK, ANALYTIC, false>(a, d_rays, d_max_dist, d_out, n, stream, d_counters, d_order);
+  if(c32) return launch_intersect_k2<MB, CNT, STACK, ANALYTIC, !CNT>(a, d_rays, d_max_dist, d_out, n, stream, d_counters);
+  return launch_intersect_k2<MB, CNT, STACK, ANALYTIC, false>(a, d_rays, d_max_dist, d_out, n, stream, d_counters);
 }
 
 template<bool MB>
 static int launch_intersect_t(const cb200_accel *a, const cb_ray_t *d_rays, const float *d_max_dist, cb_hitrec_t *d_out,
-                              uint64_t n, cudaStream_t stream, unsigned long long *d_counters, const uint32_t *d_order)
+                              uint64_t n, cudaStream_t stream, unsigned long long *d_counters)
 {
   const int need = 3*a->depth + 1;
   if(need > STACK_BIG) { cb200_set_error("tree deeper than the reference's MAX_TREE_DEPTH"); return CB200_ERR_UNSUPPORTED; }
-  if(d_counters) return launch_intersect_k<MB, true, STACK_BIG, true>(a, d_rays, d_max_dist, d_out, n, stream, d_counters, d_order);
+  if(d_counters) return launch_intersect_k<MB, true, STACK_BIG, true>(a, d_rays, d_max_dist, d_out, n, stream, d_counters);
   const bool analytic = a->scene->any_analytic != 0;
   if(need <= STACK_SMALL)
-    return analytic ? launch_intersect_k<MB, false, STACK_SMALL, true >(a, d_rays, d_max_dist, d_out, n, stream, nullptr, d_order)
-                    : launch_intersect_k<MB, false, STACK_SMALL, false>(a, d_rays, d_max_dist, d_out, n, stream, nullptr, d_order);
-  return analytic ? launch_intersect_k<MB, false, STACK_BIG, true >(a, d_rays, d_max_dist, d_out, n, stream, nullptr, d_order)
-                  : launch_intersect_k<MB, false, STACK_BIG, false>(a, d_rays, d_max_dist, d_out, n, stream, nullptr, d_order);
+    return analytic ? launch_intersect_k<MB, false, STACK_SMALL, true >(a, d_rays, d_max_dist, d_out, n, stream, nullptr)
+                    : launch_intersect_k<MB, false, STACK_SMALL, false>(a, d_rays, d_max_dist, d_out, n, stream, nullptr);
+  return analytic ? launch_intersect_k<MB, false, STACK_BIG, true >(a, d_rays, d_max_dist, d_out, n, stream, nullptr)
+                  : launch_intersect_k<MB, false, STACK_BIG, false>(a, d_rays, d_max_dist, d_out, n, stream, nullptr);
 }
 
 int cb200_launch_intersect(const cb200_accel *a, const cb_ray_t *d_rays, const float *d_max_dist, cb_hitrec_t *d_out,
-                           uint64_t n, cudaStream_t stream, unsigned long long *d_counters, const uint32_t *d_order)
+                           uint64_t n, cudaStream_t stream, unsigned long long *d_counters)
 {
   if(n == 0) return 0;
-  return a->dev.mb ? launch_intersect_t<true >(a, d_rays, d_max_dist, d_out, n, stream, d_counters, d_order)
-                   : launch_intersect_t<false>(a, d_rays, d_max_dist, d_out, n, stream, d_counters, d_order);
+  return a->dev.mb ? launch_intersect_t<true >(a, d_rays, d_max_dist, d_out, n, stream, d_counters)
+                   : launch_intersect_t<false>(a, d_rays, d_max_dist, d_out, n, stream, d_counters);
 }
 
 template<bool MB, int STACK, bool ANALYTIC>
 static int launch_visible_k(const cb200_accel *a, const cb_ray_t *d_rays, const float *d_max_dist, const uint2 *d_skip, int32_t *d_out,
                             uint64_t n, cudaStream_t stream)
 {
-  unsigned long long *ticket;
-  if(get_ticket(stream, &ticket)) return CB200_ERR_CUDA;
   const bool c32 = a->dev.num_prims < (1ull << 26) && a->dev.num_nodes < (1ull << 31) && !force_ref64();
+  for(uint64_t first=0; first<n; first+=LAUNCH_MAX_RAYS)
+  {
+    const uint64_t m = n - first < LAUNCH_MAX_RAYS ? n - first : LAUNCH_MAX_RAYS;
+    unsigned int *ticket;
+    if(int rc = get_ticket(stream, &ticket)) return rc;
 #define VIS_LAUNCH(SH, C) do { auto k = k_visible<MB, STACK, ANALYTIC, SH, C>; \
-    k<<<grid_for(n, (const void *)k), TRACE_BLOCK, 0, stream>>>(a->dev, d_rays, d_max_dist, d_skip, d_out, n, ticket, prim_threshold(), refill_threshold()); } while(0)
-  if(d_skip) { if(c32) VIS_LAUNCH(true, true); else VIS_LAUNCH(true, false); }
-  else       { if(c32) VIS_LAUNCH(false, true); else VIS_LAUNCH(false, false); }
+    k<<<grid_for(m, (const void *)k), TRACE_BLOCK, 0, stream>>>(a->dev, d_rays + first, d_max_dist + first, d_skip ? d_skip + first : nullptr, d_out + first, \
+                                                                (uint32_t)m, ticket, prim_threshold(), refill_threshold()); } while(0)
+    if(d_skip) { if(c32) VIS_LAUNCH(true, true); else VIS_LAUNCH(true, false); }
+    else       { if(c32) VIS_LAUNCH(false, true); else VIS_LAUNCH(false, false); }
 #undef VIS_LAUNCH
-  cb200_count_launch();
-  CB_CUDA(cudaGetLastError());
+    cb200_count_launch();
+    CB_CUDA(cudaGetLastError());
+  }
   return 0;
 }
 
