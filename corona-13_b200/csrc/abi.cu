@@ -215,7 +215,7 @@ cb200_accel_t *cb200_accel_import_qbvh(cb200_scene_t *s, const cb_qbvh_node_t *n
 void cb200_accel_destroy(cb200_accel_t *a)
 {
   if(!a) return;
-  cudaFree(a->d_nodes); cudaFree(a->d_recs); cudaFree(a->d_primid);
+  cudaFree(a->d_nodes); cudaFree(a->d_recs); cudaFree(a->d_primid); cudaFree(a->d_nodes8);
   delete a;
 }
 uint64_t cb200_accel_num_nodes(const cb200_accel_t *a) { return a ? a->dev.num_nodes : 0; }
@@ -229,10 +229,20 @@ int cb200_accel_aabb(const cb200_accel_t *a, float aabb[6])
 int cb200_accel_layout(const cb200_accel_t *a, uint32_t *node_bytes, uint32_t *prim_bytes)
 {
   if(!a) { g_error = "accel_layout: null accel"; return CB200_ERR_ARG; }
-  if(node_bytes) *node_bytes = a->dev.mb ? 256 : 128;
+  if(node_bytes) *node_bytes = cb200_use_wide8(a) ? (uint32_t)sizeof(Node8) : a->dev.mb ? 256 : 128;
   if(prim_bytes) *prim_bytes = a->dev.rec_units*64;
   return 0;
 }
+
+int cb200_accel_set_traversal(cb200_accel_t *a, int mode)
+{
+  if(!a || (mode != CB200_TRAVERSAL_EXACT4 && mode != CB200_TRAVERSAL_WIDE8)) { g_error = "accel_set_traversal: bad arguments"; return CB200_ERR_ARG; }
+  if(mode == CB200_TRAVERSAL_WIDE8 && !a->dev.nodes8)
+  { g_error = "accel_set_traversal: this accel has no 8-wide tree (motion blur, imported reference tree, or built with CB200_BUILD_WIDE8=0)"; return CB200_ERR_UNSUPPORTED; }
+  a->traversal = mode;
+  return 0;
+}
+int cb200_accel_traversal(const cb200_accel_t *a) { return a && cb200_use_wide8(a) ? CB200_TRAVERSAL_WIDE8 : CB200_TRAVERSAL_EXACT4; }
 
 int cb200_accel_export_qbvh(const cb200_accel_t *a, cb_qbvh_node_t *nodes, uint64_t cap, uint64_t *primid_out)
 {

@@ -354,6 +354,134 @@ __global__ void k_collapse(CollapseArgs A, const CollapseItem *__restrict__ in, 
   }
 }
 
+
+// 8-wide compressed tree (Node8, internal.h) over the SAME binary radix tree and primitive order -------------------------
+struct Collapse8Args
+{
+  const BNode *nodes;
+  const uint32_t *index;
+  const float *pbox0, *nbox0;
+  Node8 *out;
+  uint32_t *num_wide;
+  uint32_t max_wide;
+  uint32_t leaf_max;
+};
+
+__device__ __forceinline__ void bref_box0(const Collapse8Args &A, uint32_t r, float *o)
+{
+  if(r & BLEAF) { const uint32_t p = A.index[r & ~BLEAF]; for(int k=0;k<6;k++) o[k] = A.pbox0[(uint64_t)p*6+k]; }
+  else for(int k=0;k<6;k++) o[k] = A.nbox0[(uint64_t)r*6+k];
+}
+
+// one wide node per thread: open the binary subtree below `bref` greedily by surface area until it has 8 children (or nothing
+// left to open), assign the children to slots by octant, quantise their boxes outwards on the node's grid
+__global__ void k_collapse8(Collapse8Args A, const CollapseItem *__restrict__ in, uint32_t num_in,
+                            CollapseItem *__restrict__ out, uint32_t *num_out)
+{
+  const uint32_t t = blockIdx.x*blockDim.x + threadIdx.x;
+  if(t >= num_in) return;
+  const CollapseItem it = in[t];
+  if(it.wide >= A.max_wide) return;
+  uint32_t ch[8];
+  float cb[8][6];
+  int nch = 0;
+  if((it.bref & BLEAF) || bref_count(A.nodes, it.bref) <= A.leaf_max) ch[nch++] = it.bref;   // a scene that fits one leaf
+  else
+  {
+    const BNode b = A.nodes[it.bref];
+    ch[0] = b.left; ch[1] = b.right; nch = 2;
+    bref_box0(A, ch[0], cb[0]); bref_box0(A, ch[1], cb[1]);
+    while(nch < 8)
+    {
+      int best = -1;
+      float best_area = -1.0f;
+      for(int i=0;i<nch;i++)
+      {
+        if((ch[i] & BLEAF) || bref_count(A.nodes, ch[i]) <= A.leaf_max) continue;
+        const float dx = cb[i][3] - cb[i][0], dy = cb[i][4] - cb[i][1], dz = cb[i][5] - cb[i][2];
+        const float area = dx*dy + dy*dz + dz*dx;
+        if(area > best_area) { best_area = area; best = i; }
+      }
+      if(best < 0) break;
+      const BNode c = A.nodes[ch[best]];
+      ch[best] = c.left; ch[nch] = c.right;
+      bref_box0(A, ch[best], cb[best]); bref_box0(A, ch[nch], cb[nch]);
+      nch++;
+    }
+  }
+  if(nch == 1) bref_box0(A, ch[0], cb[0]);
+  float lo[3], hi[3];
+  for(int k=0;k<3;k++) { lo[k] = cb[0][k]; hi[k] = cb[0][3+k]; }
+  for(int i=1;i<nch;i++) for(int k=0;k<3;k++) { lo[k] = fminf(lo[k], cb[i][k]); hi[k] = fmaxf(hi[k], cb[i][3+k]); }
+  // slots by octant: child i wants the slot whose sign pattern matches (child centre - node centre); greedy by that score
+  int slot_of[8], taken = 0, assigned = 0;
+  for(int i=0;i<8;i++) slot_of[i] = -1;
+  for(int round=0;round<nch;round++)
+  {
+    float best = -FLT_MAX; int bi = 0, bs = 0;
+    for(int i=0;i<nch;i++)
+    {
+      if(assigned & (1 << i)) continue;
+      float d[3];
+      for(int k=0;k<3;k++) d[k] = (cb[i][k] + cb[i][3+k]) - (lo[k] + hi[k]);
+      for(int sl=0;sl<8;sl++)
+      {
+        if(taken & (1 << sl)) continue;
+        const float score = ((sl & 1) ? d[0] : -d[0]) + ((sl & 2) ? d[1] : -d[1]) + ((sl & 4) ? d[2] : -d[2]);
+        if(score > best) { best = score; bi = i; bs = sl; }
+      }
+    }
+    slot_of[bi] = bs; assigned |= 1 << bi; taken |= 1 << bs;
+  }
+  // per-axis grid: plane = lo + q * 2^e, 2^e >= extent / 255
+  int e[3];
+  for(int k=0;k<3;k++)
+  {
+    const float ext = hi[k] - lo[k];
+    int ex = -100;
+    if(ext > 0.0f && ext < FLT_MAX) { frexpf(ext/255.0f, &ex); if(ldexp(1.0, ex)*255.0 < (double)hi[k] - (double)lo[k]) ex++; }
+    e[k] = ex < -100 ? -100 : ex > 100 ? 100 : ex;
+  }
+  uint8_t qlo[3][8], qhi[3][8];
+  uint32_t child[8];
+  for(int sl=0;sl<8;sl++) { child[sl] = 0u; for(int k=0;k<3;k++) { qlo[k][sl] = 255; qhi[k][sl] = 0; } }
+  for(int i=0;i<nch;i++)
+  {
+    const int sl = slot_of[i];
+    for(int k=0;k<3;k++)
+    {
+      const double scale = ldexp(1.0, e[k]);
+      double a = floor(((double)cb[i][k] - (double)lo[k])/scale);
+      double b = ceil(((double)cb[i][3+k] - (double)lo[k])/scale);
+      a = a < 0.0 ? 0.0 : a > 255.0 ? 255.0 : a;
+      b = b < 0.0 ? 0.0 : b > 255.0 ? 255.0 : b;
+      while(a > 0.0 && (double)lo[k] + a*scale > (double)cb[i][k]) a -= 1.0;
+      while(b < 255.0 && (double)lo[k] + b*scale < (double)cb[i][3+k]) b += 1.0;
+      qlo[k][sl] = (uint8_t)a; qhi[k][sl] = (uint8_t)b;
+    }
+    const uint32_t r = ch[i], cnt = bref_count(A.nodes, r);
+    if((r & BLEAF) || cnt <= A.leaf_max) child[sl] = CB8_LEAF | (bref_first(A.nodes, r) << 3) | cnt;
+    else
+    {
+      const uint32_t w = atomicAdd(A.num_wide, 1u);
+      child[sl] = w;
+      const uint32_t o = atomicAdd(num_out, 1u);
+      if(o < A.max_wide) { out[o].bref = r; out[o].wide = w; }
+    }
+  }
+  Node8 nd;
+  for(int k=0;k<3;k++) nd.origin[k] = lo[k];
+  nd.exps = (uint32_t)(e[0] + 7 + 127) | ((uint32_t)(e[1] + 7 + 127) << 8) | ((uint32_t)(e[2] + 7 + 127) << 16);
+  for(int k=0;k<3;k++)
+    for(int h=0;h<2;h++)
+    {
+      nd.planes[4*k + h]     = (uint32_t)qlo[k][4*h] | ((uint32_t)qlo[k][4*h+1] << 8) | ((uint32_t)qlo[k][4*h+2] << 16) | ((uint32_t)qlo[k][4*h+3] << 24);
+      nd.planes[4*k + 2 + h] = (uint32_t)qhi[k][4*h] | ((uint32_t)qhi[k][4*h+1] << 8) | ((uint32_t)qhi[k][4*h+2] << 16) | ((uint32_t)qhi[k][4*h+3] << 24);
+    }
+  for(int sl=0;sl<8;sl++) nd.child[sl] = child[sl];
+  A.out[it.wide] = nd;
+}
+
 __global__ void k_parents(Node256 *nodes, uint32_t num)
 {
   const uint32_t i = blockIdx.x*blockDim.x + threadIdx.x;
@@ -554,6 +682,55 @@ int cb200_build_lbvh(cb200_accel *a, const float *ghost_aabb)
     CB_CUDA(cudaStreamSynchronize(st));
     cudaFree(a->d_nodes);
     a->d_nodes = small;
+  }
+
+  // ---- the 8-wide compressed tree over the same binary tree and primitive order (static scenes: the throughput path)
+  a->d_nodes8 = nullptr; a->dev.nodes8 = nullptr; a->dev.num_nodes8 = 0; a->dev.depth8 = 0;
+  {
+    const char *e8 = getenv("CB200_BUILD_WIDE8");
+    bool small_coords = true;   // the byte slab test keeps 2^e/d and (origin - p)/d finite for coordinates below 2^40 (traverse8.cu:ray8_ok)
+    CB_CUDA(cudaMemcpyAsync(h_box, scene_box.p, sizeof(h_box), cudaMemcpyDeviceToHost, st));
+    CB_CUDA(cudaStreamSynchronize(st));
+    for(int k=0;k<6;k++) if(!(fabsf(h_box[k]) < 1099511627776.0f)) small_coords = false;
+    if(!any_mb && n > 0 && small_coords && n < (1u << 28) && !(e8 && !atoi(e8)))
+    {
+      uint32_t leaf_max8 = LEAF_MAX_DEFAULT;
+      if(const char *e = getenv("CB200_LEAF_MAX8")) { const int v = atoi(e); if(v >= 1 && v <= 7) leaf_max8 = (uint32_t)v; }
+      Node8 *big = nullptr;
+      CB_CUDA(cudaMalloc(&big, max_wide*sizeof(Node8)));
+      uint32_t h8[2] = {1, 0};
+      CB_CUDA(cudaMemcpyAsync(counters.p, h8, sizeof(h8), cudaMemcpyHostToDevice, st));
+      CB_CUDA(cudaMemcpyAsync(q0.p, &root, sizeof(root), cudaMemcpyHostToDevice, st));
+      Collapse8Args C8;
+      C8.nodes = bnodes.p; C8.index = index_sorted.p; C8.pbox0 = pbox0.p; C8.nbox0 = nbox0.p;
+      C8.out = big; C8.num_wide = counters.p; C8.max_wide = (uint32_t)max_wide; C8.leaf_max = leaf_max8;
+      uint32_t num8 = 1;
+      int depth8 = 0;
+      qin = q0.p; qout = q1.p;
+      while(num8)
+      {
+        if(++depth8 > 100) { cudaFree(big); cb200_set_error("collapsed 8-wide tree deeper than 100 levels"); return CB200_ERR_UNSUPPORTED; }
+        k_collapse8<<<nblocks(num8), BUILD_BLOCK, 0, st>>>(C8, qin, num8, qout, counters.p + 1);
+        cb200_count_launch();
+        CB_CUDA(cudaMemcpyAsync(h8, counters.p, sizeof(h8), cudaMemcpyDeviceToHost, st));
+        CB_CUDA(cudaStreamSynchronize(st));
+        num8 = h8[1];
+        if(h8[0] > max_wide) { cudaFree(big); cb200_set_error("internal: 8-wide node buffer overflow"); return CB200_ERR_NOMEM; }
+        const uint32_t zero = 0;
+        CB_CUDA(cudaMemcpyAsync(counters.p + 1, &zero, sizeof(zero), cudaMemcpyHostToDevice, st));
+        CollapseItem *tq = qin; qin = qout; qout = tq;
+      }
+      if(h8[0] < (1u << 24))
+      { // a stack word holds the node index in 24 bits
+        CB_CUDA(cudaMalloc(&a->d_nodes8, (size_t)h8[0]*sizeof(Node8)));
+        CB_CUDA(cudaMemcpyAsync(a->d_nodes8, big, (size_t)h8[0]*sizeof(Node8), cudaMemcpyDeviceToDevice, st));
+        CB_CUDA(cudaStreamSynchronize(st));
+        a->dev.nodes8 = a->d_nodes8; a->dev.num_nodes8 = h8[0]; a->dev.depth8 = (uint32_t)depth8;
+        const char *ew = getenv("CB200_WIDE8");
+        a->traversal = (ew && atoi(ew)) ? CB200_TRAVERSAL_WIDE8 : CB200_TRAVERSAL_EXACT4;   // measured slower on the bench (profiles/README.md r2b): opt-in
+      }
+      cudaFree(big);
+    }
   }
   a->dev.nodes = a->d_nodes;
   a->dev.num_nodes = h_cnt[0];

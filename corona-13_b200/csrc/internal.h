@@ -35,8 +35,28 @@ struct __align__(16) Node128
   float    aabb0[6][4];
   uint64_t child[4];       // child[0] bits 56..61 carry axis0 | axis00<<2 | axis01<<4
 };
+// Node8 (static scenes, the throughput path): 8 children in 96 bytes = three 32-byte sectors.  The children's boxes are
+// quantised to 8 bits per plane on a per-node grid: plane = origin[k] + q * 2^e[k]; lower planes are rounded down, upper
+// planes up, so a stored box always CONTAINS the box of the 4-wide tree's child -- boxes only cull, the primitive tests
+// behind them are the reference's own arithmetic, so prim / u / v / dist are unchanged except where two primitives tie or a
+// box test decided by its last ulp (the tree-dependent cases mode B already classifies).
+//   planes[4*k+0..1] = lower planes of children 0..3 / 4..7 along axis k (one byte each), planes[4*k+2..3] = upper planes
+//   exps = E_x | E_y << 8 | E_z << 16: biased IEEE exponent of 128 * 2^e[k] (the traversal decodes a byte as q/128)
+//   child[c]: 0 = empty slot (its box is inverted: lower 255, upper 0), bit 31 = leaf (begin << 3 | count, count <= 7),
+//             else index of the child node.  Slots are assigned by octant (child centre relative to the node centre), so
+//             that slot ^ ray octant approximates the front-to-back order (Ylitie, Karras, Laine 2017).
+struct __align__(32) Node8
+{
+  float    origin[3];
+  uint32_t exps;
+  uint32_t planes[12];
+  uint32_t child[8];
+};
 static_assert(sizeof(Node256) == 256, "Node256");
 static_assert(sizeof(Node128) == 128, "Node128");
+static_assert(sizeof(Node8) == 96, "Node8");
+#define CB8_LEAF 0x80000000u
+#define CB8_STACK 32          // group entries; deeper trees fall back to the 4-wide kernels
 
 #define CB_CHILD_MASK  0x80ffffffffffffffull   // strips the axis bits from Node128::child[0]
 #define CB_AXIS_SHIFT  56
@@ -51,6 +71,9 @@ struct DevAccel
   uint32_t      pad_;
   uint64_t      num_nodes;
   uint64_t      num_prims;
+  const Node8  *nodes8;      // 8-wide compressed tree over the same primitive order (static scenes), or null
+  uint32_t      num_nodes8;
+  uint32_t      depth8;
 };
 
 struct ShapeDev   // offsets of one shape inside the concatenated device arrays
@@ -83,6 +106,8 @@ struct cb200_accel
   float        aabb[6];
   int          depth;      // levels of 4-wide nodes
   int          imported;
+  Node8       *d_nodes8;
+  int          traversal;  // CB200_TRAVERSAL_*: which tree the launchers use (set by the build, changed by cb200_accel_set_traversal)
 };
 
 // error plumbing ------------------------------------------------------------------------------
@@ -97,6 +122,8 @@ int  cb200_sm_count_cached();
 int cb200_build_lbvh(cb200_accel *a, const float *ghost_aabb);
 int cb200_build_records(cb200_accel *a, cudaStream_t stream);
 // traverse.cu
+// d_counters (optional, 4 words): rays, node visits, child boxes hit, primitive tests (ACCEL_DEBUG definitions, qbvhmp.c:83-90).
+// The tree is picked by a->traversal: the 8-wide compressed one when the accel has it, else the 4-wide tree the reference's order is defined on
 int cb200_launch_intersect(const cb200_accel *a, const cb_ray_t *d_rays, const float *d_max_dist, cb_hitrec_t *d_out,
                            uint64_t n, cudaStream_t stream, unsigned long long *d_counters);
 int cb200_launch_visible(const cb200_accel *a, const cb_ray_t *d_rays, const float *d_max_dist, int32_t *d_out,
@@ -105,3 +132,14 @@ int cb200_launch_closest(const cb200_accel *a, cb_ray_t *d_rays, cb_hitrec_t *d_
 // next-event visibility (path_visible semantics): any primitive other than d_light_prim[i] accepted by the closest-hit rules
 int cb200_launch_shadow(const cb200_accel *a, const cb_ray_t *d_rays, const float *d_max_dist, const uint2 *d_light_prim, int32_t *d_out,
                         uint64_t n, cudaStream_t stream);
+// traverse8.cu: the same three entries on the 8-wide compressed tree (a->dev.nodes8 != null)
+int cb200_launch_intersect8(const cb200_accel *a, const cb_ray_t *d_rays, const float *d_max_dist, cb_hitrec_t *d_out,
+                            uint64_t n, cudaStream_t stream, unsigned long long *d_counters);
+int cb200_launch_visible8(const cb200_accel *a, const cb_ray_t *d_rays, const float *d_max_dist, const uint2 *d_light_prim, int32_t *d_out,
+                          uint64_t n, cudaStream_t stream);
+bool cb200_use_wide8(const cb200_accel *a);
+// shared launch plumbing (traverse.cu)
+int cb200_get_ticket(cudaStream_t stream, unsigned int **t);
+int cb200_trace_grid(uint64_t n, const void *kernel);
+int cb200_prim_threshold();
+int cb200_refill_threshold();

@@ -25,120 +25,15 @@
 //   * the visiting order is three conditional swaps on (entry distance, child) pairs;
 //   * child references are 32 bits inside the kernel while the scene allows (< 2^26 primitives): one 8-byte stack word per
 //     entry; kernel variants by scene content (motion blur, analytic primitives, instrumentation).
-#include "prims.cuh"
 #include <atomic>
 #include <mutex>
 #include <cstdlib>
 #include <type_traits>
 
-#define TRACE_BLOCK 128
-#ifndef TRACE_MIN_BLOCKS
-#define TRACE_MIN_BLOCKS 8   // static triangle scenes: cap at 64 registers -> 32 resident warps per SM
-#endif
-#define FULL 0xffffffffu
-
-__device__ __forceinline__ float sse_min(float a, float b) { return a < b ? a : b; }   // _mm_min_ps
-__device__ __forceinline__ float sse_max(float a, float b) { return a > b ? a : b; }   // _mm_max_ps
-
-struct NodeOut
-{
-  float tmin[4];
-  bool hit[4];
-  uint64_t child[4];
-  int axis0, axis00, axis01;
-};
-
-// EXACT: reference select semantics; otherwise fminf/fmaxf (only valid when no NaN can occur)
-template<bool MB, bool EXACT>
-__device__ __forceinline__ void node_slabs(const void *nodes, uint64_t idx, float px, float py, float pz,
-                                           float ix, float iy, float iz, float t0, float t1, float tmax_init, NodeOut &o,
-                                           float tmin_init = 0.0f)
-{
-  float tmin[4] = {tmin_init, tmin_init, tmin_init, tmin_init};
-  float tmax[4] = {tmax_init, tmax_init, tmax_init, tmax_init};
-  const float pos[3] = {px, py, pz};
-  const float inv[3] = {ix, iy, iz};
-  const float4 *a0;
-  const ulonglong2 *ch;
-  if(MB)
-  {
-    const Node256 *n = reinterpret_cast<const Node256 *>(nodes) + idx;
-    a0 = reinterpret_cast<const float4 *>(n->aabb0);
-    ch = reinterpret_cast<const ulonglong2 *>(n->child);
-  }
-  else
-  {
-    const Node128 *n = reinterpret_cast<const Node128 *>(nodes) + idx;
-    a0 = reinterpret_cast<const float4 *>(n->aabb0);
-    ch = reinterpret_cast<const ulonglong2 *>(n->child);
-  }
-#pragma unroll
-  for(int k=0;k<3;k++)
-  {
-    const float4 m0 = __ldg(a0 + k), M0 = __ldg(a0 + k + 3);
-    float mo[4] = {m0.x, m0.y, m0.z, m0.w}, Mo[4] = {M0.x, M0.y, M0.z, M0.w};
-    if(MB)
-    {
-      const float4 m1 = __ldg(a0 + 6 + k), M1 = __ldg(a0 + 6 + k + 3);
-      const float mc[4] = {m1.x, m1.y, m1.z, m1.w}, Mc[4] = {M1.x, M1.y, M1.z, M1.w};
-#pragma unroll
-      for(int c=0;c<4;c++) { mo[c] = mo[c]*t0 + mc[c]*t1; Mo[c] = Mo[c]*t0 + Mc[c]*t1; }
-    }
-#pragma unroll
-    for(int c=0;c<4;c++)
-    {
-      const float lo = (mo[c] - pos[k]) * inv[k];
-      const float hi = (Mo[c] - pos[k]) * inv[k];
-      if(EXACT)
-      {
-        tmin[c] = sse_max(tmin[c], sse_min(lo, hi));
-        tmax[c] = sse_min(tmax[c], sse_max(lo, hi));
-      }
-      else
-      {
-        tmin[c] = fmaxf(tmin[c], fminf(lo, hi));
-        tmax[c] = fminf(tmax[c], fmaxf(lo, hi));
-      }
-    }
-  }
-  const ulonglong2 c01 = __ldg(ch), c23 = __ldg(ch + 1);
-  if(MB)
-  {
-    const ulonglong2 pa = __ldg(ch + 2), aa = __ldg(ch + 3);   // {parent, axis0}, {axis00, axis01}
-    o.child[0] = c01.x;
-    o.axis0 = (int)pa.y; o.axis00 = (int)aa.x; o.axis01 = (int)aa.y;
-  }
-  else
-  {
-    const uint32_t ax = (uint32_t)(c01.x >> CB_AXIS_SHIFT) & 63u;
-    o.child[0] = c01.x & CB_CHILD_MASK;
-    o.axis0 = ax & 3; o.axis00 = (ax >> 2) & 3; o.axis01 = (ax >> 4) & 3;
-  }
-  o.child[1] = c01.y; o.child[2] = c23.x; o.child[3] = c23.y;
-#pragma unroll
-  for(int c=0;c<4;c++) { o.tmin[c] = tmin[c]; o.hit[c] = tmin[c] <= tmax[c]; }
-}
-
-__device__ __forceinline__ void load_ray(const cb_ray_t *rays, uint32_t i, RayD &r)
-{
-  const float2 *p = reinterpret_cast<const float2 *>(rays + i);   // 40-byte records are 8-byte aligned
-  const float2 a = __ldg(p), b = __ldg(p+1), c = __ldg(p+2), d = __ldg(p+3), e = __ldg(p+4);
-  r.px = a.x; r.py = a.y; r.pz = b.x; r.dx = b.y; r.dy = c.x; r.dz = c.y;
-  r.time = d.x; r.min_dist = d.y;
-  r.ign_lo = __float_as_uint(e.x); r.ign_hi = __float_as_uint(e.y);
-}
-
-__device__ __forceinline__ bool finite_nonzero(float x) { const float a = fabsf(x); return a > 0.0f && a < __int_as_float(0x7f800000); }
-__device__ __forceinline__ bool finite(float x) { return fabsf(x) < __int_as_float(0x7f800000); }
-
-// a leaf reference with count 0 (the reference builder emits them with a non-zero begin, qbvhmp.c:989)
-__device__ __forceinline__ bool is_empty_leaf(uint64_t c) { return (c & CB_LEAF_BIT) && !(c & 31ull); }
+#include "traverse_common.cuh"
 
 #define SEL4(arr, i) ((i) == 0 ? arr[0] : (i) == 1 ? arr[1] : (i) == 2 ? arr[2] : arr[3])
 
-enum { ST_IDLE = 0, ST_NODE = 1, ST_PRIM = 2 };
-#define KEY_MISS __int_as_float(0x7fc00000)
-#define KEY_HIT(k) ((k) == (k))
 
 // Fast slab test for static nodes and rays whose direction components are all finite and non-zero: the near / far plane
 // of every axis is picked by the ray's sign when the row is LOADED (rows 0..2 = min, 3..5 = max of Node128::aabb0), so that
@@ -153,6 +48,7 @@ __device__ __forceinline__ void node_slabs_fast(const Node128 *__restrict__ n, c
   const float4 *a0 = reinterpret_cast<const float4 *>(n->aabb0);
   const float4 nx = __ldg(a0 + near_off[0]),     ny = __ldg(a0 + 1 + near_off[1]),     nz = __ldg(a0 + 2 + near_off[2]);
   const float4 fx = __ldg(a0 + 3 - near_off[0]), fy = __ldg(a0 + 4 - near_off[1]),     fz = __ldg(a0 + 5 - near_off[2]);
+#ifdef CB200_SCALAR_SLABS
   const float nxa[4] = {nx.x, nx.y, nx.z, nx.w}, nya[4] = {ny.x, ny.y, ny.z, ny.w}, nza[4] = {nz.x, nz.y, nz.z, nz.w};
   const float fxa[4] = {fx.x, fx.y, fx.z, fx.w}, fya[4] = {fy.x, fy.y, fy.z, fy.w}, fza[4] = {fz.x, fz.y, fz.z, fz.w};
 #pragma unroll
@@ -162,6 +58,24 @@ __device__ __forceinline__ void node_slabs_fast(const Node128 *__restrict__ n, c
     const float tmax = fminf(fminf(tmax_init, (fxa[c] - px)*ix), fminf((fya[c] - py)*iy, (fza[c] - pz)*iz));
     key[c] = tmin <= tmax ? tmin : KEY_MISS;
   }
+#else
+  // the 24 plane distances as 12 packed subtractions + 12 packed multiplications (two children per instruction), the entry /
+  // exit distances with the three-input min / max: no operand can be NaN here (finite non-zero 1/d, finite origin, finite planes)
+  float a[4], b[4], c[4], d[4], e[4], f[4];
+  slab2(nx.x, nx.y, px, ix, a[0], a[1]); slab2(nx.z, nx.w, px, ix, a[2], a[3]);
+  slab2(ny.x, ny.y, py, iy, b[0], b[1]); slab2(ny.z, ny.w, py, iy, b[2], b[3]);
+  slab2(nz.x, nz.y, pz, iz, c[0], c[1]); slab2(nz.z, nz.w, pz, iz, c[2], c[3]);
+  slab2(fx.x, fx.y, px, ix, d[0], d[1]); slab2(fx.z, fx.w, px, ix, d[2], d[3]);
+  slab2(fy.x, fy.y, py, iy, e[0], e[1]); slab2(fy.z, fy.w, py, iy, e[2], e[3]);
+  slab2(fz.x, fz.y, pz, iz, f[0], f[1]); slab2(fz.z, fz.w, pz, iz, f[2], f[3]);
+#pragma unroll
+  for(int k=0;k<4;k++)
+  {
+    const float tmin = fmaxf(max3f(a[k], b[k], c[k]), 0.0f);
+    const float tmax = fminf(min3f(d[k], e[k], f[k]), tmax_init);
+    key[k] = tmin <= tmax ? tmin : KEY_MISS;
+  }
+#endif
 }
 
 // the same for nodes with shutter-open and shutter-close boxes: every plane is first interpolated to the ray's time exactly
@@ -177,18 +91,19 @@ __device__ __forceinline__ void node_slabs_fast_mb(const Node256 *__restrict__ n
   q[3] = __ldg(a0 + 3 - near_off[0]); w[3] = __ldg(a1 + 3 - near_off[0]);
   q[4] = __ldg(a0 + 4 - near_off[1]); w[4] = __ldg(a1 + 4 - near_off[1]);
   q[5] = __ldg(a0 + 5 - near_off[2]); w[5] = __ldg(a1 + 5 - near_off[2]);
-  float pl[6][4];
+  float d[6][4];   // plane distances: rows 0..2 entry (x, y, z), 3..5 exit; two children per packed instruction
+  const float pos[3] = {px, py, pz}, inv[3] = {ix, iy, iz};
 #pragma unroll
   for(int k=0;k<6;k++)
   {
-    pl[k][0] = q[k].x*t0 + w[k].x*t1; pl[k][1] = q[k].y*t0 + w[k].y*t1;
-    pl[k][2] = q[k].z*t0 + w[k].z*t1; pl[k][3] = q[k].w*t0 + w[k].w*t1;
+    lerp_slab2(q[k].x, q[k].y, w[k].x, w[k].y, t0, t1, pos[k % 3], inv[k % 3], d[k][0], d[k][1]);
+    lerp_slab2(q[k].z, q[k].w, w[k].z, w[k].w, t0, t1, pos[k % 3], inv[k % 3], d[k][2], d[k][3]);
   }
 #pragma unroll
   for(int c=0;c<4;c++)
   {
-    const float tmin = fmaxf(fmaxf(0.0f, (pl[0][c] - px)*ix), fmaxf((pl[1][c] - py)*iy, (pl[2][c] - pz)*iz));
-    const float tmax = fminf(fminf(tmax_init, (pl[3][c] - px)*ix), fminf((pl[4][c] - py)*iy, (pl[5][c] - pz)*iz));
+    const float tmin = fmaxf(max3f(d[0][c], d[1][c], d[2][c]), 0.0f);
+    const float tmax = fminf(min3f(d[3][c], d[4][c], d[5][c]), tmax_init);
     key[c] = tmin <= tmax ? tmin : KEY_MISS;
   }
 }
@@ -658,7 +573,7 @@ static std::atomic<unsigned> g_ticket_next[MAX_DEVICES];
 static std::mutex g_ticket_mutex;
 static int g_prim_threshold = 1000;
 
-static int prim_threshold()
+int cb200_prim_threshold()
 {
   if(g_prim_threshold == 1000)
   {
@@ -672,7 +587,7 @@ static int prim_threshold()
   return g_prim_threshold;
 }
 
-static int get_ticket(cudaStream_t stream, unsigned int **t)
+int cb200_get_ticket(cudaStream_t stream, unsigned int **t)
 {
   int dev = 0;
   CB_CUDA(cudaGetDevice(&dev));
@@ -687,7 +602,7 @@ static int get_ticket(cudaStream_t stream, unsigned int **t)
   return 0;
 }
 
-static int grid_for(uint64_t n, const void *kernel)
+int cb200_trace_grid(uint64_t n, const void *kernel)
 {
   int per_sm = 0;
   cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, TRACE_BLOCK, 0);
@@ -698,8 +613,6 @@ static int grid_for(uint64_t n, const void *kernel)
 }
 
 // the stack must hold 3 entries per tree level (qbvhmp.c:1277); pick the smallest variant that fits
-#define STACK_SMALL 64
-#define STACK_BIG   304
 // rays per launch: tickets are 32 bits and every warp draws one batch beyond the end
 #define LAUNCH_MAX_RAYS (1ull << 30)
 
@@ -707,7 +620,7 @@ static int grid_for(uint64_t n, const void *kernel)
 static bool force_ref64() { static int v = -1; if(v < 0) { const char *e = getenv("CB200_FORCE_REF64"); v = (e && atoi(e)) ? 1 : 0; } return v == 1; }
 
 static int g_refill_threshold = -1;
-static int refill_threshold()
+int cb200_refill_threshold()
 {
   if(g_refill_threshold < 0)
   {
@@ -729,9 +642,9 @@ static int launch_intersect_k2(const cb200_accel *a, const cb_ray_t *d_rays, con
   {
     const uint64_t m = n - first < LAUNCH_MAX_RAYS ? n - first : LAUNCH_MAX_RAYS;
     unsigned int *ticket;
-    if(int rc = get_ticket(stream, &ticket)) return rc;
-    k<<<grid_for(m, (const void *)k), TRACE_BLOCK, 0, stream>>>(a->dev, d_rays + first, d_max_dist ? d_max_dist + first : nullptr, d_out + first,
-                                                                (uint32_t)m, ticket, d_counters, prim_threshold(), refill_threshold());
+    if(int rc = cb200_get_ticket(stream, &ticket)) return rc;
+    k<<<cb200_trace_grid(m, (const void *)k), TRACE_BLOCK, 0, stream>>>(a->dev, d_rays + first, d_max_dist ? d_max_dist + first : nullptr, d_out + first,
+                                                                (uint32_t)m, ticket, d_counters, cb200_prim_threshold(), cb200_refill_threshold());
     cb200_count_launch();
     CB_CUDA(cudaGetLastError());
   }
@@ -763,10 +676,18 @@ static int launch_intersect_t(const cb200_accel *a, const cb_ray_t *d_rays, cons
                   : launch_intersect_k<MB, false, STACK_BIG, false>(a, d_rays, d_max_dist, d_out, n, stream, nullptr);
 }
 
+// the 8-wide kernels serve an accel that has the compressed tree, selected it (cb200_accel_set_traversal, or CB200_WIDE8=1 in
+// the environment at build time for A/B measurements) and fits their stacks
+bool cb200_use_wide8(const cb200_accel *a)
+{
+  return a->traversal == CB200_TRAVERSAL_WIDE8 && a->dev.nodes8 && a->dev.depth8 < CB8_STACK && 3*a->depth + 4 <= STACK_SMALL;
+}
+
 int cb200_launch_intersect(const cb200_accel *a, const cb_ray_t *d_rays, const float *d_max_dist, cb_hitrec_t *d_out,
                            uint64_t n, cudaStream_t stream, unsigned long long *d_counters)
 {
   if(n == 0) return 0;
+  if(cb200_use_wide8(a)) return cb200_launch_intersect8(a, d_rays, d_max_dist, d_out, n, stream, d_counters);
   return a->dev.mb ? launch_intersect_t<true >(a, d_rays, d_max_dist, d_out, n, stream, d_counters)
                    : launch_intersect_t<false>(a, d_rays, d_max_dist, d_out, n, stream, d_counters);
 }
@@ -780,10 +701,10 @@ static int launch_visible_k(const cb200_accel *a, const cb_ray_t *d_rays, const 
   {
     const uint64_t m = n - first < LAUNCH_MAX_RAYS ? n - first : LAUNCH_MAX_RAYS;
     unsigned int *ticket;
-    if(int rc = get_ticket(stream, &ticket)) return rc;
+    if(int rc = cb200_get_ticket(stream, &ticket)) return rc;
 #define VIS_LAUNCH(SH, C) do { auto k = k_visible<MB, STACK, ANALYTIC, SH, C>; \
-    k<<<grid_for(m, (const void *)k), TRACE_BLOCK, 0, stream>>>(a->dev, d_rays + first, d_max_dist + first, d_skip ? d_skip + first : nullptr, d_out + first, \
-                                                                (uint32_t)m, ticket, prim_threshold(), refill_threshold()); } while(0)
+    k<<<cb200_trace_grid(m, (const void *)k), TRACE_BLOCK, 0, stream>>>(a->dev, d_rays + first, d_max_dist + first, d_skip ? d_skip + first : nullptr, d_out + first, \
+                                                                (uint32_t)m, ticket, cb200_prim_threshold(), cb200_refill_threshold()); } while(0)
     if(d_skip) { if(c32) VIS_LAUNCH(true, true); else VIS_LAUNCH(true, false); }
     else       { if(c32) VIS_LAUNCH(false, true); else VIS_LAUNCH(false, false); }
 #undef VIS_LAUNCH
@@ -812,6 +733,7 @@ int cb200_launch_visible(const cb200_accel *a, const cb_ray_t *d_rays, const flo
 {
   if(n == 0) return 0;
   if(!d_max_dist) { cb200_set_error("visible: max_dist is required"); return CB200_ERR_ARG; }
+  if(cb200_use_wide8(a)) return cb200_launch_visible8(a, d_rays, d_max_dist, nullptr, d_out, n, stream);
   return a->dev.mb ? launch_visible_t<true>(a, d_rays, d_max_dist, nullptr, d_out, n, stream)
                    : launch_visible_t<false>(a, d_rays, d_max_dist, nullptr, d_out, n, stream);
 }
@@ -821,6 +743,7 @@ int cb200_launch_shadow(const cb200_accel *a, const cb_ray_t *d_rays, const floa
 {
   if(n == 0) return 0;
   if(!d_max_dist || !d_light_prim) { cb200_set_error("shadow: max_dist and light prims are required"); return CB200_ERR_ARG; }
+  if(cb200_use_wide8(a)) return cb200_launch_visible8(a, d_rays, d_max_dist, d_light_prim, d_out, n, stream);
   return a->dev.mb ? launch_visible_t<true>(a, d_rays, d_max_dist, d_light_prim, d_out, n, stream)
                    : launch_visible_t<false>(a, d_rays, d_max_dist, d_light_prim, d_out, n, stream);
 }

@@ -24,6 +24,7 @@ SYMBOLS = [
     "cb200_accel_depth", "cb200_accel_aabb", "cb200_accel_export_qbvh", "cb200_accel_layout",
     "cb200_accel_intersect_n", "cb200_accel_visible_n", "cb200_accel_closest_n", "cb200_accel_intersect_dev",
     "cb200_accel_visible_dev", "cb200_accel_intersect_counted", "cb200_launch_count",
+    "cb200_accel_set_traversal", "cb200_accel_traversal",
 ]
 
 
@@ -80,6 +81,8 @@ def load():
     L.cb200_accel_visible_dev.argtypes = [vp, vp, vp, vp, u64, vp]
     L.cb200_accel_intersect_counted.argtypes = [vp, vp, vp, vp, u64, vp]
     L.cb200_launch_count.restype = u64
+    L.cb200_accel_set_traversal.argtypes = [vp, i32]
+    L.cb200_accel_traversal.argtypes = [vp]
     _lib = L
     return L
 
@@ -154,6 +157,18 @@ class Accel:
 
     def num_nodes(self):
         return int(self.L.cb200_accel_num_nodes(self.a))
+
+    def set_traversal(self, mode):
+        """EXACT4 (0) = the reference's order on the 4-wide tree, WIDE8 (1) = the 8-wide compressed tree"""
+        _check(self.L.cb200_accel_set_traversal(self.a, int(mode)), "cb200_accel_set_traversal")
+        return self
+
+    def try_traversal(self, mode):
+        """select the mode if this accel supports it (WIDE8 needs the compressed tree: static scene, GPU-built)"""
+        return self.L.cb200_accel_set_traversal(self.a, int(mode)) == 0
+
+    def traversal(self):
+        return int(self.L.cb200_accel_traversal(self.a))
 
     def depth(self):
         return int(self.L.cb200_accel_depth(self.a))

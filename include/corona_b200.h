@@ -75,6 +75,24 @@ int      cb200_accel_export_qbvh(const cb200_accel_t *a, cb_qbvh_node_t *nodes, 
 /* bytes one node / one primitive record occupy in HBM (roofline accounting) */
 int      cb200_accel_layout(const cb200_accel_t *a, uint32_t *node_bytes, uint32_t *prim_bytes);
 
+/* Which tree the traversal entries below walk.
+ *   CB200_TRAVERSAL_EXACT4: the 4-wide tree in the reference's node layout, visited in the reference's order
+ *     (qbvhmp.c:1262-1490): results are bit-identical to the reference algorithm on that tree, ties included.  Always
+ *     available; the only mode for motion-blurred scenes and imported reference trees.
+ *   CB200_TRAVERSAL_WIDE8: the 8-wide compressed tree cb200_accel_build also makes for static scenes (same primitive order,
+ *     quantised conservative child boxes, octant visiting order): a third of the node bytes per ray; opt-in, because on
+ *     B200 the traversal is issue bound, not byte bound, and the 4-wide kernel is the faster one.
+ *     Every primitive test is the reference's arithmetic, so prim / u / v / dist are the same bits except where two
+ *     primitives lie at exactly the same distance along the ray (the last one TESTED wins in the reference,
+ *     geo/triangle.h:296, and the order is the tree's) or a child box is grazed within its last ulp -- the tree-dependent
+ *     cases in which the reference's own answer changes with its builder.
+ * set_traversal fails with CB200_ERR_UNSUPPORTED when WIDE8 is asked of an accel without that tree; not thread-safe
+ * against concurrent traversal calls.                                                                                   */
+#define CB200_TRAVERSAL_EXACT4 0
+#define CB200_TRAVERSAL_WIDE8  1
+int      cb200_accel_set_traversal(cb200_accel_t *a, int mode);
+int      cb200_accel_traversal(const cb200_accel_t *a);
+
 /* ---- traversal: batched accel_intersect / accel_visible (accel.h:40,43; qbvhmp.c:1262-1490).
  *      rays: n cb_ray_t;  max_dist: n floats or NULL (= FLT_MAX; the reference presets
  *      hit->dist, pathspace.c:762);  out: n cb_hitrec_t {prim,u,v,dist}, prim == INVALID and

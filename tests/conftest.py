@@ -30,3 +30,19 @@ def built():
 @pytest.fixture(scope="session")
 def lib(built):
     return importlib.import_module("corona-13_b200.lib")
+
+
+def pytest_terminal_summary(terminalreporter):
+    """tie rate of the two traversal modes (helpers.intersect_modes): rays compared, answers that differ, all classified"""
+    try:
+        from helpers import TIE_LOG
+    except Exception:
+        return
+    if not TIE_LOG:
+        return
+    rays = sum(n for _, n, _ in TIE_LOG)
+    diff = sum(d for _, _, d in TIE_LOG)
+    terminalreporter.write_line(f"WIDE8 vs EXACT4: {rays} rays compared, {diff} answers differ ({diff / max(rays, 1):.2e}), every one classified as tie / grazed box")
+    for what, n, d in TIE_LOG:
+        if d:
+            terminalreporter.write_line(f"  {what}: {d} of {n}")

@@ -14,7 +14,7 @@ import os
 import numpy as np
 import pytest
 
-from helpers import Golden, GOLDEN_NAMES, S, R, assert_hits_equal, classify_mismatches
+from helpers import Golden, GOLDEN_NAMES, S, R, assert_hits_equal, classify_mismatches, intersect_modes, visible_modes
 from oracle.binding import Oracle
 
 pytestmark = pytest.mark.gpu
@@ -61,11 +61,11 @@ def test_mode_b_golden(gpu, name):
         assert np.array_equal(acc.aabb().view("u4"), g.aabb.view("u4"))
     for rays, want, md, what in [(g.rays, g.hits, None, "closest"), (g.bounce, g.hits_bounce, None, "bounce"),
                                  (g.rays, g.hits_md, g.max_dist, "preset dist")]:
-        got = acc.intersect(rays, md)
+        got = intersect_modes(acc, orc, rays, md, f"{name} {what}")
         assert_hits_equal(got, orc.intersect(rays, md), what + " vs oracle on the same tree")
         nm, nt = classify_mismatches(orc, rays, got, want, md)
         assert nm == nt, f"{what}: {nm - nt} of {nm} differences vs the reference are not order effects"
-    assert np.array_equal(acc.visible(g.shadow, g.shadow_max_dist), g.vis)
+    assert np.array_equal(visible_modes(acc, g.shadow, g.shadow_max_dist, name), g.vis)
     acc.close()
     orc.close()
 
@@ -106,14 +106,15 @@ def test_mode_a_and_b_vs_oracle(gpu, case):
     nodes, primid = acc.export_qbvh()
     chk = Oracle(sc).import_tree(nodes, acc.aabb(), primid)
     assert chk.check()[0] == 0
-    got = acc.intersect(rays)
+    got = intersect_modes(acc, orc, rays, None, f"{case} closest")
     assert_hits_equal(got, chk.intersect(rays), "mode B vs oracle on the GPU tree")
     nm, nt = classify_mismatches(orc, rays, got, want)
     assert nm == nt, f"{nm - nt} of {nm} mode-B differences are not order effects"
-    got_b = acc.intersect(br)
+    got_b = intersect_modes(acc, orc, br, None, f"{case} bounce")
+    assert_hits_equal(got_b, chk.intersect(br), "mode B bounce vs oracle on the GPU tree")
     nm, nt = classify_mismatches(orc, br, got_b, want_b)
     assert nm == nt
-    assert np.array_equal(acc.visible(sr, md), want_v)
+    assert np.array_equal(visible_modes(acc, sr, md, case), want_v)
     acc.close()
     orc.close()
     chk.close()
@@ -141,7 +142,7 @@ def test_zero_rays_and_tiny_scenes(gpu):
         orc = Oracle(sc).import_tree(nodes, acc.aabb(), primid)
         assert orc.check()[0] == 0
         rays = S.random_rays(2000, sc, seed=ntri)
-        assert_hits_equal(acc.intersect(rays), orc.intersect(rays), f"{ntri} triangles")
+        assert_hits_equal(intersect_modes(acc, orc, rays, None, f"{ntri} triangles"), orc.intersect(rays), f"{ntri} triangles")
         acc.close()
         orc.close()
 
@@ -160,7 +161,7 @@ def test_duplicate_and_degenerate_prims(gpu):
     orc = Oracle(sc).import_tree(nodes, acc.aabb(), primid)
     assert orc.check()[0] == 0
     rays = S.random_rays(20000, sc, seed=8)
-    assert_hits_equal(acc.intersect(rays), orc.intersect(rays), "duplicates")
+    assert_hits_equal(intersect_modes(acc, orc, rays, None, "duplicates"), orc.intersect(rays), "duplicates")
     acc.close()
     orc.close()
 
@@ -196,9 +197,9 @@ def test_large_batch_is_chunked(gpu):
     sc = S.synthetic_scene(20000, seed=11)
     acc = gpu.Accel(sc).build()
     rays = S.camera_rays((1 << 22) + 12345, sc, seed=12)
-    got = acc.intersect(rays)
     nodes, primid = acc.export_qbvh()
     orc = Oracle(sc).import_tree(nodes, acc.aabb(), primid)
+    got = intersect_modes(acc, orc, rays, None, "chunked batch")
     idx = np.concatenate([np.arange(0, 50000), np.arange(len(rays) - 50000, len(rays))])
     assert_hits_equal(got[idx], orc.intersect(rays[idx]), "chunked batch")
     acc.close()
@@ -321,7 +322,9 @@ def test_full_size_properties(gpu):
     # (4) oracle on the exported tree, 100 k ray sample
     orc = Oracle(sc).import_tree(nodes, acc.aabb(), primid)
     idx = np.random.default_rng(5).choice(len(rays), 100000, replace=False)
-    assert_hits_equal(h[idx], orc.intersect(rays[idx]), "10 M sample")
+    assert_hits_equal(intersect_modes(acc, orc, rays[idx], None, "10 M sample"), orc.intersect(rays[idx]), "10 M sample")
+    # the two traversal modes over the whole 4 Mi-ray set: differences counted (tie rate), each one classified
+    intersect_modes(acc, orc, rays, None, "10 M triangles, 4 Mi rays")
     assert orc.check()[0] == 0
     acc.close()
     orc.close()
