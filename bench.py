@@ -57,11 +57,16 @@ METRIC = "rays/s (closest-hit + shadow)"
 REFDIR = os.path.join(ROOT, "oracle", "_ref")
 
 
+NCU_SUMMARY = "profiles/r1h_k_intersect_ncu.json"
+NCU_COMMAND = ("ncu --set full --clock-control none --import-source on -k regex:k_intersect -s 20 -c 6 -o gpurun_out/r1h_k_intersect "
+               "python scripts/gpu_render_bench.py; ncu -i gpurun_out/r1h_k_intersect.ncu-rep --page raw --csv | python scripts/ncu_summary.py")
+
+
 def ncu_traffic():
     """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel from the committed `ncu --set full` capture
     of the same workload (profiles/r1h_k_intersect_ncu.json: the full ~8.3 M-ray waves among the captured launches); None when the
     summary is not there"""
-    p = os.path.join(ROOT, "profiles", "r1h_k_intersect_ncu.json")
+    p = os.path.join(ROOT, NCU_SUMMARY)
     try:
         rows = json.load(open(p))
         tot = []
@@ -144,6 +149,7 @@ class ReferenceRenderer:
             raise RuntimeError("oracle/_ref/corona_ptdl_rand is not built (python -c 'import __graft_entry__ as g; g.build()' "
                                "where /root/reference exists)")
         IO = cb.scene_io
+        self.IO = IO
         self.tmp = tempfile.mkdtemp(prefix="corona_bench_")
         shapes = []
         for i, sh in enumerate(scene.shapes):
@@ -154,11 +160,13 @@ class ReferenceRenderer:
         camera.write(os.path.join(self.tmp, "test01.cam"))
         self.cores = os.cpu_count() or 1
 
-    def run(self, binary, w, h, spp):
-        """returns (seconds per progression [list], accel build seconds, total accel_intersect calls or None)"""
+    def run(self, binary, w, h, spp, frame=1):
+        """returns (seconds per progression [list], accel build seconds, total accel_intersect calls or None); the image the
+        run leaves behind (<scene>render_fb00.pfm, fb_export at exit) is read by image()"""
         cmd = [os.path.join(REFDIR, binary), self.nra2, "-x", "-s", str(spp), "-w", str(w), "-h", str(h), "-b", "0",
-               "-t", str(self.cores), "--frame", "1"]
+               "-t", str(self.cores), "--frame", str(frame)]
         p = subprocess.run(cmd, cwd=REFDIR, capture_output=True, text=True)
+        self.last_stderr = p.stderr
         if p.returncode != 0:
             raise RuntimeError(f"{binary} failed ({p.returncode}): {p.stderr[-400:]}")
         frames = [float(x) for x in re.findall(r"([0-9.]+) s/frame, \d+ spp", p.stdout)]
@@ -166,14 +174,55 @@ class ReferenceRenderer:
         rays = [int(x) for x in re.findall(r"accel_intersect: (\d+)", p.stderr)]
         return frames, (float(build[0]) if build else None), (sum(rays) if rays else None)
 
-    def rays_per_path(self):
-        """-DACCEL_DEBUG twin at a quarter of the frame in each direction (rays per path do not depend on resolution)"""
+    def image(self):
+        return self.IO.read_pfm(os.path.splitext(self.nra2)[0] + "render_fb00.pfm")
+
+    def rays_per_path(self, counters=False):
+        """-DACCEL_DEBUG twin at a quarter of the frame in each direction (rays per path do not depend on resolution).
+        counters=True also returns the reference's own per-ray traversal work on ITS binned-SAH tree of this scene
+        (qbvhmp.c:1168-1171: calls, node tests with >= 1 child hit, child boxes hit, primitive tests -- summed over the
+        closest-hit and the next-event calls, which both go through accel_intersect in the reference)"""
         w, h = WIDTH // 4, HEIGHT // 4
         _, _, rays = self.run("corona_ptdl_rand_dbg", w, h, 1)
-        return rays / float(w * h)
+        if not counters:
+            return rays / float(w * h)
+        m = re.findall(r"accel_intersect: (\d+) aabb_intersect (\d+) / (\d+) prims_intersect (\d+)", self.last_stderr)
+        tot = np.array([[int(x) for x in row] for row in m], np.float64).sum(axis=0) if m else None
+        dbg = None
+        if tot is not None and tot[0] > 0:
+            dbg = {"rays": tot[0], "nodes_per_ray": tot[2] / tot[0], "child_boxes_hit_per_ray": tot[1] / tot[0], "prims_per_ray": tot[3] / tot[0],
+                   "note": "reference renderer, own binned-SAH tree, closest-hit + next-event calls together (qbvhmp.c ACCEL_DEBUG)"}
+        return rays / float(w * h), dbg
 
     def close(self):
         shutil.rmtree(self.tmp, ignore_errors=True)
+
+
+PARITY_SPP = 2            # progressions per image of the bench-scene parity check (reference: ~2 s each on 32 threads)
+PARITY_BLOCK = 16         # compared after averaging 16x16 pixel blocks: 8.4 M pixels at 2 spp are mostly noise
+REF_ARM_IMAGE = os.path.join(tempfile.gettempdir(), "corona_b200_reference_arm.npz")
+
+
+def downsample(img, k=PARITY_BLOCK):
+    h, w, c = img.shape
+    return img[:h // k * k, :w // k * k].astype(np.float64).reshape(h // k, k, w // k, k, c).mean(axis=(1, 3))
+
+
+def image_parity(gpu, ref_a, ref_b):
+    """bench-scene image parity: the GPU image against the reference renderer's image of the same scene, frame size and sample count
+    (rand point sampler: independent streams), with the reference's own seed-to-seed difference as the noise floor"""
+    g, a, b = downsample(gpu), downsample(ref_a), downsample(ref_b)
+    rel = lambda x, y: float(np.sqrt(((x - y) ** 2).mean()) / max(x.mean(), 1e-30))
+    floor = rel(a, b)
+    got = min(rel(a, g), rel(b, g))
+    both = 0.5 * (ref_a.astype(np.float64).mean(axis=(0, 1)) + ref_b.astype(np.float64).mean(axis=(0, 1)))
+    means = (gpu.astype(np.float64).mean(axis=(0, 1)) / both).tolist()
+    ok = bool(got <= 1.15 * floor and all(abs(m - 1) < 0.01 for m in means))
+    return {"ok": ok, "spp": PARITY_SPP, "block": PARITY_BLOCK, "rel_rmse_gpu_vs_reference": got, "rel_rmse_reference_seed_to_seed": floor,
+            "limit": "rel_rmse <= 1.15 x floor, channel means within 1 %", "channel_mean_ratio_gpu_over_reference": means,
+            "reference_channel_means": both.tolist(),
+            "what": f"{PARITY_SPP}-spp 4K images of the bench scene (ptdl, rand), {PARITY_BLOCK}x{PARITY_BLOCK} block means; reference = oracle/_ref/corona_ptdl_rand, "
+                    "--frame 1 and --frame 2"}
 
 
 def run_reference(args, rank, world):
@@ -190,6 +239,13 @@ def run_reference(args, rank, world):
     try:
         rpp = ref.rays_per_path()
         frames, build_s, _ = ref.run("corona_ptdl_rand", WIDTH, HEIGHT, args.warmup + args.steps)
+        img = ref.image()
+        # kept for the own arm, which the driver runs next on the same box: the image of these progressions, block-averaged
+        try:
+            np.savez(REF_ARM_IMAGE, image=downsample(img).astype(np.float32), spp=np.int64(args.warmup + args.steps),
+                     means=img.astype(np.float64).mean(axis=(0, 1)), tris=np.int64(scene.num_prims))
+        except OSError:
+            pass
     finally:
         ref.close()
     timed = frames[args.warmup:args.warmup + args.steps]
@@ -205,6 +261,7 @@ def run_reference(args, rank, world):
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": WORKLOAD, "num_tris": scene.num_prims, "frame": [WIDTH, HEIGHT], "sampler": "ptdl", "pointsampler": "rand"},
         "spp_per_s": len(timed) / dt, "paths_per_s": paths / dt, "rays_per_path": rpp,
+        "image_mean_xyz": [float(x) for x in img.astype(np.float64).mean(axis=(0, 1))], "image_spp": args.warmup + args.steps,
         "cpu_baseline": {"value": value, "unit": "rays/s", "cores": ref.cores, "kind": "reference", "sample": sample},
         "e2e": {"value": value, "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
@@ -214,15 +271,18 @@ def cpu_baseline(cb, scene, lines, shape_mats, cam):
     """bounded sample for the own arm's line: one 4K progression of the reference renderer (plus one warm-up)"""
     ref = ReferenceRenderer(cb, scene, lines, shape_mats, cam)
     try:
-        rpp = ref.rays_per_path()
-        frames, build_s, _ = ref.run("corona_ptdl_rand", WIDTH, HEIGHT, 2)
+        rpp, dbg = ref.rays_per_path(counters=True)
+        frames, build_s, _ = ref.run("corona_ptdl_rand", WIDTH, HEIGHT, PARITY_SPP, frame=1)
+        img_a = ref.image()
+        ref.run("corona_ptdl_rand", WIDTH, HEIGHT, PARITY_SPP, frame=2)
+        img_b = ref.image()
     finally:
         ref.close()
     dt = frames[-1]
     return {"value": WIDTH * HEIGHT * rpp / dt, "unit": "rays/s", "cores": ref.cores, "kind": "reference",
-            "spp_per_s": 1.0 / dt, "rays_per_path": rpp, "accel_build_s": build_s,
-            "sample": f"the second of two 4K progressions ({WIDTH * HEIGHT} paths) of oracle/_ref/corona_ptdl_rand on the same scene files, "
-                      f"{ref.cores} pinned threads; rays = paths x {rpp:.3f} (ACCEL_DEBUG build)"}
+            "spp_per_s": 1.0 / dt, "rays_per_path": rpp, "accel_build_s": build_s, "accel_debug": dbg,
+            "sample": f"the last of {PARITY_SPP} 4K progressions ({WIDTH * HEIGHT} paths each) of oracle/_ref/corona_ptdl_rand on the same scene files, "
+                      f"{ref.cores} pinned threads; rays = paths x {rpp:.3f} (ACCEL_DEBUG build)"}, img_a, img_b
 
 
 # ------------------------------------------------------------------------------------------------ own arm
@@ -336,6 +396,8 @@ def main():
     host_fb = torch.empty(HEIGHT, WIDTH, 3).pin_memory()
     e2e_steps = max(2, min(args.steps, 16))
     L = lib.load()
+    if world > 1 and rank == 0:
+        red.host_mirror = host_fb     # the root's running sum is copied to the host after every accumulate, on the reducer's side stream
 
     def e2e_step(s):
         if world == 1:           # == host/render_b200.c: render_b200_pass(r, first, count, fb)
@@ -343,8 +405,6 @@ def main():
             lib._check(L.cb200_render_snapshot_async(r.r, host_fb.data_ptr(), None), "cb200_render_snapshot_async")
         else:
             step(s)
-            if rank == 0:
-                host_fb.copy_(red.accum, non_blocking=True)
 
     def e2e_finish(s):           # == render_b200_finish(r, fb)
         if world == 1:
@@ -354,9 +414,7 @@ def main():
             r.set_framebuffer(red.acquire(s + 1).data_ptr())     # the last step's buffer is being reduced: stragglers go to the next one
             lib._check(L.cb200_render_flush(r.r, None), "cb200_render_flush")
             red.submit(s + 1)
-            total = red.finish()
-            if rank == 0:
-                host_fb.copy_(total)
+            red.finish()
     if world == 1:
         r.set_framebuffer(0)
     e2e_step(0)
@@ -385,6 +443,41 @@ def main():
                        "once at the end, inside the timing"}
     if world == 1:
         e2e["accel_h"] = accel_boundary(cb, lib, acc, scene, torch)
+    red.host_mirror = None
+
+    # ---- image-level checks, outside every timed region
+    multi_gpu_image = None
+    gpu_parity_img = None
+    if world > 1:
+        # the N-GPU image of progressions 0..N-1 (one per rank, reduced) against rank 0 rendering the same N progressions alone:
+        # every draw is a function of (frame, path index), so the two must agree up to fp32 summation order
+        r.clear()
+        red.clear()
+        r.set_framebuffer(red.acquire(0).data_ptr())
+        r.render_pass(rank * n_pass, n_pass, st)
+        red.submit(0)
+        total = red.finish()
+        torch.cuda.synchronize()
+        dist.barrier()
+        if rank == 0:
+            img_n = total.clone()
+            r.clear()
+            r.set_framebuffer(0)
+            for g in range(world):
+                r.render_pass(g * n_pass, n_pass, st)
+            img_1 = torch.from_numpy(r.framebuffer()).cuda()
+            d = (img_n - img_1).double()
+            scale = float(img_1.double().mean())
+            multi_gpu_image = {"progressions": world, "rel_rmse": float(d.pow(2).mean().sqrt()) / scale, "max_abs_diff_over_mean": float(d.abs().max()) / scale,
+                               "ok": bool(float(d.pow(2).mean().sqrt()) / scale < 1e-5),
+                               "what": f"sum over {world} ranks of progressions 0..{world - 1} vs the same progressions rendered by rank 0 alone"}
+        dist.barrier()
+    elif not args.no_cpu_baseline:
+        r.clear()
+        r.set_framebuffer(0)
+        for _ in range(PARITY_SPP):
+            r.render_pass(None, n_pass, st)
+        gpu_parity_img = r.image(spp=PARITY_SPP)
     r.close()
 
     if rank != 0:
@@ -412,19 +505,36 @@ def main():
         "grays_per_s_rank0": {"closest_hit": stt["rays_closest"] / (ms_closest * 1e-3) / 1e9, "shadow": stt["rays_shadow"] / max(ms_shadow * 1e-3, 1e-12) / 1e9},
         "roofline": {"bound": "hbm", "kernel": "k_intersect (closest-hit traversal, all launches of the timed region, rank 0)",
                      "achieved": achieved, "peak": hbm, "unit": "GB/s", "frac": achieved / hbm, "peak_source": which, "traffic": traffic,
-                     "traffic_note": f"DRAM bytes per ~8.3 M-ray launch from {traffic_src}: the ray and hit streams only -- nodes and primitives are "
-                                     "served by L1/L2, so HBM is not the binding roof (issue slots 72 %, L1 LSU data-pipe wavefronts 75 %)" if traffic else None,
+                     "binding_limit": "issue slots + L1 LSU wavefronts at ~15 of 32 lanes per instruction (ncu: " + NCU_SUMMARY + "), not HBM: "
+                                      "`bound`/`frac` follow SURVEY 8(d)'s algorithmic-byte definition (bytes a ray NEEDS from the tree / time), "
+                                      "`traffic` shows that almost all of them are served by L1/L2",
+                     "traffic_source": {"kind": "committed ncu --set full capture, not measured in this run", "file": traffic_src,
+                                        "command": NCU_COMMAND} if traffic else None,
+                     "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum per ~8.3 M-ray launch: the ray and hit streams only" if traffic else None,
                      "algorithmic_bytes_per_launch": bytes_per_ray * 8.3e6,
-                     "bytes_per_ray": bytes_per_ray, "nodes_per_ray": n_node, "prims_per_ray": n_prim,
+                     "bytes_per_ray": bytes_per_ray, "bytes_per_ray_formula": f"{n_node:.3f} nodes x {node_b} B + {n_prim:.3f} prims x {prim_b} B + 40 B ray + 24 B hit",
+                     "nodes_per_ray": n_node, "prims_per_ray": n_prim,
+                     "counters_definition": "ACCEL_DEBUG (qbvhmp.c:83-90): node tests with >= 1 child hit, primitive tests, per closest-hit ray; "
+                                            "counted by the instrumented kernel on one untimed progression of this workload",
                      "rays": stt["rays_closest"], "kernel_ms": ms_closest},
         "e2e": e2e,
         "gpu_launches": int(launches_all),
         "image_mean_xyz": image_mean,
         "clocks": clocks,
     }
+    if multi_gpu_image is not None:
+        out["multi_gpu_image_check"] = multi_gpu_image
     if world == 1 and not args.no_cpu_baseline:
         try:
-            out["cpu_baseline"] = cpu_baseline(cb, scene, lines, shape_mats, cam)
+            out["cpu_baseline"], ref_a, ref_b = cpu_baseline(cb, scene, lines, shape_mats, cam)
+            out["parity_vs_reference"] = image_parity(gpu_parity_img, ref_a, ref_b)
+            out["roofline"]["reference_tree"] = out["cpu_baseline"].pop("accel_debug")
+            if os.path.exists(REF_ARM_IMAGE):      # left by `bench.py --impl reference` on this box: its image at its own sample count
+                z = np.load(REF_ARM_IMAGE)
+                if int(z["tris"]) == scene.num_prims:
+                    out["parity_vs_reference"]["reference_arm"] = {
+                        "spp": int(z["spp"]), "channel_mean_ratio_gpu_over_reference_arm": (np.array(image_mean) / z["means"]).tolist(),
+                        "what": f"channel means of the {args.steps}-spp image of the timed region over those of the reference arm's {int(z['spp'])}-spp image"}
         except Exception as e:   # reference not built on this box: say so instead of inventing a number
             out["cpu_baseline"] = {"value": None, "unit": "rays/s", "cores": os.cpu_count(), "kind": "reference", "sample": f"unavailable: {e}"}
     print(json.dumps(out))

@@ -1496,7 +1496,9 @@ cb200_render_t *cb200_render_create(cb200_accel_t *a, const cb_render_desc_t *de
   D.cam.fstop = k_fstop[desc->camera.aperture_value];
   D.cam.exposure_time = k_exposure[desc->camera.exposure_value];
   D.points.mode = desc->pointsampler;
-  D.points.key = (desc->frame + 1)*0x9e3779b97f4a7c15ull ^ ((uint64_t)desc->rank << 32);
+  // the key carries the frame only: path indices are unique across the ranks of a sample-split job, so every draw is a function of
+  // (frame, path index, dimension) and an N-GPU image equals the 1-GPU image of the same progressions up to fp32 summation order
+  D.points.key = (desc->frame + 1)*0x9e3779b97f4a7c15ull;
   bool ok = true;
   // materials and tables
   std::vector<TableDev> tabs(desc->num_tables > 0 ? desc->num_tables : 1);

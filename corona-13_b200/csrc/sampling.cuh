@@ -9,7 +9,7 @@
 //   points_rand              src/points.d/sfmt.c:436 -- per-thread SFMT-19937 in the reference.  Its streams depend
 //                            on which worker thread picks which path ("RNG reproducibility"),
 //                            so only its distribution can be matched: here a counter-based generator keyed by
-//                            (frame, rank, path index, draw counter).
+//                            (frame, path index, draw counter) -- independent of which GPU or wave traces the path.
 #pragma once
 #include <stdint.h>
 
@@ -63,7 +63,7 @@ struct PointsDev
 {
   HaltonDev halton;
   int32_t mode;        // CB_POINTS_RAND / CB_POINTS_HALTON
-  uint64_t key;        // frame / rank mix for the counter generator
+  uint64_t key;        // frame mix for the counter generator
 };
 
 // pointsampler(): `dim` is already rand_beg + i.  stream 0 = dimensions, stream 1 = points_rand draws

@@ -17,31 +17,38 @@ def progression_range(step, rank, world, paths_per_progression):
 
 
 class FramebufferReducer:
-    """owns the per-rank accumulation buffers (H x W x 3 float32) and the root's running sum"""
+    """owns the per-rank accumulation buffers (H x W x 3 float32) and the root's running sum.
 
-    def __init__(self, height, width, device, rank=0, world=1, dist=None, nbuf=2):
+    On CUDA everything that follows a progression -- the reduce to rank 0, the root's accumulate, clearing the buffer for its
+    next use and (optionally) mirroring the root's running sum into pinned HOST memory -- is queued on ONE side stream in that
+    order; the render stream only waits for the event that marks its next buffer as cleared.  Nothing of it runs on the render
+    stream or blocks the host, so a progression's epilogue overlaps the next progression's kernels."""
+
+    def __init__(self, height, width, device, rank=0, world=1, dist=None, nbuf=2, host_mirror=None):
         self.rank, self.world, self.dist = rank, world, dist
         self.cuda = torch.device(device).type == "cuda"
         n = nbuf if world > 1 else 1
         self.bufs = [torch.zeros(height, width, 3, device=device) for _ in range(n)]
         self.accum = torch.zeros(height, width, 3, device=device) if (world > 1 and rank == 0) else None
-        self.pending = [None] * n
+        self.pending = [None] * n        # CPU path: the async work handle; CUDA path: the event after the buffer was cleared
         self.comm = torch.cuda.Stream() if (self.cuda and world > 1) else None
+        self.host_mirror = host_mirror   # pinned (H, W, 3) float32 tensor on rank 0 or None
         self.submitted = 0
 
     def _retire(self, k):
         if self.pending[k] is None:
             return
-        self.pending[k].wait()
-        if self.comm is not None:
-            torch.cuda.current_stream().wait_stream(self.comm)
-        if self.accum is not None:
-            self.accum.add_(self.bufs[k])
-        self.bufs[k].zero_()
+        if self.comm is not None:        # CUDA: the side stream has done (or will do) the work; order the render stream behind it
+            torch.cuda.current_stream().wait_event(self.pending[k])
+        else:
+            self.pending[k].wait()
+            if self.accum is not None:
+                self.accum.add_(self.bufs[k])
+            self.bufs[k].zero_()
         self.pending[k] = None
 
     def acquire(self, step):
-        """the buffer to render local step `step` into (waits for the reduce that last used it)"""
+        """the buffer to render local step `step` into (ordered behind the reduce that last used it)"""
         k = step % len(self.bufs)
         self._retire(k)
         return self.bufs[k]
@@ -49,12 +56,22 @@ class FramebufferReducer:
     def submit(self, step):
         """the buffer of local step `step` is complete on the current stream: start summing it into rank 0"""
         if self.world == 1:
+            if self.host_mirror is not None:
+                self.host_mirror.copy_(self.bufs[0], non_blocking=True)
             return
         k = step % len(self.bufs)
         if self.comm is not None:
             self.comm.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(self.comm):
-                self.pending[k] = self.dist.reduce(self.bufs[k], 0, async_op=True)
+                self.dist.reduce(self.bufs[k], 0, async_op=True).wait()     # stream-level wait: the host does not block
+                if self.accum is not None:
+                    self.accum.add_(self.bufs[k])
+                    if self.host_mirror is not None:
+                        self.host_mirror.copy_(self.accum, non_blocking=True)
+                self.bufs[k].zero_()
+                ev = torch.cuda.Event()
+                ev.record(self.comm)
+                self.pending[k] = ev
         else:
             self.pending[k] = self.dist.reduce(self.bufs[k], 0, async_op=True)
         self.submitted += 1

@@ -135,7 +135,8 @@ typedef struct cb_render_desc_t
   int32_t colour_camera;         /* CB_COLOUR_* */
   int32_t max_path_len;          /* ptdl: rt.sampler->max_path_len, <= 32 (PATHSPACE_MAX_VERTS) */
   uint64_t frame;                /* rt.anim_frame: seeds the Halton permutations / the counter RNG */
-  uint32_t rank, world;          /* sample-space split: decorrelates the counter RNG streams across GPUs */
+  uint32_t rank, world;          /* sample-space split (informational): every random draw is a function of (frame, path index,
+                                    dimension) only, so ranks that render disjoint index ranges sum to the single-GPU image */
   uint64_t batch_paths;          /* paths in flight per wave (0 = default) */
   int32_t sky;                   /* CB_SKY_* */
   float sky_coeff[3];            /* CB_SKY_CONST: rgb2spec coefficients of the colour and scale * mul (sky_const.c:89-101) */
