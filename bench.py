@@ -130,7 +130,7 @@ class ClockSampler(threading.Thread):
 def bench_scene(cb, tris):
     """scene, flattened materials, camera: identical for both arms"""
     IO, S = cb.scene_io, cb.scenes
-    z = np.load(os.path.join(ROOT, "tests", "golden", "bench_materials.npz"))
+    z = np.load(os.path.join(ROOT, "corona-13_b200", "data", "bench_materials.npz"))
     ms = IO.MaterialSet()
     raw = z["materials"].tobytes()
     ms.materials = list((IO.CMaterial * (len(raw) // C.sizeof(IO.CMaterial))).from_buffer_copy(raw))

@@ -282,6 +282,7 @@ int prims_add_shape_mem(prims_t *p, const cb_shape_t *sh)
 void prims_allocate_index(prims_t *p)
 { /* prims.c:741-757 */
   p->primid = (uint64_t *)malloc(sizeof(uint64_t)*(p->num_prims ? p->num_prims : 1));
+  if(!p->primid) { fprintf(stderr, "[prims] out of memory for %lu primitive ids\n", (unsigned long)p->num_prims); p->num_prims = 0; return; }
   uint64_t n = 0;
   for(uint32_t shapeid=0;shapeid<p->num_shapes;shapeid++)
     for(uint64_t k=0;k<p->shape[shapeid].num_prims;k++)

@@ -99,10 +99,15 @@ uint64_t render_b200_overlays(const struct render_t *r);
 int render_b200_set_dbor(struct render_t *r, int levels);
 int render_b200_dbor(struct render_t *r, int level, float *fb);
 void *render_b200_handle(const struct render_t *r);
+int render_b200_dbor_is_set(struct render_t *r, int set);   /* bookkeeping for the view: has set_dbor been called (and mark it) */
 
 /* ---- scene ingestion (host/scene_b200.c): .nra2 shader + shape lists, .cam, rgb2spec coefficients, measured tables ---- */
 struct scene_b200_t;
 struct scene_b200_t *scene_b200_open(const char *nra2_file, const char *coeff_file, const char *table_file);   /* no GPU needed */
+/* the sky line and the shader list only (no shapes are loaded): for hosts that own the geometry themselves, like the in-tree render module */
+struct scene_b200_t *scene_b200_open_shaders(const char *nra2_file, const char *coeff_file, const char *table_file);
+/* materials, measured tables, media and sky of s into d (pointers borrowed from s: keep s alive while d is in use) */
+void scene_b200_fill_desc(const struct scene_b200_t *s, cb_render_desc_t *d);
 void scene_b200_free(struct scene_b200_t *s);
 const cb_material_t *scene_b200_materials(const struct scene_b200_t *s, int *num);
 /* the homogeneous media the shader list defines (cb_material_t.medium / *exterior are 1 + index, 0 = vacuum) */

@@ -32,7 +32,8 @@ static rgb2spec_b200_t *rgb2spec_b200_load(const char *filename)
   if(!f) return 0;
   char header[4];
   rgb2spec_b200_t *m = (rgb2spec_b200_t *)calloc(1, sizeof(*m));
-  if(fread(header, 4, 1, f) != 1 || memcmp(header, "SPEC", 4) || fread(&m->res, 4, 1, f) != 1) { fclose(f); free(m); return 0; }
+  if(fread(header, 4, 1, f) != 1 || memcmp(header, "SPEC", 4) || fread(&m->res, 4, 1, f) != 1 || m->res < 2 || m->res > 256)
+  { fclose(f); free(m); return 0; }   /* the fetch interpolates between res-2 cells; a wild res would overflow the table size */
   const size_t ns = m->res, nd = (size_t)m->res*m->res*m->res*3*3;
   m->scale = (float *)malloc(sizeof(float)*ns);
   m->data = (float *)malloc(sizeof(float)*nd);
@@ -143,6 +144,7 @@ typedef struct nra2_t
   int medium_of[MAX_SHADERS];
   int num_media;
   int exterior_medium;
+  int flatten_calls;          /* budget of flatten() per material */
 }
 nra2_t;
 
@@ -169,7 +171,8 @@ static int parse_slot(char c)
  * returns 0, or 1 when the shader is outside the pt/ptdl surface path */
 static int flatten(nra2_t *n, int k, cb_material_t *m, int *have_bsdf, int depth)
 {
-  if(k < 0 || k >= n->num_shaders || depth > 16) return 1;
+  /* calls are budgeted per material: a list of `mult 16 -1 ... -1` lines would otherwise fan out 16^depth times */
+  if(k < 0 || k >= n->num_shaders || depth > 16 || ++n->flatten_calls > 4096) return 1;
   const shader_line_t *l = n->line + k;
   if(!strcmp(l->name, "diffuse")) { m->bsdf = CB_BSDF_DIFFUSE; *have_bsdf = 1; return 0; }
   if(!strcmp(l->name, "color"))
@@ -230,8 +233,16 @@ static int flatten(nra2_t *n, int k, cb_material_t *m, int *have_bsdf, int depth
       if(sscanf(l->args + pos, " %d%n", idx + i, &adv) < 1) return 1;
       pos += adv;
       if(idx[i] < 0) idx[i] += k;
+      if(idx[i] < 0 || idx[i] >= k) return 1;   /* upstream resolves references against the shaders loaded so far (mult.c:103-120): earlier lines only */
     }
-    for(int i=0;i<cnt;i++) { int hb = 0; if(flatten(n, idx[i], m, &hb, depth+1)) return 1; }
+    for(int i=0;i<cnt;i++)
+    { /* pre slots only run prepare(): a BSDF-type shader there contributes no callbacks upstream, so it is refused here rather than
+       * allowed to overwrite the host's */
+      int hb = 0;
+      const int bsdf0 = m->bsdf;
+      if(flatten(n, idx[i], m, &hb, depth+1) || hb) return 1;
+      m->bsdf = bsdf0;
+    }
     return flatten(n, idx[cnt], m, have_bsdf, depth+1);
   }
   return 1;   /* skies, hair, heterogeneous media, ...: SURVEY 2.1 marks them outside the hot path */
@@ -407,6 +418,7 @@ static int envmap_open(struct scene_b200_t *s, const char *args)
   fseek(f, 0, SEEK_SET);
   fb_header_b200_t h;
   if(size < (long)sizeof(h) || fread(&h, sizeof(h), 1, f) != 1 || h.magic != 1936686951lu || h.channels != 4 ||
+     h.width < 2 || h.width > (1u << 16) || h.height < 1 || h.height > (1u << 15) ||     /* bounded before multiplying: no uint64 wrap */
      (long)(h.width*h.height*4*sizeof(float) + sizeof(h)) != size || h.width != 2*h.height) { fclose(f); return 1; }
   s->env_size = (size_t)size - sizeof(h);
   s->env_map = malloc(s->env_size);
@@ -446,12 +458,24 @@ void scene_b200_free(struct scene_b200_t *s)
 
 /* parse the shader list of `nra2` into materials (no GPU needed).  coeff_file: data/ergb2spec.coeff; table_file may be NULL
  * when no shader needs measured data */
+static struct scene_b200_t *scene_open(const char *nra2_file, const char *coeff_file, const char *table_file, int load_shapes);
 struct scene_b200_t *scene_b200_open(const char *nra2_file, const char *coeff_file, const char *table_file)
+{
+  return scene_open(nra2_file, coeff_file, table_file, 1);
+}
+/* sky line + shader list only: what the in-tree render module needs beside the geometry the reference has loaded itself */
+struct scene_b200_t *scene_b200_open_shaders(const char *nra2_file, const char *coeff_file, const char *table_file)
+{
+  return scene_open(nra2_file, coeff_file, table_file, 0);
+}
+
+static struct scene_b200_t *scene_open(const char *nra2_file, const char *coeff_file, const char *table_file, int load_shapes)
 {
   FILE *f = fopen(nra2_file, "rb");
   if(!f) { fprintf(stderr, "[scene b200] can't open %s for reading!\n", nra2_file); return 0; }
   struct scene_b200_t *s = calloc(1, sizeof(*s));
-  s->nra2 = calloc(1, sizeof(nra2_t));
+  if(s) s->nra2 = calloc(1, sizeof(nra2_t));
+  if(!s || !s->nra2) { fprintf(stderr, "[scene b200] out of memory\n"); fclose(f); free(s); return 0; }
   snprintf(s->searchpath, sizeof(s->searchpath), "%s", nra2_file);
   char *c = s->searchpath + strlen(s->searchpath);
   for(;*c != '/' && c != s->searchpath;c--);
@@ -535,21 +559,25 @@ struct scene_b200_t *scene_b200_open(const char *nra2_file, const char *coeff_fi
         if(inner < 0) inner += k;
         medium = flatten_medium(s->nra2, inner);
       }
+      s->nra2->flatten_calls = 0;
       if(!medium || flatten(s->nra2, surf, m, &have_bsdf, 0)) { memset(m, 0, sizeof(*m)); m->num_ops = -1; m->bsdf = -1; continue; }
       if(!have_bsdf) m->bsdf = CB_BSDF_DIFFUSE;
       m->medium = medium;
       continue;
     }
+    s->nra2->flatten_calls = 0;
     if(flatten(s->nra2, k, m, &have_bsdf, 0)) { memset(m, 0, sizeof(*m)); m->num_ops = -1; m->bsdf = -1; continue; }
     if(!have_bsdf) m->bsdf = CB_BSDF_DIFFUSE;   /* a prepare-only shader on a shape gets the default diffuse callbacks (shader.c:761-787) */
   }
 
+  if(!load_shapes) { fclose(f); return s; }
   /* shapes: common_load_scene, src/corona_common.c:30-68 */
   int num_shapes = 0;
-  if(!fgets(line, sizeof(line), f) || sscanf(line, "%d", &num_shapes) != 1)
+  if(!fgets(line, sizeof(line), f) || sscanf(line, "%d", &num_shapes) != 1 || num_shapes < 0 || num_shapes > (1 << 24))
   { fprintf(stderr, "[common_load_scene] corrupt model file: could not read number of shapes!\n"); fclose(f); scene_b200_free(s); return 0; }
   prims_init(&s->prims);
   prims_allocate(&s->prims, num_shapes);
+  if(!s->prims.shape) { fprintf(stderr, "[common_load_scene] out of memory for %d shapes\n", num_shapes); fclose(f); scene_b200_free(s); return 0; }
   for(int shape=0;shape<num_shapes;shape++)
   {
     if(!fgets(line, sizeof(line), f)) break;
@@ -575,6 +603,18 @@ const cb_medium_t *scene_b200_media(const struct scene_b200_t *s, int *num, int 
 const char *scene_b200_basename(const struct scene_b200_t *s) { return s->basename; }
 uint64_t scene_b200_num_prims(const struct scene_b200_t *s) { return s->prims.num_prims; }
 
+/* the shader-list half of a render description: materials, measured tables, media, sky (borrowed pointers into s) */
+void scene_b200_fill_desc(const struct scene_b200_t *s, cb_render_desc_t *d)
+{
+  d->materials = s->materials; d->num_materials = s->nra2->num_shaders;
+  d->tables = s->nra2->used; d->num_tables = s->nra2->num_used;
+  d->sky = s->sky;
+  for(int k=0;k<3;k++) d->sky_coeff[k] = s->sky_coeff[k];
+  d->sky_scale = s->sky_scale;
+  d->envmap = s->sky == CB_SKY_ENVMAP ? &s->envmap : 0;
+  d->media = s->nra2->media; d->num_media = s->nra2->num_media; d->exterior_medium = s->nra2->exterior_medium;
+}
+
 /* accel_init + accel_build + camera + render_b200_init: everything main.c's init() does for the hot path (src/main.c:250-359) */
 int scene_b200_prepare(struct scene_b200_t *s, uint32_t width, uint32_t height, int sampler, int pointsampler, int colour, uint64_t frame,
                        const char *cam_file)
@@ -599,14 +639,8 @@ int scene_b200_prepare(struct scene_b200_t *s, uint32_t width, uint32_t height, 
   memset(d, 0, sizeof(*d));
   if(scene_b200_read_camera(cam, width, height, &d->camera)) { fprintf(stderr, "[scene b200] could not read camera `%s'\n", cam); return 1; }
   d->width = width; d->height = height;
-  d->materials = s->materials; d->num_materials = s->nra2->num_shaders;
-  d->tables = s->nra2->used; d->num_tables = s->nra2->num_used;
+  scene_b200_fill_desc(s, d);
   d->sampler = sampler; d->pointsampler = pointsampler; d->colour_camera = colour;
-  d->sky = s->sky;
-  for(int k=0;k<3;k++) d->sky_coeff[k] = s->sky_coeff[k];
-  d->sky_scale = s->sky_scale;
-  d->envmap = s->sky == CB_SKY_ENVMAP ? &s->envmap : 0;
-  d->media = s->nra2->media; d->num_media = s->nra2->num_media; d->exterior_medium = s->nra2->exterior_medium;
   d->max_path_len = 32; d->frame = frame; d->rank = 0; d->world = 1; d->batch_paths = 0;
   s->render = render_b200_init(s->accel, d);
   clock_gettime(CLOCK_MONOTONIC, &ts0);

@@ -17,7 +17,7 @@ for case, sampler in RUNS:
     t0 = time.time()
     p = subprocess.run([os.path.join(ROOT, "corona-13_b200", "corona_b200"), nra2, "-s", str(SPP), "-w", str(W), "-h", str(H), "--frame", "1", "--batch", "16",
                         "--sampler", sampler, "--points", "rand", "--coeff", os.path.join(REF, "data", "ergb2spec.coeff"),
-                        "--tables", os.path.join(ROOT, "tests", "golden", "ref_tables.cbt")], capture_output=True, text=True)
+                        "--tables", os.path.join(ROOT, "corona-13_b200", "data", "ref_tables.cbt")], capture_output=True, text=True)
     gpu_wall = time.time() - t0
     gpu_frame = float(re.findall(r"average of ([0-9.]+) s/frame", p.stdout)[0])
     cores = os.cpu_count()

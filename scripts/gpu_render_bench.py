@@ -8,7 +8,7 @@ lib = importlib.import_module("corona-13_b200.lib")
 IO, S = cb.scene_io, cb.scenes
 import ctypes as C
 tris = int(sys.argv[1]) if len(sys.argv) > 1 else 10_000_000
-z = np.load(os.path.join(ROOT, "tests/golden/bench_materials.npz"))
+z = np.load(os.path.join(ROOT, "corona-13_b200/data/bench_materials.npz"))
 ms = IO.MaterialSet()
 raw = z["materials"].tobytes()
 arr = (IO.CMaterial * (len(raw)//C.sizeof(IO.CMaterial))).from_buffer_copy(raw)

@@ -1,6 +1,6 @@
 """Material table of bench.py's synthetic 10 M-triangle config (terrain + icosphere soup + quad light):
 the shader list below flattened through the reference's rgb -> spectrum coefficient table (which only exists where
-oracle/_ref was built), stored so that bench.py runs anywhere.   python tests/golden/make_bench_materials.py"""
+oracle/_ref was built), stored so that bench.py runs anywhere.   python scripts/make_bench_materials.py"""
 import importlib
 import os
 import sys
@@ -9,7 +9,7 @@ import tempfile
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-ROOT = os.path.dirname(os.path.dirname(HERE))
+ROOT = os.path.dirname(HERE)
 sys.path.insert(0, ROOT)
 IO = importlib.import_module("corona-13_b200").scene_io
 
@@ -29,6 +29,6 @@ if __name__ == "__main__":
     IO.write_nra2(nra2, LINES, [(m, f"shape{i}") for i, m in enumerate(SHAPE_MATS)])
     ms, _, _ = IO.parse_nra2(nra2, IO.Rgb2Spec(IO.coeff_path(ROOT)))
     mats, _ = ms.carrays()
-    np.savez_compressed(os.path.join(HERE, "bench_materials.npz"), materials=np.frombuffer(bytes(mats), np.uint8),
+    np.savez_compressed(os.path.join(ROOT, "corona-13_b200", "data", "bench_materials.npz"), materials=np.frombuffer(bytes(mats), np.uint8),
                         shader_lines=np.array(LINES), shape_mats=np.int64(SHAPE_MATS))
     print("wrote bench_materials.npz", len(ms.materials), "materials")

@@ -37,7 +37,8 @@ def main():
     np.savez_compressed(path, **out)
     # the same tables for the C host layer (host/scene_b200.c: tables_load): "CBT1", count, {name[32], rows, cols, lambda_min, lambda_step, data}
     import struct
-    with open(os.path.join(HERE, "ref_tables.cbt"), "wb") as f:
+    cbt = os.path.join(os.path.dirname(os.path.dirname(HERE)), "corona-13_b200", "data", "ref_tables.cbt")   # product data: beside the library
+    with open(cbt, "wb") as f:
         f.write(b"CBT1" + struct.pack("<I", len(out)))
         for k, v in out.items():
             lmin, step = (380.0, 10.0) if k == "checker" else (360.0, 5.0)

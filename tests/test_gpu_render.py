@@ -426,7 +426,7 @@ def test_full_size_render_properties(gpu):
     (4) energy: every splat is finite and the image mean is the same for two disjoint index ranges within Monte Carlo noise."""
     import ctypes as C
     IO = cb.scene_io
-    z = np.load(os.path.join(GOLDEN, "bench_materials.npz"))
+    z = np.load(os.path.join(os.path.dirname(GOLDEN), "..", "corona-13_b200", "data", "bench_materials.npz"))
     ms = IO.MaterialSet()
     raw = z["materials"].tobytes()
     ms.materials = list((IO.CMaterial * (len(raw) // C.sizeof(IO.CMaterial))).from_buffer_copy(raw))

@@ -14,7 +14,7 @@ from helpers import GoldenImage
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 PKG = os.path.join(ROOT, "corona-13_b200")
 COEFF = os.path.join(ROOT, "oracle", "_ref", "data", "ergb2spec.coeff")
-TABLES = os.path.join(ROOT, "tests", "golden", "ref_tables.cbt")
+TABLES = os.path.join(ROOT, "corona-13_b200", "data", "ref_tables.cbt")
 
 pytestmark = pytest.mark.skipif(not os.path.exists(COEFF), reason="data/ergb2spec.coeff only exists where oracle/_ref was built")
 
