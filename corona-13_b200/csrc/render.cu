@@ -1171,7 +1171,8 @@ struct cb200_render
 {
   cb200_accel *accel;
   RenderDev dev;
-  cb_render_desc_t desc;
+  cb_render_desc_t desc;         // scalars only after create: the caller's arrays are not kept
+  std::vector<char> mat_ok;      // material i describes a surface the path supports (cb200_render_bsdf)
   uint64_t batch;
   // owned device memory
   std::vector<void *> owned;
@@ -1473,7 +1474,9 @@ cb200_render_t *cb200_render_create(cb200_accel_t *a, const cb_render_desc_t *de
   { cb200_set_error("render_create: unknown sampler (pt, ptdl and ptnee exist on the gpu; no CPU fallback)"); return nullptr; }
   cb200_render *r = new cb200_render();
   r->accel = a;
-  r->desc = *desc;
+  r->desc = *desc;   // the arrays behind its pointers are the caller's and only read inside this function (copied to the device below)
+  r->mat_ok.assign(desc->num_materials > 0 ? desc->num_materials : 0, 0);
+  for(int i=0;i<desc->num_materials;i++) r->mat_ok[i] = desc->materials[i].num_ops >= 0;
   memset(&r->stats, 0, sizeof(r->stats));
   r->h_cnt = nullptr;
   r->timing = r->counting = 0; r->ev_used = 0; r->d_trav_cnt = nullptr;
@@ -1557,6 +1560,7 @@ cb200_render_t *cb200_render_create(cb200_accel_t *a, const cb_render_desc_t *de
   }
   cudaMemset(D.fb, 0, (size_t)desc->width*desc->height*3*sizeof(float));
   cudaMemset(r->d_cnt, 0, sizeof(ShadeCounters));
+  r->desc.materials = nullptr; r->desc.tables = nullptr; r->desc.media = nullptr; r->desc.envmap = nullptr;   // borrowed: the caller may free them now
   return r;
 }
 
@@ -1836,7 +1840,7 @@ int cb200_render_point(cb200_render_t *r, const uint64_t *index, const int32_t *
 
 int cb200_render_bsdf(cb200_render_t *r, int32_t material, const cb_bsdf_query_t *queries, cb_bsdf_result_t *results, uint64_t n)
 {
-  if(!r || !queries || !results || material < 0 || material >= r->desc.num_materials || r->desc.materials[material].num_ops < 0)
+  if(!r || !queries || !results || material < 0 || material >= r->desc.num_materials || !r->mat_ok[material])
   { cb200_set_error("render_bsdf: bad arguments"); return CB200_ERR_ARG; }
   cb_bsdf_query_t *d_q = nullptr; cb_bsdf_result_t *d_o = nullptr;
   CB_CUDA(cudaMalloc(&d_q, (n + 1)*sizeof(cb_bsdf_query_t))); CB_CUDA(cudaMalloc(&d_o, (n + 1)*sizeof(cb_bsdf_result_t)));

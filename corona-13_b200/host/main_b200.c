@@ -2,7 +2,7 @@
  *
  *   corona_b200 <scene.nra2> [-s spp] [-w width] [-h height] [--frame n] [-x [name]] [-c camfile] [--batch n]
  *               [--sampler pt|ptdl|ptnee] [--points rand|halton] [--colour xyz|rec709] [--coeff file] [--tables file]
- *               [--dump-materials file] [--dbor n] [-q]
+ *               [--dump-materials file] [--dbor n] [--gpus n] [-q]
  *
  * Same arguments and defaults as the reference binary where they exist there (src/main.c:250-282,415-437,
  * src/view.c:262-297, src/display.d/null.c:47-56): -s samples per pixel then write the image and quit, -w/-h frame size
@@ -11,6 +11,11 @@
  * reference's compile-time MOD_sampler / MOD_pointsampler / COL_camera.  Writes <basename><name>_fb00.pfm like
  * view_write_images (src/view.c:549); --dbor n (src/view.c:291) adds the outlier rejection cascade of view_splat_col and its
  * <basename><name>_dbor%02d.pfm files (view.c:553-556).  Without a CUDA device it refuses: there is no CPU path in this binary.
+ *
+ * --gpus n: the samples per pixel are split over n GPUs of the box, one process per GPU (forked before any device
+ * work; this process is rank 0).  Rank g renders the progression groups g, g+n, ... -- the same path-index ranges a 1-GPU run
+ * uses, so the image is the 1-GPU image up to fp32 summation order -- and every group ends with one NCCL reduce of the
+ * framebuffer to rank 0 (cb200_reducer_*), overlapped with the next group.  Rank 0 writes the image.
  */
 #include "corona_host.h"
 #include "corona_b200.h"
@@ -19,6 +24,8 @@
 #include <stdlib.h>
 #include <string.h>
 #include <time.h>
+#include <unistd.h>
+#include <sys/wait.h>
 
 static double now(void) { struct timespec t; clock_gettime(CLOCK_MONOTONIC, &t); return t.tv_sec + 1e-9*t.tv_nsec; }
 
@@ -34,7 +41,7 @@ int main(int argc, char *argv[])
   char outname[256] = "render";
   uint64_t spp = 0, frame = 1, batch = 0;
   uint32_t width = 1024, height = 576;       /* src/view.c:261-262 */
-  int sampler = CB_SAMPLER_PTDL, points = CB_POINTS_RAND, colour = CB_COLOUR_XYZ, quiet = 0, dbor = 0;
+  int sampler = CB_SAMPLER_PTDL, points = CB_POINTS_RAND, colour = CB_COLOUR_XYZ, quiet = 0, dbor = 0, gpus = 1;
   for(int i=2;i<argc;i++)
   {
     if     (!strcmp(argv[i], "-s") && i+1 < argc) spp = strtoull(argv[++i], 0, 10);
@@ -51,9 +58,28 @@ int main(int argc, char *argv[])
     else if(!strcmp(argv[i], "--tables") && i+1 < argc) tables = argv[++i];
     else if(!strcmp(argv[i], "--dump-materials") && i+1 < argc) dump = argv[++i];
     else if(!strcmp(argv[i], "--dbor") && i+1 < argc) { dbor = atoi(argv[++i]); dbor = dbor < 0 ? 0 : dbor > 20 ? 20 : dbor; }   /* view.c:291 */
+    else if(!strcmp(argv[i], "--gpus") && i+1 < argc) { gpus = atoi(argv[++i]); gpus = gpus < 1 ? 1 : gpus > 64 ? 64 : gpus; }
     else if(!strcmp(argv[i], "-q")) quiet = 1;
     else if((!strcmp(argv[i], "-t") || !strcmp(argv[i], "-b") || !strcmp(argv[i], "-o")) && i+1 < argc) ++i;   /* cpu threads / backups / timeout: n/a */
   }
+  /* ---- multi-GPU: fork the other ranks before anything touches the device; the communicator id travels through a pipe */
+  int rank = 0, idpipe[2] = {-1, -1};
+  pid_t kids[64];
+  if(gpus > 1 && spp && !dump)
+  {
+    if(dbor > 1) { fprintf(stderr, "[main] --dbor with --gpus > 1 is not supported\n"); return 1; }
+    if(pipe(idpipe)) { perror("[main] pipe"); return 1; }
+    fflush(stdout); fflush(stderr);
+    for(int g=1;g<gpus;g++)
+    {
+      const pid_t pid = fork();
+      if(pid < 0) { perror("[main] fork"); return 1; }
+      if(pid == 0) { rank = g; quiet = 1; break; }
+      kids[g] = pid;
+    }
+    if(cb200_set_device(rank)) { fprintf(stderr, "[main] rank %d: %s\n", rank, cb200_last_error()); return 2; }
+  }
+  else gpus = 1;
   const double t_open = now();
   struct scene_b200_t *s = scene_b200_open(scene, coeff, tables);
   if(!s) { fprintf(stderr, "[main] could not load nra2 file!\n"); return 2; }
@@ -94,14 +120,54 @@ int main(int argc, char *argv[])
   struct render_t *r = scene_b200_render(s);
   if(dbor > 1 && render_b200_set_dbor(r, dbor)) { free(fb); scene_b200_free(s); return 3; }
   t0 = now();
-  uint64_t done = 0;
-  while(done < spp)
-  { /* run(): view_render() per progression (src/main.c:388-412, src/view.c:630-645) */
-    const uint64_t n = (spp - done) < batch ? (spp - done) : batch;
-    if(render_b200_pass(r, done*per_frame, n*per_frame, 0)) { free(fb); scene_b200_free(s); return 3; }
-    done += n;
+  if(gpus > 1)
+  { /* groups of `batch` progressions, group b rendered by rank b % gpus; every rank runs the same number of rounds (the reduce is
+     * a collective) plus one for the paths still in flight at the end */
+    char id[CB200_COMM_ID_BYTES];
+    if(rank == 0)
+    {
+      if(cb200_comm_unique_id(id)) { fprintf(stderr, "[main] %s\n", cb200_last_error()); return 3; }
+      for(int g=1;g<gpus;g++) if(write(idpipe[1], id, sizeof(id)) != (ssize_t)sizeof(id)) { perror("[main] write"); return 3; }
+    }
+    else if(read(idpipe[0], id, sizeof(id)) != (ssize_t)sizeof(id)) { fprintf(stderr, "[main] rank %d: no communicator id\n", rank); return 3; }
+    cb200_render_t *dev = (cb200_render_t *)render_b200_handle(r);
+    cb200_reducer_t *q = cb200_reducer_create(dev, id, rank, gpus, d->width, d->height);
+    if(!q) { fprintf(stderr, "[main] rank %d: %s\n", rank, cb200_last_error()); return 3; }
+    const uint64_t groups = (spp + batch - 1)/batch, rounds = (groups + gpus - 1)/gpus;
+    int rc = 0;
+    for(uint64_t k=0;k<rounds && !rc;k++)
+    {
+      const uint64_t b = k*gpus + rank;
+      rc = cb200_reducer_begin(q, k, 0);
+      if(!rc && b < groups)
+      {
+        const uint64_t first = b*batch, n = (spp - first) < batch ? (spp - first) : batch;
+        rc = render_b200_pass(r, first*per_frame, n*per_frame, 0);
+      }
+      if(!rc) rc = cb200_reducer_end(q, k, 0, 0);
+    }
+    if(!rc) rc = cb200_reducer_begin(q, rounds, 0);
+    if(!rc) rc = cb200_render_flush(dev, 0);
+    if(!rc) rc = cb200_reducer_end(q, rounds, 0, 0);
+    if(!rc) rc = cb200_reducer_finish(q, rank == 0 ? fb : 0);
+    if(rc) fprintf(stderr, "[main] rank %d: %s\n", rank, cb200_last_error());
+    cb200_reducer_destroy(q);
+    if(rank != 0) { free(fb); scene_b200_free(s); return rc ? 3 : 0; }
+    int failed = rc;
+    for(int g=1;g<gpus;g++) { int st = 0; if(waitpid(kids[g], &st, 0) < 0 || !WIFEXITED(st) || WEXITSTATUS(st)) failed = 1; }
+    if(failed) { fprintf(stderr, "[main] a rank failed\n"); free(fb); scene_b200_free(s); return 3; }
   }
-  if(render_b200_finish(r, fb)) { free(fb); scene_b200_free(s); return 3; }
+  else
+  {
+    uint64_t done = 0;
+    while(done < spp)
+    { /* run(): view_render() per progression (src/main.c:388-412, src/view.c:630-645) */
+      const uint64_t n = (spp - done) < batch ? (spp - done) : batch;
+      if(render_b200_pass(r, done*per_frame, n*per_frame, 0)) { free(fb); scene_b200_free(s); return 3; }
+      done += n;
+    }
+    if(render_b200_finish(r, fb)) { free(fb); scene_b200_free(s); return 3; }
+  }
   const double dt = now() - t0;
   if(!quiet && spp) printf("[main] rendered %lu frames in an average of %.6f s/frame\n", (unsigned long)spp, dt/spp);
   char filename[1400];

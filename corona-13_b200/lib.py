@@ -277,7 +277,9 @@ def _load_render():
 RENDER_SYMBOLS = ["cb200_render_create", "cb200_render_destroy", "cb200_render_pass", "cb200_render_pass_stream", "cb200_render_flush", "cb200_render_clear", "cb200_render_instrument",
                   "cb200_render_fb_device", "cb200_render_set_framebuffer", "cb200_render_download", "cb200_render_snapshot", "cb200_render_snapshot_async", "cb200_render_snapshot_wait", "cb200_render_stats", "cb200_render_point",
                   "cb200_render_camera_rays", "cb200_render_bsdf", "cb200_render_medium",
-                  "cb200_render_set_dbor", "cb200_render_num_dbors", "cb200_render_dbor_device", "cb200_render_download_dbor"]
+                  "cb200_render_set_dbor", "cb200_render_num_dbors", "cb200_render_dbor_device", "cb200_render_download_dbor",
+                  "cb200_comm_unique_id", "cb200_reducer_create", "cb200_reducer_destroy", "cb200_reducer_begin", "cb200_reducer_end",
+                  "cb200_reducer_finish", "cb200_reducer_clear"]
 
 
 class Render:

@@ -269,6 +269,28 @@ typedef struct cb_medium_result_t
 cb_medium_result_t;
 int  cb200_render_medium(cb200_render_t *r, int32_t medium, const cb_medium_query_t *queries, cb_medium_result_t *results, uint64_t n);
 
+/* ---- multi-GPU: samples per pixel split over the GPUs of one box ---------------------------------------------------
+ * One rank (a process, or a thread with its own device) per GPU: rank g renders progressions g, g+N, ... -- the path-index ranges a
+ * 1-GPU run uses for those progressions, so the union over ranks is the same set of paths -- and after every progression ONE reduce
+ * (ncclReduce, sum, root 0, W*H*3 floats over NVLink) adds the rank's accumulation buffer into rank 0's running sum.  The reducer owns
+ * the rank's two accumulation buffers (double buffered), the root's sum, a side stream and the NCCL communicator; reduce, accumulate,
+ * clear and the optional copy of the running sum to the host are queued on the side stream and overlap the next progression.
+ * Replaces nothing in the reference (it has no multi-device mode): it partitions view_render()'s index ranges (src/view.c:636-638).
+ * NCCL is dlopen'ed at the first call.
+ *     id     : rank 0 calls cb200_comm_unique_id and hands the CB200_COMM_ID_BYTES bytes to the other ranks (pipe, file, MPI ...)
+ *     step   : the rank's local progression counter, 0, 1, 2, ...; every rank must run the same number of begin/end rounds (the reduce
+ *              is a collective), a rank without work in a round still calls both
+ *     stream : the stream the progression is rendered on (NULL = default stream)                                                    */
+#define CB200_COMM_ID_BYTES 128
+typedef struct cb200_reducer cb200_reducer_t;
+int  cb200_comm_unique_id(void *id_bytes);
+cb200_reducer_t *cb200_reducer_create(cb200_render_t *r, const void *id_bytes, int rank, int world, uint32_t width, uint32_t height);
+void cb200_reducer_destroy(cb200_reducer_t *q);
+int  cb200_reducer_begin(cb200_reducer_t *q, uint64_t step, void *stream);    /* before cb200_render_pass[_stream] / _flush of this round */
+int  cb200_reducer_end(cb200_reducer_t *q, uint64_t step, float *fb_host, void *stream);   /* fb_host: rank 0's progressive host image (pinned) or NULL */
+int  cb200_reducer_finish(cb200_reducer_t *q, float *fb_host);               /* waits; rank 0 receives the sum of all ranks */
+int  cb200_reducer_clear(cb200_reducer_t *q);
+
 #ifdef __cplusplus
 }
 #endif

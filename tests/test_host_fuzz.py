@@ -70,3 +70,45 @@ def test_corrupted_geo_files_under_sanitizers(asan_cli, tmp_path):
             rc, clean, err = run(asan_cli, nra2, str(tmp_path))
             assert rc in (0, 2) and clean, f"{shape} trial {trial} (kind {kind}): rc {rc}\n{err}"
         open(geo, "wb").write(orig)
+
+
+def test_corrupted_scene_lists_under_sanitizers(asan_cli, tmp_path):
+    """.nra2-level mutations: wild shape counts (negative, 4 * 10^9), wild shader counts, `mult` chains that fan out
+    exponentially, forward and self references, BSDF shaders in pre slots, lines cut short"""
+    g = GoldenImage("glass_metal")
+    nra2 = g.write_files(str(tmp_path))
+    lines = open(nra2).read().split("\n")
+    nsh = int(lines[1])
+    shape_line = 2 + nsh
+
+    def variant(name, mutate):
+        l = list(lines)
+        mutate(l)
+        path = str(tmp_path / f"{name}.nra2")
+        open(path, "w").write("\n".join(l))
+        return path
+
+    cases = {
+        "shapes_negative": lambda l: l.__setitem__(shape_line, "-1"),
+        "shapes_huge": lambda l: l.__setitem__(shape_line, "4000000000"),
+        "shapes_more_than_listed": lambda l: l.__setitem__(shape_line, str(int(l[shape_line]) + 1000)),
+        "shaders_negative": lambda l: l.__setitem__(1, "-5"),
+        "shaders_huge": lambda l: l.__setitem__(1, "100000"),
+        "mult_self": lambda l: l.__setitem__(2 + nsh - 1, "mult 1 0 0"),
+        "mult_forward": lambda l: l.__setitem__(2, f"mult 1 {nsh - 1} {nsh - 1}"),
+        "truncated": lambda l: l.__delitem__(slice(4, None)),
+    }
+    for name, mutate in cases.items():
+        import time
+        t0 = time.time()
+        rc, clean, err = run(asan_cli, variant(name, mutate), str(tmp_path))
+        assert rc in (0, 2) and clean, f"{name}: rc {rc}\n{err}"
+        assert time.time() - t0 < 20, f"{name}: the reader took {time.time() - t0:.1f} s"
+    # 17 lines of `mult 16 -1 ... -1`: 16^16 prepare steps if followed naively
+    fan = ["black", "18", "diffuse"] + ["mult 16 " + " ".join(["-1"] * 17)] * 17 + ["1", "17 shape0"]
+    path = str(tmp_path / "fanout.nra2")
+    open(path, "w").write("\n".join(fan) + "\n")
+    import time
+    t0 = time.time()
+    rc, clean, err = run(asan_cli, path, str(tmp_path))
+    assert rc in (0, 2) and clean and time.time() - t0 < 20, f"fan-out: rc {rc} after {time.time() - t0:.1f} s\n{err}"
