@@ -311,6 +311,8 @@ def main():
     torch.cuda.set_device(local)
     lib.set_device(local)
     if world > 1:
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+            os.environ["NCCL_DEBUG"] = "WARN"      # NCCL_DEBUG=VERSION prints a banner on stdout, in front of the one JSON line
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     warmup = max(args.warmup, 3)
 

@@ -57,7 +57,7 @@ struct NeeRec   // pending next-event contribution, resolved after the shadow wa
   float pixel_i, pixel_j;
   float total_dist;
   uint32_t light_lo, light_hi;
-  uint32_t pad;
+  uint32_t len;      // vertices of the completed path (path->length at the splat: the vertex + the light point)
 };
 
 // The reference weighs every contribution with sampler_mis(): own pdf and competing pdf are each multiplied by the product of
@@ -161,6 +161,7 @@ struct RenderDev
   int32_t has_media;               // any medium in the scene: the free-flight / transmittance code paths are live
   float *dbor;                     // `--dbor n` (view.c:291,339-350): n cascade buffers of fb_w*fb_h*3 floats, level major; NULL = off
   int32_t num_dbors;
+  double *stat;                    // view->stat_enery / stat_cnt (view.c:470-471): [32 lanes][33 path lengths]{energy, count}; NULL = off
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -175,10 +176,17 @@ __device__ __forceinline__ float bh_w(float n)   // filter_bh_w, blackmanharris.
 }
 
 // view_splat (view.c:455-495)
-__device__ bool splat(const RenderDev &R, float pixel_i, float pixel_j, float lambda, float value)
+__device__ bool splat(const RenderDev &R, float pixel_i, float pixel_j, float lambda, float value, int len)
 {
   if(!(value > 0.0f)) return false;
   if(!(value < FLT_MAX)) return false;
+  if(R.stat)
+  { // view_deferred_splat's path statistics (view.c:470-471): energy and count per path length; one copy per lane keeps the
+    // atomics of a warp on different addresses, the host sums the copies (cb200_render_path_stats)
+    double *p = R.stat + (((threadIdx.x & 31u)*33u + (uint32_t)(len < 0 ? 0 : len > 32 ? 32 : len))*2u);
+    atomicAdd(p, (double)value);
+    atomicAdd(p + 1, 1.0);
+  }
   float col[3];
   spectrum_to_camera(lambda, value, R.colour, col);
   const int wd = (int)R.fb_w, ht = (int)R.fb_h;
@@ -627,7 +635,7 @@ k_sky_miss(RenderDev R, uint32_t n, const PathState *__restrict__ st, const cb_h
         }
         if(!pp_contributes(pp, pdf_v, pdf_nee)) w = 0.0f;   // sampler_mis in float range only (PathPdf)
         if(R.sampler == CB_SAMPLER_PTNEE) w = lre_length(s.lre) + 1 == 2 ? 1.0f : 0.0f;   // ptnee.c:53-58: only the directly visible sky
-        did = splat(R, s.pixel_i, s.pixel_j, s.lambda, (s.thr*em)*w);   // lights_eval_vertex: isotropic for the envmap (list.c:272-273)
+        did = splat(R, s.pixel_i, s.pixel_j, s.lambda, (s.thr*em)*w, lre_length(s.lre) + 1);   // lights_eval_vertex: isotropic for the envmap (list.c:272-273)
       }
     }
   }
@@ -774,7 +782,7 @@ k_shade(RenderDev R, uint32_t n, const PathState *__restrict__ st_in, const cb_r
           // directly visible emitters, unweighted.  (Upstream tests `v[2].mode` of the two-vertex path there -- the slot
           // BEHIND its last vertex, i.e. whatever the worker thread's previous path left in it -- so its own result on those
           // pixels depends on thread scheduling; the vertex the comment in the source means, v[1], is used here.)
-          if(len == 2) did_splat = splat(R, s.pixel_i, s.pixel_j, s.lambda, thr*light_eval(v, omega));
+          if(len == 2) did_splat = splat(R, s.pixel_i, s.pixel_j, s.lambda, thr*light_eval(v, omega), len);
         }
         else if(v.mode & M_EMIT)
         {
@@ -788,7 +796,7 @@ k_shade(RenderDev R, uint32_t n, const PathState *__restrict__ st_in, const cb_r
             w = pdf_v/(pdf_nee + pdf_v);        // sampler_mis, ptdl.c:78-88 with one wavelength
           }
           if(!pp_contributes(pp, pdf_v, pdf_nee)) w = 0.0f;   // ... which only exists inside the float range (PathPdf)
-          did_splat = splat(R, s.pixel_i, s.pixel_j, s.lambda, L*w);
+          did_splat = splat(R, s.pixel_i, s.pixel_j, s.lambda, L*w, len);
           if(R.sampler == CB_SAMPLER_PT && len > 3)
           { // path_russian_roulette (pathspace.c:273-292)
             const float p_survival = fminf(1.0f, thr/s.thr_prev);
@@ -865,7 +873,7 @@ k_shade(RenderDev R, uint32_t n, const PathState *__restrict__ st_in, const cb_r
                       nray.ignore[0] = v.prim_lo; nray.ignore[1] = v.prim_hi;
                       nmax = total_dist;
                       nrec.value = thr_l*w; nrec.lambda = s.lambda; nrec.pixel_i = s.pixel_i; nrec.pixel_j = s.pixel_j;
-                      nrec.total_dist = total_dist; nrec.light_lo = nrec.light_hi = 0xffffffffu; nrec.pad = 0;
+                      nrec.total_dist = total_dist; nrec.light_lo = nrec.light_hi = 0xffffffffu; nrec.len = (uint32_t)len + 1u;
                     }
                   }
                 }
@@ -945,7 +953,7 @@ k_shade(RenderDev R, uint32_t n, const PathState *__restrict__ st_in, const cb_r
                         prim_test_geo(R.geo, lpid, tr, th);
                         nmax = th.dist;
                         nrec.value = thr_l*w; nrec.lambda = s.lambda; nrec.pixel_i = s.pixel_i; nrec.pixel_j = s.pixel_j;
-                        nrec.total_dist = total_dist; nrec.light_lo = l.prim_lo; nrec.light_hi = l.prim_hi; nrec.pad = 0;
+                        nrec.total_dist = total_dist; nrec.light_lo = l.prim_lo; nrec.light_hi = l.prim_hi; nrec.len = (uint32_t)len + 1u;
                       }
                     }
                   }
@@ -1049,7 +1057,7 @@ k_nee_resolve(RenderDev R, uint32_t n, const NeeRec *__restrict__ recs, const in
   if(i < n && vis[i])
   {
     const NeeRec r = recs[i];
-    did = splat(R, r.pixel_i, r.pixel_j, r.lambda, r.value);
+    did = splat(R, r.pixel_i, r.pixel_j, r.lambda, r.value, (int)r.len);
   }
   const uint32_t m = __ballot_sync(0xffffffffu, did);
   if(m && (threadIdx.x & 31u) == 0) atomicAdd(&cnt->splats, (unsigned long long)__popc(m));
@@ -1167,6 +1175,7 @@ static const float k_fstop[] = { 0.5f, 0.7f, 1.0f, 1.4f, 2, 2.8f, 4, 5.6f, 8, 11
 static const float k_exposure[] = { 60.0f, 30.0f, 15.0f, 8.0f, 4.0f, 2.0f, 1.0f, 0.5f, 1.0f/4.0f, 1.0f/8.0f, 1.0f/15.0f, 1.0f/30.0f,
   1.0f/60.0f, 1.0f/125.0f, 1.0f/250.0f, 1.0f/500.0f, 1.0f/1000.0f, 1.0f/2000.0f, 1.0f/4000.0f, 1.0f/8000.0f };     // view.c:75-79
 
+#define PATH_STAT_DOUBLES (32*33*2)
 struct cb200_render
 {
   cb200_accel *accel;
@@ -1192,6 +1201,7 @@ struct cb200_render
   uint32_t n_alive; int cur;
   float *own_fb;
   float *own_dbor;               // cb200_render_set_dbor
+  double *own_stat;              // cb200_render_path_stats
   // asynchronous snapshots: device-side copy of the accumulation buffer, drained to the host on a stream of its own
   float *snap_stage; cudaStream_t snap_stream; cudaEvent_t snap_ready, snap_done; int snap_pending;
   int bsdf_kinds;   // bit mask of the BSDF kinds referenced by shapes (selects the k_shade variant)
@@ -1437,6 +1447,7 @@ void cb200_render_destroy(cb200_render_t *r)
   if(r->snap_stream) { cudaStreamSynchronize(r->snap_stream); cudaStreamDestroy(r->snap_stream); cudaEventDestroy(r->snap_ready); cudaEventDestroy(r->snap_done); }
   for(void *p : r->owned) cudaFree(p);
   if(r->own_dbor) cudaFree(r->own_dbor);
+  if(r->own_stat) cudaFree(r->own_stat);
   for(cudaEvent_t e : r->ev_pool) cudaEventDestroy(e);
   if(r->h_cnt) cudaFreeHost(r->h_cnt);
   delete r;
@@ -1482,6 +1493,7 @@ cb200_render_t *cb200_render_create(cb200_accel_t *a, const cb_render_desc_t *de
   r->timing = r->counting = 0; r->ev_used = 0; r->d_trav_cnt = nullptr;
   r->n_alive = 0; r->cur = 0;
   r->snap_stage = nullptr; r->snap_stream = nullptr; r->snap_pending = 0;
+  r->own_stat = nullptr;
   r->own_dbor = nullptr;
   cb200_scene *s = a->scene;
   RenderDev &D = r->dev;
@@ -1571,6 +1583,7 @@ int cb200_render_clear(cb200_render_t *r, void *stream)
   if(r->dev.dbor) CB_CUDA(cudaMemsetAsync(r->dev.dbor, 0, (size_t)r->dev.num_dbors*r->dev.fb_w*r->dev.fb_h*3*sizeof(float), (cudaStream_t)stream));
   CB_CUDA(cudaMemsetAsync(r->d_cnt, 0, sizeof(ShadeCounters), (cudaStream_t)stream));
   CB_CUDA(cudaMemsetAsync(r->d_trav_cnt, 0, 8*sizeof(unsigned long long), (cudaStream_t)stream));
+  if(r->own_stat) CB_CUDA(cudaMemsetAsync(r->own_stat, 0, PATH_STAT_DOUBLES*sizeof(double), (cudaStream_t)stream));
   r->n_alive = 0;   // paths still in flight are dropped with the image they belong to
   memset(&r->stats, 0, sizeof(r->stats));
   return 0;
@@ -1681,6 +1694,32 @@ int cb200_render_stats(cb200_render_t *r, cb_render_stats_t *out)
 {
   if(!r || !out) { cb200_set_error("render_stats: bad arguments"); return CB200_ERR_ARG; }
   *out = r->stats;
+  return 0;
+}
+
+// view->stat_enery / stat_cnt (src/view.c:46-47,470-471): energy and number of splats per path length, what view_print_info draws
+// as the histogram of the sidecar file (view.c:759-790)
+int cb200_render_path_stats(cb200_render_t *r, int enable)
+{
+  if(!r) { cb200_set_error("render_path_stats: null"); return CB200_ERR_ARG; }
+  CB_CUDA(cudaDeviceSynchronize());
+  if(enable && !r->own_stat)
+  {
+    if(cudaMalloc(&r->own_stat, PATH_STAT_DOUBLES*sizeof(double)) != cudaSuccess) { r->own_stat = nullptr; cb200_set_error("render_path_stats: out of device memory"); return CB200_ERR_NOMEM; }
+    CB_CUDA(cudaMemset(r->own_stat, 0, PATH_STAT_DOUBLES*sizeof(double)));
+  }
+  r->dev.stat = enable ? r->own_stat : nullptr;
+  return 0;
+}
+
+int cb200_render_get_path_stats(cb200_render_t *r, double energy[33], uint64_t count[33])
+{
+  if(!r || !energy || !count) { cb200_set_error("render_get_path_stats: bad arguments"); return CB200_ERR_ARG; }
+  for(int k=0;k<33;k++) { energy[k] = 0.0; count[k] = 0; }
+  if(!r->own_stat) return 0;
+  std::vector<double> h(PATH_STAT_DOUBLES);
+  CB_CUDA(cudaMemcpy(h.data(), r->own_stat, PATH_STAT_DOUBLES*sizeof(double), cudaMemcpyDeviceToHost));
+  for(int lane=0;lane<32;lane++) for(int k=0;k<33;k++) { energy[k] += h[(lane*33 + k)*2]; count[k] += (uint64_t)h[(lane*33 + k)*2 + 1]; }
   return 0;
 }
 

@@ -114,6 +114,7 @@ const cb_material_t *scene_b200_materials(const struct scene_b200_t *s, int *num
 const cb_medium_t *scene_b200_media(const struct scene_b200_t *s, int *num, int *exterior);
 const char *scene_b200_basename(const struct scene_b200_t *s);
 uint64_t scene_b200_num_prims(const struct scene_b200_t *s);
+const float *scene_b200_aabb(const struct scene_b200_t *s);          /* accel_aabb of the built scene */
 int scene_b200_read_camera(const char *filename, uint32_t width, uint32_t height, cb_camera_t *out);
 /* accel_init + accel_build + camera + render_b200_init: what main.c's init() does for the hot path */
 int scene_b200_prepare(struct scene_b200_t *s, uint32_t width, uint32_t height, int sampler, int pointsampler, int colour, uint64_t frame,

@@ -2,7 +2,7 @@
  *
  *   corona_b200 <scene.nra2> [-s spp] [-w width] [-h height] [--frame n] [-x [name]] [-c camfile] [--batch n]
  *               [--sampler pt|ptdl|ptnee] [--points rand|halton] [--colour xyz|rec709] [--coeff file] [--tables file]
- *               [--dump-materials file] [--dbor n] [--gpus n] [-q]
+ *               [--dump-materials file] [--dbor n] [--gpus n] [--retain-framebuffer] [-q]
  *
  * Same arguments and defaults as the reference binary where they exist there (src/main.c:250-282,415-437,
  * src/view.c:262-297, src/display.d/null.c:47-56): -s samples per pixel then write the image and quit, -w/-h frame size
@@ -10,7 +10,10 @@
  * `render'), data/ergb2spec.coeff relative to the working directory.  --sampler / --points / --colour stand in for the
  * reference's compile-time MOD_sampler / MOD_pointsampler / COL_camera.  Writes <basename><name>_fb00.pfm like
  * view_write_images (src/view.c:549); --dbor n (src/view.c:291) adds the outlier rejection cascade of view_splat_col and its
- * <basename><name>_dbor%02d.pfm files (view.c:553-556).  Without a CUDA device it refuses: there is no CPU path in this binary.
+ * <basename><name>_dbor%02d.pfm files (view.c:553-556).  Next to the image it writes the reference's sidecar <image>.pfm.txt
+ * (common_write_sidecar, corona_common.c:70-97: module info, spp, s/prog, mean image intensity, path-length energy histogram), a
+ * machine-readable <image>.pfm.json (rays/s, spp/s, rays per path) and, with --retain-framebuffer (view.c:279), the frame buffer file
+ * <basename>_<name>_fb00.fb (framebuffer.h).  Without a CUDA device it refuses: there is no CPU path in this binary.
  *
  * --gpus n: the samples per pixel are split over n GPUs of the box, one process per GPU (forked before any device
  * work; this process is rank 0).  Rank g renders the progression groups g, g+n, ... -- the same path-index ranges a 1-GPU run
@@ -21,6 +24,7 @@
 #include "corona_b200.h"
 #include "corona_b200_render.h"
 
+#include <math.h>
 #include <stdlib.h>
 #include <string.h>
 #include <time.h>
@@ -28,6 +32,114 @@
 #include <sys/wait.h>
 
 static double now(void) { struct timespec t; clock_gettime(CLOCK_MONOTONIC, &t); return t.tv_sec + 1e-9*t.tv_nsec; }
+
+static const float k_fstop[] = {0.5, 0.7, 1.0, 1.4, 2, 2.8, 4, 5.6, 8, 11, 16, 22, 32, 45, 64, 90, 128};   /* src/view.c:71-73 */
+static const float k_exposure[] = {60.0f, 30.0f, 15.0f, 8.0f, 4.0f, 2.0f, 1.0f, 0.5f, 1.0/4.0f, 1.0/8.0f, 1.0/15.0f, 1.0/30.0f, 1.0/60.0f,
+                                   1.0/125.0f, 1.0/250.0f, 1.0/500.0f, 1.0/1000.0f, 1.0/2000.0f, 1.0/4000.0f, 1.0/8000.0f};   /* src/view.c:75-79 */
+
+typedef struct run_info_t
+{
+  const char *basename, *sampler, *points, *colour;
+  uint64_t spp, prims, rays_closest, rays_shadow, paths;
+  uint32_t width, height;
+  int gpus;
+  double seconds;          /* wall clock of the progressions */
+  const cb_camera_t *cam;
+  const float *aabb;
+  double energy[33]; uint64_t count[33];
+}
+run_info_t;
+
+/* the reference's sidecar (common_write_sidecar, src/corona_common.c:70-97: every module's print_info) for the modules of this
+ * binary; the view block follows view_print_info (src/view.c:726-790) including the path-length energy histogram */
+static void write_sidecar(const char *pfm, const run_info_t *R, const float *fb, float gain)
+{
+  char filename[1500];
+  snprintf(filename, sizeof(filename), "%s.txt", pfm);
+  FILE *f = fopen(filename, "wb");
+  if(!f) return;
+  fprintf(f, "corona-13: %s\n", cb200_version());
+  fprintf(f, "file     : %s\n", R->basename);
+  if(R->aabb[3] < R->aabb[0]) fprintf(f, "aabb     : empty\n");
+  else fprintf(f, "aabb     : (%.3f, %.3f)x(%.3f, %.3f)x(%.3f, %.3f) dm^3\n", R->aabb[0], R->aabb[3], R->aabb[1], R->aabb[4], R->aabb[2], R->aabb[5]);
+  fprintf(f, "points   : counter generator keyed by (frame, path index, dimension)\n");
+  fprintf(f, "prims    : %lu primitives\n", (unsigned long)R->prims);
+  accel_print_info(f);
+  render_print_info(f);
+  fprintf(f, "view     : samples per pixel: %lu (%.2f s/prog) max path vertices %d\n", (unsigned long)R->spp, R->spp ? R->seconds/R->spp : 0.0, 32);
+  fprintf(f, "           res %lux%lu\n", (unsigned long)R->width, (unsigned long)R->height);
+  fprintf(f, "           elapsed wallclock prog %.2fs on %d gpu%s\n", R->seconds, R->gpus, R->gpus > 1 ? "s" : "");
+  fprintf(f, "           active cam 0\n");
+  const cb_camera_t *c = R->cam;
+  fprintf(f, "camera   : thin lens model\n  focus  : %f\n  film   : %dmm x %dmm\n", c->focus, (int)(c->film_width*100.0f+0.5f), (int)(c->film_height*100.0f + 0.5f));
+  if(c->exposure_value > 6) fprintf(f, "         : 1/%.0f f/%.1f %.0fmm iso %d\n", roundf(1.0/k_exposure[c->exposure_value]), k_fstop[c->aperture_value], 100.0*c->focal_length, (int)c->iso);
+  else fprintf(f, "         : %.1f\" f/%.1f %.0fmm iso %d\n", k_exposure[c->exposure_value], k_fstop[c->aperture_value], 100.0*c->focal_length, (int)c->iso);
+  double sum[3] = {0, 0, 0};
+  const uint64_t px = (uint64_t)R->width*R->height;
+  for(uint64_t k=0;k<px;k++) for(int i=0;i<3;i++) sum[i] += fb[3*k+i];
+  fprintf(f, "           cam 0 average image intensity (rgb): (%f %f %f)\n", gain*sum[0]/px, gain*sum[1]/px, gain*sum[2]/px);
+  /* energy per path length, log-scaled over three text lines (view.c:759-790) */
+  const int lines = 3;
+  const double base = 64.0;
+  double max = 0.0;
+  for(int k=2;k<=32;k++) if(R->count[k] && R->energy[k] > max) max = R->energy[k];
+  fprintf(f, "           ");
+  for(int k=2;k<=32;k++) if(k % 10 == 0) fprintf(f, "%d", (k/10)%10); else if(k%5==0) fprintf(f, "|"); else fprintf(f, ".");
+  fprintf(f, "\n");
+  static const char *bar[] = {" ", "\u2581", "\u2582", "\u2583", "\u2584", "\u2585", "\u2586", "\u2587", "\u2588"};
+  for(int h=lines-1;h>=0;h--)
+  {
+    fprintf(f, "           ");
+    for(int k=2;k<=32;k++)
+    {
+      double level = max > 0.0 ? R->energy[k]/max : 0.0;
+      level = log(1.0 + (base-1.0)*level)/log(base);
+      const double fill = level*lines - h;
+      const int step = fill <= 0 ? 0 : fill >= 1.0 ? 8 : (int)ceil(fill*8.0);
+      fputs(bar[step], f);
+    }
+    fprintf(f, "\n");
+  }
+  fprintf(f, "filter   : blackman harris\n");
+  fprintf(f, "sampler  : %s\n", R->sampler);
+  fprintf(f, "mutations: %s\n", R->points);
+  fprintf(f, "camera   : %s\n", R->colour);
+  fprintf(f, "input    : eRGB via rgb2spec coefficients\n");
+  fclose(f);
+}
+
+/* machine-readable twin of the sidecar: throughput of this run */
+static void write_json(const char *pfm, const run_info_t *R)
+{
+  char filename[1500];
+  snprintf(filename, sizeof(filename), "%s.json", pfm);
+  FILE *f = fopen(filename, "wb");
+  if(!f) return;
+  const double rays = (double)R->rays_closest + (double)R->rays_shadow, s = R->seconds > 0 ? R->seconds : 1e-9;
+  fprintf(f, "{\"scene\": \"%s\", \"width\": %u, \"height\": %u, \"spp\": %lu, \"gpus\": %d, \"seconds\": %.6f, \"spp_per_s\": %.3f, "
+             "\"paths\": %lu, \"paths_per_s\": %.1f, \"rays_closest\": %lu, \"rays_shadow\": %lu, \"rays_per_s\": %.1f, \"rays_per_path\": %.4f, "
+             "\"primitives\": %lu, \"sampler\": \"%s\", \"points\": \"%s\", \"counts_cover\": \"rank 0\", \"path_length_energy\": [",
+          R->basename, R->width, R->height, (unsigned long)R->spp, R->gpus, R->seconds, R->spp/s, (unsigned long)R->paths, R->paths/s,
+          (unsigned long)R->rays_closest, (unsigned long)R->rays_shadow, rays/s, R->paths ? rays/R->paths : 0.0, (unsigned long)R->prims, R->sampler, R->points);
+  for(int k=0;k<=32;k++) fprintf(f, "%s%.9g", k ? ", " : "", R->energy[k]);
+  fprintf(f, "], \"path_length_count\": [");
+  for(int k=0;k<=32;k++) fprintf(f, "%s%lu", k ? ", " : "", (unsigned long)R->count[k]);
+  fprintf(f, "]}\n");
+  fclose(f);
+}
+
+/* the reference's frame buffer file (include/framebuffer.h:19-36,76-112): header {magic, width, height, channels, flags, gain} and the
+ * UN-gained floats; what `--retain-framebuffer` leaves behind as <basename>_<name>_fb00.fb (src/view.c:333-337) */
+static int write_fb_file(const char *filename, const float *fb, uint32_t width, uint32_t height, float gain)
+{
+  struct { uint64_t magic, width, height; uint16_t channels, flags; float gain; } h = {1936686951lu, width, height, 3, 0, gain};
+  FILE *f = fopen(filename, "wb");
+  if(!f) return 1;
+  const size_t n = (size_t)width*height*3;
+  const int bad = fwrite(&h, sizeof(h), 1, f) != 1 || fwrite(fb, sizeof(float), n, f) != n;
+  fclose(f);
+  return bad;
+}
 
 int main(int argc, char *argv[])
 {
@@ -41,7 +153,7 @@ int main(int argc, char *argv[])
   char outname[256] = "render";
   uint64_t spp = 0, frame = 1, batch = 0;
   uint32_t width = 1024, height = 576;       /* src/view.c:261-262 */
-  int sampler = CB_SAMPLER_PTDL, points = CB_POINTS_RAND, colour = CB_COLOUR_XYZ, quiet = 0, dbor = 0, gpus = 1;
+  int sampler = CB_SAMPLER_PTDL, points = CB_POINTS_RAND, colour = CB_COLOUR_XYZ, quiet = 0, dbor = 0, gpus = 1, retain = 0;
   for(int i=2;i<argc;i++)
   {
     if     (!strcmp(argv[i], "-s") && i+1 < argc) spp = strtoull(argv[++i], 0, 10);
@@ -59,6 +171,7 @@ int main(int argc, char *argv[])
     else if(!strcmp(argv[i], "--dump-materials") && i+1 < argc) dump = argv[++i];
     else if(!strcmp(argv[i], "--dbor") && i+1 < argc) { dbor = atoi(argv[++i]); dbor = dbor < 0 ? 0 : dbor > 20 ? 20 : dbor; }   /* view.c:291 */
     else if(!strcmp(argv[i], "--gpus") && i+1 < argc) { gpus = atoi(argv[++i]); gpus = gpus < 1 ? 1 : gpus > 64 ? 64 : gpus; }
+    else if(!strcmp(argv[i], "--retain-framebuffer")) retain = 1;
     else if(!strcmp(argv[i], "-q")) quiet = 1;
     else if((!strcmp(argv[i], "-t") || !strcmp(argv[i], "-b") || !strcmp(argv[i], "-o")) && i+1 < argc) ++i;   /* cpu threads / backups / timeout: n/a */
   }
@@ -119,6 +232,7 @@ int main(int argc, char *argv[])
   float *fb = (float *)malloc(sizeof(float)*per_frame*3);
   struct render_t *r = scene_b200_render(s);
   if(dbor > 1 && render_b200_set_dbor(r, dbor)) { free(fb); scene_b200_free(s); return 3; }
+  cb200_render_path_stats((cb200_render_t *)render_b200_handle(r), 1);      /* view->stat_enery / stat_cnt for the sidecar */
   t0 = now();
   if(gpus > 1)
   { /* groups of `batch` progressions, group b rendered by rank b % gpus; every rank runs the same number of rounds (the reduce is
@@ -174,6 +288,30 @@ int main(int argc, char *argv[])
   snprintf(filename, sizeof(filename), "%s%s_fb00.pfm", scene_b200_basename(s), outname);
   const float gain = spp ? d->camera.iso/(100.0f*(float)spp) : 0.0f;    /* src/view.c:656 */
   if(scene_b200_write_pfm(filename, fb, d->width, d->height, gain)) { fprintf(stderr, "[main] could not write %s\n", filename); free(fb); scene_b200_free(s); return 4; }
+  {
+    run_info_t R;
+    memset(&R, 0, sizeof(R));
+    cb_render_stats_t st;
+    memset(&st, 0, sizeof(st));
+    cb200_render_t *dev = (cb200_render_t *)render_b200_handle(r);
+    cb200_render_stats(dev, &st);
+    cb200_render_get_path_stats(dev, R.energy, R.count);
+    R.basename = scene_b200_basename(s);
+    R.sampler = sampler == CB_SAMPLER_PT ? "pathtracer" : sampler == CB_SAMPLER_PTNEE ? "pathtracer with next event estimation only" : "pathtracer with next event estimation and mis";
+    R.points = points == CB_POINTS_HALTON ? "halton points" : "none";
+    R.colour = colour == CB_COLOUR_REC709 ? "linear rec709" : "CIE XYZ";
+    R.spp = spp; R.prims = scene_b200_num_prims(s); R.width = d->width; R.height = d->height; R.gpus = gpus; R.seconds = dt;
+    R.rays_closest = st.rays_closest; R.rays_shadow = st.rays_shadow; R.paths = st.paths;
+    R.cam = &d->camera; R.aabb = scene_b200_aabb(s);
+    write_sidecar(filename, &R, fb, gain);
+    write_json(filename, &R);
+    if(retain)
+    {
+      char fbname[1400];
+      snprintf(fbname, sizeof(fbname), "%s_%s_fb00.fb", scene_b200_basename(s), outname);
+      if(write_fb_file(fbname, fb, d->width, d->height, gain)) fprintf(stderr, "[main] could not write %s\n", fbname);
+    }
+  }
   for(int l=0;dbor>1&&l<dbor;l++)
   { /* view_write_images, src/view.c:553-556 (the gcov buffers next to them are never written to upstream and are not produced) */
     snprintf(filename, sizeof(filename), "%s%s_dbor%02d.pfm", scene_b200_basename(s), outname, l);

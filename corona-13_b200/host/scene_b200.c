@@ -602,6 +602,7 @@ const cb_medium_t *scene_b200_media(const struct scene_b200_t *s, int *num, int 
 { if(num) *num = s->nra2->num_media; if(exterior) *exterior = s->nra2->exterior_medium; return s->nra2->media; }
 const char *scene_b200_basename(const struct scene_b200_t *s) { return s->basename; }
 uint64_t scene_b200_num_prims(const struct scene_b200_t *s) { return s->prims.num_prims; }
+const float *scene_b200_aabb(const struct scene_b200_t *s) { static const float empty[6] = {1, 1, 1, -1, -1, -1}; return s->accel ? accel_aabb(s->accel) : empty; }
 
 /* the shader-list half of a render description: materials, measured tables, media, sky (borrowed pointers into s) */
 void scene_b200_fill_desc(const struct scene_b200_t *s, cb_render_desc_t *d)

@@ -266,6 +266,8 @@ def _load_render():
     L.cb200_render_snapshot_async.argtypes = [vp, vp, vp]
     L.cb200_render_snapshot_wait.argtypes = [vp]
     L.cb200_render_stats.argtypes = [vp, vp]
+    L.cb200_render_path_stats.argtypes = [vp, C.c_int]
+    L.cb200_render_get_path_stats.argtypes = [vp, vp, vp]
     L.cb200_render_point.argtypes = [vp, vp, vp, vp, u64]
     L.cb200_render_camera_rays.argtypes = [vp, u64, u64, vp, vp]
     L.cb200_render_bsdf.argtypes = [vp, C.c_int32, vp, vp, u64]
@@ -278,6 +280,7 @@ RENDER_SYMBOLS = ["cb200_render_create", "cb200_render_destroy", "cb200_render_p
                   "cb200_render_fb_device", "cb200_render_set_framebuffer", "cb200_render_download", "cb200_render_snapshot", "cb200_render_snapshot_async", "cb200_render_snapshot_wait", "cb200_render_stats", "cb200_render_point",
                   "cb200_render_camera_rays", "cb200_render_bsdf", "cb200_render_medium",
                   "cb200_render_set_dbor", "cb200_render_num_dbors", "cb200_render_dbor_device", "cb200_render_download_dbor",
+                  "cb200_render_path_stats", "cb200_render_get_path_stats",
                   "cb200_comm_unique_id", "cb200_reducer_create", "cb200_reducer_destroy", "cb200_reducer_begin", "cb200_reducer_end",
                   "cb200_reducer_finish", "cb200_reducer_clear"]
 
@@ -400,6 +403,15 @@ class Render:
             v = getattr(s, k)
             out[k] = list(v) if hasattr(v, "__len__") else int(v)
         return out
+
+    def path_stats(self, enable=True):
+        _check(self.L.cb200_render_path_stats(self.r, int(enable)), "cb200_render_path_stats")
+
+    def get_path_stats(self):
+        """(energy[33], count[33]) per path length, the reference's view->stat_enery / stat_cnt"""
+        e, c = np.zeros(33, np.float64), np.zeros(33, np.uint64)
+        _check(self.L.cb200_render_get_path_stats(self.r, _ptr(e), _ptr(c)), "cb200_render_get_path_stats")
+        return e, c
 
     def instrument(self, timing=True, counters=False):
         _check(self.L.cb200_render_instrument(self.r, int(timing), int(counters)), "cb200_render_instrument")

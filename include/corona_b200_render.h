@@ -209,6 +209,11 @@ int  cb200_render_snapshot(cb200_render_t *r, float *fb_host, void *stream);
 int  cb200_render_snapshot_async(cb200_render_t *r, float *fb_host, void *stream);
 int  cb200_render_snapshot_wait(cb200_render_t *r);
 int  cb200_render_stats(cb200_render_t *r, cb_render_stats_t *out);
+/* the view's path statistics (src/view.c:46-47,470-471: stat_enery / stat_cnt): summed contribution and number of splats per path
+ * length (vertices, 2..32), what view_print_info draws as the histogram of the sidecar file (view.c:759-790).  Off by default;
+ * enable before rendering (synchronises the device), cleared by cb200_render_clear. */
+int  cb200_render_path_stats(cb200_render_t *r, int enable);
+int  cb200_render_get_path_stats(cb200_render_t *r, double energy[33], uint64_t count[33]);
 
 /* component entry points for parity tests (device work, host buffers): */
 /* Halton / counter RNG value for (path index, dimension) as pointsampler() returns it (halton.c:69-84) */

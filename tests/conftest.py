@@ -35,9 +35,16 @@ def lib(built):
 def pytest_terminal_summary(terminalreporter):
     """tie rate of the two traversal modes (helpers.intersect_modes): rays compared, answers that differ, all classified"""
     try:
-        from helpers import TIE_LOG
+        from helpers import TIE_LOG, MODE_B_LOG
     except Exception:
         return
+    if MODE_B_LOG:
+        rays = sum(n for _, n, _ in MODE_B_LOG)
+        diff = sum(d for _, _, d in MODE_B_LOG)
+        terminalreporter.write_line(f"mode B (GPU-built tree vs the reference tree's answers): {rays} rays, {diff} answers differ ({diff / max(rays, 1):.2e}), "
+                                    "every one proven a tie / grazed box")
+        for what, n, d in MODE_B_LOG:
+            terminalreporter.write_line(f"  {what}: {d} of {n}")
     if not TIE_LOG:
         return
     rays = sum(n for _, n, _ in TIE_LOG)

@@ -145,6 +145,7 @@ def classify_mismatches(orc, rays, got, want, max_dist=None):
     return len(idx), explained
 
 
+MODE_B_LOG = []   # (what, rays, differences) of the GPU-built tree against the reference-built tree's answers (mode B)
 TIE_LOG = []   # (what, rays, differences) of every two-mode comparison of this session, printed by conftest at the end
 
 

@@ -14,7 +14,7 @@ import os
 import numpy as np
 import pytest
 
-from helpers import Golden, GOLDEN_NAMES, S, R, assert_hits_equal, classify_mismatches, intersect_modes, visible_modes
+from helpers import Golden, GOLDEN_NAMES, S, R, assert_hits_equal, classify_mismatches, intersect_modes, visible_modes, MODE_B_LOG
 from oracle.binding import Oracle
 
 pytestmark = pytest.mark.gpu
@@ -76,6 +76,9 @@ CASES = {
     "quads_mb_50k": dict(num_tris=50000, seed=42, quads=True, motion=True),
     "analytic_mb_20k": dict(num_tris=20000, seed=43, analytic=True, motion=True),
 }
+# rays per case and kind (camera + uniformly random; the same number again as bounce rays and as shadow rays): 15.6 M rays
+# against the oracle in total (SURVEY 8c asks for >= 10^7 including shadow sets)
+NUM_RAYS = {"tris_100k": 2_000_000, "quads_mb_50k": 400_000, "analytic_mb_20k": 200_000}
 
 
 @pytest.mark.parametrize("case", list(CASES))
@@ -84,7 +87,8 @@ def test_mode_a_and_b_vs_oracle(gpu, case):
     tmax = 1.0 if cfg.get("motion") else 0.0
     sc = S.synthetic_scene(**cfg)
     orc = Oracle(sc).build()          # == reference tree for one build thread (tests/test_oracle_vs_ref.py)
-    rays = np.concatenate([S.camera_rays(150000, sc, time_max=tmax), S.random_rays(150000, sc, time_max=tmax)])
+    nr = NUM_RAYS[case]
+    rays = np.concatenate([S.camera_rays(nr, sc, time_max=tmax), S.random_rays(nr, sc, time_max=tmax)])
     want = orc.intersect(rays)
     br = S.bounce_rays(rays, want)
     want_b = orc.intersect(br)
@@ -109,10 +113,12 @@ def test_mode_a_and_b_vs_oracle(gpu, case):
     got = intersect_modes(acc, orc, rays, None, f"{case} closest")
     assert_hits_equal(got, chk.intersect(rays), "mode B vs oracle on the GPU tree")
     nm, nt = classify_mismatches(orc, rays, got, want)
+    MODE_B_LOG.append((f"{case} closest", len(rays), nm))
     assert nm == nt, f"{nm - nt} of {nm} mode-B differences are not order effects"
     got_b = intersect_modes(acc, orc, br, None, f"{case} bounce")
     assert_hits_equal(got_b, chk.intersect(br), "mode B bounce vs oracle on the GPU tree")
     nm, nt = classify_mismatches(orc, br, got_b, want_b)
+    MODE_B_LOG.append((f"{case} bounce", len(br), nm))
     assert nm == nt
     assert np.array_equal(visible_modes(acc, sr, md, case), want_v)
     acc.close()

@@ -296,3 +296,38 @@ def test_c_readers_refuse_garbage_side_files(built, tmp_path):
     for coeff in (c, str(tmp_path / "nonexistent.coeff")):
         p = subprocess.run([BIN, nra2, "--coeff", coeff, "--tables", TABLES, "--dump-materials", dump], capture_output=True, text=True)
         assert p.returncode == 2, f"coeff {coeff}: rc {p.returncode}"
+
+
+@needs_coeff
+@pytest.mark.gpu
+def test_cli_writes_the_reference_artefacts(built, tmp_path):
+    """next to the PFM: the sidecar <image>.pfm.txt in the reference's format (corona_common.c:70-97, view.c:726-790: spp, s/prog, mean
+    image intensity, the path-length energy histogram), its JSON twin (rays/s, spp/s, rays per path) and -- with
+    --retain-framebuffer -- the frame buffer file (framebuffer.h:19-36: header + un-gained floats)"""
+    import json
+    IO = cb.scene_io
+    g = GoldenImage("c10")
+    nra2 = g.write_files(str(tmp_path))
+    p = run_cli(nra2, "-s", "16", "-w", str(g.w), "-h", str(g.h), "--frame", "1", "--sampler", "ptdl", "--points", "halton", "--retain-framebuffer")
+    assert p.returncode == 0, p.stderr + p.stdout
+    base = os.path.join(str(tmp_path), "test")
+    img = IO.read_pfm(base + "render_fb00.pfm")
+    side = open(base + "render_fb00.pfm.txt", encoding="utf-8").read()
+    assert "samples per pixel: 16 (" in side and "s/prog) max path vertices 32" in side
+    assert "accel    : b200" in side and "render   : b200" in side and "sampler  : pathtracer with next event estimation and mis" in side
+    assert "mutations: halton points" in side and f"res {img.shape[1]}x{img.shape[0]}" in side
+    mean = [float(x) for x in side.split("average image intensity (rgb): (")[1].split(")")[0].split()]
+    assert np.allclose(mean, img.astype(np.float64).mean(axis=(0, 1)), rtol=2e-4)
+    bars = [l for l in side.split("\n") if any(ch in l for ch in "▁▂▃▄▅▆▇█")]
+    assert 1 <= len(bars) <= 3 and "█" in "".join(bars)          # the tallest path length fills its column
+    j = json.load(open(base + "render_fb00.pfm.json"))
+    assert j["spp"] == 16 and j["paths"] == 16 * img.shape[0] * img.shape[1] and j["rays_shadow"] > 0
+    assert 2.0 < j["rays_per_path"] < 6.0 and j["rays_per_s"] > 1e6 and j["spp_per_s"] > 0
+    e, c = np.array(j["path_length_energy"]), np.array(j["path_length_count"])
+    assert c[:2].sum() == 0 and c[2:].sum() > 0 and (e[c > 0] > 0).all() and e[3] > 0      # direct light seen from the first hit dominates
+    fb = base + "_render_fb00.fb"
+    hdr = np.fromfile(fb, np.uint64, 3)
+    assert int(hdr[0]) == 1936686951 and (int(hdr[1]), int(hdr[2])) == (img.shape[1], img.shape[0])
+    gain = np.fromfile(fb, np.float32, 1, offset=28)[0]
+    raw = np.fromfile(fb, np.float32, offset=32).reshape(img.shape)
+    assert np.allclose(raw * gain, img, rtol=1e-6, atol=0)
