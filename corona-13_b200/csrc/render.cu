@@ -162,6 +162,12 @@ struct RenderDev
   float *dbor;                     // `--dbor n` (view.c:291,339-350): n cascade buffers of fb_w*fb_h*3 floats, level major; NULL = off
   int32_t num_dbors;
   double *stat;                    // view->stat_enery / stat_cnt (view.c:470-471): [32 lanes][33 path lengths]{energy, count}; NULL = off
+  // atomic-free accumulation (k_tile_accumulate): splats are appended to this list instead of being added to fb; a == NULL = off
+  float4 *tile_a;                  // pixel_i, pixel_j, colour[0], colour[1]
+  float *tile_b;                   // colour[2]
+  uint32_t *tile_key, *tile_idx;   // 32x32 pixel tile of the sample / the record's own index (payload of the sort)
+  unsigned int *tile_count;
+  uint32_t tile_cap, tiles_x, tiles_y, tile_shift;
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -190,6 +196,30 @@ __device__ bool splat(const RenderDev &R, float pixel_i, float pixel_j, float la
   float col[3];
   spectrum_to_camera(lambda, value, R.colour, col);
   const int wd = (int)R.fb_w, ht = (int)R.fb_h;
+  if(R.tile_a && R.num_dbors <= 1)
+  { // atomic-free mode: the sample is only recorded here; k_tile_accumulate filters it into its 32x32 tile in shared memory and the
+    // tile is added to the framebuffer by its one owner.  Samples whose footprint misses the image are dropped like below.
+    const int fx0 = (int)(pixel_i - 1.5f), fy0 = (int)(pixel_j - 1.5f);
+    if(fx0 + 4 <= 0 || fy0 + 4 <= 0 || fx0 >= wd || fy0 >= ht) return false;
+    const unsigned active = __activemask();
+    const unsigned lane = threadIdx.x & 31u;
+    const int leader = __ffs(active) - 1;
+    unsigned base = 0;
+    if((int)lane == leader) base = atomicAdd(R.tile_count, (unsigned)__popc(active));
+    base = __shfl_sync(active, base, leader);
+    const unsigned o = base + __popc(active & ((1u << lane) - 1u));
+    if(o < R.tile_cap)
+    {
+      int px = (int)floorf(pixel_i), py = (int)floorf(pixel_j);
+      px = px < 0 ? 0 : px >= wd ? wd - 1 : px;
+      py = py < 0 ? 0 : py >= ht ? ht - 1 : py;
+      R.tile_a[o] = make_float4(pixel_i, pixel_j, col[0], col[1]);
+      R.tile_b[o] = col[2];
+      R.tile_key[o] = (uint32_t)(py >> R.tile_shift)*R.tiles_x + (uint32_t)(px >> R.tile_shift);
+      R.tile_idx[o] = o;
+    }
+    return true;
+  }
   const int x0 = (int)(pixel_i - 1.5f), y0 = (int)(pixel_j - 1.5f);
   const int u0 = -x0 < 0 ? 0 : -x0, v0 = -y0 < 0 ? 0 : -y0;
   const int u4 = x0 + 4 > wd ? wd - x0 : 4, v4 = y0 + 4 > ht ? ht - y0 : 4;
@@ -246,6 +276,90 @@ __device__ bool splat(const RenderDev &R, float pixel_i, float pixel_j, float la
     }
   }
   return true;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Atomic-free framebuffer accumulation (BASELINE north_star (3); the reference accumulates with a CAS loop per tap,
+// filter/blackmanharris.h:43-77 + corona_common.h:316-329).  The recorded samples are sorted by 32x32 pixel tile; one block per
+// tile filters its samples into a 36x36 shared-memory patch (the tile plus the two pixels the 4x4 Blackman-Harris footprint can
+// reach beyond it on every side) with the same weights as splat(), then adds the patch to the framebuffer.  Patches of
+// neighbouring tiles overlap in that border, so the tiles are processed in four checkerboard phases (even/odd tile column x
+// even/odd tile row): within a phase no two blocks touch the same pixel, every pixel has exactly one writer and no global atomic
+// is issued.
+// ---------------------------------------------------------------------------------------------
+// TILE: 32 for large frames; smaller frames take 16 or 8 so that a phase still has a block for every SM (R.tile_shift = log2 TILE)
+template<int TILE>
+__global__ void __launch_bounds__(256)
+k_tile_accumulate(RenderDev R, const uint32_t *__restrict__ offsets, const uint32_t *__restrict__ idx, int phase_x, int phase_y)
+{
+  constexpr int PATCH = TILE + 4;
+  const uint32_t tx = 2u*blockIdx.x + (uint32_t)phase_x, ty = 2u*blockIdx.y + (uint32_t)phase_y;
+  if(tx >= R.tiles_x || ty >= R.tiles_y) return;
+  const uint32_t t = ty*R.tiles_x + tx;
+  const uint32_t begin = __ldg(offsets + t), end = __ldg(offsets + t + 1);   // this tile's samples in the sorted list (k_tile_offsets)
+  if(begin >= end) return;
+  __shared__ float acc[PATCH*PATCH*3];
+  for(int p=threadIdx.x;p<PATCH*PATCH*3;p+=blockDim.x) acc[p] = 0.0f;
+  __syncthreads();
+  const int wd = (int)R.fb_w, ht = (int)R.fb_h;
+  const int ox = (int)tx*TILE - 2, oy = (int)ty*TILE - 2;     // image coordinates of acc[0]
+  for(uint32_t k=begin+threadIdx.x; k<end; k+=blockDim.x)
+  {
+    const uint32_t i = __ldg(idx + k);
+    const float4 a = __ldg(R.tile_a + i);
+    const float c2 = __ldg(R.tile_b + i);
+    const float pixel_i = a.x, pixel_j = a.y;
+    // view_splat / filter_blackmanharris_splat, the arithmetic of splat() above
+    const int x0 = (int)(pixel_i - 1.5f), y0 = (int)(pixel_j - 1.5f);
+    const int u0 = -x0 < 0 ? 0 : -x0, v0 = -y0 < 0 ? 0 : -y0;
+    const int u4 = x0 + 4 > wd ? wd - x0 : 4, v4 = y0 + 4 > ht ? ht - y0 : 4;
+    float w[16];
+    float weight = 0.0f;
+    for(int v=v0;v<v4;v++) for(int u=u0;u<u4;u++)
+    {
+      const float uu = (x0 + u + .5f) - pixel_i, vv = (y0 + v + .5f) - pixel_j;
+      const float f = bh_w(sqrtf(uu*uu + vv*vv) + 1.5f);
+      w[4*v+u] = f;
+      weight += f;
+    }
+    if(weight <= 0.0f) continue;
+    weight = 1.0f/weight;
+    for(int v=v0;v<v4;v++) for(int u=u0;u<u4;u++)
+    {
+      const float f = weight*w[4*v+u];
+      if(f == 0.0f) continue;
+      const int lx = x0 + u - ox, ly = y0 + v - oy;
+      if(lx < 0 || ly < 0 || lx >= PATCH || ly >= PATCH) continue;   // cannot happen for a sample keyed to this tile
+      float *p = acc + 3*(lx + PATCH*ly);
+      atomicAdd(p+0, a.z*f); atomicAdd(p+1, a.w*f); atomicAdd(p+2, c2*f);   // shared memory
+    }
+  }
+  __syncthreads();
+  for(int p=threadIdx.x;p<PATCH*PATCH;p+=blockDim.x)
+  {
+    const int gx = ox + p % PATCH, gy = oy + p / PATCH;
+    if(gx < 0 || gy < 0 || gx >= wd || gy >= ht) continue;
+    const float r0 = acc[3*p], r1 = acc[3*p+1], r2 = acc[3*p+2];
+    if(r0 == 0.0f && r1 == 0.0f && r2 == 0.0f) continue;
+    float *q = R.fb + 3*((size_t)gx + (size_t)wd*gy);
+    q[0] += r0; q[1] += r1; q[2] += r2;      // the only writer of this pixel in this phase
+  }
+}
+
+// offsets[t] = first position of tile t in the sorted key list (the position where a key >= t first appears), for t in [0, tiles];
+// offsets[tiles] = number of real records (the unused slots behind them carry the key `tiles`)
+__global__ void k_tile_offsets(const uint32_t *__restrict__ key, uint32_t n, uint32_t tiles, uint32_t *__restrict__ offsets)
+{
+  const uint32_t i = blockIdx.x*blockDim.x + threadIdx.x;
+  if(i > n) return;
+  const uint32_t prev = i ? key[i-1] : 0u, cur = i < n ? key[i] : tiles;
+  const uint32_t from = i ? prev + 1 : 0u, to = cur < tiles ? cur : tiles;
+  for(uint32_t t=from; t<=to; t++) offsets[t] = i;
+}
+
+__global__ void k_fill_u32(uint32_t *p, uint32_t v, uint32_t n)
+{
+  for(uint32_t i=blockIdx.x*blockDim.x + threadIdx.x; i<n; i+=gridDim.x*blockDim.x) p[i] = v;
 }
 
 __device__ __forceinline__ void quat_mult(float *in, const float *p)   // quaternion.h:40-47 (w,x,y,z)
@@ -466,7 +580,7 @@ __device__ void prim_test_geo(const SceneGeo &S, uint64_t pid, const RayD &r, Hi
 
 __device__ __forceinline__ float max3abs(V3 x) { return fmaxf(fmaxf(.5f, fabsf(x.x)), fmaxf(fabsf(x.y), fabsf(x.z))); }
 
-struct ShadeCounters { unsigned long long next, nee, hits[5], splats; };   // next, nee, hits[kind] are per wave; splats keeps counting
+struct ShadeCounters { unsigned long long next, nee, hits[5], splats; unsigned int tile_count, pad_; };   // next, nee, hits[kind] are per wave; splats keeps counting; tile_count: records pending for k_tile_accumulate
 
 // path_G for the edge between a surface vertex and the sampled light point (pathspace.c:58-69)
 __device__ __forceinline__ float cos_lambert(const Vtx &v, const Vtx &l, V3 d, float dist)
@@ -1202,6 +1316,10 @@ struct cb200_render
   float *own_fb;
   float *own_dbor;               // cb200_render_set_dbor
   double *own_stat;              // cb200_render_path_stats
+  // atomic-free accumulation (cb200_render_set_accumulation): the record list lives in dev.tile_*; sort outputs and scratch here
+  int tile_mode; uint32_t tile_ub;    // tile_ub: upper bound of the records appended since the last k_tile_accumulate pass
+  uint32_t *tile_key2, *tile_idx2, *tile_offsets; void *tile_tmp; size_t tile_tmp_bytes; int tile_bits;
+  float4 *tile_a; float *tile_b; uint32_t *tile_key, *tile_idx;   // owned copies of the dev.tile_* pointers (dev's are null while the mode is off)
   // asynchronous snapshots: device-side copy of the accumulation buffer, drained to the host on a stream of its own
   float *snap_stage; cudaStream_t snap_stream; cudaEvent_t snap_ready, snap_done; int snap_pending;
   int bsdf_kinds;   // bit mask of the BSDF kinds referenced by shapes (selects the k_shade variant)
@@ -1494,6 +1612,8 @@ cb200_render_t *cb200_render_create(cb200_accel_t *a, const cb_render_desc_t *de
   r->n_alive = 0; r->cur = 0;
   r->snap_stage = nullptr; r->snap_stream = nullptr; r->snap_pending = 0;
   r->own_stat = nullptr;
+  r->tile_mode = 0; r->tile_ub = 0; r->tile_key2 = r->tile_idx2 = r->tile_offsets = nullptr; r->tile_tmp = nullptr; r->tile_tmp_bytes = 0; r->tile_bits = 0;
+  r->tile_a = nullptr; r->tile_b = nullptr; r->tile_key = r->tile_idx = nullptr;
   r->own_dbor = nullptr;
   cb200_scene *s = a->scene;
   RenderDev &D = r->dev;
@@ -1573,6 +1693,10 @@ cb200_render_t *cb200_render_create(cb200_accel_t *a, const cb_render_desc_t *de
   cudaMemset(D.fb, 0, (size_t)desc->width*desc->height*3*sizeof(float));
   cudaMemset(r->d_cnt, 0, sizeof(ShadeCounters));
   r->desc.materials = nullptr; r->desc.tables = nullptr; r->desc.media = nullptr; r->desc.envmap = nullptr;   // borrowed: the caller may free them now
+  {
+    const char *e = getenv("CB200_TILES");     // default accumulation mode of new render objects (A/B measurements)
+    if(e && atoi(e) && cb200_render_set_accumulation(r, CB200_ACCUM_TILES)) { cb200_render_destroy(r); return nullptr; }
+  }
   return r;
 }
 
@@ -1584,6 +1708,11 @@ int cb200_render_clear(cb200_render_t *r, void *stream)
   CB_CUDA(cudaMemsetAsync(r->d_cnt, 0, sizeof(ShadeCounters), (cudaStream_t)stream));
   CB_CUDA(cudaMemsetAsync(r->d_trav_cnt, 0, 8*sizeof(unsigned long long), (cudaStream_t)stream));
   if(r->own_stat) CB_CUDA(cudaMemsetAsync(r->own_stat, 0, PATH_STAT_DOUBLES*sizeof(double), (cudaStream_t)stream));
+  if(r->tile_a && r->tile_ub)
+  { // recorded samples of the dropped image
+    k_fill_u32<<<cb200_sm_count_cached()*4, 256, 0, (cudaStream_t)stream>>>(r->tile_key, r->dev.tiles_x*r->dev.tiles_y, r->tile_ub < r->dev.tile_cap ? r->tile_ub : r->dev.tile_cap);
+    r->tile_ub = 0;
+  }
   r->n_alive = 0;   // paths still in flight are dropped with the image they belong to
   memset(&r->stats, 0, sizeof(r->stats));
   return 0;
@@ -1731,6 +1860,71 @@ int cb200_render_instrument(cb200_render_t *r, int timing, int counters)
   return 0;
 }
 
+// sort the recorded samples by tile and add them to the framebuffer: four checkerboard phases of one block per tile
+static int tile_pass(cb200_render *r, cudaStream_t st)
+{
+  const uint32_t n = r->tile_ub < r->dev.tile_cap ? r->tile_ub : r->dev.tile_cap;
+  r->tile_ub = 0;
+  if(!n) return 0;
+  TimeScope ts(r, st, KC_RESOLVE, n);
+  size_t tmp = r->tile_tmp_bytes;
+  CB_CUDA(cub::DeviceRadixSort::SortPairs(r->tile_tmp, tmp, r->dev.tile_key, r->tile_key2, r->dev.tile_idx, r->tile_idx2, (int)n, 0, r->tile_bits, st));
+  const uint32_t tiles = r->dev.tiles_x*r->dev.tiles_y;
+  k_tile_offsets<<<(n + 1 + 255)/256, 256, 0, st>>>(r->tile_key2, n, tiles, r->tile_offsets);
+  const dim3 grid((r->dev.tiles_x + 1)/2, (r->dev.tiles_y + 1)/2);
+  for(int ph=0;ph<4;ph++)
+  {
+    if(r->dev.tile_shift == 5)      k_tile_accumulate<32><<<grid, 256, 0, st>>>(r->dev, r->tile_offsets, r->tile_idx2, ph & 1, ph >> 1);
+    else if(r->dev.tile_shift == 4) k_tile_accumulate<16><<<grid, 256, 0, st>>>(r->dev, r->tile_offsets, r->tile_idx2, ph & 1, ph >> 1);
+    else                            k_tile_accumulate<8><<<grid, 256, 0, st>>>(r->dev, r->tile_offsets, r->tile_idx2, ph & 1, ph >> 1);
+  }
+  // unused slots carry the key one past the last tile, so that a sort over an upper bound of the count leaves them at the end
+  k_fill_u32<<<cb200_sm_count_cached()*4, 256, 0, st>>>(r->dev.tile_key, r->dev.tiles_x*r->dev.tiles_y, n);
+  CB_CUDA(cudaMemsetAsync(r->dev.tile_count, 0, sizeof(unsigned int), st));
+  cb200_count_launch(9); r->stats.kernel_launches += 9;   // radix sort (counted as 3), offsets, four phases, fill
+  CB_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int cb200_render_set_accumulation(cb200_render_t *r, int mode)
+{
+  if(!r || (mode != CB200_ACCUM_ATOMIC && mode != CB200_ACCUM_TILES)) { cb200_set_error("render_set_accumulation: bad arguments"); return CB200_ERR_ARG; }
+  CB_CUDA(cudaDeviceSynchronize());
+  if(r->tile_ub) { const int rc = tile_pass(r, 0); if(rc) return rc; CB_CUDA(cudaDeviceSynchronize()); }
+  if(mode == CB200_ACCUM_TILES && !r->tile_a)
+  {
+    const size_t cap = 4*(size_t)r->batch;
+    r->tile_a = dev_alloc<float4>(r, cap); r->tile_b = dev_alloc<float>(r, cap);
+    r->tile_key = dev_alloc<uint32_t>(r, cap); r->tile_idx = dev_alloc<uint32_t>(r, cap);
+    r->tile_key2 = dev_alloc<uint32_t>(r, cap); r->tile_idx2 = dev_alloc<uint32_t>(r, cap);
+    // the largest tile that still gives every SM two blocks per checkerboard phase (frames are multiples of 32 pixels)
+    r->dev.tile_shift = 5;
+    while(r->dev.tile_shift > 3 && (uint64_t)(r->dev.fb_w >> r->dev.tile_shift)*(r->dev.fb_h >> r->dev.tile_shift) < 8ull*cb200_sm_count_cached()) r->dev.tile_shift--;
+    const uint32_t T = 1u << r->dev.tile_shift;
+    r->dev.tiles_x = (r->dev.fb_w + T - 1)/T; r->dev.tiles_y = (r->dev.fb_h + T - 1)/T;
+    r->tile_bits = 1;
+    while((1u << r->tile_bits) <= r->dev.tiles_x*r->dev.tiles_y) r->tile_bits++;
+    r->tile_offsets = dev_alloc<uint32_t>(r, (size_t)r->dev.tiles_x*r->dev.tiles_y + 2);
+    bool ok = r->tile_a && r->tile_b && r->tile_key && r->tile_idx && r->tile_key2 && r->tile_idx2 && r->tile_offsets;
+    if(ok)
+    {
+      cub::DeviceRadixSort::SortPairs(nullptr, r->tile_tmp_bytes, r->tile_key, r->tile_key2, r->tile_idx, r->tile_idx2, (int)cap, 0, r->tile_bits);
+      r->tile_tmp = dev_alloc<uint8_t>(r, r->tile_tmp_bytes);
+      ok = r->tile_tmp != nullptr;
+    }
+    if(!ok) { r->tile_a = nullptr; cb200_set_error("render_set_accumulation: out of device memory"); return CB200_ERR_NOMEM; }
+    r->dev.tile_cap = (uint32_t)cap;
+    k_fill_u32<<<cb200_sm_count_cached()*4, 256>>>(r->tile_key, r->dev.tiles_x*r->dev.tiles_y, (uint32_t)cap);
+    CB_CUDA(cudaDeviceSynchronize());
+  }
+  r->tile_mode = mode == CB200_ACCUM_TILES;
+  r->dev.tile_a = r->tile_mode ? r->tile_a : nullptr;
+  r->dev.tile_b = r->tile_b; r->dev.tile_key = r->tile_key; r->dev.tile_idx = r->tile_idx;
+  r->dev.tile_count = &r->d_cnt->tile_count;
+  return 0;
+}
+extern "C" int cb200_render_accumulation(cb200_render_t *r) { return r && r->tile_mode ? CB200_ACCUM_TILES : CB200_ACCUM_ATOMIC; }
+
 // One wave of the pool: trace every path's pending ray, shade, trace and resolve the next-event rays.
 static int render_wave(cb200_render *r, uint32_t n, cudaStream_t st)
 {
@@ -1773,6 +1967,7 @@ static int render_wave(cb200_render *r, uint32_t n, cudaStream_t st)
   CB_CUDA(cudaMemcpyAsync(r->h_cnt, r->d_cnt, sizeof(ShadeCounters), cudaMemcpyDeviceToHost, st));
   CB_CUDA(cudaStreamSynchronize(st));
   const uint32_t n_next = (uint32_t)r->h_cnt->next, n_nee = (uint32_t)r->h_cnt->nee;
+  if(r->tile_mode) r->tile_ub = r->h_cnt->tile_count + n_nee;   // exact up to this wave's shading + at most one record per next-event ray
   if(n_nee)
   {
     {
@@ -1789,11 +1984,15 @@ static int render_wave(cb200_render *r, uint32_t n, cudaStream_t st)
   }
   r->n_alive = n_next;
   r->cur = cur ^ 1;
+  // the list holds 4 waves' worth and the next wave adds at most 2 * batch records (one per path that finds an emitter, one per
+  // next-event ray): flush it only when that might not fit -- normally once per call, at the end (render_collect)
+  if(r->tile_mode && (uint64_t)r->tile_ub + 2ull*r->batch > r->dev.tile_cap) { rc = tile_pass(r, st); if(rc) return rc; }
   return 0;
 }
 
 static int render_collect(cb200_render *r, cudaStream_t st)
 {
+  if(r->tile_mode && r->tile_ub) { const int rc = tile_pass(r, st); if(rc) return rc; }
   CB_CUDA(cudaMemcpyAsync(r->h_cnt, r->d_cnt, sizeof(ShadeCounters), cudaMemcpyDeviceToHost, st));
   CB_CUDA(cudaStreamSynchronize(st));
   r->stats.splats = r->h_cnt->splats;

@@ -267,6 +267,8 @@ def _load_render():
     L.cb200_render_snapshot_wait.argtypes = [vp]
     L.cb200_render_stats.argtypes = [vp, vp]
     L.cb200_render_path_stats.argtypes = [vp, C.c_int]
+    L.cb200_render_set_accumulation.argtypes = [vp, C.c_int]
+    L.cb200_render_accumulation.argtypes = [vp]
     L.cb200_render_get_path_stats.argtypes = [vp, vp, vp]
     L.cb200_render_point.argtypes = [vp, vp, vp, vp, u64]
     L.cb200_render_camera_rays.argtypes = [vp, u64, u64, vp, vp]
@@ -280,7 +282,7 @@ RENDER_SYMBOLS = ["cb200_render_create", "cb200_render_destroy", "cb200_render_p
                   "cb200_render_fb_device", "cb200_render_set_framebuffer", "cb200_render_download", "cb200_render_snapshot", "cb200_render_snapshot_async", "cb200_render_snapshot_wait", "cb200_render_stats", "cb200_render_point",
                   "cb200_render_camera_rays", "cb200_render_bsdf", "cb200_render_medium",
                   "cb200_render_set_dbor", "cb200_render_num_dbors", "cb200_render_dbor_device", "cb200_render_download_dbor",
-                  "cb200_render_path_stats", "cb200_render_get_path_stats",
+                  "cb200_render_path_stats", "cb200_render_get_path_stats", "cb200_render_set_accumulation", "cb200_render_accumulation",
                   "cb200_comm_unique_id", "cb200_reducer_create", "cb200_reducer_destroy", "cb200_reducer_begin", "cb200_reducer_end",
                   "cb200_reducer_finish", "cb200_reducer_clear"]
 
@@ -403,6 +405,13 @@ class Render:
             v = getattr(s, k)
             out[k] = list(v) if hasattr(v, "__len__") else int(v)
         return out
+
+    def set_accumulation(self, mode):
+        """0 = fp32 atomics per tap (the reference's scheme), 1 = atomic-free per-tile accumulation"""
+        _check(self.L.cb200_render_set_accumulation(self.r, int(mode)), "cb200_render_set_accumulation")
+
+    def accumulation(self):
+        return int(self.L.cb200_render_accumulation(self.r))
 
     def path_stats(self, enable=True):
         _check(self.L.cb200_render_path_stats(self.r, int(enable)), "cb200_render_path_stats")

@@ -190,6 +190,15 @@ void *cb200_render_fb_device(cb200_render_t *r);
  * caller double-buffer: reduce / read one buffer while the next progression renders into the other. */
 int  cb200_render_set_framebuffer(cb200_render_t *r, void *d_fb);
 int  cb200_render_download(cb200_render_t *r, float *fb_host, void *stream);   /* flushes first: the finished image */
+/* How splats reach the framebuffer.  CB200_ACCUM_ATOMIC: like the reference (view_splat -> filter_blackmanharris_splat ->
+ * common_atomic_add, a CAS loop per tap; here fp32 atomic adds).  CB200_ACCUM_TILES: atomic-free -- samples are recorded, sorted by
+ * 32x32 pixel tile, filtered into a shared-memory patch by one block per tile and added to the framebuffer by that block alone
+ * (four checkerboard phases, so that the patches' two-pixel borders never overlap within a launch).  Same weights, same per-pixel
+ * terms; only the fp32 summation order differs.  With a `--dbor` cascade the atomic path is used regardless.  Call between passes. */
+#define CB200_ACCUM_ATOMIC 0
+#define CB200_ACCUM_TILES  1
+int  cb200_render_set_accumulation(cb200_render_t *r, int mode);
+int  cb200_render_accumulation(cb200_render_t *r);
 /* `--dbor n` (src/view.c:291,339-350): the density based outlier rejection cascade of view_splat_col (view.c:497-522).  With
  * n > 1 every splat also goes, through the same Blackman-Harris taps, into the two of n extra buffers (W*H*3 floats each)
  * whose brightness range brackets the sample; n <= 1 switches the cascade off.  Call between progressions (it synchronises the

@@ -547,3 +547,29 @@ def test_ptnee_matches_reference(gpu, name):
         assert got[~keep].mean() >= 0.98 * a[~keep].mean()
     # no emission through extension: never brighter than ptdl, which adds the mis-weighted other half of the same integrand
     assert img[keep].mean() <= 1.02 * ptdl[keep].mean()
+
+
+@pytest.mark.parametrize("scene,key", [("c10", "ptdl_halton"), ("glass_metal", "ptdl_rand"), ("sky_light", "pt_halton"), ("fog", "ptdl_halton")])
+def test_atomic_free_tile_accumulation_gives_the_same_image(gpu, scene, key):
+    """cb200_render_set_accumulation(CB200_ACCUM_TILES): samples recorded, sorted by 32x32 tile, filtered in shared memory, one writer
+    per pixel -- the same per-pixel terms as the atomic splat, only the fp32 summation order differs; also across frame sizes that
+    are not a multiple of the tile grid's checkerboard and with streamed progressions"""
+    g = GoldenImage(scene)
+    acc = gpu.Accel(g.scene).build()
+    imgs = []
+    for mode in (0, 1):
+        r = gpu.Render(acc, g.camera, g.materials, g.w, g.h, frame=1, **g.sky_args, **GoldenImage.variant_args(key))
+        r.set_accumulation(mode)
+        assert r.accumulation() == mode
+        for k in range(12):
+            r.render_pass(streaming=(k % 3 != 2))
+        r.flush()
+        imgs.append(r.image())
+        st = r.stats()
+        r.close()
+    a, b = imgs[0].astype(np.float64), imgs[1].astype(np.float64)
+    scale = a.mean()
+    assert scale > 0 and np.isfinite(b).all()
+    assert np.sqrt(((a - b) ** 2).mean()) / scale < 1e-5, f"{scene}/{key}: tile accumulation differs from the atomic splat beyond summation order"
+    assert np.abs(a - b).max() / max(a.max(), 1e-30) < 1e-4
+    acc.close()
