@@ -580,7 +580,9 @@ __device__ void prim_test_geo(const SceneGeo &S, uint64_t pid, const RayD &r, Hi
 
 __device__ __forceinline__ float max3abs(V3 x) { return fmaxf(fmaxf(.5f, fabsf(x.x)), fmaxf(fabsf(x.y), fabsf(x.z))); }
 
-struct ShadeCounters { unsigned long long next, nee, hits[5], splats; unsigned int tile_count, pad_; };   // next, nee, hits[kind] are per wave; splats keeps counting; tile_count: records pending for k_tile_accumulate
+// next, nee, hits[kind], em are per wave (the first 8 words are cleared before every wave); splats keeps counting; tile_count: records
+// pending for k_tile_accumulate
+struct ShadeCounters { unsigned long long next, nee, hits[5], em, splats; unsigned int tile_count, pad_; };
 
 // path_G for the edge between a surface vertex and the sampled light point (pathspace.c:58-69)
 __device__ __forceinline__ float cos_lambert(const Vtx &v, const Vtx &l, V3 d, float dist)
@@ -820,14 +822,18 @@ __global__ void __launch_bounds__(RB)
 k_shade(RenderDev R, uint32_t n, const PathState *__restrict__ st_in, const cb_ray_t *__restrict__ rays_in,
         const cb_hitrec_t *__restrict__ hits, PathState *__restrict__ st_out, cb_ray_t *__restrict__ rays_out,
         cb_ray_t *__restrict__ nee_rays, float *__restrict__ nee_maxdist, uint2 *__restrict__ nee_light, NeeRec *__restrict__ nee_recs,
-        ShadeCounters *cnt, const uint32_t *__restrict__ hit_list, int kind, float *__restrict__ maxd_out)
+        ShadeCounters *cnt, const uint32_t *__restrict__ hit_list, int kind, float *__restrict__ maxd_out, NeeRec *__restrict__ em_recs)
 {
   constexpr bool VOLV = KINDS == 16;   // this launch shades volume vertices
   const uint32_t t = blockIdx.x*blockDim.x + threadIdx.x;
   const uint32_t n_hits = (uint32_t)*reinterpret_cast<volatile unsigned long long *>(&cnt->hits[kind]);   // written by k_compact_hits
   if(blockIdx.x*blockDim.x >= n_hits) return;   // whole block beyond the list (the grid is sized for n, the upper bound)
   (void)n;
-  bool alive = false, have_nee = false, did_splat = false;
+  bool alive = false, have_nee = false;
+  // emission found by extension is not splatted here: the contribution is queued (em_recs) and filtered into the framebuffer by
+  // k_nee_resolve together with the wave's next-event contributions -- few paths end on an emitter, and the 4x4 Blackman-Harris
+  // footprint inlined twice into this kernel cost every path registers and instruction-cache misses (10 % of the kernel's time)
+  float em_value = 0.0f; int em_len = 0;
   PathState s;
   V3 next_pos = mk3(0, 0, 0), next_dir = mk3(0, 0, 0);
   float next_clip = FLT_MAX;
@@ -896,7 +902,7 @@ k_shade(RenderDev R, uint32_t n, const PathState *__restrict__ st_in, const cb_r
           // directly visible emitters, unweighted.  (Upstream tests `v[2].mode` of the two-vertex path there -- the slot
           // BEHIND its last vertex, i.e. whatever the worker thread's previous path left in it -- so its own result on those
           // pixels depends on thread scheduling; the vertex the comment in the source means, v[1], is used here.)
-          if(len == 2) did_splat = splat(R, s.pixel_i, s.pixel_j, s.lambda, thr*light_eval(v, omega), len);
+          if(len == 2) { em_value = thr*light_eval(v, omega); em_len = len; }
         }
         else if(v.mode & M_EMIT)
         {
@@ -910,7 +916,7 @@ k_shade(RenderDev R, uint32_t n, const PathState *__restrict__ st_in, const cb_r
             w = pdf_v/(pdf_nee + pdf_v);        // sampler_mis, ptdl.c:78-88 with one wavelength
           }
           if(!pp_contributes(pp, pdf_v, pdf_nee)) w = 0.0f;   // ... which only exists inside the float range (PathPdf)
-          did_splat = splat(R, s.pixel_i, s.pixel_j, s.lambda, L*w, len);
+          em_value = L*w; em_len = len;
           if(R.sampler == CB_SAMPLER_PT && len > 3)
           { // path_russian_roulette (pathspace.c:273-292)
             const float p_survival = fminf(1.0f, thr/s.thr_prev);
@@ -1146,8 +1152,21 @@ k_shade(RenderDev R, uint32_t n, const PathState *__restrict__ st_in, const cb_r
       if(MEDIA) maxd_out[o] = next_clip;
     }
   }
-  const uint32_t msp = __ballot_sync(0xffffffffu, did_splat);
-  if(msp && lane == 0) atomicAdd(&cnt->splats, (unsigned long long)__popc(msp));
+  const bool have_em = em_value > 0.0f && em_value < FLT_MAX;     // view_splat's own acceptance test (view.c:457-459)
+  const uint32_t me = __ballot_sync(0xffffffffu, have_em);
+  if(me)
+  {
+    unsigned long long base = 0;
+    if(lane == (uint32_t)(__ffs(me) - 1)) base = atomicAdd(&cnt->em, (unsigned long long)__popc(me));
+    base = __shfl_sync(0xffffffffu, base, __ffs(me) - 1);
+    if(have_em)
+    {
+      NeeRec e;
+      e.value = em_value; e.lambda = s.lambda; e.pixel_i = s.pixel_i; e.pixel_j = s.pixel_j; e.total_dist = 0.0f;
+      e.light_lo = e.light_hi = 0xffffffffu; e.len = (uint32_t)em_len;
+      em_recs[base + __popc(me & ((1u << lane) - 1u))] = e;
+    }
+  }
   const uint32_t mn = __ballot_sync(0xffffffffu, have_nee);
   if(mn)
   {
@@ -1168,7 +1187,7 @@ k_nee_resolve(RenderDev R, uint32_t n, const NeeRec *__restrict__ recs, const in
 {
   const uint32_t i = blockIdx.x*blockDim.x + threadIdx.x;
   bool did = false;
-  if(i < n && vis[i])
+  if(i < n && (!vis || vis[i]))
   {
     const NeeRec r = recs[i];
     did = splat(R, r.pixel_i, r.pixel_j, r.lambda, r.value, (int)r.len);
@@ -1304,6 +1323,7 @@ struct cb200_render
   cb_hitrec_t *hits;
   float *maxd[2];                // sampled free-flight distance of every pending ray (scenes with media only), rides with rays[]
   cb_ray_t *nee_rays; float *nee_md; NeeRec *nee_recs; uint2 *nee_light; int32_t *nee_vis;
+  NeeRec *em_recs;               // emission found by extension, queued by k_shade for k_nee_resolve
   ShadeCounters *d_cnt, *h_cnt;
   cb_render_stats_t stats;
   // wave ordering by pixel (k_pixel_keys + radix sort)
@@ -1671,6 +1691,7 @@ cb200_render_t *cb200_render_create(cb200_accel_t *a, const cb_render_desc_t *de
   r->maxd[0] = r->maxd[1] = nullptr;
   if(D.has_media) for(int k=0;k<2;k++) { r->maxd[k] = dev_alloc<float>(r, N); ok = ok && r->maxd[k]; }
   r->nee_rays = dev_alloc<cb_ray_t>(r, N); r->nee_md = dev_alloc<float>(r, N); r->nee_recs = dev_alloc<NeeRec>(r, N); r->nee_light = dev_alloc<uint2>(r, N); r->nee_vis = dev_alloc<int32_t>(r, N);
+  r->em_recs = dev_alloc<NeeRec>(r, N);
   r->d_cnt = dev_alloc<ShadeCounters>(r, 1);
   for(int k=0;k<2;k++) { r->keys[k] = dev_alloc<uint32_t>(r, N); r->order[k] = dev_alloc<uint32_t>(r, N); ok = ok && r->keys[k] && r->order[k]; }
   r->sort_tmp = nullptr; r->sort_tmp_bytes = 0;
@@ -1682,7 +1703,7 @@ cb200_render_t *cb200_render_create(cb200_accel_t *a, const cb_render_desc_t *de
   }
   r->d_trav_cnt = dev_alloc<unsigned long long>(r, 8);
   if(r->d_trav_cnt) cudaMemset(r->d_trav_cnt, 0, 8*sizeof(unsigned long long));
-  ok = ok && r->d_trav_cnt && D.fb && r->hits && r->nee_rays && r->nee_md && r->nee_recs && r->nee_light && r->nee_vis && r->d_cnt;
+  ok = ok && r->d_trav_cnt && D.fb && r->hits && r->nee_rays && r->nee_md && r->nee_recs && r->nee_light && r->nee_vis && r->em_recs && r->d_cnt;
   ok = ok && cudaMallocHost(&r->h_cnt, sizeof(ShadeCounters)) == cudaSuccess;
   if(!ok)
   {
@@ -1936,7 +1957,7 @@ static int render_wave(cb200_render *r, uint32_t n, cudaStream_t st)
   }
   if(rc) return rc;
   r->stats.rays_closest += n; r->stats.kernel_launches++;
-  CB_CUDA(cudaMemsetAsync(r->d_cnt, 0, 7*sizeof(unsigned long long), st));   // next, nee, hits[5] (splats keeps counting)
+  CB_CUDA(cudaMemsetAsync(r->d_cnt, 0, 8*sizeof(unsigned long long), st));   // next, nee, hits[5], em (splats keeps counting)
   {
     TimeScope ts(r, st, KC_SHADE, n);
     if(r->dev.sky != CB_SKY_BLACK)
@@ -1948,7 +1969,7 @@ static int render_wave(cb200_render *r, uint32_t n, cudaStream_t st)
     k_compact_hits<<<(n + 255)/256, 256, 0, st>>>(r->dev, r->hits, n, (uint32_t)r->batch, r->hit_list, r->d_cnt, single);
     cb200_count_launch(); r->stats.kernel_launches++;
 #define SHADE_ARGS(K) (r->dev, n, r->st[cur], r->rays[cur], r->hits, r->st[cur^1], r->rays[cur^1], \
-      r->nee_rays, r->nee_md, r->nee_light, r->nee_recs, r->d_cnt, r->hit_list + (size_t)K*r->batch, K, r->maxd[cur^1])
+      r->nee_rays, r->nee_md, r->nee_light, r->nee_recs, r->d_cnt, r->hit_list + (size_t)K*r->batch, K, r->maxd[cur^1], r->em_recs)
 #define SHADE_LAUNCH(K) do { if(r->dev.has_media) k_shade<(1 << K), true><<<(n + RB - 1)/RB, RB, 0, st>>>SHADE_ARGS(K); \
                              else k_shade<(1 << K), false><<<(n + RB - 1)/RB, RB, 0, st>>>SHADE_ARGS(K); \
                              cb200_count_launch(); r->stats.kernel_launches++; } while(0)
@@ -1966,8 +1987,14 @@ static int render_wave(cb200_render *r, uint32_t n, cudaStream_t st)
   }
   CB_CUDA(cudaMemcpyAsync(r->h_cnt, r->d_cnt, sizeof(ShadeCounters), cudaMemcpyDeviceToHost, st));
   CB_CUDA(cudaStreamSynchronize(st));
-  const uint32_t n_next = (uint32_t)r->h_cnt->next, n_nee = (uint32_t)r->h_cnt->nee;
-  if(r->tile_mode) r->tile_ub = r->h_cnt->tile_count + n_nee;   // exact up to this wave's shading + at most one record per next-event ray
+  const uint32_t n_next = (uint32_t)r->h_cnt->next, n_nee = (uint32_t)r->h_cnt->nee, n_em = (uint32_t)r->h_cnt->em;
+  if(r->tile_mode) r->tile_ub = r->h_cnt->tile_count + n_nee + n_em;   // exact up to this wave's shading + at most one record per queued contribution
+  if(n_em)
+  { // emission found by extension (k_shade's queue): no visibility to wait for
+    TimeScope ts(r, st, KC_RESOLVE, n_em);
+    k_nee_resolve<<<(n_em + RB - 1)/RB, RB, 0, st>>>(r->dev, n_em, r->em_recs, nullptr, r->d_cnt);
+    cb200_count_launch(); r->stats.kernel_launches++;
+  }
   if(n_nee)
   {
     {
