@@ -579,6 +579,12 @@ __device__ void prim_test_geo(const SceneGeo &S, uint64_t pid, const RayD &r, Hi
 }
 
 __device__ __forceinline__ float max3abs(V3 x) { return fmaxf(fmaxf(.5f, fabsf(x.x)), fmaxf(fabsf(x.y), fabsf(x.z))); }
+// prims_offset_ray (src/prims.c:374-388): the origin of a ray leaving the surface point x in direction dir
+__device__ __forceinline__ V3 offset_origin(V3 x, V3 dir)
+{
+  const float eps = max3abs(x)*1e-4f;
+  return mk3(x.x + eps*dir.x, x.y + eps*dir.y, x.z + eps*dir.z);
+}
 
 // next, nee, hits[kind], em are per wave (the first 8 words are cleared before every wave); splats keeps counting; tile_count: records
 // pending for k_tile_accumulate
@@ -1126,8 +1132,7 @@ k_shade(RenderDev R, uint32_t n, const PathState *__restrict__ st_in, const cb_r
             s.bits = (mt << 8) | ((v.material_modes & (M_DIFFUSE | M_GLOSSY)) ? 1u : 0u);
             s.med_n = media_pack(med);
             for(int k=0;k<MED_MAX;k++) { s.med_shape[k] = med.shape[k]; s.med_ior[k] = med.ior[k]; }
-            const float eps = max3abs(v.x)*1e-4f;   // prims_offset_ray (prims.c:374-388), only on geometry (pathspace.c:759-761)
-            next_pos = VOLV ? v.x : mk3(v.x.x + eps*wo.x, v.x.y + eps*wo.y, v.x.z + eps*wo.z);
+            next_pos = VOLV ? v.x : offset_origin(v.x, wo);   // prims_offset_ray, only on geometry (pathspace.c:759-761)
             next_dir = wo;
             // a scattering medium ahead: draw the free flight now, it clips the next closest-hit ray (pathspace.c:742-747)
             if(MEDIA && vnext.present && vnext.mu_s > 0.0f) next_clip = vol_free_flight(vnext, point_dim(R.points, index, rb + 0));
@@ -1194,6 +1199,14 @@ k_nee_resolve(RenderDev R, uint32_t n, const NeeRec *__restrict__ recs, const in
   }
   const uint32_t m = __ballot_sync(0xffffffffu, did);
   if(m && (threadIdx.x & 31u) == 0) atomicAdd(&cnt->splats, (unsigned long long)__popc(m));
+}
+
+__global__ void k_offset_ray(const float *__restrict__ x, const float *__restrict__ dir, float *__restrict__ out, uint32_t n)
+{
+  const uint32_t i = blockIdx.x*blockDim.x + threadIdx.x;
+  if(i >= n) return;
+  const V3 o = offset_origin(mk3(x[3*i], x[3*i+1], x[3*i+2]), mk3(dir[3*i], dir[3*i+1], dir[3*i+2]));
+  out[3*i] = o.x; out[3*i+1] = o.y; out[3*i+2] = o.z;
 }
 
 __global__ void k_bsdf(MaterialsDev M, int32_t material, const cb_bsdf_query_t *__restrict__ q, cb_bsdf_result_t *__restrict__ out, uint32_t n)
@@ -2100,6 +2113,20 @@ int cb200_render_point(cb200_render_t *r, const uint64_t *index, const int32_t *
   cb200_count_launch();
   CB_CUDA(cudaMemcpy(out, d_o, n*4, cudaMemcpyDeviceToHost));
   cudaFree(d_i); cudaFree(d_d); cudaFree(d_o);
+  return 0;
+}
+
+int cb200_render_offset_ray(cb200_render_t *r, const float *x, const float *dir, float *out_pos, uint64_t n)
+{
+  if(!r || !x || !dir || !out_pos) { cb200_set_error("render_offset_ray: bad arguments"); return CB200_ERR_ARG; }
+  float *d = nullptr;
+  CB_CUDA(cudaMalloc(&d, (n + 1)*9*sizeof(float)));
+  CB_CUDA(cudaMemcpy(d, x, n*3*sizeof(float), cudaMemcpyHostToDevice));
+  CB_CUDA(cudaMemcpy(d + 3*n, dir, n*3*sizeof(float), cudaMemcpyHostToDevice));
+  if(n) k_offset_ray<<<(unsigned)((n + 127)/128), 128>>>(d, d + 3*n, d + 6*n, (uint32_t)n);
+  cb200_count_launch();
+  CB_CUDA(cudaMemcpy(out_pos, d + 6*n, n*3*sizeof(float), cudaMemcpyDeviceToHost));
+  cudaFree(d);
   return 0;
 }
 

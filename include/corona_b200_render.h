@@ -231,6 +231,10 @@ int  cb200_render_point(cb200_render_t *r, const uint64_t *index, const int32_t 
  * out_aux[n][4] = {pixel_i, pixel_j, lambda, throughput} */
 int  cb200_render_camera_rays(cb200_render_t *r, uint64_t first_index, uint64_t n, cb_ray_t *out_rays, float *out_aux);
 
+/* the origin of the ray that leaves surface point x[i] in direction dir[i], as the integrator computes it: prims_offset_ray
+ * (src/prims.c:374-388; 3 floats per point in, 3 out) */
+int  cb200_render_offset_ray(cb200_render_t *r, const float *x, const float *dir, float *out_pos, uint64_t n);
+
 /* one BSDF in isolation, the protocol of the reference's tools/battle-test.c:57-236 (regression/0052_dielectric, 0053): a
  * surface vertex at the origin with n = gn = +z (flip: -z), tangent frame get_onb(n), vacuum outside, the shading slots preset
  * by the caller, then the host bsdf's prepare(), sample() with the three given random dimensions, and brdf()/pdf() for the
