@@ -57,9 +57,9 @@ METRIC = "rays/s (closest-hit + shadow)"
 REFDIR = os.path.join(ROOT, "oracle", "_ref")
 
 
-NCU_SUMMARY = "profiles/r1h_k_intersect_ncu.json"
-NCU_COMMAND = ("ncu --set full --clock-control none --import-source on -k regex:k_intersect -s 20 -c 6 -o gpurun_out/r1h_k_intersect "
-               "python scripts/gpu_render_bench.py; ncu -i gpurun_out/r1h_k_intersect.ncu-rep --page raw --csv | python scripts/ncu_summary.py")
+NCU_SUMMARY = "profiles/r2m_k_intersect_ncu.json"
+NCU_COMMAND = ("ncu --set full --clock-control none --import-source on -k regex:k_intersect -s 40 -c 3 -o gpurun_out/r2m_k_intersect "
+               "python scripts/gpu_render_bench.py; python scripts/ncu_summary.py gpurun_out/r2m_k_intersect.ncu-rep profiles/r2m_k_intersect_ncu.json")
 
 
 def ncu_traffic():
@@ -507,7 +507,7 @@ def main():
         "grays_per_s_rank0": {"closest_hit": stt["rays_closest"] / (ms_closest * 1e-3) / 1e9, "shadow": stt["rays_shadow"] / max(ms_shadow * 1e-3, 1e-12) / 1e9},
         "roofline": {"bound": "hbm", "kernel": "k_intersect (closest-hit traversal, all launches of the timed region, rank 0)",
                      "achieved": achieved, "peak": hbm, "unit": "GB/s", "frac": achieved / hbm, "peak_source": which, "traffic": traffic,
-                     "binding_limit": "issue slots + L1 LSU wavefronts at ~15 of 32 lanes per instruction (ncu: " + NCU_SUMMARY + "), not HBM: "
+                     "binding_limit": "issue slots (68 %) + L1 LSU wavefronts (75 %) at ~15 of 32 lanes per instruction (ncu: " + NCU_SUMMARY + "), not HBM: "
                                       "`bound`/`frac` follow SURVEY 8(d)'s algorithmic-byte definition (bytes a ray NEEDS from the tree / time), "
                                       "`traffic` shows that almost all of them are served by L1/L2",
                      "traffic_source": {"kind": "committed ncu --set full capture, not measured in this run", "file": traffic_src,

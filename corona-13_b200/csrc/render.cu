@@ -588,6 +588,7 @@ __device__ __forceinline__ V3 offset_origin(V3 x, V3 dir)
 
 // next, nee, hits[kind], em are per wave (the first 8 words are cleared before every wave); splats keeps counting; tile_count: records
 // pending for k_tile_accumulate
+// next: low word = surviving paths, high word = next-event records of the wave (reserved with one atomic); nee: unused
 struct ShadeCounters { unsigned long long next, nee, hits[5], em, splats; unsigned int tile_count, pad_; };
 
 // path_G for the edge between a surface vertex and the sampled light point (pathspace.c:58-69)
@@ -823,18 +824,23 @@ __device__ __forceinline__ float vtx_pdf(const MaterialsDev &M, const Vtx &v, V3
 // variant fills.  MEDIA compiles the participating-media terms in (free-flight sampling of the next edge, transmittance and
 // distance pdf of the finished one: pathspace.c:716-747,822-843, shader.c:46-155); scenes without media run the MEDIA = false
 // variants, which are instruction for instruction the surface-only integrator.
+#ifndef SHADE_MIN_BLOCKS
+#define SHADE_MIN_BLOCKS 1
+#endif
 template<int KINDS, bool MEDIA>
-__global__ void __launch_bounds__(RB)
+__global__ void __launch_bounds__(RB, SHADE_MIN_BLOCKS)
 k_shade(RenderDev R, uint32_t n, const PathState *__restrict__ st_in, const cb_ray_t *__restrict__ rays_in,
         const cb_hitrec_t *__restrict__ hits, PathState *__restrict__ st_out, cb_ray_t *__restrict__ rays_out,
         cb_ray_t *__restrict__ nee_rays, float *__restrict__ nee_maxdist, uint2 *__restrict__ nee_light, NeeRec *__restrict__ nee_recs,
         ShadeCounters *cnt, const uint32_t *__restrict__ hit_list, int kind, float *__restrict__ maxd_out, NeeRec *__restrict__ em_recs)
 {
   constexpr bool VOLV = KINDS == 16;   // this launch shades volume vertices
-  const uint32_t t = blockIdx.x*blockDim.x + threadIdx.x;
   const uint32_t n_hits = (uint32_t)*reinterpret_cast<volatile unsigned long long *>(&cnt->hits[kind]);   // written by k_compact_hits
-  if(blockIdx.x*blockDim.x >= n_hits) return;   // whole block beyond the list (the grid is sized for n, the upper bound)
   (void)n;
+  // (a resident-wave grid striding over the list, with the next slot's state prefetched, was measured: 3.1 -> 3.2 ms per 4K step
+  // with or without the prefetch, profiles/r2n -- the block scheduler's own refill does better)
+  const uint32_t t = blockIdx.x*blockDim.x + threadIdx.x;
+  if(blockIdx.x*blockDim.x >= n_hits) return;   // whole block beyond the list (the grid is sized for n, the upper bound)
   bool alive = false, have_nee = false;
   // emission found by extension is not splatted here: the contribution is queued (em_recs) and filtered into the framebuffer by
   // k_nee_resolve together with the wave's next-event contributions -- few paths end on an emitter, and the 4x4 Blackman-Harris
@@ -1144,18 +1150,21 @@ k_shade(RenderDev R, uint32_t n, const PathState *__restrict__ st_in, const cb_r
   // warp-aggregated compaction of surviving paths and of pending next events
   const uint32_t lane = threadIdx.x & 31u;
   const uint32_t ma = __ballot_sync(0xffffffffu, alive);
-  if(ma)
+  const uint32_t mn = __ballot_sync(0xffffffffu, have_nee);
+  // one atomic reserves the warp's slots in both lists: surviving paths in the low, next-event records in the high word of cnt->next
+  // (the two separate round trips were 9 % of the kernel's stall samples)
+  unsigned long long both = 0;
+  if(ma | mn)
   {
-    unsigned long long base = 0;
-    if(lane == (uint32_t)(__ffs(ma) - 1)) base = atomicAdd(&cnt->next, (unsigned long long)__popc(ma));
-    base = __shfl_sync(0xffffffffu, base, __ffs(ma) - 1);
-    if(alive)
-    {
-      const uint64_t o = base + __popc(ma & ((1u << lane) - 1u));
-      st_out[o] = s;
-      write_ray(rays_out, o, next_pos, next_dir, s.time, s.prim_lo, s.prim_hi);
-      if(MEDIA) maxd_out[o] = next_clip;
-    }
+    if(lane == 0) both = atomicAdd(&cnt->next, (unsigned long long)__popc(ma) | ((unsigned long long)__popc(mn) << 32));
+    both = __shfl_sync(0xffffffffu, both, 0);
+  }
+  if(alive)
+  {
+    const uint64_t o = (uint32_t)both + __popc(ma & ((1u << lane) - 1u));
+    st_out[o] = s;
+    write_ray(rays_out, o, next_pos, next_dir, s.time, s.prim_lo, s.prim_hi);
+    if(MEDIA) maxd_out[o] = next_clip;
   }
   const bool have_em = em_value > 0.0f && em_value < FLT_MAX;     // view_splat's own acceptance test (view.c:457-459)
   const uint32_t me = __ballot_sync(0xffffffffu, have_em);
@@ -1172,17 +1181,10 @@ k_shade(RenderDev R, uint32_t n, const PathState *__restrict__ st_in, const cb_r
       em_recs[base + __popc(me & ((1u << lane) - 1u))] = e;
     }
   }
-  const uint32_t mn = __ballot_sync(0xffffffffu, have_nee);
-  if(mn)
+  if(have_nee)
   {
-    unsigned long long base = 0;
-    if(lane == (uint32_t)(__ffs(mn) - 1)) base = atomicAdd(&cnt->nee, (unsigned long long)__popc(mn));
-    base = __shfl_sync(0xffffffffu, base, __ffs(mn) - 1);
-    if(have_nee)
-    {
-      const uint64_t o = base + __popc(mn & ((1u << lane) - 1u));
-      nee_rays[o] = nray; nee_maxdist[o] = nmax; nee_recs[o] = nrec; nee_light[o] = make_uint2(nrec.light_lo, nrec.light_hi);
-    }
+    const uint64_t o = (uint32_t)(both >> 32) + __popc(mn & ((1u << lane) - 1u));
+    nee_rays[o] = nray; nee_maxdist[o] = nmax; nee_recs[o] = nrec; nee_light[o] = make_uint2(nrec.light_lo, nrec.light_hi);
   }
 }
 
@@ -2000,7 +2002,7 @@ static int render_wave(cb200_render *r, uint32_t n, cudaStream_t st)
   }
   CB_CUDA(cudaMemcpyAsync(r->h_cnt, r->d_cnt, sizeof(ShadeCounters), cudaMemcpyDeviceToHost, st));
   CB_CUDA(cudaStreamSynchronize(st));
-  const uint32_t n_next = (uint32_t)r->h_cnt->next, n_nee = (uint32_t)r->h_cnt->nee, n_em = (uint32_t)r->h_cnt->em;
+  const uint32_t n_next = (uint32_t)r->h_cnt->next, n_nee = (uint32_t)(r->h_cnt->next >> 32), n_em = (uint32_t)r->h_cnt->em;   // next: two 32-bit counts
   if(r->tile_mode) r->tile_ub = r->h_cnt->tile_count + n_nee + n_em;   // exact up to this wave's shading + at most one record per queued contribution
   if(n_em)
   { // emission found by extension (k_shade's queue): no visibility to wait for
