@@ -232,7 +232,7 @@ int main(int argc, char *argv[])
   float *fb = (float *)malloc(sizeof(float)*per_frame*3);
   struct render_t *r = scene_b200_render(s);
   if(dbor > 1 && render_b200_set_dbor(r, dbor)) { free(fb); scene_b200_free(s); return 3; }
-  cb200_render_path_stats((cb200_render_t *)render_b200_handle(r), 1);      /* view->stat_enery / stat_cnt for the sidecar */
+  if(!getenv("CB200_NO_PATH_STATS")) cb200_render_path_stats((cb200_render_t *)render_b200_handle(r), 1);   /* view->stat_enery / stat_cnt for the sidecar */
   t0 = now();
   if(gpus > 1)
   { /* groups of `batch` progressions, group b rendered by rank b % gpus; every rank runs the same number of rounds (the reduce is

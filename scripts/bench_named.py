@@ -14,6 +14,9 @@ for case, sampler in RUNS:
     g = GoldenImage(case)
     tmp = tempfile.mkdtemp()
     nra2 = g.write_files(tmp)
+    cmd_warm = [os.path.join(ROOT, "corona-13_b200", "corona_b200"), nra2, "-s", "32", "-w", str(W), "-h", str(H), "--frame", "1", "--sampler", sampler, "--points", "rand",
+                "--coeff", os.path.join(REF, "data", "ergb2spec.coeff"), "--tables", os.path.join(ROOT, "corona-13_b200", "data", "ref_tables.cbt"), "-q"]
+    subprocess.run(cmd_warm, capture_output=True, text=True)     # first process on a fresh box: page cache, clocks, driver start-up (measured -25 %)
     t0 = time.time()
     p = subprocess.run([os.path.join(ROOT, "corona-13_b200", "corona_b200"), nra2, "-s", str(SPP), "-w", str(W), "-h", str(H), "--frame", "1", "--batch", "16",
                         "--sampler", sampler, "--points", "rand", "--coeff", os.path.join(REF, "data", "ergb2spec.coeff"),
