@@ -301,6 +301,11 @@ def main():
     if args.impl == "reference":
         return run_reference(args, rank, world)
 
+    # stdout carries exactly ONE line, the JSON: whatever libraries print on file descriptor 1 while the job runs (NCCL's version
+    # banner, for one) is sent to stderr; the descriptor is restored just before the line is printed
+    sys.stdout.flush()
+    saved_stdout = os.dup(1)
+    os.dup2(2, 1)
     import torch
     import torch.distributed as dist
     cb = importlib.import_module("corona-13_b200")
@@ -311,8 +316,6 @@ def main():
     torch.cuda.set_device(local)
     lib.set_device(local)
     if world > 1:
-        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-            os.environ["NCCL_DEBUG"] = "WARN"      # NCCL_DEBUG=VERSION prints a banner on stdout, in front of the one JSON line
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     warmup = max(args.warmup, 3)
 
@@ -539,8 +542,11 @@ def main():
                         "what": f"channel means of the {args.steps}-spp image of the timed region over those of the reference arm's {int(z['spp'])}-spp image"}
         except Exception as e:   # reference not built on this box: say so instead of inventing a number
             out["cpu_baseline"] = {"value": None, "unit": "rays/s", "cores": os.cpu_count(), "kind": "reference", "sample": f"unavailable: {e}"}
-    print(json.dumps(out))
+    sys.stdout.flush()
+    os.dup2(saved_stdout, 1)
+    print(json.dumps(out), flush=True)
     if world > 1:
+        os.dup2(2, 1)
         dist.destroy_process_group()
 
 
