@@ -377,12 +377,66 @@ static int run_chunked(const cb_ray_t *rays, const float *max_dist, OUT *out, ui
   return rc;
 }
 
+// Small batches -- above all the batch of ONE that accel_intersect / accel_visible of an unpatched reference renderer hands in from
+// each of its pinned worker threads (src/pathspace.c:763, :325) -- skip the staging buffers, their mutex and the three copies: every
+// host thread owns a stream and a block of mapped pinned memory; the rays are written there, the traversal kernel reads them and
+// writes its answers over the bus, and the call costs one launch and one stream synchronisation.  Calls from different threads
+// run concurrently.  (Never freed: the reference's workers live as long as the process.)
+namespace {
+struct SmallSlot
+{
+  static const uint64_t CAP = 128;
+  int device = -1;
+  cudaStream_t st = nullptr;
+  unsigned char *h = nullptr, *d = nullptr;
+  cb_ray_t *rays(unsigned char *b) const { return reinterpret_cast<cb_ray_t *>(b); }
+  float *md(unsigned char *b) const { return reinterpret_cast<float *>(b + CAP*sizeof(cb_ray_t)); }
+  void *out(unsigned char *b) const { return b + CAP*(sizeof(cb_ray_t) + sizeof(float)); }
+  int prepare()
+  {
+    int dev = 0;
+    if(cudaGetDevice(&dev) != cudaSuccess) return CB200_ERR_CUDA;
+    if(device == dev) return 0;
+    if(h) { cudaFreeHost(h); h = nullptr; }
+    if(st) { cudaStreamDestroy(st); st = nullptr; }
+    device = -1;
+    if(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking) != cudaSuccess) { st = nullptr; return CB200_ERR_CUDA; }
+    void *p = nullptr, *q = nullptr;
+    if(cudaHostAlloc(&p, CAP*(sizeof(cb_ray_t) + sizeof(float) + sizeof(cb_hitrec_t)), cudaHostAllocMapped) != cudaSuccess) return CB200_ERR_NOMEM;
+    if(cudaHostGetDevicePointer(&q, p, 0) != cudaSuccess) { cudaFreeHost(p); return CB200_ERR_CUDA; }
+    h = static_cast<unsigned char *>(p); d = static_cast<unsigned char *>(q);
+    device = dev;
+    return 0;
+  }
+};
+thread_local SmallSlot t_small;
+}
+
+template<typename OUT, typename LAUNCH>
+static int run_small(const cb_ray_t *rays, const float *max_dist, OUT *out, uint64_t n, LAUNCH launch)
+{
+  SmallSlot &s = t_small;
+  int rc = s.prepare();
+  if(rc) { g_error = "intersect_n: pinned slot allocation failed"; return rc; }
+  memcpy(s.rays(s.h), rays, n*sizeof(cb_ray_t));
+  if(max_dist) memcpy(s.md(s.h), max_dist, n*sizeof(float));
+  rc = launch(s.rays(s.d), max_dist ? s.md(s.d) : nullptr, static_cast<OUT *>(s.out(s.d)), n, s.st);
+  if(rc) return rc;
+  cudaError_t e = cudaStreamSynchronize(s.st);
+  if(e != cudaSuccess) return cb200_cuda_fail(e, "sync", __FILE__, __LINE__);
+  memcpy(out, s.out(s.h), n*sizeof(OUT));
+  return 0;
+}
+
 extern "C" {
 
 int cb200_accel_intersect_n(const cb200_accel_t *a, const cb_ray_t *rays, const float *max_dist, cb_hitrec_t *out, uint64_t n)
 {
   if(!a || (n && (!rays || !out))) { g_error = "accel_intersect_n: bad arguments"; return CB200_ERR_ARG; }
   if(n == 0) return 0;
+  if(n <= SmallSlot::CAP)
+    return run_small<cb_hitrec_t>(rays, max_dist, out, n,
+      [a](cb_ray_t *dr, float *dm, cb_hitrec_t *dout, uint64_t m, cudaStream_t s) { return cb200_launch_intersect(a, dr, dm, dout, m, s, nullptr); });
   return run_chunked<cb_hitrec_t>(rays, max_dist, out, n,
     [a](cb_ray_t *dr, float *dm, cb_hitrec_t *dout, uint64_t m, cudaStream_t s) { return cb200_launch_intersect(a, dr, dm, dout, m, s, nullptr); });
 }
@@ -410,6 +464,9 @@ int cb200_accel_visible_n(const cb200_accel_t *a, const cb_ray_t *rays, const fl
 {
   if(!a || (n && (!rays || !out || !max_dist))) { g_error = "accel_visible_n: bad arguments"; return CB200_ERR_ARG; }
   if(n == 0) return 0;
+  if(n <= SmallSlot::CAP)
+    return run_small<int32_t>(rays, max_dist, out, n,
+      [a](cb_ray_t *dr, float *dm, int32_t *dout, uint64_t m, cudaStream_t s) { return cb200_launch_visible(a, dr, dm, dout, m, s); });
   return run_chunked<int32_t>(rays, max_dist, out, n,
     [a](cb_ray_t *dr, float *dm, int32_t *dout, uint64_t m, cudaStream_t s) { return cb200_launch_visible(a, dr, dm, dout, m, s); });
 }

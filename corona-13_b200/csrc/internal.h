@@ -138,6 +138,13 @@ int cb200_launch_intersect8(const cb200_accel *a, const cb_ray_t *d_rays, const 
 int cb200_launch_visible8(const cb200_accel *a, const cb_ray_t *d_rays, const float *d_max_dist, const uint2 *d_light_prim, int32_t *d_out,
                           uint64_t n, cudaStream_t stream);
 bool cb200_use_wide8(const cb200_accel *a);
+// traverse2.cu: closest hit with two rays per lane (static scenes, 32-bit child references, small stack)
+#ifndef CB200_DUAL_DEFAULT
+#define CB200_DUAL_DEFAULT 0
+#endif
+bool cb200_dual_enabled();
+int cb200_launch_intersect_dual(const cb200_accel *a, const cb_ray_t *d_rays, const float *d_max_dist, cb_hitrec_t *d_out,
+                                uint64_t n, cudaStream_t stream);
 // shared launch plumbing (traverse.cu)
 int cb200_get_ticket(cudaStream_t stream, unsigned int **t);
 int cb200_trace_grid(uint64_t n, const void *kernel);

@@ -1693,10 +1693,18 @@ cb200_render_t *cb200_render_create(cb200_accel_t *a, const cb_render_desc_t *de
   // wave buffers
   r->batch = desc->batch_paths;
   if(!r->batch)
-  { // default: one wave per progression (W*H paths, view.c:636-638), at most 2^23 (covers a padded 4K frame, 3840 x 2176)
-    r->batch = (uint64_t)desc->width*desc->height;
-    if(r->batch > (1ull << 23)) r->batch = 1ull << 23;
+  { // default: a pool of FOUR progressions (4 W*H paths, view.c:636-638), at most 2^25.  A streamed progression then is one
+    // wave -- its new paths plus the survivors of the previous ones, ~20 M rays at 4K -- instead of two or three pool-sized
+    // ones: every persistent traversal launch ends in a tail of half-empty warps and every wave costs a counter read-back, and
+    // both are paid per launch, not per ray.  Measured on the 4K bench (profiles/r3a_batch_sweep.log): 20.7 ms per progression
+    // with a pool of 2^23, 19.8 with 2^24, 19.6 with 2^25, same image.  ~560 bytes per slot; halved while that would take more than
+    // half of the free device memory.
+    r->batch = 4ull*desc->width*desc->height;
+    if(r->batch > (1ull << 25)) r->batch = 1ull << 25;
     if(r->batch < (1ull << 21)) r->batch = 1ull << 21;   // small frames: room for several progressions per wave (--batch)
+    size_t mem_free = 0, mem_total = 0;
+    if(cudaMemGetInfo(&mem_free, &mem_total) == cudaSuccess)
+      while(r->batch > (1ull << 21) && r->batch > (uint64_t)desc->width*desc->height && r->batch*560ull > mem_free/2) r->batch >>= 1;
   }
   const uint64_t N = r->batch;
   D.fb = r->own_fb = dev_alloc<float>(r, (size_t)desc->width*desc->height*3);
@@ -2174,3 +2182,60 @@ int cb200_render_camera_rays(cb200_render_t *r, uint64_t first_index, uint64_t n
 }
 
 } // extern "C"
+
+// Next-event samples of the FIRST hit vertex of path indices [first_index, first_index + n), for known-answer tests against the
+// reference's own nee_sample (oracle/ref_path.c): the same kernels as one wave of cb200_render_pass on a fresh pool -- camera
+// sample, closest hit, vertex preparation + next-event sample (k_shade), shadow sweep -- but the records are handed back
+// instead of being splatted.  out[k][16] = {pixel_i, pixel_j, lambda, value (throughput x mis weight), total_dist, light prim
+// (2 words, bit pattern), ray pos[3], ray dir[3], search limit, visible (1 / 0), path length at the splat}; *n_out records.
+int cb200_render_nee_records(cb200_render_t *r, uint64_t first_index, uint64_t n, float *out, uint64_t *n_out)
+{
+  if(!r || !out || !n_out || n == 0 || n > r->batch) { cb200_set_error("render_nee_records: bad arguments (0 < n <= batch_paths)"); return CB200_ERR_ARG; }
+  if(r->n_alive) { cb200_set_error("render_nee_records: paths in flight (flush first)"); return CB200_ERR_ARG; }
+  cudaStream_t st = 0;
+  const int cur = r->cur;
+  const uint32_t m = (uint32_t)n;
+  k_path_start<<<(m + RB - 1)/RB, RB, 0, st>>>(r->dev, first_index, m, nullptr, r->st[cur], r->rays[cur], nullptr, r->maxd[cur]);
+  cb200_count_launch();
+  int rc = cb200_launch_intersect(r->accel, r->rays[cur], r->maxd[cur], r->hits, m, st, nullptr);
+  if(rc) return rc;
+  CB_CUDA(cudaMemsetAsync(r->d_cnt, 0, 8*sizeof(unsigned long long), st));
+  const int single = r->dev.has_media ? -1 : (r->bsdf_kinds == 1) ? 0 : (r->bsdf_kinds == 2) ? 1 : (r->bsdf_kinds == 4) ? 2 : (r->bsdf_kinds == 8) ? 3 : -1;
+  k_compact_hits<<<(m + 255)/256, 256, 0, st>>>(r->dev, r->hits, m, (uint32_t)r->batch, r->hit_list, r->d_cnt, single);
+#define NEE_SHADE(K, MED) k_shade<(1 << K), MED><<<(m + RB - 1)/RB, RB, 0, st>>>(r->dev, m, r->st[cur], r->rays[cur], r->hits, r->st[cur^1], r->rays[cur^1], \
+      r->nee_rays, r->nee_md, r->nee_light, r->nee_recs, r->d_cnt, r->hit_list + (size_t)K*r->batch, K, r->maxd[cur^1], r->em_recs)
+#define NEE_SHADE_K(K) do { if(r->dev.has_media) NEE_SHADE(K, true); else NEE_SHADE(K, false); cb200_count_launch(); } while(0)
+  if(r->bsdf_kinds & 1) NEE_SHADE_K(0);
+  if(r->bsdf_kinds & 2) NEE_SHADE_K(1);
+  if(r->bsdf_kinds & 4) NEE_SHADE_K(2);
+  if(r->bsdf_kinds & 8) NEE_SHADE_K(3);
+  if(r->dev.has_media) { NEE_SHADE(4, true); cb200_count_launch(); }
+#undef NEE_SHADE_K
+#undef NEE_SHADE
+  cb200_count_launch(2);
+  CB_CUDA(cudaMemcpyAsync(r->h_cnt, r->d_cnt, sizeof(ShadeCounters), cudaMemcpyDeviceToHost, st));
+  CB_CUDA(cudaStreamSynchronize(st));
+  const uint32_t n_nee = (uint32_t)(r->h_cnt->next >> 32);
+  *n_out = n_nee;
+  // the survivors and the queued emission of this wave are dropped: the pool stays empty, the framebuffer untouched
+  if(!n_nee) return 0;
+  rc = cb200_launch_shadow(r->accel, r->nee_rays, r->nee_md, r->nee_light, r->nee_vis, n_nee, st);
+  if(rc) return rc;
+  std::vector<cb_ray_t> rays(n_nee);
+  std::vector<float> md(n_nee);
+  std::vector<NeeRec> recs(n_nee);
+  std::vector<int32_t> vis(n_nee);
+  CB_CUDA(cudaMemcpy(rays.data(), r->nee_rays, n_nee*sizeof(cb_ray_t), cudaMemcpyDeviceToHost));
+  CB_CUDA(cudaMemcpy(md.data(), r->nee_md, n_nee*sizeof(float), cudaMemcpyDeviceToHost));
+  CB_CUDA(cudaMemcpy(recs.data(), r->nee_recs, n_nee*sizeof(NeeRec), cudaMemcpyDeviceToHost));
+  CB_CUDA(cudaMemcpy(vis.data(), r->nee_vis, n_nee*sizeof(int32_t), cudaMemcpyDeviceToHost));
+  for(uint32_t k=0;k<n_nee;k++)
+  {
+    float *o = out + 16*(size_t)k;
+    o[0] = recs[k].pixel_i; o[1] = recs[k].pixel_j; o[2] = recs[k].lambda; o[3] = recs[k].value; o[4] = recs[k].total_dist;
+    memcpy(o + 5, &recs[k].light_lo, 4); memcpy(o + 6, &recs[k].light_hi, 4);
+    for(int c=0;c<3;c++) { o[7+c] = rays[k].pos[c]; o[10+c] = rays[k].dir[c]; }
+    o[13] = md[k]; o[14] = (float)vis[k]; o[15] = (float)recs[k].len;
+  }
+  return 0;
+}

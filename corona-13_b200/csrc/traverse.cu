@@ -669,6 +669,9 @@ static int launch_intersect_t(const cb200_accel *a, const cb_ray_t *d_rays, cons
   if(need > STACK_BIG) { cb200_set_error("tree deeper than the reference's MAX_TREE_DEPTH"); return CB200_ERR_UNSUPPORTED; }
   if(d_counters) return launch_intersect_k<MB, true, STACK_BIG, true>(a, d_rays, d_max_dist, d_out, n, stream, d_counters);
   const bool analytic = a->scene->any_analytic != 0;
+  // static scenes with 32-bit child references: two rays per lane (traverse2.cu)
+  if(!MB && need <= STACK_SMALL && cb200_dual_enabled() && a->dev.num_prims < (1ull << 26) && a->dev.num_nodes < (1ull << 31) && !force_ref64())
+    return cb200_launch_intersect_dual(a, d_rays, d_max_dist, d_out, n, stream);
   if(need <= STACK_SMALL)
     return analytic ? launch_intersect_k<MB, false, STACK_SMALL, true >(a, d_rays, d_max_dist, d_out, n, stream, nullptr)
                     : launch_intersect_k<MB, false, STACK_SMALL, false>(a, d_rays, d_max_dist, d_out, n, stream, nullptr);

@@ -114,8 +114,11 @@ void accel_intersect_n(const accel_t *b, const ray_t *rays, hit_t *hits, uint64_
 {
   if(!n) return;
   if(!b) no_accel("accel_intersect");
-  float *md = (float *)malloc(sizeof(float)*n);
-  cb_hitrec_t *out = (cb_hitrec_t *)malloc(sizeof(cb_hitrec_t)*n);
+  float md1[16];
+  cb_hitrec_t out1[16];   /* the single-ray callers (accel_intersect from every pinned worker) stay off the heap */
+  float *md = n <= 16 ? md1 : (float *)malloc(sizeof(float)*n);
+  cb_hitrec_t *out = n <= 16 ? out1 : (cb_hitrec_t *)malloc(sizeof(cb_hitrec_t)*n);
+  if(!md || !out) { fprintf(stderr, "[accel b200] intersect: out of memory\n"); if(n > 16) { free(md); free(out); } return; }
   for(uint64_t i=0;i<n;i++) md[i] = hits[i].dist;
   if(cb200_accel_intersect_n(b->accel, (const cb_ray_t *)rays, md, out, n))
     fprintf(stderr, "[accel b200] intersect failed: %s\n", cb200_last_error());
@@ -127,7 +130,7 @@ void accel_intersect_n(const accel_t *b, const ray_t *rays, hit_t *hits, uint64_
     if((out[i].prim[1] >> 29) == CB_PRIM_SPHERE)   /* include/geo/sphere.h:157 */
       for(int k=0;k<3;k++) hits[i].x[k] = rays[i].pos[k] + out[i].dist*rays[i].dir[k];
   }
-  free(md); free(out);
+  if(n > 16) { free(md); free(out); }
 }
 
 void accel_intersect(const accel_t *b, const ray_t *ray, hit_t *hit)

@@ -230,6 +230,12 @@ int  cb200_render_point(cb200_render_t *r, const uint64_t *index, const int32_t 
 /* primary rays for path indices: camera_sample (thinlens.c:115-128) with the path's own random dims;
  * out_aux[n][4] = {pixel_i, pixel_j, lambda, throughput} */
 int  cb200_render_camera_rays(cb200_render_t *r, uint64_t first_index, uint64_t n, cb_ray_t *out_rays, float *out_aux);
+/* next-event samples at the first hit vertex of path indices [first_index, first_index + n) -- nee_sample (include/pathspace/
+ * nee.h:87-243: lights_pdf_type, sample_cdf over the light list, prims_sample, shader_brdf, path_G, path_visible) weighted as
+ * ptdl.c:139-147 does -- handed back instead of splatted; only on a render object without paths in flight, framebuffer untouched.
+ * out[k][16] = {pixel_i, pixel_j, lambda, throughput x mis weight, |light point - ray origin|, light prim (2 words, bit
+ * pattern), shadow ray pos[3], dir[3], search limit, visible (1/0), path length at the splat}; *n_out = records written (<= n) */
+int  cb200_render_nee_records(cb200_render_t *r, uint64_t first_index, uint64_t n, float *out, uint64_t *n_out);
 
 /* the origin of the ray that leaves surface point x[i] in direction dir[i], as the integrator computes it: prims_offset_ray
  * (src/prims.c:374-388; 3 floats per point in, 3 out) */

@@ -9,11 +9,16 @@
  *   ref_path_camera(first, n, out)    for path index i: path_init + path_extend (pathspace.c:167-260: lambda, time, camera_sample
  *                                       of the thin lens, view_cam_init_frame, path_propagate -> accel_intersect)
  *   ref_path_offset(x, dir, prim, n, out)   prims_offset_ray (src/prims.c:374-388) on given hit points / directions
+ *   ref_path_nee(first, n, out)       for path index i: path_init + path_extend, then -- like sampler.d/ptdl.c:139-147 does at every
+ *                                     vertex -- nee_sample (include/pathspace/nee.h:87-243: lights_pdf_type, the light list's
+ *                                     sample_cdf + prims_sample, shader_brdf, path_G, path_visible) and the weight of
+ *                                     sampler_mis (ptdl.c:78-88) against path_pdf_extend
  */
 #include "corona_common.h"
 #include "pathspace.h"
 #include "prims.h"
 #include "view.h"
+#include "pathspace/nee.h"
 #include <stdlib.h>
 #include <string.h>
 
@@ -21,7 +26,9 @@ extern int init(const char *filename, int argc, char *argv[]);   /* src/main.c:2
 
 int ref_path_open(const char *nra2, int argc, char **argv)
 {
-  return init(nra2, argc, argv);
+  const int rc = init(nra2, argc, argv);
+  if(!rc) lights_prepare_frame();   /* what view_render does before the first sample (src/view.c:640): light list cdf, p_sky / p_geo */
+  return rc;
 }
 
 /* out: n rows of 20 floats:
@@ -63,4 +70,43 @@ void ref_path_offset(const float *x, const float *dir, uint64_t n, float *out)
     for(int k=0;k<3;k++) out[4*i+k] = ray.pos[k];
     out[4*i+3] = ray.min_dist;
   }
+}
+
+/* out: n rows of 20 floats:
+ *  0 pixel_i, 1 pixel_j, 2 lambda, 3 path->length after path_extend (2 = camera + first hit), 4 nee_sample's return value (-1: not called),
+ *  5 path->length after nee_sample, 6 path_throughput, 7 v[2].pdf, 8 path_pdf_extend(path, 2), 9 mis weight, 10,11 v[2].hit.prim (bit
+ *  pattern), 12..14 v[2].hit.x, 15..17 e[2].omega, 18 e[2].dist, 19 v[2].mode */
+void ref_path_nee(uint64_t first, uint64_t n, float *out)
+{
+  path_t *p = (path_t *)malloc(sizeof(path_t));
+  for(uint64_t i=0;i<n;i++)
+  {
+    float *o = out + 20*i;
+    memset(o, 0, 20*sizeof(float));
+    path_init(p, first + i, 0);
+    const int rc = path_extend(p);
+    o[0] = p->sensor.pixel_i; o[1] = p->sensor.pixel_j; o[2] = mf(p->lambda, 0);
+    o[3] = (float)p->length; o[4] = -1.0f;
+    if(rc || p->length != 2) continue;
+    const int rn = nee_sample(p);
+    o[4] = (float)rn; o[5] = (float)p->length;
+    if(rn || p->length != 3) continue;
+    const int v2 = p->length - 1;
+    const float thr = mf(path_throughput(p), 0);
+    o[6] = thr; o[7] = mf(p->v[v2].pdf, 0); o[19] = (float)p->v[v2].mode;
+    memcpy(o + 10, &p->v[v2].hit.prim, 8);
+    for(int k=0;k<3;k++) { o[12+k] = p->v[v2].hit.x[k]; o[15+k] = p->e[v2].omega[k]; }
+    o[18] = p->e[v2].dist;
+    if(thr > 0.0f && (p->v[v2].mode & s_emit))
+    { /* sampler_mis (static in ptdl.c:78-88), one wavelength: both pdfs times the product of v[1..length-2].pdf in double, back
+       * to float, our / (other + our) */
+      const float pe = mf(path_pdf_extend(p, v2), 0);
+      double pdf_path = 1.0;
+      for(int v=1;v<p->length-1;v++) pdf_path *= (double)mf(p->v[v].pdf, 0);
+      const double our = (double)o[7]*pdf_path, other = (double)pe*pdf_path;
+      o[8] = pe;
+      o[9] = (float)our/(float)(other + our);
+    }
+  }
+  free(p);
 }

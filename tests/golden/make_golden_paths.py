@@ -23,6 +23,8 @@ sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 CASES = ["c10", "motion"]
+NEE_CASES = ["c10", "motion", "glass_metal", "sphere_light", "sky_light", "envmap"]   # next-event samples at the first hit vertex (ref_path_nee)
+N_NEE = 6000
 N_LOW = 6000
 SPECIAL = [2**24 - 8, 2**31 - 8, 2**32 - 8, 2**32 + 5, 2**33 + 12345, 123456789012]   # 32-bit clipping of the Halton index, wide indices
 
@@ -33,16 +35,23 @@ def indices():
 
 def worker(case, out):
     from helpers import GoldenImage
-    g = GoldenImage(case)
+    g = GoldenImage(case.split(":")[-1])
     tmp = tempfile.mkdtemp(prefix="corona_paths_")
     nra2 = g.write_files(tmp)
     os.chdir(REFDIR)
-    L = C.CDLL(os.path.join(REFDIR, "libref_path_halton.so"))
+    L = C.CDLL(os.path.join(REFDIR, "libref_path_halton.so"), mode=C.RTLD_GLOBAL)   # the shader modules it dlopens resolve rt.* against it
     args = ["-w", str(g.w), "-h", str(g.h), "--frame", "1", "-t", "1", "-s", "1", "-b", "0", "-x"]
     argv = (C.c_char_p * len(args))(*[a.encode() for a in args])
     L.ref_path_open.argtypes = [C.c_char_p, C.c_int, C.POINTER(C.c_char_p)]
     assert L.ref_path_open(nra2.encode(), len(args), argv) == 0
     L.ref_path_camera.argtypes = [C.c_uint64, C.c_uint64, C.c_void_p]
+    if case.startswith("nee:"):
+        nee = np.zeros((N_NEE, 20), np.float32)
+        L.ref_path_nee.argtypes = [C.c_uint64, C.c_uint64, C.c_void_p]
+        L.ref_path_nee(0, N_NEE, nee.ctypes.data)
+        np.savez(out, nee=nee)
+        sys.stdout.flush()
+        os._exit(0)
     idx = indices()
     rows = np.zeros((len(idx), 20), np.float32)
     # consecutive runs of indices in one call each
@@ -79,5 +88,17 @@ if __name__ == "__main__":
         os.remove(tmp)
         r = z["rows"]
         print(case, "paths", len(r), "hit fraction", float((r[:, 17] == 2).mean()), "mean lambda", float(r[:, 2].mean()), "time range", float(r[:, 3].min()), float(r[:, 3].max()))
+    for case in NEE_CASES:
+        tmp = tempfile.mktemp(suffix=".npz")
+        env = dict(os.environ, LD_LIBRARY_PATH=os.path.join(REFDIR, "shaders") + ":" + os.environ.get("LD_LIBRARY_PATH", ""))
+        subprocess.run([sys.executable, os.path.abspath(__file__), "nee:" + case, tmp], check=True, stdout=subprocess.DEVNULL, env=env)
+        nee = np.load(tmp)["nee"]
+        os.remove(tmp)
+        out[f"{case}_nee"] = nee
+        called = nee[:, 4] == 0
+        lit = nee[:, 9] > 0
+        sky = lit & (nee[:, 10:12].view("u4") == 0xffffffff).all(axis=1)
+        print(case, "nee: first hits", int((nee[:, 3] == 2).sum()), "nee_sample called", int(called.sum()), "contributing", int(lit.sum()), "of them sky", int(sky.sum()),
+              "mean weight", float(nee[lit, 9].mean()) if lit.any() else 0.0)
     np.savez_compressed(os.path.join(HERE, "paths.npz"), **out)
     print("wrote paths.npz", os.path.getsize(os.path.join(HERE, "paths.npz")) // 1024, "KiB")
