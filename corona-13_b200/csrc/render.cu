@@ -1692,6 +1692,7 @@ cb200_render_t *cb200_render_create(cb200_accel_t *a, const cb_render_desc_t *de
   if(ok && build_lights(r)) { cb200_render_destroy(r); return nullptr; }
   // wave buffers
   r->batch = desc->batch_paths;
+  if(!r->batch) { const char *e = getenv("CB200_POOL_PATHS"); if(e) r->batch = strtoull(e, nullptr, 10); }   // measurement knob (scripts/pool_sweep_named.py)
   if(!r->batch)
   { // default: a pool of FOUR progressions (4 W*H paths, view.c:636-638), at most 2^25.  A streamed progression then is one
     // wave -- its new paths plus the survivors of the previous ones, ~20 M rays at 4K -- instead of two or three pool-sized
@@ -1701,7 +1702,9 @@ cb200_render_t *cb200_render_create(cb200_accel_t *a, const cb_render_desc_t *de
     // half of the free device memory.
     r->batch = 4ull*desc->width*desc->height;
     if(r->batch > (1ull << 25)) r->batch = 1ull << 25;
-    if(r->batch < (1ull << 21)) r->batch = 1ull << 21;   // small frames: room for several progressions per wave (--batch)
+    // small frames: room for many progressions per wave (--batch).  1024 x 576, 0011_ptdl through the command line
+    // (profiles/r3f_pool_named.log): 1067 spp/s with a pool of 2^21, 1229 with 2^23, 1259 with 2^24
+    if(r->batch < (1ull << 23)) r->batch = 1ull << 23;
     size_t mem_free = 0, mem_total = 0;
     if(cudaMemGetInfo(&mem_free, &mem_total) == cudaSuccess)
       while(r->batch > (1ull << 21) && r->batch > (uint64_t)desc->width*desc->height && r->batch*560ull > mem_free/2) r->batch >>= 1;

@@ -131,6 +131,8 @@ __device__ __forceinline__ void node_slabs(const void *nodes, uint64_t idx, floa
 __device__ __forceinline__ void load_ray(const cb_ray_t *rays, uint32_t i, RayD &r)
 {
   const float2 *p = reinterpret_cast<const float2 *>(rays + i);   // 40-byte records are 8-byte aligned
+  // (evict-first loads of the ray stream and stores of the hit stream, ld.global.cs / st.global.cs, were measured: closest hit 95.8 ->
+  // 95.4 ms per 8 progressions, within noise; profiles/r3d)
   const float2 a = __ldg(p), b = __ldg(p+1), c = __ldg(p+2), d = __ldg(p+3), e = __ldg(p+4);
   r.px = a.x; r.py = a.y; r.pz = b.x; r.dx = b.y; r.dy = c.x; r.dz = c.y;
   r.time = d.x; r.min_dist = d.y;

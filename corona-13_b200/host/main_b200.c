@@ -226,7 +226,7 @@ int main(int argc, char *argv[])
   if(batch < 1)
   { /* no --batch given: hand the device as many progressions per call as fill its path pool (the image does not depend on
      * the grouping: a path is a function of its index; rt.batch_frames only groups work upstream too, src/view.c:630-638) */
-    batch = ((1ull << 22) + per_frame - 1)/per_frame;
+    batch = ((1ull << 23) + per_frame - 1)/per_frame;     /* the library's pool holds max(4 frames, 2^23 paths) */
     if(batch > 64) batch = 64;
   }
   float *fb = (float *)malloc(sizeof(float)*per_frame*3);

@@ -20,8 +20,9 @@ acc = lib.Accel(sc).build()
 cam = IO.Camera(pos=(18.0, 14.0, 14.5), lookat=(0.0, 0.0, 2.5), aperture_value=6, exposure_value=13, focal_length=0.4, iso=100.0)
 for batch in [int(x) for x in os.environ.get('BENCH_BATCHES', '0').split(',')]:
     r = lib.Render(acc, cam, ms, 3840, 2176, sampler=1, pointsampler=0, frame=1, batch_paths=batch)
-    r.render_pass()
-    r.clear()
+    if not os.environ.get('BENCH_NO_WARM'):   # (ncu captures: BENCH_NO_WARM=1, so that the first launches already are full streamed waves)
+        r.render_pass()
+        r.clear()
     r.instrument(True, False)
     t = time.time()
     NP = 8

@@ -385,6 +385,39 @@ print("ok")
     assert p.returncode == 0 and "ok" in p.stdout, p.stderr[-2000:]
 
 
+def test_two_rays_per_lane_kernel_is_bit_exact(gpu):
+    """csrc/traverse2.cu (opt-in, CB200_DUAL=1: every lane owns a register ray and a parked one and exchanges them after the
+    node / primitive vote; measured slower than k_intersect, profiles/r3c) runs the same per-ray test sequence: held to the same
+    bit-exact bar against the oracle, NaN / inf / zero-component rays (select-semantics path) and per-ray limits included"""
+    import subprocess
+    import sys
+    code = r'''
+import importlib, sys, numpy as np
+sys.path.insert(0, %r); sys.path.insert(0, %r)
+from helpers import S, R, assert_hits_equal
+from oracle.binding import Oracle
+lib = importlib.import_module("corona-13_b200.lib")
+lib.set_device(0)
+for n_tris, analytic in ((60000, False), (20000, True)):
+    sc = S.synthetic_scene(n_tris, seed=41, analytic=analytic)
+    acc = lib.Accel(sc).build()
+    nodes, primid = acc.export_qbvh()
+    orc = Oracle(sc).import_tree(nodes, acc.aabb(), primid)
+    rays = np.concatenate([S.camera_rays(150000, sc, seed=1), S.random_rays(150000, sc, seed=2)])
+    rays["dir"][::997, 0] = 0.0; rays["dir"][::1499, 1] = np.inf; rays["pos"][::2003, 2] = np.nan
+    want = orc.intersect(rays)
+    assert_hits_equal(acc.intersect(rays), want, "two rays per lane, closest")
+    b = S.bounce_rays(rays, want, seed=3)
+    assert_hits_equal(acc.intersect(b), orc.intersect(b), "two rays per lane, bounce")
+    for m in (1, 31, 32, 33, 63, 65, 4097):     # ragged launches: fewer rays than slots
+        assert_hits_equal(acc.intersect(rays[:m]), want[:m], f"two rays per lane, {m} rays")
+print("ok")
+''' % (ROOT, os.path.join(ROOT, "tests"))
+    env = dict(os.environ, CB200_DUAL="1")
+    p = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, cwd=ROOT)
+    assert p.returncode == 0 and "ok" in p.stdout, p.stderr[-2000:]
+
+
 def test_scene_create_refuses_wild_vertex_indices(gpu):
     """a vertex index outside the shape's vertex array must be refused at upload (the kernels would read outside their buffers)"""
     sc = S.synthetic_scene(500, seed=3)

@@ -97,7 +97,7 @@ def test_next_event_samples_match_the_reference(gpu, case):
     n_lit = int(lit.sum())
     assert n_lit > 1000
     missing = wrong_light = 0
-    rel, ddir, dpos = [], [], []
+    rel, val, ddir, dpos = [], [], [], []
     for k, w in zip(key(want[lit]), want[lit]):
         q = rec.get(k)
         if q is None or q[14] != 1.0:
@@ -107,6 +107,7 @@ def test_next_event_samples_match_the_reference(gpu, case):
             wrong_light += 1
             continue
         rel.append(q[3]/(w[6]*w[9]) - 1.0)
+        val.append(w[6]*w[9])
         ddir.append(np.abs(q[10:13] - w[15:18]).max())
         if (w[10:12].view("u4") != 0xffffffff).any():   # a point on a light primitive: ray origin + direction x (distance + the end offset)
             x = q[7:10].astype(np.float64) + q[10:13].astype(np.float64)*q[4]
@@ -114,16 +115,25 @@ def test_next_event_samples_match_the_reference(gpu, case):
     # first hits differ from the reference's on a few grazing / tie rays (test above: > 99.5 % agree)
     assert missing <= 0.01*n_lit, f"{case}: {missing} of {n_lit} contributing next events have no visible gpu record"
     assert wrong_light <= 0.005*n_lit, f"{case}: {wrong_light} of {n_lit} next events chose another light primitive"
-    rel, ddir = np.abs(np.array(rel)), np.array(ddir)
-    assert np.quantile(rel, 0.99) < 2e-4 and np.median(rel) < 2e-5, (np.quantile(rel, 0.99), np.median(rel))
-    assert (rel < 2e-4).mean() > 0.98
-    assert np.quantile(ddir, 0.99) < 1e-5, np.quantile(ddir, 0.99)
+    rel, val, ddir = np.array(rel, np.float64), np.array(val, np.float64), np.array(ddir)
+    # geometry of the connection: the same floats
+    assert np.quantile(ddir, 0.99) < (1e-6 if case != "envmap" else 1e-4), np.quantile(ddir, 0.99)   # envmap: sinf / cosf / acosf of the texel direction
     if dpos:
-        assert np.quantile(np.array(dpos), 0.99) < 1e-3, np.quantile(np.array(dpos), 0.99)
+        assert np.quantile(np.array(dpos), 0.99) < 1.5e-3, np.quantile(np.array(dpos), 0.99)          # the ray ends 2 x 1e-4 |x| short of the point
+    # throughput x weight.  The reference evaluates every rgb2spec spectrum (surface colour, light colour) with the hardware's
+    # APPROXIMATE reciprocal square root (_mm_rsqrt_ss, include/rgb2spec.h:147: 12 bits, relative error up to 3.7e-4, and the
+    # sigmoid 0.5 + 0.5 x / sqrt(x^2 + 1) cancels for dark colours), the device with the IEEE one: values agree to ~1e-4 where the
+    # reflectance is not tiny, and the differences are unbiased.
+    arel = np.abs(rel)
+    assert np.median(arel) < 1e-4, np.median(arel)
+    assert (arel > 1e-3).mean() < 0.08, (arel > 1e-3).mean()
+    if (arel > 1e-3).any():
+        assert np.median(val[arel > 1e-3]) < 0.15*np.median(val), "large relative differences on bright samples"
+    assert abs((rel*val).sum())/val.sum() < 1e-4, abs((rel*val).sum())/val.sum()
     # the other direction: where the reference called nee_sample and found nothing to add, no visible record may exist
     dark = (want[:, 4] == 0) & ~lit
     extra = sum(1 for k in key(want[dark]) if k in rec and rec[k][14] == 1.0 and rec[k][3] > 0)
     assert extra <= 0.01*max(1, int(dark.sum())) + 2, f"{case}: {extra} of {int(dark.sum())} samples the reference rejects are visible records here"
     sky = (want[lit][:, 10:12].view("u4") == 0xffffffff).all(axis=1).sum()
     print(f"{case}: {n_lit} contributing next events ({sky} to the sky), {missing} without a visible record, {wrong_light} other light, "
-          f"value median rel. error {np.median(rel):.2e}, 99 % {np.quantile(rel, 0.99):.2e}, direction 99 % {np.quantile(ddir, 0.99):.1e}")
+          f"value median rel. error {np.median(arel):.2e}, 90 % {np.quantile(arel, 0.9):.2e}, energy-weighted {abs((rel*val).sum())/val.sum():.1e}, direction 99 % {np.quantile(ddir, 0.99):.1e}")
