@@ -108,6 +108,21 @@ __device__ __forceinline__ void node_slabs_fast_mb(const Node256 *__restrict__ n
   }
 }
 
+// 1 when the child was hit (its key is an entry distance), 0 when the key is KEY_MISS (NaN); a word select.  Inline PTX so that the
+// optimiser sees neither a comparison chain nor a boolean it could branch on (k_intersect's node step, below).
+__device__ __forceinline__ uint32_t hit_bit(float k)
+{
+  uint32_t r;
+  asm("{ .reg .pred q;\n setp.eq.f32 q, %1, %1;\n selp.u32 %0, 1, 0, q; }" : "=r"(r) : "f"(k));
+  return r;
+}
+__device__ __forceinline__ uint32_t sel32(uint32_t c, uint32_t a, uint32_t b)
+{
+  uint32_t r;
+  asm("{ .reg .pred q;\n setp.ne.u32 q, %1, 0;\n selp.b32 %0, %2, %3, q; }" : "=r"(r) : "r"(c), "r"(a), "r"(b));
+  return r;
+}
+
 #define CSWAP(cond, ka, ca, kb, cb) do { const float tk__ = ka; const ref_t tc__ = ca; \
   ka = (cond) ? kb : ka; ca = (cond) ? cb : ca; kb = (cond) ? tk__ : kb; cb = (cond) ? tc__ : cb; } while(0)
 
@@ -144,8 +159,6 @@ k_intersect(DevAccel A, const cb_ray_t *__restrict__ rays, const float *__restri
   uint32_t nearbits = 0;
   uint32_t near_off[3] = {0, 0, 0};
   bool exact = false;
-  const float4 *rec = nullptr;
-  uint32_t prims_left = 0;
   const uint32_t rec_stride = A.rec_units*4;
   r.px = r.py = r.pz = r.dx = r.dy = r.dz = r.time = r.min_dist = 0.0f; r.ign_lo = r.ign_hi = 0;
   h.dist = 0.0f; h.u = h.v = 0.0f; h.prim_lo = h.prim_hi = 0;
@@ -195,7 +208,10 @@ k_intersect(DevAccel A, const cb_ray_t *__restrict__ rays, const float *__restri
     if(do_prims)
     {
       if(state == ST_PRIM)
-      { // the whole leaf in primid[] order (qbvhmp.c:1371-1379)
+      { // the whole leaf in primid[] order (qbvhmp.c:1371-1379); empty leaves are never pushed, so there is at least one primitive
+        const ref_t leaf_bit = C32 ? (ref_t)0x80000000u : (ref_t)CB_LEAF_BIT;
+        const float4 *rec = A.recs + (uint64_t)((cur ^ leaf_bit) >> 5)*(uint64_t)rec_stride;
+        uint32_t prims_left = (uint32_t)cur & 31u;
         do
         {
           if(CNT) cnt[3]++;
@@ -265,21 +281,24 @@ k_intersect(DevAccel A, const cb_ray_t *__restrict__ rays, const float *__restri
       CSWAP(s01, key[2], child[2], key[3], child[3]);
       CSWAP(s0,  key[0], child[0], key[2], child[2]);
       CSWAP(s0,  key[1], child[1], key[3], child[3]);
-      // nearest hit child becomes current, the others are pushed far -> near with their entry distance
-      need_pop = true;
-      const int first = KEY_HIT(key[0]) ? 0 : KEY_HIT(key[1]) ? 1 : KEY_HIT(key[2]) ? 2 : KEY_HIT(key[3]) ? 3 : 4;
-      if(first < 4)
-      {
-#define PUSH(k) do { if(C32) stack[sp++] = ((uint64_t)child[k] << 32) | __float_as_uint(key[k]); \
-                     else { stack_dist[sp] = key[k]; stack[sp++] = child[k]; } } while(0)
-        if(KEY_HIT(key[3]) && first < 3) PUSH(3);
-        if(KEY_HIT(key[2]) && first < 2) PUSH(2);
-        if(KEY_HIT(key[1]) && first < 1) PUSH(1);
-#undef PUSH
-        cur = first == 0 ? child[0] : first == 1 ? child[1] : first == 2 ? child[2] : child[3];
-        need_pop = false;
-        new_cur = true;
-      }
+      // nearest hit child becomes current, the others are pushed far -> near with their entry distance.  One straight-line block
+      // for all lanes of the node step: the source form "first = hit0 ? 0 : hit1 ? 1 : ...; if(first < 4) { pushes; cur = child[first]; }"
+      // compiled into a chain of divergent branches -- one path per value of `first`, ~75 instructions at 5-9 lanes that cost as
+      // many issue slots as the four slab tests in front of them (profiles/r3e, source view).  The hit flags are made opaque 0 / 1
+      // words, pushes are predicated stores, the new current child is a chain of selects.
+      const uint32_t h0 = hit_bit(key[0]), h1 = hit_bit(key[1]), h2 = hit_bit(key[2]), h3 = hit_bit(key[3]);
+      const uint32_t h01 = h0 | h1, h012 = h01 | h2, any = h012 | h3;
+      const uint32_t p3 = h3 & h012, p2 = h2 & h01, p1 = h1 & h0;
+#define PUSH_IF(p, k) do { if(p) { if(C32) stack[sp] = ((uint64_t)child[k] << 32) | __float_as_uint(key[k]); \
+                                  else { stack_dist[sp] = key[k]; stack[sp] = child[k]; } } sp += (int)(p); } while(0)
+      PUSH_IF(p3, 3);
+      PUSH_IF(p2, 2);
+      PUSH_IF(p1, 1);
+#undef PUSH_IF
+      if(C32) cur = (ref_t)sel32(h0, (uint32_t)child[0], sel32(h1, (uint32_t)child[1], sel32(h2, (uint32_t)child[2], sel32(h3, (uint32_t)child[3], (uint32_t)cur))));
+      else    cur = h0 ? child[0] : h1 ? child[1] : h2 ? child[2] : h3 ? child[3] : cur;
+      need_pop = any == 0u;
+      new_cur = any != 0u;
     }
     if(need_pop)
     {
@@ -309,17 +328,8 @@ k_intersect(DevAccel A, const cb_ray_t *__restrict__ rays, const float *__restri
         state = ST_IDLE;
       }
     }
-    if(new_cur)
-    {
-      const ref_t leaf_bit = C32 ? (ref_t)0x80000000u : (ref_t)CB_LEAF_BIT;
-      if(cur & leaf_bit)
-      {
-        rec = A.recs + (uint64_t)((cur ^ leaf_bit) >> 5)*(uint64_t)rec_stride;
-        prims_left = (uint32_t)cur & 31u;
-        state = ST_PRIM;   // empty leaves are never pushed, so prims_left >= 1
-      }
-      else state = ST_NODE;
-    }
+    // a leaf reference (top bit) sends the lane to the primitive step, which works out the record address itself
+    if(new_cur) state = (int)(1u + (uint32_t)(cur >> (C32 ? 31 : 63)));   // ST_NODE = 1, ST_PRIM = 2
   }
   if(CNT)
     for(int k=0;k<4;k++) if(cnt[k]) atomicAdd(counters + k, cnt[k]);
