@@ -167,7 +167,9 @@ k_intersect(DevAccel A, const cb_ray_t *__restrict__ rays, const float *__restri
   {
     // ---- refill idle lanes from the global ray queue, but only once enough of them have gathered (or nothing else is
     //      left to do): the fetch code would otherwise run on nearly every iteration for one or two lanes
-    const uint32_t idle = __ballot_sync(FULL, state == ST_IDLE);
+    uint32_t mN = __ballot_sync(FULL, state == ST_NODE);
+    const uint32_t mP = __ballot_sync(FULL, state == ST_PRIM);
+    const uint32_t idle = ~(mN | mP);
     if(idle && !exhausted && (__popc(idle) >= refill_threshold || idle == FULL))
     {
       const uint32_t want = __popc(idle);
@@ -194,9 +196,8 @@ k_intersect(DevAccel A, const cb_ray_t *__restrict__ rays, const float *__restri
           if(CNT) cnt[0]++;
         }
       }
+      mN = __ballot_sync(FULL, state == ST_NODE);   // the new rays start at the root
     }
-    const uint32_t mN = __ballot_sync(FULL, state == ST_NODE);
-    const uint32_t mP = __ballot_sync(FULL, state == ST_PRIM);
     if(!(mN | mP)) break;   // nothing in flight: the refill above ran (all lanes idle) and the queue is empty
     // prim_threshold < 0: relative to the lanes that hold a ray (-12 = 12/32 of them), so that a warp waiting for its next
     // refill with many finished lanes does not wait for nearly all remaining lanes to reach a leaf
@@ -205,6 +206,9 @@ k_intersect(DevAccel A, const cb_ray_t *__restrict__ rays, const float *__restri
     const bool do_prims = (mN == 0u) || (__popc(mP) >= thr);
 
     bool need_pop = false, new_cur = false;
+    // (loading the stack entry a pop will look at first BEFORE the primitive tests / the node's loads, so that the local-memory
+    // latency -- 14 % of this kernel's stall samples sit on the pop's comparison -- hides behind them: 86.9 -> 88.3 / 86.9 ms per 8
+    // progressions, profiles/r3l: the other warps already cover that stall)
     if(do_prims)
     {
       if(state == ST_PRIM)
@@ -362,8 +366,6 @@ k_visible(DevAccel A, const cb_ray_t *__restrict__ rays, const float *__restrict
   float ix = 0.0f, iy = 0.0f, iz = 0.0f, t0 = 1.0f, t1 = 0.0f, md = 0.0f;
   uint32_t near_off[3] = {0, 0, 0};
   bool exact = false;
-  const float4 *rec = nullptr;
-  uint32_t prims_left = 0;
   uint2 skip_id = make_uint2(0xffffffffu, 0xffffffffu);
   const uint32_t rec_stride = A.rec_units*4;
   r.px = r.py = r.pz = r.dx = r.dy = r.dz = r.time = r.min_dist = 0.0f; r.ign_lo = r.ign_hi = 0;
@@ -411,6 +413,9 @@ k_visible(DevAccel A, const cb_ray_t *__restrict__ rays, const float *__restrict
     {
       if(state == ST_PRIM)
       {
+        const ref_t leaf_bit = C32 ? (ref_t)0x80000000u : (ref_t)CB_LEAF_BIT;
+        const float4 *rec = A.recs + (uint64_t)((cur ^ leaf_bit) >> 5)*(uint64_t)rec_stride;
+        uint32_t prims_left = (uint32_t)cur & 31u;
         do
         {
           if(SHADOW)
@@ -475,14 +480,7 @@ k_visible(DevAccel A, const cb_ray_t *__restrict__ rays, const float *__restrict
       if(sp > 0)
       {
         cur = stack[--sp];
-        const ref_t leaf_bit = C32 ? (ref_t)0x80000000u : (ref_t)CB_LEAF_BIT;
-        if(cur & leaf_bit)
-        {
-          rec = A.recs + (uint64_t)((cur ^ leaf_bit) >> 5)*(uint64_t)rec_stride;
-          prims_left = (uint32_t)cur & 31u;
-          state = ST_PRIM;
-        }
-        else state = ST_NODE;
+        state = (int)(1u + (uint32_t)(cur >> (C32 ? 31 : 63)));   // ST_NODE, or ST_PRIM for a leaf reference (the primitive step works out the record address)
       }
       else result = 1;
     }
@@ -635,7 +633,7 @@ int cb200_refill_threshold()
   if(g_refill_threshold < 0)
   {
     const char *e = getenv("CB200_REFILL_THRESHOLD");
-    int v = e ? atoi(e) : 20;   // swept 4..32 on the 10 M-triangle bench: 16-20 is the flat optimum
+    int v = e ? atoi(e) : 24;   // swept 4..32 on the 10 M-triangle bench: 16-20 was the flat optimum with pool-sized waves, 24 with the ~20 M-ray waves of the larger pool (profiles/r3m)
     if(v < 1) v = 1;
     if(v > 32) v = 32;
     g_refill_threshold = v;
