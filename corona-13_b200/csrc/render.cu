@@ -2083,6 +2083,8 @@ int cb200_render_pass_stream(cb200_render_t *r, uint64_t first_index, uint64_t c
       TimeScope ts(r, st, KC_START, n_new);
       k_pixel_keys<<<(n_new + RB - 1)/RB, RB, 0, st>>>(r->dev, first_index + started, n_new, r->keys[0], r->order[0]);
       size_t tmp = r->sort_tmp_bytes;
+      // all 24 Morton bits: sorting only the upper 16 (16 x 16-pixel tiles left in index order inside, one radix pass less) costs the
+      // closest-hit kernel 9 % (86.2 -> 93.9 ms per 8 progressions), the upper 12 bits 31 %, the upper 8 44 % (profiles/r3o)
       CB_CUDA(cub::DeviceRadixSort::SortPairs(r->sort_tmp, tmp, r->keys[0], r->keys[1], r->order[0], r->order[1], (int)n_new, 0, 24, st));
       k_path_start<<<(n_new + RB - 1)/RB, RB, 0, st>>>(r->dev, first_index + started, n_new, r->order[1],
                                                         r->st[r->cur] + r->n_alive, r->rays[r->cur] + r->n_alive, nullptr,
