@@ -57,15 +57,15 @@ METRIC = "rays/s (closest-hit + shadow)"
 REFDIR = os.path.join(ROOT, "oracle", "_ref")
 
 
-NCU_SUMMARY = "profiles/r2m_k_intersect_ncu.json"
-NCU_COMMAND = ("ncu --set full --clock-control none --import-source on -k regex:k_intersect -s 40 -c 3 -o gpurun_out/r2m_k_intersect "
-               "python scripts/gpu_render_bench.py; python scripts/ncu_summary.py gpurun_out/r2m_k_intersect.ncu-rep profiles/r2m_k_intersect_ncu.json")
+NCU_SUMMARY = "profiles/r3k_k_intersect_ncu.json"
+NCU_COMMAND = ("BENCH_NO_WARM=1 ncu --set full --clock-control none --import-source on -k regex:k_intersect -s 3 -c 1 -o gpurun_out/r3k_k_intersect "
+               "python scripts/gpu_render_bench.py; python scripts/ncu_summary.py gpurun_out/r3k_k_intersect.ncu-rep profiles/r3k_k_intersect_ncu.json")
+NCU_RAYS_PER_LAUNCH = 18.0e6   # the captured launch: one streamed wave (new paths + survivors); 431 MB of 24-byte hit records written
 
 
 def ncu_traffic():
     """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel from the committed `ncu --set full` capture
-    of the same workload (profiles/r1h_k_intersect_ncu.json: the full ~8.3 M-ray waves among the captured launches); None when the
-    summary is not there"""
+    of the same workload (NCU_SUMMARY: one full streamed wave); None when the summary is not there"""
     p = os.path.join(ROOT, NCU_SUMMARY)
     try:
         rows = json.load(open(p))
@@ -502,7 +502,7 @@ def main():
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": WORKLOAD, "num_tris": scene.num_prims, "frame": [WIDTH, HEIGHT], "sampler": "ptdl", "pointsampler": "rand",
                    "paths_per_step_per_gpu": n_pass, "rays_per_path": total_rays / paths,
-                   "l2": "inputs larger than L2 (scene 0.8 GB, path pool 2.1 GB, ray/hit waves 0.5 GB per wave)",
+                   "l2": "inputs larger than L2 (scene 0.8 GB, path pool 17 GB, ray/hit streams 1.2 GB per wave)",
                    "parallelism": f"spp split over {world} GPU(s), one framebuffer reduce per progression" if world > 1 else "1 GPU",
                    "bvh": {"nodes": acc.num_nodes(), "depth": acc.depth(), "node_bytes": node_b, "prim_bytes": prim_b, "gpu_build_s": build_s}},
         "spp_per_s": args.steps * world / (ms_total * 1e-3), "paths_per_s": paths / (ms_total * 1e-3),
@@ -510,13 +510,13 @@ def main():
         "grays_per_s_rank0": {"closest_hit": stt["rays_closest"] / (ms_closest * 1e-3) / 1e9, "shadow": stt["rays_shadow"] / max(ms_shadow * 1e-3, 1e-12) / 1e9},
         "roofline": {"bound": "hbm", "kernel": "k_intersect (closest-hit traversal, all launches of the timed region, rank 0)",
                      "achieved": achieved, "peak": hbm, "unit": "GB/s", "frac": achieved / hbm, "peak_source": which, "traffic": traffic,
-                     "binding_limit": "issue slots (68 %) + L1 LSU wavefronts (75 %) at ~15 of 32 lanes per instruction (ncu: " + NCU_SUMMARY + "), not HBM: "
+                     "binding_limit": "L1 LSU wavefronts (81 %) + issue slots (65 %) at ~18 of 32 lanes per instruction (ncu: " + NCU_SUMMARY + "), not HBM: "
                                       "`bound`/`frac` follow SURVEY 8(d)'s algorithmic-byte definition (bytes a ray NEEDS from the tree / time), "
-                                      "`traffic` shows that almost all of them are served by L1/L2",
+                                      "`traffic` shows that almost all of them are served by L1/L2 (which is also why `frac` can approach or pass 1)",
                      "traffic_source": {"kind": "committed ncu --set full capture, not measured in this run", "file": traffic_src,
                                         "command": NCU_COMMAND} if traffic else None,
-                     "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum per ~8.3 M-ray launch: the ray and hit streams only" if traffic else None,
-                     "algorithmic_bytes_per_launch": bytes_per_ray * 8.3e6,
+                     "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum of one ~18 M-ray launch (a streamed wave): the ray and hit streams only" if traffic else None,
+                     "algorithmic_bytes_per_launch": bytes_per_ray * NCU_RAYS_PER_LAUNCH,
                      "bytes_per_ray": bytes_per_ray, "bytes_per_ray_formula": f"{n_node:.3f} nodes x {node_b} B + {n_prim:.3f} prims x {prim_b} B + 40 B ray + 24 B hit",
                      "nodes_per_ray": n_node, "prims_per_ray": n_prim,
                      "counters_definition": "ACCEL_DEBUG (qbvhmp.c:83-90): node tests with >= 1 child hit, primitive tests, per closest-hit ray; "
