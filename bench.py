@@ -57,9 +57,9 @@ METRIC = "rays/s (closest-hit + shadow)"
 REFDIR = os.path.join(ROOT, "oracle", "_ref")
 
 
-NCU_SUMMARY = "profiles/r3k_k_intersect_ncu.json"
-NCU_COMMAND = ("BENCH_NO_WARM=1 ncu --set full --clock-control none --import-source on -k regex:k_intersect -s 3 -c 1 -o gpurun_out/r3k_k_intersect "
-               "python scripts/gpu_render_bench.py; python scripts/ncu_summary.py gpurun_out/r3k_k_intersect.ncu-rep profiles/r3k_k_intersect_ncu.json")
+NCU_SUMMARY = "profiles/r3u_k_intersect_ncu.json"
+NCU_COMMAND = ("BENCH_NO_WARM=1 ncu --set full --clock-control none --import-source on -k regex:k_intersect -s 3 -c 1 -o gpurun_out/r3u_k_intersect "
+               "python scripts/gpu_render_bench.py; python scripts/ncu_summary.py gpurun_out/r3u_k_intersect.ncu-rep profiles/r3u_k_intersect_ncu.json")
 NCU_RAYS_PER_LAUNCH = 18.0e6   # the captured launch: one streamed wave (new paths + survivors); 431 MB of 24-byte hit records written
 
 
@@ -399,7 +399,7 @@ def main():
     red.clear()
     r.instrument(False, False)
     host_fb = torch.empty(HEIGHT, WIDTH, 3).pin_memory()
-    e2e_steps = max(2, min(args.steps, 16))
+    e2e_steps = max(2, min(args.steps, 64))   # like the device-timed loop: the final flush of the stragglers is inside the timing and amortised over the same number of steps
     L = lib.load()
     if world > 1 and rank == 0:
         red.host_mirror = host_fb     # the root's running sum is copied to the host after every accumulate, on the reducer's side stream
@@ -510,7 +510,7 @@ def main():
         "grays_per_s_rank0": {"closest_hit": stt["rays_closest"] / (ms_closest * 1e-3) / 1e9, "shadow": stt["rays_shadow"] / max(ms_shadow * 1e-3, 1e-12) / 1e9},
         "roofline": {"bound": "hbm", "kernel": "k_intersect (closest-hit traversal, all launches of the timed region, rank 0)",
                      "achieved": achieved, "peak": hbm, "unit": "GB/s", "frac": achieved / hbm, "peak_source": which, "traffic": traffic,
-                     "binding_limit": "L1 LSU wavefronts (81 %) + issue slots (65 %) at ~18 of 32 lanes per instruction (ncu: " + NCU_SUMMARY + "), not HBM: "
+                     "binding_limit": "L1 LSU wavefronts (79 %) + issue slots (66 %) at ~18 of 32 lanes per instruction (ncu: " + NCU_SUMMARY + "), not HBM: "
                                       "`bound`/`frac` follow SURVEY 8(d)'s algorithmic-byte definition (bytes a ray NEEDS from the tree / time), "
                                       "`traffic` shows that almost all of them are served by L1/L2 (which is also why `frac` can approach or pass 1)",
                      "traffic_source": {"kind": "committed ncu --set full capture, not measured in this run", "file": traffic_src,
