@@ -413,8 +413,12 @@ thread_local SmallSlot t_small;
 }
 
 template<typename OUT, typename LAUNCH>
-static int run_small(const cb_ray_t *rays, const float *max_dist, OUT *out, uint64_t n, LAUNCH launch)
+static int run_small(int device, const cb_ray_t *rays, const float *max_dist, OUT *out, uint64_t n, LAUNCH launch)
 {
+  // a worker thread that has never touched CUDA starts on device 0: follow the accel to the device it lives on
+  int cur = -1;
+  if(cudaGetDevice(&cur) != cudaSuccess) return CB200_ERR_CUDA;
+  if(cur != device && cudaSetDevice(device) != cudaSuccess) { g_error = "intersect_n: cannot select the accel's device"; return CB200_ERR_CUDA; }
   SmallSlot &s = t_small;
   int rc = s.prepare();
   if(rc) { g_error = "intersect_n: pinned slot allocation failed"; return rc; }
@@ -435,7 +439,7 @@ int cb200_accel_intersect_n(const cb200_accel_t *a, const cb_ray_t *rays, const 
   if(!a || (n && (!rays || !out))) { g_error = "accel_intersect_n: bad arguments"; return CB200_ERR_ARG; }
   if(n == 0) return 0;
   if(n <= SmallSlot::CAP)
-    return run_small<cb_hitrec_t>(rays, max_dist, out, n,
+    return run_small<cb_hitrec_t>(a->scene->device, rays, max_dist, out, n,
       [a](cb_ray_t *dr, float *dm, cb_hitrec_t *dout, uint64_t m, cudaStream_t s) { return cb200_launch_intersect(a, dr, dm, dout, m, s, nullptr); });
   return run_chunked<cb_hitrec_t>(rays, max_dist, out, n,
     [a](cb_ray_t *dr, float *dm, cb_hitrec_t *dout, uint64_t m, cudaStream_t s) { return cb200_launch_intersect(a, dr, dm, dout, m, s, nullptr); });
@@ -465,7 +469,7 @@ int cb200_accel_visible_n(const cb200_accel_t *a, const cb_ray_t *rays, const fl
   if(!a || (n && (!rays || !out || !max_dist))) { g_error = "accel_visible_n: bad arguments"; return CB200_ERR_ARG; }
   if(n == 0) return 0;
   if(n <= SmallSlot::CAP)
-    return run_small<int32_t>(rays, max_dist, out, n,
+    return run_small<int32_t>(a->scene->device, rays, max_dist, out, n,
       [a](cb_ray_t *dr, float *dm, int32_t *dout, uint64_t m, cudaStream_t s) { return cb200_launch_visible(a, dr, dm, dout, m, s); });
   return run_chunked<int32_t>(rays, max_dist, out, n,
     [a](cb_ray_t *dr, float *dm, int32_t *dout, uint64_t m, cudaStream_t s) { return cb200_launch_visible(a, dr, dm, dout, m, s); });

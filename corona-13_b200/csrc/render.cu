@@ -1339,6 +1339,8 @@ struct cb200_render
   float *maxd[2];                // sampled free-flight distance of every pending ray (scenes with media only), rides with rays[]
   cb_ray_t *nee_rays; float *nee_md; NeeRec *nee_recs; uint2 *nee_light; int32_t *nee_vis;
   NeeRec *em_recs;               // emission found by extension, queued by k_shade for k_nee_resolve
+  uint32_t nee_deferred;         // next-event records of small waves parked at the front of the nee arrays: their shadow sweep runs
+                                 // once, with the records of the following small waves, at the end of the call (render_collect)
   ShadeCounters *d_cnt, *h_cnt;
   cb_render_stats_t stats;
   // wave ordering by pixel (k_pixel_keys + radix sort)
@@ -1644,7 +1646,7 @@ cb200_render_t *cb200_render_create(cb200_accel_t *a, const cb_render_desc_t *de
   memset(&r->stats, 0, sizeof(r->stats));
   r->h_cnt = nullptr;
   r->timing = r->counting = 0; r->ev_used = 0; r->d_trav_cnt = nullptr;
-  r->n_alive = 0; r->cur = 0;
+  r->n_alive = 0; r->cur = 0; r->nee_deferred = 0;
   r->snap_stage = nullptr; r->snap_stream = nullptr; r->snap_pending = 0;
   r->own_stat = nullptr;
   r->tile_mode = 0; r->tile_ub = 0; r->tile_key2 = r->tile_idx2 = r->tile_offsets = nullptr; r->tile_tmp = nullptr; r->tile_tmp_bytes = 0; r->tile_bits = 0;
@@ -1761,6 +1763,7 @@ int cb200_render_clear(cb200_render_t *r, void *stream)
     r->tile_ub = 0;
   }
   r->n_alive = 0;   // paths still in flight are dropped with the image they belong to
+  r->nee_deferred = 0;
   memset(&r->stats, 0, sizeof(r->stats));
   return 0;
 }
@@ -1972,6 +1975,30 @@ extern "C" int cb200_render_set_accumulation(cb200_render_t *r, int mode)
 }
 extern "C" int cb200_render_accumulation(cb200_render_t *r) { return r && r->tile_mode ? CB200_ACCUM_TILES : CB200_ACCUM_ATOMIC; }
 
+#define DEFER_MAX (1u << 18)   // parked next-event records that trigger their shadow sweep
+
+// shadow sweep + splat of the parked next-event records
+static int resolve_deferred(cb200_render *r, cudaStream_t st)
+{
+  const uint32_t n_nee = r->nee_deferred;
+  r->nee_deferred = 0;
+  if(!n_nee) return 0;
+  int rc;
+  {
+    TimeScope ts(r, st, KC_SHADOW, n_nee);
+    rc = cb200_launch_shadow(r->accel, r->nee_rays, r->nee_md, r->nee_light, r->nee_vis, n_nee, st);
+  }
+  if(rc) return rc;
+  {
+    TimeScope ts(r, st, KC_RESOLVE, n_nee);
+    k_nee_resolve<<<(n_nee + RB - 1)/RB, RB, 0, st>>>(r->dev, n_nee, r->nee_recs, r->nee_vis, r->d_cnt);
+  }
+  cb200_count_launch(2); r->stats.kernel_launches += 2;
+  r->stats.rays_shadow += n_nee;
+  CB_CUDA(cudaGetLastError());
+  return 0;
+}
+
 // One wave of the pool: trace every path's pending ray, shade, trace and resolve the next-event rays.
 static int render_wave(cb200_render *r, uint32_t n, cudaStream_t st)
 {
@@ -1984,6 +2011,9 @@ static int render_wave(cb200_render *r, uint32_t n, cudaStream_t st)
   if(rc) return rc;
   r->stats.rays_closest += n; r->stats.kernel_launches++;
   CB_CUDA(cudaMemsetAsync(r->d_cnt, 0, 8*sizeof(unsigned long long), st));   // next, nee, hits[5], em (splats keeps counting)
+  // a wave that cannot fill the parked records' room up (every path makes at most one) runs its shadow sweep at once
+  if(r->nee_deferred && (uint64_t)r->nee_deferred + n > r->batch) { rc = resolve_deferred(r, st); if(rc) return rc; }
+  const uint32_t nd = r->nee_deferred;
   {
     TimeScope ts(r, st, KC_SHADE, n);
     if(r->dev.sky != CB_SKY_BLACK)
@@ -1995,7 +2025,7 @@ static int render_wave(cb200_render *r, uint32_t n, cudaStream_t st)
     k_compact_hits<<<(n + 255)/256, 256, 0, st>>>(r->dev, r->hits, n, (uint32_t)r->batch, r->hit_list, r->d_cnt, single);
     cb200_count_launch(); r->stats.kernel_launches++;
 #define SHADE_ARGS(K) (r->dev, n, r->st[cur], r->rays[cur], r->hits, r->st[cur^1], r->rays[cur^1], \
-      r->nee_rays, r->nee_md, r->nee_light, r->nee_recs, r->d_cnt, r->hit_list + (size_t)K*r->batch, K, r->maxd[cur^1], r->em_recs)
+      r->nee_rays + nd, r->nee_md + nd, r->nee_light + nd, r->nee_recs + nd, r->d_cnt, r->hit_list + (size_t)K*r->batch, K, r->maxd[cur^1], r->em_recs)
 #define SHADE_LAUNCH(K) do { if(r->dev.has_media) k_shade<(1 << K), true><<<(n + RB - 1)/RB, RB, 0, st>>>SHADE_ARGS(K); \
                              else k_shade<(1 << K), false><<<(n + RB - 1)/RB, RB, 0, st>>>SHADE_ARGS(K); \
                              cb200_count_launch(); r->stats.kernel_launches++; } while(0)
@@ -2014,27 +2044,18 @@ static int render_wave(cb200_render *r, uint32_t n, cudaStream_t st)
   CB_CUDA(cudaMemcpyAsync(r->h_cnt, r->d_cnt, sizeof(ShadeCounters), cudaMemcpyDeviceToHost, st));
   CB_CUDA(cudaStreamSynchronize(st));
   const uint32_t n_next = (uint32_t)r->h_cnt->next, n_nee = (uint32_t)(r->h_cnt->next >> 32), n_em = (uint32_t)r->h_cnt->em;   // next: two 32-bit counts
-  if(r->tile_mode) r->tile_ub = r->h_cnt->tile_count + n_nee + n_em;   // exact up to this wave's shading + at most one record per queued contribution
+  if(r->tile_mode) r->tile_ub = r->h_cnt->tile_count + nd + n_nee + n_em;   // exact up to this wave's shading + at most one record per queued (or parked) contribution
   if(n_em)
   { // emission found by extension (k_shade's queue): no visibility to wait for
     TimeScope ts(r, st, KC_RESOLVE, n_em);
     k_nee_resolve<<<(n_em + RB - 1)/RB, RB, 0, st>>>(r->dev, n_em, r->em_recs, nullptr, r->d_cnt);
     cb200_count_launch(); r->stats.kernel_launches++;
   }
-  if(n_nee)
-  {
-    {
-      TimeScope ts(r, st, KC_SHADOW, n_nee);
-      rc = cb200_launch_shadow(r->accel, r->nee_rays, r->nee_md, r->nee_light, r->nee_vis, n_nee, st);
-    }
-    if(rc) return rc;
-    {
-      TimeScope ts(r, st, KC_RESOLVE, n_nee);
-      k_nee_resolve<<<(n_nee + RB - 1)/RB, RB, 0, st>>>(r->dev, n_nee, r->nee_recs, r->nee_vis, r->d_cnt);
-    }
-    cb200_count_launch(2); r->stats.kernel_launches += 2;
-    r->stats.rays_shadow += n_nee;
-  }
+  // Small waves (the tail of a flush: ~22 waves of fewer than 100 k rays) only PARK their next-event records; one shadow sweep at
+  // the end of the call traces them together: a sweep of a few thousand rays costs the latency floor of its launch (~0.15 ms),
+  // and nothing waits for its answers but the framebuffer.
+  r->nee_deferred = nd + n_nee;
+  if(r->nee_deferred >= DEFER_MAX) { rc = resolve_deferred(r, st); if(rc) return rc; }
   r->n_alive = n_next;
   r->cur = cur ^ 1;
   // the list holds 4 waves' worth and the next wave adds at most 2 * batch records (one per path that finds an emitter, one per
@@ -2045,6 +2066,7 @@ static int render_wave(cb200_render *r, uint32_t n, cudaStream_t st)
 
 static int render_collect(cb200_render *r, cudaStream_t st)
 {
+  if(r->nee_deferred) { const int rc = resolve_deferred(r, st); if(rc) return rc; }
   if(r->tile_mode && r->tile_ub) { const int rc = tile_pass(r, st); if(rc) return rc; }
   CB_CUDA(cudaMemcpyAsync(r->h_cnt, r->d_cnt, sizeof(ShadeCounters), cudaMemcpyDeviceToHost, st));
   CB_CUDA(cudaStreamSynchronize(st));
