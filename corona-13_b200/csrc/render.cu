@@ -168,6 +168,7 @@ struct RenderDev
   uint32_t *tile_key, *tile_idx;   // 32x32 pixel tile of the sample / the record's own index (payload of the sort)
   unsigned int *tile_count;
   uint32_t tile_cap, tiles_x, tiles_y, tile_shift;
+  float force_scramble;            // > 0: path->tangent_frame_scrambling of every new path (known-answer entries only)
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -417,6 +418,7 @@ __device__ void path_start(const RenderDev &R, uint64_t index, PathState &s, V3 
   s.index_lo = (uint32_t)index; s.index_hi = (uint32_t)(index >> 32);
   uint32_t mt = 0;
   s.scramble = 0.1f + point_mt(P, index, mt++)*(0.9f - 0.1f);
+  if(R.force_scramble > 0.0f) s.scramble = R.force_scramble;
   s.lambda = 360.0f + (830.0f - 360.0f)*fmodf(point_dim(P, index, 2) + 0.0f, 1.0f);   // spectrum_sample_lambda
   const float exposure_time = C.exposure_time;
   s.time = point_dim(P, index, 3)*fminf(1.0f, exposure_time/(1.0f/30.0f));             // view_sample_time
@@ -2210,19 +2212,15 @@ int cb200_render_camera_rays(cb200_render_t *r, uint64_t first_index, uint64_t n
 
 } // extern "C"
 
-// Next-event samples of the FIRST hit vertex of path indices [first_index, first_index + n), for known-answer tests against the
-// reference's own nee_sample (oracle/ref_path.c): the same kernels as one wave of cb200_render_pass on a fresh pool -- camera
-// sample, closest hit, vertex preparation + next-event sample (k_shade), shadow sweep -- but the records are handed back
-// instead of being splatted.  out[k][16] = {pixel_i, pixel_j, lambda, value (throughput x mis weight), total_dist, light prim
-// (2 words, bit pattern), ray pos[3], ray dir[3], search limit, visible (1 / 0), path length at the splat}; *n_out records.
-int cb200_render_nee_records(cb200_render_t *r, uint64_t first_index, uint64_t n, float *out, uint64_t *n_out)
+// The first wave of path indices [first_index, first_index + n) on an empty pool, for the known-answer entries below: camera sample,
+// closest hit, vertex preparation + next-event sample + BSDF sample (k_shade) -- the same kernels as cb200_render_pass; what they
+// queue is left in the wave buffers instead of being traced / splatted.  scramble > 0 presets path->tangent_frame_scrambling.
+static int first_wave(cb200_render *r, uint64_t first_index, uint32_t m, float scramble, cudaStream_t st)
 {
-  if(!r || !out || !n_out || n == 0 || n > r->batch) { cb200_set_error("render_nee_records: bad arguments (0 < n <= batch_paths)"); return CB200_ERR_ARG; }
-  if(r->n_alive) { cb200_set_error("render_nee_records: paths in flight (flush first)"); return CB200_ERR_ARG; }
-  cudaStream_t st = 0;
   const int cur = r->cur;
-  const uint32_t m = (uint32_t)n;
+  r->dev.force_scramble = scramble;
   k_path_start<<<(m + RB - 1)/RB, RB, 0, st>>>(r->dev, first_index, m, nullptr, r->st[cur], r->rays[cur], nullptr, r->maxd[cur]);
+  r->dev.force_scramble = 0.0f;
   cb200_count_launch();
   int rc = cb200_launch_intersect(r->accel, r->rays[cur], r->maxd[cur], r->hits, m, st, nullptr);
   if(rc) return rc;
@@ -2242,9 +2240,21 @@ int cb200_render_nee_records(cb200_render_t *r, uint64_t first_index, uint64_t n
   cb200_count_launch(2);
   CB_CUDA(cudaMemcpyAsync(r->h_cnt, r->d_cnt, sizeof(ShadeCounters), cudaMemcpyDeviceToHost, st));
   CB_CUDA(cudaStreamSynchronize(st));
+  return 0;   // the survivors and the queued emission of this wave are dropped by the callers: the pool stays empty, the framebuffer untouched
+}
+
+// Next-event samples of the FIRST hit vertex of path indices [first_index, first_index + n), for known-answer tests against the
+// reference's own nee_sample (oracle/ref_path.c): out[k][16] = {pixel_i, pixel_j, lambda, value (throughput x mis weight), total_dist,
+// light prim (2 words, bit pattern), ray pos[3], ray dir[3], search limit, visible (1 / 0), path length at the splat}; *n_out records.
+int cb200_render_nee_records(cb200_render_t *r, uint64_t first_index, uint64_t n, float *out, uint64_t *n_out)
+{
+  if(!r || !out || !n_out || n == 0 || n > r->batch) { cb200_set_error("render_nee_records: bad arguments (0 < n <= batch_paths)"); return CB200_ERR_ARG; }
+  if(r->n_alive || r->nee_deferred) { cb200_set_error("render_nee_records: paths in flight (flush first)"); return CB200_ERR_ARG; }
+  cudaStream_t st = 0;
+  int rc = first_wave(r, first_index, (uint32_t)n, 0.0f, st);
+  if(rc) return rc;
   const uint32_t n_nee = (uint32_t)(r->h_cnt->next >> 32);
   *n_out = n_nee;
-  // the survivors and the queued emission of this wave are dropped: the pool stays empty, the framebuffer untouched
   if(!n_nee) return 0;
   rc = cb200_launch_shadow(r->accel, r->nee_rays, r->nee_md, r->nee_light, r->nee_vis, n_nee, st);
   if(rc) return rc;
@@ -2263,6 +2273,36 @@ int cb200_render_nee_records(cb200_render_t *r, uint64_t first_index, uint64_t n
     memcpy(o + 5, &recs[k].light_lo, 4); memcpy(o + 6, &recs[k].light_hi, 4);
     for(int c=0;c<3;c++) { o[7+c] = rays[k].pos[c]; o[10+c] = rays[k].dir[c]; }
     o[13] = md[k]; o[14] = (float)vis[k]; o[15] = (float)recs[k].len;
+  }
+  return 0;
+}
+
+// The paths that go on after their first hit vertex, as the first wave leaves them: the BSDF-sampled direction and everything
+// path_extend records for the next edge, plus the ray the next wave will trace.  out[k][16] = {pixel_i, pixel_j, lambda, omega[3]
+// (e[2].omega), ray pos[3] (prims_offset_ray applied), throughput into the next vertex, throughput into this one, bsdf pdf (projected
+// solid angle), |n . omega|, vertex position x[3]}; *n_out records.  tangent_frame_scrambling > 0 presets the path's scrambling
+// number (upstream draws it from the worker's twister) so that the reference harness can be run with the same one.
+int cb200_render_bounce_records(cb200_render_t *r, uint64_t first_index, uint64_t n, float tangent_frame_scrambling, float *out, uint64_t *n_out)
+{
+  if(!r || !out || !n_out || n == 0 || n > r->batch) { cb200_set_error("render_bounce_records: bad arguments (0 < n <= batch_paths)"); return CB200_ERR_ARG; }
+  if(r->n_alive || r->nee_deferred) { cb200_set_error("render_bounce_records: paths in flight (flush first)"); return CB200_ERR_ARG; }
+  cudaStream_t st = 0;
+  const int rc = first_wave(r, first_index, (uint32_t)n, tangent_frame_scrambling, st);
+  if(rc) return rc;
+  const uint32_t n_next = (uint32_t)r->h_cnt->next;
+  *n_out = n_next;
+  if(!n_next) return 0;
+  std::vector<PathState> stv(n_next);
+  std::vector<cb_ray_t> rays(n_next);
+  CB_CUDA(cudaMemcpy(stv.data(), r->st[r->cur^1], n_next*sizeof(PathState), cudaMemcpyDeviceToHost));
+  CB_CUDA(cudaMemcpy(rays.data(), r->rays[r->cur^1], n_next*sizeof(cb_ray_t), cudaMemcpyDeviceToHost));
+  for(uint32_t k=0;k<n_next;k++)
+  {
+    float *o = out + 16*(size_t)k;
+    const PathState &s = stv[k];
+    o[0] = s.pixel_i; o[1] = s.pixel_j; o[2] = s.lambda;
+    for(int c=0;c<3;c++) { o[3+c] = s.omega[c]; o[6+c] = rays[k].pos[c]; o[13+c] = s.x[c]; }
+    o[9] = s.thr; o[10] = s.thr_prev; o[11] = s.pdf_proj; o[12] = s.cos_prev;
   }
   return 0;
 }

@@ -236,6 +236,12 @@ int  cb200_render_camera_rays(cb200_render_t *r, uint64_t first_index, uint64_t 
  * out[k][16] = {pixel_i, pixel_j, lambda, throughput x mis weight, |light point - ray origin|, light prim (2 words, bit
  * pattern), shadow ray pos[3], dir[3], search limit, visible (1/0), path length at the splat}; *n_out = records written (<= n) */
 int  cb200_render_nee_records(cb200_render_t *r, uint64_t first_index, uint64_t n, float *out, uint64_t *n_out);
+/* the paths that go on behind their first hit vertex, as path_extend leaves them (src/pathspace.c:186-260: shader_sample of the
+ * BSDF with the vertex' own random dimensions, prims_offset_ray): out[k][16] = {pixel_i, pixel_j, lambda, e[2].omega[3], origin of
+ * the next ray[3], throughput into the next vertex, throughput into this one, bsdf pdf (projected solid angle), |n . omega|, vertex
+ * position[3]}.  tangent_frame_scrambling > 0 presets path->tangent_frame_scrambling (upstream draws it from the worker thread's
+ * twister, pathspace.c:212-213) so that a reference harness can run with the same number.  Same preconditions as above. */
+int  cb200_render_bounce_records(cb200_render_t *r, uint64_t first_index, uint64_t n, float tangent_frame_scrambling, float *out, uint64_t *n_out);
 
 /* the origin of the ray that leaves surface point x[i] in direction dir[i], as the integrator computes it: prims_offset_ray
  * (src/prims.c:374-388; 3 floats per point in, 3 out) */

@@ -9,6 +9,10 @@
  *   ref_path_camera(first, n, out)    for path index i: path_init + path_extend (pathspace.c:167-260: lambda, time, camera_sample
  *                                       of the thin lens, view_cam_init_frame, path_propagate -> accel_intersect)
  *   ref_path_offset(x, dir, prim, n, out)   prims_offset_ray (src/prims.c:374-388) on given hit points / directions
+ *   ref_path_bounce(first, n, scr, nee, out)   for path index i: path_init, tangent_frame_scrambling preset to `scr` (upstream draws it
+ *                                     from the worker's own twister, pathspace.c:212-213), path_extend to the first hit, optionally what
+ *                                     ptdl.c does there (nee_sample + path_pop, which folds four random dimensions into the vertex,
+ *                                     pathspace.c:298), then path_extend AGAIN: the BSDF-sampled direction, the second hit, pdf, throughput
  *   ref_path_nee(first, n, out)       for path index i: path_init + path_extend, then -- like sampler.d/ptdl.c:139-147 does at every
  *                                     vertex -- nee_sample (include/pathspace/nee.h:87-243: lights_pdf_type, the light list's
  *                                     sample_cdf + prims_sample, shader_brdf, path_G, path_visible) and the weight of
@@ -107,6 +111,42 @@ void ref_path_nee(uint64_t first, uint64_t n, float *out)
       o[8] = pe;
       o[9] = (float)our/(float)(other + our);
     }
+  }
+  free(p);
+}
+
+/* out: n rows of 20 floats:
+ *  0 pixel_i, 1 pixel_j, 2 lambda, 3 path->length after the first path_extend, 4 return value of the second path_extend (-1: not
+ *  called), 5 path->length after it, 6..8 e[2].omega, 9 e[2].dist, 10,11 v[2].hit.prim (bit pattern), 12..14 v[1].hit.x,
+ *  15 v[2].throughput, 16 v[2].pdf, 17 v[1].mode after sampling, 18 v[2].flags, 19 v[1].throughput */
+void ref_path_bounce(uint64_t first, uint64_t n, float scrambling, int with_nee, float *out)
+{
+  path_t *p = (path_t *)malloc(sizeof(path_t));
+  for(uint64_t i=0;i<n;i++)
+  {
+    float *o = out + 20*i;
+    memset(o, 0, 20*sizeof(float));
+    path_init(p, first + i, 0);
+    p->tangent_frame_scrambling = scrambling;
+    const int rc = path_extend(p);
+    o[0] = p->sensor.pixel_i; o[1] = p->sensor.pixel_j; o[2] = mf(p->lambda, 0);
+    o[3] = (float)p->length; o[4] = -1.0f;
+    if(rc || p->length != 2) continue;
+    o[19] = mf(p->v[1].throughput, 0);
+    if(with_nee)
+    { /* sampler.d/ptdl.c:136-148 */
+      if(nee_sample(p)) continue;
+      path_pop(p);
+    }
+    const int r2 = path_extend(p);
+    o[4] = (float)r2; o[5] = (float)p->length;
+    for(int k=0;k<3;k++) o[12+k] = p->v[1].hit.x[k];
+    o[17] = (float)p->v[1].mode;
+    if(p->length < 3) continue;
+    for(int k=0;k<3;k++) o[6+k] = p->e[2].omega[k];
+    o[9] = p->e[2].dist;
+    memcpy(o + 10, &p->v[2].hit.prim, 8);
+    o[15] = mf(p->v[2].throughput, 0); o[16] = mf(p->v[2].pdf, 0); o[18] = (float)p->v[2].flags;
   }
   free(p);
 }

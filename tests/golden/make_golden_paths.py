@@ -25,6 +25,9 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 CASES = ["c10", "motion"]
 NEE_CASES = ["c10", "motion", "glass_metal", "sphere_light", "sky_light", "envmap"]   # next-event samples at the first hit vertex (ref_path_nee)
 N_NEE = 6000
+BOUNCE_CASES = ["c10", "glass_metal", "motion", "sphere_light"]   # the second path_extend (ref_path_bounce), pt and ptdl bookkeeping
+N_BOUNCE = 4000
+SCRAMBLING = 0.5
 N_LOW = 6000
 SPECIAL = [2**24 - 8, 2**31 - 8, 2**32 - 8, 2**32 + 5, 2**33 + 12345, 123456789012]   # 32-bit clipping of the Halton index, wide indices
 
@@ -50,6 +53,16 @@ def worker(case, out):
         L.ref_path_nee.argtypes = [C.c_uint64, C.c_uint64, C.c_void_p]
         L.ref_path_nee(0, N_NEE, nee.ctypes.data)
         np.savez(out, nee=nee)
+        sys.stdout.flush()
+        os._exit(0)
+    if case.startswith("bounce:"):
+        L.ref_path_bounce.argtypes = [C.c_uint64, C.c_uint64, C.c_float, C.c_int, C.c_void_p]
+        res = {}
+        for name, with_nee in (("pt", 0), ("ptdl", 1)):
+            b = np.zeros((N_BOUNCE, 20), np.float32)
+            L.ref_path_bounce(0, N_BOUNCE, SCRAMBLING, with_nee, b.ctypes.data)
+            res[name] = b
+        np.savez(out, **res)
         sys.stdout.flush()
         os._exit(0)
     idx = indices()
@@ -100,5 +113,16 @@ if __name__ == "__main__":
         sky = lit & (nee[:, 10:12].view("u4") == 0xffffffff).all(axis=1)
         print(case, "nee: first hits", int((nee[:, 3] == 2).sum()), "nee_sample called", int(called.sum()), "contributing", int(lit.sum()), "of them sky", int(sky.sum()),
               "mean weight", float(nee[lit, 9].mean()) if lit.any() else 0.0)
+    for case in BOUNCE_CASES:
+        tmp = tempfile.mktemp(suffix=".npz")
+        env = dict(os.environ, LD_LIBRARY_PATH=os.path.join(REFDIR, "shaders") + ":" + os.environ.get("LD_LIBRARY_PATH", ""))
+        subprocess.run([sys.executable, os.path.abspath(__file__), "bounce:" + case, tmp], check=True, stdout=subprocess.DEVNULL, env=env)
+        z = np.load(tmp)
+        for name in ("pt", "ptdl"):
+            b = z[name]
+            out[f"{case}_bounce_{name}"] = b
+            print(case, name, "bounce: first hits", int((b[:, 3] == 2).sum()), "second extend called", int((b[:, 4] != -1).sum()), "went on", int((b[:, 5] == 3).sum()),
+                  "second vertex on geometry", int(((b[:, 5] == 3) & ~(b[:, 10:12].view("u4") == 0xffffffff).all(axis=1)).sum()))
+        os.remove(tmp)
     np.savez_compressed(os.path.join(HERE, "paths.npz"), **out)
     print("wrote paths.npz", os.path.getsize(os.path.join(HERE, "paths.npz")) // 1024, "KiB")
