@@ -23,7 +23,7 @@ sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 CASES = ["c10", "motion"]
-NEE_CASES = ["c10", "motion", "glass_metal", "sphere_light", "sky_light", "envmap"]   # next-event samples at the first hit vertex (ref_path_nee)
+NEE_CASES = ["c10", "motion", "glass_metal", "sphere_light", "sky_light", "envmap", "fog", "subsurf", "skin"]   # next-event samples at the first hit vertex (ref_path_nee)
 N_NEE = 6000
 BOUNCE_CASES = ["c10", "glass_metal", "motion", "sphere_light", "fog", "subsurf", "skin", "vstack"]   # the second path_extend (ref_path_bounce), pt and ptdl bookkeeping
 N_BOUNCE = 4000
