@@ -2215,13 +2215,16 @@ int cb200_render_camera_rays(cb200_render_t *r, uint64_t first_index, uint64_t n
 // The first wave of path indices [first_index, first_index + n) on an empty pool, for the known-answer entries below: camera sample,
 // closest hit, vertex preparation + next-event sample + BSDF sample (k_shade) -- the same kernels as cb200_render_pass; what they
 // queue is left in the wave buffers instead of being traced / splatted.  scramble > 0 presets path->tangent_frame_scrambling.
-static int first_wave(cb200_render *r, uint64_t first_index, uint32_t m, float scramble, cudaStream_t st)
+static int first_wave(cb200_render *r, uint64_t first_index, uint32_t m, float scramble, cudaStream_t st, int cur = -1)
 {
-  const int cur = r->cur;
-  r->dev.force_scramble = scramble;
-  k_path_start<<<(m + RB - 1)/RB, RB, 0, st>>>(r->dev, first_index, m, nullptr, r->st[cur], r->rays[cur], nullptr, r->maxd[cur]);
-  r->dev.force_scramble = 0.0f;
-  cb200_count_launch();
+  if(cur < 0)
+  {
+    cur = r->cur;
+    r->dev.force_scramble = scramble;
+    k_path_start<<<(m + RB - 1)/RB, RB, 0, st>>>(r->dev, first_index, m, nullptr, r->st[cur], r->rays[cur], nullptr, r->maxd[cur]);
+    r->dev.force_scramble = 0.0f;
+    cb200_count_launch();
+  }   // else: the wave behind it -- the survivors the previous call left in the buffers of side `cur`
   int rc = cb200_launch_intersect(r->accel, r->rays[cur], r->maxd[cur], r->hits, m, st, nullptr);
   if(rc) return rc;
   CB_CUDA(cudaMemsetAsync(r->d_cnt, 0, 8*sizeof(unsigned long long), st));
@@ -2303,6 +2306,40 @@ int cb200_render_bounce_records(cb200_render_t *r, uint64_t first_index, uint64_
     o[0] = s.pixel_i; o[1] = s.pixel_j; o[2] = s.lambda;
     for(int c=0;c<3;c++) { o[3+c] = s.omega[c]; o[6+c] = rays[k].pos[c]; o[13+c] = s.x[c]; }
     o[9] = s.thr; o[10] = s.thr_prev; o[11] = s.pdf_proj; o[12] = s.cos_prev;
+  }
+  return 0;
+}
+
+// Emission found by EXTENSION, as the sampler would splat it: wave == 1: emitters (and nothing else) the camera sees directly
+// (weight 1); wave == 2: emitters the first BSDF-sampled edge ends on, weighted against next-event estimation (ptdl.c:124-131,
+// sampler_mis :78-88; pt.c: weight 1).  out[k][8] = {pixel_i, pixel_j, lambda, value (throughput x emission x mis weight), path
+// length at the splat, 0, 0, 0}; *n_out records.  Same preconditions and scrambling preset as cb200_render_bounce_records.
+int cb200_render_emission_records(cb200_render_t *r, uint64_t first_index, uint64_t n, float tangent_frame_scrambling, int32_t wave,
+                                  float *out, uint64_t *n_out)
+{
+  if(!r || !out || !n_out || n == 0 || n > r->batch || wave < 1 || wave > 2) { cb200_set_error("render_emission_records: bad arguments (0 < n <= batch_paths, wave 1 or 2)"); return CB200_ERR_ARG; }
+  if(r->n_alive || r->nee_deferred) { cb200_set_error("render_emission_records: paths in flight (flush first)"); return CB200_ERR_ARG; }
+  cudaStream_t st = 0;
+  int rc = first_wave(r, first_index, (uint32_t)n, tangent_frame_scrambling, st);
+  if(rc) return rc;
+  if(wave == 2)
+  {
+    const uint32_t n_next = (uint32_t)r->h_cnt->next;
+    *n_out = 0;
+    if(!n_next) return 0;
+    rc = first_wave(r, 0, n_next, 0.0f, st, r->cur ^ 1);
+    if(rc) return rc;
+  }
+  const uint32_t n_em = (uint32_t)r->h_cnt->em;
+  *n_out = n_em;
+  if(!n_em) return 0;
+  std::vector<NeeRec> recs(n_em);
+  CB_CUDA(cudaMemcpy(recs.data(), r->em_recs, n_em*sizeof(NeeRec), cudaMemcpyDeviceToHost));
+  for(uint32_t k=0;k<n_em;k++)
+  {
+    float *o = out + 8*(size_t)k;
+    o[0] = recs[k].pixel_i; o[1] = recs[k].pixel_j; o[2] = recs[k].lambda; o[3] = recs[k].value; o[4] = (float)recs[k].len;
+    o[5] = o[6] = o[7] = 0.0f;
   }
   return 0;
 }

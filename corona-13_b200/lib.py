@@ -275,6 +275,7 @@ def _load_render():
     L.cb200_render_offset_ray.argtypes = [vp, vp, vp, vp, u64]
     L.cb200_render_nee_records.argtypes = [vp, u64, u64, vp, vp]
     L.cb200_render_bounce_records.argtypes = [vp, u64, u64, C.c_float, vp, vp]
+    L.cb200_render_emission_records.argtypes = [vp, u64, u64, C.c_float, C.c_int32, vp, vp]
     L.cb200_render_bsdf.argtypes = [vp, C.c_int32, vp, vp, u64]
     L.cb200_render_medium.argtypes = [vp, C.c_int32, vp, vp, u64]
     L._render_ready = True
@@ -283,7 +284,7 @@ def _load_render():
 
 RENDER_SYMBOLS = ["cb200_render_create", "cb200_render_destroy", "cb200_render_pass", "cb200_render_pass_stream", "cb200_render_flush", "cb200_render_clear", "cb200_render_instrument",
                   "cb200_render_fb_device", "cb200_render_set_framebuffer", "cb200_render_download", "cb200_render_snapshot", "cb200_render_snapshot_async", "cb200_render_snapshot_wait", "cb200_render_stats", "cb200_render_point",
-                  "cb200_render_camera_rays", "cb200_render_offset_ray", "cb200_render_nee_records", "cb200_render_bounce_records", "cb200_render_bsdf", "cb200_render_medium",
+                  "cb200_render_camera_rays", "cb200_render_offset_ray", "cb200_render_nee_records", "cb200_render_bounce_records", "cb200_render_emission_records", "cb200_render_bsdf", "cb200_render_medium",
                   "cb200_render_set_dbor", "cb200_render_num_dbors", "cb200_render_dbor_device", "cb200_render_download_dbor",
                   "cb200_render_path_stats", "cb200_render_get_path_stats", "cb200_render_set_accumulation", "cb200_render_accumulation",
                   "cb200_comm_unique_id", "cb200_reducer_create", "cb200_reducer_destroy", "cb200_reducer_begin", "cb200_reducer_end",
@@ -470,6 +471,13 @@ class Render:
         out = np.zeros((n, 16), np.float32)
         m = C.c_uint64(0)
         _check(self.L.cb200_render_bounce_records(self.r, first, n, scrambling, _ptr(out), C.byref(m)), "cb200_render_bounce_records")
+        return out[:m.value]
+
+    def emission_records(self, first, n, wave, scrambling=0.5):
+        """emission found by extension at the first (wave 1) / second (wave 2) vertex: (m, 8) float32 rows, see the header"""
+        out = np.zeros((n, 8), np.float32)
+        m = C.c_uint64(0)
+        _check(self.L.cb200_render_emission_records(self.r, first, n, scrambling, wave, _ptr(out), C.byref(m)), "cb200_render_emission_records")
         return out[:m.value]
 
     def offset_ray(self, x, direction):

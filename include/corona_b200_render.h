@@ -242,6 +242,11 @@ int  cb200_render_nee_records(cb200_render_t *r, uint64_t first_index, uint64_t 
  * position[3]}.  tangent_frame_scrambling > 0 presets path->tangent_frame_scrambling (upstream draws it from the worker thread's
  * twister, pathspace.c:212-213) so that a reference harness can run with the same number.  Same preconditions as above. */
 int  cb200_render_bounce_records(cb200_render_t *r, uint64_t first_index, uint64_t n, float tangent_frame_scrambling, float *out, uint64_t *n_out);
+/* emission found by extension as the sampler splats it (pt.c:44-50, ptdl.c:124-131 with sampler_mis :78-88): wave 1 = emitters the
+ * camera sees directly, wave 2 = emitters the first BSDF-sampled edge ends on, weighted against next-event estimation;
+ * out[k][8] = {pixel_i, pixel_j, lambda, throughput x emission x mis weight, path length at the splat, 0, 0, 0} */
+int  cb200_render_emission_records(cb200_render_t *r, uint64_t first_index, uint64_t n, float tangent_frame_scrambling, int32_t wave,
+                                   float *out, uint64_t *n_out);
 
 /* the origin of the ray that leaves surface point x[i] in direction dir[i], as the integrator computes it: prims_offset_ray
  * (src/prims.c:374-388; 3 floats per point in, 3 out) */

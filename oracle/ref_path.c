@@ -150,3 +150,48 @@ void ref_path_bounce(uint64_t first, uint64_t n, float scrambling, int with_nee,
   }
   free(p);
 }
+
+/* sampler.d/ptdl.c's (or pt.c's) loop up to the second vertex, recording what it would splat for emission found by EXTENSION:
+ * out: n rows of 8 floats: 0 pixel_i, 1 pixel_j, 2 lambda, 3 value at v[1] (throughput x weight; 0: not an emitter), 4 value at v[2],
+ * 5 mis weight at v[2], 6 path->length at the end, 7 v[2].pdf */
+static float ref_mis(const path_t *p, const float pdf, const float pdf2)
+{ /* sampler_mis (static in ptdl.c:78-88), one wavelength */
+  double pdf_path = 1.0;
+  for(int v=1;v<p->length-1;v++) pdf_path *= (double)mf(p->v[v].pdf, 0);
+  const double our = (double)pdf*pdf_path, other = (double)pdf2*pdf_path;
+  return (float)our/(float)(other + our);
+}
+void ref_path_emission(uint64_t first, uint64_t n, float scrambling, int ptdl, float *out)
+{
+  path_t *p = (path_t *)malloc(sizeof(path_t));
+  for(uint64_t i=0;i<n;i++)
+  {
+    float *o = out + 8*i;
+    memset(o, 0, 8*sizeof(float));
+    path_init(p, first + i, 0);
+    p->tangent_frame_scrambling = scrambling;
+    const int rc = path_extend(p);
+    o[0] = p->sensor.pixel_i; o[1] = p->sensor.pixel_j; o[2] = mf(p->lambda, 0); o[6] = (float)p->length;
+    if(rc) continue;
+    int v = p->length - 1;
+    if(p->v[v].mode & s_emit)
+    { /* ptdl.c:124-127 / pt.c:44-47 (pt's sampler_mis is 1 for a single technique) */
+      const float w = ptdl ? ref_mis(p, mf(p->v[v].pdf, 0), mf(nee_pdf(p, v), 0)) : 1.0f;
+      o[3] = mf(path_throughput(p), 0)*w;
+    }
+    if(ptdl)
+    {
+      if(nee_sample(p)) continue;
+      path_pop(p);
+    }
+    if(path_extend(p)) { o[6] = (float)p->length; continue; }
+    v = p->length - 1;
+    o[6] = (float)p->length; o[7] = mf(p->v[v].pdf, 0);
+    if(p->v[v].mode & s_emit)
+    {
+      const float w = ptdl ? ref_mis(p, mf(p->v[v].pdf, 0), mf(nee_pdf(p, v), 0)) : 1.0f;
+      o[4] = mf(path_throughput(p), 0)*w; o[5] = w;
+    }
+  }
+  free(p);
+}

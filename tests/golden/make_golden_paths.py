@@ -27,6 +27,8 @@ NEE_CASES = ["c10", "motion", "glass_metal", "sphere_light", "sky_light", "envma
 N_NEE = 6000
 BOUNCE_CASES = ["c10", "glass_metal", "motion", "sphere_light", "fog", "subsurf", "skin", "vstack"]   # the second path_extend (ref_path_bounce), pt and ptdl bookkeeping
 N_BOUNCE = 4000
+EMISSION_CASES = ["c10", "glass_metal", "motion", "sphere_light"]   # what the samplers splat for emission found by extension (ref_path_emission)
+N_EMISSION = 20000
 SCRAMBLING = 0.5
 N_LOW = 6000
 SPECIAL = [2**24 - 8, 2**31 - 8, 2**32 - 8, 2**32 + 5, 2**33 + 12345, 123456789012]   # 32-bit clipping of the Halton index, wide indices
@@ -62,6 +64,17 @@ def worker(case, out):
             b = np.zeros((N_BOUNCE, 20), np.float32)
             L.ref_path_bounce(0, N_BOUNCE, SCRAMBLING, with_nee, b.ctypes.data)
             res[name] = b
+        np.savez(out, **res)
+        sys.stdout.flush()
+        os._exit(0)
+    if case.startswith("emission:"):
+        L.ref_path_emission.argtypes = [C.c_uint64, C.c_uint64, C.c_float, C.c_int, C.c_void_p]
+        res = {}
+        for name, ptdl in (("pt", 0), ("ptdl", 1)):
+            b = np.zeros((N_EMISSION, 8), np.float32)
+            L.ref_path_emission(0, N_EMISSION, SCRAMBLING, ptdl, b.ctypes.data)
+            keep = (b[:, 3] > 0) | (b[:, 4] > 0)          # only the paths that found an emitter
+            res[name] = b[keep]
         np.savez(out, **res)
         sys.stdout.flush()
         os._exit(0)
@@ -123,6 +136,17 @@ if __name__ == "__main__":
             out[f"{case}_bounce_{name}"] = b
             print(case, name, "bounce: first hits", int((b[:, 3] == 2).sum()), "second extend called", int((b[:, 4] != -1).sum()), "went on", int((b[:, 5] == 3).sum()),
                   "second vertex on geometry", int(((b[:, 5] == 3) & ~(b[:, 10:12].view("u4") == 0xffffffff).all(axis=1)).sum()))
+        os.remove(tmp)
+    for case in EMISSION_CASES:
+        tmp = tempfile.mktemp(suffix=".npz")
+        env = dict(os.environ, LD_LIBRARY_PATH=os.path.join(REFDIR, "shaders") + ":" + os.environ.get("LD_LIBRARY_PATH", ""))
+        subprocess.run([sys.executable, os.path.abspath(__file__), "emission:" + case, tmp], check=True, stdout=subprocess.DEVNULL, env=env)
+        z = np.load(tmp)
+        for name in ("pt", "ptdl"):
+            b = z[name]
+            out[f"{case}_emission_{name}"] = b
+            print(case, name, "emission by extension: at the first vertex", int((b[:, 3] > 0).sum()), "at the second", int((b[:, 4] > 0).sum()),
+                  "mean mis weight there", float(b[b[:, 4] > 0, 5].mean()) if (b[:, 4] > 0).any() else 0.0)
         os.remove(tmp)
     np.savez_compressed(os.path.join(HERE, "paths.npz"), **out)
     print("wrote paths.npz", os.path.getsize(os.path.join(HERE, "paths.npz")) // 1024, "KiB")

@@ -204,3 +204,51 @@ def test_second_path_extend_matches_the_reference(gpu, case, mode):
     # throughput: the rgb2spec evaluations of the surface colour carry the reference's approximate rsqrt (see the next-event test)
     assert np.median(np.abs(rel)) < 1e-4 and (np.abs(rel) > 1e-3).mean() < 0.08, (np.median(np.abs(rel)), (np.abs(rel) > 1e-3).mean())
     assert abs((rel*val).sum())/val.sum() < 1e-4
+
+
+@pytest.mark.parametrize("case", ["c10", "glass_metal", "motion", "sphere_light"])
+@pytest.mark.parametrize("mode", ["pt", "ptdl"])
+def test_emission_found_by_extension_matches_the_reference(gpu, case, mode):
+    """Rows a20 / a21 / a23 at vertex level: what the reference's own sampler loop would splat for emitters a path reaches by
+    EXTENSION (oracle/ref_path.c: ref_path_emission -- pt.c:44-47 / ptdl.c:124-131 up to the second vertex: path_throughput x
+    sampler_mis(v.pdf, nee_pdf), i.e. lights_eval_vertex, lights_pdf_next_event, path_pdf_extend) for 20 000 path indices against
+    the emission records k_shade queues in its first and second wave (cb200_render_emission_records): the same paths find an
+    emitter, with the same value (weight 1 where the camera sees the emitter and in pt, the balance heuristic against next-event
+    estimation at the second vertex in ptdl)."""
+    z = np.load(os.path.join(GOLDEN, "paths.npz"))
+    want = z[f"{case}_emission_{mode}"]
+    g = GoldenImage(case)
+    acc = gpu.Accel(g.scene).build()
+    r = gpu.Render(acc, g.camera, g.materials, g.w, g.h, frame=1, **g.sky_args, **GoldenImage.variant_args(mode + "_halton"))
+    got = [r.emission_records(0, 20000, wave, 0.5) for wave in (1, 2)]
+    if os.environ.get("CB200_DUMP_NEE"):
+        for wave in (1, 2):
+            np.save(os.path.join(os.environ["CB200_DUMP_NEE"], f"emission_{case}_{mode}_{wave}.npy"), got[wave - 1])
+    r.close()
+    acc.close()
+    key = lambda a: [tuple(x) for x in np.ascontiguousarray(a[:, :3]).view("u4")]
+    total = 0
+    for wave, col in ((1, 3), (2, 4)):
+        rec = {k: row for k, row in zip(key(got[wave - 1]), got[wave - 1])}
+        assert len(rec) == len(got[wave - 1])
+        assert (got[wave - 1][:, 4] == wave + 1).all(), "path length at the splat"
+        lit = want[want[:, col] > 0]
+        missing, rel = 0, []
+        for k, w in zip(key(lit), lit):
+            q = rec.get(k)
+            if q is None:
+                missing += 1
+                continue
+            rel.append(q[3]/w[col] - 1.0)
+        ref_keys = set(key(lit))
+        extra = sum(1 for k in rec if k not in ref_keys)
+        rel = np.abs(np.array(rel, np.float64))
+        print(f"{case}/{mode} vertex {wave}: {len(lit)} emitters found by the reference, {missing} without a record here, {extra} records the reference has not; "
+              + (f"value median rel. error {np.median(rel):.1e}, 99 % {np.quantile(rel, 0.99):.1e}" if len(rel) else "no values"))
+        # first / second hits differ from the reference's on a few grazing rays; the light's colour goes through rgb2spec (approximate
+        # rsqrt upstream, see the next-event test)
+        assert missing <= 0.02*len(lit) + 2 and extra <= 0.02*len(lit) + 2, (missing, extra)
+        if len(rel):
+            assert np.median(rel) < 2e-4 and np.quantile(rel, 0.95) < 2e-3, (np.median(rel), np.quantile(rel, 0.95))
+        total += len(rel)
+    assert total > 150
