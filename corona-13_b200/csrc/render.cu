@@ -752,10 +752,12 @@ __device__ __forceinline__ V3 sky_sample(const RenderDev &R, float x1, float x2,
 // A path whose ray left the scene under a non-black sky gets an environment vertex: emission with the sampler's weight, then
 // the path ends (path_propagate pathspace.c:856-873, path_extend / nee_sample refuse to continue :196 / nee.h:91).
 __global__ void __launch_bounds__(RB)
-k_sky_miss(RenderDev R, uint32_t n, const PathState *__restrict__ st, const cb_hitrec_t *__restrict__ hits, ShadeCounters *cnt)
+k_sky_miss(RenderDev R, uint32_t n, const PathState *__restrict__ st, const cb_hitrec_t *__restrict__ hits, ShadeCounters *cnt,
+           NeeRec *__restrict__ em_recs)
 {
   const uint32_t i = blockIdx.x*blockDim.x + threadIdx.x;
-  bool did = false;
+  NeeRec e;
+  e.value = 0.0f;
   if(i < n)
   {
     const uint2 p = *reinterpret_cast<const uint2 *>(hits + i);
@@ -784,12 +786,23 @@ k_sky_miss(RenderDev R, uint32_t n, const PathState *__restrict__ st, const cb_h
         }
         if(!pp_contributes(pp, pdf_v, pdf_nee)) w = 0.0f;   // sampler_mis in float range only (PathPdf)
         if(R.sampler == CB_SAMPLER_PTNEE) w = lre_length(s.lre) + 1 == 2 ? 1.0f : 0.0f;   // ptnee.c:53-58: only the directly visible sky
-        did = splat(R, s.pixel_i, s.pixel_j, s.lambda, (s.thr*em)*w, lre_length(s.lre) + 1);   // lights_eval_vertex: isotropic for the envmap (list.c:272-273)
+        // queued like the emission k_shade finds on surfaces: k_nee_resolve is the one kernel that splats
+        e.value = (s.thr*em)*w;   // lights_eval_vertex: isotropic for the envmap (list.c:272-273)
+        e.lambda = s.lambda; e.pixel_i = s.pixel_i; e.pixel_j = s.pixel_j; e.total_dist = 0.0f;
+        e.light_lo = e.light_hi = 0xffffffffu; e.len = (uint32_t)(lre_length(s.lre) + 1);
       }
     }
   }
-  const uint32_t m = __ballot_sync(0xffffffffu, did);
-  if(m && (threadIdx.x & 31u) == 0) atomicAdd(&cnt->splats, (unsigned long long)__popc(m));
+  const bool have = e.value > 0.0f && e.value < FLT_MAX;      // view_splat's own acceptance test (view.c:457-459)
+  const uint32_t m = __ballot_sync(0xffffffffu, have);
+  if(m)
+  {
+    const uint32_t lane = threadIdx.x & 31u;
+    unsigned long long base = 0;
+    if(lane == (uint32_t)(__ffs(m) - 1)) base = atomicAdd(&cnt->em, (unsigned long long)__popc(m));
+    base = __shfl_sync(0xffffffffu, base, __ffs(m) - 1);
+    if(have) em_recs[base + __popc(m & ((1u << lane) - 1u))] = e;
+  }
 }
 
 // Paths whose ray escaped into the (black) sky have nothing left to do (pathspace.c:856-873): the shading kernel only runs
@@ -2044,7 +2057,7 @@ static int render_wave(cb200_render *r, uint32_t n, cudaStream_t st)
     TimeScope ts(r, st, KC_SHADE, n);
     if(r->dev.sky != CB_SKY_BLACK)
     {
-      k_sky_miss<<<(n + RB - 1)/RB, RB, 0, st>>>(r->dev, n, r->st[cur], r->hits, r->d_cnt);
+      k_sky_miss<<<(n + RB - 1)/RB, RB, 0, st>>>(r->dev, n, r->st[cur], r->hits, r->d_cnt, r->em_recs);
       cb200_count_launch(); r->stats.kernel_launches++;
     }
     const int single = r->dev.has_media ? -1 : (r->bsdf_kinds == 1) ? 0 : (r->bsdf_kinds == 2) ? 1 : (r->bsdf_kinds == 4) ? 2 : (r->bsdf_kinds == 8) ? 3 : -1;
@@ -2253,6 +2266,7 @@ static int first_wave(cb200_render *r, uint64_t first_index, uint32_t m, float s
   if(rc) return rc;
   CB_CUDA(cudaMemsetAsync(r->d_cnt, 0, 8*sizeof(unsigned long long), st));
   const int single = r->dev.has_media ? -1 : (r->bsdf_kinds == 1) ? 0 : (r->bsdf_kinds == 2) ? 1 : (r->bsdf_kinds == 4) ? 2 : (r->bsdf_kinds == 8) ? 3 : -1;
+  if(r->dev.sky != CB_SKY_BLACK) { k_sky_miss<<<(m + RB - 1)/RB, RB, 0, st>>>(r->dev, m, r->st[cur], r->hits, r->d_cnt, r->em_recs); cb200_count_launch(); }
   k_compact_hits<<<(m + 255)/256, 256, 0, st>>>(r->dev, r->hits, m, (uint32_t)r->batch, r->hit_list, r->d_cnt, single);
 #define NEE_SHADE(K, MED) k_shade<(1 << K), MED><<<(m + RB - 1)/RB, RB, 0, st>>>(r->dev, m, r->st[cur], r->rays[cur], r->hits, r->st[cur^1], r->rays[cur^1], \
       r->nee_rays, r->nee_md, r->nee_light, r->nee_recs, r->d_cnt, r->hit_list + (size_t)K*r->batch, K, r->maxd[cur^1], r->em_recs)

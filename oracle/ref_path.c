@@ -98,11 +98,12 @@ void ref_path_nee(uint64_t first, uint64_t n, float *out)
     const int v2 = p->length - 1;
     const float thr = mf(path_throughput(p), 0);
     o[6] = thr; o[7] = mf(p->v[v2].pdf, 0); o[19] = (float)p->v[v2].mode;
-    memcpy(o + 10, &p->v[v2].hit.prim, 8);
-    for(int k=0;k<3;k++) { o[12+k] = p->v[v2].hit.x[k]; o[15+k] = p->e[v2].omega[k]; }
-    o[18] = p->e[v2].dist;
     if(thr > 0.0f && (p->v[v2].mode & s_emit))
-    { /* sampler_mis (static in ptdl.c:78-88), one wavelength: both pdfs times the product of v[1..length-2].pdf in double, back
+    { /* (a failed nee_sample leaves parts of v[2] / e[2] as the previous path left them: only contributing samples are recorded) */
+      memcpy(o + 10, &p->v[v2].hit.prim, 8);
+      for(int k=0;k<3;k++) { o[12+k] = p->v[v2].hit.x[k]; o[15+k] = p->e[v2].omega[k]; }
+      o[18] = p->e[v2].dist;
+      /* sampler_mis (static in ptdl.c:78-88), one wavelength: both pdfs times the product of v[1..length-2].pdf in double, back
        * to float, our / (other + our) */
       const float pe = mf(path_pdf_extend(p, v2), 0);
       double pdf_path = 1.0;

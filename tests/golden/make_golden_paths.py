@@ -27,7 +27,7 @@ NEE_CASES = ["c10", "motion", "glass_metal", "sphere_light", "sky_light", "envma
 N_NEE = 6000
 BOUNCE_CASES = ["c10", "glass_metal", "motion", "sphere_light", "fog", "subsurf", "skin", "vstack"]   # the second path_extend (ref_path_bounce), pt and ptdl bookkeeping
 N_BOUNCE = 4000
-EMISSION_CASES = ["c10", "glass_metal", "motion", "sphere_light"]   # what the samplers splat for emission found by extension (ref_path_emission)
+EMISSION_CASES = ["c10", "glass_metal", "motion", "sphere_light", "sky_light", "envmap", "sky_const"]   # what the samplers splat for emission found by extension (ref_path_emission)
 N_EMISSION = 20000
 SCRAMBLING = 0.5
 N_LOW = 6000

@@ -206,7 +206,7 @@ def test_second_path_extend_matches_the_reference(gpu, case, mode):
     assert abs((rel*val).sum())/val.sum() < 1e-4
 
 
-@pytest.mark.parametrize("case", ["c10", "glass_metal", "motion", "sphere_light"])
+@pytest.mark.parametrize("case", ["c10", "glass_metal", "motion", "sphere_light", "sky_light", "envmap", "sky_const"])
 @pytest.mark.parametrize("mode", ["pt", "ptdl"])
 def test_emission_found_by_extension_matches_the_reference(gpu, case, mode):
     """Rows a20 / a21 / a23 at vertex level: what the reference's own sampler loop would splat for emitters a path reaches by
