@@ -100,8 +100,11 @@ int      cb200_accel_traversal(const cb200_accel_t *a);
  *      *_n take HOST pointers and include the copies; *_dev take DEVICE pointers and only
  *      enqueue on `stream` (a cudaStream_t, NULL = default stream).
  *      intersect_n / visible_n stage through persistent device buffers in 512 Ki-ray chunks on four streams (upload,
- *      traversal and download of consecutive chunks overlap when the host buffers are pinned); calls from several host
- *      threads are serialised.                                                                  */
+ *      traversal and download of consecutive chunks overlap when the host buffers are pinned); such calls from several host
+ *      threads are serialised.  Batches of up to 128 rays -- the batch of one behind accel_intersect / accel_visible of every
+ *      pinned worker thread -- take another route: the calling thread's own stream and block of mapped pinned memory (made at its
+ *      first call, kept for the life of the thread), one launch + one stream synchronisation, no lock, concurrent across
+ *      threads; the calling thread's current device is set to the accel's and left there.                               */
 int cb200_accel_intersect_n(const cb200_accel_t *a, const cb_ray_t *rays, const float *max_dist,
                             cb_hitrec_t *out, uint64_t n);
 int cb200_accel_visible_n(const cb200_accel_t *a, const cb_ray_t *rays, const float *max_dist,
