@@ -74,6 +74,27 @@ def test_camera_sample_and_first_hit_match_the_reference(gpu, case):
     acc.close()
 
 
+def test_ptnee_next_event_values_are_the_unweighted_throughput(gpu):
+    """src/sampler.d/ptnee.c:60-66: the same next-event samples, splatted without a competing technique -- the reference's
+    path_throughput after nee_sample (column 6 of the golden rows) is the value, the mis weight (column 9) is not applied"""
+    z = np.load(os.path.join(GOLDEN, "paths.npz"))
+    for case in ("c10", "sphere_light"):
+        want = z[f"{case}_nee"]
+        g = GoldenImage(case)
+        acc = gpu.Accel(g.scene).build()
+        r = gpu.Render(acc, g.camera, g.materials, g.w, g.h, frame=1, **g.sky_args, **GoldenImage.variant_args("ptnee_halton"))
+        got = r.nee_records(0, len(want))
+        r.close()
+        acc.close()
+        key = lambda a: [tuple(x) for x in np.ascontiguousarray(a[:, :3]).view("u4")]
+        rec = {k: row for k, row in zip(key(got), got)}
+        lit = want[want[:, 9] > 0]
+        rel = np.array([rec[k][3]/w[6] - 1.0 for k, w in zip(key(lit), lit) if k in rec and rec[k][14] == 1.0], np.float64)
+        assert len(rel) >= 0.99*len(lit), (len(rel), len(lit))
+        assert np.median(np.abs(rel)) < 1e-4 and (np.abs(rel) > 1e-3).mean() < 0.08, (np.median(np.abs(rel)), (np.abs(rel) > 1e-3).mean())
+        print(f"{case}: ptnee, {len(rel)} next events, value = throughput without weight: median rel. difference {np.median(np.abs(rel)):.1e}")
+
+
 @pytest.mark.parametrize("case", ["c10", "motion", "glass_metal", "sphere_light", "sky_light", "envmap", "fog", "subsurf", "skin"])
 def test_next_event_samples_match_the_reference(gpu, case):
     """Row a21: for 6000 path indices the reference's own nee_sample at the first hit vertex (oracle/ref_path.c: ref_path_nee --
