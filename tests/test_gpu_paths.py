@@ -273,3 +273,25 @@ def test_emission_found_by_extension_matches_the_reference(gpu, case, mode):
             assert np.median(rel) < 2e-4 and np.quantile(rel, 0.95) < 2e-3, (np.median(rel), np.quantile(rel, 0.95))
         total += len(rel)
     assert total > 150
+
+
+def test_record_entries_refuse_a_pool_with_paths_in_flight(gpu):
+    """the known-answer entries run one wave on an EMPTY pool; with stragglers of a streamed pass in it they must say so instead of
+    overwriting them, and work again after the flush; bad sizes are argument errors"""
+    g = GoldenImage("c10")
+    acc = gpu.Accel(g.scene).build()
+    r = gpu.Render(acc, g.camera, g.materials, g.w, g.h, frame=1, **g.sky_args, **GoldenImage.variant_args("ptdl_halton"))
+    r.render_pass(streaming=True)
+    for call in (lambda: r.nee_records(0, 1000), lambda: r.bounce_records(0, 1000), lambda: r.emission_records(0, 1000, 1)):
+        with pytest.raises(Exception, match="in flight"):
+            call()
+    r.flush()
+    before = r.image().copy()
+    assert len(r.nee_records(0, 1000)) > 0 and len(r.bounce_records(0, 1000)) > 0
+    assert np.array_equal(before, r.image()), "the record entries must leave the framebuffer alone"
+    with pytest.raises(Exception, match="bad arguments"):
+        r.emission_records(0, 1000, 3)
+    with pytest.raises(Exception, match="bad arguments"):
+        r.nee_records(0, 0)
+    r.close()
+    acc.close()
